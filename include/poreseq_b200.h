@@ -1,0 +1,134 @@
+/* poreseq_b200.h -- C-ABI of the B200-native PoreSeq scoring path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  Each entry point
+ * replaces one native function the reference's Cython module binds through `cdef extern`
+ * (poreseq/_poreseqcpp.pyx:63-83); the citation beside each declaration is the reference
+ * interface it stands in for.  INTEGRATION.md shows the Cython stub a PoreSeq maintainer would
+ * add to call these instead of cpp/*.cpp.
+ *
+ * Model: a `ps_ctx` owns one CUDA device/stream and its scratch memory; a `ps_region` is the
+ * native twin of the reference's `AlignData` (cpp/AlignData.h:24-34): one sequence, its events
+ * (per-read level arrays + pore model + transition probabilities) and the alignment parameters.
+ * Inputs are caller-owned and copied on entry (the reference copies too, cpp/EventData.h:208-215);
+ * outputs are written into caller-allocated arrays or fetched with the getters.
+ *
+ * Error convention: every int-returning function returns 0 on success and a negative PS_E_* code
+ * on failure; ps_last_error() gives the message.  There is NO CPU fallback: without a usable
+ * sm_100 device every compute entry point fails with PS_E_CUDA.  (The reference itself never
+ * reports errors from C++; degenerate inputs follow its silent conventions -- e.g. a mutation with
+ * start > len(sequence) keeps the score -1e-6, cpp/MakeMutations.cpp:46.)
+ *
+ * Threading: a ctx and its regions must be used from one thread at a time (the reference holds
+ * the GIL for the whole call).  CUDA is initialised lazily on the first compute call, so a
+ * process may fork before that (poreseq train forks workers, poreseq/cmdline.py:258).
+ */
+#ifndef PORESEQ_B200_H_
+#define PORESEQ_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PS_OK            0
+#define PS_E_ARG        -1   /* bad argument / unsupported parameter value                      */
+#define PS_E_CUDA       -2   /* CUDA runtime failure or no device                               */
+#define PS_E_CAPACITY   -3   /* caller-supplied output buffer too small                         */
+#define PS_E_INTERNAL   -4
+
+#define PS_N_STATES   1024   /* cpp/AlignUtil.h:19                                              */
+
+typedef struct ps_ctx ps_ctx;
+typedef struct ps_region ps_region;
+
+/* cpp/AlignUtil.h:57-66 AlignParams (defaults lik_offset 4.5, scoring_width 150,
+ * realign_width 300, verbose 0). */
+typedef struct ps_params
+{
+    double lik_offset;
+    int    scoring_width;
+    int    realign_width;
+    int    verbose;
+} ps_params;
+
+/* One timing record per phase of the last compute call, CUDA-event milliseconds on the ctx
+ * stream (bench.py reads these for the roofline; see ps_last_timing). */
+#define PS_T_H2D        0
+#define PS_T_CENTRES    1
+#define PS_T_FORWARD    2
+#define PS_T_BACKWARD   3
+#define PS_T_BACKTRACE  4
+#define PS_T_JOIN       5
+#define PS_T_MUTSCORE   6
+#define PS_T_REDUCE     7
+#define PS_T_D2H        8
+#define PS_T_TOTAL      9
+#define PS_T_COUNT     10
+
+/* ---- context ---------------------------------------------------------------------------- */
+ps_ctx*     ps_create(int device);             /* no reference analogue (the reference is CPU-only) */
+void        ps_destroy(ps_ctx* ctx);
+const char* ps_last_error(ps_ctx* ctx);        /* ctx may be NULL: last error of a failed ps_create */
+const char* ps_version(void);
+/* Number of kernels this library launched on ctx since creation / algorithmic DP cells of the
+ * last compute call (wide fill cells, narrow mutation cells), for bench.py. */
+long long   ps_launch_count(ps_ctx* ctx);
+int         ps_last_timing(ps_ctx* ctx, double* ms /*PS_T_COUNT*/);
+int         ps_last_cells(ps_ctx* ctx, double* wide_cells, double* narrow_cells);
+
+/* ---- region = AlignData (cpp/AlignData.h:24-34) ------------------------------------------ */
+ps_region*  ps_region_create(ps_ctx* ctx, const char* bases, int len, const ps_params* params);
+void        ps_region_destroy(ps_region* r);
+/* EventData::setData + ModelData::setData/setParams (cpp/EventData.h:48-73,208-224), as
+ * marshalled by PythonToEvents (poreseq/_poreseqcpp.pyx:99-129).  The four level arrays have n0
+ * entries, the four model arrays PS_N_STATES.  seq2d may be NULL. */
+int         ps_region_add_event(ps_region* r, int n0,
+                                const double* mean, const double* stdv,
+                                const double* ref_align, const double* ref_like,
+                                const double* level_mean, const double* level_stdv,
+                                const double* sd_mean, const double* sd_stdv,
+                                int complement, double prob_skip, double prob_stay,
+                                double prob_extend, double prob_insert, const char* seq2d);
+int         ps_region_set_params(ps_region* r, const ps_params* params);
+int         ps_region_num_events(ps_region* r);
+int         ps_region_sequence_length(ps_region* r);
+/* data.sequence.bases / data.events[e].ref_align, ref_like as read back by the boundary
+ * (poreseq/_poreseqcpp.pyx:131-137, 374, 433, 470). */
+int         ps_region_get_sequence(ps_region* r, char* out, int cap);
+int         ps_region_get_event_align(ps_region* r, int e, double* ref_align, double* ref_like);
+
+/* ---- scoring ------------------------------------------------------------------------------ */
+/* vector<double> ScoreAlignments(AlignData&, double* likes)   cpp/Mutations.h:24,
+ * cpp/MakeMutations.cpp:148-195.  scores[n_events]; likes[len(sequence)] is accumulated into
+ * when non-NULL.  Realigns every event in place. */
+int         ps_score_alignments(ps_region* r, double* scores, double* likes);
+/* vector<MutScore> ScoreMutations(AlignData&, const vector<MutInfo>&)   cpp/Mutations.h:23,
+ * cpp/MakeMutations.cpp:23-69.  orig[i]/mut[i] are NUL-terminated. */
+int         ps_score_mutations(ps_region* r, int n, const int* start, const char* const* orig,
+                               const char* const* mut, double* scores);
+/* vector<MutInfo> FindPointMutations(AlignData&)   cpp/Mutations.h:19, cpp/FindMutations.cpp:191-234.
+ * Writes up to cap single-base edits (orig/mut as one char, 0 = empty); *n = 8 per state. */
+int         ps_find_point_mutations(ps_region* r, int cap, int* n, int* start, char* orig, char* mut);
+/* FindPointMutations + ScoreMutations in one call (PSAlign.ScorePoints, _poreseqcpp.pyx:278-308). */
+int         ps_score_points(ps_region* r, int cap, int* n, int* start, char* orig, char* mut, double* scores);
+/* int MakeMutations(AlignData&, vector<MutScore>)   cpp/Mutations.h:22, cpp/MakeMutations.cpp:74-146. */
+int         ps_make_mutations(ps_region* r, int n, const int* start, const char* const* orig,
+                              const char* const* mut, const double* scores, int* nbases);
+/* PSAlign.Refine body (_poreseqcpp.pyx:463-469): FindPointMutations, ScoreMutations, MakeMutations. */
+int         ps_refine(ps_region* r, int* nbases);
+
+/* Batched form of ps_score_points over independent regions (same ctx): one launch sequence for
+ * all of them.  n_out[k] edits are written for region k at offset off_out[k] of the flat output
+ * arrays (cap entries in total).  No reference analogue: the reference scales by running one
+ * process per region (README.md:48-54). */
+int         ps_score_points_batch(ps_region* const* regions, int n_regions, int cap,
+                                  int* n_out, long long* off_out,
+                                  int* start, char* orig, char* mut, double* scores);
+
+/* ---- helpers that stay on the host ---------------------------------------------------------- */
+/* Sequence::populateStates (cpp/Sequence.h:69-100); returns the number of states written. */
+int         ps_seq_to_states(const char* seq, int len, int* states);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

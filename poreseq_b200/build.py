@@ -1,0 +1,48 @@
+"""Builds libporeseq_b200.so in-tree with nvcc for sm_100a (no torch, no JIT cache).
+
+    python -m poreseq_b200.build [--force]
+
+-fmad=false keeps the FP64 recurrence bit-identical to the reference's x86-64 build (which emits no
+FMA); FP32 kernels that want FMA ask for it explicitly with intrinsics.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libporeseq_b200.so")
+SOURCES = ["ps_host.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-fmad=false", "--shared", "-Xcompiler", "-fPIC,-ffp-contract=off,-O3",
+              "-Xptxas", "-v"]
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "poreseq_b200.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    log = proc.stdout + proc.stderr
+    with open(os.path.join(HERE, "build.log"), "w") as f:
+        f.write(" ".join(cmd) + "\n" + log)
+    if proc.returncode != 0:
+        sys.stderr.write(log)
+        raise RuntimeError("nvcc failed building %s" % LIB)
+    if verbose:
+        sys.stderr.write(log)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True)
+    print(LIB)

@@ -1,0 +1,801 @@
+// ps_device.cuh -- device-side data layout and the exact (FP64) kernels of the PoreSeq scoring
+// path, written for sm_100a.  Compiled with -fmad=false: the recurrence has no transcendentals
+// (every log() is hoisted to the host, cpp/EventData.h:57-62,220), so IEEE double add/mul/div
+// evaluated in the reference's order reproduces the reference's x86-64 results bit for bit.
+//
+// Kernels (SURVEY.md 2.1 numbering):
+//   k_centres      band-centre table  imid[e][c] = lower_bound(ref_index, c)   (cpp/EventData.h:172-183)
+//   k_fill         K1/K2  wide-band forward + reverse fill, anti-diagonal wavefront,
+//                  one CTA per (event, direction), one thread per column   (cpp/Alignment.cpp:111-444)
+//   k_backtrace    K3     best-path pointer chase + updaterefs               (cpp/Alignment.cpp:516-624,
+//                                                                             cpp/EventData.h:110-169)
+//   k_join         K4a    old[e][c] = columnMax(c)                           (cpp/Alignment.h:169-214)
+//   k_mutscore     K4     one thread per (mutation, event): narrow re-fill + join (cpp/Alignment.cpp:447-512)
+//   k_reduce       K5     score[m] = -1e-6 + sum over events in event order  (cpp/MakeMutations.cpp:38-52)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace psdev {
+
+constexpr int    N_STATES = 1024;
+constexpr double NEG      = -1e300;       // cpp/AlignUtil.h:20 ("inf" is 1e300)
+
+// packed step byte written by the forward fill: low 3 bits main-matrix move, bits 3-4 stay-matrix move
+// main : 0 skip, 1 match, 2 insert, 3 ignore, 4 stay, 6 implicit (cpp/Alignment.cpp:19-28), 7 = score <= 0
+// stay : 0 = score <= 0, 1 = stay, 2 = extend
+constexpr int ST_SKIP = 0, ST_MATCH = 1, ST_INSERT = 2, ST_IGNORE = 3, ST_STAY = 4, ST_IMPLICIT = 6, ST_STOP = 7;
+
+struct StateParams            // one 64-byte record per 5-mer state (cpp/EventData.h:21-45)
+{
+    double lev_mean, lev_stdv, log_lev, sd_mean, sd_lambda, log_lambda, pad0, pad1;
+};
+
+struct ModelDev               // cpp/EventData.h:21-74
+{
+    StateParams st[N_STATES];
+    double lskip, lstay, lext, lins;
+};
+
+struct EvDesc                 // one event of one region in the batch
+{
+    int       region;
+    int       n0;             // levels
+    int       N;              // states of the region sequence
+    int       L;              // bases of the region sequence
+    int       usable;         // cpp/Alignment.cpp:51-59 (ref_index non-empty at call start)
+    int       model;          // index into the model table
+    int       n_muts;         // mutations of this event's region
+    int       pad;
+    long long lev_off;        // into the per-level arrays
+    long long col_off;        // band column g = col_off + c,  c = 1..N
+    long long state_off;      // into states[]
+    long long base_off;       // into bases[]
+    long long cen_off;        // into centre tables: index cen_off + c, c = 0..N+cen_pad
+    long long mut_off;        // first mutation of the region in the mutation arrays
+    long long task_off;       // first (event, mutation) task of this event; delta[task_off + m]
+};
+
+struct MutDev
+{
+    int start, n_orig, n_mut, str_off;   // str_off: offset of the mut string in the char pool
+};
+
+struct Batch                  // everything the kernels need, passed by value
+{
+    const EvDesc*     ev;
+    int               n_events;
+    const ModelDev*   models;
+    const int*        states;
+    const char*       bases;
+    // per level
+    const double*     mean;
+    const double*     stdv;
+    const double*     log_stdv;
+    double*           ref_align;
+    double*           ref_like;
+    double*           ref_index;
+    int*              bt_src;        // scratch for the backtrace gather
+    // per event
+    int*              ri_empty;      // ref_index empty after the last updaterefs
+    int*              refstart;
+    int*              refend;
+    int*              mono;          // band centres nondecreasing (wavefront schedule is valid)
+    // centre tables (forward lower_bound index, 0..n0), old = before backtrace, new = after
+    int*              cen_old;
+    int*              cen_new;
+    int               cen_pad;
+    // band storage, RS doubles per column
+    int               RS;
+    double*           Fm; double* Fs; double* Bm; double* Bs;
+    uint8_t*          Fstep;
+    int*              Fi0; int* Flen; int* Bi0; int* Blen;
+    double*           Fcb; int* Fcbi;          // per-column best (score, row) before the running max
+    double*           Bcb; int* Bcbi;
+    double*           Fbest; int* Fbi; int* Fbj; // running best up to and including the column
+    double*           Bbest;
+    double*           old;                      // columnMax(c) per band column
+    // mutations
+    const MutDev*     muts;
+    const char*       mut_str;
+    double*           delta;                    // per task
+    double*           scores;                   // per mutation
+    long long         n_tasks;
+    // narrow-fill scratch
+    double*           scratch;
+    long long         scratch_slots;
+    // parameters
+    double            lik_offset;
+    double            log2pi;
+    int               realign_width;
+    int               scoring_width;
+};
+
+// ------------------------------------------------------------------------------------------
+// emission: lognormpdf + logigpdf + lik_offset   (cpp/AlignUtil.h:34-53, cpp/Alignment.cpp:169-173)
+// x = level mean, y = level stdv, lsd = log(stdv) of the level the reference indexes (quirk A.3-1)
+__device__ __forceinline__ double emission(double x, double y, double lsd, const StateParams& p,
+                                           double log2pi, double offset)
+{
+    double d = (x - p.lev_mean) / p.lev_stdv;
+    double l = -0.5 * (d * d + log2pi) - p.log_lev;
+    double g = (y - p.sd_mean) / p.sd_mean;
+    l += 0.5 * (p.log_lambda - 3 * lsd - log2pi - g * g * p.sd_lambda / y);
+    l += offset;
+    return l;
+}
+
+struct Trans { double lskip, lstay, lext, lins; };
+
+// One cell of the coupled (main C, stay S) recurrence, cpp/Alignment.cpp:194-271 (forward) and
+// :370-441 (reverse).  eM = emission added on the diagonal move (forward: this cell's; reverse:
+// the source cell's, 0 when implicit), eU = emission added on stay/extend.
+__device__ __forceinline__ void dp_cell(bool first_row, bool skip_ok, bool diag_ok, double Pi, double Pi1,
+                                        double eM, double eU, double upC, double upS, const Trans& t,
+                                        double& C, double& S, int& step)
+{
+    double skip = skip_ok ? Pi + t.lskip : t.lskip;
+    double match = diag_ok ? Pi1 + eM : eM;
+    double ignore = diag_ok ? Pi1 + t.lins : 0.0;
+    double stay = NEG, ext = NEG, ins = 0.0;
+    if (!first_row)
+    {
+        stay = upC + eU + t.lstay;
+        ins = upC + t.lins;
+        ext = upS + eU + t.lext;
+    }
+    double s = first_row ? NEG : 0.0;
+    int ss = 0;
+    if (stay > s) { s = stay; ss = 1; }
+    if (ext > s) { s = ext; ss = 2; }
+    double c = 0.0;
+    int sc = ST_STOP;
+    if (skip > c) { c = skip; sc = skip_ok ? ST_SKIP : ST_IMPLICIT; }
+    if (match > c) { c = match; sc = diag_ok ? ST_MATCH : ST_IMPLICIT; }
+    if (ins > c) { c = ins; sc = ST_INSERT; }
+    if (ignore > c) { c = ignore; sc = ST_IGNORE; }
+    if (s > c) { c = s; sc = ST_STAY; }
+    C = c; S = s; step = sc | (ss << 3);
+}
+
+// std::lower_bound over ref_index restated as libstdc++'s halving search (cpp/EventData.h:172-183)
+__device__ __forceinline__ int lower_bound_index(const double* a, int n, double v)
+{
+    int first = 0, len = n;
+    while (len > 0)
+    {
+        int half = len >> 1;
+        if (a[first + half] < v) { first += half + 1; len -= half + 1; }
+        else len = half;
+    }
+    return first;
+}
+
+__device__ __forceinline__ void band_of(int mid, int n0, int w, int& i0, int& i1)
+{
+    if (mid < 1) mid = 1;
+    if (mid > n0) mid = n0;
+    i0 = max(1, mid - w);
+    i1 = min(n0, mid + w);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_centres: cen[cen_off + c] = lower_bound(ref_index, c) for c = 0..N+pad (1 when ref_index is
+// empty, cpp/Alignment.cpp:129-132); optionally flags non-monotone centres per event.
+__global__ void k_centres(Batch b, int* cen, int check_mono)
+{
+    const EvDesc ev = b.ev[blockIdx.y];
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    int cmax = ev.N + b.cen_pad;
+    if (c > cmax) return;
+    int v = 1;
+    if (!b.ri_empty[blockIdx.y])
+    {
+        const double* ri = b.ref_index + ev.lev_off;
+        v = lower_bound_index(ri, ev.n0, (double)c);
+        if (check_mono && c >= 1)
+        {
+            int u = lower_bound_index(ri, ev.n0, (double)(c - 1));
+            if (u > v) b.mono[blockIdx.y] = 0;
+        }
+    }
+    cen[ev.cen_off + c] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_fill: wide-band fill of one (event, direction) per CTA.
+//
+// Wavefront: the cell (column k, row i) -- k counts columns in processing order, so k = c forward
+// and k = N-c+1 in reverse -- is computed at step d = k + i.  Its three inputs (k-1,i), (k-1,i-1),
+// (k,i-1) were produced at steps d-1, d-2, d-1.  Thread t owns columns k = t+1, t+1+T, ...; the
+// vertical dependency stays in registers, the two horizontal ones come from the left neighbour
+// through a 3-deep shared-memory ring indexed by step.  With nondecreasing band centres and
+// T >= 2*realign_width+1 a thread never has two live columns (host/k_centres check `mono`);
+// otherwise thread 0 runs the same cells serially.
+struct ColSetup
+{
+    int k;            // processing-order column (1..N), INT_MAX/2 when past the end
+    int s;            // 5-mer state or -1
+    int i0, i1;       // band rows
+    int p0, p1;       // previous column's band rows
+    long long g;      // storage column
+    StateParams p;
+};
+
+__device__ __forceinline__ void fill_setup(const Batch& b, const EvDesc& ev, bool rev, int k, ColSetup& cs)
+{
+    if (k > ev.N) { cs.k = 1 << 29; cs.i0 = 1; cs.i1 = 0; cs.s = -1; return; }
+    cs.k = k;
+    int c = rev ? ev.N - k + 1 : k;
+    int n0 = ev.n0, w = b.realign_width;
+    int cen = b.cen_old[ev.cen_off + c];
+    band_of(rev ? n0 - cen + 1 : cen, n0, w, cs.i0, cs.i1);
+    if (k == 1) { cs.p0 = 0; cs.p1 = n0; }
+    else
+    {
+        int cp = rev ? c + 1 : c - 1;
+        int cenp = b.cen_old[ev.cen_off + cp];
+        band_of(rev ? n0 - cenp + 1 : cenp, n0, w, cs.p0, cs.p1);
+    }
+    cs.s = b.states[ev.state_off + c - 1];
+    cs.g = ev.col_off + k;
+    if (cs.s >= 0) cs.p = b.models[ev.model].st[cs.s];
+}
+
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT) k_fill(Batch b, int dir_base)
+{
+    extern __shared__ double smem[];
+    const int T = blockDim.x, tid = threadIdx.x;
+    const EvDesc ev = b.ev[blockIdx.x];
+    const bool rev = (dir_base + blockIdx.y) != 0;
+    if (!ev.usable || ev.N <= 0) return;
+    const int n0 = ev.n0, N = ev.N, RS = b.RS;
+    double* Cb = smem;               // [3][T]
+    double* Eb = smem + 3 * T;       // [3][T] emissions (reverse needs the neighbour's)
+    double* Mm = rev ? b.Bm : b.Fm;
+    double* Ms = rev ? b.Bs : b.Fs;
+    int* Mi0 = rev ? b.Bi0 : b.Fi0;
+    int* Mlen = rev ? b.Blen : b.Flen;
+    double* Mcb = rev ? b.Bcb : b.Fcb;
+    int* Mcbi = rev ? b.Bcbi : b.Fcbi;
+    const double* mean = b.mean + ev.lev_off;
+    const double* stdv = b.stdv + ev.lev_off;
+    const double* lsdv = b.log_stdv + ev.lev_off;
+    const ModelDev& md = b.models[ev.model];
+    const Trans tr = {md.lskip, md.lstay, md.lext, md.lins};
+    const double off = b.lik_offset, l2p = b.log2pi;
+    const bool wave = b.mono[blockIdx.x] && T >= 2 * b.realign_width + 1;
+
+    if (wave)
+    {
+        ColSetup cur, nxt;
+        fill_setup(b, ev, rev, tid + 1, cur);
+        fill_setup(b, ev, rev, tid + 1 + T, nxt);
+        ColSetup first, last;
+        fill_setup(b, ev, rev, 1, first);
+        fill_setup(b, ev, rev, N, last);
+        const int dstart = 1 + first.i0, dend = N + last.i1;
+        double upC = 0, upS = 0, upE = 0, best = NEG;
+        int besti = 0;
+        const int left = (tid + T - 1) % T;
+        for (int d = dstart; d <= dend; d++)
+        {
+            if (d > cur.k + cur.i1)
+            {
+                // column finished: publish its shape and best cell, move on
+                if (cur.k <= N)
+                {
+                    Mi0[cur.g] = cur.i0; Mlen[cur.g] = cur.i1 - cur.i0 + 1;
+                    Mcb[cur.g] = best; Mcbi[cur.g] = besti;
+                }
+                cur = nxt;
+                fill_setup(b, ev, rev, cur.k + T, nxt);
+                best = NEG; besti = 0;
+            }
+            const int i = d - cur.k;
+            const int w0 = d % 3, w1 = (d + 2) % 3, w2 = (d + 1) % 3;   // this step, d-1, d-2
+            if (i >= cur.i0 && i <= cur.i1)
+            {
+                double C = 0, S = 0, e = 0;
+                int step = ST_STOP;
+                if (cur.s >= 0)
+                {
+                    const int lv = rev ? n0 - i : i - 1;
+                    e = emission(mean[lv], stdv[lv], lsdv[n0 - i], cur.p, l2p, off);
+                    const bool skip_ok = i >= cur.p0 && i <= cur.p1;
+                    const bool diag_ok = i > cur.p0 && i <= cur.p1;
+                    double Pi = 0, Pi1 = 0, PE = 0;
+                    if (cur.k > 1)
+                    {
+                        Pi = Cb[w1 * T + left];
+                        Pi1 = Cb[w2 * T + left];
+                        PE = Eb[w2 * T + left];
+                    }
+                    const double eM = rev ? (diag_ok ? PE : 0.0) : e;
+                    const double eU = rev ? upE : e;
+                    dp_cell(i == cur.i0, skip_ok, diag_ok, Pi, Pi1, eM, eU, upC, upS, tr, C, S, step);
+                    if (C > best) { best = C; besti = i; }
+                }
+                Cb[w0 * T + tid] = C;
+                Eb[w0 * T + tid] = e;
+                const long long a = cur.g * RS + (i - cur.i0);
+                Mm[a] = C; Ms[a] = S;
+                if (!rev) b.Fstep[a] = (uint8_t)step;
+                upC = C; upS = S; upE = e;
+            }
+            __syncthreads();
+        }
+        if (cur.k <= N)
+        {
+            Mi0[cur.g] = cur.i0; Mlen[cur.g] = cur.i1 - cur.i0 + 1;
+            Mcb[cur.g] = best; Mcbi[cur.g] = besti;
+        }
+    }
+    else if (tid == 0)
+    {
+        // serial schedule (arbitrary band layout): same cells, column by column; the previous
+        // column's emissions (reverse pass only) alternate between two RS-long strips of smem
+        ColSetup cs;
+        for (int k = 1; k <= N; k++)
+        {
+            fill_setup(b, ev, rev, k, cs);
+            double upC = 0, upS = 0, upE = 0, best = NEG;
+            int besti = 0;
+            const long long gp = cs.g - 1;
+            double* Ecur = smem + (k & 1) * RS;
+            const double* Eprev = smem + ((k - 1) & 1) * RS;
+            for (int i = cs.i0; i <= cs.i1; i++)
+            {
+                double C = 0, S = 0, e = 0;
+                int step = ST_STOP;
+                if (cs.s >= 0)
+                {
+                    const int lv = rev ? n0 - i : i - 1;
+                    e = emission(mean[lv], stdv[lv], lsdv[n0 - i], cs.p, l2p, off);
+                    const bool skip_ok = i >= cs.p0 && i <= cs.p1;
+                    const bool diag_ok = i > cs.p0 && i <= cs.p1;
+                    double Pi = 0, Pi1 = 0, PE = 0;
+                    if (k > 1)
+                    {
+                        if (skip_ok) Pi = Mm[gp * RS + (i - cs.p0)];
+                        if (diag_ok) { Pi1 = Mm[gp * RS + (i - 1 - cs.p0)]; PE = Eprev[i - 1 - cs.p0]; }
+                    }
+                    const double eM = rev ? (diag_ok ? PE : 0.0) : e;
+                    const double eU = rev ? upE : e;
+                    dp_cell(i == cs.i0, skip_ok, diag_ok, Pi, Pi1, eM, eU, upC, upS, tr, C, S, step);
+                    if (C > best) { best = C; besti = i; }
+                }
+                const long long a = cs.g * RS + (i - cs.i0);
+                Mm[a] = C; Ms[a] = S;
+                if (!rev) b.Fstep[a] = (uint8_t)step;
+                Ecur[i - cs.i0] = e;
+                upC = C; upS = S; upE = e;
+            }
+            Mi0[cs.g] = cs.i0; Mlen[cs.g] = cs.i1 - cs.i0 + 1;
+            Mcb[cs.g] = best; Mcbi[cs.g] = besti;
+        }
+    }
+    __syncthreads();
+
+    // running best over columns: first maximum in (column, row) order wins (cpp/Alignment.cpp:31-36,
+    // :158, :270).  Columns whose best is not > the carried one leave it untouched.
+    double* Mbest = rev ? b.Bbest : b.Fbest;
+    __shared__ double sh_s[32];
+    __shared__ int sh_i[32], sh_j[32];
+    __shared__ double car_s;
+    __shared__ int car_i, car_j;
+    if (tid == 0) { car_s = 0.0; car_i = 0; car_j = 0; }
+    __syncthreads();
+    const int lane = tid & 31, wid = tid >> 5, nw = (T + 31) >> 5;
+    for (int base = 0; base < N; base += T)
+    {
+        int k = base + tid + 1;
+        double s = NEG; int bi = 0, bj = 0;
+        if (k <= N) { s = Mcb[ev.col_off + k]; bi = Mcbi[ev.col_off + k]; bj = rev ? N - k + 1 : k; }
+        // inclusive scan, earlier element wins ties
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            double s2 = __shfl_up_sync(0xffffffffu, s, o);
+            int i2 = __shfl_up_sync(0xffffffffu, bi, o), j2 = __shfl_up_sync(0xffffffffu, bj, o);
+            if (lane >= o && !(s > s2)) { s = s2; bi = i2; bj = j2; }
+        }
+        if (lane == 31) { sh_s[wid] = s; sh_i[wid] = bi; sh_j[wid] = bj; }
+        __syncthreads();
+        if (wid == 0)
+        {
+            double ws = lane < nw ? sh_s[lane] : NEG;
+            int wi = lane < nw ? sh_i[lane] : 0, wj = lane < nw ? sh_j[lane] : 0;
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                double s2 = __shfl_up_sync(0xffffffffu, ws, o);
+                int i2 = __shfl_up_sync(0xffffffffu, wi, o), j2 = __shfl_up_sync(0xffffffffu, wj, o);
+                if (lane >= o && !(ws > s2)) { ws = s2; wi = i2; wj = j2; }
+            }
+            if (lane < nw) { sh_s[lane] = ws; sh_i[lane] = wi; sh_j[lane] = wj; }
+        }
+        __syncthreads();
+        if (wid > 0 && !(s > sh_s[wid - 1])) { s = sh_s[wid - 1]; bi = sh_i[wid - 1]; bj = sh_j[wid - 1]; }
+        if (!(s > car_s)) { s = car_s; bi = car_i; bj = car_j; }
+        if (k <= N)
+        {
+            Mbest[ev.col_off + k] = s;
+            if (!rev) { b.Fbi[ev.col_off + k] = bi; b.Fbj[ev.col_off + k] = bj; }
+        }
+        __syncthreads();
+        if (tid == T - 1) { car_s = s; car_i = bi; car_j = bj; }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// updaterefs (cpp/EventData.h:110-169), sequential restatement used by k_backtrace's thread 0.
+__device__ void dev_updaterefs(const double* ra, double* ri, int n0, int& empty, int& refstart, int& refend)
+{
+    int a = 0, z = n0 - 1;
+    while (a < n0 && !(ra[a] > 0)) a++;
+    while (z >= 0 && !(ra[z] > 0)) z--;
+    if (a == n0 || z < 0) { empty = 1; refstart = -1; refend = -1; return; }
+    empty = 0;
+    refstart = (int)ra[a];
+    refend = (int)ra[z];
+    double slope = (ra[z] - ra[a]) / (double)(z - a);
+    double icpt = ra[a] - slope * a;
+    int last = -1;
+    for (int i = 0; i < n0; i++)
+    {
+        double v = ra[i];
+        if (i < a || i > z) ri[i] = slope * i + icpt;
+        else
+        {
+            ri[i] = v;
+            if (v > 0)
+            {
+                if (last > 0)
+                {
+                    double m = (v - ra[last]) / (i - last);
+                    for (int j = last + 1; j < i; j++) ri[j] = m * (j - last) + ra[last];
+                }
+                last = i;
+            }
+        }
+    }
+}
+
+// k_backtrace: one CTA per event.  Thread 0 follows the packed step bytes from the best cell
+// (cpp/Alignment.cpp:516-605); every visited level records its column and matrix, the CTA then
+// gathers ref_like in parallel and thread 0 rebuilds ref_index.
+__global__ void k_backtrace(Batch b)
+{
+    const EvDesc ev = b.ev[blockIdx.x];
+    if (!ev.usable) return;
+    const int n0 = ev.n0, N = ev.N, RS = b.RS, tid = threadIdx.x;
+    double* ra = b.ref_align + ev.lev_off;
+    double* rl = b.ref_like + ev.lev_off;
+    int* src = b.bt_src + ev.lev_off;
+    for (int i = tid; i < n0; i += blockDim.x) { ra[i] = 0.0; rl[i] = 0.0; src[i] = 0; }
+    __syncthreads();
+    if (tid == 0 && N > 0)
+    {
+        int i = b.Fbi[ev.col_off + N], j = b.Fbj[ev.col_off + N], arr = 0;
+        while (i > 0 && j > 0)
+        {
+            const long long g = ev.col_off + j;
+            const int st = b.Fstep[g * RS + (i - b.Fi0[g])];
+            const int mv = arr ? ((st >> 3) & 3) : (st & 7);
+            if (arr == 0)
+            {
+                if (mv == ST_STOP || mv == ST_IMPLICIT || mv == 5) break;
+                if (mv == ST_SKIP) { j--; }
+                else if (mv == ST_MATCH) { ra[i - 1] = (double)j; src[i - 1] = 2 * j; i--; j--; }
+                else if (mv == ST_IGNORE) { ra[i - 1] = -1.0; src[i - 1] = 2 * j; i--; j--; }
+                else if (mv == ST_INSERT) { ra[i - 1] = -1.0; src[i - 1] = 2 * j; i--; }
+                else /* ST_STAY: hop to the stay matrix, same cell */ arr = 1;
+            }
+            else
+            {
+                if (mv == 0) break;
+                ra[i - 1] = (double)j; src[i - 1] = 2 * j + 1;
+                i--;
+                if (mv == 1) arr = 0;          // stay: back to the main matrix one row up
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < n0; i += blockDim.x)
+    {
+        int s = src[i];
+        if (s)
+        {
+            const long long g = ev.col_off + (s >> 1);
+            const long long a = g * RS + (i + 1 - b.Fi0[g]);
+            rl[i] = (s & 1) ? b.Fs[a] : b.Fm[a];
+        }
+    }
+    __syncthreads();
+    if (tid == 0)
+    {
+        int empty, rs, re;
+        dev_updaterefs(ra, b.ref_index + ev.lev_off, n0, empty, rs, re);
+        b.ri_empty[blockIdx.x] = empty;
+        b.refstart[blockIdx.x] = rs;
+        b.refend[blockIdx.x] = re;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Join of a forward column with a reverse column (cpp/Alignment.h:178-214).  Every cell has
+// main >= stay and every column's running best >= each of its main cells, so rows present in only
+// one of the two bands can never beat the two running bests: the maximum over all rows reduces to
+// the rows present in BOTH bands plus the two running bests (and the floor 0).
+// This warp-cooperative form takes explicit band descriptions so it also serves the blank column.
+__device__ __forceinline__ double warp_join(const double* Fm, const double* Fs, int f0, int flen,
+                                            const double* Bm, const double* Bs, int b0, int blen,
+                                            int n0, int lane)
+{
+    // jf in [f0, f0+flen-1], jb = n0-jf+1 in [b0, b0+blen-1]
+    int lo = max(f0, n0 + 1 - (b0 + blen - 1)), hi = min(f0 + flen - 1, n0 + 1 - b0);
+    lo = max(lo, 1); hi = min(hi, n0);
+    double m = 0.0;
+    for (int jf = lo + lane; jf <= hi; jf += 32)
+    {
+        int jb = n0 - jf + 1;
+        double fm = Fm ? Fm[jf - f0] : 0.0, fs = Fs ? Fs[jf - f0] : 0.0;
+        double bm = Bm ? Bm[jb - b0] : 0.0, bs = Bs ? Bs[jb - b0] : 0.0;
+        m = fmax(m, fmax(fm + bm, fs + bs));
+    }
+    for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    return m;
+}
+
+// k_join: old[g] = columnMax(c) = join(F[c], B[N-c+1]) for every band column; one warp each.
+__global__ void k_join(Batch b)
+{
+    const EvDesc ev = b.ev[blockIdx.y];
+    if (!ev.usable) return;
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5) + 1;
+    if (c > ev.N) return;
+    const long long gf = ev.col_off + c, gb = ev.col_off + (ev.N - c + 1);
+    const int RS = b.RS;
+    double m = warp_join(b.Fm + gf * RS, b.Fs + gf * RS, b.Fi0[gf], b.Flen[gf],
+                         b.Bm + gb * RS, b.Bs + gb * RS, b.Bi0[gb], b.Blen[gb], ev.n0, lane);
+    m = fmax(m, fmax(b.Fbest[gf], b.Bbest[gb]));
+    if (lane == 0) b.old[gf] = m;
+}
+
+// ------------------------------------------------------------------------------------------
+// Mutated-sequence helpers (cpp/Sequence.h:38-100).
+struct MutView
+{
+    const char* bases; int L;        // region sequence
+    const char* mstr;                // mutation's replacement bases
+    int start, n_orig, n_mut;
+    bool applied;                    // start < L (cpp/Sequence.h:41)
+    int Lm;                          // mutated length
+};
+
+__device__ __forceinline__ int base_code(char ch)
+{
+    return ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : (int)ch;
+}
+
+__device__ __forceinline__ int mut_base(const MutView& v, int q)
+{
+    char ch;
+    if (!v.applied || q < v.start) ch = v.bases[q];
+    else if (q < v.start + v.n_mut) ch = v.mstr[q - v.start];
+    else ch = v.bases[q - v.n_mut + v.n_orig];
+    return base_code(ch);
+}
+
+// state of mutated position k (0-based): -1 iff the leftmost base of the window is not ACGT; bases
+// added before the most recent such reset are dropped (cpp/Sequence.h:79-98)
+__device__ __forceinline__ int mut_state(const MutView& v, int k)
+{
+    int b0 = mut_base(v, k);
+    if (b0 >= 4) return -1;                          // cpp/Sequence.h:87 tests `< 4` only
+    int from = k;                                   // first base index still contributing
+    for (int kk = k - 1; kk >= max(0, k - 4); kk--)
+    {
+        int bb = mut_base(v, kk);
+        if (bb >= 4) { from = max(from, kk + 5); break; }
+    }
+    int cur = 0;
+    for (int q = max(k, from); q <= k + 4; q++) cur += mut_base(v, q) << (2 * (k + 4 - q));
+    return cur & (N_STATES - 1);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_mutscore (generic form): one thread per (event, mutation) task, columns one after another,
+// the previous column's main-matrix values kept in a per-thread scratch strip (interleaved over
+// threads so accesses coalesce).  Handles any mutation length and every boundary case of
+// cpp/Alignment.cpp:447-512; the register-resident fast form for short edits lives in
+// ps_mutscore_fast.cuh.
+__device__ __forceinline__ bool task_decode(const Batch& b, long long t, int& e, int& m)
+{
+    // events are laid out with nondecreasing task_off; find the event owning task t
+    int lo = 0, hi = b.n_events - 1;
+    while (lo < hi)
+    {
+        int mid = (lo + hi + 1) >> 1;
+        if (b.ev[mid].task_off <= t) lo = mid; else hi = mid - 1;
+    }
+    e = lo;
+    m = (int)(t - b.ev[lo].task_off);
+    return m < b.ev[lo].n_muts;
+}
+
+// single-thread join used for the boundary cases (seed column joined directly, blank columns)
+__device__ double thread_join(const Batch& b, const EvDesc& ev, int raf, int rab)
+{
+    const int N = ev.N, n0 = ev.n0, RS = b.RS;
+    raf = min(max(raf, 0), N); rab = min(max(rab, 0), N);
+    const long long gf = ev.col_off + raf, gb = ev.col_off + rab;
+    int f0 = 0, flen = n0 + 1, b0 = 0, blen = n0 + 1;
+    double mf = 0.0, mb = 0.0;
+    if (raf > 0) { f0 = b.Fi0[gf]; flen = b.Flen[gf]; mf = b.Fbest[gf]; }
+    if (rab > 0) { b0 = b.Bi0[gb]; blen = b.Blen[gb]; mb = b.Bbest[gb]; }
+    int lo = max(max(f0, n0 + 1 - (b0 + blen - 1)), 1), hi = min(min(f0 + flen - 1, n0 + 1 - b0), n0);
+    double m = fmax(0.0, fmax(mf, mb));
+    for (int jf = lo; jf <= hi; jf++)
+    {
+        int jb = n0 - jf + 1;
+        double fm = raf > 0 ? b.Fm[gf * RS + jf - f0] : 0.0, fs = raf > 0 ? b.Fs[gf * RS + jf - f0] : 0.0;
+        double bm = rab > 0 ? b.Bm[gb * RS + jb - b0] : 0.0, bs = rab > 0 ? b.Bs[gb * RS + jb - b0] : 0.0;
+        m = fmax(m, fmax(fm + bm, fs + bs));
+    }
+    return m;
+}
+
+__global__ void __launch_bounds__(128) k_mutscore(Batch b)
+{
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int W = b.scoring_width, RS = b.RS;
+    const int strip = 2 * W + 1;
+    double* bufA = b.scratch + gtid;                       // element r at bufA[r * nthreads]
+    double* bufB = b.scratch + (long long)strip * nthreads + gtid;
+    for (long long t = gtid; t < b.n_tasks; t += nthreads)
+    {
+        int e, m;
+        if (!task_decode(b, t, e, m)) continue;
+        const EvDesc ev = b.ev[e];
+        const MutDev mu = b.muts[ev.mut_off + m];
+        double result = 0.0;
+        if (ev.usable && !((unsigned)mu.start > (unsigned)ev.L))        // cpp/MakeMutations.cpp:46
+        {
+            const int N = ev.N, n0 = ev.n0, L = ev.L;
+            MutView mv;
+            mv.bases = b.bases + ev.base_off; mv.L = L; mv.mstr = b.mut_str + mu.str_off;
+            mv.start = mu.start; mv.n_orig = mu.n_orig; mv.n_mut = mu.n_mut;
+            mv.applied = mu.start < L;
+            mv.Lm = mv.applied ? mu.start + mu.n_mut + max(0, L - mu.start - mu.n_orig) : L;
+            const int Nm = mv.Lm >= 5 ? mv.Lm - 4 : 0;
+            // old score: columnMax(max(start-3,1)) with the reference's clamps
+            const int raf = max(mu.start - 3, 1);
+            double old;
+            if (raf <= N) old = b.old[ev.col_off + raf];
+            else old = thread_join(b, ev, raf, N - raf + 1);
+            const int startind = max(mu.start - 4, 0);
+            int refind = mu.start + mu.n_mut + 1;
+            int last = min(min(refind, startind + mu.n_mut + 6), Nm);      // last column that gets filled
+            if (W == 0) last = startind;
+            double neu;
+            if (last <= startind)
+            {
+                // nothing appended: the seed column itself is joined (cpp/Alignment.cpp:483-499)
+                neu = thread_join(b, ev, startind, Nm - startind + 1);
+            }
+            else
+            {
+                const double* mean = b.mean + ev.lev_off;
+                const double* stdv = b.stdv + ev.lev_off;
+                const double* lsdv = b.log_stdv + ev.lev_off;
+                const ModelDev& md = b.models[ev.model];
+                const Trans tr = {md.lskip, md.lstay, md.lext, md.lins};
+                const bool ri_empty = b.ri_empty[e] != 0;
+                // seed column
+                int p0 = 0, p1 = n0;
+                const double* seed = nullptr;
+                double best = 0.0;
+                if (startind > 0)
+                {
+                    const long long gs = ev.col_off + startind;
+                    p0 = b.Fi0[gs]; p1 = p0 + b.Flen[gs] - 1;
+                    seed = b.Fm + gs * RS;
+                    best = b.Fbest[gs];
+                }
+                // reverse column to join with
+                int rab = min(max(Nm - last + 1, 0), N);
+                const long long gb = ev.col_off + rab;
+                int b0 = 0, blen = n0 + 1;
+                double mb = 0.0;
+                if (rab > 0) { b0 = b.Bi0[gb]; blen = b.Blen[gb]; mb = b.Bbest[gb]; }
+                double joinmax = 0.0;
+                double* prev = bufA; double* cur = bufB;
+                for (int c = startind + 1; c <= last; c++)
+                {
+                    int mid = ri_empty ? 1 : b.cen_new[ev.cen_off + c];
+                    int i0, i1;
+                    band_of(mid, n0, W, i0, i1);
+                    const int s = mut_state(mv, c - 1);
+                    const bool first_col = (c == startind + 1), last_col = (c == last);
+                    if (s >= 0)
+                    {
+                        const StateParams sp = md.st[s];
+                        double upC = 0, upS = 0;
+                        for (int i = i0; i <= i1; i++)
+                        {
+                            const double e_i = emission(mean[i - 1], stdv[i - 1], lsdv[n0 - i], sp, b.log2pi, b.lik_offset);
+                            const bool skip_ok = i >= p0 && i <= p1;
+                            const bool diag_ok = i > p0 && i <= p1;
+                            double Pi = 0, Pi1 = 0;
+                            if (first_col)
+                            {
+                                if (seed) { if (skip_ok) Pi = seed[i - p0]; if (diag_ok) Pi1 = seed[i - 1 - p0]; }
+                            }
+                            else
+                            {
+                                if (skip_ok) Pi = prev[(long long)(i - p0) * nthreads];
+                                if (diag_ok) Pi1 = prev[(long long)(i - 1 - p0) * nthreads];
+                            }
+                            double C, S; int step;
+                            dp_cell(i == i0, skip_ok, diag_ok, Pi, Pi1, e_i, e_i, upC, upS, tr, C, S, step);
+                            if (C > best) best = C;
+                            if (last_col)
+                            {
+                                const int jb = n0 - i + 1;
+                                if (jb >= b0 && jb < b0 + blen)
+                                {
+                                    double bm = rab > 0 ? b.Bm[gb * RS + jb - b0] : 0.0;
+                                    double bs = rab > 0 ? b.Bs[gb * RS + jb - b0] : 0.0;
+                                    joinmax = fmax(joinmax, fmax(C + bm, S + bs));
+                                }
+                            }
+                            else cur[(long long)(i - i0) * nthreads] = C;
+                            upC = C; upS = S;
+                        }
+                    }
+                    else
+                    {
+                        // invalid state: an all-zero column that inherits the running best
+                        if (last_col)
+                        {
+                            for (int i = i0; i <= i1; i++)
+                            {
+                                const int jb = n0 - i + 1;
+                                if (jb >= b0 && jb < b0 + blen)
+                                {
+                                    double bm = rab > 0 ? b.Bm[gb * RS + jb - b0] : 0.0;
+                                    double bs = rab > 0 ? b.Bs[gb * RS + jb - b0] : 0.0;
+                                    joinmax = fmax(joinmax, fmax(bm, bs));
+                                }
+                            }
+                        }
+                        else for (int i = i0; i <= i1; i++) cur[(long long)(i - i0) * nthreads] = 0.0;
+                    }
+                    p0 = i0; p1 = i1;
+                    double* tmp = prev; prev = cur; cur = tmp;
+                }
+                neu = fmax(fmax(joinmax, 0.0), fmax(best, mb));
+            }
+            result = neu - old;
+        }
+        b.delta[t] = result;
+    }
+}
+
+// k_reduce: score[m] = -1e-6 + sum_e delta(e, m), events in order (cpp/MakeMutations.cpp:38-52,
+// cpp/AlignUtil.h:84-90).  One thread per mutation; region_ev0/region_nev give its events.
+__global__ void k_reduce(Batch b, const int* mut_ev0, const int* mut_nev, const int* mut_local, long long n_muts)
+{
+    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_muts) return;
+    double s = -1e-6;
+    const int e0 = mut_ev0[g], ne = mut_nev[g], m = mut_local[g];
+    for (int e = e0; e < e0 + ne; e++) s += b.delta[b.ev[e].task_off + m];
+    b.scores[g] = s;
+}
+
+} // namespace psdev

@@ -1,0 +1,930 @@
+// ps_host.cu -- host side of the B200-native PoreSeq scoring path: context / region objects, the
+// batch scheduler that lays regions out in HBM and launches the kernels of ps_device.cuh, the host
+// drivers that stay sequential by nature (MakeMutations accept loop, FindPointMutations), and the
+// C-ABI of include/poreseq_b200.h.
+//
+// There is deliberately no CPU implementation of the DP here: if CUDA is unavailable every compute
+// entry point fails with PS_E_CUDA.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/poreseq_b200.h"
+#include "ps_device.cuh"
+#include "ps_internal.h"
+
+using namespace psdev;
+
+// ------------------------------------------------------------------------------------------
+// errors
+static std::string g_create_error;
+
+void ps_set_error(ps_ctx* ctx, const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->error = buf; else g_create_error = buf;
+}
+
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t err__ = (call);                                                               \
+        if (err__ != cudaSuccess)                                                                 \
+        {                                                                                         \
+            ps_set_error(ctx, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(err__), __FILE__, \
+                         __LINE__, #call);                                                        \
+            return PS_E_CUDA;                                                                     \
+        }                                                                                         \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// context
+int ps_ctx::init()
+{
+    ps_ctx* ctx = this;
+    if (ready) return PS_OK;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+    {
+        ps_set_error(ctx, "no CUDA device available (%s); poreseq_b200 has no CPU fallback",
+                     e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        return PS_E_CUDA;
+    }
+    if (device < 0 || device >= n) { ps_set_error(ctx, "device %d out of range (0..%d)", device, n - 1); return PS_E_ARG; }
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+    {
+        ps_set_error(ctx, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        return PS_E_CUDA;
+    }
+    sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreate(&stream));
+    for (int i = 0; i <= PS_T_COUNT; i++) CU(cudaEventCreate(&tev[i]));
+    CU(cudaFuncSetAttribute(k_fill<640>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CU(cudaFuncSetAttribute(k_fill<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    ready = true;
+    return PS_OK;
+}
+
+int ps_ctx::ensure(DevBuf& b, size_t bytes)
+{
+    ps_ctx* ctx = this;
+    if (bytes <= b.cap) return PS_OK;
+    if (b.p) CU(cudaFree(b.p));
+    b.p = nullptr; b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess)
+    {
+        cudaGetLastError();
+        e = cudaMalloc(&b.p, bytes);
+        want = bytes;
+    }
+    if (e != cudaSuccess)
+    {
+        ps_set_error(ctx, "out of device memory allocating %zu bytes (%s)", bytes, cudaGetErrorString(e));
+        b.p = nullptr;
+        return PS_E_CUDA;
+    }
+    b.cap = want;
+    return PS_OK;
+}
+
+ps_ctx::~ps_ctx()
+{
+    if (!ready) return;
+    cudaSetDevice(device);
+    for (auto& kv : bufs) if (kv.second.p) cudaFree(kv.second.p);
+    for (int i = 0; i <= PS_T_COUNT; i++) cudaEventDestroy(tev[i]);
+    cudaStreamDestroy(stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side sequence / event helpers
+std::vector<int> ps_states_of(const std::string& bases)     // cpp/Sequence.h:69-100
+{
+    std::vector<int> st;
+    const int n = (int)bases.size();
+    if (n < 5) return st;
+    st.reserve(n - 4);
+    auto code = [](char ch) -> int { return ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : (int)ch; };
+    int window = 0;
+    for (int i = 0; i < 4; i++) window = (window << 2) + code(bases[i]);
+    for (int i = 4; i < n; i++)
+    {
+        if (code(bases[i - 4]) < 4)
+        {
+            window = (N_STATES - 1) & ((window << 2) + code(bases[i]));
+            st.push_back(window);
+        }
+        else { window = 0; st.push_back(-1); }
+    }
+    return st;
+}
+
+std::string ps_apply_mutation(const std::string& bases, int start, const std::string& orig, const std::string& mut)
+{   // cpp/Sequence.h:38-59
+    if ((size_t)start >= bases.size()) return bases;
+    std::string out(bases, 0, start);
+    out += mut;
+    size_t rest = (size_t)start + orig.size();
+    if (rest < bases.size()) out.append(bases, rest, std::string::npos);
+    return out;
+}
+
+void HostEvent::update_refs()                                // cpp/EventData.h:110-169
+{
+    const int n = n0;
+    refstart = refend = -1;
+    int lo = 0, hi = n - 1;
+    while (lo < n && !(ref_align[lo] > 0)) lo++;
+    while (hi >= 0 && !(ref_align[hi] > 0)) hi--;
+    if (lo == n || hi < 0) { ri_empty = true; return; }
+    ri_empty = false;
+    refstart = (int)ref_align[lo];
+    refend = (int)ref_align[hi];
+    ref_index = ref_align;
+    const double slope = (ref_align[hi] - ref_align[lo]) / (double)(hi - lo);
+    const double icpt = ref_align[lo] - slope * lo;
+    int anchor = -1;
+    for (int i = 0; i < n; i++)
+    {
+        if (i < lo || i > hi) { ref_index[i] = slope * i + icpt; continue; }
+        if (!(ref_align[i] > 0)) continue;
+        if (anchor > 0)
+        {
+            const double m = (ref_align[i] - ref_align[anchor]) / (i - anchor);
+            for (int j = anchor + 1; j < i; j++) ref_index[j] = m * (j - anchor) + ref_align[anchor];
+        }
+        anchor = i;
+    }
+}
+
+static void build_model(const HostModel& hm, ModelDev& md)     // cpp/EventData.h:48-73
+{
+    for (int s = 0; s < N_STATES; s++)
+    {
+        StateParams& p = md.st[s];
+        p.lev_mean = hm.raw[0][s];
+        p.lev_stdv = hm.raw[1][s];
+        p.log_lev = std::log(hm.raw[1][s]);
+        p.sd_mean = hm.raw[2][s];
+        p.sd_lambda = std::pow(hm.raw[2][s], 3) / std::pow(hm.raw[3][s], 2);
+        p.log_lambda = std::log(p.sd_lambda);
+        p.pad0 = p.pad1 = 0;
+    }
+    md.lskip = std::log(hm.trans[0]);
+    md.lstay = std::log(hm.trans[1]);
+    md.lext = std::log(hm.trans[2]);
+    md.lins = std::log(hm.trans[3]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Job: one launch sequence over a batch of regions
+struct Job
+{
+    ps_ctx* ctx;
+    std::vector<ps_region*> regs;
+    std::vector<std::vector<HostMut>> muts;      // per region (empty for alignment-only jobs)
+    bool want_muts;
+
+    // host staging
+    std::vector<EvDesc> ev;
+    std::vector<const HostModel*> model_src;
+    std::vector<int> states;
+    std::string bases;
+    std::vector<double> mean, stdv, log_stdv, ref_align, ref_like, ref_index;
+    std::vector<int> ri_empty, mono;
+    std::vector<MutDev> mdev;
+    std::string mut_str;
+    std::vector<int> mut_ev0, mut_nev, mut_local;
+    long long n_levels, n_cols, n_cen, n_tasks, n_muts;
+    int cen_pad;
+    Batch b;
+
+    Job(ps_ctx* c) : ctx(c), want_muts(false), n_levels(0), n_cols(0), n_cen(0), n_tasks(0), n_muts(0), cen_pad(8) {}
+
+    int build();
+    int upload();
+    int run(bool backward_and_muts);
+    int download(std::vector<double>* align_scores, std::vector<double>* mut_scores);
+};
+
+int Job::build()
+{
+    const ps_params& P = regs[0]->params;
+    for (size_t r = 0; r < regs.size(); r++)
+    {
+        const ps_params& Q = regs[r]->params;
+        if (Q.lik_offset != P.lik_offset || Q.realign_width != P.realign_width || Q.scoring_width != P.scoring_width)
+        {
+            ps_set_error(ctx, "all regions of a batch must share lik_offset / realign_width / scoring_width");
+            return PS_E_ARG;
+        }
+    }
+    if (P.realign_width < 0 || P.realign_width > 511 || P.scoring_width < 0)
+    {
+        ps_set_error(ctx, "realign_width must be in 0..511 and scoring_width >= 0 (got %d, %d)", P.realign_width, P.scoring_width);
+        return PS_E_ARG;
+    }
+    // longest net insertion decides how far past N the post-backtrace centre table must reach
+    cen_pad = 8;
+    if (want_muts)
+        for (size_t r = 0; r < regs.size(); r++)
+            for (const HostMut& m : muts[r])
+                cen_pad = std::max(cen_pad, (int)m.mut.size() - (int)m.orig.size() + 8);
+
+    for (size_t r = 0; r < regs.size(); r++)
+    {
+        ps_region* R = regs[r];
+        const long long state_off = (long long)states.size();
+        const long long base_off = (long long)bases.size();
+        states.insert(states.end(), R->states.begin(), R->states.end());
+        bases += R->bases;
+        const long long mut_off = (long long)mdev.size();
+        const int nm = want_muts ? (int)muts[r].size() : 0;
+        const int ev0 = (int)ev.size();
+        for (int m = 0; m < nm; m++)
+        {
+            const HostMut& hm = muts[r][m];
+            MutDev d;
+            d.start = hm.start; d.n_orig = (int)hm.orig.size(); d.n_mut = (int)hm.mut.size();
+            d.str_off = (int)mut_str.size();
+            mut_str += hm.mut;
+            mdev.push_back(d);
+            mut_ev0.push_back(ev0);
+            mut_nev.push_back((int)R->events.size());
+            mut_local.push_back(m);
+        }
+        for (size_t k = 0; k < R->events.size(); k++)
+        {
+            const HostEvent& he = R->events[k];
+            EvDesc d;
+            memset(&d, 0, sizeof d);
+            d.region = (int)r;
+            d.n0 = he.n0;
+            d.N = (int)R->states.size();
+            d.L = (int)R->bases.size();
+            d.usable = (!he.ri_empty && R->params.realign_width != 0 && he.n0 > 0) ? 1 : 0;
+            // model de-duplication across the whole batch (events usually share two models)
+            const HostModel* hm = &R->models[he.model];
+            int mi = -1;
+            for (size_t q = 0; q < model_src.size(); q++)
+                if (model_src[q] == hm || memcmp(model_src[q], hm, sizeof(HostModel)) == 0) { mi = (int)q; break; }
+            if (mi < 0) { mi = (int)model_src.size(); model_src.push_back(hm); }
+            d.model = mi;
+            d.n_muts = nm;
+            d.lev_off = n_levels;
+            d.col_off = n_cols;
+            d.state_off = state_off;
+            d.base_off = base_off;
+            d.cen_off = n_cen;
+            d.mut_off = mut_off;
+            d.task_off = n_tasks;
+            n_levels += he.n0;
+            n_cols += d.N;                       // columns 1..N live at col_off+1 .. col_off+N
+            n_cen += d.N + cen_pad + 1;
+            n_tasks += nm;
+            ev.push_back(d);
+            mean.insert(mean.end(), he.mean.begin(), he.mean.end());
+            stdv.insert(stdv.end(), he.stdv.begin(), he.stdv.end());
+            log_stdv.insert(log_stdv.end(), he.log_stdv.begin(), he.log_stdv.end());
+            ref_align.insert(ref_align.end(), he.ref_align.begin(), he.ref_align.end());
+            ref_like.insert(ref_like.end(), he.ref_like.begin(), he.ref_like.end());
+            if (he.ri_empty) ref_index.insert(ref_index.end(), he.n0, 0.0);
+            else ref_index.insert(ref_index.end(), he.ref_index.begin(), he.ref_index.end());
+            ri_empty.push_back(he.ri_empty ? 1 : 0);
+        }
+    }
+    n_cols += 1;                                  // index 0 of the first event is never used
+    n_muts = (long long)mdev.size();
+    mono.assign(ev.size(), 1);
+    return PS_OK;
+}
+
+template <class T>
+static int up(ps_ctx* ctx, const char* name, const T* src, size_t count, T** out)
+{
+    DevBuf& buf = ctx->bufs[name];
+    int rc = ctx->ensure(buf, std::max<size_t>(count, 1) * sizeof(T));
+    if (rc) return rc;
+    if (count) CU(cudaMemcpyAsync(buf.p, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    *out = (T*)buf.p;
+    return PS_OK;
+}
+
+template <class T>
+static int room(ps_ctx* ctx, const char* name, size_t count, T** out)
+{
+    DevBuf& buf = ctx->bufs[name];
+    int rc = ctx->ensure(buf, std::max<size_t>(count, 1) * sizeof(T));
+    if (rc) return rc;
+    *out = (T*)buf.p;
+    return PS_OK;
+}
+
+#define TRY(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
+
+int Job::upload()
+{
+    memset(&b, 0, sizeof b);
+    const ps_params& P = regs[0]->params;
+    b.n_events = (int)ev.size();
+    b.lik_offset = P.lik_offset;
+    b.log2pi = std::log(2 * M_PI);                 // cpp/AlignUtil.h:24
+    b.realign_width = P.realign_width;
+    b.scoring_width = P.scoring_width;
+    b.cen_pad = cen_pad;
+    b.RS = ((2 * P.realign_width + 1) + 3) & ~3;
+    b.n_tasks = n_tasks;
+
+    std::vector<ModelDev> models(model_src.size());
+    for (size_t q = 0; q < model_src.size(); q++) build_model(*model_src[q], models[q]);
+
+    EvDesc* d_ev; ModelDev* d_models; int* d_states; char* d_bases;
+    double *d_mean, *d_stdv, *d_lsd;
+    TRY(up(ctx, "ev", ev.data(), ev.size(), &d_ev));
+    TRY(up(ctx, "models", models.data(), models.size(), &d_models));
+    TRY(up(ctx, "states", states.data(), states.size(), &d_states));
+    TRY(up(ctx, "bases", bases.data(), bases.size(), &d_bases));
+    TRY(up(ctx, "mean", mean.data(), mean.size(), &d_mean));
+    TRY(up(ctx, "stdv", stdv.data(), stdv.size(), &d_stdv));
+    TRY(up(ctx, "log_stdv", log_stdv.data(), log_stdv.size(), &d_lsd));
+    TRY(up(ctx, "ref_align", ref_align.data(), ref_align.size(), &b.ref_align));
+    TRY(up(ctx, "ref_like", ref_like.data(), ref_like.size(), &b.ref_like));
+    TRY(up(ctx, "ref_index", ref_index.data(), ref_index.size(), &b.ref_index));
+    TRY(up(ctx, "ri_empty", ri_empty.data(), ri_empty.size(), &b.ri_empty));
+    TRY(up(ctx, "mono", mono.data(), mono.size(), &b.mono));
+    b.ev = d_ev; b.models = d_models; b.states = d_states; b.bases = d_bases;
+    b.mean = d_mean; b.stdv = d_stdv; b.log_stdv = d_lsd;
+    TRY(room(ctx, "bt_src", (size_t)n_levels, &b.bt_src));
+    TRY(room(ctx, "refstart", ev.size(), &b.refstart));
+    TRY(room(ctx, "refend", ev.size(), &b.refend));
+    TRY(room(ctx, "cen_old", (size_t)n_cen, &b.cen_old));
+    TRY(room(ctx, "cen_new", (size_t)n_cen, &b.cen_new));
+
+    const size_t cells = (size_t)n_cols * b.RS;
+    TRY(room(ctx, "Fm", cells, &b.Fm));
+    TRY(room(ctx, "Fs", cells, &b.Fs));
+    TRY(room(ctx, "Fstep", cells, &b.Fstep));
+    TRY(room(ctx, "Fi0", (size_t)n_cols, &b.Fi0));
+    TRY(room(ctx, "Flen", (size_t)n_cols, &b.Flen));
+    TRY(room(ctx, "Fcb", (size_t)n_cols, &b.Fcb));
+    TRY(room(ctx, "Fcbi", (size_t)n_cols, &b.Fcbi));
+    TRY(room(ctx, "Fbest", (size_t)n_cols, &b.Fbest));
+    TRY(room(ctx, "Fbi", (size_t)n_cols, &b.Fbi));
+    TRY(room(ctx, "Fbj", (size_t)n_cols, &b.Fbj));
+    if (want_muts)
+    {
+        TRY(room(ctx, "Bm", cells, &b.Bm));
+        TRY(room(ctx, "Bs", cells, &b.Bs));
+        TRY(room(ctx, "Bi0", (size_t)n_cols, &b.Bi0));
+        TRY(room(ctx, "Blen", (size_t)n_cols, &b.Blen));
+        TRY(room(ctx, "Bcb", (size_t)n_cols, &b.Bcb));
+        TRY(room(ctx, "Bcbi", (size_t)n_cols, &b.Bcbi));
+        TRY(room(ctx, "Bbest", (size_t)n_cols, &b.Bbest));
+        TRY(room(ctx, "old", (size_t)n_cols, &b.old));
+        MutDev* d_m; char* d_ms;
+        TRY(up(ctx, "muts", mdev.data(), mdev.size(), &d_m));
+        TRY(up(ctx, "mut_str", mut_str.data(), mut_str.size(), &d_ms));
+        b.muts = d_m; b.mut_str = d_ms;
+        TRY(room(ctx, "delta", (size_t)n_tasks, &b.delta));
+        TRY(room(ctx, "scores", (size_t)n_muts, &b.scores));
+    }
+    return PS_OK;
+}
+
+#define MARK(i) CU(cudaEventRecord(ctx->tev[i], ctx->stream))
+#define LAUNCHED() do { ctx->launches++; CU(cudaGetLastError()); } while (0)
+
+int Job::run(bool full)
+{
+    const int nev = (int)ev.size();
+    int maxN = 0;
+    for (const EvDesc& d : ev) maxN = std::max(maxN, d.N);
+    if (nev == 0) return PS_OK;
+    MARK(PS_T_CENTRES);
+    {
+        dim3 grid((maxN + cen_pad + 1 + 127) / 128, nev);
+        k_centres<<<grid, 128, 0, ctx->stream>>>(b, b.cen_old, 1);
+        LAUNCHED();
+    }
+    MARK(PS_T_FORWARD);
+    // wavefront fill: T threads >= band length; forward and reverse in one launch (grid.y = 2)
+    {
+        const int band = 2 * b.realign_width + 1;
+        int T = std::min(1024, ((band + 31) / 32) * 32);
+        T = std::max(T, 64);
+        const size_t smem = std::max<size_t>(6 * T, 2 * b.RS) * sizeof(double);
+        dim3 grid(nev, full ? 2 : 1);
+        if (T <= 640) k_fill<640><<<grid, T, smem, ctx->stream>>>(b, 0);
+        else k_fill<1024><<<grid, T, smem, ctx->stream>>>(b, 0);
+        LAUNCHED();
+    }
+    MARK(PS_T_BACKWARD);   // (reverse fill shares the launch above; kept as a phase marker)
+    MARK(PS_T_BACKTRACE);
+    k_backtrace<<<nev, 128, 0, ctx->stream>>>(b);
+    LAUNCHED();
+    MARK(PS_T_JOIN);
+    if (full && n_tasks > 0)
+    {
+        {
+            dim3 grid((maxN + cen_pad + 1 + 127) / 128, nev);
+            k_centres<<<grid, 128, 0, ctx->stream>>>(b, b.cen_new, 0);
+            LAUNCHED();
+        }
+        {
+            dim3 grid((maxN + 3) / 4, nev);
+            k_join<<<grid, 128, 0, ctx->stream>>>(b);
+            LAUNCHED();
+        }
+        MARK(PS_T_MUTSCORE);
+        {
+            const int threads = 128;
+            long long blocks = std::min<long long>((n_tasks + threads - 1) / threads, (long long)ctx->sm_count * 8);
+            b.scratch_slots = blocks * threads;
+            const size_t strip = (size_t)(2 * b.scoring_width + 1);
+            TRY(room(ctx, "scratch", (size_t)b.scratch_slots * strip * 2, &b.scratch));
+            k_mutscore<<<(unsigned)blocks, threads, 0, ctx->stream>>>(b);
+            LAUNCHED();
+        }
+        MARK(PS_T_REDUCE);
+        {
+            int *d_e0, *d_ne, *d_ml;
+            TRY(up(ctx, "mut_ev0", mut_ev0.data(), mut_ev0.size(), &d_e0));
+            TRY(up(ctx, "mut_nev", mut_nev.data(), mut_nev.size(), &d_ne));
+            TRY(up(ctx, "mut_local", mut_local.data(), mut_local.size(), &d_ml));
+            k_reduce<<<(unsigned)((n_muts + 127) / 128), 128, 0, ctx->stream>>>(b, d_e0, d_ne, d_ml, n_muts);
+            LAUNCHED();
+        }
+    }
+    else { MARK(PS_T_MUTSCORE); MARK(PS_T_REDUCE); }
+    MARK(PS_T_D2H);
+    return PS_OK;
+}
+
+int Job::download(std::vector<double>* align_scores, std::vector<double>* mut_scores)
+{
+    const size_t nl = (size_t)n_levels, ne = ev.size();
+    std::vector<int> rs(ne), re(ne);
+    if (nl)
+    {
+        CU(cudaMemcpyAsync(ref_align.data(), b.ref_align, nl * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(ref_like.data(), b.ref_like, nl * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(ref_index.data(), b.ref_index, nl * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (ne)
+    {
+        CU(cudaMemcpyAsync(ri_empty.data(), b.ri_empty, ne * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(rs.data(), b.refstart, ne * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(re.data(), b.refend, ne * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    std::vector<double> best(ne, 0.0);
+    if (align_scores)
+        for (size_t e = 0; e < ne; e++)
+            if (ev[e].usable && ev[e].N > 0)
+                CU(cudaMemcpyAsync(&best[e], b.Fbest + ev[e].col_off + ev[e].N, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (mut_scores)
+    {
+        mut_scores->assign((size_t)n_muts, -1e-6);
+        if (n_muts && n_tasks)
+            CU(cudaMemcpyAsync(mut_scores->data(), b.scores, (size_t)n_muts * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    MARK(PS_T_TOTAL);
+    CU(cudaStreamSynchronize(ctx->stream));
+    // scatter the realigned events back into their regions
+    size_t e = 0;
+    for (ps_region* R : regs)
+        for (HostEvent& he : R->events)
+        {
+            const EvDesc& d = ev[e];
+            if (d.usable)
+            {
+                std::copy(ref_align.begin() + d.lev_off, ref_align.begin() + d.lev_off + d.n0, he.ref_align.begin());
+                std::copy(ref_like.begin() + d.lev_off, ref_like.begin() + d.lev_off + d.n0, he.ref_like.begin());
+                he.ri_empty = ri_empty[e] != 0;
+                he.refstart = rs[e]; he.refend = re[e];
+                if (he.ri_empty) he.ref_index.clear();
+                else he.ref_index.assign(ref_index.begin() + d.lev_off, ref_index.begin() + d.lev_off + d.n0);
+            }
+            e++;
+        }
+    if (align_scores)
+    {
+        align_scores->resize(ne);
+        for (size_t k = 0; k < ne; k++) (*align_scores)[k] = std::max(best[k], 0.0);   // cpp/Alignment.h:127-130
+    }
+    // timings + algorithmic cell counts
+    for (int i = 0; i < PS_T_TOTAL; i++)
+    {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->tev[i], ctx->tev[i + 1]);
+        ctx->timing[i] = ms;
+    }
+    float tot = 0;
+    cudaEventElapsedTime(&tot, ctx->tev[PS_T_H2D], ctx->tev[PS_T_TOTAL]);
+    ctx->timing[PS_T_TOTAL] = tot;
+    return PS_OK;
+}
+
+// algorithmic DP cells: wide = sum over usable events and columns of the band
+// length; narrow = (|mut|+5) * band rows per (mutation, usable event) pair.  Computed on the host
+// from the same band rules the kernels use, with the event's pre-call alignment (the definition
+// is about problem size, not about what was executed).
+static void count_cells(const Job& job, bool full, double* wide, double* narrow)
+{
+    *wide = 0; *narrow = 0;
+    size_t e = 0;
+    for (size_t r = 0; r < job.regs.size(); r++)
+    {
+        const ps_region* R = job.regs[r];
+        const int N = (int)R->states.size();
+        const int rw = R->params.realign_width, sw = R->params.scoring_width;
+        for (const HostEvent& he : R->events)
+        {
+            const EvDesc& d = job.ev[e++];
+            if (!d.usable) continue;
+            double w = 0;
+            const int n0 = he.n0;
+            for (int c = 1; c <= N; c++)
+            {
+                int mid = (int)(std::lower_bound(he.ref_index.begin(), he.ref_index.end(), (double)c) - he.ref_index.begin());
+                mid = std::min(std::max(mid, 1), n0);
+                w += std::min(n0, mid + rw) - std::max(1, mid - rw) + 1;
+            }
+            *wide += full ? 2 * w : w;
+            if (full)
+            {
+                const double rows = std::min(n0, 2 * sw + 1);
+                for (const HostMut& m : job.muts[r])
+                    if (!((size_t)m.start > R->bases.size())) *narrow += (double)(m.mut.size() + 5) * rows;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// drivers shared by the C entry points
+static int run_job(ps_ctx* ctx, std::vector<ps_region*> regs, std::vector<std::vector<HostMut>>* muts,
+                   std::vector<double>* align_scores, std::vector<double>* mut_scores)
+{
+    TRY(ctx->init());
+    CU(cudaSetDevice(ctx->device));
+    for (ps_region* R : regs)
+        if (R->bases.size() < 5) { ps_set_error(ctx, "sequences shorter than 5 bases are not supported"); return PS_E_ARG; }
+    Job job(ctx);
+    job.regs = regs;
+    job.want_muts = muts != nullptr;
+    if (muts) job.muts = *muts;
+    TRY(job.build());
+    MARK(PS_T_H2D);
+    TRY(job.upload());
+    TRY(job.run(muts != nullptr));
+    TRY(job.download(align_scores, mut_scores));
+    count_cells(job, muts != nullptr, &ctx->wide_cells, &ctx->narrow_cells);
+    return PS_OK;
+}
+
+std::vector<HostMut> ps_point_mutations(const ps_region* R)      // cpp/FindMutations.cpp:191-234
+{
+    static const char acgt[] = "ACGT";
+    std::vector<HostMut> v;
+    v.reserve(R->states.size() * 8);
+    for (int i = 0; i < (int)R->states.size(); i++)
+    {
+        const char here = R->bases[i];
+        HostMut m;
+        m.start = i; m.score = -1e-6;
+        m.orig.assign(1, here);
+        v.push_back(m);                                   // deletion
+        for (int j = 0; j < 4; j++)
+            if (acgt[j] != here) { m.mut.assign(1, acgt[j]); v.push_back(m); }    // substitutions
+        m.orig.clear();
+        for (int j = 0; j < 4; j++) { m.mut.assign(1, acgt[j]); v.push_back(m); } // insertions
+    }
+    return v;
+}
+
+int ps_score_mutation_list(ps_region* R, std::vector<HostMut>& muts)
+{
+    std::vector<std::vector<HostMut>> per(1, muts);
+    std::vector<double> sc;
+    TRY(run_job(R->ctx, std::vector<ps_region*>(1, R), &per, nullptr, &sc));
+    for (size_t i = 0; i < muts.size(); i++) muts[i].score = sc[i];
+    return PS_OK;
+}
+
+static bool by_score_desc(const HostMut& a, const HostMut& b) { return a.score > b.score; }
+
+// cpp/MakeMutations.cpp:74-146.  std::sort with the same ordering predicate on the same element
+// order reproduces the reference's (unstable) tie placement.
+int ps_make_mutation_list(ps_region* R, std::vector<HostMut> muts, int* nbases)
+{
+    const int spacing = 10;
+    int changed = 0;
+    std::sort(muts.begin(), muts.end(), by_score_desc);
+    while (!muts.empty() && muts.back().score < 0) muts.pop_back();
+    *nbases = 0;
+    if (muts.empty()) return PS_OK;
+    std::vector<HostMut> deferred;
+    for (size_t i = 0; i < muts.size(); i++)
+    {
+        HostMut& a = muts[i];
+        if (a.score < 0) { deferred.push_back(a); continue; }
+        R->set_sequence(ps_apply_mutation(R->bases, a.start, a.orig, a.mut));
+        changed += (int)std::max(a.orig.size(), a.mut.size());
+        for (size_t j = i + 1; j < muts.size(); j++)
+        {
+            HostMut& c = muts[j];
+            const int lo = std::max(a.start, c.start);
+            const int hi = (int)std::min((size_t)a.start + a.mut.size(), (size_t)c.start + c.mut.size());
+            if (lo < hi + spacing && c.score > 0) { c.score = -1; continue; }
+            if ((size_t)c.start >= (size_t)a.start + a.orig.size())
+                c.start += (int)(a.mut.size() - a.orig.size());
+        }
+    }
+    if (deferred.size() > 10)
+    {
+        int more = 0;
+        TRY(ps_score_mutation_list(R, deferred));
+        TRY(ps_make_mutation_list(R, deferred, &more));
+        changed += more;
+    }
+    *nbases = changed;
+    return PS_OK;
+}
+
+void ps_region::set_sequence(const std::string& s)
+{
+    bases = s;
+    states = ps_states_of(s);
+}
+
+// ------------------------------------------------------------------------------------------
+// C-ABI
+extern "C" {
+
+const char* ps_version(void) { return "poreseq_b200 0.1 (sm_100a, fp64-exact)"; }
+
+ps_ctx* ps_create(int device)
+{
+    ps_ctx* ctx = new ps_ctx();
+    ctx->device = device;
+    return ctx;                       // CUDA is initialised lazily (fork-safe)
+}
+
+void ps_destroy(ps_ctx* ctx) { delete ctx; }
+
+const char* ps_last_error(ps_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+long long ps_launch_count(ps_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int ps_last_timing(ps_ctx* ctx, double* ms)
+{
+    if (!ctx || !ms) return PS_E_ARG;
+    for (int i = 0; i < PS_T_COUNT; i++) ms[i] = ctx->timing[i];
+    return PS_OK;
+}
+
+int ps_last_cells(ps_ctx* ctx, double* wide, double* narrow)
+{
+    if (!ctx) return PS_E_ARG;
+    if (wide) *wide = ctx->wide_cells;
+    if (narrow) *narrow = ctx->narrow_cells;
+    return PS_OK;
+}
+
+ps_region* ps_region_create(ps_ctx* ctx, const char* bases, int len, const ps_params* params)
+{
+    if (!ctx || !bases || len < 0) { ps_set_error(ctx, "ps_region_create: bad arguments"); return nullptr; }
+    ps_region* R = new ps_region();
+    R->ctx = ctx;
+    R->set_sequence(std::string(bases, len));
+    if (params) R->params = *params;
+    else { R->params.lik_offset = 4.5; R->params.scoring_width = 150; R->params.realign_width = 300; R->params.verbose = 0; }
+    return R;
+}
+
+void ps_region_destroy(ps_region* r) { delete r; }
+
+int ps_region_add_event(ps_region* R, int n0, const double* mean, const double* stdv, const double* ref_align,
+                        const double* ref_like, const double* level_mean, const double* level_stdv,
+                        const double* sd_mean, const double* sd_stdv, int complement, double prob_skip,
+                        double prob_stay, double prob_extend, double prob_insert, const char* seq2d)
+{
+    if (!R) return PS_E_ARG;
+    ps_ctx* ctx = R->ctx;
+    if (n0 < 0 || (n0 > 0 && (!mean || !stdv || !ref_align || !ref_like)) || !level_mean || !level_stdv || !sd_mean || !sd_stdv)
+    {
+        ps_set_error(ctx, "ps_region_add_event: bad arguments");
+        return PS_E_ARG;
+    }
+    HostModel hm;
+    memset(&hm, 0, sizeof hm);
+    memcpy(hm.raw[0], level_mean, sizeof hm.raw[0]);
+    memcpy(hm.raw[1], level_stdv, sizeof hm.raw[1]);
+    memcpy(hm.raw[2], sd_mean, sizeof hm.raw[2]);
+    memcpy(hm.raw[3], sd_stdv, sizeof hm.raw[3]);
+    hm.trans[0] = prob_skip; hm.trans[1] = prob_stay; hm.trans[2] = prob_extend; hm.trans[3] = prob_insert;
+    int mi = -1;
+    for (size_t q = 0; q < R->models.size(); q++)
+        if (memcmp(&R->models[q], &hm, sizeof hm) == 0) { mi = (int)q; break; }
+    if (mi < 0) { mi = (int)R->models.size(); R->models.push_back(hm); }
+    HostEvent he;
+    he.n0 = n0;
+    he.model = mi;
+    he.complement = complement != 0;
+    he.mean.assign(mean, mean + n0);
+    he.stdv.assign(stdv, stdv + n0);
+    he.ref_align.assign(ref_align, ref_align + n0);
+    he.ref_like.assign(ref_like, ref_like + n0);
+    he.log_stdv.resize(n0);
+    for (int i = 0; i < n0; i++) he.log_stdv[i] = std::log(he.stdv[i]);      // cpp/EventData.h:218-220
+    if (seq2d) he.seq2d = seq2d;
+    he.update_refs();
+    R->events.push_back(std::move(he));
+    return PS_OK;
+}
+
+int ps_region_set_params(ps_region* R, const ps_params* p)
+{
+    if (!R || !p) return PS_E_ARG;
+    R->params = *p;
+    return PS_OK;
+}
+
+int ps_region_num_events(ps_region* R) { return R ? (int)R->events.size() : PS_E_ARG; }
+int ps_region_sequence_length(ps_region* R) { return R ? (int)R->bases.size() : PS_E_ARG; }
+
+int ps_region_get_sequence(ps_region* R, char* out, int cap)
+{
+    if (!R || !out) return PS_E_ARG;
+    if ((int)R->bases.size() + 1 > cap) { ps_set_error(R->ctx, "sequence buffer too small"); return PS_E_CAPACITY; }
+    memcpy(out, R->bases.c_str(), R->bases.size() + 1);
+    return PS_OK;
+}
+
+int ps_region_get_event_align(ps_region* R, int e, double* ref_align, double* ref_like)
+{
+    if (!R || e < 0 || e >= (int)R->events.size()) return PS_E_ARG;
+    const HostEvent& he = R->events[e];
+    if (ref_align) std::copy(he.ref_align.begin(), he.ref_align.end(), ref_align);
+    if (ref_like) std::copy(he.ref_like.begin(), he.ref_like.end(), ref_like);
+    return PS_OK;
+}
+
+int ps_score_alignments(ps_region* R, double* scores, double* likes)
+{
+    if (!R || !scores) return PS_E_ARG;
+    std::vector<double> sc;
+    TRY(run_job(R->ctx, std::vector<ps_region*>(1, R), nullptr, &sc, nullptr));
+    std::copy(sc.begin(), sc.end(), scores);
+    if (likes)
+    {
+        // per-base likelihood profile, cpp/MakeMutations.cpp:168-189 (events in order)
+        const int N = (int)R->states.size();
+        for (const HostEvent& he : R->events)
+        {
+            double carried = 0;
+            int at = 1;
+            for (int j = 0; j < he.n0; j++)
+                if (he.ref_align[j] > 0)
+                {
+                    for (int k = at; k < he.ref_align[j]; k++) likes[k + 1] += carried;
+                    carried = he.ref_like[j];
+                    at = (int)he.ref_align[j];
+                }
+            for (int k = at; k < N + 3; k++) likes[k + 1] += carried;
+        }
+    }
+    return PS_OK;
+}
+
+static std::vector<HostMut> gather_muts(int n, const int* start, const char* const* orig, const char* const* mut,
+                                        const double* scores)
+{
+    std::vector<HostMut> v(n);
+    for (int i = 0; i < n; i++)
+    {
+        v[i].start = start[i];
+        v[i].orig = orig[i] ? orig[i] : "";
+        v[i].mut = mut[i] ? mut[i] : "";
+        v[i].score = scores ? scores[i] : -1e-6;
+    }
+    return v;
+}
+
+int ps_score_mutations(ps_region* R, int n, const int* start, const char* const* orig, const char* const* mut, double* scores)
+{
+    if (!R || n < 0 || (n > 0 && (!start || !orig || !mut || !scores))) return PS_E_ARG;
+    std::vector<HostMut> v = gather_muts(n, start, orig, mut, nullptr);
+    TRY(ps_score_mutation_list(R, v));
+    for (int i = 0; i < n; i++) scores[i] = v[i].score;
+    return PS_OK;
+}
+
+static int emit_points(ps_ctx* ctx, const std::vector<HostMut>& v, int cap, int* n, int* start, char* orig, char* mut, double* scores)
+{
+    if (n) *n = (int)v.size();
+    if ((int)v.size() > cap) { ps_set_error(ctx, "output capacity %d < %zu point mutations", cap, v.size()); return PS_E_CAPACITY; }
+    for (size_t i = 0; i < v.size(); i++)
+    {
+        if (start) start[i] = v[i].start;
+        if (orig) orig[i] = v[i].orig.empty() ? 0 : v[i].orig[0];
+        if (mut) mut[i] = v[i].mut.empty() ? 0 : v[i].mut[0];
+        if (scores) scores[i] = v[i].score;
+    }
+    return PS_OK;
+}
+
+int ps_find_point_mutations(ps_region* R, int cap, int* n, int* start, char* orig, char* mut)
+{
+    if (!R) return PS_E_ARG;
+    return emit_points(R->ctx, ps_point_mutations(R), cap, n, start, orig, mut, nullptr);
+}
+
+int ps_score_points(ps_region* R, int cap, int* n, int* start, char* orig, char* mut, double* scores)
+{
+    if (!R) return PS_E_ARG;
+    std::vector<HostMut> v = ps_point_mutations(R);
+    if ((int)v.size() > cap) { if (n) *n = (int)v.size(); ps_set_error(R->ctx, "output capacity too small"); return PS_E_CAPACITY; }
+    TRY(ps_score_mutation_list(R, v));
+    return emit_points(R->ctx, v, cap, n, start, orig, mut, scores);
+}
+
+int ps_score_points_batch(ps_region* const* regions, int n_regions, int cap, int* n_out, long long* off_out,
+                          int* start, char* orig, char* mut, double* scores)
+{
+    if (!regions || n_regions <= 0) return PS_E_ARG;
+    ps_ctx* ctx = regions[0]->ctx;
+    std::vector<ps_region*> regs(regions, regions + n_regions);
+    std::vector<std::vector<HostMut>> per(n_regions);
+    long long total = 0;
+    for (int r = 0; r < n_regions; r++)
+    {
+        if (regs[r]->ctx != ctx) { ps_set_error(ctx, "all regions of a batch must belong to one context"); return PS_E_ARG; }
+        per[r] = ps_point_mutations(regs[r]);
+        total += (long long)per[r].size();
+    }
+    if (total > cap) { ps_set_error(ctx, "output capacity %d < %lld point mutations", cap, total); return PS_E_CAPACITY; }
+    std::vector<double> sc;
+    TRY(run_job(ctx, regs, &per, nullptr, &sc));
+    long long at = 0;
+    for (int r = 0; r < n_regions; r++)
+    {
+        if (n_out) n_out[r] = (int)per[r].size();
+        if (off_out) off_out[r] = at;
+        for (size_t i = 0; i < per[r].size(); i++, at++)
+        {
+            if (start) start[at] = per[r][i].start;
+            if (orig) orig[at] = per[r][i].orig.empty() ? 0 : per[r][i].orig[0];
+            if (mut) mut[at] = per[r][i].mut.empty() ? 0 : per[r][i].mut[0];
+            if (scores) scores[at] = sc[at];
+        }
+    }
+    return PS_OK;
+}
+
+int ps_make_mutations(ps_region* R, int n, const int* start, const char* const* orig, const char* const* mut,
+                      const double* scores, int* nbases)
+{
+    if (!R || n < 0 || (n > 0 && (!start || !orig || !mut || !scores))) return PS_E_ARG;
+    int nb = 0;
+    TRY(ps_make_mutation_list(R, gather_muts(n, start, orig, mut, scores), &nb));
+    if (nbases) *nbases = nb;
+    return PS_OK;
+}
+
+int ps_refine(ps_region* R, int* nbases)
+{
+    if (!R) return PS_E_ARG;
+    std::vector<HostMut> v = ps_point_mutations(R);
+    TRY(ps_score_mutation_list(R, v));
+    int nb = 0;
+    TRY(ps_make_mutation_list(R, v, &nb));
+    if (nbases) *nbases = nb;
+    return PS_OK;
+}
+
+int ps_seq_to_states(const char* seq, int len, int* states)
+{
+    if (!seq || len < 0) return PS_E_ARG;
+    std::vector<int> st = ps_states_of(std::string(seq, len));
+    if (states) std::copy(st.begin(), st.end(), states);
+    return (int)st.size();
+}
+
+} // extern "C"

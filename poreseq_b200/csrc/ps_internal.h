@@ -1,0 +1,73 @@
+// ps_internal.h -- host-side objects behind the opaque handles of include/poreseq_b200.h.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/poreseq_b200.h"
+
+struct DevBuf { void* p = nullptr; size_t cap = 0; };
+
+struct ps_ctx
+{
+    int device = 0;
+    bool ready = false;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t tev[PS_T_COUNT + 1];
+    double timing[PS_T_COUNT] = {0};
+    double wide_cells = 0, narrow_cells = 0;
+    long long launches = 0;
+    std::string error;
+    std::map<std::string, DevBuf> bufs;       // grow-only named device buffers, reused across calls
+
+    int init();                               // lazy CUDA initialisation
+    int ensure(DevBuf& b, size_t bytes);
+    ~ps_ctx();
+};
+
+struct HostModel                              // raw inputs of ModelData::setData/setParams
+{
+    double raw[4][PS_N_STATES];               // level_mean, level_stdv, sd_mean, sd_stdv
+    double trans[4];                          // prob_skip, prob_stay, prob_extend, prob_insert
+};
+
+struct HostEvent                              // cpp/EventData.h:78-229
+{
+    int n0 = 0;
+    int model = 0;
+    bool complement = false;
+    bool ri_empty = true;
+    int refstart = -1, refend = -1;
+    std::vector<double> mean, stdv, log_stdv, ref_align, ref_like, ref_index;
+    std::string seq2d;
+    void update_refs();
+};
+
+struct HostMut                                // cpp/AlignUtil.h:69-92 MutInfo / MutScore
+{
+    int start = 0;
+    std::string orig, mut;
+    double score = -1e-6;
+};
+
+struct ps_region                              // cpp/AlignData.h:24-34
+{
+    ps_ctx* ctx = nullptr;
+    std::string bases;
+    std::vector<int> states;
+    std::vector<HostEvent> events;
+    std::vector<HostModel> models;
+    ps_params params;
+    std::map<std::string, std::vector<double>> seqlikes;   // FindMutations cache (cpp/AlignData.h:34)
+    void set_sequence(const std::string& s);
+};
+
+void ps_set_error(ps_ctx* ctx, const char* fmt, ...);
+std::vector<int> ps_states_of(const std::string& bases);
+std::string ps_apply_mutation(const std::string& bases, int start, const std::string& orig, const std::string& mut);
+std::vector<HostMut> ps_point_mutations(const ps_region* R);
+int ps_score_mutation_list(ps_region* R, std::vector<HostMut>& muts);
+int ps_make_mutation_list(ps_region* R, std::vector<HostMut> muts, int* nbases);

@@ -1,0 +1,376 @@
+"""Drop-in mirror of the reference's Cython module `poreseq.poreseqcpp`
+(poreseq/_poreseqcpp.pyx:155-473): `PSAlign`, `swalign`, `seqtostates`, with every native call going
+through the C-ABI of include/poreseq_b200.h into the sm_100a library.
+
+Like the reference, every PSAlign method re-marshals the Python-side state into a fresh native
+region (PythonToAlignData, pyx:139-153), and only Mutate / Refine / ApplyMuts write the realigned
+events back (pyx:131-137, 374, 433, 470).
+
+There is no CPU fallback: importing works anywhere, but any compute call raises RuntimeError when
+the CUDA library is missing or no sm_100 device is present.
+"""
+import copy
+import ctypes as C
+import os
+
+import numpy as np
+
+from .Util import MutationInfo, MutationScore  # noqa: F401  (re-exported like the reference)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libporeseq_b200.so")
+_c_double_p = C.POINTER(C.c_double)
+_c_int_p = C.POINTER(C.c_int)
+
+PS_T_NAMES = ["h2d", "centres", "forward", "backward", "backtrace", "join", "mutscore", "reduce", "d2h", "total"]
+
+
+class PSParams(C.Structure):
+    _fields_ = [("lik_offset", C.c_double), ("scoring_width", C.c_int), ("realign_width", C.c_int), ("verbose", C.c_int)]
+
+
+_lib = None
+
+
+def lib():
+    """The native library; raises loudly if it has not been built (python -m poreseq_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise RuntimeError("poreseq_b200: %s is missing -- build it with `python -m poreseq_b200.build`; "
+                           "there is no CPU fallback" % _LIB_PATH)
+    L = C.CDLL(_LIB_PATH)
+    L.ps_create.restype = C.c_void_p
+    L.ps_create.argtypes = [C.c_int]
+    L.ps_destroy.argtypes = [C.c_void_p]
+    L.ps_last_error.restype = C.c_char_p
+    L.ps_last_error.argtypes = [C.c_void_p]
+    L.ps_version.restype = C.c_char_p
+    L.ps_launch_count.restype = C.c_longlong
+    L.ps_launch_count.argtypes = [C.c_void_p]
+    L.ps_last_timing.argtypes = [C.c_void_p, _c_double_p]
+    L.ps_last_cells.argtypes = [C.c_void_p, _c_double_p, _c_double_p]
+    L.ps_region_create.restype = C.c_void_p
+    L.ps_region_create.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(PSParams)]
+    L.ps_region_destroy.argtypes = [C.c_void_p]
+    L.ps_region_add_event.argtypes = [C.c_void_p, C.c_int] + [_c_double_p] * 8 + [C.c_int] + [C.c_double] * 4 + [C.c_char_p]
+    L.ps_region_set_params.argtypes = [C.c_void_p, C.POINTER(PSParams)]
+    L.ps_region_num_events.argtypes = [C.c_void_p]
+    L.ps_region_sequence_length.argtypes = [C.c_void_p]
+    L.ps_region_get_sequence.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    L.ps_region_get_event_align.argtypes = [C.c_void_p, C.c_int, _c_double_p, _c_double_p]
+    L.ps_score_alignments.argtypes = [C.c_void_p, _c_double_p, _c_double_p]
+    L.ps_score_mutations.argtypes = [C.c_void_p, C.c_int, _c_int_p, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), _c_double_p]
+    L.ps_find_point_mutations.argtypes = [C.c_void_p, C.c_int, _c_int_p, _c_int_p, C.c_char_p, C.c_char_p]
+    L.ps_score_points.argtypes = [C.c_void_p, C.c_int, _c_int_p, _c_int_p, C.c_char_p, C.c_char_p, _c_double_p]
+    L.ps_score_points_batch.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, _c_int_p, C.POINTER(C.c_longlong),
+                                        _c_int_p, C.c_char_p, C.c_char_p, _c_double_p]
+    L.ps_make_mutations.argtypes = [C.c_void_p, C.c_int, _c_int_p, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), _c_double_p, _c_int_p]
+    L.ps_refine.argtypes = [C.c_void_p, _c_int_p]
+    L.ps_seq_to_states.argtypes = [C.c_char_p, C.c_int, _c_int_p]
+    _lib = L
+    return L
+
+
+class Context(object):
+    """One CUDA device + stream + scratch memory (ps_ctx)."""
+
+    def __init__(self, device=0):
+        self.lib = lib()
+        self.handle = self.lib.ps_create(int(device))
+        if not self.handle:
+            raise RuntimeError("ps_create failed: %s" % self.lib.ps_last_error(None).decode())
+        self.device = device
+
+    def close(self):
+        if self.handle:
+            self.lib.ps_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc != 0:
+            raise RuntimeError("poreseq_b200 error %d: %s" % (rc, self.lib.ps_last_error(self.handle).decode()))
+
+    def launch_count(self):
+        return int(self.lib.ps_launch_count(self.handle))
+
+    def last_timing(self):
+        ms = (C.c_double * len(PS_T_NAMES))()
+        self.check(self.lib.ps_last_timing(self.handle, ms))
+        return dict(zip(PS_T_NAMES, list(ms)))
+
+    def last_cells(self):
+        w, n = C.c_double(0), C.c_double(0)
+        self.check(self.lib.ps_last_cells(self.handle, C.byref(w), C.byref(n)))
+        return w.value, n.value
+
+
+_default_ctx = {}
+
+
+def default_context(device=None):
+    """Per-process context for a device (default: LOCAL_RANK or 0)."""
+    if device is None:
+        device = int(os.environ.get("PORESEQ_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+def _dp(a):
+    return a.ctypes.data_as(_c_double_p)
+
+
+def _f8(a):
+    return np.ascontiguousarray(a, dtype="f8")
+
+
+def _cstrs(items):
+    arr = (C.c_char_p * max(len(items), 1))()
+    for i, s in enumerate(items):
+        arr[i] = s.encode("ascii") if isinstance(s, str) else bytes(s)
+    return arr
+
+
+class NativeRegion(object):
+    """ps_region built from a PSAlign-like object (sequence, events, params)."""
+
+    def __init__(self, ctx, sequence, events, params, width_key=None):
+        self.ctx = ctx
+        L = ctx.lib
+        p = PSParams(4.5, 150, 300, 0)          # cpp/AlignUtil.h:64 defaults
+        if "verbose" in params:
+            p.verbose = int(params["verbose"])
+        if "lik_offset" in params:
+            p.lik_offset = float(params["lik_offset"])
+        if "realign_width" in params:
+            p.realign_width = int(params["realign_width"])
+        if "scoring_width" in params:
+            p.scoring_width = int(params["scoring_width"])
+        if width_key is not None and width_key in params:   # point_width override, pyx:293,361,465
+            p.scoring_width = int(params[width_key])
+        seq = sequence.encode("ascii") if isinstance(sequence, str) else bytes(sequence)
+        self.handle = L.ps_region_create(ctx.handle, seq, len(seq), C.byref(p))
+        if not self.handle:
+            raise RuntimeError("ps_region_create failed: %s" % L.ps_last_error(ctx.handle).decode())
+        self.n_levels = []
+        for ev in events:
+            if hasattr(ev, "makecontiguous"):
+                ev.makecontiguous()
+            mean, stdv, ra, rl = _f8(ev.mean), _f8(ev.stdv), _f8(ev.ref_align), _f8(ev.ref_like)
+            m = ev.model
+            lm, ls, sm, ss = _f8(m.level_mean), _f8(m.level_stdv), _f8(m.sd_mean), _f8(m.sd_stdv)
+            if not (len(stdv) == len(ra) == len(rl) == len(mean)) or min(len(lm), len(ls), len(sm), len(ss)) < 1024:
+                raise ValueError("event arrays must have equal length and models 1024 states")
+            seq2d = getattr(ev, "sequence", "") or ""
+            ctx.check(L.ps_region_add_event(self.handle, len(mean), _dp(mean), _dp(stdv), _dp(ra), _dp(rl),
+                                            _dp(lm), _dp(ls), _dp(sm), _dp(ss), int(bool(m.complement)),
+                                            float(m.prob_skip), float(m.prob_stay), float(m.prob_extend),
+                                            float(m.prob_insert), seq2d.encode("ascii")))
+            self.n_levels.append(len(mean))
+
+    def close(self):
+        if self.handle:
+            self.ctx.lib.ps_region_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sequence(self):
+        n = self.ctx.lib.ps_region_sequence_length(self.handle)
+        buf = C.create_string_buffer(n + 1)
+        self.ctx.check(self.ctx.lib.ps_region_get_sequence(self.handle, buf, n + 1))
+        return buf.value.decode("ascii")
+
+    def event_align(self, e):
+        ra = np.zeros(self.n_levels[e])
+        rl = np.zeros(self.n_levels[e])
+        self.ctx.check(self.ctx.lib.ps_region_get_event_align(self.handle, e, _dp(ra), _dp(rl)))
+        return ra, rl
+
+    def write_back(self, events):
+        """UpdatePythonEvents (pyx:131-137): in-place ref_align / ref_like."""
+        for e, ev in enumerate(events):
+            ra, rl = self.event_align(e)
+            ev.ref_align[:] = ra
+            ev.ref_like[:] = rl
+
+    # -- compute ---------------------------------------------------------------------------
+    def score_alignments(self, want_likes=False):
+        n = len(self.n_levels)
+        scores = np.zeros(n)
+        likes = np.zeros(self.ctx.lib.ps_region_sequence_length(self.handle)) if want_likes else None
+        self.ctx.check(self.ctx.lib.ps_score_alignments(self.handle, _dp(scores), _dp(likes) if want_likes else None))
+        return scores, likes
+
+    def score_mutations(self, starts, origs, muts):
+        n = len(starts)
+        st = np.ascontiguousarray(starts, dtype=np.int32)
+        scores = np.zeros(n)
+        self.ctx.check(self.ctx.lib.ps_score_mutations(self.handle, n, st.ctypes.data_as(_c_int_p), _cstrs(origs),
+                                                       _cstrs(muts), _dp(scores)))
+        return scores
+
+    def score_points(self):
+        cap = 8 * max(self.ctx.lib.ps_region_sequence_length(self.handle), 1)
+        n = C.c_int(0)
+        st = np.zeros(cap, dtype=np.int32)
+        og = C.create_string_buffer(cap)
+        mu = C.create_string_buffer(cap)
+        sc = np.zeros(cap)
+        self.ctx.check(self.ctx.lib.ps_score_points(self.handle, cap, C.byref(n), st.ctypes.data_as(_c_int_p), og, mu, _dp(sc)))
+        k = n.value
+        return st[:k], og.raw[:k], mu.raw[:k], sc[:k]
+
+    def make_mutations(self, starts, origs, muts, scores):
+        n = len(starts)
+        st = np.ascontiguousarray(starts, dtype=np.int32)
+        sc = np.ascontiguousarray(scores, dtype="f8")
+        nb = C.c_int(0)
+        self.ctx.check(self.ctx.lib.ps_make_mutations(self.handle, n, st.ctypes.data_as(_c_int_p), _cstrs(origs),
+                                                      _cstrs(muts), _dp(sc), C.byref(nb)))
+        return nb.value
+
+    def refine(self):
+        nb = C.c_int(0)
+        self.ctx.check(self.ctx.lib.ps_refine(self.handle, C.byref(nb)))
+        return nb.value
+
+
+def score_points_batch(ctx, regions):
+    """ps_score_points_batch over NativeRegion objects: one launch sequence for all of them.
+    Returns a list of (start, orig bytes, mut bytes, score) tuples of arrays, one per region."""
+    n = len(regions)
+    handles = (C.c_void_p * n)(*[r.handle for r in regions])
+    cap = sum(8 * max(ctx.lib.ps_region_sequence_length(r.handle), 1) for r in regions)
+    n_out = (C.c_int * n)()
+    off = (C.c_longlong * n)()
+    st = np.zeros(cap, dtype=np.int32)
+    og = C.create_string_buffer(cap)
+    mu = C.create_string_buffer(cap)
+    sc = np.zeros(cap)
+    ctx.check(ctx.lib.ps_score_points_batch(handles, n, cap, n_out, off, st.ctypes.data_as(_c_int_p), og, mu, _dp(sc)))
+    out = []
+    for k in range(n):
+        a, b = off[k], off[k] + n_out[k]
+        out.append((st[a:b], og.raw[a:b], mu.raw[a:b], sc[a:b]))
+    return out
+
+
+def _score_objects(starts, origs, muts, scores):
+    out = []
+    for s, o, m, sc in zip(starts, origs, muts, scores):
+        ms = MutationScore()
+        ms.start = int(s)
+        ms.orig = o
+        ms.mut = m
+        ms.score = float(sc)
+        out.append(ms)
+    return out
+
+
+def _ch(b):
+    return "" if b == 0 else chr(b)
+
+
+def seqtostates(seq):
+    """5-mer states [0,1023] of a nucleotide sequence (pyx:176-187, cpp/Sequence.h:69-100)."""
+    s = seq.encode("ascii") if isinstance(seq, str) else bytes(seq)
+    out = np.zeros(max(len(s), 1), dtype=np.int32)
+    n = lib().ps_seq_to_states(s, len(s), out.ctypes.data_as(_c_int_p))
+    return out[:max(n, 0)].tolist()
+
+
+class PSAlign(object):
+    """All data associated with reads aligned to a reference (pyx:189-472).
+
+    Attributes: sequence (str), events (list of PSEvent-like), params (dict)."""
+
+    def __init__(self):
+        self.sequence = ""
+        self.events = []
+        self.params = {}
+
+    # -- plumbing --------------------------------------------------------------------------
+    def _native(self, width_key=None):
+        return NativeRegion(default_context(), self.sequence, self.events, self.params, width_key)
+
+    def Copy(self):
+        return copy.deepcopy(self)
+
+    def Coverage(self):
+        """Depth of coverage across the reference (pyx:233-247)."""
+        cov = np.zeros(len(self.sequence))
+        for ev in self.events:
+            nzs = ev.ref_align[ev.ref_align > 0]
+            if len(nzs) == 0:
+                continue
+            lo = int(nzs[0])
+            hi = int(np.minimum(nzs[-1], len(cov) - 1))
+            cov[lo:hi] += 1
+        return cov
+
+    # -- scoring ---------------------------------------------------------------------------
+    def ScoreEvents(self):
+        """Likelihood score of every event (pyx:263-276).  Like the reference, the realignment is
+        not propagated back to the Python events."""
+        reg = self._native()
+        try:
+            scores, _ = reg.score_alignments()
+        finally:
+            reg.close()
+        return scores.tolist()
+
+    def ScorePoints(self):
+        """Scores of all single-base mutations, at point_width (pyx:278-308)."""
+        reg = self._native("point_width")
+        try:
+            st, og, mu, sc = reg.score_points()
+        finally:
+            reg.close()
+        return _score_objects(st, [_ch(b) for b in og], [_ch(b) for b in mu], sc)
+
+    def ScoreMutations(self, muts):
+        """Scores of the given MutationInfo list, at scoring_width (pyx:310-345)."""
+        reg = self._native()
+        try:
+            starts = [int(m.start) for m in muts]
+            origs = [m.orig for m in muts]
+            mutss = [m.mut for m in muts]
+            sc = reg.score_mutations(starts, origs, mutss)
+        finally:
+            reg.close()
+        return _score_objects(starts, origs, mutss, sc)
+
+    def ApplyMuts(self, pymuts):
+        """MakeMutations on an already scored list, at point_width (pyx:347-375)."""
+        reg = self._native("point_width")
+        try:
+            reg.make_mutations([int(m.start) for m in pymuts], [m.orig for m in pymuts],
+                               [m.mut for m in pymuts], [float(m.score) for m in pymuts])
+            self.sequence = reg.sequence()
+            reg.write_back(self.events)
+        finally:
+            reg.close()
+
+    def Refine(self):
+        """Test all single-base mutations and make the improving ones (pyx:437-472)."""
+        reg = self._native("point_width")
+        try:
+            nbases = reg.refine()
+            self.sequence = reg.sequence()
+            reg.write_back(self.events)
+        finally:
+            reg.close()
+        return nbases

@@ -1,0 +1,111 @@
+"""CUDA path vs the CPU checkers, through the C-ABI.  Bit-exact: the FP64 kernels evaluate the
+reference's recurrence in the reference's order (no FMA), so scores, accepted mutations, final
+sequences and per-level alignments must all be identical, not merely within 1e-4."""
+import numpy as np
+import pytest
+
+from poreseq_b200 import poreseqcpp, synth
+from util import CASES, edge_mutations, region, same_aligns
+
+pytestmark = pytest.mark.gpu
+
+
+def native(ctx, reg, width_key=None):
+    return poreseqcpp.NativeRegion(ctx, reg.sequence, reg.events, reg.params, width_key)
+
+
+def native_aligns(nr, reg):
+    return [nr.event_align(e) for e in range(len(reg.events))]
+
+
+@pytest.mark.parametrize("name", [c[0] for c in CASES])
+def test_score_alignments(ctx, orc, name):
+    reg = region(name)
+    want_s, want_l, want_a = orc.score_alignments(reg, True)
+    nr = native(ctx, reg)
+    got_s, got_l = nr.score_alignments(True)
+    assert np.array_equal(got_s, want_s)
+    assert np.array_equal(got_l, want_l)
+    assert same_aligns(native_aligns(nr, reg), want_a)
+
+
+@pytest.mark.parametrize("name", [c[0] for c in CASES])
+def test_score_points(ctx, orc, name):
+    reg = region(name)
+    want, want_a = orc.score_points(reg)
+    nr = native(ctx, reg, "point_width")
+    st, og, mu, sc = nr.score_points()
+    assert len(st) == len(want)
+    assert [int(s) for s in st] == [w[0] for w in want]
+    assert [chr(b) if b else "" for b in og] == [w[1] for w in want]
+    assert [chr(b) if b else "" for b in mu] == [w[2] for w in want]
+    assert np.array_equal(sc, np.array([w[3] for w in want]))
+    assert same_aligns(native_aligns(nr, reg), want_a)
+
+
+@pytest.mark.parametrize("name", [c[0] for c in CASES])
+def test_score_mutations_edges(ctx, orc, name):
+    reg = region(name)
+    st, og, mu = edge_mutations(reg.sequence, 11)
+    want, want_a = orc.score_mutations(reg, st, og, mu)
+    nr = native(ctx, reg)
+    got = nr.score_mutations(st, og, mu)
+    bad = np.nonzero(got != want)[0]
+    assert len(bad) == 0, [(int(i), st[i], og[i], mu[i], got[i], want[i]) for i in bad[:8]]
+    assert same_aligns(native_aligns(nr, reg), want_a)
+
+
+@pytest.mark.parametrize("name", [c[0] for c in CASES])
+def test_refine(ctx, orc, name):
+    reg = region(name)
+    want_seq, want_nb, want_a = orc.refine(reg)
+    nr = native(ctx, reg, "point_width")
+    nb = nr.refine()
+    assert nb == want_nb
+    assert nr.sequence() == want_seq
+    assert same_aligns(native_aligns(nr, reg), want_a)
+
+
+def test_psalign_surface(ctx, orc):
+    """The PSAlign mirror: same call sequence a poreseq driver makes (Variant.py:48-78, Mutate.py:76-85)."""
+    reg = region("draft_partial")
+    pa = poreseqcpp.PSAlign()
+    pa.sequence, pa.events, pa.params = reg.sequence, [e.copy() for e in reg.events], dict(reg.params)
+    scores = pa.ScoreEvents()
+    assert np.array_equal(np.array(scores), orc.score_alignments(reg)[0])
+    pts = pa.ScorePoints()
+    want, _ = orc.score_points(reg)
+    assert [(p.start, p.orig, p.mut, p.score) for p in pts] == want
+    nb = pa.Refine()
+    want_seq, want_nb, want_a = orc.refine(reg)
+    assert (nb, pa.sequence) == (want_nb, want_seq)
+    assert same_aligns([(e.ref_align, e.ref_like) for e in pa.events], want_a)
+
+
+def test_batch_matches_single(ctx, orc):
+    regs = [region("clean"), region("draft_partial"), region("ragged")]
+    nrs = [native(ctx, r, "point_width") for r in regs]
+    out = poreseqcpp.score_points_batch(ctx, nrs)
+    for r, (st, og, mu, sc) in zip(regs, out):
+        want, _ = orc.score_points(r)
+        assert np.array_equal(sc, np.array([w[3] for w in want]))
+
+
+def test_unusable_and_invalid_bases(ctx, orc):
+    reg = region("clean")
+    reg.events[1].ref_align[:] = 0            # no alignment -> event unusable (cpp/Alignment.cpp:51-59)
+    seq = list(reg.sequence)
+    seq[50] = "N"; seq[51] = "N"; seq[200] = "-"
+    reg.sequence = "".join(seq)
+    want_s, _, want_a = orc.score_alignments(reg)
+    nr = native(ctx, reg)
+    got_s, _ = nr.score_alignments()
+    assert np.array_equal(got_s, want_s)
+    st, og, mu = edge_mutations(reg.sequence, 5, count=150)
+    st += [48, 49, 50, 51, 52, 196, 199, 200]; og += ["", "A", "N", "N", "", "", "", "-"]; mu += ["A", "", "C", "", "G", "T", "A", "A"]
+    want, want_a = orc.score_mutations(reg, st, og, mu)
+    nr = native(ctx, reg)
+    got = nr.score_mutations(st, og, mu)
+    bad = np.nonzero(got != want)[0]
+    assert len(bad) == 0, [(int(i), st[i], og[i], mu[i], got[i], want[i]) for i in bad[:8]]
+    assert same_aligns(native_aligns(nr, reg), want_a)

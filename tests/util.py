@@ -1,0 +1,36 @@
+"""Shared helpers for the parity tests."""
+import numpy as np
+
+from poreseq_b200 import synth
+
+SMALL = dict(realign_width=60, scoring_width=15, point_width=8)
+
+# (name, kwargs for synth.make_region) -- small enough for the CPU checkers to finish in seconds
+CASES = [
+    ("clean", dict(length=400, coverage=4, seed=1, params=SMALL)),
+    ("draft_partial", dict(length=400, coverage=4, seed=2, draft_error=0.03, partial=0.3, params=SMALL)),
+    ("ragged", dict(length=400, coverage=4, seed=3, draft_error=0.05, partial=0.5, p_unaligned=0.3, jitter=3, params=SMALL)),
+    ("default_widths", dict(length=700, coverage=3, seed=4, draft_error=0.02)),
+]
+
+
+def region(name):
+    return synth.make_region(**dict(CASES)[name])
+
+
+def edge_mutations(seq, seed, count=200, max_len=5):
+    """Random multi-base edits plus the boundary cases of cpp/MakeMutations.cpp:46 and
+    cpp/Sequence.h:41-46 (start at / past the end, long deletions at 0, empty regions)."""
+    rng = np.random.default_rng(seed)
+    st, og, mu = synth.random_mutations(seq, count, rng, max_len)
+    L = len(seq)
+    extra = [(L, "", "A"), (L - 1, seq[-1:], ""), (L + 1, "", "C"), (0, "", "ACGTACGT"), (0, seq[:5], ""),
+             (L + 7, "", "G"), (L - 4, seq[-4:], ""), (L - 5, seq[-5:-2], "TT"), (1, seq[1:2], "GGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGG"),
+             (3, seq[3:30], ""), (L - 2, "", "ACGT"), (2, "", "N"), (5, seq[5:6], "N")]
+    for s, o, m in extra:
+        st.append(s); og.append(o); mu.append(m)
+    return st, og, mu
+
+
+def same_aligns(a, b):
+    return all(np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1]) for x, y in zip(a, b))
