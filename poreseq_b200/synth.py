@@ -8,7 +8,7 @@ a ``sequence`` string, ``makecontiguous()``, ``mapaligns(pairs)`` and a ``model`
 ``level_mean, level_stdv, sd_mean, sd_stdv`` plus ``prob_skip/stay/extend/insert`` and ``complement``.
 That is exactly what the boundary marshals (poreseq/_poreseqcpp.pyx:99-129).
 
-Nothing here touches the GPU or the oracle; it is pure numpy.
+Pure numpy: no GPU and no native code involved.
 """
 import copy
 

@@ -1,0 +1,71 @@
+"""CPU tests of the product's host side: the C-ABI library loads and exports every symbol the
+header declares, host-only helpers match the checker, and compute calls fail loudly without a GPU
+(no silent CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from poreseq_b200 import build, poreseqcpp, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def native_lib():
+    build.build()
+    return ctypes.CDLL(build.LIB)
+
+
+def test_every_declared_symbol_is_exported(native_lib):
+    header = open(os.path.join(ROOT, "include", "poreseq_b200.h")).read()
+    names = set(re.findall(r"\b(ps_[a-z0-9_]+)\s*\(", header))
+    assert len(names) >= 20
+    missing = [n for n in sorted(names) if not hasattr(native_lib, n)]
+    assert not missing, missing
+
+
+def test_seq_to_states_matches_checker(orc):
+    rng = np.random.default_rng(3)
+    for seq in [synth.random_sequence(50, rng), "ACGTACGTNACGTACGGTNNACGTTGCA", "NACGT", "ACGT", "ACG-TACGTAC"]:
+        assert poreseqcpp.seqtostates(seq) == orc.seq_to_states(seq).tolist()
+
+
+def test_point_mutation_enumeration_is_host_only(orc):
+    """FindPointMutations order (cpp/FindMutations.cpp:191-234) without touching the GPU."""
+    reg = synth.make_region(60, 1, seed=9)
+    c = poreseqcpp.Context(0)
+    nr = poreseqcpp.NativeRegion(c, reg.sequence, reg.events, reg.params)
+    cap = 8 * len(reg.sequence)
+    n = ctypes.c_int(0)
+    st = np.zeros(cap, dtype=np.int32)
+    og = ctypes.create_string_buffer(cap)
+    mu = ctypes.create_string_buffer(cap)
+    c.check(c.lib.ps_find_point_mutations(nr.handle, cap, ctypes.byref(n), st.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), og, mu))
+    s2, o2, m2 = synth.point_mutations(reg.sequence)
+    assert n.value == len(s2) == 8 * (len(reg.sequence) - 4)
+    assert st[:n.value].tolist() == s2
+    assert [chr(b) if b else "" for b in og.raw[:n.value]] == o2
+    assert [chr(b) if b else "" for b in mu.raw[:n.value]] == m2
+
+
+def test_compute_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    reg = synth.make_region(60, 1, seed=9)
+    pa = poreseqcpp.PSAlign()
+    pa.sequence, pa.events, pa.params = reg.sequence, reg.events, reg.params
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pa.ScoreEvents()
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under poreseq_b200/ may mention it."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "poreseq_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower(), os.path.join(dirpath, f)

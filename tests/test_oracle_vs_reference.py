@@ -1,0 +1,54 @@
+"""CPU tests (-m "not gpu"): the restatement in oracle/ps_oracle.cpp is pinned against
+(a) the committed fixtures generated from the reference's own C++ (tests/golden/*.npz) and
+(b) the compiled reference itself (oracle/_ref/libps_ref.so) where it is available."""
+import glob
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+from make_golden import aligns_array, unpack_region  # noqa: E402
+from util import CASES, edge_mutations, region, same_aligns  # noqa: E402
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_restatement_matches_golden(orc, path):
+    z = np.load(path)
+    reg = unpack_region(z)
+    s, l, a = orc.score_alignments(reg, True)
+    assert np.array_equal(s, z["sa_scores"]) and np.array_equal(l, z["sa_likes"])
+    assert np.array_equal(aligns_array(a), z["sa_aligns"])
+    pts, a = orc.score_points(reg)
+    assert np.array_equal(np.array([p[3] for p in pts]), z["sp_scores"])
+    assert np.array_equal(aligns_array(a), z["sp_aligns"])
+    sm, _ = orc.score_mutations(reg, z["sm_start"].tolist(), z["sm_orig"].tolist(), z["sm_mut"].tolist())
+    assert np.array_equal(sm, z["sm_scores"])
+    seq, nb, a = orc.refine(reg)
+    assert seq == str(z["rf_seq"]) and nb == int(z["rf_nbases"])
+    assert np.array_equal(aligns_array(a), z["rf_aligns"])
+
+
+@pytest.mark.parametrize("name", [c[0] for c in CASES[:3]])
+def test_restatement_matches_reference(orc, ref, name):
+    reg = region(name)
+    s1, l1, a1 = ref.score_alignments(reg, True)
+    s2, l2, a2 = orc.score_alignments(reg, True)
+    assert np.array_equal(s1, s2) and np.array_equal(l1, l2) and same_aligns(a1, a2)
+    p1, a1 = ref.score_points(reg)
+    p2, a2 = orc.score_points(reg)
+    assert p1 == p2 and same_aligns(a1, a2)
+    st, og, mu = edge_mutations(reg.sequence, 11)
+    m1, a1 = ref.score_mutations(reg, st, og, mu)
+    m2, a2 = orc.score_mutations(reg, st, og, mu)
+    assert np.array_equal(m1, m2) and same_aligns(a1, a2)
+    r1, r2 = ref.refine(reg), orc.refine(reg)
+    assert r1[0] == r2[0] and r1[1] == r2[1] and same_aligns(r1[2], r2[2])
+
+
+def test_states_with_invalid_bases(orc, ref):
+    for seq in ["ACGTACGTNACGTACGGTNNACGTTGCA", "NACGT", "ACGT", "ACGTN", "ACG-TACGTAC", "TTTTTTTTTT"]:
+        assert orc.seq_to_states(seq).tolist() == ref.seq_to_states(seq).tolist()
