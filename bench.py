@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py -- the hot-path benchmark (BASELINE.json metric: FindMutations / ScoreMutations GCUPS).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--regions R] [--impl reference]
+
+Workload (BASELINE.json configs[1]): the full single-base sub/ins/del scan (`PSAlign.ScorePoints` =
+FindPointMutations + ScoreMutations, point_width 20, realign_width 300) of 1 kb regions at 10x
+coverage (20 events of ~940 levels each, synthetic 5-mer pore model, injected skips/stays).  One
+"step" is one pass of that scan over a batch of R independent regions per GPU, submitted through the
+C-ABI in one call; with N GPUs every rank scans its own R regions (weak scaling, no data-path
+collective: regions are independent).
+
+Reported numbers
+  value       GCUPS with inputs resident in HBM: algorithmic DP cells (wide fill both
+              directions + (|mut|+5) x band rows per (mutation, event) pair) / device time of the kernel
+              sequence, CUDA events on the library's stream, max over ranks
+  e2e         same metric through the public API with HOST buffers: region marshalling, H2D, kernels,
+              D2H all inside the timed region (wall clock bracketed by barrier + synchronize)
+  roofline    dominant kernel against the FP32-issue roofline SURVEY.md 8d defines
+              (24 lane-ops per cell, peak = SMs x 128 lanes x measured SM clock), plus HBM GB/s
+  cpu_baseline  the reference's own C++ (oracle/_ref) on one host core, one region, same run
+
+`--impl reference` times the reference's CPU implementation on all host cores (one process per
+region, the reference's own scaling model, README.md:48-54).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from poreseq_b200 import synth  # noqa: E402
+
+METRIC = "FindMutations GCUPS (ScorePoints full single-base scan)"
+UNIT = "GCUPS"
+OPS_PER_CELL = 24            # 8 emission + 8 add + 8 max lane-ops per cell
+REGION_LEN, COVERAGE = 1000, 10
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p.get("hbm_gbs", 6650.0)), float(p.get("sm_max_mhz", 1965.0)), "measured"
+    return 6650.0, 1965.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        mhz = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def make_regions(count, seed0):
+    return [synth.make_region(REGION_LEN, COVERAGE, seed=seed0 + i) for i in range(count)]
+
+
+def region_bytes(reg):
+    """Host bytes marshalled per region: 4 level arrays + 4x1024 model doubles + 4 probs per event + bases."""
+    return sum(4 * 8 * len(ev.mean) + 4 * 1024 * 8 + 4 * 8 for ev in reg.events) + len(reg.sequence)
+
+
+def algorithmic_cells(reg):
+    """SURVEY.md 8d cell count for ScorePoints on one region (same formula the library reports)."""
+    rw, w = int(reg.params["realign_width"]), int(reg.params["point_width"])
+    n_states = len(reg.sequence) - 4
+    wide = 0.0
+    for ev in reg.events:
+        n0 = len(ev.mean)
+        idx = np.asarray(ev.ref_align)          # generator emits a dense monotone seed alignment
+        mid = np.clip(np.searchsorted(idx, np.arange(1, n_states + 1), side="left"), 1, n0)
+        wide += float(np.sum(np.minimum(n0, mid + rw) - np.maximum(1, mid - rw) + 1))
+    narrow = 0.0
+    for ev in reg.events:
+        rows = min(len(ev.mean), 2 * w + 1)
+        narrow += n_states * (5 + 3 * 6 + 4 * 6) * rows
+    return 2 * wide, narrow
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_score_points_worker(args):
+    which, seed = args
+    from oracle import binding
+    chk = binding.load(which)
+    reg = synth.make_region(REGION_LEN, COVERAGE, seed=seed)
+    t0 = time.perf_counter()
+    chk.score_points(reg)
+    return time.perf_counter() - t0
+
+
+def cpu_checker_kind():
+    from oracle import binding
+    if binding.available("ref"):
+        return "ref", "reference"
+    binding.build("oracle")
+    return "oracle", "port"
+
+
+def run_cpu_baseline():
+    """One region on one host core, timed beside the GPU run (rank 0, N=1 only)."""
+    which, kind = cpu_checker_kind()
+    reg = synth.make_region(REGION_LEN, COVERAGE, seed=1)
+    wide, narrow = algorithmic_cells(reg)
+    dt = cpu_score_points_worker((which, 1))
+    return {"value": (wide + narrow) / dt / 1e9, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": "ScorePoints on 1 of the step's 1 kb x 10x regions (%.0f M cells, %.1f s)" % ((wide + narrow) / 1e6, dt)}
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the reference CPU path on all host cores, one process per region."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    which, kind = cpu_checker_kind()
+    cores = max(1, min(os.cpu_count() or 1, 64))
+    reg = synth.make_region(REGION_LEN, COVERAGE, seed=1)
+    wide, narrow = algorithmic_cells(reg)
+    cells_per_region = wide + narrow
+    with mp.get_context("spawn").Pool(cores) as pool:
+        for w in range(args.warmup_ref):
+            pool.map(cpu_score_points_worker, [(which, 1000 + i) for i in range(cores)])
+        t0 = time.perf_counter()
+        for k in range(args.steps_ref):
+            pool.map(cpu_score_points_worker, [(which, 2000 + k * cores + i) for i in range(cores)])
+        dt = time.perf_counter() - t0
+    value = cells_per_region * cores * args.steps_ref / dt / 1e9
+    sample = "%d regions of 1 kb x 10x per step, one process per region on %d host cores" % (cores, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps_ref, "warmup": args.warmup_ref, "ms_per_step": dt / args.steps_ref * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "ScorePoints 1 kb region x 10x coverage, point_width 20, realign_width 300",
+                       "regions_per_step": cores},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--regions", type=int, default=16, help="1 kb regions per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        # bounded: each step is `cores` regions (~5 s); cap the step count so the run ends in minutes
+        args.steps_ref = max(1, min(args.steps, 6))
+        args.warmup_ref = max(0, min(args.warmup, 1))
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from poreseq_b200 import build, poreseqcpp
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the scoring path has no CPU fallback")
+    build.build()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    ctx = poreseqcpp.Context(local_rank)
+    regions = make_regions(args.regions, seed0=1 + rank * args.regions)
+    cells = [algorithmic_cells(r) for r in regions]
+    wide_cells = sum(c[0] for c in cells)
+    narrow_cells = sum(c[1] for c in cells)
+    step_cells = wide_cells + narrow_cells
+    h2d = sum(region_bytes(r) for r in regions)
+
+    def step():
+        nrs = [poreseqcpp.NativeRegion(ctx, r.sequence, r.events, r.params, "point_width") for r in regions]
+        out = poreseqcpp.score_points_batch(ctx, nrs)
+        for nr in nrs:
+            nr.close()
+        return out
+
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    d2h = sum(8 * len(o[3]) for o in out) + sum(2 * 8 * len(ev.mean) for r in regions for ev in r.events)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    phase = {}
+    launches0 = ctx.launch_count()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+        for k, v in ctx.last_timing().items():
+            phase[k] = phase.get(k, 0.0) + v
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = ctx.launch_count() - launches0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    kernel_keys = ["centres", "forward", "backward", "backtrace", "join", "mutscore", "reduce"]
+    dev_ms = sum(phase[k] for k in kernel_keys) / args.steps
+    wall_ms = wall / args.steps * 1e3
+    times = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms, wall_ms = times.tolist()
+    total_cells = step_cells * world
+
+    hbm_peak, sm_max_mhz, peak_src = measured_peaks()
+    clocks = sampler.summary()
+    props = torch.cuda.get_device_properties(local_rank)
+    sms = props.multi_processor_count
+    # dominant kernel: whichever phase took longest; its algorithmic cells / its own CUDA-event time
+    phase_ms = {k: phase[k] / args.steps for k in kernel_keys}
+    dom = max(phase_ms, key=phase_ms.get)
+    dom_cells = {"forward": wide_cells, "mutscore": narrow_cells}.get(dom, 0.0)
+    clock_hz = (clocks["sm_mhz"] or sm_max_mhz) * 1e6
+    peak_ops = sms * 128 * sm_max_mhz * 1e6 / 1e12                  # T lane-ops/s at max clock
+    achieved_ops = dom_cells * OPS_PER_CELL / (phase_ms[dom] * 1e-3) / 1e12 if phase_ms[dom] > 0 else 0.0
+    # algorithmic bytes of the dominant kernel: wide fill writes 2 matrices x 8 B + 1 step byte
+    # per cell (forward) / 16 B (reverse); the mutation kernel reads 8 B seed + 16 B join rows per band row
+    dom_bytes = {"forward": wide_cells * 16.5, "mutscore": narrow_cells / 5.875 * 24.0}.get(dom, 0.0)
+    line = {
+        "metric": METRIC, "value": total_cells / (dev_ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": wall_ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "ScorePoints (FindPointMutations+ScoreMutations) on 1 kb regions x 10x coverage, "
+                               "point_width 20, realign_width 300",
+                   "regions_per_gpu_per_step": args.regions, "events_per_region": 2 * COVERAGE,
+                   "mutations_per_region": 8 * (REGION_LEN - 4), "cells_per_step_per_gpu": step_cells,
+                   "l2": "band working set %.0f MB per step exceeds the 126 MB L2" % (wide_cells * 16.5 / 1e6),
+                   "precision": "fp64 exact (bit-identical to the reference)"},
+        "e2e": {"value": total_cells / (wall_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "phase_ms": phase_ms,
+        "roofline": {"bound": "fp32-issue", "kernel": {"forward": "k_fill", "mutscore": "k_mutscore"}.get(dom, dom),
+                     "achieved": achieved_ops, "peak": peak_ops, "unit": "Tlane-op/s", "frac": achieved_ops / peak_ops,
+                     "ops_per_cell": OPS_PER_CELL, "clock_mhz_under_load": clock_hz / 1e6, "peak_source": peak_src,
+                     "traffic": None},
+        "roofline_hbm": {"bound": "hbm", "achieved": dom_bytes / (phase_ms[dom] * 1e-3) / 1e9 if phase_ms[dom] > 0 else 0.0,
+                         "peak": hbm_peak, "unit": "GB/s", "frac": dom_bytes / (phase_ms[dom] * 1e-3) / 1e9 / hbm_peak if phase_ms[dom] > 0 else 0.0,
+                         "peak_source": peak_src},
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = run_cpu_baseline()
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
