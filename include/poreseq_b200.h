@@ -124,9 +124,27 @@ int         ps_score_points_batch(ps_region* const* regions, int n_regions, int 
                                   int* n_out, long long* off_out,
                                   int* start, char* orig, char* mut, double* scores);
 
+/* ---- candidate discovery and the consensus iteration ------------------------------------------- */
+/* vector<MutInfo> FindMutations(AlignData&, const vector<Sequence>&)   cpp/Mutations.h:18,
+ * cpp/FindMutations.cpp:24-186.  The result is held by the region; fetch entry i with
+ * ps_get_found_mutation (sizes first with ps_found_mutation_sizes). */
+int         ps_find_mutations(ps_region* r, int n_seeds, const char* const* seeds, int* n_found);
+int         ps_found_mutation_sizes(ps_region* r, int i, int* n_orig, int* n_mut);
+int         ps_get_found_mutation(ps_region* r, int i, int* start, char* orig, int orig_cap, char* mut, int mut_cap);
+/* Loop body of PSAlign.Mutate (poreseq/_poreseqcpp.pyx:424-431): reps x (FindMutations,
+ * ScoreMutations, MakeMutations), stopping when a round changes nothing. */
+int         ps_mutate(ps_region* r, int n_seeds, const char* const* seeds, int reps, int* totbases);
+/* SWAlignment MapAlignments(AlignData&, const Sequence&)   cpp/EventUtil.h:17, cpp/EventUtil.cpp:12-55:
+ * swfull + fillinds, then every level's ref_align is carried over to newseq. */
+int         ps_map_alignments(ps_region* r, const char* newseq);
+
 /* ---- helpers that stay on the host ---------------------------------------------------------- */
 /* Sequence::populateStates (cpp/Sequence.h:69-100); returns the number of states written. */
 int         ps_seq_to_states(const char* seq, int len, int* states);
+/* SWAlignment swfull(const string&, const string&)   cpp/swlib.h:36, cpp/swlib.cpp:211-340.
+ * Aligned index pairs (1-based, 0 = gap) into inds1/inds2 (cap entries), count in *n. */
+int         ps_swfull(const char* seq1, const char* seq2, int* inds1, int* inds2, int cap,
+                      int* n, int* score, double* accuracy);
 
 #ifdef __cplusplus
 }

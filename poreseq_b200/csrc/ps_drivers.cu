@@ -1,0 +1,298 @@
+// ps_drivers.cu -- host drivers around the kernels: integer Smith-Waterman (swfull), alignment
+// re-mapping (MapAlignments), seed-based candidate discovery (FindMutations) and the
+// Find/Score/Make iteration of PSAlign.Mutate.  All DP over events runs on the GPU through
+// ps_run_job(); what stays here is sequential glue the reference also runs on one core.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ps_internal.h"
+
+#define TRY(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
+
+// ------------------------------------------------------------------------------------------
+// swfull: full-matrix local alignment, +5 match / -4 mismatch / -8 gap (cpp/swlib.h:21-23,
+// cpp/swlib.cpp:211-340).  Tie rules: left and up must beat the running best strictly, the
+// diagonal wins ties; the best cell is the first maximum in (column of seq2, row of seq1) order.
+// Only one byte per cell is kept: the move (0..3) plus a flag for "score is zero", which is all the
+// traceback ever asks of the score matrix; scores themselves roll over two columns.
+SWResult psi_swfull(const std::string& s1, const std::string& s2)
+{
+    const int n1 = (int)s1.size(), n2 = (int)s2.size();
+    const size_t stride = (size_t)n1 + 1;
+    std::vector<uint8_t> move(stride * ((size_t)n2 + 1), 0);
+    std::vector<int> prev(stride, 0), cur(stride, 0);
+    int best = 0, bi = 0, bj = 0;
+    for (int j = 1; j <= n2; j++)
+    {
+        uint8_t* mv = move.data() + (size_t)j * stride;
+        const char cj = s2[j - 1];
+        cur[0] = 0;
+        for (int i = 1; i <= n1; i++)
+        {
+            int sc = 0, m = 0;
+            int v = prev[i] - 8;
+            if (v > sc) { sc = v; m = 1; }
+            v = cur[i - 1] - 8;
+            if (v > sc) { sc = v; m = 2; }
+            v = prev[i - 1] + (s1[i - 1] == cj ? 5 : -4);
+            if (v >= sc) { sc = v; m = 3; }
+            cur[i] = sc;
+            mv[i] = (uint8_t)(m | (sc <= 0 ? 4 : 0));
+            if (sc > best) { best = sc; bi = i; bj = j; }
+        }
+        prev.swap(cur);
+    }
+    SWResult r;
+    r.score = best;
+    int i = bi, j = bj, nmatch = 0;
+    while (i > 0 && j > 0)
+    {
+        const uint8_t mv = move[(size_t)j * stride + i];
+        if (mv & 4) break;
+        const int m = mv & 3;
+        if (m == 1) { r.inds1.push_back(0); r.inds2.push_back(j); j--; }
+        else if (m == 2) { r.inds1.push_back(i); r.inds2.push_back(0); i--; }
+        else if (m == 3)
+        {
+            r.inds1.push_back(i); r.inds2.push_back(j);
+            if (s1[i - 1] == s2[j - 1]) nmatch++;
+            i--; j--;
+        }
+        else break;      // cannot happen for a positive score
+    }
+    std::reverse(r.inds1.begin(), r.inds1.end());
+    std::reverse(r.inds2.begin(), r.inds2.end());
+    r.accuracy = 100.0 * nmatch / (double)r.inds1.size();
+    return r;
+}
+
+// fillinds (cpp/swlib.cpp:342-365): gaps take the previous aligned index of their own sequence
+void psi_fillinds(SWResult& al)
+{
+    if (al.inds1.empty()) return;
+    int a = al.inds1[0], b = al.inds2[0];
+    for (size_t k = 0; k < al.inds1.size(); k++)
+    {
+        if (al.inds1[k] > 0) a = al.inds1[k]; else al.inds1[k] = a;
+        if (al.inds2[k] > 0) b = al.inds2[k]; else al.inds2[k] = b;
+    }
+}
+
+// MapAlignments (cpp/EventUtil.cpp:12-55): realign the region to `newseq` by integer SW and carry
+// every level's ref_align across: value v -> inds2[lower_bound(inds1, v)], 0 outside the aligned span.
+SWResult psi_map_alignments(ps_region* R, const std::string& newseq)
+{
+    SWResult al = psi_swfull(R->bases, newseq);
+    psi_fillinds(al);
+    R->set_sequence(newseq);
+    const std::vector<int>& a = al.inds1;
+    const std::vector<int>& b = al.inds2;
+    for (HostEvent& ev : R->events)
+    {
+        for (int j = 0; j < ev.n0; j++)
+        {
+            const int v = (int)ev.ref_align[j];
+            if (a.empty() || v < a.front() || v > a.back()) { ev.ref_align[j] = 0; continue; }
+            const size_t at = std::lower_bound(a.begin(), a.end(), v) - a.begin();
+            ev.ref_align[j] = at < b.size() ? b[at] : 0;
+        }
+        ev.update_refs();
+    }
+    return al;
+}
+
+// ------------------------------------------------------------------------------------------
+// FindMutations (cpp/FindMutations.cpp:24-186).  The S seed realignments (S x E wide forward
+// fills + backtraces) that dominate it are submitted as ONE batched GPU job: every distinct,
+// not-yet-cached seed becomes a shadow region (copy of the events, alignments mapped through SW).
+int ps_find_mutation_list(ps_region* R, const std::vector<std::string>& seeds, std::vector<HostMut>& found)
+{
+    found.clear();
+    ps_ctx* ctx = R->ctx;
+    const size_t L = R->bases.size();
+    // 1. realign to the current sequence, keep its per-base likelihood profile
+    std::vector<double> base(L, 0.0);
+    {
+        std::vector<ps_region*> one(1, R);
+        std::vector<std::vector<double>> likes;
+        TRY(ps_run_alignments(ctx, one, nullptr, &likes));
+        base = likes[0];
+    }
+    // 2. per seed: SW map, likelihood profile (cached by seed string for the life of the region)
+    const size_t S = seeds.size();
+    std::vector<SWResult> als(S);
+    std::vector<ps_region*> shadows;
+    std::vector<std::string> shadow_key;
+    for (size_t s = 0; s < S; s++)
+    {
+        ps_region* nd = new ps_region(*R);
+        nd->seqlikes.clear();
+        als[s] = psi_map_alignments(nd, seeds[s]);
+        const bool cached = R->seqlikes.count(seeds[s]) && !R->seqlikes[seeds[s]].empty();
+        const bool queued = std::find(shadow_key.begin(), shadow_key.end(), seeds[s]) != shadow_key.end();
+        if (!cached && !queued && seeds[s].size() >= 5) { shadows.push_back(nd); shadow_key.push_back(seeds[s]); }
+        else delete nd;
+    }
+    if (!shadows.empty())
+    {
+        std::vector<std::vector<double>> likes;
+        int rc = ps_run_alignments(ctx, shadows, nullptr, &likes);
+        for (size_t k = 0; k < shadows.size(); k++)
+        {
+            if (!rc) R->seqlikes[shadow_key[k]] = likes[k];
+            delete shadows[k];
+        }
+        if (rc) return rc;
+    }
+    // 3. CUSUM of the profile difference along each SW alignment (:51-94)
+    std::vector<std::vector<double>> dl(S);
+    for (size_t s = 0; s < S; s++)
+    {
+        std::vector<double>& prof = R->seqlikes[seeds[s]];
+        if (prof.empty()) prof.assign(seeds[s].size(), 0.0);
+        std::vector<int>& i1 = als[s].inds1;
+        std::vector<int>& i2 = als[s].inds2;
+        for (size_t j = 0; j < i1.size(); j++) { i1[j] -= 2; i2[j] -= 2; }
+        size_t drop = 0;
+        while (drop < i1.size() && (i1[drop] < 0 || i2[drop] < 0)) drop++;
+        i1.erase(i1.begin(), i1.begin() + drop);
+        i2.erase(i2.begin(), i2.begin() + drop);
+        const size_t n = i1.size();
+        std::vector<double> a1(n), a2(n);
+        for (size_t j = 0; j < n; j++) { a1[j] = base[i1[j]]; a2[j] = prof[i2[j]]; }
+        for (size_t j = n; j-- > 1;) { a1[j] -= a1[j - 1]; a2[j] -= a2[j - 1]; }
+        if (n) { a1[0] = 0; a2[0] = 0; }
+        dl[s].resize(n);
+        double cus = 0;
+        for (size_t j = 0; j < n; j++)
+        {
+            cus += a2[j] - a1[j];
+            if (cus < 0) cus = 0;
+            dl[s][j] = std::fabs(a1[j] - a2[j]) < 1e-5 ? 0.0 : cus;
+        }
+    }
+    // 4. greedy peak picking (:111-183)
+    while (found.size() < L / 3)
+    {
+        int smax = -1, ind = 0;
+        double vmax = 0;
+        for (size_t s = 0; s < S; s++)
+        {
+            if (dl[s].empty()) continue;
+            const size_t at = std::max_element(dl[s].begin(), dl[s].end()) - dl[s].begin();
+            if (smax < 0 || dl[s][at] > vmax) { smax = (int)s; ind = (int)at; vmax = dl[s][at]; }
+        }
+        if (smax < 0 || vmax < 0.25) break;
+        std::vector<double>& d = dl[smax];
+        const int n = (int)d.size();
+        int i1 = ind;
+        while (i1 < n && d[i1] != 0) i1++;
+        int i0 = ind;
+        while (i0 >= 0 && d[i0] != 0) i0--;
+        if (i0 < 0) i0 = 0;
+        if (i1 >= n) i1 = n - 1;
+        const int start1 = als[smax].inds1[i0], start2 = als[smax].inds2[i0];
+        const int end1 = als[smax].inds1[ind], end2 = als[smax].inds2[ind];
+        HostMut m;
+        m.start = start1;
+        m.orig = R->bases.substr(start1, end1 - start1);
+        m.mut = seeds[smax].substr(start2, end2 - start2);
+        while (!m.orig.empty() && !m.mut.empty() && m.orig.front() == m.mut.front())
+        {
+            m.orig.erase(0, 1); m.mut.erase(0, 1); m.start++;
+        }
+        while (!m.orig.empty() && !m.mut.empty() && m.orig.back() == m.mut.back())
+        {
+            m.orig.pop_back(); m.mut.pop_back();
+        }
+        if (!m.orig.empty() || !m.mut.empty()) found.push_back(m);
+        std::fill(d.begin() + i0, d.begin() + i1 + 1, 0.0);
+    }
+    return PS_OK;
+}
+
+// PSAlign.Mutate loop body (poreseq/_poreseqcpp.pyx:424-431)
+int ps_mutate_loop(ps_region* R, const std::vector<std::string>& seeds, int reps, int* totbases)
+{
+    int total = 0;
+    for (int rep = 0; rep < reps; rep++)
+    {
+        std::vector<HostMut> cand;
+        TRY(ps_find_mutation_list(R, seeds, cand));
+        TRY(ps_score_mutation_list(R, cand));
+        int nb = 0;
+        TRY(ps_make_mutation_list(R, cand, &nb));
+        if (nb == 0) break;
+        total += nb;
+    }
+    *totbases = total;
+    return PS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int ps_swfull(const char* seq1, const char* seq2, int* inds1, int* inds2, int cap, int* n, int* score, double* accuracy)
+{
+    if (!seq1 || !seq2) return PS_E_ARG;
+    SWResult r = psi_swfull(std::string(seq1), std::string(seq2));
+    if (n) *n = (int)r.inds1.size();
+    if (score) *score = r.score;
+    if (accuracy) *accuracy = r.accuracy;
+    if ((int)r.inds1.size() > cap) return PS_E_CAPACITY;
+    for (size_t k = 0; k < r.inds1.size(); k++) { if (inds1) inds1[k] = r.inds1[k]; if (inds2) inds2[k] = r.inds2[k]; }
+    return PS_OK;
+}
+
+int ps_map_alignments(ps_region* R, const char* newseq)
+{
+    if (!R || !newseq) return PS_E_ARG;
+    psi_map_alignments(R, std::string(newseq));
+    return PS_OK;
+}
+
+int ps_find_mutations(ps_region* R, int n_seeds, const char* const* seeds, int* n_found)
+{
+    if (!R || n_seeds < 0 || (n_seeds > 0 && !seeds)) return PS_E_ARG;
+    std::vector<std::string> sv(n_seeds);
+    for (int i = 0; i < n_seeds; i++) sv[i] = seeds[i] ? seeds[i] : "";
+    TRY(ps_find_mutation_list(R, sv, R->found));
+    if (n_found) *n_found = (int)R->found.size();
+    return PS_OK;
+}
+
+int ps_get_found_mutation(ps_region* R, int i, int* start, char* orig, int orig_cap, char* mut, int mut_cap)
+{
+    if (!R || i < 0 || i >= (int)R->found.size()) return PS_E_ARG;
+    const HostMut& m = R->found[i];
+    if ((int)m.orig.size() + 1 > orig_cap || (int)m.mut.size() + 1 > mut_cap) return PS_E_CAPACITY;
+    if (start) *start = m.start;
+    memcpy(orig, m.orig.c_str(), m.orig.size() + 1);
+    memcpy(mut, m.mut.c_str(), m.mut.size() + 1);
+    return PS_OK;
+}
+
+int ps_found_mutation_sizes(ps_region* R, int i, int* n_orig, int* n_mut)
+{
+    if (!R || i < 0 || i >= (int)R->found.size()) return PS_E_ARG;
+    if (n_orig) *n_orig = (int)R->found[i].orig.size();
+    if (n_mut) *n_mut = (int)R->found[i].mut.size();
+    return PS_OK;
+}
+
+int ps_mutate(ps_region* R, int n_seeds, const char* const* seeds, int reps, int* totbases)
+{
+    if (!R || n_seeds < 0 || (n_seeds > 0 && !seeds)) return PS_E_ARG;
+    std::vector<std::string> sv(n_seeds);
+    for (int i = 0; i < n_seeds; i++) sv[i] = seeds[i] ? seeds[i] : "";
+    int tot = 0;
+    TRY(ps_mutate_loop(R, sv, reps, &tot));
+    if (totbases) *totbases = tot;
+    return PS_OK;
+}
+
+} // extern "C"

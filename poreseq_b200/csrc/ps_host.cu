@@ -598,6 +598,41 @@ static int run_job(ps_ctx* ctx, std::vector<ps_region*> regs, std::vector<std::v
     return PS_OK;
 }
 
+int ps_run_alignments(ps_ctx* ctx, const std::vector<ps_region*>& regs,
+                      std::vector<std::vector<double>>* scores, std::vector<std::vector<double>>* likes)
+{
+    std::vector<double> flat;
+    TRY(run_job(ctx, regs, nullptr, &flat, nullptr));
+    size_t e = 0;
+    if (scores) scores->assign(regs.size(), std::vector<double>());
+    if (likes) likes->assign(regs.size(), std::vector<double>());
+    for (size_t r = 0; r < regs.size(); r++)
+    {
+        const ps_region* R = regs[r];
+        if (scores) (*scores)[r].assign(flat.begin() + e, flat.begin() + e + R->events.size());
+        e += R->events.size();
+        if (!likes) continue;
+        // per-base likelihood profile, cpp/MakeMutations.cpp:168-189 (events in order)
+        std::vector<double>& lk = (*likes)[r];
+        lk.assign(R->bases.size(), 0.0);
+        const int N = (int)R->states.size();
+        for (const HostEvent& he : R->events)
+        {
+            double carried = 0;
+            int at = 1;
+            for (int j = 0; j < he.n0; j++)
+                if (he.ref_align[j] > 0)
+                {
+                    for (int k = at; k < he.ref_align[j]; k++) lk[k + 1] += carried;
+                    carried = he.ref_like[j];
+                    at = (int)he.ref_align[j];
+                }
+            for (int k = at; k < N + 3; k++) lk[k + 1] += carried;
+        }
+    }
+    return PS_OK;
+}
+
 std::vector<HostMut> ps_point_mutations(const ps_region* R)      // cpp/FindMutations.cpp:191-234
 {
     static const char acgt[] = "ACGT";
@@ -789,27 +824,10 @@ int ps_region_get_event_align(ps_region* R, int e, double* ref_align, double* re
 int ps_score_alignments(ps_region* R, double* scores, double* likes)
 {
     if (!R || !scores) return PS_E_ARG;
-    std::vector<double> sc;
-    TRY(run_job(R->ctx, std::vector<ps_region*>(1, R), nullptr, &sc, nullptr));
-    std::copy(sc.begin(), sc.end(), scores);
-    if (likes)
-    {
-        // per-base likelihood profile, cpp/MakeMutations.cpp:168-189 (events in order)
-        const int N = (int)R->states.size();
-        for (const HostEvent& he : R->events)
-        {
-            double carried = 0;
-            int at = 1;
-            for (int j = 0; j < he.n0; j++)
-                if (he.ref_align[j] > 0)
-                {
-                    for (int k = at; k < he.ref_align[j]; k++) likes[k + 1] += carried;
-                    carried = he.ref_like[j];
-                    at = (int)he.ref_align[j];
-                }
-            for (int k = at; k < N + 3; k++) likes[k + 1] += carried;
-        }
-    }
+    std::vector<std::vector<double>> sc, lk;
+    TRY(ps_run_alignments(R->ctx, std::vector<ps_region*>(1, R), &sc, likes ? &lk : nullptr));
+    std::copy(sc[0].begin(), sc[0].end(), scores);
+    if (likes) for (size_t k = 0; k < lk[0].size(); k++) likes[k] += lk[0][k];
     return PS_OK;
 }
 

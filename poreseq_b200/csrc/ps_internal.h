@@ -62,6 +62,8 @@ struct ps_region                              // cpp/AlignData.h:24-34
     std::vector<HostModel> models;
     ps_params params;
     std::map<std::string, std::vector<double>> seqlikes;   // FindMutations cache (cpp/AlignData.h:34)
+    std::vector<HostMut> found;                            // result of the last ps_find_mutations
+    std::vector<std::string> viterbi;                      // result of the last ps_viterbi_mutate
     void set_sequence(const std::string& s);
 };
 
@@ -71,3 +73,20 @@ std::string ps_apply_mutation(const std::string& bases, int start, const std::st
 std::vector<HostMut> ps_point_mutations(const ps_region* R);
 int ps_score_mutation_list(ps_region* R, std::vector<HostMut>& muts);
 int ps_make_mutation_list(ps_region* R, std::vector<HostMut> muts, int* nbases);
+
+struct SWResult                               // cpp/swlib.h:25-33
+{
+    int score = 0;
+    double accuracy = 0;
+    std::vector<int> inds1, inds2;
+};
+
+SWResult psi_swfull(const std::string& s1, const std::string& s2);
+void psi_fillinds(SWResult& al);
+SWResult psi_map_alignments(ps_region* R, const std::string& newseq);
+// forward fill + backtrace of every event of every region (ScoreAlignments); per-region score
+// vectors and per-base likelihood profiles on request
+int ps_run_alignments(ps_ctx* ctx, const std::vector<ps_region*>& regs,
+                      std::vector<std::vector<double>>* scores, std::vector<std::vector<double>>* likes);
+int ps_find_mutation_list(ps_region* R, const std::vector<std::string>& seeds, std::vector<HostMut>& found);
+int ps_mutate_loop(ps_region* R, const std::vector<std::string>& seeds, int reps, int* totbases);

@@ -69,6 +69,12 @@ def lib():
     L.ps_make_mutations.argtypes = [C.c_void_p, C.c_int, _c_int_p, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), _c_double_p, _c_int_p]
     L.ps_refine.argtypes = [C.c_void_p, _c_int_p]
     L.ps_seq_to_states.argtypes = [C.c_char_p, C.c_int, _c_int_p]
+    L.ps_swfull.argtypes = [C.c_char_p, C.c_char_p, _c_int_p, _c_int_p, C.c_int, _c_int_p, _c_int_p, _c_double_p]
+    L.ps_map_alignments.argtypes = [C.c_void_p, C.c_char_p]
+    L.ps_find_mutations.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), _c_int_p]
+    L.ps_found_mutation_sizes.argtypes = [C.c_void_p, C.c_int, _c_int_p, _c_int_p]
+    L.ps_get_found_mutation.argtypes = [C.c_void_p, C.c_int, _c_int_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+    L.ps_mutate.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.c_int, _c_int_p]
     _lib = L
     return L
 
@@ -247,6 +253,26 @@ class NativeRegion(object):
         self.ctx.check(self.ctx.lib.ps_refine(self.handle, C.byref(nb)))
         return nb.value
 
+    def map_alignments(self, newseq):
+        self.ctx.check(self.ctx.lib.ps_map_alignments(self.handle, newseq.encode("ascii")))
+
+    def find_mutations(self, seeds):
+        n = C.c_int(0)
+        self.ctx.check(self.ctx.lib.ps_find_mutations(self.handle, len(seeds), _cstrs(seeds), C.byref(n)))
+        out = []
+        for i in range(n.value):
+            no, nm, st = C.c_int(0), C.c_int(0), C.c_int(0)
+            self.ctx.check(self.ctx.lib.ps_found_mutation_sizes(self.handle, i, C.byref(no), C.byref(nm)))
+            ob, mb = C.create_string_buffer(no.value + 1), C.create_string_buffer(nm.value + 1)
+            self.ctx.check(self.ctx.lib.ps_get_found_mutation(self.handle, i, C.byref(st), ob, no.value + 1, mb, nm.value + 1))
+            out.append((st.value, ob.value.decode("ascii"), mb.value.decode("ascii")))
+        return out
+
+    def mutate(self, seeds, reps=4):
+        tot = C.c_int(0)
+        self.ctx.check(self.ctx.lib.ps_mutate(self.handle, len(seeds), _cstrs(seeds), int(reps), C.byref(tot)))
+        return tot.value
+
 
 def score_points_batch(ctx, regions):
     """ps_score_points_batch over NativeRegion objects: one launch sequence for all of them.
@@ -282,6 +308,22 @@ def _score_objects(starts, origs, muts, scores):
 
 def _ch(b):
     return "" if b == 0 else chr(b)
+
+
+def swalign(seq1, seq2):
+    """Smith-Waterman align two sequences (pyx:155-174, cpp/swlib.cpp:211-340).
+
+    Returns (accuracy in %, list of pairwise aligned 1-based indices, 0 = gap)."""
+    a = seq1.encode("ascii") if isinstance(seq1, str) else bytes(seq1)
+    b = seq2.encode("ascii") if isinstance(seq2, str) else bytes(seq2)
+    cap = len(a) + len(b) + 8
+    i1 = np.zeros(cap, dtype=np.int32)
+    i2 = np.zeros(cap, dtype=np.int32)
+    n, score, acc = C.c_int(0), C.c_int(0), C.c_double(0)
+    rc = lib().ps_swfull(a, b, i1.ctypes.data_as(_c_int_p), i2.ctypes.data_as(_c_int_p), cap, C.byref(n), C.byref(score), C.byref(acc))
+    if rc != 0:
+        raise RuntimeError("ps_swfull failed (%d)" % rc)
+    return (acc.value, list(zip(i1[:n.value].tolist(), i2[:n.value].tolist())))
 
 
 def seqtostates(seq):
@@ -320,6 +362,15 @@ class PSAlign(object):
             hi = int(np.minimum(nzs[-1], len(cov) - 1))
             cov[lo:hi] += 1
         return cov
+
+    def RealignTo(self, newseq):
+        """Realign all events to a new reference sequence using swalign (pyx:249-261)."""
+        align = swalign(self.sequence, newseq)
+        if align[0] < 0.6:
+            raise Exception('Error rate too large for realignment!')
+        for ev in self.events:
+            ev.mapaligns(np.array(align[1]))
+        self.sequence = newseq
 
     # -- scoring ---------------------------------------------------------------------------
     def ScoreEvents(self):
@@ -363,6 +414,25 @@ class PSAlign(object):
             reg.write_back(self.events)
         finally:
             reg.close()
+
+    def Mutate(self, seqs='self', reps=4):
+        """Use similar sequences as seeds to mutate the consensus (pyx:378-435).
+
+        seqs: 'self' (2D sequences of every other event), 'viterbi', or a list of sequences."""
+        reg = self._native()
+        try:
+            if isinstance(seqs, str) and seqs == 'self':
+                seeds = [ev.sequence for ev in self.events[::2]]
+            elif isinstance(seqs, str) and seqs == 'viterbi':
+                seeds = reg.viterbi_mutate(16, 0.05, 0.01, 0.33, 0.75)
+            else:
+                seeds = list(seqs)
+            tot = reg.mutate(seeds, reps)
+            self.sequence = reg.sequence()
+            reg.write_back(self.events)
+        finally:
+            reg.close()
+        return tot
 
     def Refine(self):
         """Test all single-base mutations and make the improving ones (pyx:437-472)."""

@@ -109,3 +109,38 @@ def test_unusable_and_invalid_bases(ctx, orc):
     bad = np.nonzero(got != want)[0]
     assert len(bad) == 0, [(int(i), st[i], og[i], mu[i], got[i], want[i]) for i in bad[:8]]
     assert same_aligns(native_aligns(nr, reg), want_a)
+
+
+@pytest.mark.parametrize("name", ["draft_partial", "ragged"])
+def test_find_mutations(ctx, ref, name):
+    """Seed-based candidate discovery (cpp/FindMutations.cpp:24-186): same candidates, same order."""
+    reg = region(name)
+    seeds = [ev.sequence for ev in reg.events[::2]]
+    want, want_a = ref.find_mutations(reg, seeds)
+    nr = native(ctx, reg)
+    got = nr.find_mutations(seeds)
+    assert got == want
+    assert same_aligns(native_aligns(nr, reg), want_a)
+
+
+@pytest.mark.parametrize("name", ["draft_partial", "ragged"])
+def test_mutate_self(ctx, ref, name):
+    """PSAlign.Mutate('self') loop: reps x (FindMutations, ScoreMutations, MakeMutations)."""
+    reg = region(name)
+    seeds = [ev.sequence for ev in reg.events[::2]]
+    want_seq, want_nb, want_a = ref.mutate(reg, seeds, reps=4)
+    pa = poreseqcpp.PSAlign()
+    pa.sequence, pa.events, pa.params = reg.sequence, [e.copy() for e in reg.events], dict(reg.params)
+    nb = pa.Mutate(reps=4)
+    assert (nb, pa.sequence) == (want_nb, want_seq)
+    assert same_aligns([(e.ref_align, e.ref_like) for e in pa.events], want_a)
+
+
+def test_map_alignments_and_realign(ctx, ref):
+    reg = region("draft_partial")
+    rng = np.random.default_rng(3)
+    newseq, _ = synth.corrupt_sequence(reg.sequence, 0.08, rng)
+    want_a = ref.map_alignments(reg, newseq)
+    nr = native(ctx, reg)
+    nr.map_alignments(newseq)
+    assert same_aligns(native_aligns(nr, reg), want_a)

@@ -69,3 +69,21 @@ def test_product_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.lower(), os.path.join(dirpath, f)
+
+
+def test_swalign_matches_reference(ref):
+    """Host-side integer Smith-Waterman (cpp/swlib.cpp:211-340): pairs, accuracy, tie-breaking."""
+    rng = np.random.default_rng(5)
+    for n, rate in [(1, 0.0), (8, 0.3), (60, 0.2), (300, 0.15), (700, 0.4), (500, 0.02)]:
+        a = synth.random_sequence(n, rng)
+        b, _ = synth.corrupt_sequence(a, rate, rng)
+        if not b:
+            b = "A"
+        acc, pairs = poreseqcpp.swalign(a, b)
+        want_acc, _, want_pairs = ref.swfull(a, b)
+        assert pairs == want_pairs
+        assert acc == want_acc or (np.isnan(acc) and np.isnan(want_acc))
+    # low-complexity sequences exercise the tie rules
+    acc, pairs = poreseqcpp.swalign("AAAAAAAAAACCCCCCCCCC", "AAAAACCCCCCCCCCCCAAAAA")
+    want_acc, _, want_pairs = ref.swfull("AAAAAAAAAACCCCCCCCCC", "AAAAACCCCCCCCCCCCAAAAA")
+    assert pairs == want_pairs and acc == want_acc
