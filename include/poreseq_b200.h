@@ -134,6 +134,14 @@ int         ps_get_found_mutation(ps_region* r, int i, int* start, char* orig, i
 /* Loop body of PSAlign.Mutate (poreseq/_poreseqcpp.pyx:424-431): reps x (FindMutations,
  * ScoreMutations, MakeMutations), stopping when a round changes nothing. */
 int         ps_mutate(ps_region* r, int n_seeds, const char* const* seeds, int reps, int* totbases);
+/* vector<Sequence> ViterbiMutate(vector<EventData>&, int nkeep, double skip, double stay,
+ * double mut_min, double mut_max, bool verbose)   cpp/Viterbi.h:67-68, cpp/Viterbi.cpp:239-426.
+ * nkeep == 0: the best path; otherwise nkeep forward-weighted samples drawn with libc rand()
+ * (never seeded by the reference; call srand() first for a reproducible stream).  The sequences
+ * are held by the region; ps_get_viterbi_sequence(r, i, NULL, 0) returns the length of entry i. */
+int         ps_viterbi_mutate(ps_region* r, int nkeep, double skip_prob, double stay_prob,
+                              double mut_min, double mut_max, int* n_seqs);
+int         ps_get_viterbi_sequence(ps_region* r, int i, char* out, int cap);
 /* SWAlignment MapAlignments(AlignData&, const Sequence&)   cpp/EventUtil.h:17, cpp/EventUtil.cpp:12-55:
  * swfull + fillinds, then every level's ref_align is carried over to newseq. */
 int         ps_map_alignments(ps_region* r, const char* newseq);

@@ -16,26 +16,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "ps_types.cuh"
+
 namespace psdev {
-
-constexpr int    N_STATES = 1024;
-constexpr double NEG      = -1e300;       // cpp/AlignUtil.h:20 ("inf" is 1e300)
-
-// packed step byte written by the forward fill: low 3 bits main-matrix move, bits 3-4 stay-matrix move
-// main : 0 skip, 1 match, 2 insert, 3 ignore, 4 stay, 6 implicit (cpp/Alignment.cpp:19-28), 7 = score <= 0
-// stay : 0 = score <= 0, 1 = stay, 2 = extend
-constexpr int ST_SKIP = 0, ST_MATCH = 1, ST_INSERT = 2, ST_IGNORE = 3, ST_STAY = 4, ST_IMPLICIT = 6, ST_STOP = 7;
-
-struct StateParams            // one 64-byte record per 5-mer state (cpp/EventData.h:21-45)
-{
-    double lev_mean, lev_stdv, log_lev, sd_mean, sd_lambda, log_lambda, pad0, pad1;
-};
-
-struct ModelDev               // cpp/EventData.h:21-74
-{
-    StateParams st[N_STATES];
-    double lskip, lstay, lext, lins;
-};
 
 struct EvDesc                 // one event of one region in the batch
 {

@@ -173,7 +173,7 @@ void HostEvent::update_refs()                                // cpp/EventData.h:
     }
 }
 
-static void build_model(const HostModel& hm, ModelDev& md)     // cpp/EventData.h:48-73
+void ps_build_model(const HostModel& hm, ModelDev& md)     // cpp/EventData.h:48-73
 {
     for (int s = 0; s < N_STATES; s++)
     {
@@ -352,7 +352,7 @@ int Job::upload()
     b.n_tasks = n_tasks;
 
     std::vector<ModelDev> models(model_src.size());
-    for (size_t q = 0; q < model_src.size(); q++) build_model(*model_src[q], models[q]);
+    for (size_t q = 0; q < model_src.size(); q++) ps_build_model(*model_src[q], models[q]);
 
     EvDesc* d_ev; ModelDev* d_models; int* d_states; char* d_bases;
     double *d_mean, *d_stdv, *d_lsd;

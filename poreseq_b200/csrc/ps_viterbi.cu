@@ -1,0 +1,444 @@
+// ps_viterbi.cu -- ViterbiMutate (cpp/Viterbi.cpp:239-426): per reference position, pooled
+// trimmed-mean emissions over the reads, a 1024-state Viterbi + normalised forward step with
+// 1/2/3-base advances and stays, then the best path or `nkeep` forward-weighted random back-samples,
+// turned back into sequences.
+//
+// Split of work:
+//   host   which levels of which read sit on each position (getrefstates, cpp/EventData.h:187-204),
+//          their mean level / stdv and log(stdv) (libm), the skip/stop rule (:310-325), the glibc
+//          rand() stream (:108), StatesToSequence (:171-237)
+//   K8     k_vit_obs      1024 x n_reads pdfs per position, per-state sort + trimmed mean (:300-343)
+//   K7     k_vit_chain    one 1024-thread CTA walks the positions: max-plus (Viterbi, first maximum
+//                         wins) and sum-product (forward) over 84 predecessors + stay from shared
+//                         memory, x exp(obs), normalise (:39-102)
+//          k_vit_sample   one CTA per sample: T-row x fwd^atten, normalise, inverse CDF (:105-131)
+//
+// Exactness: emissions, the sort/trimmed mean and the Viterbi recursion are IEEE double in the
+// reference's order, so liks / backptrs (hence the nkeep=0 path) are bit-identical.  The forward
+// probabilities use the device exp() and a tree sum, the sampler the device pow(): they differ from
+// glibc in the last ulps, which can move an inverse-CDF boundary by ~1e-16 -- a sampled state flips
+// with probability ~1e-13 per draw.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "ps_internal.h"
+#include "ps_types.cuh"
+
+using namespace psdev;
+
+#define TRY(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t err__ = (call);                                                               \
+        if (err__ != cudaSuccess)                                                                 \
+        {                                                                                         \
+            ps_set_error(ctx, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(err__), __FILE__, \
+                         __LINE__, #call);                                                        \
+            return PS_E_CUDA;                                                                     \
+        }                                                                                         \
+    } while (0)
+
+struct VitSlot { int model; int pad; double lvl, sd, logsd; };   // one read on one position
+
+// ------------------------------------------------------------------------------------------
+// K8: obs[t][state] = trimmed mean over the reads on position t of lognormpdf + logigpdf
+// (no lik_offset, cpp/Viterbi.cpp:300-306).  One thread per (position, state); its per-read values
+// sit in shared memory (vals[s * blockDim + tid]) for the ascending sort.
+__global__ void k_vit_obs(const ModelDev* models, const VitSlot* slots, const int* slot_off, int n_pos,
+                          double log2pi, double* obs, double* eobs)
+{
+    extern __shared__ double vals[];
+    const int t = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int T = blockDim.x, tid = threadIdx.x;
+    const int s0 = slot_off[t], nlik = slot_off[t + 1] - s0;
+    for (int s = 0; s < nlik; s++)
+    {
+        const VitSlot sl = slots[s0 + s];
+        const StateParams& p = models[sl.model].st[j];
+        double d = (sl.lvl - p.lev_mean) / p.lev_stdv;
+        double l = -0.5 * (d * d + log2pi) - p.log_lev;
+        double g = (sl.sd - p.sd_mean) / p.sd_mean;
+        l += 0.5 * (p.log_lambda - 3 * sl.logsd - log2pi - g * g * p.sd_lambda / sl.sd);
+        vals[s * T + tid] = l;
+    }
+    double o;
+    if (nlik > 1)
+    {
+        for (int a = 1; a < nlik; a++)              // insertion sort, ascending
+        {
+            double v = vals[a * T + tid];
+            int b = a - 1;
+            while (b >= 0 && vals[b * T + tid] > v) { vals[(b + 1) * T + tid] = vals[b * T + tid]; b--; }
+            vals[(b + 1) * T + tid] = v;
+        }
+        int nskip = (int)floor(nlik * 0.25);
+        if (nskip > nlik - 2) nskip = 0;
+        double lik = 0.0;
+        for (int k = nskip; k < nlik; k++) lik += vals[k * T + tid];
+        o = lik / (nlik - nskip);
+    }
+    else o = vals[tid];
+    obs[(size_t)t * N_STATES + j] = o;
+    eobs[(size_t)t * N_STATES + j] = exp(o);
+}
+
+// ------------------------------------------------------------------------------------------
+// K7: the chain.  liks/backptrs exactly as V_LIK::V_LIK; fwd normalised with a tree sum.
+struct VitConst { double lsp[3], sp[3], stay_lik, stay_prob; };
+
+__global__ void __launch_bounds__(1024) k_vit_chain(const double* obs, const double* eobs, int n_pos, VitConst vc,
+                                                     double* fwd, int* backptr, double* last_liks)
+{
+    __shared__ double lk[2][N_STATES];
+    __shared__ double fw[2][N_STATES];
+    __shared__ double red[32];
+    const int d = threadIdx.x, lane = d & 31, wid = d >> 5;
+    lk[0][d] = 0.0;
+    fw[0][d] = 1.0 / N_STATES;
+    __syncthreads();
+    for (int t = 0; t < n_pos; t++)
+    {
+        const double* pl = lk[t & 1];
+        const double* pf = fw[t & 1];
+        const double o = obs[(size_t)t * N_STATES + d];
+        double best = NEG, f = 0.0;
+        int ptr = -1;
+#pragma unroll
+        for (int j = 1; j <= 3; j++)
+        {
+            const double lsp = vc.lsp[j - 1], sp = vc.sp[j - 1];
+            const double base = o + lsp;
+            const int lowbits = d >> (2 * j), shift = 10 - 2 * j;
+#pragma unroll 4
+            for (int k = 0; k < (1 << (2 * j)); k++)
+            {
+                const int p = lowbits + (k << shift);
+                const double l = base + pl[p];
+                f += sp * pf[p];
+                if (l > best) { best = l; ptr = p; }
+            }
+        }
+        {
+            const double l = o + vc.stay_lik + pl[d];
+            if (l > best) { best = l; ptr = d; }
+            f += vc.stay_prob * pf[d];
+        }
+        f *= eobs[(size_t)t * N_STATES + d];
+        // normalise forward probabilities (tree sum over the block)
+        double s = f;
+        for (int o2 = 16; o2; o2 >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2);
+        if (lane == 0) red[wid] = s;
+        __syncthreads();
+        if (wid == 0)
+        {
+            double w = red[lane];
+            for (int o2 = 16; o2; o2 >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o2);
+            if (lane == 0) red[0] = 1.0 / w;
+        }
+        __syncthreads();
+        f *= red[0];
+        lk[(t + 1) & 1][d] = best;
+        fw[(t + 1) & 1][d] = f;
+        fwd[(size_t)t * N_STATES + d] = f;
+        backptr[(size_t)t * N_STATES + d] = ptr;
+        __syncthreads();
+    }
+    last_liks[d] = lk[n_pos & 1][d];
+}
+
+// ------------------------------------------------------------------------------------------
+// Sampler (V_LIK::randbp + buildT): sample k walks back from `startst`; at chain step t the
+// predecessor is drawn from  T[cur][i] * fwd[t][i]^atten  normalised, by inverse CDF on r[k][n-1-t].
+// T[cur][i] = sum over advances j=1..4 of 0.25 * (0.25*skip)^(j-1) for which i is a j-step
+// predecessor of cur, diagonal overwritten by stay (cpp/Viterbi.cpp:134-169).
+__global__ void __launch_bounds__(1024) k_vit_sample(const double* fwd, int n_pos, int startst, const double* rnd,
+                                                      double skip_prob, double stay_prob, double mut_min,
+                                                      double mut_max, int nkeep, int* paths)
+{
+    __shared__ double red[32];
+    __shared__ double scan[32];
+    __shared__ int chosen;
+    const int i = threadIdx.x, lane = i & 31, wid = i >> 5, k = blockIdx.x;
+    const double atten = mut_min + (mut_max - mut_min) * k / (double)nkeep;
+    double spj[4];
+    spj[0] = 0.25;
+    for (int j = 1; j < 4; j++) spj[j] = spj[j - 1] * 0.25 * skip_prob;
+    int cur = startst;
+    for (int t = n_pos - 1; t >= 0; t--)
+    {
+        if (i == 0) { paths[(size_t)k * n_pos + (n_pos - 1 - t)] = cur; chosen = N_STATES - 1; }
+        double w = 0.0;
+#pragma unroll
+        for (int j = 1; j <= 4; j++)
+            if ((i & ((1 << (10 - 2 * j)) - 1)) == (cur >> (2 * j))) w += spj[j - 1];
+        if (i == cur) w = stay_prob;
+        double p = 0.0;
+        if (w != 0.0) p = w * pow(fwd[(size_t)t * N_STATES + i], atten);
+        // total
+        double s = p;
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) red[wid] = s;
+        __syncthreads();
+        if (wid == 0)
+        {
+            double v = red[lane];
+            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) red[0] = 1.0 / v;
+        }
+        __syncthreads();
+        p *= red[0];
+        // inclusive prefix sum
+        double c = p;
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            double v = __shfl_up_sync(0xffffffffu, c, o);
+            if (lane >= o) c += v;
+        }
+        if (lane == 31) scan[wid] = c;
+        __syncthreads();
+        if (wid == 0)
+        {
+            double v = scan[lane];
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                double u = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += u;
+            }
+            scan[lane] = v;
+        }
+        __syncthreads();
+        if (wid > 0) c += scan[wid - 1];
+        const double r = rnd[(size_t)k * n_pos + (n_pos - 1 - t)];
+        // first index whose running sum exceeds r: lowest lane per warp, then lowest warp
+        const unsigned hit = __ballot_sync(0xffffffffu, r < c);
+        if (hit && lane == 0) atomicMin(&chosen, wid * 32 + (__ffs(hit) - 1));
+        __syncthreads();
+        cur = chosen;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+void ps_build_model(const HostModel& hm, ModelDev& md);      // ps_host.cu
+
+static char base_of(int state, int ind) { return "ACGT"[3 & (state >> (2 * (4 - ind)))]; }
+
+// StatesToSequence (cpp/Viterbi.cpp:171-237)
+static std::string states_to_sequence(const std::vector<int>& st)
+{
+    std::string seq;
+    int cur = st[0];
+    seq.push_back(base_of(cur, 0));
+    for (size_t i = 1; i < st.size(); i++)
+    {
+        const int nxt = st[i];
+        if (nxt == cur) continue;                                   // stay
+        bool linked = false;
+        for (int n = 1; n <= 4 && !linked; n++)
+            for (int ind = 0; ind < (1 << (2 * n)); ind++)
+                if ((((cur << (2 * n)) & (N_STATES - 1)) + ind) == nxt)
+                {
+                    for (int j = 1; j <= n; j++) seq.push_back(base_of(cur, j));
+                    cur = nxt;
+                    linked = true;
+                    break;
+                }
+        if (!linked) { cur = nxt; seq.push_back(base_of(cur, 0)); }   // mismatch: jump
+    }
+    for (int j = 1; j <= 4; j++) seq.push_back(base_of(cur, j));
+    return seq;
+}
+
+template <class T>
+static int vroom(ps_ctx* ctx, const char* name, size_t count, T** out)
+{
+    DevBuf& buf = ctx->bufs[name];
+    int rc = ctx->ensure(buf, std::max<size_t>(count, 1) * sizeof(T));
+    if (rc) return rc;
+    *out = (T*)buf.p;
+    return PS_OK;
+}
+
+int ps_viterbi_list(ps_region* R, int nkeep, double skip_prob, double stay_prob, double mut_min, double mut_max,
+                    std::vector<std::string>& out)
+{
+    out.clear();
+    ps_ctx* ctx = R->ctx;
+    TRY(ctx->init());
+    CU(cudaSetDevice(ctx->device));
+    const int E = (int)R->events.size();
+    if (E == 0) { ps_set_error(ctx, "ViterbiMutate needs at least one event"); return PS_E_ARG; }
+    for (const HostEvent& ev : R->events)
+        if (ev.ri_empty)
+        {
+            // the reference dereferences an empty path here (cpp/Viterbi.cpp:262-264, 385-400)
+            ps_set_error(ctx, "ViterbiMutate needs every event to carry an alignment");
+            return PS_E_ARG;
+        }
+    // ---- host: which reads sit on which position -------------------------------------------
+    int refind = R->events[0].refstart;
+    int maxref = 0;
+    for (const HostEvent& ev : R->events) { refind = std::min(refind, ev.refstart); maxref = std::max(maxref, ev.refend); }
+    // first level whose ref_index equals a given integer exactly (std::find in getrefstates)
+    std::vector<std::vector<int>> first(E);
+    for (int k = 0; k < E; k++)
+    {
+        const HostEvent& ev = R->events[k];
+        first[k].assign(maxref + 2, -1);
+        for (int i = 0; i < ev.n0; i++)
+        {
+            const double v = ev.ref_index[i];
+            if (v >= 0 && v <= maxref + 1 && v == std::floor(v))
+            {
+                int& slot = first[k][(int)v];
+                if (slot < 0) slot = i;
+            }
+        }
+    }
+    std::vector<VitSlot> slots;
+    std::vector<int> slot_off(1, 0);
+    int max_lik = 1;
+    while (true)
+    {
+        const size_t mark = slots.size();
+        int nlik = 0;
+        if (refind >= 0 && refind <= maxref + 1)
+            for (int k = 0; k < E; k++)
+            {
+                const HostEvent& ev = R->events[k];
+                int f = first[k][refind];
+                if (f < 0) continue;
+                double lvl = ev.mean[f], sd = ev.stdv[f];
+                int cnt = 1;
+                for (int i = f + 1; i < ev.n0 && ev.ref_align[i] <= refind; i++)
+                    if (ev.ref_align[i] > 0) { lvl += ev.mean[i]; sd += ev.stdv[i]; cnt++; }
+                lvl = lvl / cnt;
+                sd = sd / cnt;
+                VitSlot s;
+                s.model = ev.model; s.pad = 0; s.lvl = lvl; s.sd = sd; s.logsd = std::log(sd);
+                slots.push_back(s);
+                nlik++;
+            }
+        int nal = 0;
+        for (const HostEvent& ev : R->events)
+            if (refind >= ev.refstart && refind <= ev.refend) nal++;
+        if (nlik <= nal * 0.2)
+        {
+            slots.resize(mark);
+            if (nal == 0) break;
+            refind++;
+            continue;
+        }
+        slot_off.push_back((int)slots.size());
+        max_lik = std::max(max_lik, nlik);
+        refind++;
+    }
+    const int n_pos = (int)slot_off.size() - 1;
+    if (n_pos == 0) { ps_set_error(ctx, "ViterbiMutate: no position is covered by the events"); return PS_E_ARG; }
+
+    // ---- device ------------------------------------------------------------------------------
+    std::vector<ModelDev> models(R->models.size());
+    for (size_t q = 0; q < models.size(); q++) ps_build_model(R->models[q], models[q]);
+    ModelDev* d_models; VitSlot* d_slots; int* d_off;
+    double *d_obs, *d_eobs, *d_fwd, *d_last, *d_rnd;
+    int *d_bp, *d_paths;
+    TRY(vroom(ctx, "vit_models", models.size(), &d_models));
+    TRY(vroom(ctx, "vit_slots", slots.size(), &d_slots));
+    TRY(vroom(ctx, "vit_off", slot_off.size(), &d_off));
+    TRY(vroom(ctx, "vit_obs", (size_t)n_pos * N_STATES, &d_obs));
+    TRY(vroom(ctx, "vit_eobs", (size_t)n_pos * N_STATES, &d_eobs));
+    TRY(vroom(ctx, "vit_fwd", (size_t)n_pos * N_STATES, &d_fwd));
+    TRY(vroom(ctx, "vit_bp", (size_t)n_pos * N_STATES, &d_bp));
+    TRY(vroom(ctx, "vit_last", (size_t)N_STATES, &d_last));
+    CU(cudaMemcpyAsync(d_models, models.data(), models.size() * sizeof(ModelDev), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_slots, slots.data(), slots.size() * sizeof(VitSlot), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_off, slot_off.data(), slot_off.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    {
+        int threads = 128;
+        while (threads > 32 && (size_t)threads * max_lik * sizeof(double) > 200 * 1024) threads >>= 1;
+        const size_t smem = (size_t)threads * max_lik * sizeof(double);
+        if (smem > 200 * 1024) { ps_set_error(ctx, "ViterbiMutate: %d reads on one position exceed shared memory", max_lik); return PS_E_ARG; }
+        CU(cudaFuncSetAttribute(k_vit_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+        dim3 grid(N_STATES / threads, n_pos);
+        k_vit_obs<<<grid, threads, smem, ctx->stream>>>(d_models, d_slots, d_off, n_pos, std::log(2 * M_PI), d_obs, d_eobs);
+        ctx->launches++;
+        CU(cudaGetLastError());
+    }
+    VitConst vc;
+    {
+        // cpp/Viterbi.cpp:42-44, 57-58, 76-77: sp_1 = .25, sp_{j+1} = sp_j*.25*skip; lsp likewise in logs
+        const double skip_lik = std::log(skip_prob);
+        double sp = 0.25, lsp = std::log(0.25);
+        for (int j = 0; j < 3; j++) { vc.sp[j] = sp; vc.lsp[j] = lsp; sp = sp * 0.25 * skip_prob; lsp = lsp + std::log(0.25) + skip_lik; }
+        vc.stay_lik = std::log(stay_prob);
+        vc.stay_prob = stay_prob;
+    }
+    k_vit_chain<<<1, N_STATES, 0, ctx->stream>>>(d_obs, d_eobs, n_pos, vc, d_fwd, d_bp, d_last);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    std::vector<double> last(N_STATES);
+    CU(cudaMemcpyAsync(last.data(), d_last, N_STATES * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const int startst = (int)(std::max_element(last.begin(), last.end()) - last.begin());
+
+    std::vector<int> path(n_pos);
+    if (nkeep == 0)
+    {
+        std::vector<int> bp((size_t)n_pos * N_STATES);
+        CU(cudaMemcpy(bp.data(), d_bp, bp.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        int cur = startst;
+        for (int t = n_pos - 1; t >= 0; t--) { path[t] = cur; cur = bp[(size_t)t * N_STATES + cur]; }
+        out.push_back(states_to_sequence(path));
+        return PS_OK;
+    }
+    // glibc rand() stream in the reference's call order: sample-major, positions from the end
+    std::vector<double> rnd((size_t)nkeep * n_pos);
+    for (size_t q = 0; q < rnd.size(); q++) rnd[q] = rand() / (double(RAND_MAX) + 1);
+    TRY(vroom(ctx, "vit_rnd", rnd.size(), &d_rnd));
+    TRY(vroom(ctx, "vit_paths", rnd.size(), &d_paths));
+    CU(cudaMemcpyAsync(d_rnd, rnd.data(), rnd.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    k_vit_sample<<<nkeep, N_STATES, 0, ctx->stream>>>(d_fwd, n_pos, startst, d_rnd, skip_prob, stay_prob, mut_min, mut_max, nkeep, d_paths);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    std::vector<int> paths((size_t)nkeep * n_pos);
+    CU(cudaMemcpyAsync(paths.data(), d_paths, paths.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < nkeep; k++)
+    {
+        // paths are stored end-first (as walked); flip to chain order
+        for (int t = 0; t < n_pos; t++) path[t] = paths[(size_t)k * n_pos + (n_pos - 1 - t)];
+        out.push_back(states_to_sequence(path));
+    }
+    return PS_OK;
+}
+
+extern "C" {
+
+int ps_viterbi_mutate(ps_region* R, int nkeep, double skip_prob, double stay_prob, double mut_min, double mut_max, int* n_seqs)
+{
+    if (!R || nkeep < 0) return PS_E_ARG;
+    TRY(ps_viterbi_list(R, nkeep, skip_prob, stay_prob, mut_min, mut_max, R->viterbi));
+    if (n_seqs) *n_seqs = (int)R->viterbi.size();
+    return PS_OK;
+}
+
+int ps_get_viterbi_sequence(ps_region* R, int i, char* out, int cap)
+{
+    if (!R || i < 0 || i >= (int)R->viterbi.size()) return PS_E_ARG;
+    const std::string& s = R->viterbi[i];
+    if (!out) return (int)s.size();
+    if ((int)s.size() + 1 > cap) return PS_E_CAPACITY;
+    memcpy(out, s.c_str(), s.size() + 1);
+    return (int)s.size();
+}
+
+} // extern "C"

@@ -75,6 +75,8 @@ def lib():
     L.ps_found_mutation_sizes.argtypes = [C.c_void_p, C.c_int, _c_int_p, _c_int_p]
     L.ps_get_found_mutation.argtypes = [C.c_void_p, C.c_int, _c_int_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
     L.ps_mutate.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.c_int, _c_int_p]
+    L.ps_viterbi_mutate.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, _c_int_p]
+    L.ps_get_viterbi_sequence.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
     _lib = L
     return L
 
@@ -266,6 +268,17 @@ class NativeRegion(object):
             ob, mb = C.create_string_buffer(no.value + 1), C.create_string_buffer(nm.value + 1)
             self.ctx.check(self.ctx.lib.ps_get_found_mutation(self.handle, i, C.byref(st), ob, no.value + 1, mb, nm.value + 1))
             out.append((st.value, ob.value.decode("ascii"), mb.value.decode("ascii")))
+        return out
+
+    def viterbi_mutate(self, nkeep=16, skip=0.05, stay=0.01, mut_min=0.33, mut_max=0.75):
+        n = C.c_int(0)
+        self.ctx.check(self.ctx.lib.ps_viterbi_mutate(self.handle, int(nkeep), skip, stay, mut_min, mut_max, C.byref(n)))
+        out = []
+        for i in range(n.value):
+            ln = self.ctx.lib.ps_get_viterbi_sequence(self.handle, i, None, 0)
+            buf = C.create_string_buffer(ln + 1)
+            self.ctx.lib.ps_get_viterbi_sequence(self.handle, i, buf, ln + 1)
+            out.append(buf.value.decode("ascii"))
         return out
 
     def mutate(self, seeds, reps=4):

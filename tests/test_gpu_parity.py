@@ -144,3 +144,36 @@ def test_map_alignments_and_realign(ctx, ref):
     nr = native(ctx, reg)
     nr.map_alignments(newseq)
     assert same_aligns(native_aligns(nr, reg), want_a)
+
+
+@pytest.mark.parametrize("name", ["clean", "draft_partial", "ragged"])
+def test_viterbi_best_path(ctx, ref, name):
+    """nkeep=0: Viterbi liks/backptrs are IEEE-exact, so the best-path sequence is identical."""
+    reg = region(name)
+    want = ref.viterbi_mutate(reg, nkeep=0)
+    got = native(ctx, reg).viterbi_mutate(0)
+    assert got == want
+
+
+@pytest.mark.parametrize("name", ["draft_partial", "ragged"])
+def test_viterbi_samples(ctx, ref, name):
+    """nkeep=16 forward-weighted samples on the same libc rand() stream (srand(1) before each side)."""
+    reg = region(name)
+    want = ref.viterbi_mutate(reg, nkeep=16, seed=1)
+    ref.srand(1)
+    got = native(ctx, reg).viterbi_mutate(16)
+    assert len(got) == 16
+    assert got == want
+
+
+def test_mutate_viterbi(ctx, ref):
+    """PSAlign.Mutate('viterbi') = ViterbiMutate seeds + Find/Score/Make loop (pyx:415-431)."""
+    reg = region("draft_partial")
+    seeds = ref.viterbi_mutate(reg, nkeep=16, seed=1)
+    want_seq, want_nb, want_a = ref.mutate(reg, seeds, reps=4)
+    pa = poreseqcpp.PSAlign()
+    pa.sequence, pa.events, pa.params = reg.sequence, [e.copy() for e in reg.events], dict(reg.params)
+    ref.srand(1)
+    nb = pa.Mutate(seqs='viterbi')
+    assert (nb, pa.sequence) == (want_nb, want_seq)
+    assert same_aligns([(e.ref_align, e.ref_like) for e in pa.events], want_a)
