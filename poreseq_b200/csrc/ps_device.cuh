@@ -10,7 +10,8 @@
 //   k_backtrace    K3     best-path pointer chase + updaterefs               (cpp/Alignment.cpp:516-624,
 //                                                                             cpp/EventData.h:110-169)
 //   k_join         K4a    old[e][c] = columnMax(c)                           (cpp/Alignment.h:169-214)
-//   k_mutscore     K4     one thread per (mutation, event): narrow re-fill + join (cpp/Alignment.cpp:447-512)
+//   k_mutscore     K4     one thread per (mutation, event): narrow re-fill + join (cpp/Alignment.cpp:447-512),
+//                         previous column kept in an in-place shared-memory ring
 //   k_reduce       K5     score[m] = -1e-6 + sum over events in event order  (cpp/MakeMutations.cpp:38-52)
 #pragma once
 #include <cuda_runtime.h>
@@ -52,9 +53,7 @@ struct Batch                  // everything the kernels need, passed by value
     const int*        states;
     const char*       bases;
     // per level
-    const double*     mean;
-    const double*     stdv;
-    const double*     log_stdv;
+    const LevelRec*   lev;
     double*           ref_align;
     double*           ref_like;
     double*           ref_index;
@@ -95,17 +94,41 @@ struct Batch                  // everything the kernels need, passed by value
 };
 
 // ------------------------------------------------------------------------------------------
+// Division by a divisor whose correctly rounded reciprocal r = RN(1/b) is already known
+// (per state / per level, computed once with an IEEE division): q0 = a*r followed by two
+// Markstein corrections q <- fma(fma(-q, b, a), r, q).  After the first correction q is within an
+// ulp of a/b, so the second one returns RN(a/b) -- the same bits the reference's `a / b` gives --
+// for 5 FP64 instructions instead of the ~25 of a generic double division.
+__device__ __forceinline__ double div_by(double a, double b, double r)
+{
+    double q = a * r;
+    q = __fma_rn(__fma_rn(-q, b, a), r, q);
+    q = __fma_rn(__fma_rn(-q, b, a), r, q);
+    return q;
+}
+
 // emission: lognormpdf + logigpdf + lik_offset   (cpp/AlignUtil.h:34-53, cpp/Alignment.cpp:169-173)
-// x = level mean, y = level stdv, lsd = log(stdv) of the level the reference indexes (quirk A.3-1)
-__device__ __forceinline__ double emission(double x, double y, double lsd, const StateParams& p,
+// x = level mean, y = level stdv (ry its reciprocal), lsd3 = 3*log(stdv) of the level the
+// reference indexes (quirk A.3-1: the forward pass reads log_stdv[n0-i] beside stdv[i-1])
+__device__ __forceinline__ double emission(double x, double y, double ry, double lsd3, const StateParams& p,
                                            double log2pi, double offset)
 {
-    double d = (x - p.lev_mean) / p.lev_stdv;
+    double d = div_by(x - p.lev_mean, p.lev_stdv, p.r_lev_stdv);
     double l = -0.5 * (d * d + log2pi) - p.log_lev;
-    double g = (y - p.sd_mean) / p.sd_mean;
-    l += 0.5 * (p.log_lambda - 3 * lsd - log2pi - g * g * p.sd_lambda / y);
+    double g = div_by(y - p.sd_mean, p.sd_mean, p.r_sd_mean);
+    l += 0.5 * (p.log_lambda - lsd3 - log2pi - div_by(g * g * p.sd_lambda, y, ry));
     l += offset;
     return l;
+}
+
+// emission of the cell (row i) of a forward (level i-1) or reverse (level n0-i) column
+template <bool REV>
+__device__ __forceinline__ double cell_emission(const LevelRec* lev, int n0, int i, const StateParams& p,
+                                                double log2pi, double offset)
+{
+    const LevelRec a = lev[REV ? n0 - i : i - 1];
+    const double lsd3 = REV ? a.lsd3 : lev[n0 - i].lsd3;
+    return emission(a.mean, a.stdv, a.rstdv, lsd3, p, log2pi, offset);
 }
 
 struct Trans { double lskip, lstay, lext, lins; };
@@ -225,139 +248,235 @@ __device__ __forceinline__ void fill_setup(const Batch& b, const EvDesc& ev, boo
     if (cs.s >= 0) cs.p = b.models[ev.model].st[cs.s];
 }
 
-template <int MAXT>
-__global__ void __launch_bounds__(MAXT) k_fill(Batch b, int dir_base)
+struct FillOut               // where one direction's band columns go
+{
+    double* Mm; double* Ms; int* Mi0; int* Mlen; double* Mcb; int* Mcbi;
+};
+
+// Pipelined wavefront of one (event, direction).
+//
+// The columns (in processing order k = 1..N) are cut into blocks of 32.  A warp owns one block at
+// a time, lane l = column 32j+1+l, and sweeps the rows with a one-row skew between neighbouring
+// lanes: at step t lane l computes row rlo + t - l.  The vertical dependency (k, i-1) stays in the
+// lane's registers; the horizontal ones (k-1, i) and (k-1, i-1) are what lane l-1 produced one and
+// two steps earlier and arrive by __shfl_up.  Lane 0 takes them from the previous block's last
+// column, which the warp that owns block j-1 publishes row by row into a shared-memory strip,
+// guarded by two monotone progress words (rows produced / rows consumed, tagged with the block
+// index) -- no block-wide barrier anywhere in the sweep.  Warp w runs blocks w, w+NW, ..., so up to
+// NW blocks are in flight, each trailing its predecessor by about 32 steps.
+// The emission of the next row is evaluated alongside the recurrence of the current one.
+template <bool REV>
+__device__ __forceinline__ void fill_pipe(const Batch& b, const EvDesc& ev, const FillOut& o, double* smem)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, NW = blockDim.x >> 5;
+    const int n0 = ev.n0, N = ev.N, RS = b.RS, RW = b.realign_width;
+    volatile int* prod = (volatile int*)smem;             // [NW] rows produced, tagged with the block
+    volatile int* cons = prod + NW;                       // [NW] rows consumed
+    double* bndC = smem + NW;                             // [NW][RS] last-column main values
+    double* bndE = bndC + NW * RS;                        // [NW][RS] its emissions (reverse pass only)
+    const LevelRec* lev = b.lev + ev.lev_off;
+    const ModelDev& md = b.models[ev.model];
+    const Trans tr = {md.lskip, md.lstay, md.lext, md.lins};
+    const double off = b.lik_offset, l2p = b.log2pi;
+    const unsigned full = 0xffffffffu;
+    const int nblocks = (N + 31) >> 5;
+    const int wprev = w == 0 ? NW - 1 : w - 1;
+    double* outC = bndC + w * RS;
+    double* outE = bndE + w * RS;
+    const double* inC = bndC + wprev * RS;
+    const double* inE = bndE + wprev * RS;
+    int seen_prod = 0, seen_cons = 0;
+
+    for (int j = w; j < nblocks; j += NW)
+    {
+        const int k = 32 * j + 1 + lane;
+        const bool have = k <= N;
+        const int c = REV ? N - k + 1 : k;
+        int i0 = 1, i1 = 0, s = -1;
+        StateParams p;
+        if (have)
+        {
+            const int cen = b.cen_old[ev.cen_off + c];
+            band_of(REV ? n0 - cen + 1 : cen, n0, RW, i0, i1);
+            s = b.states[ev.state_off + c - 1];
+            if (s >= 0) p = md.st[s];
+        }
+        int p0 = __shfl_up_sync(full, i0, 1), p1 = __shfl_up_sync(full, i1, 1);
+        if (lane == 0)
+        {
+            if (k == 1) { p0 = 0; p1 = n0; }
+            else
+            {
+                const int cenp = b.cen_old[ev.cen_off + (REV ? c + 1 : c - 1)];
+                band_of(REV ? n0 - cenp + 1 : cenp, n0, RW, p0, p1);
+            }
+        }
+        const int nl = min(32, N - 32 * j);               // lanes with a column
+        const int rlo = __shfl_sync(full, i0, 0), rhi = __shfl_sync(full, i1, nl - 1);
+        const int nsteps = rhi - rlo + nl;
+        const long long gbase = (ev.col_off + k) * (long long)RS - i0;   // element of row i at gbase + i
+        const bool feeds = (lane == nl - 1) && (j + 1 < nblocks);        // publishes the boundary column
+        const int tag_in = (j - 1) << 12, tag_out = j << 12, tag_old = (j - NW) << 12;
+
+        double upC = 0, upS = 0, upE = 0, best = NEG;
+        int besti = 0;
+        double Cl1 = 0, El1 = 0;          // this lane's values of the previous step
+        double Pd = 0, PEd = 0;           // left neighbour's values two steps ago = (k-1, i-1)
+        // lane 0: (k-1, rlo-1) may already be needed as the diagonal input of the first row
+        if (lane == 0 && j > 0 && rlo - 1 >= p0 && rlo - 1 <= p1)
+        {
+            const int need = tag_in | (rlo - 1 - p0 + 1);
+            while (seen_prod < need) { seen_prod = prod[wprev]; }
+            __threadfence_block();
+            Pd = inC[rlo - 1 - p0];
+            if (REV) PEd = inE[rlo - 1 - p0];
+        }
+        // emission pipeline: e_next belongs to the row of the coming step
+        double e_next = 0.0;
+        {
+            const int i = rlo - lane;
+            if (s >= 0 && i >= i0 && i <= i1) e_next = cell_emission<REV>(lev, n0, i, p, l2p, off);
+        }
+        for (int t = 0; t < nsteps; t++)
+        {
+            const int i = rlo + t - lane;
+            const bool act = have && i >= i0 && i <= i1;
+            const double e = e_next;
+            e_next = 0.0;
+            if (s >= 0 && i + 1 >= i0 && i + 1 <= i1) e_next = cell_emission<REV>(lev, n0, i + 1, p, l2p, off);
+            double Pi = __shfl_up_sync(full, Cl1, 1);
+            double PE = 0.0;
+            if (REV) PE = __shfl_up_sync(full, El1, 1);
+            if (lane == 0)
+            {
+                Pi = 0.0; PE = 0.0;
+                if (j > 0 && i >= p0 && i <= p1)
+                {
+                    const int need = tag_in | (i - p0 + 1);
+                    while (seen_prod < need) { seen_prod = prod[wprev]; }
+                    __threadfence_block();
+                    Pi = inC[i - p0];
+                    if (REV) PE = inE[i - p0];
+                    cons[wprev] = need;                   // row i of the strip may now be overwritten
+                }
+            }
+            double C = 0, S = 0;
+            if (act)
+            {
+                int step = ST_STOP;
+                if (s >= 0)
+                {
+                    const bool skip_ok = i >= p0 && i <= p1;
+                    const bool diag_ok = i > p0 && i <= p1;
+                    const double eM = REV ? (diag_ok ? PEd : 0.0) : e;
+                    const double eU = REV ? upE : e;
+                    dp_cell(i == i0, skip_ok, diag_ok, k > 1 ? Pi : 0.0, k > 1 ? Pd : 0.0, eM, eU, upC, upS, tr, C, S, step);
+                    if (C > best) { best = C; besti = i; }
+                }
+                o.Mm[gbase + i] = C;
+                o.Ms[gbase + i] = S;
+                if (!REV) b.Fstep[gbase + i] = (uint8_t)step;
+                upC = C; upS = S; upE = e;
+                if (feeds)
+                {
+                    const int q = i - i0;
+                    if (j >= NW)
+                    {
+                        // the strip still holds block j-NW's column until the warp after us has read it
+                        const int need = tag_old | (q + 1);
+                        while (seen_cons < need) { seen_cons = cons[w]; }
+                    }
+                    outC[q] = C;
+                    if (REV) outE[q] = e;
+                    __threadfence_block();
+                    prod[w] = tag_out | (q + 1);
+                }
+            }
+            Pd = Pi; PEd = PE;
+            Cl1 = C; El1 = e;
+        }
+        if (lane == 0 && j > 0) cons[wprev] = tag_in | 4095;   // rows this block never needed are free too
+        if (have)
+        {
+            const long long g = ev.col_off + k;
+            o.Mi0[g] = i0; o.Mlen[g] = i1 - i0 + 1;
+            o.Mcb[g] = best; o.Mcbi[g] = besti;
+        }
+    }
+}
+
+// Serial schedule (arbitrary band layout): the same cells, column by column, by one thread; the
+// previous column's emissions (reverse pass only) alternate between two RS-long strips of smem.
+template <bool REV>
+__device__ void fill_serial(const Batch& b, const EvDesc& ev, const FillOut& o, double* smem)
+{
+    const int n0 = ev.n0, N = ev.N, RS = b.RS;
+    const LevelRec* lev = b.lev + ev.lev_off;
+    const ModelDev& md = b.models[ev.model];
+    const Trans tr = {md.lskip, md.lstay, md.lext, md.lins};
+    ColSetup cs;
+    for (int k = 1; k <= N; k++)
+    {
+        fill_setup(b, ev, REV, k, cs);
+        double upC = 0, upS = 0, upE = 0, best = NEG;
+        int besti = 0;
+        const long long gp = cs.g - 1;
+        double* Ecur = smem + (k & 1) * RS;
+        const double* Eprev = smem + ((k - 1) & 1) * RS;
+        for (int i = cs.i0; i <= cs.i1; i++)
+        {
+            double C = 0, S = 0, e = 0;
+            int step = ST_STOP;
+            if (cs.s >= 0)
+            {
+                e = cell_emission<REV>(lev, n0, i, cs.p, b.log2pi, b.lik_offset);
+                const bool skip_ok = i >= cs.p0 && i <= cs.p1;
+                const bool diag_ok = i > cs.p0 && i <= cs.p1;
+                double Pi = 0, Pi1 = 0, PE = 0;
+                if (k > 1)
+                {
+                    if (skip_ok) Pi = o.Mm[gp * RS + (i - cs.p0)];
+                    if (diag_ok) { Pi1 = o.Mm[gp * RS + (i - 1 - cs.p0)]; PE = Eprev[i - 1 - cs.p0]; }
+                }
+                const double eM = REV ? (diag_ok ? PE : 0.0) : e;
+                const double eU = REV ? upE : e;
+                dp_cell(i == cs.i0, skip_ok, diag_ok, Pi, Pi1, eM, eU, upC, upS, tr, C, S, step);
+                if (C > best) { best = C; besti = i; }
+            }
+            const long long a = cs.g * RS + (i - cs.i0);
+            o.Mm[a] = C; o.Ms[a] = S;
+            if (!REV) b.Fstep[a] = (uint8_t)step;
+            Ecur[i - cs.i0] = e;
+            upC = C; upS = S; upE = e;
+        }
+        o.Mi0[cs.g] = cs.i0; o.Mlen[cs.g] = cs.i1 - cs.i0 + 1;
+        o.Mcb[cs.g] = best; o.Mcbi[cs.g] = besti;
+    }
+}
+
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_fill(Batch b, int dir_base)
 {
     extern __shared__ double smem[];
     const int T = blockDim.x, tid = threadIdx.x;
     const EvDesc ev = b.ev[blockIdx.x];
     const bool rev = (dir_base + blockIdx.y) != 0;
     if (!ev.usable || ev.N <= 0) return;
-    const int n0 = ev.n0, N = ev.N, RS = b.RS;
-    double* Cb = smem;               // [3][T]
-    double* Eb = smem + 3 * T;       // [3][T] emissions (reverse needs the neighbour's)
-    double* Mm = rev ? b.Bm : b.Fm;
-    double* Ms = rev ? b.Bs : b.Fs;
-    int* Mi0 = rev ? b.Bi0 : b.Fi0;
-    int* Mlen = rev ? b.Blen : b.Flen;
-    double* Mcb = rev ? b.Bcb : b.Fcb;
-    int* Mcbi = rev ? b.Bcbi : b.Fcbi;
-    const double* mean = b.mean + ev.lev_off;
-    const double* stdv = b.stdv + ev.lev_off;
-    const double* lsdv = b.log_stdv + ev.lev_off;
-    const ModelDev& md = b.models[ev.model];
-    const Trans tr = {md.lskip, md.lstay, md.lext, md.lins};
-    const double off = b.lik_offset, l2p = b.log2pi;
-    const bool wave = b.mono[blockIdx.x] && T >= 2 * b.realign_width + 1;
-
-    if (wave)
+    const int N = ev.N;
+    FillOut o;
+    o.Mm = rev ? b.Bm : b.Fm; o.Ms = rev ? b.Bs : b.Fs;
+    o.Mi0 = rev ? b.Bi0 : b.Fi0; o.Mlen = rev ? b.Blen : b.Flen;
+    o.Mcb = rev ? b.Bcb : b.Fcb; o.Mcbi = rev ? b.Bcbi : b.Fcbi;
+    double* Mcb = o.Mcb; int* Mcbi = o.Mcbi;
+    if (tid < 2 * (T >> 5)) ((volatile int*)smem)[tid] = 0;     // progress words start below every tag
+    __syncthreads();
+    if (b.mono[blockIdx.x])
     {
-        ColSetup cur, nxt;
-        fill_setup(b, ev, rev, tid + 1, cur);
-        fill_setup(b, ev, rev, tid + 1 + T, nxt);
-        ColSetup first, last;
-        fill_setup(b, ev, rev, 1, first);
-        fill_setup(b, ev, rev, N, last);
-        const int dstart = 1 + first.i0, dend = N + last.i1;
-        double upC = 0, upS = 0, upE = 0, best = NEG;
-        int besti = 0;
-        const int left = (tid + T - 1) % T;
-        for (int d = dstart; d <= dend; d++)
-        {
-            if (d > cur.k + cur.i1)
-            {
-                // column finished: publish its shape and best cell, move on
-                if (cur.k <= N)
-                {
-                    Mi0[cur.g] = cur.i0; Mlen[cur.g] = cur.i1 - cur.i0 + 1;
-                    Mcb[cur.g] = best; Mcbi[cur.g] = besti;
-                }
-                cur = nxt;
-                fill_setup(b, ev, rev, cur.k + T, nxt);
-                best = NEG; besti = 0;
-            }
-            const int i = d - cur.k;
-            const int w0 = d % 3, w1 = (d + 2) % 3, w2 = (d + 1) % 3;   // this step, d-1, d-2
-            if (i >= cur.i0 && i <= cur.i1)
-            {
-                double C = 0, S = 0, e = 0;
-                int step = ST_STOP;
-                if (cur.s >= 0)
-                {
-                    const int lv = rev ? n0 - i : i - 1;
-                    e = emission(mean[lv], stdv[lv], lsdv[n0 - i], cur.p, l2p, off);
-                    const bool skip_ok = i >= cur.p0 && i <= cur.p1;
-                    const bool diag_ok = i > cur.p0 && i <= cur.p1;
-                    double Pi = 0, Pi1 = 0, PE = 0;
-                    if (cur.k > 1)
-                    {
-                        Pi = Cb[w1 * T + left];
-                        Pi1 = Cb[w2 * T + left];
-                        PE = Eb[w2 * T + left];
-                    }
-                    const double eM = rev ? (diag_ok ? PE : 0.0) : e;
-                    const double eU = rev ? upE : e;
-                    dp_cell(i == cur.i0, skip_ok, diag_ok, Pi, Pi1, eM, eU, upC, upS, tr, C, S, step);
-                    if (C > best) { best = C; besti = i; }
-                }
-                Cb[w0 * T + tid] = C;
-                Eb[w0 * T + tid] = e;
-                const long long a = cur.g * RS + (i - cur.i0);
-                Mm[a] = C; Ms[a] = S;
-                if (!rev) b.Fstep[a] = (uint8_t)step;
-                upC = C; upS = S; upE = e;
-            }
-            __syncthreads();
-        }
-        if (cur.k <= N)
-        {
-            Mi0[cur.g] = cur.i0; Mlen[cur.g] = cur.i1 - cur.i0 + 1;
-            Mcb[cur.g] = best; Mcbi[cur.g] = besti;
-        }
+        if (rev) fill_pipe<true>(b, ev, o, smem); else fill_pipe<false>(b, ev, o, smem);
     }
     else if (tid == 0)
     {
-        // serial schedule (arbitrary band layout): same cells, column by column; the previous
-        // column's emissions (reverse pass only) alternate between two RS-long strips of smem
-        ColSetup cs;
-        for (int k = 1; k <= N; k++)
-        {
-            fill_setup(b, ev, rev, k, cs);
-            double upC = 0, upS = 0, upE = 0, best = NEG;
-            int besti = 0;
-            const long long gp = cs.g - 1;
-            double* Ecur = smem + (k & 1) * RS;
-            const double* Eprev = smem + ((k - 1) & 1) * RS;
-            for (int i = cs.i0; i <= cs.i1; i++)
-            {
-                double C = 0, S = 0, e = 0;
-                int step = ST_STOP;
-                if (cs.s >= 0)
-                {
-                    const int lv = rev ? n0 - i : i - 1;
-                    e = emission(mean[lv], stdv[lv], lsdv[n0 - i], cs.p, l2p, off);
-                    const bool skip_ok = i >= cs.p0 && i <= cs.p1;
-                    const bool diag_ok = i > cs.p0 && i <= cs.p1;
-                    double Pi = 0, Pi1 = 0, PE = 0;
-                    if (k > 1)
-                    {
-                        if (skip_ok) Pi = Mm[gp * RS + (i - cs.p0)];
-                        if (diag_ok) { Pi1 = Mm[gp * RS + (i - 1 - cs.p0)]; PE = Eprev[i - 1 - cs.p0]; }
-                    }
-                    const double eM = rev ? (diag_ok ? PE : 0.0) : e;
-                    const double eU = rev ? upE : e;
-                    dp_cell(i == cs.i0, skip_ok, diag_ok, Pi, Pi1, eM, eU, upC, upS, tr, C, S, step);
-                    if (C > best) { best = C; besti = i; }
-                }
-                const long long a = cs.g * RS + (i - cs.i0);
-                Mm[a] = C; Ms[a] = S;
-                if (!rev) b.Fstep[a] = (uint8_t)step;
-                Ecur[i - cs.i0] = e;
-                upC = C; upS = S; upE = e;
-            }
-            Mi0[cs.g] = cs.i0; Mlen[cs.g] = cs.i1 - cs.i0 + 1;
-            Mcb[cs.g] = best; Mcbi[cs.g] = besti;
-        }
+        if (rev) fill_serial<true>(b, ev, o, smem); else fill_serial<false>(b, ev, o, smem);
     }
     __syncthreads();
 
@@ -591,10 +710,8 @@ __device__ __forceinline__ int mut_state(const MutView& v, int k)
 
 // ------------------------------------------------------------------------------------------
 // k_mutscore (generic form): one thread per (event, mutation) task, columns one after another,
-// the previous column's main-matrix values kept in a per-thread scratch strip (interleaved over
-// threads so accesses coalesce).  Handles any mutation length and every boundary case of
-// cpp/Alignment.cpp:447-512; the register-resident fast form for short edits lives in
-// ps_mutscore_fast.cuh.
+// the previous column's main-matrix values kept in a per-thread ring (see below).  Handles any
+// mutation length and every boundary case of cpp/Alignment.cpp:447-512.
 __device__ __forceinline__ bool task_decode(const Batch& b, long long t, int& e, int& m)
 {
     // events are laid out with nondecreasing task_off; find the event owning task t
@@ -631,14 +748,21 @@ __device__ double thread_join(const Batch& b, const EvDesc& ev, int raf, int rab
     return m;
 }
 
+// Strip storage of the previous narrow column's main-matrix values.  SMEM: a ring of S = 2W+2
+// slots per thread in shared memory, updated in place (slot = row % S; the cell (c, i) reads the
+// old value of its own slot = (c-1, i) and keeps it one more iteration as (c-1, i-1)).
+// GLOBAL: the same ring in a per-thread strip of global scratch, for widths whose ring does not
+// fit in shared memory.
+template <bool SMEM>
 __global__ void __launch_bounds__(128) k_mutscore(Batch b)
 {
+    extern __shared__ double ring_smem[];
     const long long nthreads = (long long)gridDim.x * blockDim.x;
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int W = b.scoring_width, RS = b.RS;
-    const int strip = 2 * W + 1;
-    double* bufA = b.scratch + gtid;                       // element r at bufA[r * nthreads]
-    double* bufB = b.scratch + (long long)strip * nthreads + gtid;
+    const int S = 2 * W + 2;
+    double* ring = SMEM ? ring_smem + threadIdx.x : b.scratch + gtid;
+    const long long rstride = SMEM ? blockDim.x : nthreads;       // element r at ring[r * rstride]
     for (long long t = gtid; t < b.n_tasks; t += nthreads)
     {
         int e, m;
@@ -661,7 +785,7 @@ __global__ void __launch_bounds__(128) k_mutscore(Batch b)
             if (raf <= N) old = b.old[ev.col_off + raf];
             else old = thread_join(b, ev, raf, N - raf + 1);
             const int startind = max(mu.start - 4, 0);
-            int refind = mu.start + mu.n_mut + 1;
+            const int refind = mu.start + mu.n_mut + 1;
             int last = min(min(refind, startind + mu.n_mut + 6), Nm);      // last column that gets filled
             if (W == 0) last = startind;
             double neu;
@@ -672,9 +796,7 @@ __global__ void __launch_bounds__(128) k_mutscore(Batch b)
             }
             else
             {
-                const double* mean = b.mean + ev.lev_off;
-                const double* stdv = b.stdv + ev.lev_off;
-                const double* lsdv = b.log_stdv + ev.lev_off;
+                const LevelRec* lev = b.lev + ev.lev_off;
                 const ModelDev& md = b.models[ev.model];
                 const Trans tr = {md.lskip, md.lstay, md.lext, md.lins};
                 const bool ri_empty = b.ri_empty[e] != 0;
@@ -690,76 +812,74 @@ __global__ void __launch_bounds__(128) k_mutscore(Batch b)
                     best = b.Fbest[gs];
                 }
                 // reverse column to join with
-                int rab = min(max(Nm - last + 1, 0), N);
+                const int rab = min(max(Nm - last + 1, 0), N);
                 const long long gb = ev.col_off + rab;
                 int b0 = 0, blen = n0 + 1;
                 double mb = 0.0;
                 if (rab > 0) { b0 = b.Bi0[gb]; blen = b.Blen[gb]; mb = b.Bbest[gb]; }
+                const double* Bm = b.Bm + gb * RS - b0;          // indexed by reverse row jb
+                const double* Bs = b.Bs + gb * RS - b0;
                 double joinmax = 0.0;
-                double* prev = bufA; double* cur = bufB;
                 for (int c = startind + 1; c <= last; c++)
                 {
-                    int mid = ri_empty ? 1 : b.cen_new[ev.cen_off + c];
+                    const int mid = ri_empty ? 1 : b.cen_new[ev.cen_off + c];
                     int i0, i1;
                     band_of(mid, n0, W, i0, i1);
                     const int s = mut_state(mv, c - 1);
                     const bool first_col = (c == startind + 1), last_col = (c == last);
+                    int slot = i0 % S;
                     if (s >= 0)
                     {
                         const StateParams sp = md.st[s];
                         double upC = 0, upS = 0;
+                        // (c-1, i0-1): still in its slot, nothing of this column overwrites it
+                        double diag = 0.0;
+                        if (i0 > p0 && i0 <= p1)
+                            diag = first_col ? (seed ? seed[i0 - 1 - p0] : 0.0) : ring[(long long)((i0 - 1) % S) * rstride];
                         for (int i = i0; i <= i1; i++)
                         {
-                            const double e_i = emission(mean[i - 1], stdv[i - 1], lsdv[n0 - i], sp, b.log2pi, b.lik_offset);
+                            const double e_i = cell_emission<false>(lev, n0, i, sp, b.log2pi, b.lik_offset);
                             const bool skip_ok = i >= p0 && i <= p1;
                             const bool diag_ok = i > p0 && i <= p1;
-                            double Pi = 0, Pi1 = 0;
-                            if (first_col)
-                            {
-                                if (seed) { if (skip_ok) Pi = seed[i - p0]; if (diag_ok) Pi1 = seed[i - 1 - p0]; }
-                            }
-                            else
-                            {
-                                if (skip_ok) Pi = prev[(long long)(i - p0) * nthreads];
-                                if (diag_ok) Pi1 = prev[(long long)(i - 1 - p0) * nthreads];
-                            }
-                            double C, S; int step;
-                            dp_cell(i == i0, skip_ok, diag_ok, Pi, Pi1, e_i, e_i, upC, upS, tr, C, S, step);
+                            double Pi = 0.0;
+                            if (skip_ok) Pi = first_col ? (seed ? seed[i - p0] : 0.0) : ring[(long long)slot * rstride];
+                            double C, Sv; int step;
+                            dp_cell(i == i0, skip_ok, diag_ok, Pi, diag, e_i, e_i, upC, upS, tr, C, Sv, step);
                             if (C > best) best = C;
                             if (last_col)
                             {
                                 const int jb = n0 - i + 1;
                                 if (jb >= b0 && jb < b0 + blen)
                                 {
-                                    double bm = rab > 0 ? b.Bm[gb * RS + jb - b0] : 0.0;
-                                    double bs = rab > 0 ? b.Bs[gb * RS + jb - b0] : 0.0;
-                                    joinmax = fmax(joinmax, fmax(C + bm, S + bs));
+                                    const double bm = rab > 0 ? Bm[jb] : 0.0, bs = rab > 0 ? Bs[jb] : 0.0;
+                                    joinmax = fmax(joinmax, fmax(C + bm, Sv + bs));
                                 }
                             }
-                            else cur[(long long)(i - i0) * nthreads] = C;
-                            upC = C; upS = S;
+                            else ring[(long long)slot * rstride] = C;
+                            diag = Pi;
+                            upC = C; upS = Sv;
+                            slot = slot + 1 == S ? 0 : slot + 1;
                         }
                     }
                     else
                     {
                         // invalid state: an all-zero column that inherits the running best
-                        if (last_col)
+                        for (int i = i0; i <= i1; i++)
                         {
-                            for (int i = i0; i <= i1; i++)
+                            if (last_col)
                             {
                                 const int jb = n0 - i + 1;
                                 if (jb >= b0 && jb < b0 + blen)
                                 {
-                                    double bm = rab > 0 ? b.Bm[gb * RS + jb - b0] : 0.0;
-                                    double bs = rab > 0 ? b.Bs[gb * RS + jb - b0] : 0.0;
+                                    const double bm = rab > 0 ? Bm[jb] : 0.0, bs = rab > 0 ? Bs[jb] : 0.0;
                                     joinmax = fmax(joinmax, fmax(bm, bs));
                                 }
                             }
+                            else ring[(long long)slot * rstride] = 0.0;
+                            slot = slot + 1 == S ? 0 : slot + 1;
                         }
-                        else for (int i = i0; i <= i1; i++) cur[(long long)(i - i0) * nthreads] = 0.0;
                     }
                     p0 = i0; p1 = i1;
-                    double* tmp = prev; prev = cur; cur = tmp;
                 }
                 neu = fmax(fmax(joinmax, 0.0), fmax(best, mb));
             }

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -71,10 +72,12 @@ int ps_ctx::init()
         return PS_E_CUDA;
     }
     sm_count = prop.multiProcessorCount;
+    if (const char* fw = getenv("PORESEQ_B200_FILL_WARPS")) fill_warps = std::min(16, std::max(1, atoi(fw)));
     CU(cudaStreamCreate(&stream));
     for (int i = 0; i <= PS_T_COUNT; i++) CU(cudaEventCreate(&tev[i]));
-    CU(cudaFuncSetAttribute(k_fill<640>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    CU(cudaFuncSetAttribute(k_fill<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CU(cudaFuncSetAttribute(k_fill<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(k_fill<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(k_mutscore<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     ready = true;
     return PS_OK;
 }
@@ -184,7 +187,8 @@ void ps_build_model(const HostModel& hm, ModelDev& md)     // cpp/EventData.h:48
         p.sd_mean = hm.raw[2][s];
         p.sd_lambda = std::pow(hm.raw[2][s], 3) / std::pow(hm.raw[3][s], 2);
         p.log_lambda = std::log(p.sd_lambda);
-        p.pad0 = p.pad1 = 0;
+        p.r_lev_stdv = 1.0 / p.lev_stdv;
+        p.r_sd_mean = 1.0 / p.sd_mean;
     }
     md.lskip = std::log(hm.trans[0]);
     md.lstay = std::log(hm.trans[1]);
@@ -206,7 +210,8 @@ struct Job
     std::vector<const HostModel*> model_src;
     std::vector<int> states;
     std::string bases;
-    std::vector<double> mean, stdv, log_stdv, ref_align, ref_like, ref_index;
+    std::vector<LevelRec> lev;
+    std::vector<double> ref_align, ref_like, ref_index;
     std::vector<int> ri_empty, mono;
     std::vector<MutDev> mdev;
     std::string mut_str;
@@ -299,9 +304,14 @@ int Job::build()
             n_cen += d.N + cen_pad + 1;
             n_tasks += nm;
             ev.push_back(d);
-            mean.insert(mean.end(), he.mean.begin(), he.mean.end());
-            stdv.insert(stdv.end(), he.stdv.begin(), he.stdv.end());
-            log_stdv.insert(log_stdv.end(), he.log_stdv.begin(), he.log_stdv.end());
+            for (int i = 0; i < he.n0; i++)
+            {
+                LevelRec lr;
+                lr.mean = he.mean[i]; lr.stdv = he.stdv[i];
+                lr.rstdv = 1.0 / he.stdv[i];
+                lr.lsd3 = 3 * he.log_stdv[i];
+                lev.push_back(lr);
+            }
             ref_align.insert(ref_align.end(), he.ref_align.begin(), he.ref_align.end());
             ref_like.insert(ref_like.end(), he.ref_like.begin(), he.ref_like.end());
             if (he.ri_empty) ref_index.insert(ref_index.end(), he.n0, 0.0);
@@ -355,21 +365,19 @@ int Job::upload()
     for (size_t q = 0; q < model_src.size(); q++) ps_build_model(*model_src[q], models[q]);
 
     EvDesc* d_ev; ModelDev* d_models; int* d_states; char* d_bases;
-    double *d_mean, *d_stdv, *d_lsd;
+    LevelRec* d_lev;
     TRY(up(ctx, "ev", ev.data(), ev.size(), &d_ev));
     TRY(up(ctx, "models", models.data(), models.size(), &d_models));
     TRY(up(ctx, "states", states.data(), states.size(), &d_states));
     TRY(up(ctx, "bases", bases.data(), bases.size(), &d_bases));
-    TRY(up(ctx, "mean", mean.data(), mean.size(), &d_mean));
-    TRY(up(ctx, "stdv", stdv.data(), stdv.size(), &d_stdv));
-    TRY(up(ctx, "log_stdv", log_stdv.data(), log_stdv.size(), &d_lsd));
+    TRY(up(ctx, "lev", lev.data(), lev.size(), &d_lev));
     TRY(up(ctx, "ref_align", ref_align.data(), ref_align.size(), &b.ref_align));
     TRY(up(ctx, "ref_like", ref_like.data(), ref_like.size(), &b.ref_like));
     TRY(up(ctx, "ref_index", ref_index.data(), ref_index.size(), &b.ref_index));
     TRY(up(ctx, "ri_empty", ri_empty.data(), ri_empty.size(), &b.ri_empty));
     TRY(up(ctx, "mono", mono.data(), mono.size(), &b.mono));
     b.ev = d_ev; b.models = d_models; b.states = d_states; b.bases = d_bases;
-    b.mean = d_mean; b.stdv = d_stdv; b.log_stdv = d_lsd;
+    b.lev = d_lev;
     TRY(room(ctx, "bt_src", (size_t)n_levels, &b.bt_src));
     TRY(room(ctx, "refstart", ev.size(), &b.refstart));
     TRY(room(ctx, "refend", ev.size(), &b.refend));
@@ -423,15 +431,14 @@ int Job::run(bool full)
         LAUNCHED();
     }
     MARK(PS_T_FORWARD);
-    // wavefront fill: T threads >= band length; forward and reverse in one launch (grid.y = 2)
+    // pipelined wavefront fill: NW warps per (event, direction), forward and reverse in one launch
     {
-        const int band = 2 * b.realign_width + 1;
-        int T = std::min(1024, ((band + 31) / 32) * 32);
-        T = std::max(T, 64);
-        const size_t smem = std::max<size_t>(6 * T, 2 * b.RS) * sizeof(double);
+        const int NW = ctx->fill_warps;
+        const size_t smem = ((size_t)NW + (size_t)NW * b.RS * (full ? 2 : 1)) * sizeof(double);
         dim3 grid(nev, full ? 2 : 1);
-        if (T <= 640) k_fill<640><<<grid, T, smem, ctx->stream>>>(b, 0);
-        else k_fill<1024><<<grid, T, smem, ctx->stream>>>(b, 0);
+        if (smem > 200 * 1024) { ps_set_error(ctx, "realign_width %d needs %zu bytes of shared memory", b.realign_width, smem); return PS_E_ARG; }
+        if (NW <= 8) k_fill<256, 2><<<grid, NW * 32, smem, ctx->stream>>>(b, 0);
+        else k_fill<512, 1><<<grid, NW * 32, smem, ctx->stream>>>(b, 0);
         LAUNCHED();
     }
     MARK(PS_T_BACKWARD);   // (reverse fill shares the launch above; kept as a phase marker)
@@ -453,12 +460,23 @@ int Job::run(bool full)
         }
         MARK(PS_T_MUTSCORE);
         {
-            const int threads = 128;
-            long long blocks = std::min<long long>((n_tasks + threads - 1) / threads, (long long)ctx->sm_count * 8);
-            b.scratch_slots = blocks * threads;
-            const size_t strip = (size_t)(2 * b.scoring_width + 1);
-            TRY(room(ctx, "scratch", (size_t)b.scratch_slots * strip * 2, &b.scratch));
-            k_mutscore<<<(unsigned)blocks, threads, 0, ctx->stream>>>(b);
+            // previous-column ring: shared memory when 2W+2 doubles per thread fit, else global scratch
+            const size_t ring = (size_t)(2 * b.scoring_width + 2) * sizeof(double);
+            int threads = 128;
+            while (threads > 32 && ring * threads > 96 * 1024) threads >>= 1;
+            const bool in_smem = ring * threads <= 96 * 1024;
+            if (!in_smem) threads = 128;
+            long long blocks = std::min<long long>((n_tasks + threads - 1) / threads, (long long)ctx->sm_count * 16);
+            if (in_smem)
+            {
+                k_mutscore<true><<<(unsigned)blocks, threads, ring * threads, ctx->stream>>>(b);
+            }
+            else
+            {
+                b.scratch_slots = blocks * threads;
+                TRY(room(ctx, "scratch", (size_t)b.scratch_slots * (2 * b.scoring_width + 2), &b.scratch));
+                k_mutscore<false><<<(unsigned)blocks, threads, 0, ctx->stream>>>(b);
+            }
             LAUNCHED();
         }
         MARK(PS_T_REDUCE);

@@ -15,6 +15,7 @@ struct ps_ctx
     int device = 0;
     bool ready = false;
     int sm_count = 0;
+    int fill_warps = 8;                       // warps per (event, direction) in the wide fill (PORESEQ_B200_FILL_WARPS)
     cudaStream_t stream = nullptr;
     cudaEvent_t tev[PS_T_COUNT + 1];
     double timing[PS_T_COUNT] = {0};

@@ -13,7 +13,15 @@ constexpr int ST_SKIP = 0, ST_MATCH = 1, ST_INSERT = 2, ST_IGNORE = 3, ST_STAY =
 
 struct StateParams            // one 64-byte record per 5-mer state (cpp/EventData.h:21-45)
 {
-    double lev_mean, lev_stdv, log_lev, sd_mean, sd_lambda, log_lambda, pad0, pad1;
+    double lev_mean, lev_stdv, log_lev, sd_mean, sd_lambda, log_lambda;
+    double r_lev_stdv, r_sd_mean;      // correctly rounded reciprocals of the two divisors (host IEEE division)
+};
+
+struct LevelRec               // one 32-byte record per event level (cpp/EventData.h:96-101, :218-220)
+{
+    double mean, stdv;
+    double rstdv;                      // RN(1 / stdv)
+    double lsd3;                       // 3 * log(stdv)
 };
 
 struct ModelDev               // cpp/EventData.h:21-74

@@ -177,3 +177,52 @@ def test_mutate_viterbi(ctx, ref):
     nb = pa.Mutate(seqs='viterbi')
     assert (nb, pa.sequence) == (want_nb, want_seq)
     assert same_aligns([(e.ref_align, e.ref_like) for e in pa.events], want_a)
+
+
+def test_consensus_loop(ctx, ref):
+    """The whole Mutate.py policy on the CUDA path vs the same policy driven through the reference:
+    final consensus sequence identical, and better than the draft."""
+    from poreseq_b200 import drivers
+    reg = synth.make_region(500, 5, seed=21, draft_error=0.06, partial=0.2,
+                            params=dict(realign_width=80, scoring_width=25, point_width=10, end_trim=20))
+    # reference side: same call sequence through the checker
+    import copy
+    rr = copy.deepcopy(reg)
+
+    def sync(al):
+        for ev, (ra, rl) in zip(rr.events, al):
+            ev.ref_align, ev.ref_like = ra, rl
+
+    ref.srand(1)
+    seq, _, al = ref.mutate(rr, [ev.sequence for ev in rr.events[::2]], reps=4)
+    rr.sequence = seq; sync(al)
+    for _ in range(4):
+        seeds = ref.viterbi_mutate(rr, nkeep=16, seed=None)
+        seq, _, al = ref.mutate(rr, seeds, reps=4)
+        rr.sequence = seq; sync(al)
+        seq, nb, al = ref.refine(rr)
+        rr.sequence = seq; sync(al)
+        if nb == 0:
+            break
+    want = rr.sequence[20:-20]
+    ref.srand(1)
+    pa = drivers.make_psalign(reg)
+    got, acc = drivers.consensus(pa, refseq=reg.truth, reps=4)
+    assert got == want
+    assert acc > poreseqcpp.swalign(reg.sequence, reg.truth)[0]
+
+
+def test_variant_modes(ctx, orc):
+    from poreseq_b200 import drivers
+    from poreseq_b200.Util import MutationInfo
+    reg = region("draft_partial")
+    pa = drivers.make_psalign(reg)
+    st, og, mu = edge_mutations(reg.sequence, 3, count=40)
+    muts = []
+    for s, o, m in zip(st, og, mu):
+        mi = MutationInfo(); mi.start, mi.orig, mi.mut = s + 1000, o, m
+        muts.append(mi)
+    got = drivers.variant(pa, muts=muts, region_start=1000)
+    want, _ = orc.score_mutations(reg, st, og, mu)
+    assert [g.score for g in got] == want.tolist()
+    assert [g.start for g in got] == [s + 1000 for s in st]
