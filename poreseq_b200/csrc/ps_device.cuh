@@ -38,6 +38,9 @@ struct EvDesc                 // one event of one region in the batch
     long long cen_off;        // into centre tables: index cen_off + c, c = 0..N+cen_pad
     long long mut_off;        // first mutation of the region in the mutation arrays
     long long task_off;       // first (event, mutation) task of this event; delta[task_off + m]
+    long long band_off;       // first element of this event's band storage (same for F and B arrays)
+    int       ts;             // band storage stride: cell (k, i) lives at band_off + (k+i)*ts + k%ts
+    int       pad2;
 };
 
 struct MutDev
@@ -67,8 +70,9 @@ struct Batch                  // everything the kernels need, passed by value
     int*              cen_old;
     int*              cen_new;
     int               cen_pad;
-    // band storage, RS doubles per column
-    int               RS;
+    // band storage, wavefront-major: the cells of one anti-diagonal d = k+i of an event are
+    // contiguous (slot k % ts), so the fill's per-step stores and the join's loads coalesce
+    int               RS;            // 2*realign_width+1 rounded up (serial-fallback smem strips)
     double*           Fm; double* Fs; double* Bm; double* Bs;
     uint8_t*          Fstep;
     int*              Fi0; int* Flen; int* Bi0; int* Blen;
@@ -132,6 +136,12 @@ __device__ __forceinline__ double cell_emission(const LevelRec* lev, int n0, int
 }
 
 struct Trans { double lskip, lstay, lext, lins; };
+
+// band storage address of cell (column k in processing order, row i)
+__device__ __forceinline__ long long cell_at(const EvDesc& ev, int k, int i)
+{
+    return ev.band_off + (long long)(k + i) * ev.ts + (k % ev.ts);
+}
 
 // One cell of the coupled (main C, stay S) recurrence, cpp/Alignment.cpp:194-271 (forward) and
 // :370-441 (reverse).  eM = emission added on the diagonal move (forward: this cell's; reverse:
@@ -253,155 +263,106 @@ struct FillOut               // where one direction's band columns go
     double* Mm; double* Ms; int* Mi0; int* Mlen; double* Mcb; int* Mcbi;
 };
 
-// Pipelined wavefront of one (event, direction).
-//
-// The columns (in processing order k = 1..N) are cut into blocks of 32.  A warp owns one block at
-// a time, lane l = column 32j+1+l, and sweeps the rows with a one-row skew between neighbouring
-// lanes: at step t lane l computes row rlo + t - l.  The vertical dependency (k, i-1) stays in the
-// lane's registers; the horizontal ones (k-1, i) and (k-1, i-1) are what lane l-1 produced one and
-// two steps earlier and arrive by __shfl_up.  Lane 0 takes them from the previous block's last
-// column, which the warp that owns block j-1 publishes row by row into a shared-memory strip,
-// guarded by two monotone progress words (rows produced / rows consumed, tagged with the block
-// index) -- no block-wide barrier anywhere in the sweep.  Warp w runs blocks w, w+NW, ..., so up to
-// NW blocks are in flight, each trailing its predecessor by about 32 steps.
-// The emission of the next row is evaluated alongside the recurrence of the current one.
+// Wavefront schedule of one (event, direction): cell (k, i) is computed at step d = k + i by the
+// thread that owns column k (k = tid+1, tid+1+T, ...).  Steps are taken four at a time:
+//   * the emissions of the thread's next four cells do not depend on the recurrence, so they are
+//     evaluated first, back to back (independent division-free chains);
+//   * the four barrier-separated steps that follow only carry the max-plus recurrence; the two
+//     horizontal inputs come from the left neighbour through a 4-deep shared-memory ring indexed
+//     by the (compile-time) step-in-batch, the vertical one stays in registers.
+// A thread moves to its next column only at a batch boundary; the host guarantees
+// dlo(k+T) >= dhi(k) + 5 for every k (ps_host.cu: wave_threads), so no cell is skipped.
 template <bool REV>
-__device__ __forceinline__ void fill_pipe(const Batch& b, const EvDesc& ev, const FillOut& o, double* smem)
+__device__ __forceinline__ void fill_wave(const Batch& b, const EvDesc& ev, const FillOut& o, double* smem)
 {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, NW = blockDim.x >> 5;
-    const int n0 = ev.n0, N = ev.N, RS = b.RS, RW = b.realign_width;
-    volatile int* prod = (volatile int*)smem;             // [NW] rows produced, tagged with the block
-    volatile int* cons = prod + NW;                       // [NW] rows consumed
-    double* bndC = smem + NW;                             // [NW][RS] last-column main values
-    double* bndE = bndC + NW * RS;                        // [NW][RS] its emissions (reverse pass only)
+    const int T = blockDim.x, tid = threadIdx.x;
+    const int n0 = ev.n0, N = ev.N;
+    double* Cb = smem;               // [4][T] main-matrix values of the last four steps
+    double* Eb = smem + 4 * T;       // [4][T] emissions (the reverse pass adds the source cell's)
     const LevelRec* lev = b.lev + ev.lev_off;
     const ModelDev& md = b.models[ev.model];
     const Trans tr = {md.lskip, md.lstay, md.lext, md.lins};
     const double off = b.lik_offset, l2p = b.log2pi;
-    const unsigned full = 0xffffffffu;
-    const int nblocks = (N + 31) >> 5;
-    const int wprev = w == 0 ? NW - 1 : w - 1;
-    double* outC = bndC + w * RS;
-    double* outE = bndE + w * RS;
-    const double* inC = bndC + wprev * RS;
-    const double* inE = bndE + wprev * RS;
-    int seen_prod = 0, seen_cons = 0;
 
-    for (int j = w; j < nblocks; j += NW)
+    ColSetup cur, nxt;
+    fill_setup(b, ev, REV, tid + 1, cur);
+    fill_setup(b, ev, REV, tid + 1 + T, nxt);
+    int dstart, dend;
     {
-        const int k = 32 * j + 1 + lane;
-        const bool have = k <= N;
-        const int c = REV ? N - k + 1 : k;
-        int i0 = 1, i1 = 0, s = -1;
-        StateParams p;
-        if (have)
+        int a0, a1, z0, z1;
+        const int c1 = REV ? N : 1, cN = REV ? 1 : N;
+        const int cen1 = b.cen_old[ev.cen_off + c1], cenN = b.cen_old[ev.cen_off + cN];
+        band_of(REV ? n0 - cen1 + 1 : cen1, n0, b.realign_width, a0, a1);
+        band_of(REV ? n0 - cenN + 1 : cenN, n0, b.realign_width, z0, z1);
+        dstart = 1 + a0; dend = N + z1;
+    }
+    double upC = 0, upS = 0, upE = 0, best = NEG;
+    int besti = 0;
+    const int left = tid == 0 ? T - 1 : tid - 1;
+    for (int db = dstart; db <= dend; db += 4)
+    {
+        if (db > cur.k + cur.i1)
         {
-            const int cen = b.cen_old[ev.cen_off + c];
-            band_of(REV ? n0 - cen + 1 : cen, n0, RW, i0, i1);
-            s = b.states[ev.state_off + c - 1];
-            if (s >= 0) p = md.st[s];
-        }
-        int p0 = __shfl_up_sync(full, i0, 1), p1 = __shfl_up_sync(full, i1, 1);
-        if (lane == 0)
-        {
-            if (k == 1) { p0 = 0; p1 = n0; }
-            else
+            // column finished: publish its shape and best cell, move on to the prefetched one
+            if (cur.k <= N)
             {
-                const int cenp = b.cen_old[ev.cen_off + (REV ? c + 1 : c - 1)];
-                band_of(REV ? n0 - cenp + 1 : cenp, n0, RW, p0, p1);
+                o.Mi0[cur.g] = cur.i0; o.Mlen[cur.g] = cur.i1 - cur.i0 + 1;
+                o.Mcb[cur.g] = best; o.Mcbi[cur.g] = besti;
             }
+            cur = nxt;
+            fill_setup(b, ev, REV, cur.k + T, nxt);
+            best = NEG; besti = 0;
         }
-        const int nl = min(32, N - 32 * j);               // lanes with a column
-        const int rlo = __shfl_sync(full, i0, 0), rhi = __shfl_sync(full, i1, nl - 1);
-        const int nsteps = rhi - rlo + nl;
-        const long long gbase = (ev.col_off + k) * (long long)RS - i0;   // element of row i at gbase + i
-        const bool feeds = (lane == nl - 1) && (j + 1 < nblocks);        // publishes the boundary column
-        const int tag_in = (j - 1) << 12, tag_out = j << 12, tag_old = (j - NW) << 12;
-
-        double upC = 0, upS = 0, upE = 0, best = NEG;
-        int besti = 0;
-        double Cl1 = 0, El1 = 0;          // this lane's values of the previous step
-        double Pd = 0, PEd = 0;           // left neighbour's values two steps ago = (k-1, i-1)
-        // lane 0: (k-1, rlo-1) may already be needed as the diagonal input of the first row
-        if (lane == 0 && j > 0 && rlo - 1 >= p0 && rlo - 1 <= p1)
+        const int ib = db - cur.k;                                    // row of the first step of the batch
+        const bool mine = ib + 3 >= cur.i0 && ib <= cur.i1;           // any of my four cells in the band
+        const bool warp_busy = __any_sync(0xffffffffu, mine);
+        double e4[4] = {0.0, 0.0, 0.0, 0.0};
+        if (mine && cur.s >= 0)
         {
-            const int need = tag_in | (rlo - 1 - p0 + 1);
-            while (seen_prod < need) { seen_prod = prod[wprev]; }
-            __threadfence_block();
-            Pd = inC[rlo - 1 - p0];
-            if (REV) PEd = inE[rlo - 1 - p0];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (ib + u >= cur.i0 && ib + u <= cur.i1) e4[u] = cell_emission<REV>(lev, n0, ib + u, cur.p, l2p, off);
         }
-        // emission pipeline: e_next belongs to the row of the coming step
-        double e_next = 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; u++)
         {
-            const int i = rlo - lane;
-            if (s >= 0 && i >= i0 && i <= i1) e_next = cell_emission<REV>(lev, n0, i, p, l2p, off);
-        }
-        for (int t = 0; t < nsteps; t++)
-        {
-            const int i = rlo + t - lane;
-            const bool act = have && i >= i0 && i <= i1;
-            const double e = e_next;
-            e_next = 0.0;
-            if (s >= 0 && i + 1 >= i0 && i + 1 <= i1) e_next = cell_emission<REV>(lev, n0, i + 1, p, l2p, off);
-            double Pi = __shfl_up_sync(full, Cl1, 1);
-            double PE = 0.0;
-            if (REV) PE = __shfl_up_sync(full, El1, 1);
-            if (lane == 0)
+            if (db + u > dend) break;                                 // uniform across the CTA
+            const int i = ib + u;
+            if (warp_busy && i >= cur.i0 && i <= cur.i1)
             {
-                Pi = 0.0; PE = 0.0;
-                if (j > 0 && i >= p0 && i <= p1)
-                {
-                    const int need = tag_in | (i - p0 + 1);
-                    while (seen_prod < need) { seen_prod = prod[wprev]; }
-                    __threadfence_block();
-                    Pi = inC[i - p0];
-                    if (REV) PE = inE[i - p0];
-                    cons[wprev] = need;                   // row i of the strip may now be overwritten
-                }
-            }
-            double C = 0, S = 0;
-            if (act)
-            {
+                double C = 0, S = 0;
+                const double e = e4[u];
                 int step = ST_STOP;
-                if (s >= 0)
+                if (cur.s >= 0)
                 {
-                    const bool skip_ok = i >= p0 && i <= p1;
-                    const bool diag_ok = i > p0 && i <= p1;
-                    const double eM = REV ? (diag_ok ? PEd : 0.0) : e;
+                    const bool skip_ok = i >= cur.p0 && i <= cur.p1;
+                    const bool diag_ok = i > cur.p0 && i <= cur.p1;
+                    double Pi = 0, Pi1 = 0, PE = 0;
+                    if (cur.k > 1)
+                    {
+                        Pi = Cb[((u + 3) & 3) * T + left];            // step d-1: (k-1, i)
+                        Pi1 = Cb[((u + 2) & 3) * T + left];           // step d-2: (k-1, i-1)
+                        if (REV) PE = Eb[((u + 2) & 3) * T + left];
+                    }
+                    const double eM = REV ? (diag_ok ? PE : 0.0) : e;
                     const double eU = REV ? upE : e;
-                    dp_cell(i == i0, skip_ok, diag_ok, k > 1 ? Pi : 0.0, k > 1 ? Pd : 0.0, eM, eU, upC, upS, tr, C, S, step);
+                    dp_cell(i == cur.i0, skip_ok, diag_ok, Pi, Pi1, eM, eU, upC, upS, tr, C, S, step);
                     if (C > best) { best = C; besti = i; }
                 }
-                o.Mm[gbase + i] = C;
-                o.Ms[gbase + i] = S;
-                if (!REV) b.Fstep[gbase + i] = (uint8_t)step;
+                Cb[u * T + tid] = C;
+                if (REV) Eb[u * T + tid] = e;
+                const long long a = cell_at(ev, cur.k, i);
+                o.Mm[a] = C; o.Ms[a] = S;
+                if (!REV) b.Fstep[a] = (uint8_t)step;
                 upC = C; upS = S; upE = e;
-                if (feeds)
-                {
-                    const int q = i - i0;
-                    if (j >= NW)
-                    {
-                        // the strip still holds block j-NW's column until the warp after us has read it
-                        const int need = tag_old | (q + 1);
-                        while (seen_cons < need) { seen_cons = cons[w]; }
-                    }
-                    outC[q] = C;
-                    if (REV) outE[q] = e;
-                    __threadfence_block();
-                    prod[w] = tag_out | (q + 1);
-                }
             }
-            Pd = Pi; PEd = PE;
-            Cl1 = C; El1 = e;
+            __syncthreads();
         }
-        if (lane == 0 && j > 0) cons[wprev] = tag_in | 4095;   // rows this block never needed are free too
-        if (have)
-        {
-            const long long g = ev.col_off + k;
-            o.Mi0[g] = i0; o.Mlen[g] = i1 - i0 + 1;
-            o.Mcb[g] = best; o.Mcbi[g] = besti;
-        }
+    }
+    if (cur.k <= N)
+    {
+        o.Mi0[cur.g] = cur.i0; o.Mlen[cur.g] = cur.i1 - cur.i0 + 1;
+        o.Mcb[cur.g] = best; o.Mcbi[cur.g] = besti;
     }
 }
 
@@ -420,7 +381,6 @@ __device__ void fill_serial(const Batch& b, const EvDesc& ev, const FillOut& o, 
         fill_setup(b, ev, REV, k, cs);
         double upC = 0, upS = 0, upE = 0, best = NEG;
         int besti = 0;
-        const long long gp = cs.g - 1;
         double* Ecur = smem + (k & 1) * RS;
         const double* Eprev = smem + ((k - 1) & 1) * RS;
         for (int i = cs.i0; i <= cs.i1; i++)
@@ -435,15 +395,15 @@ __device__ void fill_serial(const Batch& b, const EvDesc& ev, const FillOut& o, 
                 double Pi = 0, Pi1 = 0, PE = 0;
                 if (k > 1)
                 {
-                    if (skip_ok) Pi = o.Mm[gp * RS + (i - cs.p0)];
-                    if (diag_ok) { Pi1 = o.Mm[gp * RS + (i - 1 - cs.p0)]; PE = Eprev[i - 1 - cs.p0]; }
+                    if (skip_ok) Pi = o.Mm[cell_at(ev, k - 1, i)];
+                    if (diag_ok) { Pi1 = o.Mm[cell_at(ev, k - 1, i - 1)]; PE = Eprev[i - 1 - cs.p0]; }
                 }
                 const double eM = REV ? (diag_ok ? PE : 0.0) : e;
                 const double eU = REV ? upE : e;
                 dp_cell(i == cs.i0, skip_ok, diag_ok, Pi, Pi1, eM, eU, upC, upS, tr, C, S, step);
                 if (C > best) { best = C; besti = i; }
             }
-            const long long a = cs.g * RS + (i - cs.i0);
+            const long long a = cell_at(ev, k, i);
             o.Mm[a] = C; o.Ms[a] = S;
             if (!REV) b.Fstep[a] = (uint8_t)step;
             Ecur[i - cs.i0] = e;
@@ -468,11 +428,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_fill(Batch b, int dir_base)
     o.Mi0 = rev ? b.Bi0 : b.Fi0; o.Mlen = rev ? b.Blen : b.Flen;
     o.Mcb = rev ? b.Bcb : b.Fcb; o.Mcbi = rev ? b.Bcbi : b.Fcbi;
     double* Mcb = o.Mcb; int* Mcbi = o.Mcbi;
-    if (tid < 2 * (T >> 5)) ((volatile int*)smem)[tid] = 0;     // progress words start below every tag
-    __syncthreads();
     if (b.mono[blockIdx.x])
     {
-        if (rev) fill_pipe<true>(b, ev, o, smem); else fill_pipe<false>(b, ev, o, smem);
+        if (rev) fill_wave<true>(b, ev, o, smem); else fill_wave<false>(b, ev, o, smem);
     }
     else if (tid == 0)
     {
@@ -564,65 +522,119 @@ __device__ void dev_updaterefs(const double* ra, double* ri, int n0, int& empty,
     }
 }
 
-// k_backtrace: one CTA per event.  Thread 0 follows the packed step bytes from the best cell
-// (cpp/Alignment.cpp:516-605); every visited level records its column and matrix, the CTA then
-// gathers ref_like in parallel and thread 0 rebuilds ref_index.
-__global__ void k_backtrace(Batch b)
+// k_backtrace: one CTA per event.  The best path is followed from the best cell through the packed
+// step bytes (cpp/Alignment.cpp:516-605).  A pointer chase through global memory costs one L2 round
+// trip per move, so the CTA stages a window of step bytes (BT_D anti-diagonals x BT_C columns
+// ending at the current cell) into shared memory with coalesced loads, thread 0 walks inside it,
+// and the window is re-staged where the walk leaves it.  Every visited level records its column
+// and matrix; the CTA then gathers ref_like in parallel and thread 0 rebuilds ref_index.
+constexpr int BT_D = 128, BT_C = 64;
+
+__global__ void __launch_bounds__(256) k_backtrace(Batch b, int smem_levels)
 {
+    extern __shared__ double bt_dyn[];
     const EvDesc ev = b.ev[blockIdx.x];
     if (!ev.usable) return;
-    const int n0 = ev.n0, N = ev.N, RS = b.RS, tid = threadIdx.x;
+    const int n0 = ev.n0, N = ev.N, tid = threadIdx.x;
     double* ra = b.ref_align + ev.lev_off;
     double* rl = b.ref_like + ev.lev_off;
-    int* src = b.bt_src + ev.lev_off;
-    for (int i = tid; i < n0; i += blockDim.x) { ra[i] = 0.0; rl[i] = 0.0; src[i] = 0; }
-    __syncthreads();
-    if (tid == 0 && N > 0)
+    double* ri = b.ref_index + ev.lev_off;
+    // the per-level scratch of the walk lives in shared memory when the event fits
+    const bool in_smem = n0 <= smem_levels;
+    double* val = in_smem ? bt_dyn : ra;
+    int* src = in_smem ? (int*)(bt_dyn + smem_levels) : b.bt_src + ev.lev_off;
+    __shared__ uint8_t win[BT_D][BT_C];
+    __shared__ int w_i0[BT_C], w_i1[BT_C];
+    __shared__ int s_i, s_j, s_arr, s_go, s_empty;
+    for (int i = tid; i < n0; i += blockDim.x) { val[i] = 0.0; src[i] = 0; }
+    if (tid == 0)
     {
-        int i = b.Fbi[ev.col_off + N], j = b.Fbj[ev.col_off + N], arr = 0;
-        while (i > 0 && j > 0)
-        {
-            const long long g = ev.col_off + j;
-            const int st = b.Fstep[g * RS + (i - b.Fi0[g])];
-            const int mv = arr ? ((st >> 3) & 3) : (st & 7);
-            if (arr == 0)
-            {
-                if (mv == ST_STOP || mv == ST_IMPLICIT || mv == 5) break;
-                if (mv == ST_SKIP) { j--; }
-                else if (mv == ST_MATCH) { ra[i - 1] = (double)j; src[i - 1] = 2 * j; i--; j--; }
-                else if (mv == ST_IGNORE) { ra[i - 1] = -1.0; src[i - 1] = 2 * j; i--; j--; }
-                else if (mv == ST_INSERT) { ra[i - 1] = -1.0; src[i - 1] = 2 * j; i--; }
-                else /* ST_STAY: hop to the stay matrix, same cell */ arr = 1;
-            }
-            else
-            {
-                if (mv == 0) break;
-                ra[i - 1] = (double)j; src[i - 1] = 2 * j + 1;
-                i--;
-                if (mv == 1) arr = 0;          // stay: back to the main matrix one row up
-            }
-        }
+        s_i = N > 0 ? b.Fbi[ev.col_off + N] : 0;
+        s_j = N > 0 ? b.Fbj[ev.col_off + N] : 0;
+        s_arr = 0;
+        s_go = (s_i > 0 && s_j > 0) ? 1 : 0;
     }
     __syncthreads();
+    while (s_go)
+    {
+        const int ktop = s_j, dtop = s_j + s_i;
+        const int kbot = ktop - BT_C + 1;                 // columns kbot..ktop, diagonals dtop-BT_D+1..dtop
+        __syncthreads();                                  // everyone has read the walk position
+        for (int q = tid; q < BT_C; q += blockDim.x)
+        {
+            const int k = kbot + q;
+            int a0 = 1, a1 = 0;
+            if (k >= 1) { const long long g = ev.col_off + k; a0 = b.Fi0[g]; a1 = a0 + b.Flen[g] - 1; }
+            w_i0[q] = a0; w_i1[q] = a1;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < BT_D * BT_C; idx += blockDim.x)
+        {
+            const int r = idx / BT_C, q = idx % BT_C;
+            const int k = kbot + q, i = dtop - r - k;
+            uint8_t v = ST_STOP;
+            if (i >= w_i0[q] && i <= w_i1[q]) v = b.Fstep[cell_at(ev, k, i)];
+            win[r][q] = v;
+        }
+        __syncthreads();
+        if (tid == 0)
+        {
+            int i = s_i, j = s_j, arr = s_arr, go = 1;
+            while (i > 0 && j > 0)
+            {
+                const int r = dtop - (j + i), q = j - kbot;
+                if (r >= BT_D || q < 0) break;            // left the window: re-stage
+                const int st = win[r][q];
+                const int mv = arr ? ((st >> 3) & 3) : (st & 7);
+                if (arr == 0)
+                {
+                    if (mv == ST_STOP || mv == ST_IMPLICIT || mv == 5) { go = 0; break; }
+                    if (mv == ST_SKIP) { j--; }
+                    else if (mv == ST_MATCH) { val[i - 1] = (double)j; src[i - 1] = 2 * j; i--; j--; }
+                    else if (mv == ST_IGNORE) { val[i - 1] = -1.0; src[i - 1] = 2 * j; i--; j--; }
+                    else if (mv == ST_INSERT) { val[i - 1] = -1.0; src[i - 1] = 2 * j; i--; }
+                    else /* ST_STAY: hop to the stay matrix, same cell */ arr = 1;
+                }
+                else
+                {
+                    if (mv == 0) { go = 0; break; }
+                    val[i - 1] = (double)j; src[i - 1] = 2 * j + 1;
+                    i--;
+                    if (mv == 1) arr = 0;                 // stay: back to the main matrix one row up
+                }
+            }
+            if (!(i > 0 && j > 0)) go = 0;
+            s_i = i; s_j = j; s_arr = arr; s_go = go;
+        }
+        __syncthreads();
+    }
+    // ref_align out, ref_like gathered from the recorded (column, matrix) of every aligned level
     for (int i = tid; i < n0; i += blockDim.x)
     {
-        int s = src[i];
+        if (in_smem) ra[i] = val[i];
+        const int s = src[i];
+        double like = 0.0;
         if (s)
         {
-            const long long g = ev.col_off + (s >> 1);
-            const long long a = g * RS + (i + 1 - b.Fi0[g]);
-            rl[i] = (s & 1) ? b.Fs[a] : b.Fm[a];
+            const long long a = cell_at(ev, s >> 1, i + 1);
+            like = (s & 1) ? b.Fs[a] : b.Fm[a];
         }
+        rl[i] = like;
     }
     __syncthreads();
     if (tid == 0)
     {
         int empty, rs, re;
-        dev_updaterefs(ra, b.ref_index + ev.lev_off, n0, empty, rs, re);
+        // in shared memory the interpolation runs in place (every entry is read before it is rewritten)
+        dev_updaterefs(val, in_smem ? val : ri, n0, empty, rs, re);
         b.ri_empty[blockIdx.x] = empty;
         b.refstart[blockIdx.x] = rs;
         b.refend[blockIdx.x] = re;
+        s_empty = empty;
     }
+    __syncthreads();
+    if (in_smem && !s_empty)
+        for (int i = tid; i < n0; i += blockDim.x) ri[i] = val[i];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -630,40 +642,60 @@ __global__ void k_backtrace(Batch b)
 // main >= stay and every column's running best >= each of its main cells, so rows present in only
 // one of the two bands can never beat the two running bests: the maximum over all rows reduces to
 // the rows present in BOTH bands plus the two running bests (and the floor 0).
-// This warp-cooperative form takes explicit band descriptions so it also serves the blank column.
-__device__ __forceinline__ double warp_join(const double* Fm, const double* Fs, int f0, int flen,
-                                            const double* Bm, const double* Bs, int b0, int blen,
-                                            int n0, int lane)
-{
-    // jf in [f0, f0+flen-1], jb = n0-jf+1 in [b0, b0+blen-1]
-    int lo = max(f0, n0 + 1 - (b0 + blen - 1)), hi = min(f0 + flen - 1, n0 + 1 - b0);
-    lo = max(lo, 1); hi = min(hi, n0);
-    double m = 0.0;
-    for (int jf = lo + lane; jf <= hi; jf += 32)
-    {
-        int jb = n0 - jf + 1;
-        double fm = Fm ? Fm[jf - f0] : 0.0, fs = Fs ? Fs[jf - f0] : 0.0;
-        double bm = Bm ? Bm[jb - b0] : 0.0, bs = Bs ? Bs[jb - b0] : 0.0;
-        m = fmax(m, fmax(fm + bm, fs + bs));
-    }
-    for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-    return m;
-}
-
-// k_join: old[g] = columnMax(c) = join(F[c], B[N-c+1]) for every band column; one warp each.
-__global__ void k_join(Batch b)
+//
+// k_join: old[g] = columnMax(c) = join(F[c], B[N-c+1]) for every band column.  A block covers 32
+// consecutive columns (lane = column) with 8 warps that take the anti-diagonals d = c + jf round
+// robin; with the wavefront-major layout a warp's forward cells (diagonal d) and the matching
+// reverse cells (diagonal N+n0+2-d, columns descending) are each one contiguous 256-byte run.
+__global__ void __launch_bounds__(256) k_join(Batch b)
 {
     const EvDesc ev = b.ev[blockIdx.y];
     if (!ev.usable) return;
-    const int lane = threadIdx.x & 31;
-    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5) + 1;
-    if (c > ev.N) return;
-    const long long gf = ev.col_off + c, gb = ev.col_off + (ev.N - c + 1);
-    const int RS = b.RS;
-    double m = warp_join(b.Fm + gf * RS, b.Fs + gf * RS, b.Fi0[gf], b.Flen[gf],
-                         b.Bm + gb * RS, b.Bs + gb * RS, b.Bi0[gb], b.Blen[gb], ev.n0, lane);
-    m = fmax(m, fmax(b.Fbest[gf], b.Bbest[gb]));
-    if (lane == 0) b.old[gf] = m;
+    const int N = ev.N, n0 = ev.n0;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane + 1;
+    const bool have = c <= N;
+    const int cb = N - c + 1;                           // reverse column joined with forward column c
+    int lo = 1, hi = 0;
+    double m = 0.0;
+    long long gf = 0;
+    if (have)
+    {
+        gf = ev.col_off + c;
+        const long long gb = ev.col_off + cb;
+        const int f0 = b.Fi0[gf], flen = b.Flen[gf], b0 = b.Bi0[gb], blen = b.Blen[gb];
+        // jf in [f0, f0+flen-1] and jb = n0-jf+1 in [b0, b0+blen-1]
+        lo = max(max(f0, n0 + 1 - (b0 + blen - 1)), 1);
+        hi = min(min(f0 + flen - 1, n0 + 1 - b0), n0);
+        m = fmax(b.Fbest[gf], b.Bbest[gb]);
+    }
+    // common diagonal range of the 32 columns
+    int dlo = have && lo <= hi ? c + lo : 1 << 30, dhi = have && lo <= hi ? c + hi : -1;
+    for (int o = 16; o; o >>= 1)
+    {
+        dlo = min(dlo, __shfl_xor_sync(0xffffffffu, dlo, o));
+        dhi = max(dhi, __shfl_xor_sync(0xffffffffu, dhi, o));
+    }
+    const int kf = c % ev.ts, kb = cb % ev.ts;
+    for (int d = dlo + w; d <= dhi; d += 8)
+    {
+        const int jf = d - c;
+        if (have && jf >= lo && jf <= hi)
+        {
+            const long long af = ev.band_off + (long long)d * ev.ts + kf;
+            const long long ab = ev.band_off + (long long)(N + n0 + 2 - d) * ev.ts + kb;
+            m = fmax(m, fmax(b.Fm[af] + b.Bm[ab], b.Fs[af] + b.Bs[ab]));
+        }
+    }
+    __shared__ double part[8][32];
+    part[w][lane] = m;
+    __syncthreads();
+    if (w == 0 && have)
+    {
+#pragma unroll
+        for (int q = 1; q < 8; q++) m = fmax(m, part[q][lane]);
+        b.old[gf] = fmax(m, 0.0);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -729,7 +761,7 @@ __device__ __forceinline__ bool task_decode(const Batch& b, long long t, int& e,
 // single-thread join used for the boundary cases (seed column joined directly, blank columns)
 __device__ double thread_join(const Batch& b, const EvDesc& ev, int raf, int rab)
 {
-    const int N = ev.N, n0 = ev.n0, RS = b.RS;
+    const int N = ev.N, n0 = ev.n0;
     raf = min(max(raf, 0), N); rab = min(max(rab, 0), N);
     const long long gf = ev.col_off + raf, gb = ev.col_off + rab;
     int f0 = 0, flen = n0 + 1, b0 = 0, blen = n0 + 1;
@@ -741,8 +773,9 @@ __device__ double thread_join(const Batch& b, const EvDesc& ev, int raf, int rab
     for (int jf = lo; jf <= hi; jf++)
     {
         int jb = n0 - jf + 1;
-        double fm = raf > 0 ? b.Fm[gf * RS + jf - f0] : 0.0, fs = raf > 0 ? b.Fs[gf * RS + jf - f0] : 0.0;
-        double bm = rab > 0 ? b.Bm[gb * RS + jb - b0] : 0.0, bs = rab > 0 ? b.Bs[gb * RS + jb - b0] : 0.0;
+        const long long af = cell_at(ev, raf, jf), ab = cell_at(ev, rab, jb);
+        double fm = raf > 0 ? b.Fm[af] : 0.0, fs = raf > 0 ? b.Fs[af] : 0.0;
+        double bm = rab > 0 ? b.Bm[ab] : 0.0, bs = rab > 0 ? b.Bs[ab] : 0.0;
         m = fmax(m, fmax(fm + bm, fs + bs));
     }
     return m;
@@ -759,7 +792,7 @@ __global__ void __launch_bounds__(128) k_mutscore(Batch b)
     extern __shared__ double ring_smem[];
     const long long nthreads = (long long)gridDim.x * blockDim.x;
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int W = b.scoring_width, RS = b.RS;
+    const int W = b.scoring_width;
     const int S = 2 * W + 2;
     double* ring = SMEM ? ring_smem + threadIdx.x : b.scratch + gtid;
     const long long rstride = SMEM ? blockDim.x : nthreads;       // element r at ring[r * rstride]
@@ -808,7 +841,7 @@ __global__ void __launch_bounds__(128) k_mutscore(Batch b)
                 {
                     const long long gs = ev.col_off + startind;
                     p0 = b.Fi0[gs]; p1 = p0 + b.Flen[gs] - 1;
-                    seed = b.Fm + gs * RS;
+                    seed = b.Fm + ev.band_off + (long long)startind * ev.ts + (startind % ev.ts);   // + row * ts
                     best = b.Fbest[gs];
                 }
                 // reverse column to join with
@@ -817,8 +850,10 @@ __global__ void __launch_bounds__(128) k_mutscore(Batch b)
                 int b0 = 0, blen = n0 + 1;
                 double mb = 0.0;
                 if (rab > 0) { b0 = b.Bi0[gb]; blen = b.Blen[gb]; mb = b.Bbest[gb]; }
-                const double* Bm = b.Bm + gb * RS - b0;          // indexed by reverse row jb
-                const double* Bs = b.Bs + gb * RS - b0;
+                const long long bbase = ev.band_off + (long long)rab * ev.ts + (rab % ev.ts);   // + reverse row * ts
+                const double* Bm = b.Bm + bbase;
+                const double* Bs = b.Bs + bbase;
+                const long long ts = ev.ts;
                 double joinmax = 0.0;
                 for (int c = startind + 1; c <= last; c++)
                 {
@@ -835,14 +870,14 @@ __global__ void __launch_bounds__(128) k_mutscore(Batch b)
                         // (c-1, i0-1): still in its slot, nothing of this column overwrites it
                         double diag = 0.0;
                         if (i0 > p0 && i0 <= p1)
-                            diag = first_col ? (seed ? seed[i0 - 1 - p0] : 0.0) : ring[(long long)((i0 - 1) % S) * rstride];
+                            diag = first_col ? (seed ? seed[(long long)(i0 - 1) * ev.ts] : 0.0) : ring[(long long)((i0 - 1) % S) * rstride];
                         for (int i = i0; i <= i1; i++)
                         {
                             const double e_i = cell_emission<false>(lev, n0, i, sp, b.log2pi, b.lik_offset);
                             const bool skip_ok = i >= p0 && i <= p1;
                             const bool diag_ok = i > p0 && i <= p1;
                             double Pi = 0.0;
-                            if (skip_ok) Pi = first_col ? (seed ? seed[i - p0] : 0.0) : ring[(long long)slot * rstride];
+                            if (skip_ok) Pi = first_col ? (seed ? seed[(long long)i * ev.ts] : 0.0) : ring[(long long)slot * rstride];
                             double C, Sv; int step;
                             dp_cell(i == i0, skip_ok, diag_ok, Pi, diag, e_i, e_i, upC, upS, tr, C, Sv, step);
                             if (C > best) best = C;
@@ -851,7 +886,7 @@ __global__ void __launch_bounds__(128) k_mutscore(Batch b)
                                 const int jb = n0 - i + 1;
                                 if (jb >= b0 && jb < b0 + blen)
                                 {
-                                    const double bm = rab > 0 ? Bm[jb] : 0.0, bs = rab > 0 ? Bs[jb] : 0.0;
+                                    const double bm = rab > 0 ? Bm[jb * ts] : 0.0, bs = rab > 0 ? Bs[jb * ts] : 0.0;
                                     joinmax = fmax(joinmax, fmax(C + bm, Sv + bs));
                                 }
                             }
@@ -871,7 +906,7 @@ __global__ void __launch_bounds__(128) k_mutscore(Batch b)
                                 const int jb = n0 - i + 1;
                                 if (jb >= b0 && jb < b0 + blen)
                                 {
-                                    const double bm = rab > 0 ? Bm[jb] : 0.0, bs = rab > 0 ? Bs[jb] : 0.0;
+                                    const double bm = rab > 0 ? Bm[jb * ts] : 0.0, bs = rab > 0 ? Bs[jb * ts] : 0.0;
                                     joinmax = fmax(joinmax, fmax(bm, bs));
                                 }
                             }

@@ -75,8 +75,10 @@ int ps_ctx::init()
     if (const char* fw = getenv("PORESEQ_B200_FILL_WARPS")) fill_warps = std::min(16, std::max(1, atoi(fw)));
     CU(cudaStreamCreate(&stream));
     for (int i = 0; i <= PS_T_COUNT; i++) CU(cudaEventCreate(&tev[i]));
-    CU(cudaFuncSetAttribute(k_fill<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CU(cudaFuncSetAttribute(k_fill<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(k_backtrace, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
+    CU(cudaFuncSetAttribute(k_fill<352, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CU(cudaFuncSetAttribute(k_fill<640, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CU(cudaFuncSetAttribute(k_fill<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU(cudaFuncSetAttribute(k_mutscore<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     ready = true;
     return PS_OK;
@@ -212,21 +214,69 @@ struct Job
     std::string bases;
     std::vector<LevelRec> lev;
     std::vector<double> ref_align, ref_like, ref_index;
-    std::vector<int> ri_empty, mono;
+    std::vector<int> ri_empty, mono, cen_old, wave_need;
+    int wave_threads = 64;
+    double wide_cells_fwd = 0;
     std::vector<MutDev> mdev;
     std::string mut_str;
     std::vector<int> mut_ev0, mut_nev, mut_local;
-    long long n_levels, n_cols, n_cen, n_tasks, n_muts;
+    long long n_levels, n_cols, n_cen, n_tasks, n_muts, n_band;
     int cen_pad;
     Batch b;
 
-    Job(ps_ctx* c) : ctx(c), want_muts(false), n_levels(0), n_cols(0), n_cen(0), n_tasks(0), n_muts(0), cen_pad(8) {}
+    Job(ps_ctx* c) : ctx(c), want_muts(false), n_levels(0), n_cols(0), n_cen(0), n_tasks(0), n_muts(0), n_band(0), cen_pad(8) {}
 
+    void plan_event(const HostEvent& he, const EvDesc& d);
     int build();
     int upload();
     int run(bool backward_and_muts);
     int download(std::vector<double>* align_scores, std::vector<double>* mut_scores);
 };
+
+// Band centres of the wide fill (cpp/EventData.h:172-183: lower_bound over ref_index; 1 when the
+// event has no alignment, cpp/Alignment.cpp:129-132), whether they are nondecreasing, and the
+// number of threads the wavefront needs so that a thread's next column starts at least 5 steps
+// after its current one ends (fill_wave switches columns only every 4 steps).
+void Job::plan_event(const HostEvent& he, const EvDesc& d)
+{
+    const int N = d.N, n0 = he.n0, rw = regs[0]->params.realign_width;
+    const size_t base = cen_old.size();
+    cen_old.resize(base + N + cen_pad + 1, 1);
+    int ok = 1, need = 64;
+    if (!he.ri_empty)
+        for (int c = 0; c <= N + cen_pad; c++)
+        {
+            const int v = (int)(std::lower_bound(he.ref_index.begin(), he.ref_index.end(), (double)c) - he.ref_index.begin());
+            cen_old[base + c] = v;
+            if (c > 0 && v < cen_old[base + c - 1]) ok = 0;
+        }
+    if (d.usable && ok)
+    {
+        std::vector<int> lo(N + 2), hi(N + 2);
+        for (int dir = 0; dir < 2; dir++)
+        {
+            for (int k = 1; k <= N; k++)
+            {
+                const int c = dir ? N - k + 1 : k;
+                int mid = dir ? n0 - cen_old[base + c] + 1 : cen_old[base + c];
+                mid = std::min(std::max(mid, 1), n0);
+                const int i0 = std::max(1, mid - rw), i1 = std::min(n0, mid + rw);
+                lo[k] = k + i0; hi[k] = k + i1;
+                if (!dir) wide_cells_fwd += i1 - i0 + 1;
+            }
+            int kk = 1;
+            for (int k = 1; k <= N; k++)
+            {
+                if (kk <= k) kk = k + 1;
+                while (kk <= N && lo[kk] < hi[k] + 5) kk++;
+                need = std::max(need, kk - k);
+            }
+        }
+        if (need <= 1024) wave_threads = std::max(wave_threads, need);
+    }
+    mono.push_back(ok);
+    wave_need.push_back(need);
+}
 
 int Job::build()
 {
@@ -317,11 +367,23 @@ int Job::build()
             if (he.ri_empty) ref_index.insert(ref_index.end(), he.n0, 0.0);
             else ref_index.insert(ref_index.end(), he.ref_index.begin(), he.ref_index.end());
             ri_empty.push_back(he.ri_empty ? 1 : 0);
+            plan_event(he, d);
         }
     }
     n_cols += 1;                                  // index 0 of the first event is never used
     n_muts = (long long)mdev.size();
-    mono.assign(ev.size(), 1);
+    // wavefront-major band storage: stride = wavefront width for monotone events (at most that many
+    // columns are live on one anti-diagonal), N+1 for the serially filled ones
+    wave_threads = std::min(std::max(((wave_threads + 31) / 32) * 32, 64), 1024);
+    for (size_t e = 0; e < ev.size(); e++)
+    {
+        EvDesc& d = ev[e];
+        if (!d.usable) { d.ts = 1; d.band_off = n_band; continue; }
+        if (mono[e] && wave_need[e] > wave_threads) mono[e] = 0;
+        d.ts = mono[e] ? wave_threads : d.N + 1;
+        d.band_off = n_band;
+        n_band += (long long)(d.N + d.n0 + 3) * d.ts;
+    }
     return PS_OK;
 }
 
@@ -381,10 +443,10 @@ int Job::upload()
     TRY(room(ctx, "bt_src", (size_t)n_levels, &b.bt_src));
     TRY(room(ctx, "refstart", ev.size(), &b.refstart));
     TRY(room(ctx, "refend", ev.size(), &b.refend));
-    TRY(room(ctx, "cen_old", (size_t)n_cen, &b.cen_old));
+    TRY(up(ctx, "cen_old", cen_old.data(), cen_old.size(), &b.cen_old));
     TRY(room(ctx, "cen_new", (size_t)n_cen, &b.cen_new));
 
-    const size_t cells = (size_t)n_cols * b.RS;
+    const size_t cells = (size_t)std::max<long long>(n_band, 1);
     TRY(room(ctx, "Fm", cells, &b.Fm));
     TRY(room(ctx, "Fs", cells, &b.Fs));
     TRY(room(ctx, "Fstep", cells, &b.Fstep));
@@ -424,26 +486,26 @@ int Job::run(bool full)
     int maxN = 0;
     for (const EvDesc& d : ev) maxN = std::max(maxN, d.N);
     if (nev == 0) return PS_OK;
-    MARK(PS_T_CENTRES);
-    {
-        dim3 grid((maxN + cen_pad + 1 + 127) / 128, nev);
-        k_centres<<<grid, 128, 0, ctx->stream>>>(b, b.cen_old, 1);
-        LAUNCHED();
-    }
+    MARK(PS_T_CENTRES);    // (pre-call band centres are planned on the host, see plan_event)
     MARK(PS_T_FORWARD);
-    // pipelined wavefront fill: NW warps per (event, direction), forward and reverse in one launch
+    // wavefront fill: one CTA per (event, direction), forward and reverse in one launch (grid.y = 2)
     {
-        const int NW = ctx->fill_warps;
-        const size_t smem = ((size_t)NW + (size_t)NW * b.RS * (full ? 2 : 1)) * sizeof(double);
+        const int T = wave_threads;
+        const size_t smem = std::max<size_t>(8 * T, 2 * b.RS) * sizeof(double);
         dim3 grid(nev, full ? 2 : 1);
-        if (smem > 200 * 1024) { ps_set_error(ctx, "realign_width %d needs %zu bytes of shared memory", b.realign_width, smem); return PS_E_ARG; }
-        if (NW <= 8) k_fill<256, 2><<<grid, NW * 32, smem, ctx->stream>>>(b, 0);
-        else k_fill<512, 1><<<grid, NW * 32, smem, ctx->stream>>>(b, 0);
+        if (T <= 352) k_fill<352, 2><<<grid, T, smem, ctx->stream>>>(b, 0);
+        else if (T <= 640) k_fill<640, 1><<<grid, T, smem, ctx->stream>>>(b, 0);
+        else k_fill<1024, 1><<<grid, T, smem, ctx->stream>>>(b, 0);
         LAUNCHED();
     }
     MARK(PS_T_BACKWARD);   // (reverse fill shares the launch above; kept as a phase marker)
     MARK(PS_T_BACKTRACE);
-    k_backtrace<<<nev, 128, 0, ctx->stream>>>(b);
+    {
+        int max_n0 = 0;
+        for (const EvDesc& d : ev) max_n0 = std::max(max_n0, d.n0);
+        int smem_levels = std::min((max_n0 + 1) & ~1, (int)(160 * 1024 / 12) & ~1);   // 8 B value + 4 B source per level
+        k_backtrace<<<nev, 256, (size_t)smem_levels * 12, ctx->stream>>>(b, smem_levels);
+    }
     LAUNCHED();
     MARK(PS_T_JOIN);
     if (full && n_tasks > 0)
@@ -454,8 +516,8 @@ int Job::run(bool full)
             LAUNCHED();
         }
         {
-            dim3 grid((maxN + 3) / 4, nev);
-            k_join<<<grid, 128, 0, ctx->stream>>>(b);
+            dim3 grid((maxN + 31) / 32, nev);
+            k_join<<<grid, 256, 0, ctx->stream>>>(b);
             LAUNCHED();
         }
         MARK(PS_T_MUTSCORE);
