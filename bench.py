@@ -263,7 +263,7 @@ def main():
     achieved_ops = dom_cells * OPS_PER_CELL / (phase_ms[dom] * 1e-3) / 1e12 if phase_ms[dom] > 0 else 0.0
     # algorithmic bytes of the dominant kernel: wide fill writes 2 matrices x 8 B + 1 step byte
     # per cell (forward) / 16 B (reverse); the mutation kernel reads 8 B seed + 16 B join rows per band row
-    dom_bytes = {"forward": wide_cells * 16.5, "mutscore": narrow_cells / 5.875 * 24.0}.get(dom, 0.0)
+    dom_bytes = {"forward": wide_cells * 16.5 + wide_cells / 2 * 0.0, "mutscore": narrow_cells / 5.875 * 24.0}.get(dom, 0.0)
     line = {
         "metric": METRIC, "value": total_cells / (dev_ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": wall_ms, "higher_is_better": True,

@@ -925,15 +925,32 @@ __global__ void __launch_bounds__(128) k_mutscore(Batch b)
 }
 
 // k_reduce: score[m] = -1e-6 + sum_e delta(e, m), events in order (cpp/MakeMutations.cpp:38-52,
-// cpp/AlignUtil.h:84-90).  One thread per mutation; region_ev0/region_nev give its events.
-__global__ void k_reduce(Batch b, const int* mut_ev0, const int* mut_nev, const int* mut_local, long long n_muts)
+// cpp/AlignUtil.h:84-90).  One thread per mutation; the region table gives its events.
+struct RegTabDev { long long mut_off; int ev0, nev; };
+
+__global__ void k_reduce(Batch b, const RegTabDev* regs, int n_regs, long long n_muts)
 {
     long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_muts) return;
+    int lo = 0, hi = n_regs - 1;
+    while (lo < hi)
+    {
+        int mid = (lo + hi + 1) >> 1;
+        if (regs[mid].mut_off <= g) lo = mid; else hi = mid - 1;
+    }
+    const int m = (int)(g - regs[lo].mut_off);
     double s = -1e-6;
-    const int e0 = mut_ev0[g], ne = mut_nev[g], m = mut_local[g];
-    for (int e = e0; e < e0 + ne; e++) s += b.delta[b.ev[e].task_off + m];
+    for (int e = regs[lo].ev0; e < regs[lo].ev0 + regs[lo].nev; e++) s += b.delta[b.ev[e].task_off + m];
     b.scores[g] = s;
+}
+
+// per-event alignment score = running best of the last forward column (cpp/Alignment.h:127-130)
+__global__ void k_event_scores(Batch b, double* out)
+{
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= b.n_events) return;
+    const EvDesc ev = b.ev[e];
+    out[e] = (ev.usable && ev.N > 0) ? b.Fbest[ev.col_off + ev.N] : 0.0;
 }
 
 } // namespace psdev

@@ -6,6 +6,7 @@
 // There is deliberately no CPU implementation of the DP here: if CUDA is unavailable every compute
 // entry point fails with PS_E_CUDA.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -108,11 +109,34 @@ int ps_ctx::ensure(DevBuf& b, size_t bytes)
     return PS_OK;
 }
 
+bool ps_pin_reserve(PinBuf* b, size_t bytes, size_t keep)
+{
+    if (bytes <= b->cap) return true;
+    size_t want = bytes + bytes / 2 + 4096;
+    void* q = nullptr;
+    if (cudaHostAlloc(&q, want, cudaHostAllocDefault) != cudaSuccess)
+    {
+        cudaGetLastError();
+        q = malloc(want);                       // pageable staging still works, only slower
+        if (!q) return false;
+        if (b->p && keep) memcpy(q, b->p, keep);
+        // pageable blocks are leaked into the context map as cap with the low bit set
+        if (b->p) { if (b->cap & 1) free(b->p); else cudaFreeHost(b->p); }
+        b->p = q; b->cap = want | 1;
+        return true;
+    }
+    if (b->p && keep) memcpy(q, b->p, keep);
+    if (b->p) { if (b->cap & 1) free(b->p); else cudaFreeHost(b->p); }
+    b->p = q; b->cap = want & ~(size_t)1;
+    return true;
+}
+
 ps_ctx::~ps_ctx()
 {
     if (!ready) return;
     cudaSetDevice(device);
     for (auto& kv : bufs) if (kv.second.p) cudaFree(kv.second.p);
+    for (auto& kv : pins) if (kv.second.p) { if (kv.second.cap & 1) free(kv.second.p); else cudaFreeHost(kv.second.p); }
     for (int i = 0; i <= PS_T_COUNT; i++) cudaEventDestroy(tev[i]);
     cudaStreamDestroy(stream);
 }
@@ -200,31 +224,50 @@ void ps_build_model(const HostModel& hm, ModelDev& md)     // cpp/EventData.h:48
 
 // ------------------------------------------------------------------------------------------
 // Job: one launch sequence over a batch of regions
+struct MutSpec                      // the mutations of one region: an explicit list or every point edit
+{
+    const std::vector<HostMut>* list = nullptr;
+    bool points = false;
+};
+
+struct RegTab { long long mut_off; int ev0, nev; };   // per region: first mutation, its events
+
 struct Job
 {
     ps_ctx* ctx;
     std::vector<ps_region*> regs;
-    std::vector<std::vector<HostMut>> muts;      // per region (empty for alignment-only jobs)
+    std::vector<MutSpec> muts;                   // per region (empty for alignment-only jobs)
     bool want_muts;
 
-    // host staging
-    std::vector<EvDesc> ev;
+    // host staging (pinned, owned by the context)
+    PinVec<EvDesc> ev;
+    PinVec<int> states;
+    PinVec<char> bases;
+    PinVec<LevelRec> lev;
+    PinVec<double> ref_align, ref_like, ref_index;
+    PinVec<int> ri_empty, mono, cen_old;
+    PinVec<MutDev> mdev;
+    PinVec<char> mut_str;
+    PinVec<RegTab> regtab;
     std::vector<const HostModel*> model_src;
-    std::vector<int> states;
-    std::string bases;
-    std::vector<LevelRec> lev;
-    std::vector<double> ref_align, ref_like, ref_index;
-    std::vector<int> ri_empty, mono, cen_old, wave_need;
+    std::vector<int> wave_need, plan_lo, plan_hi;
+    std::vector<double> narrow_cols;             // per region: sum over its mutations of (|mut|+5)
     int wave_threads = 64;
-    double wide_cells_fwd = 0;
-    std::vector<MutDev> mdev;
-    std::string mut_str;
-    std::vector<int> mut_ev0, mut_nev, mut_local;
+    double wide_cells_fwd = 0, narrow_cells = 0;
     long long n_levels, n_cols, n_cen, n_tasks, n_muts, n_band;
     int cen_pad;
     Batch b;
+    RegTab* d_regtab = nullptr;
+    double* d_evbest = nullptr;
 
-    Job(ps_ctx* c) : ctx(c), want_muts(false), n_levels(0), n_cols(0), n_cen(0), n_tasks(0), n_muts(0), n_band(0), cen_pad(8) {}
+    Job(ps_ctx* c) : ctx(c), want_muts(false), n_levels(0), n_cols(0), n_cen(0), n_tasks(0), n_muts(0), n_band(0), cen_pad(8)
+    {
+        ev = c->pinned<EvDesc>("ev"); states = c->pinned<int>("states"); bases = c->pinned<char>("bases");
+        lev = c->pinned<LevelRec>("lev"); ref_align = c->pinned<double>("ref_align");
+        ref_like = c->pinned<double>("ref_like"); ref_index = c->pinned<double>("ref_index");
+        ri_empty = c->pinned<int>("ri_empty"); mono = c->pinned<int>("mono"); cen_old = c->pinned<int>("cen_old");
+        mdev = c->pinned<MutDev>("mdev"); mut_str = c->pinned<char>("mut_str"); regtab = c->pinned<RegTab>("regtab");
+    }
 
     void plan_event(const HostEvent& he, const EvDesc& d);
     int build();
@@ -241,18 +284,35 @@ void Job::plan_event(const HostEvent& he, const EvDesc& d)
 {
     const int N = d.N, n0 = he.n0, rw = regs[0]->params.realign_width;
     const size_t base = cen_old.size();
-    cen_old.resize(base + N + cen_pad + 1, 1);
+    cen_old.fill((size_t)N + cen_pad + 1, 1);
     int ok = 1, need = 64;
     if (!he.ri_empty)
-        for (int c = 0; c <= N + cen_pad; c++)
+    {
+        const std::vector<double>& ri = he.ref_index;
+        bool sorted = true;
+        for (int i = 1; i < n0 && sorted; i++) sorted = !(ri[i] < ri[i - 1]);
+        if (sorted)
         {
-            const int v = (int)(std::lower_bound(he.ref_index.begin(), he.ref_index.end(), (double)c) - he.ref_index.begin());
-            cen_old[base + c] = v;
-            if (c > 0 && v < cen_old[base + c - 1]) ok = 0;
+            // on sorted data lower_bound is "first element >= c": one linear merge for all columns
+            int idx = 0;
+            for (int c = 0; c <= N + cen_pad; c++)
+            {
+                while (idx < n0 && ri[idx] < (double)c) idx++;
+                cen_old[base + c] = idx;
+            }
         }
+        else
+            for (int c = 0; c <= N + cen_pad; c++)
+            {
+                const int v = (int)(std::lower_bound(ri.begin(), ri.end(), (double)c) - ri.begin());
+                cen_old[base + c] = v;
+                if (c > 0 && v < cen_old[base + c - 1]) ok = 0;
+            }
+    }
     if (d.usable && ok)
     {
-        std::vector<int> lo(N + 2), hi(N + 2);
+        plan_lo.resize(N + 2); plan_hi.resize(N + 2);
+        std::vector<int>& lo = plan_lo; std::vector<int>& hi = plan_hi;
         for (int dir = 0; dir < 2; dir++)
         {
             for (int k = 1; k <= N; k++)
@@ -297,33 +357,70 @@ int Job::build()
     }
     // longest net insertion decides how far past N the post-backtrace centre table must reach
     cen_pad = 8;
-    if (want_muts)
-        for (size_t r = 0; r < regs.size(); r++)
-            for (const HostMut& m : muts[r])
+    size_t tot_levels = 0, tot_states = 0, tot_bases = 0, tot_events = 0, tot_muts = 0;
+    for (size_t r = 0; r < regs.size(); r++)
+    {
+        if (want_muts && muts[r].list)
+            for (const HostMut& m : *muts[r].list)
                 cen_pad = std::max(cen_pad, (int)m.mut.size() - (int)m.orig.size() + 8);
+        for (const HostEvent& he : regs[r]->events) tot_levels += he.n0;
+        tot_states += regs[r]->states.size(); tot_bases += regs[r]->bases.size(); tot_events += regs[r]->events.size();
+        if (want_muts) tot_muts += muts[r].points ? regs[r]->states.size() * 8 : muts[r].list->size();
+    }
+    if (!lev.reserve(tot_levels) || !ref_align.reserve(tot_levels) || !ref_like.reserve(tot_levels) ||
+        !ref_index.reserve(tot_levels) || !states.reserve(tot_states) || !bases.reserve(tot_bases) ||
+        !ev.reserve(tot_events) || !mdev.reserve(tot_muts) || !ri_empty.reserve(tot_events) ||
+        !mono.reserve(tot_events) || !cen_old.reserve(tot_events * 64 + tot_states * 2) || !regtab.reserve(regs.size()))
+    {
+        ps_set_error(ctx, "out of host memory staging the batch");
+        return PS_E_INTERNAL;
+    }
+    mut_str.append("ACGT", 4);                  // single-base replacement strings live at offsets 0..3
 
     for (size_t r = 0; r < regs.size(); r++)
     {
         ps_region* R = regs[r];
         const long long state_off = (long long)states.size();
         const long long base_off = (long long)bases.size();
-        states.insert(states.end(), R->states.begin(), R->states.end());
-        bases += R->bases;
+        states.append(R->states.data(), R->states.size());
+        bases.append(R->bases.data(), R->bases.size());
         const long long mut_off = (long long)mdev.size();
-        const int nm = want_muts ? (int)muts[r].size() : 0;
         const int ev0 = (int)ev.size();
-        for (int m = 0; m < nm; m++)
+        double cols = 0;
+        if (want_muts && muts[r].points)
         {
-            const HostMut& hm = muts[r][m];
-            MutDev d;
-            d.start = hm.start; d.n_orig = (int)hm.orig.size(); d.n_mut = (int)hm.mut.size();
-            d.str_off = (int)mut_str.size();
-            mut_str += hm.mut;
-            mdev.push_back(d);
-            mut_ev0.push_back(ev0);
-            mut_nev.push_back((int)R->events.size());
-            mut_local.push_back(m);
+            // FindPointMutations order (cpp/FindMutations.cpp:191-234): del, 3 subs, 4 ins per state
+            for (int i = 0; i < (int)R->states.size(); i++)
+            {
+                const char here = R->bases[i];
+                MutDev d;
+                d.start = i; d.n_orig = 1; d.n_mut = 0; d.str_off = 0;
+                mdev.push_back(d);
+                d.n_mut = 1;
+                int nsub = 0;                    // 3, or 4 for a non-ACGT base
+                for (int j = 0; j < 4; j++)
+                    if ("ACGT"[j] != here) { d.str_off = j; mdev.push_back(d); nsub++; }
+                d.n_orig = 0;
+                for (int j = 0; j < 4; j++) { d.str_off = j; mdev.push_back(d); }
+                cols += 5 + 6.0 * nsub + 6.0 * 4;
+            }
         }
+        else if (want_muts)
+        {
+            for (const HostMut& hm : *muts[r].list)
+            {
+                MutDev d;
+                d.start = hm.start; d.n_orig = (int)hm.orig.size(); d.n_mut = (int)hm.mut.size();
+                d.str_off = (int)mut_str.size();
+                mut_str.append(hm.mut.data(), hm.mut.size());
+                mdev.push_back(d);
+                if (!((size_t)hm.start > R->bases.size())) cols += (double)hm.mut.size() + 5;
+            }
+        }
+        const int nm = (int)(mdev.size() - mut_off);
+        narrow_cols.push_back(cols);
+        RegTab rt; rt.mut_off = mut_off; rt.ev0 = ev0; rt.nev = (int)R->events.size();
+        regtab.push_back(rt);
         for (size_t k = 0; k < R->events.size(); k++)
         {
             const HostEvent& he = R->events[k];
@@ -354,20 +451,14 @@ int Job::build()
             n_cen += d.N + cen_pad + 1;
             n_tasks += nm;
             ev.push_back(d);
-            for (int i = 0; i < he.n0; i++)
-            {
-                LevelRec lr;
-                lr.mean = he.mean[i]; lr.stdv = he.stdv[i];
-                lr.rstdv = 1.0 / he.stdv[i];
-                lr.lsd3 = 3 * he.log_stdv[i];
-                lev.push_back(lr);
-            }
-            ref_align.insert(ref_align.end(), he.ref_align.begin(), he.ref_align.end());
-            ref_like.insert(ref_like.end(), he.ref_like.begin(), he.ref_like.end());
-            if (he.ri_empty) ref_index.insert(ref_index.end(), he.n0, 0.0);
-            else ref_index.insert(ref_index.end(), he.ref_index.begin(), he.ref_index.end());
+            lev.append((const LevelRec*)he.levrec.data(), (size_t)he.n0);
+            ref_align.append(he.ref_align.data(), he.ref_align.size());
+            ref_like.append(he.ref_like.data(), he.ref_like.size());
+            if (he.ri_empty) ref_index.fill(he.n0, 0.0);
+            else ref_index.append(he.ref_index.data(), he.ref_index.size());
             ri_empty.push_back(he.ri_empty ? 1 : 0);
             plan_event(he, d);
+            if (d.usable && want_muts) narrow_cells += cols * std::min(he.n0, 2 * R->params.scoring_width + 1);
         }
     }
     n_cols += 1;                                  // index 0 of the first event is never used
@@ -467,10 +558,12 @@ int Job::upload()
         TRY(room(ctx, "Bcbi", (size_t)n_cols, &b.Bcbi));
         TRY(room(ctx, "Bbest", (size_t)n_cols, &b.Bbest));
         TRY(room(ctx, "old", (size_t)n_cols, &b.old));
-        MutDev* d_m; char* d_ms;
+        MutDev* d_m; char* d_ms; RegTab* d_rt;
         TRY(up(ctx, "muts", mdev.data(), mdev.size(), &d_m));
         TRY(up(ctx, "mut_str", mut_str.data(), mut_str.size(), &d_ms));
+        TRY(up(ctx, "regtab", regtab.data(), regtab.size(), &d_rt));
         b.muts = d_m; b.mut_str = d_ms;
+        d_regtab = d_rt;
         TRY(room(ctx, "delta", (size_t)n_tasks, &b.delta));
         TRY(room(ctx, "scores", (size_t)n_muts, &b.scores));
     }
@@ -543,15 +636,14 @@ int Job::run(bool full)
         }
         MARK(PS_T_REDUCE);
         {
-            int *d_e0, *d_ne, *d_ml;
-            TRY(up(ctx, "mut_ev0", mut_ev0.data(), mut_ev0.size(), &d_e0));
-            TRY(up(ctx, "mut_nev", mut_nev.data(), mut_nev.size(), &d_ne));
-            TRY(up(ctx, "mut_local", mut_local.data(), mut_local.size(), &d_ml));
-            k_reduce<<<(unsigned)((n_muts + 127) / 128), 128, 0, ctx->stream>>>(b, d_e0, d_ne, d_ml, n_muts);
+            k_reduce<<<(unsigned)((n_muts + 127) / 128), 128, 0, ctx->stream>>>(b, (const RegTabDev*)d_regtab, (int)regs.size(), n_muts);
             LAUNCHED();
         }
     }
     else { MARK(PS_T_MUTSCORE); MARK(PS_T_REDUCE); }
+    TRY(room(ctx, "evbest", ev.size(), &d_evbest));
+    k_event_scores<<<(nev + 127) / 128, 128, 0, ctx->stream>>>(b, d_evbest);
+    LAUNCHED();
     MARK(PS_T_D2H);
     return PS_OK;
 }
@@ -559,7 +651,13 @@ int Job::run(bool full)
 int Job::download(std::vector<double>* align_scores, std::vector<double>* mut_scores)
 {
     const size_t nl = (size_t)n_levels, ne = ev.size();
-    std::vector<int> rs(ne), re(ne);
+    PinVec<int> rs = ctx->pinned<int>("refstart"), re = ctx->pinned<int>("refend");
+    PinVec<double> best = ctx->pinned<double>("evbest"), msc = ctx->pinned<double>("mscores");
+    if (!rs.resize(ne) || !re.resize(ne) || !best.resize(ne) || !msc.resize((size_t)n_muts))
+    {
+        ps_set_error(ctx, "out of host memory staging the results");
+        return PS_E_INTERNAL;
+    }
     if (nl)
     {
         CU(cudaMemcpyAsync(ref_align.data(), b.ref_align, nl * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -571,18 +669,11 @@ int Job::download(std::vector<double>* align_scores, std::vector<double>* mut_sc
         CU(cudaMemcpyAsync(ri_empty.data(), b.ri_empty, ne * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaMemcpyAsync(rs.data(), b.refstart, ne * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaMemcpyAsync(re.data(), b.refend, ne * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(best.data(), d_evbest, ne * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     }
-    std::vector<double> best(ne, 0.0);
-    if (align_scores)
-        for (size_t e = 0; e < ne; e++)
-            if (ev[e].usable && ev[e].N > 0)
-                CU(cudaMemcpyAsync(&best[e], b.Fbest + ev[e].col_off + ev[e].N, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    if (mut_scores)
-    {
-        mut_scores->assign((size_t)n_muts, -1e-6);
-        if (n_muts && n_tasks)
-            CU(cudaMemcpyAsync(mut_scores->data(), b.scores, (size_t)n_muts * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    }
+    const bool have_scores = mut_scores && n_muts && n_tasks;
+    if (have_scores)
+        CU(cudaMemcpyAsync(msc.data(), b.scores, (size_t)n_muts * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     MARK(PS_T_TOTAL);
     CU(cudaStreamSynchronize(ctx->stream));
     // scatter the realigned events back into their regions
@@ -593,12 +684,12 @@ int Job::download(std::vector<double>* align_scores, std::vector<double>* mut_sc
             const EvDesc& d = ev[e];
             if (d.usable)
             {
-                std::copy(ref_align.begin() + d.lev_off, ref_align.begin() + d.lev_off + d.n0, he.ref_align.begin());
-                std::copy(ref_like.begin() + d.lev_off, ref_like.begin() + d.lev_off + d.n0, he.ref_like.begin());
+                std::copy(ref_align.data() + d.lev_off, ref_align.data() + d.lev_off + d.n0, he.ref_align.begin());
+                std::copy(ref_like.data() + d.lev_off, ref_like.data() + d.lev_off + d.n0, he.ref_like.begin());
                 he.ri_empty = ri_empty[e] != 0;
                 he.refstart = rs[e]; he.refend = re[e];
                 if (he.ri_empty) he.ref_index.clear();
-                else he.ref_index.assign(ref_index.begin() + d.lev_off, ref_index.begin() + d.lev_off + d.n0);
+                else he.ref_index.assign(ref_index.data() + d.lev_off, ref_index.data() + d.lev_off + d.n0);
             }
             e++;
         }
@@ -607,7 +698,13 @@ int Job::download(std::vector<double>* align_scores, std::vector<double>* mut_sc
         align_scores->resize(ne);
         for (size_t k = 0; k < ne; k++) (*align_scores)[k] = std::max(best[k], 0.0);   // cpp/Alignment.h:127-130
     }
-    // timings + algorithmic cell counts
+    if (mut_scores)
+    {
+        if (have_scores) mut_scores->assign(msc.data(), msc.data() + n_muts);
+        else mut_scores->assign((size_t)n_muts, -1e-6);
+    }
+    // timings + algorithmic cell counts (wide = band cells of the usable events, both
+    // directions when the reverse fill ran; narrow = (|mut|+5) x band rows per (mutation, usable event))
     for (int i = 0; i < PS_T_TOTAL; i++)
     {
         float ms = 0;
@@ -617,64 +714,38 @@ int Job::download(std::vector<double>* align_scores, std::vector<double>* mut_sc
     float tot = 0;
     cudaEventElapsedTime(&tot, ctx->tev[PS_T_H2D], ctx->tev[PS_T_TOTAL]);
     ctx->timing[PS_T_TOTAL] = tot;
+    ctx->wide_cells = want_muts ? 2 * wide_cells_fwd : wide_cells_fwd;
+    ctx->narrow_cells = narrow_cells;
     return PS_OK;
-}
-
-// algorithmic DP cells: wide = sum over usable events and columns of the band
-// length; narrow = (|mut|+5) * band rows per (mutation, usable event) pair.  Computed on the host
-// from the same band rules the kernels use, with the event's pre-call alignment (the definition
-// is about problem size, not about what was executed).
-static void count_cells(const Job& job, bool full, double* wide, double* narrow)
-{
-    *wide = 0; *narrow = 0;
-    size_t e = 0;
-    for (size_t r = 0; r < job.regs.size(); r++)
-    {
-        const ps_region* R = job.regs[r];
-        const int N = (int)R->states.size();
-        const int rw = R->params.realign_width, sw = R->params.scoring_width;
-        for (const HostEvent& he : R->events)
-        {
-            const EvDesc& d = job.ev[e++];
-            if (!d.usable) continue;
-            double w = 0;
-            const int n0 = he.n0;
-            for (int c = 1; c <= N; c++)
-            {
-                int mid = (int)(std::lower_bound(he.ref_index.begin(), he.ref_index.end(), (double)c) - he.ref_index.begin());
-                mid = std::min(std::max(mid, 1), n0);
-                w += std::min(n0, mid + rw) - std::max(1, mid - rw) + 1;
-            }
-            *wide += full ? 2 * w : w;
-            if (full)
-            {
-                const double rows = std::min(n0, 2 * sw + 1);
-                for (const HostMut& m : job.muts[r])
-                    if (!((size_t)m.start > R->bases.size())) *narrow += (double)(m.mut.size() + 5) * rows;
-            }
-        }
-    }
 }
 
 // ------------------------------------------------------------------------------------------
 // drivers shared by the C entry points
-static int run_job(ps_ctx* ctx, std::vector<ps_region*> regs, std::vector<std::vector<HostMut>>* muts,
+static int run_job(ps_ctx* ctx, const std::vector<ps_region*>& regs, const std::vector<MutSpec>* muts,
                    std::vector<double>* align_scores, std::vector<double>* mut_scores)
 {
     TRY(ctx->init());
     CU(cudaSetDevice(ctx->device));
     for (ps_region* R : regs)
         if (R->bases.size() < 5) { ps_set_error(ctx, "sequences shorter than 5 bases are not supported"); return PS_E_ARG; }
+    const bool trace = getenv("PORESEQ_B200_TRACE") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     Job job(ctx);
     job.regs = regs;
     job.want_muts = muts != nullptr;
     if (muts) job.muts = *muts;
     TRY(job.build());
+    const double t1 = now();
     MARK(PS_T_H2D);
     TRY(job.upload());
+    const double t2 = now();
     TRY(job.run(muts != nullptr));
+    const double t3 = now();
     TRY(job.download(align_scores, mut_scores));
-    count_cells(job, muts != nullptr, &ctx->wide_cells, &ctx->narrow_cells);
+    const double t4 = now();
+    if (trace) fprintf(stderr, "[ps] build %.2f ms  upload(enqueue) %.2f  run(enqueue) %.2f  download+sync+scatter %.2f  (device %.2f)\n",
+                       t1 - t0, t2 - t1, t3 - t2, t4 - t3, ctx->timing[PS_T_TOTAL]);
     return PS_OK;
 }
 
@@ -735,7 +806,8 @@ std::vector<HostMut> ps_point_mutations(const ps_region* R)      // cpp/FindMuta
 
 int ps_score_mutation_list(ps_region* R, std::vector<HostMut>& muts)
 {
-    std::vector<std::vector<HostMut>> per(1, muts);
+    std::vector<MutSpec> per(1);
+    per[0].list = &muts;
     std::vector<double> sc;
     TRY(run_job(R->ctx, std::vector<ps_region*>(1, R), &per, nullptr, &sc));
     for (size_t i = 0; i < muts.size(); i++) muts[i].score = sc[i];
@@ -867,7 +939,14 @@ int ps_region_add_event(ps_region* R, int n0, const double* mean, const double* 
     he.ref_align.assign(ref_align, ref_align + n0);
     he.ref_like.assign(ref_like, ref_like + n0);
     he.log_stdv.resize(n0);
-    for (int i = 0; i < n0; i++) he.log_stdv[i] = std::log(he.stdv[i]);      // cpp/EventData.h:218-220
+    he.levrec.resize((size_t)n0 * 4);
+    for (int i = 0; i < n0; i++)
+    {
+        he.log_stdv[i] = std::log(he.stdv[i]);                               // cpp/EventData.h:218-220
+        // device level record: mean, stdv, RN(1/stdv), 3*log(stdv)  (psdev::LevelRec)
+        he.levrec[4 * i] = he.mean[i]; he.levrec[4 * i + 1] = he.stdv[i];
+        he.levrec[4 * i + 2] = 1.0 / he.stdv[i]; he.levrec[4 * i + 3] = 3 * he.log_stdv[i];
+    }
     if (seq2d) he.seq2d = seq2d;
     he.update_refs();
     R->events.push_back(std::move(he));
@@ -954,13 +1033,28 @@ int ps_find_point_mutations(ps_region* R, int cap, int* n, int* start, char* ori
     return emit_points(R->ctx, ps_point_mutations(R), cap, n, start, orig, mut, nullptr);
 }
 
-int ps_score_points(ps_region* R, int cap, int* n, int* start, char* orig, char* mut, double* scores)
+// Enumerates the point edits of one region in FindPointMutations order straight into the flat
+// output arrays (no per-edit objects), returning how many there are.
+static long long write_points(const ps_region* R, long long at, long long cap, int* start, char* orig, char* mut)
 {
-    if (!R) return PS_E_ARG;
-    std::vector<HostMut> v = ps_point_mutations(R);
-    if ((int)v.size() > cap) { if (n) *n = (int)v.size(); ps_set_error(R->ctx, "output capacity too small"); return PS_E_CAPACITY; }
-    TRY(ps_score_mutation_list(R, v));
-    return emit_points(R->ctx, v, cap, n, start, orig, mut, scores);
+    long long n = 0;
+    for (int i = 0; i < (int)R->states.size(); i++)
+    {
+        const char here = R->bases[i];
+        for (int kind = 0; kind < 9; kind++)
+        {
+            // kind 0: deletion; 1..4: substitution by ACGT[kind-1] (skipping the base itself); 5..8: insertion
+            if (kind >= 1 && kind <= 4 && "ACGT"[kind - 1] == here) continue;
+            if (at + n < cap)
+            {
+                if (start) start[at + n] = i;
+                if (orig) orig[at + n] = kind <= 4 ? here : 0;
+                if (mut) mut[at + n] = kind == 0 ? 0 : "ACGT"[(kind - 1) & 3];
+            }
+            n++;
+        }
+    }
+    return n;
 }
 
 int ps_score_points_batch(ps_region* const* regions, int n_regions, int cap, int* n_out, long long* off_out,
@@ -969,31 +1063,33 @@ int ps_score_points_batch(ps_region* const* regions, int n_regions, int cap, int
     if (!regions || n_regions <= 0) return PS_E_ARG;
     ps_ctx* ctx = regions[0]->ctx;
     std::vector<ps_region*> regs(regions, regions + n_regions);
-    std::vector<std::vector<HostMut>> per(n_regions);
-    long long total = 0;
-    for (int r = 0; r < n_regions; r++)
-    {
-        if (regs[r]->ctx != ctx) { ps_set_error(ctx, "all regions of a batch must belong to one context"); return PS_E_ARG; }
-        per[r] = ps_point_mutations(regs[r]);
-        total += (long long)per[r].size();
-    }
-    if (total > cap) { ps_set_error(ctx, "output capacity %d < %lld point mutations", cap, total); return PS_E_CAPACITY; }
-    std::vector<double> sc;
-    TRY(run_job(ctx, regs, &per, nullptr, &sc));
+    std::vector<MutSpec> per(n_regions);
     long long at = 0;
     for (int r = 0; r < n_regions; r++)
     {
-        if (n_out) n_out[r] = (int)per[r].size();
+        if (!regs[r] || regs[r]->ctx != ctx) { ps_set_error(ctx, "all regions of a batch must belong to one context"); return PS_E_ARG; }
+        per[r].points = true;
+        const long long n = write_points(regs[r], at, cap, start, orig, mut);
+        if (n_out) n_out[r] = (int)n;
         if (off_out) off_out[r] = at;
-        for (size_t i = 0; i < per[r].size(); i++, at++)
-        {
-            if (start) start[at] = per[r][i].start;
-            if (orig) orig[at] = per[r][i].orig.empty() ? 0 : per[r][i].orig[0];
-            if (mut) mut[at] = per[r][i].mut.empty() ? 0 : per[r][i].mut[0];
-            if (scores) scores[at] = sc[at];
-        }
+        at += n;
     }
+    if (at > cap) { ps_set_error(ctx, "output capacity %d < %lld point mutations", cap, at); return PS_E_CAPACITY; }
+    std::vector<double> sc;
+    TRY(run_job(ctx, regs, &per, nullptr, &sc));
+    if (scores) std::copy(sc.begin(), sc.end(), scores);
     return PS_OK;
+}
+
+int ps_score_points(ps_region* R, int cap, int* n, int* start, char* orig, char* mut, double* scores)
+{
+    if (!R) return PS_E_ARG;
+    int count = 0;
+    long long off = 0;
+    ps_region* one = R;
+    int rc = ps_score_points_batch(&one, 1, cap, &count, &off, start, orig, mut, scores);
+    if (n) *n = count;
+    return rc;
 }
 
 int ps_make_mutations(ps_region* R, int n, const int* start, const char* const* orig, const char* const* mut,

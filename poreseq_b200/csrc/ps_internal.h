@@ -1,5 +1,6 @@
 // ps_internal.h -- host-side objects behind the opaque handles of include/poreseq_b200.h.
 #pragma once
+#include <cstring>
 #include <map>
 #include <string>
 #include <vector>
@@ -9,6 +10,28 @@
 #include "../../include/poreseq_b200.h"
 
 struct DevBuf { void* p = nullptr; size_t cap = 0; };
+
+// Growable array in pinned host memory (owned by the context, reused across calls): the staging
+// area the H2D / D2H copies run from at full PCIe rate.
+struct PinBuf { void* p = nullptr; size_t cap = 0; };
+template <class T>
+struct PinVec
+{
+    PinBuf* buf = nullptr;
+    size_t n = 0;
+    T* data() const { return (T*)buf->p; }
+    size_t size() const { return n; }
+    T& operator[](size_t i) const { return ((T*)buf->p)[i]; }
+    T* begin() const { return (T*)buf->p; }
+    T* end() const { return (T*)buf->p + n; }
+    bool reserve(size_t count);                 // false on allocation failure
+    bool resize(size_t count) { if (!reserve(count)) return false; n = count; return true; }
+    void push_back(const T& v) { if (n + 1 > buf->cap / sizeof(T)) reserve((n + 1) * 2); ((T*)buf->p)[n++] = v; }
+    void append(const T* src, size_t count) { reserve(n + count); memcpy((T*)buf->p + n, src, count * sizeof(T)); n += count; }
+    void fill(size_t count, const T& v) { reserve(n + count); for (size_t i = 0; i < count; i++) ((T*)buf->p)[n + i] = v; n += count; }
+};
+bool ps_pin_reserve(PinBuf* b, size_t bytes, size_t keep);
+template <class T> bool PinVec<T>::reserve(size_t count) { return ps_pin_reserve(buf, count * sizeof(T), n * sizeof(T)); }
 
 struct ps_ctx
 {
@@ -23,6 +46,8 @@ struct ps_ctx
     long long launches = 0;
     std::string error;
     std::map<std::string, DevBuf> bufs;       // grow-only named device buffers, reused across calls
+    std::map<std::string, PinBuf> pins;       // grow-only named pinned host buffers
+    template <class T> PinVec<T> pinned(const char* name) { PinVec<T> v; v.buf = &pins[name]; v.n = 0; return v; }
 
     int init();                               // lazy CUDA initialisation
     int ensure(DevBuf& b, size_t bytes);
@@ -43,6 +68,7 @@ struct HostEvent                              // cpp/EventData.h:78-229
     bool ri_empty = true;
     int refstart = -1, refend = -1;
     std::vector<double> mean, stdv, log_stdv, ref_align, ref_like, ref_index;
+    std::vector<double> levrec;               // 4 doubles per level, the device LevelRec layout
     std::string seq2d;
     void update_refs();
 };

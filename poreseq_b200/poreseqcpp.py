@@ -54,7 +54,7 @@ def lib():
     L.ps_region_create.restype = C.c_void_p
     L.ps_region_create.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(PSParams)]
     L.ps_region_destroy.argtypes = [C.c_void_p]
-    L.ps_region_add_event.argtypes = [C.c_void_p, C.c_int] + [_c_double_p] * 8 + [C.c_int] + [C.c_double] * 4 + [C.c_char_p]
+    L.ps_region_add_event.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 8 + [C.c_int] + [C.c_double] * 4 + [C.c_char_p]
     L.ps_region_set_params.argtypes = [C.c_void_p, C.POINTER(PSParams)]
     L.ps_region_num_events.argtypes = [C.c_void_p]
     L.ps_region_sequence_length.argtypes = [C.c_void_p]
@@ -136,8 +136,17 @@ def _dp(a):
     return a.ctypes.data_as(_c_double_p)
 
 
+_F8 = np.dtype("f8")
+
+
 def _f8(a):
+    if type(a) is np.ndarray and a.dtype == _F8 and a.flags.c_contiguous:
+        return a
     return np.ascontiguousarray(a, dtype="f8")
+
+
+def _addr(a):
+    return a.__array_interface__["data"][0]
 
 
 def _cstrs(items):
@@ -170,16 +179,14 @@ class NativeRegion(object):
             raise RuntimeError("ps_region_create failed: %s" % L.ps_last_error(ctx.handle).decode())
         self.n_levels = []
         for ev in events:
-            if hasattr(ev, "makecontiguous"):
-                ev.makecontiguous()
             mean, stdv, ra, rl = _f8(ev.mean), _f8(ev.stdv), _f8(ev.ref_align), _f8(ev.ref_like)
             m = ev.model
             lm, ls, sm, ss = _f8(m.level_mean), _f8(m.level_stdv), _f8(m.sd_mean), _f8(m.sd_stdv)
             if not (len(stdv) == len(ra) == len(rl) == len(mean)) or min(len(lm), len(ls), len(sm), len(ss)) < 1024:
                 raise ValueError("event arrays must have equal length and models 1024 states")
             seq2d = getattr(ev, "sequence", "") or ""
-            ctx.check(L.ps_region_add_event(self.handle, len(mean), _dp(mean), _dp(stdv), _dp(ra), _dp(rl),
-                                            _dp(lm), _dp(ls), _dp(sm), _dp(ss), int(bool(m.complement)),
+            ctx.check(L.ps_region_add_event(self.handle, len(mean), _addr(mean), _addr(stdv), _addr(ra), _addr(rl),
+                                            _addr(lm), _addr(ls), _addr(sm), _addr(ss), int(bool(m.complement)),
                                             float(m.prob_skip), float(m.prob_stay), float(m.prob_extend),
                                             float(m.prob_insert), seq2d.encode("ascii")))
             self.n_levels.append(len(mean))
