@@ -105,6 +105,11 @@ int         ps_score_alignments(ps_region* r, double* scores, double* likes);
  * cpp/MakeMutations.cpp:23-69.  orig[i]/mut[i] are NUL-terminated. */
 int         ps_score_mutations(ps_region* r, int n, const int* start, const char* const* orig,
                                const char* const* mut, double* scores);
+/* Same, but the per-mutation sums start at 0 instead of -1e-6: the partial sum over THIS region's
+ * events, for callers that split one region's events across GPUs and all-reduce the partials
+ * (the reference's comment at cpp/MakeMutations.cpp:19-22 anticipates exactly that split). */
+int         ps_score_mutations_partial(ps_region* r, int n, const int* start, const char* const* orig,
+                                       const char* const* mut, double* partial);
 /* vector<MutInfo> FindPointMutations(AlignData&)   cpp/Mutations.h:19, cpp/FindMutations.cpp:191-234.
  * Writes up to cap single-base edits (orig/mut as one char, 0 = empty); *n = 8 per state. */
 int         ps_find_point_mutations(ps_region* r, int cap, int* n, int* start, char* orig, char* mut);

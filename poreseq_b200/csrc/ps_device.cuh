@@ -928,7 +928,7 @@ __global__ void __launch_bounds__(128) k_mutscore(Batch b)
 // cpp/AlignUtil.h:84-90).  One thread per mutation; the region table gives its events.
 struct RegTabDev { long long mut_off; int ev0, nev; };
 
-__global__ void k_reduce(Batch b, const RegTabDev* regs, int n_regs, long long n_muts)
+__global__ void k_reduce(Batch b, const RegTabDev* regs, int n_regs, long long n_muts, double start)
 {
     long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_muts) return;
@@ -939,7 +939,7 @@ __global__ void k_reduce(Batch b, const RegTabDev* regs, int n_regs, long long n
         if (regs[mid].mut_off <= g) lo = mid; else hi = mid - 1;
     }
     const int m = (int)(g - regs[lo].mut_off);
-    double s = -1e-6;
+    double s = start;                      // -1e-6 (cpp/AlignUtil.h:86), or 0 for a partial sum over an event shard
     for (int e = regs[lo].ev0; e < regs[lo].ev0 + regs[lo].nev; e++) s += b.delta[b.ev[e].task_off + m];
     b.scores[g] = s;
 }

@@ -253,6 +253,7 @@ struct Job
     std::vector<int> wave_need, plan_lo, plan_hi;
     std::vector<double> narrow_cols;             // per region: sum over its mutations of (|mut|+5)
     int wave_threads = 64;
+    double bias = -1e-6;                         // start value of every mutation's sum over events
     double wide_cells_fwd = 0, narrow_cells = 0;
     long long n_levels, n_cols, n_cen, n_tasks, n_muts, n_band;
     int cen_pad;
@@ -636,7 +637,7 @@ int Job::run(bool full)
         }
         MARK(PS_T_REDUCE);
         {
-            k_reduce<<<(unsigned)((n_muts + 127) / 128), 128, 0, ctx->stream>>>(b, (const RegTabDev*)d_regtab, (int)regs.size(), n_muts);
+            k_reduce<<<(unsigned)((n_muts + 127) / 128), 128, 0, ctx->stream>>>(b, (const RegTabDev*)d_regtab, (int)regs.size(), n_muts, bias);
             LAUNCHED();
         }
     }
@@ -701,7 +702,7 @@ int Job::download(std::vector<double>* align_scores, std::vector<double>* mut_sc
     if (mut_scores)
     {
         if (have_scores) mut_scores->assign(msc.data(), msc.data() + n_muts);
-        else mut_scores->assign((size_t)n_muts, -1e-6);
+        else mut_scores->assign((size_t)n_muts, bias);
     }
     // timings + algorithmic cell counts (wide = band cells of the usable events, both
     // directions when the reverse fill ran; narrow = (|mut|+5) x band rows per (mutation, usable event))
@@ -722,7 +723,7 @@ int Job::download(std::vector<double>* align_scores, std::vector<double>* mut_sc
 // ------------------------------------------------------------------------------------------
 // drivers shared by the C entry points
 static int run_job(ps_ctx* ctx, const std::vector<ps_region*>& regs, const std::vector<MutSpec>* muts,
-                   std::vector<double>* align_scores, std::vector<double>* mut_scores)
+                   std::vector<double>* align_scores, std::vector<double>* mut_scores, double bias = -1e-6)
 {
     TRY(ctx->init());
     CU(cudaSetDevice(ctx->device));
@@ -735,6 +736,7 @@ static int run_job(ps_ctx* ctx, const std::vector<ps_region*>& regs, const std::
     job.regs = regs;
     job.want_muts = muts != nullptr;
     if (muts) job.muts = *muts;
+    job.bias = bias;
     TRY(job.build());
     const double t1 = now();
     MARK(PS_T_H2D);
@@ -804,12 +806,12 @@ std::vector<HostMut> ps_point_mutations(const ps_region* R)      // cpp/FindMuta
     return v;
 }
 
-int ps_score_mutation_list(ps_region* R, std::vector<HostMut>& muts)
+int ps_score_mutation_list(ps_region* R, std::vector<HostMut>& muts, double bias)
 {
     std::vector<MutSpec> per(1);
     per[0].list = &muts;
     std::vector<double> sc;
-    TRY(run_job(R->ctx, std::vector<ps_region*>(1, R), &per, nullptr, &sc));
+    TRY(run_job(R->ctx, std::vector<ps_region*>(1, R), &per, nullptr, &sc, bias));
     for (size_t i = 0; i < muts.size(); i++) muts[i].score = sc[i];
     return PS_OK;
 }
@@ -1010,6 +1012,15 @@ int ps_score_mutations(ps_region* R, int n, const int* start, const char* const*
     std::vector<HostMut> v = gather_muts(n, start, orig, mut, nullptr);
     TRY(ps_score_mutation_list(R, v));
     for (int i = 0; i < n; i++) scores[i] = v[i].score;
+    return PS_OK;
+}
+
+int ps_score_mutations_partial(ps_region* R, int n, const int* start, const char* const* orig, const char* const* mut, double* partial)
+{
+    if (!R || n < 0 || (n > 0 && (!start || !orig || !mut || !partial))) return PS_E_ARG;
+    std::vector<HostMut> v = gather_muts(n, start, orig, mut, nullptr);
+    TRY(ps_score_mutation_list(R, v, 0.0));
+    for (int i = 0; i < n; i++) partial[i] = v[i].score;
     return PS_OK;
 }
 

@@ -98,7 +98,7 @@ void ps_set_error(ps_ctx* ctx, const char* fmt, ...);
 std::vector<int> ps_states_of(const std::string& bases);
 std::string ps_apply_mutation(const std::string& bases, int start, const std::string& orig, const std::string& mut);
 std::vector<HostMut> ps_point_mutations(const ps_region* R);
-int ps_score_mutation_list(ps_region* R, std::vector<HostMut>& muts);
+int ps_score_mutation_list(ps_region* R, std::vector<HostMut>& muts, double bias = -1e-6);
 int ps_make_mutation_list(ps_region* R, std::vector<HostMut> muts, int* nbases);
 
 struct SWResult                               // cpp/swlib.h:25-33

@@ -62,6 +62,7 @@ def lib():
     L.ps_region_get_event_align.argtypes = [C.c_void_p, C.c_int, _c_double_p, _c_double_p]
     L.ps_score_alignments.argtypes = [C.c_void_p, _c_double_p, _c_double_p]
     L.ps_score_mutations.argtypes = [C.c_void_p, C.c_int, _c_int_p, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), _c_double_p]
+    L.ps_score_mutations_partial.argtypes = L.ps_score_mutations.argtypes
     L.ps_find_point_mutations.argtypes = [C.c_void_p, C.c_int, _c_int_p, _c_int_p, C.c_char_p, C.c_char_p]
     L.ps_score_points.argtypes = [C.c_void_p, C.c_int, _c_int_p, _c_int_p, C.c_char_p, C.c_char_p, _c_double_p]
     L.ps_score_points_batch.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, _c_int_p, C.POINTER(C.c_longlong),
@@ -236,6 +237,15 @@ class NativeRegion(object):
         self.ctx.check(self.ctx.lib.ps_score_mutations(self.handle, n, st.ctypes.data_as(_c_int_p), _cstrs(origs),
                                                        _cstrs(muts), _dp(scores)))
         return scores
+
+    def score_mutations_partial(self, starts, origs, muts):
+        """Per-mutation sums over this region's events only, starting at 0 (for event-sharded scoring)."""
+        n = len(starts)
+        st = np.ascontiguousarray(starts, dtype=np.int32)
+        out = np.zeros(n)
+        self.ctx.check(self.ctx.lib.ps_score_mutations_partial(self.handle, n, st.ctypes.data_as(_c_int_p), _cstrs(origs),
+                                                               _cstrs(muts), _dp(out)))
+        return out
 
     def score_points(self):
         cap = 8 * max(self.ctx.lib.ps_region_sequence_length(self.handle), 1)

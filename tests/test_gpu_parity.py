@@ -226,3 +226,18 @@ def test_variant_modes(ctx, orc):
     want, _ = orc.score_mutations(reg, st, og, mu)
     assert [g.score for g in got] == want.tolist()
     assert [g.start for g in got] == [s + 1000 for s in st]
+
+
+def test_event_sharded_partials(ctx, orc):
+    """Two event shards scored separately on the GPU (partial sums from 0) add up to the full score."""
+    from poreseq_b200 import sharding
+    reg = region("draft_partial")
+    st, og, mu = edge_mutations(reg.sequence, 4, count=120)
+    want, _ = orc.score_mutations(reg, st, og, mu)
+    fn = sharding.cuda_partial(ctx)
+    total = np.zeros(len(st))
+    for rank in range(2):
+        total += fn(sharding.RegionShard(reg, rank, 2), st, og, mu)
+    got = -1e-6 + total
+    assert np.allclose(got, want, rtol=1e-12, atol=1e-12)
+    assert np.array_equal(got >= 0, want >= 0)
