@@ -234,7 +234,8 @@ struct ColSetup
     int s;            // 5-mer state or -1
     int i0, i1;       // band rows
     int p0, p1;       // previous column's band rows
-    long long g;      // storage column
+    long long g;      // per-column meta index
+    long long abase;  // band storage address of row 0 of this column: cell (k, i) at abase + i*ts
     StateParams p;
 };
 
@@ -255,6 +256,7 @@ __device__ __forceinline__ void fill_setup(const Batch& b, const EvDesc& ev, boo
     }
     cs.s = b.states[ev.state_off + c - 1];
     cs.g = ev.col_off + k;
+    cs.abase = ev.band_off + (long long)k * ev.ts + (k % ev.ts);
     if (cs.s >= 0) cs.p = b.models[ev.model].st[cs.s];
 }
 
@@ -272,13 +274,16 @@ struct FillOut               // where one direction's band columns go
 //     by the (compile-time) step-in-batch, the vertical one stays in registers.
 // A thread moves to its next column only at a batch boundary; the host guarantees
 // dlo(k+T) >= dhi(k) + 5 for every k (ps_host.cu: wave_threads), so no cell is skipped.
-template <bool REV>
+template <bool REV, int MAXT>
 __device__ __forceinline__ void fill_wave(const Batch& b, const EvDesc& ev, const FillOut& o, double* smem)
 {
     const int T = blockDim.x, tid = threadIdx.x;
     const int n0 = ev.n0, N = ev.N;
-    double* Cb = smem;               // [4][T] main-matrix values of the last four steps
-    double* Eb = smem + 4 * T;       // [4][T] emissions (the reverse pass adds the source cell's)
+    const long long ts = ev.ts;
+    // [4][MAXT] rings of the last four steps: main-matrix values, and emissions (the reverse pass adds
+    // the source cell's); the stride is the compile-time MAXT so every slot is an immediate offset
+    double* myC = smem + tid;
+    double* myE = smem + 4 * MAXT + tid;
     const LevelRec* lev = b.lev + ev.lev_off;
     const ModelDev& md = b.models[ev.model];
     const Trans tr = {md.lskip, md.lstay, md.lext, md.lins};
@@ -299,6 +304,8 @@ __device__ __forceinline__ void fill_wave(const Batch& b, const EvDesc& ev, cons
     double upC = 0, upS = 0, upE = 0, best = NEG;
     int besti = 0;
     const int left = tid == 0 ? T - 1 : tid - 1;
+    const double* lfC = smem + left;
+    const double* lfE = smem + 4 * MAXT + left;
     for (int db = dstart; db <= dend; db += 4)
     {
         if (db > cur.k + cur.i1)
@@ -314,6 +321,7 @@ __device__ __forceinline__ void fill_wave(const Batch& b, const EvDesc& ev, cons
             best = NEG; besti = 0;
         }
         const int ib = db - cur.k;                                    // row of the first step of the batch
+        const long long a0 = cur.abase + (long long)ib * ts;
         const bool mine = ib + 3 >= cur.i0 && ib <= cur.i1;           // any of my four cells in the band
         const bool warp_busy = __any_sync(0xffffffffu, mine);
         double e4[4] = {0.0, 0.0, 0.0, 0.0};
@@ -340,18 +348,18 @@ __device__ __forceinline__ void fill_wave(const Batch& b, const EvDesc& ev, cons
                     double Pi = 0, Pi1 = 0, PE = 0;
                     if (cur.k > 1)
                     {
-                        Pi = Cb[((u + 3) & 3) * T + left];            // step d-1: (k-1, i)
-                        Pi1 = Cb[((u + 2) & 3) * T + left];           // step d-2: (k-1, i-1)
-                        if (REV) PE = Eb[((u + 2) & 3) * T + left];
+                        Pi = lfC[((u + 3) & 3) * MAXT];               // step d-1: (k-1, i)
+                        Pi1 = lfC[((u + 2) & 3) * MAXT];              // step d-2: (k-1, i-1)
+                        if (REV) PE = lfE[((u + 2) & 3) * MAXT];
                     }
                     const double eM = REV ? (diag_ok ? PE : 0.0) : e;
                     const double eU = REV ? upE : e;
                     dp_cell(i == cur.i0, skip_ok, diag_ok, Pi, Pi1, eM, eU, upC, upS, tr, C, S, step);
                     if (C > best) { best = C; besti = i; }
                 }
-                Cb[u * T + tid] = C;
-                if (REV) Eb[u * T + tid] = e;
-                const long long a = cell_at(ev, cur.k, i);
+                myC[u * MAXT] = C;
+                if (REV) myE[u * MAXT] = e;
+                const long long a = a0 + u * ts;
                 o.Mm[a] = C; o.Ms[a] = S;
                 if (!REV) b.Fstep[a] = (uint8_t)step;
                 upC = C; upS = S; upE = e;
@@ -430,7 +438,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_fill(Batch b, int dir_base)
     double* Mcb = o.Mcb; int* Mcbi = o.Mcbi;
     if (b.mono[blockIdx.x])
     {
-        if (rev) fill_wave<true>(b, ev, o, smem); else fill_wave<false>(b, ev, o, smem);
+        if (rev) fill_wave<true, MAXT>(b, ev, o, smem); else fill_wave<false, MAXT>(b, ev, o, smem);
     }
     else if (tid == 0)
     {
@@ -795,7 +803,7 @@ __global__ void __launch_bounds__(128) k_mutscore(Batch b)
     const int W = b.scoring_width;
     const int S = 2 * W + 2;
     double* ring = SMEM ? ring_smem + threadIdx.x : b.scratch + gtid;
-    const long long rstride = SMEM ? blockDim.x : nthreads;       // element r at ring[r * rstride]
+    const long long rstride = SMEM ? 128 : nthreads;              // element r at ring[r * rstride]
     for (long long t = gtid; t < b.n_tasks; t += nthreads)
     {
         int e, m;
@@ -870,25 +878,52 @@ __global__ void __launch_bounds__(128) k_mutscore(Batch b)
                         // (c-1, i0-1): still in its slot, nothing of this column overwrites it
                         double diag = 0.0;
                         if (i0 > p0 && i0 <= p1)
-                            diag = first_col ? (seed ? seed[(long long)(i0 - 1) * ev.ts] : 0.0) : ring[(long long)((i0 - 1) % S) * rstride];
+                            diag = first_col ? (seed ? seed[(long long)(i0 - 1) * ts] : 0.0) : ring[(long long)((i0 - 1) % S) * rstride];
+                        // software pipeline: level record, seed value and join values of row i+1 are
+                        // requested while row i is computed (the loads are the latency that matters here)
+                        const LevelRec* lv = lev + (i0 - 1);                 // row i reads level i-1 ...
+                        const LevelRec* lq = lev + (n0 - i0);                // ... and 3 log stdv of level n0-i
+                        const double* sd = (first_col && seed) ? seed + (long long)i0 * ts : nullptr;
+                        const bool joinB = last_col && rab > 0;
+                        const double* qm = Bm + (long long)(n0 - i0 + 1) * ts;   // reverse row jb = n0-i+1
+                        const double* qs = Bs + (long long)(n0 - i0 + 1) * ts;
+                        LevelRec lr = *lv;
+                        double lsd3 = lq->lsd3;
+                        double sv = (sd && i0 >= p0 && i0 <= p1) ? *sd : 0.0;
+                        double bmv = 0.0, bsv = 0.0;
+                        {
+                            const int jb = n0 - i0 + 1;
+                            if (joinB && jb >= b0 && jb < b0 + blen) { bmv = *qm; bsv = *qs; }
+                        }
                         for (int i = i0; i <= i1; i++)
                         {
-                            const double e_i = cell_emission<false>(lev, n0, i, sp, b.log2pi, b.lik_offset);
+                            const LevelRec lr_c = lr;
+                            const double lsd3_c = lsd3, sv_c = sv, bm_c = bmv, bs_c = bsv;
+                            if (i < i1)
+                            {
+                                lv++; lq--;
+                                lr = *lv; lsd3 = lq->lsd3;
+                                if (sd) { sd += ts; sv = (i + 1 >= p0 && i + 1 <= p1) ? *sd : 0.0; }
+                                if (joinB)
+                                {
+                                    qm -= ts; qs -= ts;
+                                    const int jn = n0 - i;
+                                    bmv = 0.0; bsv = 0.0;
+                                    if (jn >= b0 && jn < b0 + blen) { bmv = *qm; bsv = *qs; }
+                                }
+                            }
+                            const double e_i = emission(lr_c.mean, lr_c.stdv, lr_c.rstdv, lsd3_c, sp, b.log2pi, b.lik_offset);
                             const bool skip_ok = i >= p0 && i <= p1;
                             const bool diag_ok = i > p0 && i <= p1;
                             double Pi = 0.0;
-                            if (skip_ok) Pi = first_col ? (seed ? seed[(long long)i * ev.ts] : 0.0) : ring[(long long)slot * rstride];
+                            if (skip_ok) Pi = first_col ? sv_c : ring[(long long)slot * rstride];
                             double C, Sv; int step;
                             dp_cell(i == i0, skip_ok, diag_ok, Pi, diag, e_i, e_i, upC, upS, tr, C, Sv, step);
                             if (C > best) best = C;
                             if (last_col)
                             {
                                 const int jb = n0 - i + 1;
-                                if (jb >= b0 && jb < b0 + blen)
-                                {
-                                    const double bm = rab > 0 ? Bm[jb * ts] : 0.0, bs = rab > 0 ? Bs[jb * ts] : 0.0;
-                                    joinmax = fmax(joinmax, fmax(C + bm, Sv + bs));
-                                }
+                                if (jb >= b0 && jb < b0 + blen) joinmax = fmax(joinmax, fmax(C + bm_c, Sv + bs_c));
                             }
                             else ring[(long long)slot * rstride] = C;
                             diag = Pi;

@@ -585,7 +585,7 @@ int Job::run(bool full)
     // wavefront fill: one CTA per (event, direction), forward and reverse in one launch (grid.y = 2)
     {
         const int T = wave_threads;
-        const size_t smem = std::max<size_t>(8 * T, 2 * b.RS) * sizeof(double);
+        const size_t smem = std::max<size_t>(8 * (T <= 352 ? 352 : T <= 640 ? 640 : 1024), 2 * b.RS) * sizeof(double);
         dim3 grid(nev, full ? 2 : 1);
         if (T <= 352) k_fill<352, 2><<<grid, T, smem, ctx->stream>>>(b, 0);
         else if (T <= 640) k_fill<640, 1><<<grid, T, smem, ctx->stream>>>(b, 0);
@@ -619,13 +619,12 @@ int Job::run(bool full)
             // previous-column ring: shared memory when 2W+2 doubles per thread fit, else global scratch
             const size_t ring = (size_t)(2 * b.scoring_width + 2) * sizeof(double);
             int threads = 128;
-            while (threads > 32 && ring * threads > 96 * 1024) threads >>= 1;
-            const bool in_smem = ring * threads <= 96 * 1024;
-            if (!in_smem) threads = 128;
+            const bool in_smem = ring * 128 <= 96 * 1024;            // the smem ring is laid out for 128 threads
+            threads = 128;
             long long blocks = std::min<long long>((n_tasks + threads - 1) / threads, (long long)ctx->sm_count * 16);
             if (in_smem)
             {
-                k_mutscore<true><<<(unsigned)blocks, threads, ring * threads, ctx->stream>>>(b);
+                k_mutscore<true><<<(unsigned)blocks, threads, ring * 128, ctx->stream>>>(b);
             }
             else
             {
