@@ -72,6 +72,14 @@ const char* ps_version(void);
 /* Number of kernels this library launched on ctx since creation / algorithmic DP cells of the
  * last compute call (wide fill cells, narrow mutation cells), for bench.py. */
 long long   ps_launch_count(ps_ctx* ctx);
+/* Arithmetic of the per-(mutation, event) scan.  EXACT (default): IEEE double in the reference's
+ * order, every score bit-identical to cpp/Alignment.cpp.  FAST: all pairs in rebased log-space
+ * FP32, then every mutation whose total is not clearly negative (> -tau) is re-scored exactly, so
+ * accepted mutations and consensus sequences stay bit-identical while clearly negative scores carry
+ * ~1e-6 relative error (BASELINE.json tolerance: 1e-4).  The wide fills and backtrace are always FP64. */
+#define PS_PRECISION_EXACT 0
+#define PS_PRECISION_FAST  1
+int         ps_set_precision(ps_ctx* ctx, int mode);
 int         ps_last_timing(ps_ctx* ctx, double* ms /*PS_T_COUNT*/);
 int         ps_last_cells(ps_ctx* ctx, double* wide_cells, double* narrow_cells);
 

@@ -95,6 +95,16 @@ struct Batch                  // everything the kernels need, passed by value
     double            log2pi;
     int               realign_width;
     int               scoring_width;
+    // FP32 fast pass + exact re-score of the candidates that matter (ps_fast.cuh)
+    const StateParamsF* stf;                    // [models][1024]
+    const LevelRecF*  levf;                     // per level
+    const float4*     trf;                      // per model: log skip, stay, extend, insert
+    const RegTabDev*  regs;                     // per region
+    int               n_regs;
+    int               max_ev;                   // most events in one region
+    int*              flag_list;                // global indices of the mutations to re-score exactly
+    int*              flag_count;
+    double            tau;                      // re-score when the FP32 total is above -tau
 };
 
 // ------------------------------------------------------------------------------------------
@@ -794,7 +804,25 @@ __device__ double thread_join(const Batch& b, const EvDesc& ev, int raf, int rab
 // old value of its own slot = (c-1, i) and keeps it one more iteration as (c-1, i-1)).
 // GLOBAL: the same ring in a per-thread strip of global scratch, for widths whose ring does not
 // fit in shared memory.
-template <bool SMEM>
+// LIST: the tasks are the (flagged mutation, event of its region) pairs of b.flag_list instead of all pairs
+__device__ __forceinline__ bool list_task(const Batch& b, long long t, int& e, int& m)
+{
+    const long long q = t / b.max_ev;
+    const int el = (int)(t % b.max_ev);
+    const long long g = b.flag_list[q];
+    int lo = 0, hi = b.n_regs - 1;
+    while (lo < hi)
+    {
+        int mid = (lo + hi + 1) >> 1;
+        if (b.regs[mid].mut_off <= g) lo = mid; else hi = mid - 1;
+    }
+    if (el >= b.regs[lo].nev) return false;
+    e = b.regs[lo].ev0 + el;
+    m = (int)(g - b.regs[lo].mut_off);
+    return true;
+}
+
+template <bool SMEM, bool LIST>
 __global__ void __launch_bounds__(128) k_mutscore(Batch b)
 {
     extern __shared__ double ring_smem[];
@@ -804,10 +832,11 @@ __global__ void __launch_bounds__(128) k_mutscore(Batch b)
     const int S = 2 * W + 2;
     double* ring = SMEM ? ring_smem + threadIdx.x : b.scratch + gtid;
     const long long rstride = SMEM ? 128 : nthreads;              // element r at ring[r * rstride]
-    for (long long t = gtid; t < b.n_tasks; t += nthreads)
+    const long long n_total = LIST ? (long long)(*b.flag_count) * b.max_ev : b.n_tasks;
+    for (long long t = gtid; t < n_total; t += nthreads)
     {
         int e, m;
-        if (!task_decode(b, t, e, m)) continue;
+        if (LIST ? !list_task(b, t, e, m) : !task_decode(b, t, e, m)) continue;
         const EvDesc ev = b.ev[e];
         const MutDev mu = b.muts[ev.mut_off + m];
         double result = 0.0;
@@ -955,18 +984,21 @@ __global__ void __launch_bounds__(128) k_mutscore(Batch b)
             }
             result = neu - old;
         }
-        b.delta[t] = result;
+        b.delta[LIST ? ev.task_off + m : t] = result;
     }
 }
 
 // k_reduce: score[m] = -1e-6 + sum_e delta(e, m), events in order (cpp/MakeMutations.cpp:38-52,
 // cpp/AlignUtil.h:84-90).  One thread per mutation; the region table gives its events.
-struct RegTabDev { long long mut_off; int ev0, nev; };
-
-__global__ void k_reduce(Batch b, const RegTabDev* regs, int n_regs, long long n_muts, double start)
+__global__ void k_reduce(Batch b, const RegTabDev* regs, int n_regs, long long n_muts, double start, int from_list)
 {
     long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_muts) return;
+    if (from_list)
+    {
+        if (g >= *b.flag_count) return;
+        g = b.flag_list[g];
+    }
+    else if (g >= n_muts) return;
     int lo = 0, hi = n_regs - 1;
     while (lo < hi)
     {

@@ -20,6 +20,7 @@
 
 #include "../../include/poreseq_b200.h"
 #include "ps_device.cuh"
+#include "ps_fast.cuh"
 #include "ps_internal.h"
 
 using namespace psdev;
@@ -80,7 +81,9 @@ int ps_ctx::init()
     CU(cudaFuncSetAttribute(k_fill<352, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU(cudaFuncSetAttribute(k_fill<640, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU(cudaFuncSetAttribute(k_fill<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    CU(cudaFuncSetAttribute(k_mutscore<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CU(cudaFuncSetAttribute(k_mutscore<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CU(cudaFuncSetAttribute(k_mutscore<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CU(cudaFuncSetAttribute(k_mutscore_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     ready = true;
     return PS_OK;
 }
@@ -230,7 +233,7 @@ struct MutSpec                      // the mutations of one region: an explicit 
     bool points = false;
 };
 
-struct RegTab { long long mut_off; int ev0, nev; };   // per region: first mutation, its events
+typedef RegTabDev RegTab;
 
 struct Job
 {
@@ -244,6 +247,9 @@ struct Job
     PinVec<int> states;
     PinVec<char> bases;
     PinVec<LevelRec> lev;
+    PinVec<LevelRecF> levf;
+    bool fast = false;                           // FP32 pass + exact re-score (PS_PRECISION_FAST)
+    int max_ev = 1;
     PinVec<double> ref_align, ref_like, ref_index;
     PinVec<int> ri_empty, mono, cen_old;
     PinVec<MutDev> mdev;
@@ -264,7 +270,7 @@ struct Job
     Job(ps_ctx* c) : ctx(c), want_muts(false), n_levels(0), n_cols(0), n_cen(0), n_tasks(0), n_muts(0), n_band(0), cen_pad(8)
     {
         ev = c->pinned<EvDesc>("ev"); states = c->pinned<int>("states"); bases = c->pinned<char>("bases");
-        lev = c->pinned<LevelRec>("lev"); ref_align = c->pinned<double>("ref_align");
+        lev = c->pinned<LevelRec>("lev"); levf = c->pinned<LevelRecF>("levf"); ref_align = c->pinned<double>("ref_align");
         ref_like = c->pinned<double>("ref_like"); ref_index = c->pinned<double>("ref_index");
         ri_empty = c->pinned<int>("ri_empty"); mono = c->pinned<int>("mono"); cen_old = c->pinned<int>("cen_old");
         mdev = c->pinned<MutDev>("mdev"); mut_str = c->pinned<char>("mut_str"); regtab = c->pinned<RegTab>("regtab");
@@ -421,6 +427,7 @@ int Job::build()
         const int nm = (int)(mdev.size() - mut_off);
         narrow_cols.push_back(cols);
         RegTab rt; rt.mut_off = mut_off; rt.ev0 = ev0; rt.nev = (int)R->events.size();
+        max_ev = std::max(max_ev, rt.nev);
         regtab.push_back(rt);
         for (size_t k = 0; k < R->events.size(); k++)
         {
@@ -453,6 +460,7 @@ int Job::build()
             n_tasks += nm;
             ev.push_back(d);
             lev.append((const LevelRec*)he.levrec.data(), (size_t)he.n0);
+            if (fast) levf.append((const LevelRecF*)he.levrecf.data(), (size_t)he.n0);
             ref_align.append(he.ref_align.data(), he.ref_align.size());
             ref_like.append(he.ref_like.data(), he.ref_like.size());
             if (he.ri_empty) ref_index.fill(he.n0, 0.0);
@@ -567,6 +575,39 @@ int Job::upload()
         d_regtab = d_rt;
         TRY(room(ctx, "delta", (size_t)n_tasks, &b.delta));
         TRY(room(ctx, "scores", (size_t)n_muts, &b.scores));
+        b.regs = d_rt; b.n_regs = (int)regs.size(); b.max_ev = max_ev;
+        TRY(room(ctx, "flag_list", (size_t)n_muts + 1, &b.flag_list));
+        TRY(room(ctx, "flag_count", 1, &b.flag_count));
+        if (fast)
+        {
+            // FP32 twins: fused emission coefficients per state, log transition costs per model
+            std::vector<StateParamsF> stf(model_src.size() * N_STATES);
+            std::vector<float4> trf(model_src.size());
+            const double l2p = std::log(2 * M_PI);
+            for (size_t q = 0; q < model_src.size(); q++)
+            {
+                const ModelDev& md = models[q];
+                for (int st = 0; st < N_STATES; st++)
+                {
+                    const StateParams& sp = md.st[st];
+                    StateParamsF& f = stf[q * N_STATES + st];
+                    f.mu = (float)sp.lev_mean;
+                    f.a_s = (float)(-0.5 / (sp.lev_stdv * sp.lev_stdv));
+                    f.c_s = (float)(-0.5 * l2p - sp.log_lev + 0.5 * (sp.log_lambda - l2p) + P.lik_offset);
+                    f.mu2 = (float)sp.sd_mean;
+                    f.f_s = (float)(-0.5 * sp.sd_lambda / (sp.sd_mean * sp.sd_mean));
+                    f.pad0 = f.pad1 = f.pad2 = 0.f;
+                }
+                trf[q] = make_float4((float)md.lskip, (float)md.lstay, (float)md.lext, (float)md.lins);
+            }
+            StateParamsF* d_stf; float4* d_trf; LevelRecF* d_levf;
+            TRY(up(ctx, "stf", stf.data(), stf.size(), &d_stf));
+            TRY(up(ctx, "trf", trf.data(), trf.size(), &d_trf));
+            TRY(up(ctx, "levf", levf.data(), levf.size(), &d_levf));
+            CU(cudaStreamSynchronize(ctx->stream));          // stf/trf are stack vectors
+            b.stf = d_stf; b.trf = d_trf; b.levf = d_levf;
+            b.tau = 0.02 + 5e-4 * max_ev;
+        }
     }
     return PS_OK;
 }
@@ -618,26 +659,42 @@ int Job::run(bool full)
         {
             // previous-column ring: shared memory when 2W+2 doubles per thread fit, else global scratch
             const size_t ring = (size_t)(2 * b.scoring_width + 2) * sizeof(double);
-            int threads = 128;
+            const int threads = 128;
             const bool in_smem = ring * 128 <= 96 * 1024;            // the smem ring is laid out for 128 threads
-            threads = 128;
             long long blocks = std::min<long long>((n_tasks + threads - 1) / threads, (long long)ctx->sm_count * 16);
-            if (in_smem)
+            int mask = 1;
+            while (mask + 1 < 2 * b.scoring_width + 2) mask = 2 * mask + 1;     // power-of-two ring >= 2W+2 rows
+            const size_t ringf_bytes = (size_t)(mask + 1) * 128 * sizeof(float);
+            if (fast && in_smem && ringf_bytes <= 96 * 1024)
             {
-                k_mutscore<true><<<(unsigned)blocks, threads, ring * 128, ctx->stream>>>(b);
+                // pass 1: every pair in rebased FP32; pass 2: exact FP64 for the mutations that matter
+                k_mutscore_f32<<<(unsigned)blocks, threads, ringf_bytes, ctx->stream>>>(b, mask);
+                LAUNCHED();
+                k_reduce<<<(unsigned)((n_muts + 127) / 128), 128, 0, ctx->stream>>>(b, (const RegTabDev*)d_regtab, (int)regs.size(), n_muts, bias, 0);
+                LAUNCHED();
+                CU(cudaMemsetAsync(b.flag_count, 0, sizeof(int), ctx->stream));
+                k_flag<<<(unsigned)((n_muts + 127) / 128), 128, 0, ctx->stream>>>(b, n_muts);
+                LAUNCHED();
+                k_mutscore<true, true><<<(unsigned)std::min<long long>(blocks, (long long)ctx->sm_count * 4), threads, ring * 128, ctx->stream>>>(b);
+                LAUNCHED();
+                MARK(PS_T_REDUCE);
+                k_reduce<<<(unsigned)((n_muts + 127) / 128), 128, 0, ctx->stream>>>(b, (const RegTabDev*)d_regtab, (int)regs.size(), n_muts, bias, 1);
+                LAUNCHED();
             }
             else
             {
-                b.scratch_slots = blocks * threads;
-                TRY(room(ctx, "scratch", (size_t)b.scratch_slots * (2 * b.scoring_width + 2), &b.scratch));
-                k_mutscore<false><<<(unsigned)blocks, threads, 0, ctx->stream>>>(b);
+                if (in_smem) k_mutscore<true, false><<<(unsigned)blocks, threads, ring * 128, ctx->stream>>>(b);
+                else
+                {
+                    b.scratch_slots = blocks * threads;
+                    TRY(room(ctx, "scratch", (size_t)b.scratch_slots * (2 * b.scoring_width + 2), &b.scratch));
+                    k_mutscore<false, false><<<(unsigned)blocks, threads, 0, ctx->stream>>>(b);
+                }
+                LAUNCHED();
+                MARK(PS_T_REDUCE);
+                k_reduce<<<(unsigned)((n_muts + 127) / 128), 128, 0, ctx->stream>>>(b, (const RegTabDev*)d_regtab, (int)regs.size(), n_muts, bias, 0);
+                LAUNCHED();
             }
-            LAUNCHED();
-        }
-        MARK(PS_T_REDUCE);
-        {
-            k_reduce<<<(unsigned)((n_muts + 127) / 128), 128, 0, ctx->stream>>>(b, (const RegTabDev*)d_regtab, (int)regs.size(), n_muts, bias);
-            LAUNCHED();
         }
     }
     else { MARK(PS_T_MUTSCORE); MARK(PS_T_REDUCE); }
@@ -736,6 +793,7 @@ static int run_job(ps_ctx* ctx, const std::vector<ps_region*>& regs, const std::
     job.want_muts = muts != nullptr;
     if (muts) job.muts = *muts;
     job.bias = bias;
+    job.fast = ctx->precision == PS_PRECISION_FAST && muts != nullptr;
     TRY(job.build());
     const double t1 = now();
     MARK(PS_T_H2D);
@@ -880,6 +938,13 @@ const char* ps_last_error(ps_ctx* ctx) { return ctx ? ctx->error.c_str() : g_cre
 
 long long ps_launch_count(ps_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int ps_set_precision(ps_ctx* ctx, int mode)
+{
+    if (!ctx || (mode != PS_PRECISION_EXACT && mode != PS_PRECISION_FAST)) return PS_E_ARG;
+    ctx->precision = mode;
+    return PS_OK;
+}
+
 int ps_last_timing(ps_ctx* ctx, double* ms)
 {
     if (!ctx || !ms) return PS_E_ARG;
@@ -941,12 +1006,16 @@ int ps_region_add_event(ps_region* R, int n0, const double* mean, const double* 
     he.ref_like.assign(ref_like, ref_like + n0);
     he.log_stdv.resize(n0);
     he.levrec.resize((size_t)n0 * 4);
+    he.levrecf.resize((size_t)n0 * 4);
     for (int i = 0; i < n0; i++)
     {
         he.log_stdv[i] = std::log(he.stdv[i]);                               // cpp/EventData.h:218-220
         // device level record: mean, stdv, RN(1/stdv), 3*log(stdv)  (psdev::LevelRec)
         he.levrec[4 * i] = he.mean[i]; he.levrec[4 * i + 1] = he.stdv[i];
         he.levrec[4 * i + 2] = 1.0 / he.stdv[i]; he.levrec[4 * i + 3] = 3 * he.log_stdv[i];
+        // FP32 twin (psdev::LevelRecF): mean, stdv, 1/stdv, -1.5 log(stdv)
+        he.levrecf[4 * i] = (float)he.mean[i]; he.levrecf[4 * i + 1] = (float)he.stdv[i];
+        he.levrecf[4 * i + 2] = (float)(1.0 / he.stdv[i]); he.levrecf[4 * i + 3] = (float)(-1.5 * he.log_stdv[i]);
     }
     if (seq2d) he.seq2d = seq2d;
     he.update_refs();

@@ -38,6 +38,7 @@ struct ps_ctx
     int device = 0;
     bool ready = false;
     int sm_count = 0;
+    int precision = 0;                        // PS_PRECISION_EXACT / PS_PRECISION_FAST
     int fill_warps = 8;                       // warps per (event, direction) in the wide fill (PORESEQ_B200_FILL_WARPS)
     cudaStream_t stream = nullptr;
     cudaEvent_t tev[PS_T_COUNT + 1];
@@ -69,6 +70,7 @@ struct HostEvent                              // cpp/EventData.h:78-229
     int refstart = -1, refend = -1;
     std::vector<double> mean, stdv, log_stdv, ref_align, ref_like, ref_index;
     std::vector<double> levrec;               // 4 doubles per level, the device LevelRec layout
+    std::vector<float> levrecf;               // 4 floats per level, the device LevelRecF layout
     std::string seq2d;
     void update_refs();
 };

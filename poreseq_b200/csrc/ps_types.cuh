@@ -24,6 +24,23 @@ struct LevelRec               // one 32-byte record per event level (cpp/EventDa
     double lsd3;                       // 3 * log(stdv)
 };
 
+struct StateParamsF           // FP32 fused emission coefficients of one state (ps_fast.cuh)
+{
+    float mu;                          // lev_mean
+    float a_s;                         // -0.5 / lev_stdv^2
+    float c_s;                         // -0.5 log2pi - log lev_stdv + 0.5 (log lambda - log2pi) + lik_offset
+    float mu2;                         // sd_mean
+    float f_s;                         // -0.5 lambda / sd_mean^2
+    float pad0, pad1, pad2;
+};
+
+struct LevelRecF              // FP32 level record: mean, stdv, 1/stdv, -1.5 log(stdv)
+{
+    float x, y, ry, ey;
+};
+
+struct RegTabDev { long long mut_off; int ev0, nev; };   // per region: first mutation, its events
+
 struct ModelDev               // cpp/EventData.h:21-74
 {
     StateParams st[N_STATES];

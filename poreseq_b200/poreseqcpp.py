@@ -49,6 +49,7 @@ def lib():
     L.ps_version.restype = C.c_char_p
     L.ps_launch_count.restype = C.c_longlong
     L.ps_launch_count.argtypes = [C.c_void_p]
+    L.ps_set_precision.argtypes = [C.c_void_p, C.c_int]
     L.ps_last_timing.argtypes = [C.c_void_p, _c_double_p]
     L.ps_last_cells.argtypes = [C.c_void_p, _c_double_p, _c_double_p]
     L.ps_region_create.restype = C.c_void_p
@@ -106,6 +107,10 @@ class Context(object):
     def check(self, rc):
         if rc != 0:
             raise RuntimeError("poreseq_b200 error %d: %s" % (rc, self.lib.ps_last_error(self.handle).decode()))
+
+    def set_precision(self, mode):
+        """'exact' (default, bit-identical FP64) or 'fast' (FP32 scan + exact re-score of candidates)."""
+        self.check(self.lib.ps_set_precision(self.handle, {"exact": 0, "fast": 1}[mode]))
 
     def launch_count(self):
         return int(self.lib.ps_launch_count(self.handle))

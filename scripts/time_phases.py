@@ -8,6 +8,8 @@ L = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 cov = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 nreg = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 ctx = poreseqcpp.Context(0)
+if len(sys.argv) > 4:
+    ctx.set_precision(sys.argv[4])
 regs = [synth.make_region(L, cov, seed=s + 1) for s in range(nreg)]
 for it in range(4):
     t0 = time.time()

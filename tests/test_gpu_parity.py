@@ -241,3 +241,36 @@ def test_event_sharded_partials(ctx, orc):
     got = -1e-6 + total
     assert np.allclose(got, want, rtol=1e-12, atol=1e-12)
     assert np.array_equal(got >= 0, want >= 0)
+
+
+@pytest.mark.parametrize("name", [c[0] for c in CASES])
+def test_fast_mode_decisions_exact(orc, name):
+    """PS_PRECISION_FAST: FP32 scan + exact re-score.  Every score above -tau (in particular every
+    accepted mutation) is bit-identical; the rest is within 1e-4 relative (BASELINE.json tolerance,
+    plus 1e-3 absolute for scores near zero magnitude); Refine gives the identical sequence."""
+    c2 = poreseqcpp.Context(0)
+    c2.set_precision("fast")
+    try:
+        reg = region(name)
+        want, want_a = orc.score_points(reg)
+        w = np.array([x[3] for x in want])
+        nr = poreseqcpp.NativeRegion(c2, reg.sequence, reg.events, reg.params, "point_width")
+        st, og, mu, sc = nr.score_points()
+        keep = w > -0.02
+        assert np.array_equal(sc[keep], w[keep])
+        assert np.array_equal(sc >= 0, w >= 0)
+        assert np.all(np.abs(sc - w) <= 1e-4 * np.abs(w) + 1e-3), float(np.max(np.abs(sc - w)))
+        assert same_aligns([nr.event_align(e) for e in range(len(reg.events))], want_a)
+        st2, og2, mu2 = edge_mutations(reg.sequence, 11)
+        w2, _ = orc.score_mutations(reg, st2, og2, mu2)
+        nr = poreseqcpp.NativeRegion(c2, reg.sequence, reg.events, reg.params)
+        s2 = nr.score_mutations(st2, og2, mu2)
+        assert np.array_equal(s2 >= 0, w2 >= 0)
+        assert np.all(np.abs(s2 - w2) <= 1e-4 * np.abs(w2) + 1e-3), float(np.max(np.abs(s2 - w2)))
+        nr = poreseqcpp.NativeRegion(c2, reg.sequence, reg.events, reg.params, "point_width")
+        nb = nr.refine()
+        seq, want_nb, want_a = orc.refine(reg)
+        assert (nb, nr.sequence()) == (want_nb, seq)
+        assert same_aligns([nr.event_align(e) for e in range(len(reg.events))], want_a)
+    finally:
+        c2.close()
