@@ -39,8 +39,8 @@ struct EvDesc                 // one event of one region in the batch
     long long mut_off;        // first mutation of the region in the mutation arrays
     long long task_off;       // first (event, mutation) task of this event; delta[task_off + m]
     long long band_off;       // first element of this event's band storage (same for F and B arrays)
-    int       ts;             // band storage stride: cell (k, i) lives at band_off + (k+i)*ts + k%ts
-    int       pad2;
+    int       ts;             // strips that can be live on one wavefront step (band storage slot count)
+    int       rs;             // row stride of the band storage = ts * CW
 };
 
 struct MutDev
@@ -147,10 +147,23 @@ __device__ __forceinline__ double cell_emission(const LevelRec* lev, int n0, int
 
 struct Trans { double lskip, lstay, lext, lins; };
 
-// band storage address of cell (column k in processing order, row i)
+// Band storage, wavefront-major.  The fill gives every thread a strip of CW consecutive columns
+// (strip j = columns CW*j+1 .. CW*j+CW) and computes row i of strip j at step j + i.  A cell is
+// stored where its step puts it: the CW cells of (strip j, row i) are contiguous, strips that are
+// computed in the same step are neighbours (slot j % ts), successive rows of a column are `rs`
+// apart.  So every step of the fill writes one contiguous run per warp, and a reader that walks
+// down a column uses a fixed stride:   cell (k, i)  ->  col_base(k) + i * rs.
+constexpr int CW = 4;
+
+__device__ __forceinline__ long long col_base(const EvDesc& ev, int k)
+{
+    const int j = (k - 1) >> 2, c = (k - 1) & 3;
+    return ev.band_off + ((long long)j * ev.ts + (j % ev.ts)) * CW + c;
+}
+
 __device__ __forceinline__ long long cell_at(const EvDesc& ev, int k, int i)
 {
-    return ev.band_off + (long long)(k + i) * ev.ts + (k % ev.ts);
+    return col_base(ev, k) + (long long)i * ev.rs;
 }
 
 // One cell of the coupled (main C, stay S) recurrence, cpp/Alignment.cpp:194-271 (forward) and
@@ -231,43 +244,56 @@ __global__ void k_centres(Batch b, int* cen, int check_mono)
 // ------------------------------------------------------------------------------------------
 // k_fill: wide-band fill of one (event, direction) per CTA.
 //
-// Wavefront: the cell (column k, row i) -- k counts columns in processing order, so k = c forward
-// and k = N-c+1 in reverse -- is computed at step d = k + i.  Its three inputs (k-1,i), (k-1,i-1),
-// (k,i-1) were produced at steps d-1, d-2, d-1.  Thread t owns columns k = t+1, t+1+T, ...; the
-// vertical dependency stays in registers, the two horizontal ones come from the left neighbour
-// through a 3-deep shared-memory ring indexed by step.  With nondecreasing band centres and
-// T >= 2*realign_width+1 a thread never has two live columns (host/k_centres check `mono`);
-// otherwise thread 0 runs the same cells serially.
-struct ColSetup
+// Wavefront over (strip, row): thread t owns the strips j = t, t+T, ... (CW = 4 consecutive columns
+// each, in processing order k = c forward, k = N-c+1 reverse) and at step d computes row i = d - j of
+// its current strip, left to right through the 4 columns.  Inside the strip every dependency is a
+// register: (k, i-1) and (k-1, i-1) are last row's values, (k-1, i) was computed a moment ago.  Only
+// the strip's first column looks outside: (k-1, i) and (k-1, i-1) are the left neighbour's last
+// column at steps d-1 and d-2, read from a 4-deep shared-memory ring.  One level record feeds the 4
+// emissions of the row (4 independent division-free chains), one barrier separates steps, and the
+// row's 4 cells leave as one contiguous 32-byte run per matrix.
+// With nondecreasing band centres and T >= the number of strips that can be live on one step
+// (planned on the host, Job::plan_event) a thread never has two live strips; events whose centres
+// go backwards are filled serially by thread 0.
+struct ColMeta { int s, i0, i1; };
+
+struct Strip
 {
-    int k;            // processing-order column (1..N), INT_MAX/2 when past the end
-    int s;            // 5-mer state or -1
-    int i0, i1;       // band rows
-    int p0, p1;       // previous column's band rows
-    long long g;      // per-column meta index
-    long long abase;  // band storage address of row 0 of this column: cell (k, i) at abase + i*ts
-    StateParams p;
+    int j;                    // strip index, 1<<29 when past the end
+    int rlo, rhi;             // union of the 4 bands
+    int pp0, pp1;             // band of the column just before the strip
+    ColMeta col[CW];
+    StateParams p[CW];
 };
 
-__device__ __forceinline__ void fill_setup(const Batch& b, const EvDesc& ev, bool rev, int k, ColSetup& cs)
+__device__ __forceinline__ void col_band(const Batch& b, const EvDesc& ev, bool rev, int k, int& i0, int& i1)
 {
-    if (k > ev.N) { cs.k = 1 << 29; cs.i0 = 1; cs.i1 = 0; cs.s = -1; return; }
-    cs.k = k;
-    int c = rev ? ev.N - k + 1 : k;
-    int n0 = ev.n0, w = b.realign_width;
-    int cen = b.cen_old[ev.cen_off + c];
-    band_of(rev ? n0 - cen + 1 : cen, n0, w, cs.i0, cs.i1);
-    if (k == 1) { cs.p0 = 0; cs.p1 = n0; }
-    else
+    const int c = rev ? ev.N - k + 1 : k;
+    const int cen = b.cen_old[ev.cen_off + c];
+    band_of(rev ? ev.n0 - cen + 1 : cen, ev.n0, b.realign_width, i0, i1);
+}
+
+__device__ __forceinline__ void strip_setup(const Batch& b, const EvDesc& ev, bool rev, int j, Strip& st)
+{
+    const int k0 = CW * j + 1;
+    if (k0 > ev.N) { st.j = 1 << 29; st.rlo = 1; st.rhi = 0; return; }
+    st.j = j;
+    st.rlo = 1 << 30; st.rhi = 0;
+#pragma unroll
+    for (int c = 0; c < CW; c++)
     {
-        int cp = rev ? c + 1 : c - 1;
-        int cenp = b.cen_old[ev.cen_off + cp];
-        band_of(rev ? n0 - cenp + 1 : cenp, n0, w, cs.p0, cs.p1);
+        const int k = k0 + c;
+        st.col[c].s = -1; st.col[c].i0 = 1; st.col[c].i1 = 0;
+        if (k <= ev.N)
+        {
+            col_band(b, ev, rev, k, st.col[c].i0, st.col[c].i1);
+            st.col[c].s = b.states[ev.state_off + (rev ? ev.N - k + 1 : k) - 1];
+            if (st.col[c].s >= 0) st.p[c] = b.models[ev.model].st[st.col[c].s];
+            st.rlo = min(st.rlo, st.col[c].i0); st.rhi = max(st.rhi, st.col[c].i1);
+        }
     }
-    cs.s = b.states[ev.state_off + c - 1];
-    cs.g = ev.col_off + k;
-    cs.abase = ev.band_off + (long long)k * ev.ts + (k % ev.ts);
-    if (cs.s >= 0) cs.p = b.models[ev.model].st[cs.s];
+    if (k0 == 1) { st.pp0 = 0; st.pp1 = ev.n0; }
+    else col_band(b, ev, rev, k0 - 1, st.pp0, st.pp1);
 }
 
 struct FillOut               // where one direction's band columns go
@@ -275,112 +301,131 @@ struct FillOut               // where one direction's band columns go
     double* Mm; double* Ms; int* Mi0; int* Mlen; double* Mcb; int* Mcbi;
 };
 
-// Wavefront schedule of one (event, direction): cell (k, i) is computed at step d = k + i by the
-// thread that owns column k (k = tid+1, tid+1+T, ...).  Steps are taken four at a time:
-//   * the emissions of the thread's next four cells do not depend on the recurrence, so they are
-//     evaluated first, back to back (independent division-free chains);
-//   * the four barrier-separated steps that follow only carry the max-plus recurrence; the two
-//     horizontal inputs come from the left neighbour through a 4-deep shared-memory ring indexed
-//     by the (compile-time) step-in-batch, the vertical one stays in registers.
-// A thread moves to its next column only at a batch boundary; the host guarantees
-// dlo(k+T) >= dhi(k) + 5 for every k (ps_host.cu: wave_threads), so no cell is skipped.
 template <bool REV, int MAXT>
 __device__ __forceinline__ void fill_wave(const Batch& b, const EvDesc& ev, const FillOut& o, double* smem)
 {
     const int T = blockDim.x, tid = threadIdx.x;
     const int n0 = ev.n0, N = ev.N;
-    const long long ts = ev.ts;
-    // [4][MAXT] rings of the last four steps: main-matrix values, and emissions (the reverse pass adds
-    // the source cell's); the stride is the compile-time MAXT so every slot is an immediate offset
+    const long long rs = ev.rs;
+    const int J = (N + CW - 1) / CW;                      // strips
+    // [4][MAXT] rings of the last four steps: last-column main values and (reverse pass) emissions
     double* myC = smem + tid;
     double* myE = smem + 4 * MAXT + tid;
+    const int left = tid == 0 ? T - 1 : tid - 1;
+    const double* lfC = smem + left;
+    const double* lfE = smem + 4 * MAXT + left;
     const LevelRec* lev = b.lev + ev.lev_off;
     const ModelDev& md = b.models[ev.model];
     const Trans tr = {md.lskip, md.lstay, md.lext, md.lins};
     const double off = b.lik_offset, l2p = b.log2pi;
 
-    ColSetup cur, nxt;
-    fill_setup(b, ev, REV, tid + 1, cur);
-    fill_setup(b, ev, REV, tid + 1 + T, nxt);
+    Strip cur;
+    strip_setup(b, ev, REV, tid, cur);
     int dstart, dend;
     {
-        int a0, a1, z0, z1;
-        const int c1 = REV ? N : 1, cN = REV ? 1 : N;
-        const int cen1 = b.cen_old[ev.cen_off + c1], cenN = b.cen_old[ev.cen_off + cN];
-        band_of(REV ? n0 - cen1 + 1 : cen1, n0, b.realign_width, a0, a1);
-        band_of(REV ? n0 - cenN + 1 : cenN, n0, b.realign_width, z0, z1);
-        dstart = 1 + a0; dend = N + z1;
+        int a0, a1, z0 = 1 << 30, z1 = 0;
+        col_band(b, ev, REV, 1, a0, a1);
+        for (int k = CW * (J - 1) + 1; k <= N; k++) { int u0, u1; col_band(b, ev, REV, k, u0, u1); z0 = min(z0, u0); z1 = max(z1, u1); }
+        // the first strip starts at its lowest row; the last one ends at its highest
+        int f0 = a0;
+        for (int k = 2; k <= min(CW, N); k++) { int u0, u1; col_band(b, ev, REV, k, u0, u1); f0 = min(f0, u0); }
+        dstart = 0 + f0; dend = (J - 1) + z1;
     }
-    double upC = 0, upS = 0, upE = 0, best = NEG;
-    int besti = 0;
-    const int left = tid == 0 ? T - 1 : tid - 1;
-    const double* lfC = smem + left;
-    const double* lfE = smem + 4 * MAXT + left;
-    for (int db = dstart; db <= dend; db += 4)
+    double upC[CW], upS[CW], upE[CW], best[CW];
+    int besti[CW];
+#pragma unroll
+    for (int c = 0; c < CW; c++) { upC[c] = 0; upS[c] = 0; upE[c] = 0; best[c] = NEG; besti[c] = 0; }
+    int ph = dstart & 3;
+    for (int d = dstart; d <= dend; d++)
     {
-        if (db > cur.k + cur.i1)
+        if (d > cur.j + cur.rhi)
         {
-            // column finished: publish its shape and best cell, move on to the prefetched one
-            if (cur.k <= N)
-            {
-                o.Mi0[cur.g] = cur.i0; o.Mlen[cur.g] = cur.i1 - cur.i0 + 1;
-                o.Mcb[cur.g] = best; o.Mcbi[cur.g] = besti;
-            }
-            cur = nxt;
-            fill_setup(b, ev, REV, cur.k + T, nxt);
-            best = NEG; besti = 0;
-        }
-        const int ib = db - cur.k;                                    // row of the first step of the batch
-        const long long a0 = cur.abase + (long long)ib * ts;
-        const bool mine = ib + 3 >= cur.i0 && ib <= cur.i1;           // any of my four cells in the band
-        const bool warp_busy = __any_sync(0xffffffffu, mine);
-        double e4[4] = {0.0, 0.0, 0.0, 0.0};
-        if (mine && cur.s >= 0)
-        {
+            // strip finished: publish the shape and best cell of its columns, take the next strip
 #pragma unroll
-            for (int u = 0; u < 4; u++)
-                if (ib + u >= cur.i0 && ib + u <= cur.i1) e4[u] = cell_emission<REV>(lev, n0, ib + u, cur.p, l2p, off);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-        {
-            if (db + u > dend) break;                                 // uniform across the CTA
-            const int i = ib + u;
-            if (warp_busy && i >= cur.i0 && i <= cur.i1)
+            for (int c = 0; c < CW; c++)
             {
-                double C = 0, S = 0;
-                const double e = e4[u];
-                int step = ST_STOP;
-                if (cur.s >= 0)
+                const int k = CW * cur.j + 1 + c;
+                if (cur.j < J && k <= N)
                 {
-                    const bool skip_ok = i >= cur.p0 && i <= cur.p1;
-                    const bool diag_ok = i > cur.p0 && i <= cur.p1;
-                    double Pi = 0, Pi1 = 0, PE = 0;
-                    if (cur.k > 1)
-                    {
-                        Pi = lfC[((u + 3) & 3) * MAXT];               // step d-1: (k-1, i)
-                        Pi1 = lfC[((u + 2) & 3) * MAXT];              // step d-2: (k-1, i-1)
-                        if (REV) PE = lfE[((u + 2) & 3) * MAXT];
-                    }
-                    const double eM = REV ? (diag_ok ? PE : 0.0) : e;
-                    const double eU = REV ? upE : e;
-                    dp_cell(i == cur.i0, skip_ok, diag_ok, Pi, Pi1, eM, eU, upC, upS, tr, C, S, step);
-                    if (C > best) { best = C; besti = i; }
+                    const long long g = ev.col_off + k;
+                    o.Mi0[g] = cur.col[c].i0; o.Mlen[g] = cur.col[c].i1 - cur.col[c].i0 + 1;
+                    o.Mcb[g] = best[c]; o.Mcbi[g] = besti[c];
                 }
-                myC[u * MAXT] = C;
-                if (REV) myE[u * MAXT] = e;
-                const long long a = a0 + u * ts;
-                o.Mm[a] = C; o.Ms[a] = S;
-                if (!REV) b.Fstep[a] = (uint8_t)step;
-                upC = C; upS = S; upE = e;
+                best[c] = NEG; besti[c] = 0;
             }
-            __syncthreads();
+            strip_setup(b, ev, REV, cur.j + T, cur);
         }
+        const int i = d - cur.j;
+        const int w0 = ph, w1 = (ph + 3) & 3, w2 = (ph + 2) & 3;        // steps d, d-1, d-2
+        if (i >= cur.rlo && i <= cur.rhi)
+        {
+            const LevelRec lr = lev[REV ? n0 - i : i - 1];
+            const double lsd3 = REV ? lr.lsd3 : lev[n0 - i].lsd3;
+            // the column left of the strip: left neighbour's last column, or the blank column 0
+            double Pc = 0, Pd = 0, PEd = 0;                              // (k-1, i), (k-1, i-1), E(k-1, i-1)
+            if (cur.j > 0)
+            {
+                Pc = lfC[w1 * MAXT];
+                Pd = lfC[w2 * MAXT];
+                if (REV) PEd = lfE[w2 * MAXT];
+            }
+            int p0 = cur.pp0, p1 = cur.pp1;
+            double Cout[CW], Sout[CW];
+            unsigned steps = 0;
+#pragma unroll
+            for (int c = 0; c < CW; c++)
+            {
+                const ColMeta cm = cur.col[c];
+                double C = 0, S = 0, e = 0;
+                int step = ST_STOP;
+                const bool act = i >= cm.i0 && i <= cm.i1;
+                const double oldC = upC[c], oldE = upE[c];               // (k, i-1) before this row overwrites it
+                if (act)
+                {
+                    if (cm.s >= 0)
+                    {
+                        e = emission(lr.mean, lr.stdv, lr.rstdv, lsd3, cur.p[c], l2p, off);
+                        const bool skip_ok = i >= p0 && i <= p1;
+                        const bool diag_ok = i > p0 && i <= p1;
+                        const double eM = REV ? (diag_ok ? PEd : 0.0) : e;
+                        const double eU = REV ? oldE : e;
+                        dp_cell(i == cm.i0, skip_ok, diag_ok, Pc, Pd, eM, eU, oldC, upS[c], tr, C, S, step);
+                        if (C > best[c]) { best[c] = C; besti[c] = i; }
+                    }
+                    upC[c] = C; upS[c] = S; upE[c] = e;
+                }
+                Cout[c] = C; Sout[c] = S;
+                steps |= (unsigned)step << (8 * c);
+                // this column is the next one's left neighbour
+                Pc = C; Pd = oldC; PEd = oldE;
+                p0 = cm.i0; p1 = cm.i1;
+            }
+            // the last column of the strip is what the right neighbour reads
+            myC[w0 * MAXT] = Pc;
+            if (REV) myE[w0 * MAXT] = upE[CW - 1];
+            const long long a = ev.band_off + ((long long)d * ev.ts + (cur.j % ev.ts)) * CW;   // (strip, row) run
+            double2* pm = reinterpret_cast<double2*>(o.Mm + a);
+            double2* ps = reinterpret_cast<double2*>(o.Ms + a);
+            pm[0] = make_double2(Cout[0], Cout[1]); pm[1] = make_double2(Cout[2], Cout[3]);
+            ps[0] = make_double2(Sout[0], Sout[1]); ps[1] = make_double2(Sout[2], Sout[3]);
+            if (!REV) *reinterpret_cast<unsigned*>(b.Fstep + a) = steps;
+        }
+        __syncthreads();
+        ph = (ph + 1) & 3;
     }
-    if (cur.k <= N)
+    if (cur.j < J)
     {
-        o.Mi0[cur.g] = cur.i0; o.Mlen[cur.g] = cur.i1 - cur.i0 + 1;
-        o.Mcb[cur.g] = best; o.Mcbi[cur.g] = besti;
+#pragma unroll
+        for (int c = 0; c < CW; c++)
+        {
+            const int k = CW * cur.j + 1 + c;
+            if (k <= N)
+            {
+                const long long g = ev.col_off + k;
+                o.Mi0[g] = cur.col[c].i0; o.Mlen[g] = cur.col[c].i1 - cur.col[c].i0 + 1;
+                o.Mcb[g] = best[c]; o.Mcbi[g] = besti[c];
+            }
+        }
     }
 }
 
@@ -393,42 +438,48 @@ __device__ void fill_serial(const Batch& b, const EvDesc& ev, const FillOut& o, 
     const LevelRec* lev = b.lev + ev.lev_off;
     const ModelDev& md = b.models[ev.model];
     const Trans tr = {md.lskip, md.lstay, md.lext, md.lins};
-    ColSetup cs;
+    int p0 = 0, p1 = n0;
     for (int k = 1; k <= N; k++)
     {
-        fill_setup(b, ev, REV, k, cs);
+        int i0, i1;
+        col_band(b, ev, REV, k, i0, i1);
+        const int s = b.states[ev.state_off + (REV ? N - k + 1 : k) - 1];
+        StateParams sp;
+        if (s >= 0) sp = md.st[s];
         double upC = 0, upS = 0, upE = 0, best = NEG;
         int besti = 0;
         double* Ecur = smem + (k & 1) * RS;
         const double* Eprev = smem + ((k - 1) & 1) * RS;
-        for (int i = cs.i0; i <= cs.i1; i++)
+        for (int i = i0; i <= i1; i++)
         {
             double C = 0, S = 0, e = 0;
             int step = ST_STOP;
-            if (cs.s >= 0)
+            if (s >= 0)
             {
-                e = cell_emission<REV>(lev, n0, i, cs.p, b.log2pi, b.lik_offset);
-                const bool skip_ok = i >= cs.p0 && i <= cs.p1;
-                const bool diag_ok = i > cs.p0 && i <= cs.p1;
+                e = cell_emission<REV>(lev, n0, i, sp, b.log2pi, b.lik_offset);
+                const bool skip_ok = i >= p0 && i <= p1;
+                const bool diag_ok = i > p0 && i <= p1;
                 double Pi = 0, Pi1 = 0, PE = 0;
                 if (k > 1)
                 {
                     if (skip_ok) Pi = o.Mm[cell_at(ev, k - 1, i)];
-                    if (diag_ok) { Pi1 = o.Mm[cell_at(ev, k - 1, i - 1)]; PE = Eprev[i - 1 - cs.p0]; }
+                    if (diag_ok) { Pi1 = o.Mm[cell_at(ev, k - 1, i - 1)]; PE = Eprev[i - 1 - p0]; }
                 }
                 const double eM = REV ? (diag_ok ? PE : 0.0) : e;
                 const double eU = REV ? upE : e;
-                dp_cell(i == cs.i0, skip_ok, diag_ok, Pi, Pi1, eM, eU, upC, upS, tr, C, S, step);
+                dp_cell(i == i0, skip_ok, diag_ok, Pi, Pi1, eM, eU, upC, upS, tr, C, S, step);
                 if (C > best) { best = C; besti = i; }
             }
             const long long a = cell_at(ev, k, i);
             o.Mm[a] = C; o.Ms[a] = S;
             if (!REV) b.Fstep[a] = (uint8_t)step;
-            Ecur[i - cs.i0] = e;
+            Ecur[i - i0] = e;
             upC = C; upS = S; upE = e;
         }
-        o.Mi0[cs.g] = cs.i0; o.Mlen[cs.g] = cs.i1 - cs.i0 + 1;
-        o.Mcb[cs.g] = best; o.Mcbi[cs.g] = besti;
+        const long long g = ev.col_off + k;
+        o.Mi0[g] = i0; o.Mlen[g] = i1 - i0 + 1;
+        o.Mcb[g] = best; o.Mcbi[g] = besti;
+        p0 = i0; p1 = i1;
     }
 }
 
@@ -662,9 +713,10 @@ __global__ void __launch_bounds__(256) k_backtrace(Batch b, int smem_levels)
 // the rows present in BOTH bands plus the two running bests (and the floor 0).
 //
 // k_join: old[g] = columnMax(c) = join(F[c], B[N-c+1]) for every band column.  A block covers 32
-// consecutive columns (lane = column) with 8 warps that take the anti-diagonals d = c + jf round
-// robin; with the wavefront-major layout a warp's forward cells (diagonal d) and the matching
-// reverse cells (diagonal N+n0+2-d, columns descending) are each one contiguous 256-byte run.
+// consecutive columns = 8 forward strips (lane = column) with 8 warps that take the wavefront steps
+// d = strip + row round robin; in the wavefront-major layout the forward cells a warp reads in one
+// step are one contiguous 256-byte run, and the matching reverse cells (column N-c+1, row n0-jf+1)
+// form at most two runs.
 __global__ void __launch_bounds__(256) k_join(Batch b)
 {
     const EvDesc ev = b.ev[blockIdx.y];
@@ -674,6 +726,7 @@ __global__ void __launch_bounds__(256) k_join(Batch b)
     const int c = blockIdx.x * 32 + lane + 1;
     const bool have = c <= N;
     const int cb = N - c + 1;                           // reverse column joined with forward column c
+    const int j = (c - 1) >> 2;                         // forward strip of this lane
     int lo = 1, hi = 0;
     double m = 0.0;
     long long gf = 0;
@@ -687,21 +740,21 @@ __global__ void __launch_bounds__(256) k_join(Batch b)
         hi = min(min(f0 + flen - 1, n0 + 1 - b0), n0);
         m = fmax(b.Fbest[gf], b.Bbest[gb]);
     }
-    // common diagonal range of the 32 columns
-    int dlo = have && lo <= hi ? c + lo : 1 << 30, dhi = have && lo <= hi ? c + hi : -1;
+    // common step range of the 32 columns
+    int dlo = have && lo <= hi ? j + lo : 1 << 30, dhi = have && lo <= hi ? j + hi : -1;
     for (int o = 16; o; o >>= 1)
     {
         dlo = min(dlo, __shfl_xor_sync(0xffffffffu, dlo, o));
         dhi = max(dhi, __shfl_xor_sync(0xffffffffu, dhi, o));
     }
-    const int kf = c % ev.ts, kb = cb % ev.ts;
+    const long long fb = have ? col_base(ev, c) : 0, bb = have ? col_base(ev, cb) : 0;
     for (int d = dlo + w; d <= dhi; d += 8)
     {
-        const int jf = d - c;
+        const int jf = d - j;
         if (have && jf >= lo && jf <= hi)
         {
-            const long long af = ev.band_off + (long long)d * ev.ts + kf;
-            const long long ab = ev.band_off + (long long)(N + n0 + 2 - d) * ev.ts + kb;
+            const long long af = fb + (long long)jf * ev.rs;
+            const long long ab = bb + (long long)(n0 - jf + 1) * ev.rs;
             m = fmax(m, fmax(b.Fm[af] + b.Bm[ab], b.Fs[af] + b.Bs[ab]));
         }
     }
@@ -878,7 +931,7 @@ __global__ void __launch_bounds__(128) k_mutscore(Batch b)
                 {
                     const long long gs = ev.col_off + startind;
                     p0 = b.Fi0[gs]; p1 = p0 + b.Flen[gs] - 1;
-                    seed = b.Fm + ev.band_off + (long long)startind * ev.ts + (startind % ev.ts);   // + row * ts
+                    seed = b.Fm + col_base(ev, startind);          // + row * rs
                     best = b.Fbest[gs];
                 }
                 // reverse column to join with
@@ -887,10 +940,10 @@ __global__ void __launch_bounds__(128) k_mutscore(Batch b)
                 int b0 = 0, blen = n0 + 1;
                 double mb = 0.0;
                 if (rab > 0) { b0 = b.Bi0[gb]; blen = b.Blen[gb]; mb = b.Bbest[gb]; }
-                const long long bbase = ev.band_off + (long long)rab * ev.ts + (rab % ev.ts);   // + reverse row * ts
+                const long long bbase = col_base(ev, rab);            // + reverse row * rs
                 const double* Bm = b.Bm + bbase;
                 const double* Bs = b.Bs + bbase;
-                const long long ts = ev.ts;
+                const long long ts = ev.rs;
                 double joinmax = 0.0;
                 for (int c = startind + 1; c <= last; c++)
                 {

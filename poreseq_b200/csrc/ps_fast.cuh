@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(128) k_mutscore_f32(Batch b, int mask)
             {
                 const StateParamsF* stf = b.stf + (size_t)ev.model * N_STATES;
                 const bool ri_empty = b.ri_empty[e] != 0;
-                const long long ts = ev.ts;
+                const long long ts = ev.rs;
                 ColF q;
                 q.ringC = ringf + threadIdx.x;
                 q.lev = b.levf + ev.lev_off;
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(128) k_mutscore_f32(Batch b, int mask)
                 {
                     const long long gs = ev.col_off + startind;
                     q.p0 = b.Fi0[gs]; q.p1 = q.p0 + b.Flen[gs] - 1;
-                    const double* seed = b.Fm + ev.band_off + (long long)startind * ts + (startind % ev.ts);
+                    const double* seed = b.Fm + col_base(ev, startind);
                     best_d = b.Fbest[gs];
                     // rebase to the seed value on the band centre of the first narrow column
                     const int mid = min(max((f0 + f1) >> 1, q.p0), q.p1);
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(128) k_mutscore_f32(Batch b, int mask)
                     const long long gb = ev.col_off + rab;
                     q.b0 = b.Bi0[gb]; q.b1 = q.b0 + b.Blen[gb] - 1;
                     mb = b.Bbest[gb];
-                    const long long bbase = ev.band_off + (long long)rab * ts + (rab % ev.ts);
+                    const long long bbase = col_base(ev, rab);
                     q.Bm = b.Bm + bbase; q.Bs = b.Bs + bbase;
                 }
                 int i0 = f0, i1 = f1;

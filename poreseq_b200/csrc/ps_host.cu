@@ -78,8 +78,9 @@ int ps_ctx::init()
     CU(cudaStreamCreate(&stream));
     for (int i = 0; i <= PS_T_COUNT; i++) CU(cudaEventCreate(&tev[i]));
     CU(cudaFuncSetAttribute(k_backtrace, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
-    CU(cudaFuncSetAttribute(k_fill<352, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    CU(cudaFuncSetAttribute(k_fill<640, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CU(cudaFuncSetAttribute(k_fill<160, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CU(cudaFuncSetAttribute(k_fill<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CU(cudaFuncSetAttribute(k_fill<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU(cudaFuncSetAttribute(k_fill<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU(cudaFuncSetAttribute(k_mutscore<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU(cudaFuncSetAttribute(k_mutscore<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -258,7 +259,7 @@ struct Job
     std::vector<const HostModel*> model_src;
     std::vector<int> wave_need, plan_lo, plan_hi;
     std::vector<double> narrow_cols;             // per region: sum over its mutations of (|mut|+5)
-    int wave_threads = 64;
+    int wave_threads = 32;
     double bias = -1e-6;                         // start value of every mutation's sum over events
     double wide_cells_fwd = 0, narrow_cells = 0;
     long long n_levels, n_cols, n_cen, n_tasks, n_muts, n_band;
@@ -292,7 +293,7 @@ void Job::plan_event(const HostEvent& he, const EvDesc& d)
     const int N = d.N, n0 = he.n0, rw = regs[0]->params.realign_width;
     const size_t base = cen_old.size();
     cen_old.fill((size_t)N + cen_pad + 1, 1);
-    int ok = 1, need = 64;
+    int ok = 1, need = 32;
     if (!he.ri_empty)
     {
         const std::vector<double>& ri = he.ref_index;
@@ -318,25 +319,30 @@ void Job::plan_event(const HostEvent& he, const EvDesc& d)
     }
     if (d.usable && ok)
     {
-        plan_lo.resize(N + 2); plan_hi.resize(N + 2);
+        // strips of CW columns in processing order: strip j runs rows [lo_j, hi_j] at steps j + row
+        const int J = (N + CW - 1) / CW;
+        plan_lo.resize(J + 1); plan_hi.resize(J + 1);
         std::vector<int>& lo = plan_lo; std::vector<int>& hi = plan_hi;
         for (int dir = 0; dir < 2; dir++)
         {
+            for (int j = 0; j < J; j++) { lo[j] = 1 << 30; hi[j] = 0; }
             for (int k = 1; k <= N; k++)
             {
                 const int c = dir ? N - k + 1 : k;
                 int mid = dir ? n0 - cen_old[base + c] + 1 : cen_old[base + c];
                 mid = std::min(std::max(mid, 1), n0);
                 const int i0 = std::max(1, mid - rw), i1 = std::min(n0, mid + rw);
-                lo[k] = k + i0; hi[k] = k + i1;
+                const int j = (k - 1) / CW;
+                lo[j] = std::min(lo[j], j + i0); hi[j] = std::max(hi[j], j + i1);
                 if (!dir) wide_cells_fwd += i1 - i0 + 1;
             }
-            int kk = 1;
-            for (int k = 1; k <= N; k++)
+            // a thread's next strip (j+T) must start after its current one (j) has ended
+            int jj = 1;
+            for (int j = 0; j < J; j++)
             {
-                if (kk <= k) kk = k + 1;
-                while (kk <= N && lo[kk] < hi[k] + 5) kk++;
-                need = std::max(need, kk - k);
+                if (jj <= j) jj = j + 1;
+                while (jj < J && lo[jj] <= hi[j]) jj++;
+                need = std::max(need, jj - j);
             }
         }
         if (need <= 1024) wave_threads = std::max(wave_threads, need);
@@ -474,15 +480,18 @@ int Job::build()
     n_muts = (long long)mdev.size();
     // wavefront-major band storage: stride = wavefront width for monotone events (at most that many
     // columns are live on one anti-diagonal), N+1 for the serially filled ones
-    wave_threads = std::min(std::max(((wave_threads + 31) / 32) * 32, 64), 1024);
+    wave_threads = std::min(std::max(((wave_threads + 31) / 32) * 32, 32), 1024);
     for (size_t e = 0; e < ev.size(); e++)
     {
         EvDesc& d = ev[e];
-        if (!d.usable) { d.ts = 1; d.band_off = n_band; continue; }
+        if (!d.usable) { d.ts = 1; d.rs = CW; d.band_off = n_band; continue; }
         if (mono[e] && wave_need[e] > wave_threads) mono[e] = 0;
-        d.ts = mono[e] ? wave_threads : d.N + 1;
-        d.band_off = n_band;
-        n_band += (long long)(d.N + d.n0 + 3) * d.ts;
+        // slots per wavefront step: the wavefront width for monotone events, one per strip for the serial ones
+        const int J = (d.N + CW - 1) / CW;
+        d.ts = mono[e] ? wave_threads : J + 1;
+        d.rs = d.ts * CW;
+        d.band_off = n_band;                      // multiple of CW: keeps the 32-byte row runs aligned
+        n_band += (long long)(J + d.n0 + 3) * d.rs;
     }
     return PS_OK;
 }
@@ -626,10 +635,12 @@ int Job::run(bool full)
     // wavefront fill: one CTA per (event, direction), forward and reverse in one launch (grid.y = 2)
     {
         const int T = wave_threads;
-        const size_t smem = std::max<size_t>(8 * (T <= 352 ? 352 : T <= 640 ? 640 : 1024), 2 * b.RS) * sizeof(double);
+        const int maxt = T <= 160 ? 160 : T <= 256 ? 256 : T <= 512 ? 512 : 1024;
+        const size_t smem = std::max<size_t>(8 * maxt, 2 * b.RS) * sizeof(double);
         dim3 grid(nev, full ? 2 : 1);
-        if (T <= 352) k_fill<352, 2><<<grid, T, smem, ctx->stream>>>(b, 0);
-        else if (T <= 640) k_fill<640, 1><<<grid, T, smem, ctx->stream>>>(b, 0);
+        if (T <= 160) k_fill<160, 3><<<grid, T, smem, ctx->stream>>>(b, 0);
+        else if (T <= 256) k_fill<256, 1><<<grid, T, smem, ctx->stream>>>(b, 0);
+        else if (T <= 512) k_fill<512, 1><<<grid, T, smem, ctx->stream>>>(b, 0);
         else k_fill<1024, 1><<<grid, T, smem, ctx->stream>>>(b, 0);
         LAUNCHED();
     }
