@@ -175,9 +175,12 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--regions", type=int, default=16, help="1 kb regions per GPU per step")
+    ap.add_argument("--regions", type=int, default=22, help="1 kb regions per GPU per step (22 x 40 fill CTAs ~ 2 full waves of 148 SMs x 3)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="fast", choices=["fast", "exact"],
+                    help="fast: FP32 mutation scan + exact FP64 re-score of every candidate (decisions and accepted scores "
+                         "bit-identical, other scores within 1e-4 relative); exact: everything FP64 bit-identical")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -206,38 +209,54 @@ def main():
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize()
 
-    ctx = poreseqcpp.Context(local_rank)
+    # two contexts (two streams, two sets of staging / device buffers) on this rank's GPU: while the GPU
+    # works on step k the host marshals and stages step k+1 (ps_score_points_batch_begin / _end)
+    ctxs = [poreseqcpp.Context(local_rank), poreseqcpp.Context(local_rank)]
+    for c in ctxs:
+        c.set_precision(args.precision)
+    ctx = ctxs[0]
     regions = make_regions(args.regions, seed0=1 + rank * args.regions)
     cells = [algorithmic_cells(r) for r in regions]
     wide_cells = sum(c[0] for c in cells)
     narrow_cells = sum(c[1] for c in cells)
     step_cells = wide_cells + narrow_cells
     h2d = sum(region_bytes(r) for r in regions)
+    phase = {}
 
-    def step():
-        nrs = [poreseqcpp.NativeRegion(ctx, r.sequence, r.events, r.params, "point_width") for r in regions]
-        out = poreseqcpp.score_points_batch(ctx, nrs)
-        for nr in nrs:
+    def begin(c):
+        nrs = [poreseqcpp.NativeRegion(c, r.sequence, r.events, r.params, "point_width") for r in regions]
+        return poreseqcpp.score_points_batch_begin(c, nrs)
+
+    def end(p, record):
+        out = p.end()
+        if record:
+            for k, v in p.ctx.last_timing().items():
+                phase[k] = phase.get(k, 0.0) + v
+        for nr in p.regions:
             nr.close()
         return out
 
-    for _ in range(max(args.warmup, 3)):
-        out = step()
+    def run_steps(count, record):
+        pending, out = None, None
+        for k in range(count):
+            p = begin(ctxs[k % 2])
+            if pending is not None:
+                out = end(pending, record)
+            pending = p
+        return end(pending, record)
+
+    out = run_steps(max(args.warmup, 3), False)
     d2h = sum(8 * len(o[3]) for o in out) + sum(2 * 8 * len(ev.mean) for r in regions for ev in r.events)
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    phase = {}
-    launches0 = ctx.launch_count()
+    launches0 = sum(c.launch_count() for c in ctxs)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-        for k, v in ctx.last_timing().items():
-            phase[k] = phase.get(k, 0.0) + v
+    run_steps(args.steps, True)
     barrier()
     wall = time.perf_counter() - t0
-    launches = ctx.launch_count() - launches0
+    launches = sum(c.launch_count() for c in ctxs) - launches0
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -267,13 +286,15 @@ def main():
     line = {
         "metric": METRIC, "value": total_cells / (dev_ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": wall_ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64" if args.precision == "fast" else "f64", "data": "synthetic",
         "config": {"workload": "ScorePoints (FindPointMutations+ScoreMutations) on 1 kb regions x 10x coverage, "
                                "point_width 20, realign_width 300",
                    "regions_per_gpu_per_step": args.regions, "events_per_region": 2 * COVERAGE,
                    "mutations_per_region": 8 * (REGION_LEN - 4), "cells_per_step_per_gpu": step_cells,
                    "l2": "band working set %.0f MB per step exceeds the 126 MB L2" % (wide_cells * 16.5 / 1e6),
-                   "precision": "fp64 exact (bit-identical to the reference)"},
+                   "pipelining": "2 contexts: host staging of step k+1 overlaps kernels of step k",
+                   "precision": ("fp32 mutation scan + exact fp64 re-score of all candidates > -tau; wide fills/backtrace fp64"
+                                 if args.precision == "fast" else "fp64 exact (bit-identical to the reference)")},
         "e2e": {"value": total_cells / (wall_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
         "clocks": clocks,

@@ -137,6 +137,14 @@ int         ps_score_points_batch(ps_region* const* regions, int n_regions, int 
                                   int* n_out, long long* off_out,
                                   int* start, char* orig, char* mut, double* scores);
 
+/* Asynchronous form: _begin stages the batch and enqueues copies + kernels on the context's stream
+ * and returns; _end waits and delivers the scores.  One batch in flight per context; the regions
+ * must stay alive and untouched in between.  Two contexts on one device let the host stage batch
+ * k+1 while the GPU works on batch k. */
+int         ps_score_points_batch_begin(ps_region* const* regions, int n_regions, int cap,
+                                        int* n_out, long long* off_out, int* start, char* orig, char* mut);
+int         ps_score_points_batch_end(ps_ctx* ctx, double* scores);
+
 /* ---- candidate discovery and the consensus iteration ------------------------------------------- */
 /* vector<MutInfo> FindMutations(AlignData&, const vector<Sequence>&)   cpp/Mutations.h:18,
  * cpp/FindMutations.cpp:24-186.  The result is held by the region; fetch entry i with

@@ -281,7 +281,11 @@ struct Job
     int build();
     int upload();
     int run(bool backward_and_muts);
-    int download(std::vector<double>* align_scores, std::vector<double>* mut_scores);
+    int download_enqueue();                      // D2H copies + completion event on the stream
+    int finish(std::vector<double>* align_scores, std::vector<double>* mut_scores);   // sync + scatter
+    PinVec<int> rs, re;
+    PinVec<double> best, msc;
+    bool have_scores = false;
 };
 
 // Band centres of the wide fill (cpp/EventData.h:172-183: lower_bound over ref_index; 1 when the
@@ -716,11 +720,11 @@ int Job::run(bool full)
     return PS_OK;
 }
 
-int Job::download(std::vector<double>* align_scores, std::vector<double>* mut_scores)
+int Job::download_enqueue()
 {
     const size_t nl = (size_t)n_levels, ne = ev.size();
-    PinVec<int> rs = ctx->pinned<int>("refstart"), re = ctx->pinned<int>("refend");
-    PinVec<double> best = ctx->pinned<double>("evbest"), msc = ctx->pinned<double>("mscores");
+    rs = ctx->pinned<int>("refstart"); re = ctx->pinned<int>("refend");
+    best = ctx->pinned<double>("evbest"); msc = ctx->pinned<double>("mscores");
     if (!rs.resize(ne) || !re.resize(ne) || !best.resize(ne) || !msc.resize((size_t)n_muts))
     {
         ps_set_error(ctx, "out of host memory staging the results");
@@ -739,10 +743,16 @@ int Job::download(std::vector<double>* align_scores, std::vector<double>* mut_sc
         CU(cudaMemcpyAsync(re.data(), b.refend, ne * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaMemcpyAsync(best.data(), d_evbest, ne * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     }
-    const bool have_scores = mut_scores && n_muts && n_tasks;
+    have_scores = want_muts && n_muts && n_tasks;
     if (have_scores)
         CU(cudaMemcpyAsync(msc.data(), b.scores, (size_t)n_muts * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     MARK(PS_T_TOTAL);
+    return PS_OK;
+}
+
+int Job::finish(std::vector<double>* align_scores, std::vector<double>* mut_scores)
+{
+    const size_t ne = ev.size();
     CU(cudaStreamSynchronize(ctx->stream));
     // scatter the realigned events back into their regions
     size_t e = 0;
@@ -789,34 +799,48 @@ int Job::download(std::vector<double>* align_scores, std::vector<double>* mut_sc
 
 // ------------------------------------------------------------------------------------------
 // drivers shared by the C entry points
-static int run_job(ps_ctx* ctx, const std::vector<ps_region*>& regs, const std::vector<MutSpec>* muts,
-                   std::vector<double>* align_scores, std::vector<double>* mut_scores, double bias = -1e-6)
+// One job = build (host staging) + upload + kernels + result copies, all enqueued on the context's
+// stream by job_begin; job_end waits for the stream and scatters the results into the regions.
+// Between the two the host is free (e.g. to stage the next batch on another context).
+static int job_begin(ps_ctx* ctx, const std::vector<ps_region*>& regs, const std::vector<MutSpec>* muts, double bias)
 {
     TRY(ctx->init());
     CU(cudaSetDevice(ctx->device));
+    if (ctx->pending) { ps_set_error(ctx, "a batch is already in flight on this context"); return PS_E_ARG; }
     for (ps_region* R : regs)
         if (R->bases.size() < 5) { ps_set_error(ctx, "sequences shorter than 5 bases are not supported"); return PS_E_ARG; }
-    const bool trace = getenv("PORESEQ_B200_TRACE") != nullptr;
-    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    const double t0 = now();
-    Job job(ctx);
-    job.regs = regs;
-    job.want_muts = muts != nullptr;
-    if (muts) job.muts = *muts;
-    job.bias = bias;
-    job.fast = ctx->precision == PS_PRECISION_FAST && muts != nullptr;
-    TRY(job.build());
-    const double t1 = now();
-    MARK(PS_T_H2D);
-    TRY(job.upload());
-    const double t2 = now();
-    TRY(job.run(muts != nullptr));
-    const double t3 = now();
-    TRY(job.download(align_scores, mut_scores));
-    const double t4 = now();
-    if (trace) fprintf(stderr, "[ps] build %.2f ms  upload(enqueue) %.2f  run(enqueue) %.2f  download+sync+scatter %.2f  (device %.2f)\n",
-                       t1 - t0, t2 - t1, t3 - t2, t4 - t3, ctx->timing[PS_T_TOTAL]);
+    Job* job = new Job(ctx);
+    job->regs = regs;
+    job->want_muts = muts != nullptr;
+    if (muts) job->muts = *muts;
+    job->bias = bias;
+    job->fast = ctx->precision == PS_PRECISION_FAST && muts != nullptr;
+    int rc = job->build();
+    if (!rc) rc = (cudaEventRecord(ctx->tev[PS_T_H2D], ctx->stream) == cudaSuccess) ? PS_OK : PS_E_CUDA;
+    if (!rc) rc = job->upload();
+    if (!rc) rc = job->run(muts != nullptr);
+    if (!rc) rc = job->download_enqueue();
+    if (rc) { delete job; return rc; }
+    ctx->pending = job;
     return PS_OK;
+}
+
+static int job_end(ps_ctx* ctx, std::vector<double>* align_scores, std::vector<double>* mut_scores)
+{
+    Job* job = (Job*)ctx->pending;
+    if (!job) { ps_set_error(ctx, "no batch in flight on this context"); return PS_E_ARG; }
+    CU(cudaSetDevice(ctx->device));
+    ctx->pending = nullptr;
+    int rc = job->finish(align_scores, mut_scores);
+    delete job;
+    return rc;
+}
+
+static int run_job(ps_ctx* ctx, const std::vector<ps_region*>& regs, const std::vector<MutSpec>* muts,
+                   std::vector<double>* align_scores, std::vector<double>* mut_scores, double bias = -1e-6)
+{
+    TRY(job_begin(ctx, regs, muts, bias));
+    return job_end(ctx, align_scores, mut_scores);
 }
 
 int ps_run_alignments(ps_ctx* ctx, const std::vector<ps_region*>& regs,
@@ -1147,10 +1171,10 @@ static long long write_points(const ps_region* R, long long at, long long cap, i
     return n;
 }
 
-int ps_score_points_batch(ps_region* const* regions, int n_regions, int cap, int* n_out, long long* off_out,
-                          int* start, char* orig, char* mut, double* scores)
+int ps_score_points_batch_begin(ps_region* const* regions, int n_regions, int cap, int* n_out, long long* off_out,
+                                int* start, char* orig, char* mut)
 {
-    if (!regions || n_regions <= 0) return PS_E_ARG;
+    if (!regions || n_regions <= 0 || !regions[0]) return PS_E_ARG;
     ps_ctx* ctx = regions[0]->ctx;
     std::vector<ps_region*> regs(regions, regions + n_regions);
     std::vector<MutSpec> per(n_regions);
@@ -1165,10 +1189,23 @@ int ps_score_points_batch(ps_region* const* regions, int n_regions, int cap, int
         at += n;
     }
     if (at > cap) { ps_set_error(ctx, "output capacity %d < %lld point mutations", cap, at); return PS_E_CAPACITY; }
+    return job_begin(ctx, regs, &per, -1e-6);
+}
+
+int ps_score_points_batch_end(ps_ctx* ctx, double* scores)
+{
+    if (!ctx) return PS_E_ARG;
     std::vector<double> sc;
-    TRY(run_job(ctx, regs, &per, nullptr, &sc));
+    TRY(job_end(ctx, nullptr, &sc));
     if (scores) std::copy(sc.begin(), sc.end(), scores);
     return PS_OK;
+}
+
+int ps_score_points_batch(ps_region* const* regions, int n_regions, int cap, int* n_out, long long* off_out,
+                          int* start, char* orig, char* mut, double* scores)
+{
+    TRY(ps_score_points_batch_begin(regions, n_regions, cap, n_out, off_out, start, orig, mut));
+    return ps_score_points_batch_end(regions[0]->ctx, scores);
 }
 
 int ps_score_points(ps_region* R, int cap, int* n, int* start, char* orig, char* mut, double* scores)

@@ -45,6 +45,7 @@ struct ps_ctx
     double timing[PS_T_COUNT] = {0};
     double wide_cells = 0, narrow_cells = 0;
     long long launches = 0;
+    void* pending = nullptr;                  // the batch in flight between *_begin and *_end (a Job)
     std::string error;
     std::map<std::string, DevBuf> bufs;       // grow-only named device buffers, reused across calls
     std::map<std::string, PinBuf> pins;       // grow-only named pinned host buffers

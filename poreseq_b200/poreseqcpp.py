@@ -68,6 +68,9 @@ def lib():
     L.ps_score_points.argtypes = [C.c_void_p, C.c_int, _c_int_p, _c_int_p, C.c_char_p, C.c_char_p, _c_double_p]
     L.ps_score_points_batch.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, _c_int_p, C.POINTER(C.c_longlong),
                                         _c_int_p, C.c_char_p, C.c_char_p, _c_double_p]
+    L.ps_score_points_batch_begin.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, _c_int_p, C.POINTER(C.c_longlong),
+                                              _c_int_p, C.c_char_p, C.c_char_p]
+    L.ps_score_points_batch_end.argtypes = [C.c_void_p, _c_double_p]
     L.ps_make_mutations.argtypes = [C.c_void_p, C.c_int, _c_int_p, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), _c_double_p, _c_int_p]
     L.ps_refine.argtypes = [C.c_void_p, _c_int_p]
     L.ps_seq_to_states.argtypes = [C.c_char_p, C.c_int, _c_int_p]
@@ -327,6 +330,39 @@ def score_points_batch(ctx, regions):
         a, b = off[k], off[k] + n_out[k]
         out.append((st[a:b], og.raw[a:b], mu.raw[a:b], sc[a:b]))
     return out
+
+
+class PendingBatch(object):
+    """A ps_score_points_batch in flight (ps_score_points_batch_begin / _end)."""
+
+    def __init__(self, ctx, regions):
+        self.ctx, self.regions = ctx, regions
+        n = len(regions)
+        handles = (C.c_void_p * n)(*[r.handle for r in regions])
+        cap = sum(8 * max(ctx.lib.ps_region_sequence_length(r.handle), 1) for r in regions)
+        self.n_out = (C.c_int * n)()
+        self.off = (C.c_longlong * n)()
+        self.st = np.zeros(cap, dtype=np.int32)
+        self.og = C.create_string_buffer(cap)
+        self.mu = C.create_string_buffer(cap)
+        self.sc = np.zeros(cap)
+        ctx.check(ctx.lib.ps_score_points_batch_begin(handles, n, cap, self.n_out, self.off,
+                                                      self.st.ctypes.data_as(_c_int_p), self.og, self.mu))
+
+    def end(self):
+        """Wait for the batch; returns [(start, orig bytes, mut bytes, score)] per region."""
+        self.ctx.check(self.ctx.lib.ps_score_points_batch_end(self.ctx.handle, _dp(self.sc)))
+        out = []
+        for k in range(len(self.regions)):
+            a, b = self.off[k], self.off[k] + self.n_out[k]
+            out.append((self.st[a:b], self.og.raw[a:b], self.mu.raw[a:b], self.sc[a:b]))
+        return out
+
+
+def score_points_batch_begin(ctx, regions):
+    """Asynchronous ps_score_points_batch: stage + enqueue now, `.end()` later.  With two contexts on
+    one device the host can stage batch k+1 while the GPU works on batch k."""
+    return PendingBatch(ctx, regions)
 
 
 def _score_objects(starts, origs, muts, scores):
