@@ -220,11 +220,15 @@ def main():
     wide_cells = sum(c[0] for c in cells)
     narrow_cells = sum(c[1] for c in cells)
     step_cells = wide_cells + narrow_cells
-    h2d = sum(region_bytes(r) for r in regions)
+    h2d = sum(region_bytes(r) for r in regions)      # host bytes marshalled per step (the H2D payload is the same data re-laid out)
     phase = {}
 
+    # the step's inputs as host buffers (one set of concatenated level arrays + model table per region);
+    # every step marshals them into fresh native regions: 1 ps_region_create + 1 ps_region_add_events each
+    packs = [poreseqcpp.PackedRegion(r.sequence, r.events, r.params) for r in regions]
+
     def begin(c):
-        nrs = [poreseqcpp.NativeRegion(c, r.sequence, r.events, r.params, "point_width") for r in regions]
+        nrs = [poreseqcpp.NativeRegion.from_packed(c, p, "point_width") for p in packs]
         return poreseqcpp.score_points_batch_begin(c, nrs)
 
     def end(p, record):

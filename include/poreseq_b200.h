@@ -96,6 +96,16 @@ int         ps_region_add_event(ps_region* r, int n0,
                                 const double* sd_mean, const double* sd_stdv,
                                 int complement, double prob_skip, double prob_stay,
                                 double prob_extend, double prob_insert, const char* seq2d);
+/* The same for all events of a region in one call (the whole PythonToEvents loop,
+ * poreseq/_poreseqcpp.pyx:99-129): the level arrays of the events are concatenated (sum of n0[e]
+ * entries each), models is a table of n_models x 4 x PS_N_STATES doubles (level_mean, level_stdv,
+ * sd_mean, sd_stdv per model), probs n_models x 4 (skip, stay, extend, insert), model_index[e]
+ * picks the event's model.  complement and seq2d may be NULL. */
+int         ps_region_add_events(ps_region* r, int n_events, const int* n0,
+                                 const double* mean, const double* stdv,
+                                 const double* ref_align, const double* ref_like,
+                                 const int* model_index, int n_models, const double* models,
+                                 const double* probs, const int* complement, const char* const* seq2d);
 int         ps_region_set_params(ps_region* r, const ps_params* params);
 int         ps_region_num_events(ps_region* r);
 int         ps_region_sequence_length(ps_region* r);

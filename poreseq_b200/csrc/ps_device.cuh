@@ -147,23 +147,29 @@ __device__ __forceinline__ double cell_emission(const LevelRec* lev, int n0, int
 
 struct Trans { double lskip, lstay, lext, lins; };
 
-// Band storage, wavefront-major.  The fill gives every thread a strip of CW consecutive columns
-// (strip j = columns CW*j+1 .. CW*j+CW) and computes row i of strip j at step j + i.  A cell is
-// stored where its step puts it: the CW cells of (strip j, row i) are contiguous, strips that are
-// computed in the same step are neighbours (slot j % ts), successive rows of a column are `rs`
-// apart.  So every step of the fill writes one contiguous run per warp, and a reader that walks
-// down a column uses a fixed stride:   cell (k, i)  ->  col_base(k) + i * rs.
-constexpr int CW = 4;
+// Band storage, wavefront-major.  The fill gives every thread a strip of CW = 2 consecutive columns
+// (strip j = columns 2j+1, 2j+2) and computes one row pair r (rows 2r+1, 2r+2) of its strip per step
+// d = j + r.  The 2x2 tile of (strip j, row pair r) is stored where its step puts it: 4 contiguous
+// cells [row 2r+1: col 0, col 1; row 2r+2: col 0, col 1], tiles computed in the same step are
+// neighbours (slot j % ts).  So every step of the fill writes one contiguous run per warp, and a
+// reader that walks down a column alternates between +2 and the row-pair stride rs = 4 ts:
+//   cell (k, i)  ->  col_base(k) + row_off(rs, i).
+constexpr int CW = 2;
 
 __device__ __forceinline__ long long col_base(const EvDesc& ev, int k)
 {
-    const int j = (k - 1) >> 2, c = (k - 1) & 3;
-    return ev.band_off + ((long long)j * ev.ts + (j % ev.ts)) * CW + c;
+    const int j = (k - 1) >> 1;
+    return ev.band_off + ((long long)j * ev.ts + (j % ev.ts)) * 4 + ((k - 1) & 1);
+}
+
+__device__ __forceinline__ long long row_off(long long rs, int i)      // i >= 1
+{
+    return (long long)((i - 1) >> 1) * rs + (((i - 1) & 1) << 1);
 }
 
 __device__ __forceinline__ long long cell_at(const EvDesc& ev, int k, int i)
 {
-    return col_base(ev, k) + (long long)i * ev.rs;
+    return col_base(ev, k) + row_off(ev.rs, i);
 }
 
 // One cell of the coupled (main C, stay S) recurrence, cpp/Alignment.cpp:194-271 (forward) and
@@ -244,26 +250,34 @@ __global__ void k_centres(Batch b, int* cen, int check_mono)
 // ------------------------------------------------------------------------------------------
 // k_fill: wide-band fill of one (event, direction) per CTA.
 //
-// Wavefront over (strip, row): thread t owns the strips j = t, t+T, ... (CW = 4 consecutive columns
-// each, in processing order k = c forward, k = N-c+1 reverse) and at step d computes row i = d - j of
-// its current strip, left to right through the 4 columns.  Inside the strip every dependency is a
-// register: (k, i-1) and (k-1, i-1) are last row's values, (k-1, i) was computed a moment ago.  Only
-// the strip's first column looks outside: (k-1, i) and (k-1, i-1) are the left neighbour's last
-// column at steps d-1 and d-2, read from a 4-deep shared-memory ring.  One level record feeds the 4
-// emissions of the row (4 independent division-free chains), one barrier separates steps, and the
-// row's 4 cells leave as one contiguous 32-byte run per matrix.
+// Wavefront over (strip, row pair): thread t owns the strips j = t, t+T, ... (2 consecutive columns
+// each, in processing order k = c forward, k = N-c+1 reverse) and at step d computes the 2x2 tile of
+// row pair r = d - j of its current strip.  Inside the tile and down the strip every dependency is a
+// register; only the strip's first column looks outside: rows 2r, 2r+1, 2r+2 of the left
+// neighbour's second column were produced at steps d-2 and d-1 and are read from a 4-deep
+// shared-memory ring.  One barrier separates steps.
+//
+// The step body is branch-free so that the four emissions (3 reciprocal divisions each) and the four
+// cells' candidate scores interleave: every term of a cell except the horizontal move is folded into
+// (M1, code) first, and the only serial dependency between horizontally adjacent cells is
+//     C = (skip_ok && Pc + lskip >= M1) ? Pc + lskip : M1
+// which returns the value and step code of cpp/Alignment.cpp:252-267 (ties: skip precedes every other
+// main-matrix move and the stay matrix only wins when strictly greater) as long as lskip <= 0;
+// events with prob_skip > 1 take the serial schedule.
+//
 // With nondecreasing band centres and T >= the number of strips that can be live on one step
 // (planned on the host, Job::plan_event) a thread never has two live strips; events whose centres
-// go backwards are filled serially by thread 0.
+// go backwards are filled serially by thread 0.  The 5-mer parameters of a thread's next strip are
+// fetched into shared memory with cp.async one step after the current strip was taken up, so the
+// switch costs a shared-memory read instead of two dependent global round trips.
 struct ColMeta { int s, i0, i1; };
 
-struct Strip
+struct StripMeta
 {
     int j;                    // strip index, 1<<29 when past the end
-    int rlo, rhi;             // union of the 4 bands
+    int rlo, rhi;             // row pairs covered by the union of the 2 bands
     int pp0, pp1;             // band of the column just before the strip
     ColMeta col[CW];
-    StateParams p[CW];
 };
 
 __device__ __forceinline__ void col_band(const Batch& b, const EvDesc& ev, bool rev, int k, int& i0, int& i1)
@@ -273,27 +287,28 @@ __device__ __forceinline__ void col_band(const Batch& b, const EvDesc& ev, bool 
     band_of(rev ? ev.n0 - cen + 1 : cen, ev.n0, b.realign_width, i0, i1);
 }
 
-__device__ __forceinline__ void strip_setup(const Batch& b, const EvDesc& ev, bool rev, int j, Strip& st)
+__device__ __forceinline__ void strip_meta(const Batch& b, const EvDesc& ev, bool rev, int j, StripMeta& st)
 {
     const int k0 = CW * j + 1;
-    if (k0 > ev.N) { st.j = 1 << 29; st.rlo = 1; st.rhi = 0; return; }
+    st.pp0 = 0; st.pp1 = ev.n0;
+#pragma unroll
+    for (int c = 0; c < CW; c++) { st.col[c].s = -1; st.col[c].i0 = 1; st.col[c].i1 = 0; }
+    if (j < 0 || k0 > ev.N) { st.j = 1 << 29; st.rlo = 1; st.rhi = 0; return; }
     st.j = j;
-    st.rlo = 1 << 30; st.rhi = 0;
+    int lo = 1 << 30, hi = 0;
 #pragma unroll
     for (int c = 0; c < CW; c++)
     {
         const int k = k0 + c;
-        st.col[c].s = -1; st.col[c].i0 = 1; st.col[c].i1 = 0;
         if (k <= ev.N)
         {
             col_band(b, ev, rev, k, st.col[c].i0, st.col[c].i1);
             st.col[c].s = b.states[ev.state_off + (rev ? ev.N - k + 1 : k) - 1];
-            if (st.col[c].s >= 0) st.p[c] = b.models[ev.model].st[st.col[c].s];
-            st.rlo = min(st.rlo, st.col[c].i0); st.rhi = max(st.rhi, st.col[c].i1);
+            lo = min(lo, st.col[c].i0); hi = max(hi, st.col[c].i1);
         }
     }
-    if (k0 == 1) { st.pp0 = 0; st.pp1 = ev.n0; }
-    else col_band(b, ev, rev, k0 - 1, st.pp0, st.pp1);
+    st.rlo = (lo - 1) >> 1; st.rhi = (hi - 1) >> 1;
+    if (k0 > 1) col_band(b, ev, rev, k0 - 1, st.pp0, st.pp1);
 }
 
 struct FillOut               // where one direction's band columns go
@@ -301,132 +316,210 @@ struct FillOut               // where one direction's band columns go
     double* Mm; double* Ms; int* Mi0; int* Mlen; double* Mcb; int* Mcbi;
 };
 
+// everything of one cell except the horizontal (skip) move: M1 = max(0, match, insert, ignore, S)
+// with the step code the reference's compare order gives, and the stay-matrix value S
+__device__ __forceinline__ void cell_pre(bool ok, bool first, bool diag_ok, double Pd, double eM, double eU,
+                                         double upC, double upS, const Trans& t,
+                                         double& M1, int& m1, double& S, int& ss)
+{
+    const double match = (diag_ok ? Pd : 0.0) + eM;
+    const double ignore = diag_ok ? Pd + t.lins : 0.0;
+    const double stay = first ? NEG : (upC + eU) + t.lstay;
+    const double ins = first ? 0.0 : upC + t.lins;
+    const double ext = first ? NEG : (upS + eU) + t.lext;
+    double s = first ? NEG : 0.0;
+    int q = 0;
+    if (stay > s) { s = stay; q = 1; }
+    if (ext > s) { s = ext; q = 2; }
+    double c = 0.0;
+    int sc = ST_STOP;
+    if (match > c) { c = match; sc = diag_ok ? ST_MATCH : ST_IMPLICIT; }
+    if (ins > c) { c = ins; sc = ST_INSERT; }
+    if (ignore > c) { c = ignore; sc = ST_IGNORE; }
+    if (s > c) { c = s; sc = ST_STAY; }
+    M1 = ok ? c : 0.0; m1 = ok ? sc : ST_STOP; S = ok ? s : 0.0; ss = ok ? q : 0;
+}
+
+__device__ __forceinline__ void cell_fin(bool skip_pred, double Pc, double M1, int m1, const Trans& t, double& C, int& code)
+{
+    const double skip = Pc + t.lskip;
+    const bool w = skip_pred && (skip >= M1);
+    C = w ? skip : M1;
+    code = (w && skip > 0.0) ? ST_SKIP : m1;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+
 template <bool REV, int MAXT>
 __device__ __forceinline__ void fill_wave(const Batch& b, const EvDesc& ev, const FillOut& o, double* smem)
 {
     const int T = blockDim.x, tid = threadIdx.x;
     const int n0 = ev.n0, N = ev.N;
-    const long long rs = ev.rs;
     const int J = (N + CW - 1) / CW;                      // strips
-    // [4][MAXT] rings of the last four steps: last-column main values and (reverse pass) emissions
-    double* myC = smem + tid;
-    double* myE = smem + 4 * MAXT + tid;
+    // [4][MAXT] rings of the last four steps: second-column main values (and, reverse pass, emissions)
+    // of both rows of the tile; then the [8][MAXT] 16-byte chunks of the next strip's two states
+    double2* myC = reinterpret_cast<double2*>(smem) + tid;
+    double2* myE = myC + 4 * MAXT;
     const int left = tid == 0 ? T - 1 : tid - 1;
-    const double* lfC = smem + left;
-    const double* lfE = smem + 4 * MAXT + left;
+    const double2* lfC = reinterpret_cast<const double2*>(smem) + left;
+    const double2* lfE = lfC + 4 * MAXT;
+    double2* nxt = reinterpret_cast<double2*>(smem) + 8 * MAXT + tid;    // chunk q at nxt[q * MAXT]
     const LevelRec* lev = b.lev + ev.lev_off;
     const ModelDev& md = b.models[ev.model];
     const Trans tr = {md.lskip, md.lstay, md.lext, md.lins};
     const double off = b.lik_offset, l2p = b.log2pi;
 
-    Strip cur;
-    strip_setup(b, ev, REV, tid, cur);
+    StripMeta cur, nx;
+    StateParams p0, p1;
+    strip_meta(b, ev, REV, tid, cur);
+    if (cur.col[0].s >= 0) p0 = md.st[cur.col[0].s];
+    if (cur.col[1].s >= 0) p1 = md.st[cur.col[1].s];
+    strip_meta(b, ev, REV, tid + T, nx);
+    bool fetch = true;                                    // the next strip's parameters are still to be requested
     int dstart, dend;
     {
-        int a0, a1, z0 = 1 << 30, z1 = 0;
-        col_band(b, ev, REV, 1, a0, a1);
-        for (int k = CW * (J - 1) + 1; k <= N; k++) { int u0, u1; col_band(b, ev, REV, k, u0, u1); z0 = min(z0, u0); z1 = max(z1, u1); }
-        // the first strip starts at its lowest row; the last one ends at its highest
-        int f0 = a0;
-        for (int k = 2; k <= min(CW, N); k++) { int u0, u1; col_band(b, ev, REV, k, u0, u1); f0 = min(f0, u0); }
-        dstart = 0 + f0; dend = (J - 1) + z1;
+        StripMeta f, l;
+        strip_meta(b, ev, REV, 0, f);
+        strip_meta(b, ev, REV, J - 1, l);
+        dstart = f.rlo; dend = (J - 1) + l.rhi;
     }
-    double upC[CW], upS[CW], upE[CW], best[CW];
-    int besti[CW];
-#pragma unroll
-    for (int c = 0; c < CW; c++) { upC[c] = 0; upS[c] = 0; upE[c] = 0; best[c] = NEG; besti[c] = 0; }
+    double upC0 = 0, upS0 = 0, upE0 = 0, upC1 = 0, upS1 = 0, upE1 = 0;
+    double best0 = NEG, best1 = NEG;
+    int besti0 = 0, besti1 = 0;
     int ph = dstart & 3;
     for (int d = dstart; d <= dend; d++)
     {
         if (d > cur.j + cur.rhi)
         {
             // strip finished: publish the shape and best cell of its columns, take the next strip
-#pragma unroll
-            for (int c = 0; c < CW; c++)
+            if (cur.j < J)
             {
-                const int k = CW * cur.j + 1 + c;
-                if (cur.j < J && k <= N)
+                const int k = CW * cur.j + 1;
+                const long long g = ev.col_off + k;
+                o.Mi0[g] = cur.col[0].i0; o.Mlen[g] = cur.col[0].i1 - cur.col[0].i0 + 1;
+                o.Mcb[g] = best0; o.Mcbi[g] = besti0;
+                if (k + 1 <= N)
                 {
-                    const long long g = ev.col_off + k;
-                    o.Mi0[g] = cur.col[c].i0; o.Mlen[g] = cur.col[c].i1 - cur.col[c].i0 + 1;
-                    o.Mcb[g] = best[c]; o.Mcbi[g] = besti[c];
+                    o.Mi0[g + 1] = cur.col[1].i0; o.Mlen[g + 1] = cur.col[1].i1 - cur.col[1].i0 + 1;
+                    o.Mcb[g + 1] = best1; o.Mcbi[g + 1] = besti1;
                 }
-                best[c] = NEG; besti[c] = 0;
             }
-            strip_setup(b, ev, REV, cur.j + T, cur);
+            best0 = NEG; best1 = NEG; besti0 = 0; besti1 = 0;
+            cur = nx;
+            if (cur.j < J && fetch)
+            {
+                // the strip that just ended lasted a single step: its successor's parameters were never requested
+                p0 = md.st[max(cur.col[0].s, 0)]; p1 = md.st[max(cur.col[1].s, 0)];
+            }
+            else if (cur.j < J)
+            {
+                asm volatile("cp.async.wait_all;\n" ::: "memory");
+                double2 v[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) v[q] = nxt[q * MAXT];
+                p0.lev_mean = v[0].x; p0.lev_stdv = v[0].y; p0.log_lev = v[1].x; p0.sd_mean = v[1].y;
+                p0.sd_lambda = v[2].x; p0.log_lambda = v[2].y; p0.r_lev_stdv = v[3].x; p0.r_sd_mean = v[3].y;
+                p1.lev_mean = v[4].x; p1.lev_stdv = v[4].y; p1.log_lev = v[5].x; p1.sd_mean = v[5].y;
+                p1.sd_lambda = v[6].x; p1.log_lambda = v[6].y; p1.r_lev_stdv = v[7].x; p1.r_sd_mean = v[7].y;
+            }
+            strip_meta(b, ev, REV, cur.j < J ? cur.j + T : -1, nx);
+            fetch = true;
         }
-        const int i = d - cur.j;
-        const int w0 = ph, w1 = (ph + 3) & 3, w2 = (ph + 2) & 3;        // steps d, d-1, d-2
-        if (i >= cur.rlo && i <= cur.rhi)
+        else if (fetch)
         {
-            const LevelRec lr = lev[REV ? n0 - i : i - 1];
-            const double lsd3 = REV ? lr.lsd3 : lev[n0 - i].lsd3;
-            // the column left of the strip: left neighbour's last column, or the blank column 0
-            double Pc = 0, Pd = 0, PEd = 0;                              // (k-1, i), (k-1, i-1), E(k-1, i-1)
+            // one step after the switch the next strip's states have arrived: request their parameters
+            fetch = false;
+            if (nx.j < J)
+            {
+                const double2* s0 = reinterpret_cast<const double2*>(&md.st[max(nx.col[0].s, 0)]);
+                const double2* s1 = reinterpret_cast<const double2*>(&md.st[max(nx.col[1].s, 0)]);
+#pragma unroll
+                for (int q = 0; q < 4; q++) { cp_async16(&nxt[q * MAXT], s0 + q); cp_async16(&nxt[(4 + q) * MAXT], s1 + q); }
+            }
+        }
+        const int r = d - cur.j;
+        const int w0 = ph, w1 = (ph + 3) & 3, w2 = (ph + 2) & 3;        // steps d, d-1, d-2
+        if (r >= cur.rlo && r <= cur.rhi)
+        {
+            const int ia = 2 * r + 1, ib = ia + 1;
+            const int ibc = min(ib, n0);                                 // row n0+1 of an odd event is never in a band
+            const LevelRec la = lev[REV ? n0 - ia : ia - 1];
+            const LevelRec lb = lev[REV ? n0 - ibc : ibc - 1];
+            const double lsa = REV ? la.lsd3 : lev[n0 - ia].lsd3;
+            const double lsb = REV ? lb.lsd3 : lev[n0 - ibc].lsd3;
+            // the column left of the strip: left neighbour's second column, or the blank column 0
+            double Lm = 0, La = 0, Lb = 0, LEm = 0, LEa = 0;             // rows ia-1, ia, ib
             if (cur.j > 0)
             {
-                Pc = lfC[w1 * MAXT];
-                Pd = lfC[w2 * MAXT];
-                if (REV) PEd = lfE[w2 * MAXT];
+                const double2 u = lfC[w1 * MAXT];
+                La = u.x; Lb = u.y;
+                Lm = lfC[w2 * MAXT].y;
+                if (REV) { LEa = lfE[w1 * MAXT].x; LEm = lfE[w2 * MAXT].y; }
             }
-            int p0 = cur.pp0, p1 = cur.pp1;
-            double Cout[CW], Sout[CW];
-            unsigned steps = 0;
-#pragma unroll
-            for (int c = 0; c < CW; c++)
-            {
-                const ColMeta cm = cur.col[c];
-                double C = 0, S = 0, e = 0;
-                int step = ST_STOP;
-                const bool act = i >= cm.i0 && i <= cm.i1;
-                const double oldC = upC[c], oldE = upE[c];               // (k, i-1) before this row overwrites it
-                if (act)
-                {
-                    if (cm.s >= 0)
-                    {
-                        e = emission(lr.mean, lr.stdv, lr.rstdv, lsd3, cur.p[c], l2p, off);
-                        const bool skip_ok = i >= p0 && i <= p1;
-                        const bool diag_ok = i > p0 && i <= p1;
-                        const double eM = REV ? (diag_ok ? PEd : 0.0) : e;
-                        const double eU = REV ? oldE : e;
-                        dp_cell(i == cm.i0, skip_ok, diag_ok, Pc, Pd, eM, eU, oldC, upS[c], tr, C, S, step);
-                        if (C > best[c]) { best[c] = C; besti[c] = i; }
-                    }
-                    upC[c] = C; upS[c] = S; upE[c] = e;
-                }
-                Cout[c] = C; Sout[c] = S;
-                steps |= (unsigned)step << (8 * c);
-                // this column is the next one's left neighbour
-                Pc = C; Pd = oldC; PEd = oldE;
-                p0 = cm.i0; p1 = cm.i1;
-            }
-            // the last column of the strip is what the right neighbour reads
-            myC[w0 * MAXT] = Pc;
-            if (REV) myE[w0 * MAXT] = upE[CW - 1];
-            const long long a = ev.band_off + ((long long)d * ev.ts + (cur.j % ev.ts)) * CW;   // (strip, row) run
+            const ColMeta c0 = cur.col[0], c1 = cur.col[1];
+            const bool okA = ia >= c0.i0 && ia <= c0.i1 && c0.s >= 0;
+            const bool okB = ia >= c1.i0 && ia <= c1.i1 && c1.s >= 0;
+            const bool okC = ib >= c0.i0 && ib <= c0.i1 && c0.s >= 0;
+            const bool okD = ib >= c1.i0 && ib <= c1.i1 && c1.s >= 0;
+            double eA = emission(la.mean, la.stdv, la.rstdv, lsa, p0, l2p, off);
+            double eB = emission(la.mean, la.stdv, la.rstdv, lsa, p1, l2p, off);
+            double eC = emission(lb.mean, lb.stdv, lb.rstdv, lsb, p0, l2p, off);
+            double eD = emission(lb.mean, lb.stdv, lb.rstdv, lsb, p1, l2p, off);
+            eA = okA ? eA : 0.0; eB = okB ? eB : 0.0; eC = okC ? eC : 0.0; eD = okD ? eD : 0.0;
+            // band predicates of the horizontal / diagonal moves (previous column's band)
+            const bool skA = ia >= cur.pp0 && ia <= cur.pp1, dgA = ia > cur.pp0 && ia <= cur.pp1;
+            const bool skC = ib >= cur.pp0 && ib <= cur.pp1, dgC = ib > cur.pp0 && ib <= cur.pp1;
+            const bool skB = ia >= c0.i0 && ia <= c0.i1, dgB = ia > c0.i0 && ia <= c0.i1;
+            const bool skD = ib >= c0.i0 && ib <= c0.i1, dgD = ib > c0.i0 && ib <= c0.i1;
+            double CA, CB, CC, CD, SA, SB, SC, SD, M;
+            int kA, kB, kC, kD, qA, qB, qC, qD, m;
+            // row ia
+            cell_pre(okA, ia == c0.i0, dgA, Lm, REV ? (dgA ? LEm : 0.0) : eA, REV ? upE0 : eA, upC0, upS0, tr, M, m, SA, qA);
+            cell_fin(skA && okA, La, M, m, tr, CA, kA);
+            cell_pre(okB, ia == c1.i0, dgB, upC0, REV ? (dgB ? upE0 : 0.0) : eB, REV ? upE1 : eB, upC1, upS1, tr, M, m, SB, qB);
+            cell_fin(skB && okB, CA, M, m, tr, CB, kB);
+            // row ib
+            cell_pre(okC, ib == c0.i0, dgC, La, REV ? (dgC ? LEa : 0.0) : eC, REV ? eA : eC, CA, SA, tr, M, m, SC, qC);
+            cell_fin(skC && okC, Lb, M, m, tr, CC, kC);
+            cell_pre(okD, ib == c1.i0, dgD, CA, REV ? (dgD ? eA : 0.0) : eD, REV ? eB : eD, CB, SB, tr, M, m, SD, qD);
+            cell_fin(skD && okD, CC, M, m, tr, CD, kD);
+            if (okA && CA > best0) { best0 = CA; besti0 = ia; }
+            if (okC && CC > best0) { best0 = CC; besti0 = ib; }
+            if (okB && CB > best1) { best1 = CB; besti1 = ia; }
+            if (okD && CD > best1) { best1 = CD; besti1 = ib; }
+            upC0 = CC; upS0 = SC; upE0 = eC; upC1 = CD; upS1 = SD; upE1 = eD;
+            // the second column of the strip is what the right neighbour reads
+            myC[w0 * MAXT] = make_double2(CB, CD);
+            if (REV) myE[w0 * MAXT] = make_double2(eB, eD);
+            const long long a = ev.band_off + ((long long)d * ev.ts + (cur.j % ev.ts)) * 4;   // the tile's run
             double2* pm = reinterpret_cast<double2*>(o.Mm + a);
             double2* ps = reinterpret_cast<double2*>(o.Ms + a);
-            pm[0] = make_double2(Cout[0], Cout[1]); pm[1] = make_double2(Cout[2], Cout[3]);
-            ps[0] = make_double2(Sout[0], Sout[1]); ps[1] = make_double2(Sout[2], Sout[3]);
-            if (!REV) *reinterpret_cast<unsigned*>(b.Fstep + a) = steps;
+            pm[0] = make_double2(CA, CB); pm[1] = make_double2(CC, CD);
+            ps[0] = make_double2(SA, SB); ps[1] = make_double2(SC, SD);
+            if (!REV)
+                *reinterpret_cast<unsigned*>(b.Fstep + a) = (unsigned)(kA | (qA << 3)) | ((unsigned)(kB | (qB << 3)) << 8) |
+                                                           ((unsigned)(kC | (qC << 3)) << 16) | ((unsigned)(kD | (qD << 3)) << 24);
         }
         __syncthreads();
         ph = (ph + 1) & 3;
     }
     if (cur.j < J)
     {
-#pragma unroll
-        for (int c = 0; c < CW; c++)
+        const int k = CW * cur.j + 1;
+        const long long g = ev.col_off + k;
+        o.Mi0[g] = cur.col[0].i0; o.Mlen[g] = cur.col[0].i1 - cur.col[0].i0 + 1;
+        o.Mcb[g] = best0; o.Mcbi[g] = besti0;
+        if (k + 1 <= N)
         {
-            const int k = CW * cur.j + 1 + c;
-            if (k <= N)
-            {
-                const long long g = ev.col_off + k;
-                o.Mi0[g] = cur.col[c].i0; o.Mlen[g] = cur.col[c].i1 - cur.col[c].i0 + 1;
-                o.Mcb[g] = best[c]; o.Mcbi[g] = besti[c];
-            }
+            o.Mi0[g + 1] = cur.col[1].i0; o.Mlen[g + 1] = cur.col[1].i1 - cur.col[1].i0 + 1;
+            o.Mcb[g + 1] = best1; o.Mcbi[g + 1] = besti1;
         }
     }
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
 }
 
 // Serial schedule (arbitrary band layout): the same cells, column by column, by one thread; the
@@ -713,10 +806,10 @@ __global__ void __launch_bounds__(256) k_backtrace(Batch b, int smem_levels)
 // the rows present in BOTH bands plus the two running bests (and the floor 0).
 //
 // k_join: old[g] = columnMax(c) = join(F[c], B[N-c+1]) for every band column.  A block covers 32
-// consecutive columns = 8 forward strips (lane = column) with 8 warps that take the wavefront steps
-// d = strip + row round robin; in the wavefront-major layout the forward cells a warp reads in one
-// step are one contiguous 256-byte run, and the matching reverse cells (column N-c+1, row n0-jf+1)
-// form at most two runs.
+// consecutive columns = 16 forward strips (lane = column) with 8 warps that take the wavefront steps
+// d = strip + row pair round robin; in the wavefront-major layout the forward tiles a warp reads in
+// one step are one contiguous 512-byte run, and the matching reverse cells (column N-c+1, rows
+// n0-jf+1) belong to one reverse step as well.
 __global__ void __launch_bounds__(256) k_join(Batch b)
 {
     const EvDesc ev = b.ev[blockIdx.y];
@@ -726,7 +819,7 @@ __global__ void __launch_bounds__(256) k_join(Batch b)
     const int c = blockIdx.x * 32 + lane + 1;
     const bool have = c <= N;
     const int cb = N - c + 1;                           // reverse column joined with forward column c
-    const int j = (c - 1) >> 2;                         // forward strip of this lane
+    const int j = (c - 1) >> 1;                         // forward strip of this lane
     int lo = 1, hi = 0;
     double m = 0.0;
     long long gf = 0;
@@ -741,21 +834,27 @@ __global__ void __launch_bounds__(256) k_join(Batch b)
         m = fmax(b.Fbest[gf], b.Bbest[gb]);
     }
     // common step range of the 32 columns
-    int dlo = have && lo <= hi ? j + lo : 1 << 30, dhi = have && lo <= hi ? j + hi : -1;
+    int dlo = have && lo <= hi ? j + ((lo - 1) >> 1) : 1 << 30, dhi = have && lo <= hi ? j + ((hi - 1) >> 1) : -1;
     for (int o = 16; o; o >>= 1)
     {
         dlo = min(dlo, __shfl_xor_sync(0xffffffffu, dlo, o));
         dhi = max(dhi, __shfl_xor_sync(0xffffffffu, dhi, o));
     }
     const long long fb = have ? col_base(ev, c) : 0, bb = have ? col_base(ev, cb) : 0;
+    const long long rs = ev.rs;
     for (int d = dlo + w; d <= dhi; d += 8)
     {
-        const int jf = d - j;
-        if (have && jf >= lo && jf <= hi)
+        const int r = d - j;
+#pragma unroll
+        for (int h = 0; h < 2; h++)
         {
-            const long long af = fb + (long long)jf * ev.rs;
-            const long long ab = bb + (long long)(n0 - jf + 1) * ev.rs;
-            m = fmax(m, fmax(b.Fm[af] + b.Bm[ab], b.Fs[af] + b.Bs[ab]));
+            const int jf = 2 * r + 1 + h;
+            if (have && jf >= lo && jf <= hi)
+            {
+                const long long af = fb + (long long)r * rs + 2 * h;
+                const long long ab = bb + row_off(rs, n0 - jf + 1);
+                m = fmax(m, fmax(b.Fm[af] + b.Bm[ab], b.Fs[af] + b.Bs[ab]));
+            }
         }
     }
     __shared__ double part[8][32];
@@ -960,22 +1059,21 @@ __global__ void __launch_bounds__(128) k_mutscore(Batch b)
                         // (c-1, i0-1): still in its slot, nothing of this column overwrites it
                         double diag = 0.0;
                         if (i0 > p0 && i0 <= p1)
-                            diag = first_col ? (seed ? seed[(long long)(i0 - 1) * ts] : 0.0) : ring[(long long)((i0 - 1) % S) * rstride];
+                            diag = first_col ? (seed ? seed[row_off(ts, i0 - 1)] : 0.0) : ring[(long long)((i0 - 1) % S) * rstride];
                         // software pipeline: level record, seed value and join values of row i+1 are
                         // requested while row i is computed (the loads are the latency that matters here)
                         const LevelRec* lv = lev + (i0 - 1);                 // row i reads level i-1 ...
                         const LevelRec* lq = lev + (n0 - i0);                // ... and 3 log stdv of level n0-i
-                        const double* sd = (first_col && seed) ? seed + (long long)i0 * ts : nullptr;
+                        const double* sd = (first_col && seed) ? seed : nullptr;                // + row_off(ts, row)
                         const bool joinB = last_col && rab > 0;
-                        const double* qm = Bm + (long long)(n0 - i0 + 1) * ts;   // reverse row jb = n0-i+1
-                        const double* qs = Bs + (long long)(n0 - i0 + 1) * ts;
+                        // reverse row jb = n0-i+1 lives at + row_off(ts, jb)
                         LevelRec lr = *lv;
                         double lsd3 = lq->lsd3;
-                        double sv = (sd && i0 >= p0 && i0 <= p1) ? *sd : 0.0;
+                        double sv = (sd && i0 >= p0 && i0 <= p1) ? sd[row_off(ts, i0)] : 0.0;
                         double bmv = 0.0, bsv = 0.0;
                         {
                             const int jb = n0 - i0 + 1;
-                            if (joinB && jb >= b0 && jb < b0 + blen) { bmv = *qm; bsv = *qs; }
+                            if (joinB && jb >= b0 && jb < b0 + blen) { const long long ro = row_off(ts, jb); bmv = Bm[ro]; bsv = Bs[ro]; }
                         }
                         for (int i = i0; i <= i1; i++)
                         {
@@ -985,13 +1083,12 @@ __global__ void __launch_bounds__(128) k_mutscore(Batch b)
                             {
                                 lv++; lq--;
                                 lr = *lv; lsd3 = lq->lsd3;
-                                if (sd) { sd += ts; sv = (i + 1 >= p0 && i + 1 <= p1) ? *sd : 0.0; }
+                                if (sd) sv = (i + 1 >= p0 && i + 1 <= p1) ? sd[row_off(ts, i + 1)] : 0.0;
                                 if (joinB)
                                 {
-                                    qm -= ts; qs -= ts;
                                     const int jn = n0 - i;
                                     bmv = 0.0; bsv = 0.0;
-                                    if (jn >= b0 && jn < b0 + blen) { bmv = *qm; bsv = *qs; }
+                                    if (jn >= b0 && jn < b0 + blen) { const long long ro = row_off(ts, jn); bmv = Bm[ro]; bsv = Bs[ro]; }
                                 }
                             }
                             const double e_i = emission(lr_c.mean, lr_c.stdv, lr_c.rstdv, lsd3_c, sp, b.log2pi, b.lik_offset);
@@ -1023,7 +1120,7 @@ __global__ void __launch_bounds__(128) k_mutscore(Batch b)
                                 const int jb = n0 - i + 1;
                                 if (jb >= b0 && jb < b0 + blen)
                                 {
-                                    const double bm = rab > 0 ? Bm[jb * ts] : 0.0, bs = rab > 0 ? Bs[jb * ts] : 0.0;
+                                    const double bm = rab > 0 ? Bm[row_off(ts, jb)] : 0.0, bs = rab > 0 ? Bs[row_off(ts, jb)] : 0.0;
                                     joinmax = fmax(joinmax, fmax(bm, bs));
                                 }
                             }

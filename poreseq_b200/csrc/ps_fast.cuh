@@ -55,7 +55,7 @@ struct ColF
 {
     float* ringC;                // + (row & mask) * 128
     const LevelRecF* lev;        // event levels
-    const double* Bm; const double* Bs;   // reverse column (last narrow column only): + jb*ts
+    const double* Bm; const double* Bs;   // reverse column (last narrow column only): + row_off(ts, jb)
     long long ts;
     double dRa;
     int n0, mask;
@@ -69,8 +69,7 @@ struct ColF
 template <bool EDGE, bool LAST>
 __device__ __forceinline__ void row_f(ColF& q, const StateParamsF& sp, int i, int i0, int i1,
                                       const LevelRecF*& lv, const LevelRecF*& lq, LevelRecF& lr, float& ey,
-                                      const double*& pm, const double*& ps, float& bm, float& bs,
-                                      float& diag, float& upC, float& upS)
+                                      float& bm, float& bs, float& diag, float& upC, float& upS)
 {
     const LevelRecF lr_c = lr;
     const float ey_c = ey, bm_c = bm, bs_c = bs;
@@ -81,9 +80,12 @@ __device__ __forceinline__ void row_f(ColF& q, const StateParamsF& sp, int i, in
         lr = *lv; ey = lq->ey;
         if (LAST)
         {
-            pm -= q.ts; ps -= q.ts;
             const int jn = q.n0 - i;
-            if (!EDGE || (jn >= q.b0 && jn <= q.b1)) { bm = (float)(*pm - q.dRa); bs = (float)(*ps - q.dRa); }
+            if (!EDGE || (jn >= q.b0 && jn <= q.b1))
+            {
+                const long long ro = row_off(q.ts, jn);
+                bm = (float)(q.Bm[ro] - q.dRa); bs = (float)(q.Bs[ro] - q.dRa);
+            }
         }
     }
     const float e = emission_f(lr_c, ey_c, sp);
@@ -121,18 +123,16 @@ __device__ __forceinline__ void column_f(ColF& q, const StateParamsF& sp, int i0
     const LevelRecF* lq = q.lev + (q.n0 - i0);
     LevelRecF lr = *lv;
     float ey = lq->ey;
-    const double* pm = q.Bm + (long long)(q.n0 - i0 + 1) * q.ts;
-    const double* ps = q.Bs + (long long)(q.n0 - i0 + 1) * q.ts;
     float bm = 0.f, bs = 0.f;
     if (LAST)
     {
         const int jb = q.n0 - i0 + 1;
-        if (jb >= q.b0 && jb <= q.b1) { bm = (float)(*pm - q.dRa); bs = (float)(*ps - q.dRa); }
+        if (jb >= q.b0 && jb <= q.b1) { const long long ro = row_off(q.ts, jb); bm = (float)(q.Bm[ro] - q.dRa); bs = (float)(q.Bs[ro] - q.dRa); }
     }
     int i = i0;
-    for (; i < lo; i++) row_f<true, LAST>(q, sp, i, i0, i1, lv, lq, lr, ey, pm, ps, bm, bs, diag, upC, upS);
-    for (; i <= hi; i++) row_f<false, LAST>(q, sp, i, i0, i1, lv, lq, lr, ey, pm, ps, bm, bs, diag, upC, upS);
-    for (; i <= i1; i++) row_f<true, LAST>(q, sp, i, i0, i1, lv, lq, lr, ey, pm, ps, bm, bs, diag, upC, upS);
+    for (; i < lo; i++) row_f<true, LAST>(q, sp, i, i0, i1, lv, lq, lr, ey, bm, bs, diag, upC, upS);
+    for (; i <= hi; i++) row_f<false, LAST>(q, sp, i, i0, i1, lv, lq, lr, ey, bm, bs, diag, upC, upS);
+    for (; i <= i1; i++) row_f<true, LAST>(q, sp, i, i0, i1, lv, lq, lr, ey, bm, bs, diag, upC, upS);
 }
 
 __global__ void __launch_bounds__(128) k_mutscore_f32(Batch b, int mask)
@@ -188,11 +188,10 @@ __global__ void __launch_bounds__(128) k_mutscore_f32(Batch b, int mask)
                     best_d = b.Fbest[gs];
                     // rebase to the seed value on the band centre of the first narrow column
                     const int mid = min(max((f0 + f1) >> 1, q.p0), q.p1);
-                    a = seed[(long long)mid * ts];
+                    a = seed[row_off(ts, mid)];
                     // stage the seed rows the first column reads, rebased, into the ring
                     const int s0 = max(f0 - 1, q.p0), s1 = min(f1, q.p1);
-                    const double* sp = seed + (long long)s0 * ts;
-                    for (int i = s0; i <= s1; i++, sp += ts) q.ringC[(i & mask) * 128] = (float)(*sp - a);
+                    for (int i = s0; i <= s1; i++) q.ringC[(i & mask) * 128] = (float)(seed[row_off(ts, i)] - a);
                 }
                 q.fl = (float)(-a);
                 q.best = (float)(best_d - a);
@@ -235,7 +234,7 @@ __global__ void __launch_bounds__(128) k_mutscore_f32(Batch b, int mask)
                             for (int i = max(i0, n0 + 1 - q.b1); i <= min(i1, n0 + 1 - q.b0); i++)
                             {
                                 const long long jb = n0 - i + 1;
-                                q.joinmax = fmaxf(q.joinmax, q.fl + fmaxf((float)(q.Bm[jb * ts] - dRa), (float)(q.Bs[jb * ts] - dRa)));
+                                q.joinmax = fmaxf(q.joinmax, q.fl + fmaxf((float)(q.Bm[row_off(ts, (int)jb)] - dRa), (float)(q.Bs[row_off(ts, (int)jb)] - dRa)));
                             }
                     }
                     q.p0 = i0; q.p1 = i1;

@@ -6,8 +6,13 @@
 // There is deliberately no CPU implementation of the DP here: if CUDA is unavailable every compute
 // entry point fails with PS_E_CUDA.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <pthread.h>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -51,6 +56,87 @@ void ps_set_error(ps_ctx* ctx, const char* fmt, ...)
     } while (0)
 
 // ------------------------------------------------------------------------------------------
+// host worker threads: the per-event staging of a batch (log(stdv), band planning, copies into the
+// pinned buffers, result scatter) is independent per event
+namespace {
+struct Pool
+{
+    std::vector<std::thread> workers;
+    std::mutex m;
+    std::condition_variable wake, done;
+    const std::function<void(int)>* fn = nullptr;
+    std::atomic<int> next{0};
+    int n = 0, busy = 0;
+    unsigned long long generation = 0;
+    bool stop = false;
+
+    explicit Pool(int threads)
+    {
+        for (int t = 0; t < threads; t++) workers.emplace_back([this] { loop(); });
+    }
+    void drain()
+    {
+        for (;;)
+        {
+            const int i = next.fetch_add(1);
+            if (i >= n) break;
+            (*fn)(i);
+        }
+    }
+    void loop()
+    {
+        unsigned long long seen = 0;
+        std::unique_lock<std::mutex> lk(m);
+        for (;;)
+        {
+            wake.wait(lk, [&] { return stop || generation != seen; });
+            if (stop) return;
+            seen = generation;
+            lk.unlock();
+            drain();
+            lk.lock();
+            if (--busy == 0) done.notify_all();
+        }
+    }
+    void run(int count, const std::function<void(int)>& f)
+    {
+        std::unique_lock<std::mutex> lk(m);
+        fn = &f; n = count; next.store(0);
+        busy = (int)workers.size();
+        generation++;
+        wake.notify_all();
+        lk.unlock();
+        drain();
+        lk.lock();
+        done.wait(lk, [&] { return busy == 0; });
+        fn = nullptr;
+    }
+};
+Pool* g_pool = nullptr;
+std::once_flag g_pool_fork;
+std::mutex g_pool_make;
+void pool_forget() { g_pool = nullptr; }          // worker threads do not survive fork(): start over in the child
+}
+
+void ps_parallel_for(int n, const std::function<void(int)>& fn)
+{
+    if (n <= 0) return;
+    if (n < 4) { for (int i = 0; i < n; i++) fn(i); return; }
+    {
+        std::lock_guard<std::mutex> g(g_pool_make);
+        if (!g_pool)
+        {
+            std::call_once(g_pool_fork, [] { pthread_atfork(nullptr, nullptr, pool_forget); });
+            int threads = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+            if (const char* e = getenv("PORESEQ_B200_THREADS")) threads = std::max(1, atoi(e));
+            g_pool = new Pool(threads - 1);
+        }
+    }
+    if (g_pool->workers.empty()) { for (int i = 0; i < n; i++) fn(i); return; }
+    g_pool->run(n, fn);
+}
+
+// ------------------------------------------------------------------------------------------
 // context
 int ps_ctx::init()
 {
@@ -78,10 +164,9 @@ int ps_ctx::init()
     CU(cudaStreamCreate(&stream));
     for (int i = 0; i <= PS_T_COUNT; i++) CU(cudaEventCreate(&tev[i]));
     CU(cudaFuncSetAttribute(k_backtrace, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
-    CU(cudaFuncSetAttribute(k_fill<160, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CU(cudaFuncSetAttribute(k_fill<160, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CU(cudaFuncSetAttribute(k_fill<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    CU(cudaFuncSetAttribute(k_fill<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    CU(cudaFuncSetAttribute(k_fill<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CU(cudaFuncSetAttribute(k_fill<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CU(cudaFuncSetAttribute(k_mutscore<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU(cudaFuncSetAttribute(k_mutscore<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU(cudaFuncSetAttribute(k_mutscore_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -206,6 +291,23 @@ void HostEvent::update_refs()                                // cpp/EventData.h:
     }
 }
 
+void HostEvent::ensure_levrec()
+{
+    if (levrec.size() == (size_t)n0 * 4) return;
+    levrec.resize((size_t)n0 * 4);
+    levrecf.resize((size_t)n0 * 4);
+    for (int i = 0; i < n0; i++)
+    {
+        const double lsd = std::log(stdv[i]);                                // cpp/EventData.h:218-220
+        const double r = 1.0 / stdv[i];
+        // device level record: mean, stdv, RN(1/stdv), 3*log(stdv)  (psdev::LevelRec)
+        levrec[4 * i] = mean[i]; levrec[4 * i + 1] = stdv[i]; levrec[4 * i + 2] = r; levrec[4 * i + 3] = 3 * lsd;
+        // FP32 twin (psdev::LevelRecF): mean, stdv, 1/stdv, -1.5 log(stdv)
+        levrecf[4 * i] = (float)mean[i]; levrecf[4 * i + 1] = (float)stdv[i];
+        levrecf[4 * i + 2] = (float)r; levrecf[4 * i + 3] = (float)(-1.5 * lsd);
+    }
+}
+
 void ps_build_model(const HostModel& hm, ModelDev& md)     // cpp/EventData.h:48-73
 {
     for (int s = 0; s < N_STATES; s++)
@@ -257,8 +359,7 @@ struct Job
     PinVec<char> mut_str;
     PinVec<RegTab> regtab;
     std::vector<const HostModel*> model_src;
-    std::vector<int> wave_need, plan_lo, plan_hi;
-    std::vector<double> narrow_cols;             // per region: sum over its mutations of (|mut|+5)
+    std::vector<int> wave_need;
     int wave_threads = 32;
     double bias = -1e-6;                         // start value of every mutation's sum over events
     double wide_cells_fwd = 0, narrow_cells = 0;
@@ -277,7 +378,7 @@ struct Job
         mdev = c->pinned<MutDev>("mdev"); mut_str = c->pinned<char>("mut_str"); regtab = c->pinned<RegTab>("regtab");
     }
 
-    void plan_event(const HostEvent& he, const EvDesc& d);
+    void plan_event(const HostEvent& he, const EvDesc& d, int rw, int* cen, int* ok_out, int* need_out, double* cells_out);
     int build();
     int upload();
     int run(bool backward_and_muts);
@@ -289,15 +390,15 @@ struct Job
 };
 
 // Band centres of the wide fill (cpp/EventData.h:172-183: lower_bound over ref_index; 1 when the
-// event has no alignment, cpp/Alignment.cpp:129-132), whether they are nondecreasing, and the
-// number of threads the wavefront needs so that a thread's next column starts at least 5 steps
-// after its current one ends (fill_wave switches columns only every 4 steps).
-void Job::plan_event(const HostEvent& he, const EvDesc& d)
+// event has no alignment, cpp/Alignment.cpp:129-132), whether they are nondecreasing, the forward
+// band cell count, and the number of threads the wavefront needs so that a thread's next strip
+// starts after its current one has ended.  Writes cen_old[d.cen_off ..]; one call per event, any thread.
+void Job::plan_event(const HostEvent& he, const EvDesc& d, int rw, int* cen, int* ok_out, int* need_out, double* cells_out)
 {
-    const int N = d.N, n0 = he.n0, rw = regs[0]->params.realign_width;
-    const size_t base = cen_old.size();
-    cen_old.fill((size_t)N + cen_pad + 1, 1);
+    const int N = d.N, n0 = he.n0;
+    for (int c = 0; c <= N + cen_pad; c++) cen[c] = 1;
     int ok = 1, need = 32;
+    double cells = 0;
     if (!he.ri_empty)
     {
         const std::vector<double>& ri = he.ref_index;
@@ -310,35 +411,34 @@ void Job::plan_event(const HostEvent& he, const EvDesc& d)
             for (int c = 0; c <= N + cen_pad; c++)
             {
                 while (idx < n0 && ri[idx] < (double)c) idx++;
-                cen_old[base + c] = idx;
+                cen[c] = idx;
             }
         }
         else
             for (int c = 0; c <= N + cen_pad; c++)
             {
                 const int v = (int)(std::lower_bound(ri.begin(), ri.end(), (double)c) - ri.begin());
-                cen_old[base + c] = v;
-                if (c > 0 && v < cen_old[base + c - 1]) ok = 0;
+                cen[c] = v;
+                if (c > 0 && v < cen[c - 1]) ok = 0;
             }
     }
     if (d.usable && ok)
     {
-        // strips of CW columns in processing order: strip j runs rows [lo_j, hi_j] at steps j + row
+        // strips of CW columns in processing order: strip j runs row pairs [lo_j, hi_j] at steps j + pair
         const int J = (N + CW - 1) / CW;
-        plan_lo.resize(J + 1); plan_hi.resize(J + 1);
-        std::vector<int>& lo = plan_lo; std::vector<int>& hi = plan_hi;
+        std::vector<int> lo(J + 1), hi(J + 1);
         for (int dir = 0; dir < 2; dir++)
         {
             for (int j = 0; j < J; j++) { lo[j] = 1 << 30; hi[j] = 0; }
             for (int k = 1; k <= N; k++)
             {
                 const int c = dir ? N - k + 1 : k;
-                int mid = dir ? n0 - cen_old[base + c] + 1 : cen_old[base + c];
+                int mid = dir ? n0 - cen[c] + 1 : cen[c];
                 mid = std::min(std::max(mid, 1), n0);
                 const int i0 = std::max(1, mid - rw), i1 = std::min(n0, mid + rw);
                 const int j = (k - 1) / CW;
-                lo[j] = std::min(lo[j], j + i0); hi[j] = std::max(hi[j], j + i1);
-                if (!dir) wide_cells_fwd += i1 - i0 + 1;
+                lo[j] = std::min(lo[j], j + ((i0 - 1) >> 1)); hi[j] = std::max(hi[j], j + ((i1 - 1) >> 1));
+                if (!dir) cells += i1 - i0 + 1;
             }
             // a thread's next strip (j+T) must start after its current one (j) has ended
             int jj = 1;
@@ -349,10 +449,8 @@ void Job::plan_event(const HostEvent& he, const EvDesc& d)
                 need = std::max(need, jj - j);
             }
         }
-        if (need <= 1024) wave_threads = std::max(wave_threads, need);
     }
-    mono.push_back(ok);
-    wave_need.push_back(need);
+    *ok_out = ok; *need_out = need; *cells_out = cells;
 }
 
 int Job::build()
@@ -374,26 +472,32 @@ int Job::build()
     }
     // longest net insertion decides how far past N the post-backtrace centre table must reach
     cen_pad = 8;
-    size_t tot_levels = 0, tot_states = 0, tot_bases = 0, tot_events = 0, tot_muts = 0;
+    size_t tot_levels = 0, tot_states = 0, tot_bases = 0, tot_events = 0, tot_muts = 0, tot_cen = 0;
     for (size_t r = 0; r < regs.size(); r++)
-    {
         if (want_muts && muts[r].list)
             for (const HostMut& m : *muts[r].list)
                 cen_pad = std::max(cen_pad, (int)m.mut.size() - (int)m.orig.size() + 8);
+    for (size_t r = 0; r < regs.size(); r++)
+    {
         for (const HostEvent& he : regs[r]->events) tot_levels += he.n0;
         tot_states += regs[r]->states.size(); tot_bases += regs[r]->bases.size(); tot_events += regs[r]->events.size();
-        if (want_muts) tot_muts += muts[r].points ? regs[r]->states.size() * 8 : muts[r].list->size();
+        tot_cen += regs[r]->events.size() * (regs[r]->states.size() + cen_pad + 1);
+        if (want_muts) tot_muts += muts[r].points ? regs[r]->states.size() * 9 : muts[r].list->size();
     }
-    if (!lev.reserve(tot_levels) || !ref_align.reserve(tot_levels) || !ref_like.reserve(tot_levels) ||
-        !ref_index.reserve(tot_levels) || !states.reserve(tot_states) || !bases.reserve(tot_bases) ||
-        !ev.reserve(tot_events) || !mdev.reserve(tot_muts) || !ri_empty.reserve(tot_events) ||
-        !mono.reserve(tot_events) || !cen_old.reserve(tot_events * 64 + tot_states * 2) || !regtab.reserve(regs.size()))
+    if (!lev.resize(tot_levels) || !(fast ? levf.resize(tot_levels) : true) || !ref_align.resize(tot_levels) ||
+        !ref_like.resize(tot_levels) || !ref_index.resize(tot_levels) || !states.reserve(tot_states) ||
+        !bases.reserve(tot_bases) || !ev.reserve(tot_events) || !mdev.reserve(tot_muts) || !ri_empty.resize(tot_events) ||
+        !mono.resize(tot_events) || !cen_old.resize(tot_cen) || !regtab.reserve(regs.size()))
     {
         ps_set_error(ctx, "out of host memory staging the batch");
         return PS_E_INTERNAL;
     }
     mut_str.append("ACGT", 4);                  // single-base replacement strings live at offsets 0..3
 
+    // pass 1 (serial, cheap): region tables, mutation tables, event descriptors and offsets
+    std::vector<const HostEvent*> hev;
+    std::vector<double> ev_cols;                  // per event: narrow columns of its region's mutations
+    hev.reserve(tot_events); ev_cols.reserve(tot_events);
     for (size_t r = 0; r < regs.size(); r++)
     {
         ps_region* R = regs[r];
@@ -435,7 +539,6 @@ int Job::build()
             }
         }
         const int nm = (int)(mdev.size() - mut_off);
-        narrow_cols.push_back(cols);
         RegTab rt; rt.mut_off = mut_off; rt.ev0 = ev0; rt.nev = (int)R->events.size();
         max_ev = std::max(max_ev, rt.nev);
         regtab.push_back(rt);
@@ -469,33 +572,59 @@ int Job::build()
             n_cen += d.N + cen_pad + 1;
             n_tasks += nm;
             ev.push_back(d);
-            lev.append((const LevelRec*)he.levrec.data(), (size_t)he.n0);
-            if (fast) levf.append((const LevelRecF*)he.levrecf.data(), (size_t)he.n0);
-            ref_align.append(he.ref_align.data(), he.ref_align.size());
-            ref_like.append(he.ref_like.data(), he.ref_like.size());
-            if (he.ri_empty) ref_index.fill(he.n0, 0.0);
-            else ref_index.append(he.ref_index.data(), he.ref_index.size());
-            ri_empty.push_back(he.ri_empty ? 1 : 0);
-            plan_event(he, d);
-            if (d.usable && want_muts) narrow_cells += cols * std::min(he.n0, 2 * R->params.scoring_width + 1);
+            hev.push_back(&he);
+            ev_cols.push_back(cols);
         }
     }
     n_cols += 1;                                  // index 0 of the first event is never used
     n_muts = (long long)mdev.size();
+
+    // pass 2 (parallel over events): level records, alignment arrays, band centres, wavefront plan
+    const int ne = (int)ev.size();
+    wave_need.assign(ne, 32);
+    std::vector<double> ev_cells(ne, 0.0);
+    const int rw = P.realign_width;
+    ps_parallel_for(ne, [&](int e) {
+        HostEvent& he = *const_cast<HostEvent*>(hev[e]);
+        const EvDesc& d = ev[e];
+        he.ensure_levrec();
+        const size_t at = (size_t)d.lev_off, n = (size_t)he.n0;
+        memcpy(lev.data() + at, he.levrec.data(), n * sizeof(LevelRec));
+        if (fast) memcpy(levf.data() + at, he.levrecf.data(), n * sizeof(LevelRecF));
+        memcpy(ref_align.data() + at, he.ref_align.data(), n * sizeof(double));
+        memcpy(ref_like.data() + at, he.ref_like.data(), n * sizeof(double));
+        if (he.ri_empty) std::fill(ref_index.data() + at, ref_index.data() + at + n, 0.0);
+        else memcpy(ref_index.data() + at, he.ref_index.data(), n * sizeof(double));
+        ri_empty[e] = he.ri_empty ? 1 : 0;
+        int ok = 1;
+        plan_event(he, d, rw, cen_old.data() + d.cen_off, &ok, &wave_need[e], &ev_cells[e]);
+        // the wavefront fill assumes log(prob_skip) <= 0 (see fill_wave)
+        if (!(model_src[d.model]->trans[0] <= 1.0)) ok = 0;
+        mono[e] = ok;
+    });
+    for (int e = 0; e < ne; e++)
+    {
+        const EvDesc& d = ev[e];
+        if (d.usable && mono[e])
+        {
+            wide_cells_fwd += ev_cells[e];
+            if (wave_need[e] <= 512) wave_threads = std::max(wave_threads, wave_need[e]);
+        }
+        if (d.usable && want_muts) narrow_cells += ev_cols[e] * std::min(d.n0, 2 * P.scoring_width + 1);
+    }
     // wavefront-major band storage: stride = wavefront width for monotone events (at most that many
-    // columns are live on one anti-diagonal), N+1 for the serially filled ones
-    wave_threads = std::min(std::max(((wave_threads + 31) / 32) * 32, 32), 1024);
+    // strips are live on one step), one slot per strip for the serially filled ones
+    wave_threads = std::min(std::max(((wave_threads + 31) / 32) * 32, 32), 512);
     for (size_t e = 0; e < ev.size(); e++)
     {
         EvDesc& d = ev[e];
-        if (!d.usable) { d.ts = 1; d.rs = CW; d.band_off = n_band; continue; }
+        if (!d.usable) { d.ts = 1; d.rs = 4; d.band_off = n_band; continue; }
         if (mono[e] && wave_need[e] > wave_threads) mono[e] = 0;
-        // slots per wavefront step: the wavefront width for monotone events, one per strip for the serial ones
         const int J = (d.N + CW - 1) / CW;
         d.ts = mono[e] ? wave_threads : J + 1;
-        d.rs = d.ts * CW;
-        d.band_off = n_band;                      // multiple of CW: keeps the 32-byte row runs aligned
-        n_band += (long long)(J + d.n0 + 3) * d.rs;
+        d.rs = d.ts * 4;                          // one 2x2 tile per slot
+        d.band_off = n_band;                      // multiple of 4: keeps the 32-byte tiles aligned
+        n_band += (long long)(J + (d.n0 + 1) / 2 + 2) * d.rs;
     }
     return PS_OK;
 }
@@ -536,8 +665,9 @@ int Job::upload()
     b.RS = ((2 * P.realign_width + 1) + 3) & ~3;
     b.n_tasks = n_tasks;
 
-    std::vector<ModelDev> models(model_src.size());
-    for (size_t q = 0; q < model_src.size(); q++) ps_build_model(*model_src[q], models[q]);
+    PinVec<ModelDev> models = ctx->pinned<ModelDev>("models");
+    if (!models.resize(model_src.size())) { ps_set_error(ctx, "out of host memory staging the models"); return PS_E_INTERNAL; }
+    ps_parallel_for((int)model_src.size(), [&](int q) { ps_build_model(*model_src[q], models[q]); });
 
     EvDesc* d_ev; ModelDev* d_models; int* d_states; char* d_bases;
     LevelRec* d_lev;
@@ -594,8 +724,13 @@ int Job::upload()
         if (fast)
         {
             // FP32 twins: fused emission coefficients per state, log transition costs per model
-            std::vector<StateParamsF> stf(model_src.size() * N_STATES);
-            std::vector<float4> trf(model_src.size());
+            PinVec<StateParamsF> stf = ctx->pinned<StateParamsF>("stf");
+            PinVec<float4> trf = ctx->pinned<float4>("trf");
+            if (!stf.resize(model_src.size() * N_STATES) || !trf.resize(model_src.size()))
+            {
+                ps_set_error(ctx, "out of host memory staging the models");
+                return PS_E_INTERNAL;
+            }
             const double l2p = std::log(2 * M_PI);
             for (size_t q = 0; q < model_src.size(); q++)
             {
@@ -617,7 +752,6 @@ int Job::upload()
             TRY(up(ctx, "stf", stf.data(), stf.size(), &d_stf));
             TRY(up(ctx, "trf", trf.data(), trf.size(), &d_trf));
             TRY(up(ctx, "levf", levf.data(), levf.size(), &d_levf));
-            CU(cudaStreamSynchronize(ctx->stream));          // stf/trf are stack vectors
             b.stf = d_stf; b.trf = d_trf; b.levf = d_levf;
             b.tau = 0.02 + 5e-4 * max_ev;
         }
@@ -639,13 +773,13 @@ int Job::run(bool full)
     // wavefront fill: one CTA per (event, direction), forward and reverse in one launch (grid.y = 2)
     {
         const int T = wave_threads;
-        const int maxt = T <= 160 ? 160 : T <= 256 ? 256 : T <= 512 ? 512 : 1024;
-        const size_t smem = std::max<size_t>(8 * maxt, 2 * b.RS) * sizeof(double);
+        if (getenv("PORESEQ_B200_TRACE")) fprintf(stderr, "[ps] fill: %d events, wavefront threads %d, band cells %lld\n", nev, T, n_band);
+        const int maxt = T <= 160 ? 160 : T <= 256 ? 256 : 512;
+        const size_t smem = std::max<size_t>(32 * maxt, 2 * b.RS) * sizeof(double);   // rings + next-strip parameters
         dim3 grid(nev, full ? 2 : 1);
         if (T <= 160) k_fill<160, 3><<<grid, T, smem, ctx->stream>>>(b, 0);
         else if (T <= 256) k_fill<256, 1><<<grid, T, smem, ctx->stream>>>(b, 0);
-        else if (T <= 512) k_fill<512, 1><<<grid, T, smem, ctx->stream>>>(b, 0);
-        else k_fill<1024, 1><<<grid, T, smem, ctx->stream>>>(b, 0);
+        else k_fill<512, 1><<<grid, T, smem, ctx->stream>>>(b, 0);
         LAUNCHED();
     }
     MARK(PS_T_BACKWARD);   // (reverse fill shares the launch above; kept as a phase marker)
@@ -755,22 +889,21 @@ int Job::finish(std::vector<double>* align_scores, std::vector<double>* mut_scor
     const size_t ne = ev.size();
     CU(cudaStreamSynchronize(ctx->stream));
     // scatter the realigned events back into their regions
-    size_t e = 0;
+    std::vector<HostEvent*> hev;
+    hev.reserve(ne);
     for (ps_region* R : regs)
-        for (HostEvent& he : R->events)
-        {
-            const EvDesc& d = ev[e];
-            if (d.usable)
-            {
-                std::copy(ref_align.data() + d.lev_off, ref_align.data() + d.lev_off + d.n0, he.ref_align.begin());
-                std::copy(ref_like.data() + d.lev_off, ref_like.data() + d.lev_off + d.n0, he.ref_like.begin());
-                he.ri_empty = ri_empty[e] != 0;
-                he.refstart = rs[e]; he.refend = re[e];
-                if (he.ri_empty) he.ref_index.clear();
-                else he.ref_index.assign(ref_index.data() + d.lev_off, ref_index.data() + d.lev_off + d.n0);
-            }
-            e++;
-        }
+        for (HostEvent& he : R->events) hev.push_back(&he);
+    ps_parallel_for((int)ne, [&](int e) {
+        const EvDesc& d = ev[e];
+        if (!d.usable) return;
+        HostEvent& he = *hev[e];
+        std::copy(ref_align.data() + d.lev_off, ref_align.data() + d.lev_off + d.n0, he.ref_align.begin());
+        std::copy(ref_like.data() + d.lev_off, ref_like.data() + d.lev_off + d.n0, he.ref_like.begin());
+        he.ri_empty = ri_empty[e] != 0;
+        he.refstart = rs[e]; he.refend = re[e];
+        if (he.ri_empty) he.ref_index.clear();
+        else he.ref_index.assign(ref_index.data() + d.lev_off, ref_index.data() + d.lev_off + d.n0);
+    });
     if (align_scores)
     {
         align_scores->resize(ne);
@@ -815,11 +948,18 @@ static int job_begin(ps_ctx* ctx, const std::vector<ps_region*>& regs, const std
     if (muts) job->muts = *muts;
     job->bias = bias;
     job->fast = ctx->precision == PS_PRECISION_FAST && muts != nullptr;
+    const bool trace = getenv("PORESEQ_B200_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     int rc = job->build();
+    const double t1 = now();
     if (!rc) rc = (cudaEventRecord(ctx->tev[PS_T_H2D], ctx->stream) == cudaSuccess) ? PS_OK : PS_E_CUDA;
     if (!rc) rc = job->upload();
+    const double t2 = now();
     if (!rc) rc = job->run(muts != nullptr);
     if (!rc) rc = job->download_enqueue();
+    const double t3 = now();
+    if (trace) fprintf(stderr, "[ps] host: build %.2f ms, upload(enqueue) %.2f, kernels+d2h(enqueue) %.2f\n", t1 - t0, t2 - t1, t3 - t2);
     if (rc) { delete job; return rc; }
     ctx->pending = job;
     return PS_OK;
@@ -831,7 +971,10 @@ static int job_end(ps_ctx* ctx, std::vector<double>* align_scores, std::vector<d
     if (!job) { ps_set_error(ctx, "no batch in flight on this context"); return PS_E_ARG; }
     CU(cudaSetDevice(ctx->device));
     ctx->pending = nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     int rc = job->finish(align_scores, mut_scores);
+    if (getenv("PORESEQ_B200_TRACE")) fprintf(stderr, "[ps] host: wait+scatter %.2f ms (device total %.2f)\n", now() - t0, ctx->timing[PS_T_TOTAL]);
     delete job;
     return rc;
 }
@@ -1039,22 +1182,61 @@ int ps_region_add_event(ps_region* R, int n0, const double* mean, const double* 
     he.stdv.assign(stdv, stdv + n0);
     he.ref_align.assign(ref_align, ref_align + n0);
     he.ref_like.assign(ref_like, ref_like + n0);
-    he.log_stdv.resize(n0);
-    he.levrec.resize((size_t)n0 * 4);
-    he.levrecf.resize((size_t)n0 * 4);
-    for (int i = 0; i < n0; i++)
-    {
-        he.log_stdv[i] = std::log(he.stdv[i]);                               // cpp/EventData.h:218-220
-        // device level record: mean, stdv, RN(1/stdv), 3*log(stdv)  (psdev::LevelRec)
-        he.levrec[4 * i] = he.mean[i]; he.levrec[4 * i + 1] = he.stdv[i];
-        he.levrec[4 * i + 2] = 1.0 / he.stdv[i]; he.levrec[4 * i + 3] = 3 * he.log_stdv[i];
-        // FP32 twin (psdev::LevelRecF): mean, stdv, 1/stdv, -1.5 log(stdv)
-        he.levrecf[4 * i] = (float)he.mean[i]; he.levrecf[4 * i + 1] = (float)he.stdv[i];
-        he.levrecf[4 * i + 2] = (float)(1.0 / he.stdv[i]); he.levrecf[4 * i + 3] = (float)(-1.5 * he.log_stdv[i]);
-    }
     if (seq2d) he.seq2d = seq2d;
     he.update_refs();
     R->events.push_back(std::move(he));
+    return PS_OK;
+}
+
+int ps_region_add_events(ps_region* R, int n_events, const int* n0, const double* mean, const double* stdv,
+                         const double* ref_align, const double* ref_like, const int* model_index, int n_models,
+                         const double* models, const double* probs, const int* complement, const char* const* seq2d)
+{
+    if (!R) return PS_E_ARG;
+    ps_ctx* ctx = R->ctx;
+    if (n_events < 0 || n_models < 0 || (n_events > 0 && (!n0 || !model_index || !models || !probs || n_models == 0)))
+    {
+        ps_set_error(ctx, "ps_region_add_events: bad arguments");
+        return PS_E_ARG;
+    }
+    // model table -> region models (de-duplicated against the ones already there)
+    std::vector<int> map(n_models, -1);
+    for (int q = 0; q < n_models; q++)
+    {
+        HostModel hm;
+        memcpy(hm.raw, models + (size_t)q * 4 * PS_N_STATES, sizeof hm.raw);
+        memcpy(hm.trans, probs + (size_t)q * 4, sizeof hm.trans);
+        for (size_t k = 0; k < R->models.size() && map[q] < 0; k++)
+            if (memcmp(&R->models[k], &hm, sizeof hm) == 0) map[q] = (int)k;
+        if (map[q] < 0) { map[q] = (int)R->models.size(); R->models.push_back(hm); }
+    }
+    const size_t first = R->events.size();
+    std::vector<size_t> at(n_events + 1, 0);
+    for (int e = 0; e < n_events; e++)
+    {
+        if (n0[e] < 0 || model_index[e] < 0 || model_index[e] >= n_models || (n0[e] > 0 && (!mean || !stdv || !ref_align || !ref_like)))
+        {
+            ps_set_error(ctx, "ps_region_add_events: bad event %d", e);
+            return PS_E_ARG;
+        }
+        at[e + 1] = at[e] + (size_t)n0[e];
+    }
+    R->events.resize(first + n_events);
+    for (int e = 0; e < n_events; e++)                   // (too little work per event to farm out)
+    {
+        const int n = n0[e];
+        const size_t a = at[e];
+        HostEvent& he = R->events[first + e];
+        he.n0 = n;
+        he.model = map[model_index[e]];
+        he.complement = complement ? complement[e] != 0 : false;
+        he.mean.assign(mean + a, mean + a + n);
+        he.stdv.assign(stdv + a, stdv + a + n);
+        he.ref_align.assign(ref_align + a, ref_align + a + n);
+        he.ref_like.assign(ref_like + a, ref_like + a + n);
+        if (seq2d && seq2d[e]) he.seq2d = seq2d[e];
+        he.update_refs();
+    }
     return PS_OK;
 }
 

@@ -1,6 +1,7 @@
 // ps_internal.h -- host-side objects behind the opaque handles of include/poreseq_b200.h.
 #pragma once
 #include <cstring>
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -69,11 +70,12 @@ struct HostEvent                              // cpp/EventData.h:78-229
     bool complement = false;
     bool ri_empty = true;
     int refstart = -1, refend = -1;
-    std::vector<double> mean, stdv, log_stdv, ref_align, ref_like, ref_index;
-    std::vector<double> levrec;               // 4 doubles per level, the device LevelRec layout
+    std::vector<double> mean, stdv, ref_align, ref_like, ref_index;
+    std::vector<double> levrec;               // 4 doubles per level, the device LevelRec layout (built on first use)
     std::vector<float> levrecf;               // 4 floats per level, the device LevelRecF layout
     std::string seq2d;
     void update_refs();
+    void ensure_levrec();                     // log(stdv) etc. (cpp/EventData.h:218-220), cached
 };
 
 struct HostMut                                // cpp/AlignUtil.h:69-92 MutInfo / MutScore
@@ -98,6 +100,9 @@ struct ps_region                              // cpp/AlignData.h:24-34
 };
 
 void ps_set_error(ps_ctx* ctx, const char* fmt, ...);
+// fn(i) for i in [0, n) on the library's host worker threads (PORESEQ_B200_THREADS, default
+// min(cores, 8)); the caller takes part.  Used for the per-event staging work of a batch.
+void ps_parallel_for(int n, const std::function<void(int)>& fn);
 std::vector<int> ps_states_of(const std::string& bases);
 std::string ps_apply_mutation(const std::string& bases, int start, const std::string& orig, const std::string& mut);
 std::vector<HostMut> ps_point_mutations(const ps_region* R);

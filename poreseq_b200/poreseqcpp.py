@@ -56,6 +56,8 @@ def lib():
     L.ps_region_create.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(PSParams)]
     L.ps_region_destroy.argtypes = [C.c_void_p]
     L.ps_region_add_event.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 8 + [C.c_int] + [C.c_double] * 4 + [C.c_char_p]
+    L.ps_region_add_events.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                                                                   C.c_void_p, C.c_void_p]
     L.ps_region_set_params.argtypes = [C.c_void_p, C.POINTER(PSParams)]
     L.ps_region_num_events.argtypes = [C.c_void_p]
     L.ps_region_sequence_length.argtypes = [C.c_void_p]
@@ -165,8 +167,72 @@ def _cstrs(items):
     return arr
 
 
+class PackedRegion(object):
+    """Host buffers of one region laid out for ps_region_add_events: the level arrays of all events
+    concatenated, one table of distinct pore models.  Built once from a PSAlign-like object; the
+    marshalling of a call is then one C-ABI call per region instead of one per event."""
+
+    def __init__(self, sequence, events, params):
+        self.sequence = sequence.encode("ascii") if isinstance(sequence, str) else bytes(sequence)
+        self.params = dict(params)
+        self.n0 = np.array([len(ev.mean) for ev in events], dtype=np.int32)
+        cat = lambda name: np.ascontiguousarray(np.concatenate([_f8(getattr(ev, name)) for ev in events]) if len(events) else np.zeros(0))
+        self.mean, self.stdv, self.ref_align, self.ref_like = cat("mean"), cat("stdv"), cat("ref_align"), cat("ref_like")
+        seen, tables, probs, index = {}, [], [], []
+        for ev in events:
+            m = ev.model
+            if id(m) not in seen:
+                seen[id(m)] = len(tables)
+                tables.append(np.stack([_f8(m.level_mean)[:1024], _f8(m.level_stdv)[:1024], _f8(m.sd_mean)[:1024], _f8(m.sd_stdv)[:1024]]))
+                probs.append([float(m.prob_skip), float(m.prob_stay), float(m.prob_extend), float(m.prob_insert)])
+            index.append(seen[id(m)])
+        self.model_index = np.array(index, dtype=np.int32)
+        self.models = np.ascontiguousarray(np.stack(tables)) if tables else np.zeros((0, 4, 1024))
+        self.probs = np.ascontiguousarray(np.array(probs, dtype="f8").reshape(-1, 4))
+        self.complement = np.array([int(bool(ev.model.complement)) for ev in events], dtype=np.int32)
+        self.seq2d = [(getattr(ev, "sequence", "") or "") for ev in events]
+        self._seq2d_c = _cstrs(self.seq2d)
+
+    def nbytes(self):
+        return (self.mean.nbytes + self.stdv.nbytes + self.ref_align.nbytes + self.ref_like.nbytes + self.models.nbytes +
+                self.probs.nbytes + self.n0.nbytes + self.model_index.nbytes + self.complement.nbytes + len(self.sequence))
+
+
+def _ps_params(params, width_key):
+    p = PSParams(4.5, 150, 300, 0)          # cpp/AlignUtil.h:64 defaults
+    if "verbose" in params:
+        p.verbose = int(params["verbose"])
+    if "lik_offset" in params:
+        p.lik_offset = float(params["lik_offset"])
+    if "realign_width" in params:
+        p.realign_width = int(params["realign_width"])
+    if "scoring_width" in params:
+        p.scoring_width = int(params["scoring_width"])
+    if width_key is not None and width_key in params:   # point_width override, pyx:293,361,465
+        p.scoring_width = int(params[width_key])
+    return p
+
+
 class NativeRegion(object):
     """ps_region built from a PSAlign-like object (sequence, events, params)."""
+
+    @classmethod
+    def from_packed(cls, ctx, pack, width_key=None):
+        """One ps_region_create + one ps_region_add_events from the host buffers of a PackedRegion."""
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        L = ctx.lib
+        p = _ps_params(pack.params, width_key)
+        self.handle = L.ps_region_create(ctx.handle, pack.sequence, len(pack.sequence), C.byref(p))
+        if not self.handle:
+            raise RuntimeError("ps_region_create failed: %s" % L.ps_last_error(ctx.handle).decode())
+        self.n_levels = pack.n0.tolist()
+        ctx.check(L.ps_region_add_events(self.handle, len(pack.n0), pack.n0.ctypes.data, pack.mean.ctypes.data,
+                                         pack.stdv.ctypes.data, pack.ref_align.ctypes.data, pack.ref_like.ctypes.data,
+                                         pack.model_index.ctypes.data, len(pack.models), pack.models.ctypes.data,
+                                         pack.probs.ctypes.data, pack.complement.ctypes.data,
+                                         C.cast(pack._seq2d_c, C.c_void_p)))
+        return self
 
     def __init__(self, ctx, sequence, events, params, width_key=None):
         self.ctx = ctx

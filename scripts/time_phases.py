@@ -1,4 +1,5 @@
-"""Quick phase timing of ScorePoints on synthetic regions (run under gpurun)."""
+"""Quick phase timing of ScorePoints on synthetic regions (run under gpurun).
+usage: time_phases.py L coverage regions [fast|exact] [packed]"""
 import sys, time
 import numpy as np
 sys.path.insert(0, ".")
@@ -10,10 +11,15 @@ nreg = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 ctx = poreseqcpp.Context(0)
 if len(sys.argv) > 4:
     ctx.set_precision(sys.argv[4])
+packed = len(sys.argv) > 5 and sys.argv[5] == "packed"
 regs = [synth.make_region(L, cov, seed=s + 1) for s in range(nreg)]
+packs = [poreseqcpp.PackedRegion(r.sequence, r.events, r.params) for r in regs]
 for it in range(4):
     t0 = time.time()
-    nrs = [poreseqcpp.NativeRegion(ctx, r.sequence, r.events, r.params, "point_width") for r in regs]
+    if packed:
+        nrs = [poreseqcpp.NativeRegion.from_packed(ctx, p, "point_width") for p in packs]
+    else:
+        nrs = [poreseqcpp.NativeRegion(ctx, r.sequence, r.events, r.params, "point_width") for r in regs]
     t1 = time.time()
     out = poreseqcpp.score_points_batch(ctx, nrs)
     t2 = time.time()
