@@ -30,7 +30,7 @@ struct EvDesc                 // one event of one region in the batch
     int       usable;         // cpp/Alignment.cpp:51-59 (ref_index non-empty at call start)
     int       model;          // index into the model table
     int       n_muts;         // mutations of this event's region
-    int       pad;
+    int       inv;            // the region sequence has a non-ACGT base (some state is -1)
     long long lev_off;        // into the per-level arrays
     long long col_off;        // band column g = col_off + c,  c = 1..N
     long long state_off;      // into states[]
@@ -39,6 +39,7 @@ struct EvDesc                 // one event of one region in the batch
     long long mut_off;        // first mutation of the region in the mutation arrays
     long long task_off;       // first (event, mutation) task of this event; delta[task_off + m]
     long long band_off;       // first element of this event's band storage (same for F and B arrays)
+    long long strip_off;      // first StripRec of this event: forward strips 0..J (J = sentinel), then reverse
     int       ts;             // strips that can be live on one wavefront step (band storage slot count)
     int       rs;             // row stride of the band storage = ts * CW
 };
@@ -66,6 +67,10 @@ struct Batch                  // everything the kernels need, passed by value
     int*              refstart;
     int*              refend;
     int*              mono;          // band centres nondecreasing (wavefront schedule is valid)
+    const int*        fill_list;     // event indices grouped by wavefront width class (k_fill grid.x indexes it)
+    struct StripRec*  strips;        // per (event, direction, strip): everything the fill needs to take the strip up
+    LevelRec*         rowF;          // per level: forward row record (row i = level i-1, with 3 log stdv of level n0-i)
+    LevelRec*         rowB;          // per level: reverse row record (row i = level n0-i)
     // centre tables (forward lower_bound index, 0..n0), old = before backtrace, new = after
     int*              cen_old;
     int*              cen_new;
@@ -270,15 +275,16 @@ __global__ void k_centres(Batch b, int* cen, int check_mono)
 // go backwards are filled serially by thread 0.  The 5-mer parameters of a thread's next strip are
 // fetched into shared memory with cp.async one step after the current strip was taken up, so the
 // switch costs a shared-memory read instead of two dependent global round trips.
-struct ColMeta { int s, i0, i1; };
-
-struct StripMeta
+struct StripRec               // 192 bytes: the two columns of a strip, ready to be copied into registers
 {
-    int j;                    // strip index, 1<<29 when past the end
-    int rlo, rhi;             // row pairs covered by the union of the 2 bands
+    StateParams p[2];
+    int i0[2], i1[2], s[2];   // band and state of each column (empty band, s = -1 past the last column)
     int pp0, pp1;             // band of the column just before the strip
-    ColMeta col[CW];
+    int rlo, rhi;             // row pairs covered by the union of the two bands (1, 0 for the sentinel strip J)
+    int slot4;                // (j % ts) * 4: offset of the strip's tile inside a step's run
+    int pad[5];
 };
+static_assert(sizeof(StripRec) == 192, "StripRec is copied as 16-byte chunks (the first eleven carry data)");
 
 __device__ __forceinline__ void col_band(const Batch& b, const EvDesc& ev, bool rev, int k, int& i0, int& i1)
 {
@@ -287,28 +293,59 @@ __device__ __forceinline__ void col_band(const Batch& b, const EvDesc& ev, bool 
     band_of(rev ? ev.n0 - cen + 1 : cen, ev.n0, b.realign_width, i0, i1);
 }
 
-__device__ __forceinline__ void strip_meta(const Batch& b, const EvDesc& ev, bool rev, int j, StripMeta& st)
+// k_strips: one thread per (event, direction, strip) builds the strip's record and publishes the band
+// shape of its columns (Fi0/Flen, Bi0/Blen); grid (ceil((Jmax+1)/128), events, directions)
+__global__ void k_strips(Batch b)
 {
-    const int k0 = CW * j + 1;
-    st.pp0 = 0; st.pp1 = ev.n0;
-#pragma unroll
-    for (int c = 0; c < CW; c++) { st.col[c].s = -1; st.col[c].i0 = 1; st.col[c].i1 = 0; }
-    if (j < 0 || k0 > ev.N) { st.j = 1 << 29; st.rlo = 1; st.rhi = 0; return; }
-    st.j = j;
+    const EvDesc ev = b.ev[blockIdx.y];
+    if (!ev.usable || ev.N <= 0) return;
+    const bool rev = blockIdx.z != 0;
+    const int J = (ev.N + CW - 1) / CW;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > J) return;
+    StripRec r;
+    memset(&r, 0, sizeof r);
+    r.pp0 = 0; r.pp1 = ev.n0;
+    r.rlo = 1; r.rhi = 0;
+    r.slot4 = (j % ev.ts) * 4;
+    const ModelDev& md = b.models[ev.model];
     int lo = 1 << 30, hi = 0;
-#pragma unroll
     for (int c = 0; c < CW; c++)
     {
-        const int k = k0 + c;
-        if (k <= ev.N)
+        r.s[c] = -1; r.i0[c] = 1; r.i1[c] = 0;
+        const int k = CW * j + 1 + c;
+        if (j < J && k <= ev.N)
         {
-            col_band(b, ev, rev, k, st.col[c].i0, st.col[c].i1);
-            st.col[c].s = b.states[ev.state_off + (rev ? ev.N - k + 1 : k) - 1];
-            lo = min(lo, st.col[c].i0); hi = max(hi, st.col[c].i1);
+            col_band(b, ev, rev, k, r.i0[c], r.i1[c]);
+            r.s[c] = b.states[ev.state_off + (rev ? ev.N - k + 1 : k) - 1];
+            lo = min(lo, r.i0[c]); hi = max(hi, r.i1[c]);
+            const long long g = ev.col_off + k;
+            (rev ? b.Bi0 : b.Fi0)[g] = r.i0[c];
+            (rev ? b.Blen : b.Flen)[g] = r.i1[c] - r.i0[c] + 1;
         }
+        r.p[c] = md.st[max(r.s[c], 0)];
     }
-    st.rlo = (lo - 1) >> 1; st.rhi = (hi - 1) >> 1;
-    if (k0 > 1) col_band(b, ev, rev, k0 - 1, st.pp0, st.pp1);
+    if (j < J)
+    {
+        r.rlo = (lo - 1) >> 1; r.rhi = (hi - 1) >> 1;
+        if (j > 0) col_band(b, ev, rev, CW * j, r.pp0, r.pp1);
+    }
+    b.strips[ev.strip_off + (rev ? J + 1 : 0) + j] = r;
+}
+
+// k_rows: the level record each fill row reads, per direction (quirk A.3-1: the forward pass pairs
+// stdv[i-1] with log_stdv[n0-i], cpp/Alignment.cpp:171-172)
+__global__ void k_rows(Batch b)
+{
+    const EvDesc ev = b.ev[blockIdx.y];
+    if (!ev.usable) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;       // row 1..n0
+    if (i > ev.n0) return;
+    const LevelRec* lev = b.lev + ev.lev_off;
+    LevelRec f = lev[i - 1];
+    f.lsd3 = lev[ev.n0 - i].lsd3;
+    b.rowF[ev.lev_off + i - 1] = f;
+    b.rowB[ev.lev_off + i - 1] = lev[ev.n0 - i];
 }
 
 struct FillOut               // where one direction's band columns go
@@ -316,17 +353,23 @@ struct FillOut               // where one direction's band columns go
     double* Mm; double* Ms; int* Mi0; int* Mlen; double* Mcb; int* Mcbi;
 };
 
-// everything of one cell except the horizontal (skip) move: M1 = max(0, match, insert, ignore, S)
-// with the step code the reference's compare order gives, and the stay-matrix value S
-__device__ __forceinline__ void cell_pre(bool ok, bool first, bool diag_ok, double Pd, double eM, double eU,
+// Everything of one cell except the horizontal (skip) move: M1 = max(0, match, insert, ignore, S) with
+// the step code the reference's compare order gives, and the stay-matrix value S.
+// Rows outside a column's band are computed too (the body is branch-free) and deliver NEG in both
+// matrices; nobody reads them except the column's own first row, for which NEG is exactly what makes
+// stay / extend / insert lose (cpp/Alignment.cpp:229-237: a first row has no cell above).  INV: the
+// column's state may be invalid (non-ACGT base), its in-band cells are all zero (cpp/Alignment.cpp:162).
+template <bool INV>
+__device__ __forceinline__ void cell_pre(bool inb, bool valid, bool first, bool diag_ok, double Pd, double eM, double eU,
                                          double upC, double upS, const Trans& t,
                                          double& M1, int& m1, double& S, int& ss)
 {
-    const double match = (diag_ok ? Pd : 0.0) + eM;
-    const double ignore = diag_ok ? Pd + t.lins : 0.0;
-    const double stay = first ? NEG : (upC + eU) + t.lstay;
-    const double ins = first ? 0.0 : upC + t.lins;
-    const double ext = first ? NEG : (upS + eU) + t.lext;
+    const double Pe = diag_ok ? Pd : 0.0;
+    const double match = Pe + eM;
+    const double ignore = Pe + t.lins;                    // lins <= 0: an implicit diagonal never yields a positive ignore
+    const double stay = (upC + eU) + t.lstay;             // upC = upS = NEG on a first row
+    const double ins = upC + t.lins;
+    const double ext = (upS + eU) + t.lext;
     double s = first ? NEG : 0.0;
     int q = 0;
     if (stay > s) { s = stay; q = 1; }
@@ -337,7 +380,8 @@ __device__ __forceinline__ void cell_pre(bool ok, bool first, bool diag_ok, doub
     if (ins > c) { c = ins; sc = ST_INSERT; }
     if (ignore > c) { c = ignore; sc = ST_IGNORE; }
     if (s > c) { c = s; sc = ST_STAY; }
-    M1 = ok ? c : 0.0; m1 = ok ? sc : ST_STOP; S = ok ? s : 0.0; ss = ok ? q : 0;
+    if (INV && !valid) { c = 0.0; s = 0.0; sc = ST_STOP; q = 0; }
+    M1 = inb ? c : NEG; m1 = inb ? sc : ST_STOP; S = inb ? s : NEG; ss = inb ? q : 0;
 }
 
 __device__ __forceinline__ void cell_fin(bool skip_pred, double Pc, double M1, int m1, const Trans& t, double& C, int& code)
@@ -354,103 +398,132 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
 
-template <bool REV, int MAXT>
+// The strip a thread works on, in registers
+struct StripRegs
+{
+    int j;                    // strip index, 1<<29 when past the end
+    int rlo, rhi, pp0, pp1;
+    int i0a, i1a, sa, i0b, i1b, sb;
+    int slot4;
+};
+
+template <int MAXT>
+__device__ __forceinline__ void strip_from_smem(const double2* nxt, StripRegs& c, StateParams& p0, StateParams& p1)
+{
+    double2 v[11];
+#pragma unroll
+    for (int q = 0; q < 11; q++) v[q] = nxt[q * MAXT];
+    p0.lev_mean = v[0].x; p0.lev_stdv = v[0].y; p0.log_lev = v[1].x; p0.sd_mean = v[1].y;
+    p0.sd_lambda = v[2].x; p0.log_lambda = v[2].y; p0.r_lev_stdv = v[3].x; p0.r_sd_mean = v[3].y;
+    p1.lev_mean = v[4].x; p1.lev_stdv = v[4].y; p1.log_lev = v[5].x; p1.sd_mean = v[5].y;
+    p1.sd_lambda = v[6].x; p1.log_lambda = v[6].y; p1.r_lev_stdv = v[7].x; p1.r_sd_mean = v[7].y;
+    c.i0a = __double2loint(v[8].x); c.i0b = __double2hiint(v[8].x);
+    c.i1a = __double2loint(v[8].y); c.i1b = __double2hiint(v[8].y);
+    c.sa = __double2loint(v[9].x); c.sb = __double2hiint(v[9].x);
+    c.pp0 = __double2loint(v[9].y); c.pp1 = __double2hiint(v[9].y);
+    c.rlo = __double2loint(v[10].x); c.rhi = __double2hiint(v[10].x);
+    c.slot4 = __double2loint(v[10].y);
+}
+
+template <int MAXT>
+__device__ __forceinline__ void strip_request(double2* nxt, const StripRec* rec)
+{
+    const double2* src = reinterpret_cast<const double2*>(rec);
+#pragma unroll
+    for (int q = 0; q < 11; q++) cp_async16(&nxt[q * MAXT], src + q);
+}
+
+struct RowRecs { LevelRec a, b; };                        // row records of the two rows of a tile
+
+__device__ __forceinline__ void load_rows(const LevelRec* rows, int n0, int r, RowRecs& o)
+{
+    // rows ia = 2r+1, ib = 2r+2 clamped into the event (a clamped row is outside every band)
+    const int ia = min(max(2 * r + 1, 1), n0), ib = min(max(2 * r + 2, 1), n0);
+    o.a = rows[ia - 1];
+    o.b = rows[ib - 1];
+}
+
+// split-phase CTA barrier on an mbarrier object: a warp signals that its step is written, prepares its
+// next step (strip switch, emissions) and only then waits for the others
+__device__ __forceinline__ void mbar_init(unsigned bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
+template <bool REV, int MAXT, bool INV>
 __device__ __forceinline__ void fill_wave(const Batch& b, const EvDesc& ev, const FillOut& o, double* smem)
 {
     const int T = blockDim.x, tid = threadIdx.x;
     const int n0 = ev.n0, N = ev.N;
     const int J = (N + CW - 1) / CW;                      // strips
     // [4][MAXT] rings of the last four steps: second-column main values (and, reverse pass, emissions)
-    // of both rows of the tile; then the [8][MAXT] 16-byte chunks of the next strip's two states
+    // of both rows of the tile; then the [11][MAXT] 16-byte chunks of the thread's next strip record
     double2* myC = reinterpret_cast<double2*>(smem) + tid;
     double2* myE = myC + 4 * MAXT;
     const int left = tid == 0 ? T - 1 : tid - 1;
     const double2* lfC = reinterpret_cast<const double2*>(smem) + left;
     const double2* lfE = lfC + 4 * MAXT;
     double2* nxt = reinterpret_cast<double2*>(smem) + 8 * MAXT + tid;    // chunk q at nxt[q * MAXT]
-    const LevelRec* lev = b.lev + ev.lev_off;
+    __shared__ unsigned long long step_bar;
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&step_bar);
+    if (tid == 0) mbar_init(bar, T >> 5);                 // one arrival per warp and step
+    const LevelRec* rows = (REV ? b.rowB : b.rowF) + ev.lev_off;
+    const StripRec* srec = b.strips + ev.strip_off + (REV ? J + 1 : 0);  // strips 0..J-1, sentinel J
     const ModelDev& md = b.models[ev.model];
     const Trans tr = {md.lskip, md.lstay, md.lext, md.lins};
     const double off = b.lik_offset, l2p = b.log2pi;
 
-    StripMeta cur, nx;
+    StripRegs cur;
     StateParams p0, p1;
-    strip_meta(b, ev, REV, tid, cur);
-    if (cur.col[0].s >= 0) p0 = md.st[cur.col[0].s];
-    if (cur.col[1].s >= 0) p1 = md.st[cur.col[1].s];
-    strip_meta(b, ev, REV, tid + T, nx);
-    bool fetch = true;                                    // the next strip's parameters are still to be requested
-    int dstart, dend;
-    {
-        StripMeta f, l;
-        strip_meta(b, ev, REV, 0, f);
-        strip_meta(b, ev, REV, J - 1, l);
-        dstart = f.rlo; dend = (J - 1) + l.rhi;
-    }
-    double upC0 = 0, upS0 = 0, upE0 = 0, upC1 = 0, upS1 = 0, upE1 = 0;
+    strip_request<MAXT>(nxt, srec + min(tid, J));
+    const int dstart = srec[0].rlo, dend = (J - 1) + srec[J - 1].rhi;
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    strip_from_smem<MAXT>(nxt, cur, p0, p1);
+    cur.j = tid < J ? tid : 1 << 29;
+    strip_request<MAXT>(nxt, srec + min(tid + T, J));
+    double upC0 = NEG, upS0 = NEG, upE0 = 0, upC1 = NEG, upS1 = NEG, upE1 = 0;
     double best0 = NEG, best1 = NEG;
     int besti0 = 0, besti1 = 0;
     int ph = dstart & 3;
+    unsigned parity = 0;
+    RowRecs rr;
+    double eA = 0, eB = 0, eC = 0, eD = 0;                // emissions of the tile of the coming step
+    load_rows(rows, n0, dstart - cur.j, rr);
+    if (dstart - cur.j >= cur.rlo && dstart - cur.j <= cur.rhi)
+    {
+        eA = emission(rr.a.mean, rr.a.stdv, rr.a.rstdv, rr.a.lsd3, p0, l2p, off);
+        eB = emission(rr.a.mean, rr.a.stdv, rr.a.rstdv, rr.a.lsd3, p1, l2p, off);
+        eC = emission(rr.b.mean, rr.b.stdv, rr.b.rstdv, rr.b.lsd3, p0, l2p, off);
+        eD = emission(rr.b.mean, rr.b.stdv, rr.b.rstdv, rr.b.lsd3, p1, l2p, off);
+    }
+    load_rows(rows, n0, dstart + 1 - ((dstart + 1 > cur.j + cur.rhi) ? (cur.j + T < J ? cur.j + T : 1 << 29) : cur.j), rr);
+    __syncthreads();                                      // the barrier object is initialised
     for (int d = dstart; d <= dend; d++)
     {
-        if (d > cur.j + cur.rhi)
-        {
-            // strip finished: publish the shape and best cell of its columns, take the next strip
-            if (cur.j < J)
-            {
-                const int k = CW * cur.j + 1;
-                const long long g = ev.col_off + k;
-                o.Mi0[g] = cur.col[0].i0; o.Mlen[g] = cur.col[0].i1 - cur.col[0].i0 + 1;
-                o.Mcb[g] = best0; o.Mcbi[g] = besti0;
-                if (k + 1 <= N)
-                {
-                    o.Mi0[g + 1] = cur.col[1].i0; o.Mlen[g + 1] = cur.col[1].i1 - cur.col[1].i0 + 1;
-                    o.Mcb[g + 1] = best1; o.Mcbi[g + 1] = besti1;
-                }
-            }
-            best0 = NEG; best1 = NEG; besti0 = 0; besti1 = 0;
-            cur = nx;
-            if (cur.j < J && fetch)
-            {
-                // the strip that just ended lasted a single step: its successor's parameters were never requested
-                p0 = md.st[max(cur.col[0].s, 0)]; p1 = md.st[max(cur.col[1].s, 0)];
-            }
-            else if (cur.j < J)
-            {
-                asm volatile("cp.async.wait_all;\n" ::: "memory");
-                double2 v[8];
-#pragma unroll
-                for (int q = 0; q < 8; q++) v[q] = nxt[q * MAXT];
-                p0.lev_mean = v[0].x; p0.lev_stdv = v[0].y; p0.log_lev = v[1].x; p0.sd_mean = v[1].y;
-                p0.sd_lambda = v[2].x; p0.log_lambda = v[2].y; p0.r_lev_stdv = v[3].x; p0.r_sd_mean = v[3].y;
-                p1.lev_mean = v[4].x; p1.lev_stdv = v[4].y; p1.log_lev = v[5].x; p1.sd_mean = v[5].y;
-                p1.sd_lambda = v[6].x; p1.log_lambda = v[6].y; p1.r_lev_stdv = v[7].x; p1.r_sd_mean = v[7].y;
-            }
-            strip_meta(b, ev, REV, cur.j < J ? cur.j + T : -1, nx);
-            fetch = true;
-        }
-        else if (fetch)
-        {
-            // one step after the switch the next strip's states have arrived: request their parameters
-            fetch = false;
-            if (nx.j < J)
-            {
-                const double2* s0 = reinterpret_cast<const double2*>(&md.st[max(nx.col[0].s, 0)]);
-                const double2* s1 = reinterpret_cast<const double2*>(&md.st[max(nx.col[1].s, 0)]);
-#pragma unroll
-                for (int q = 0; q < 4; q++) { cp_async16(&nxt[q * MAXT], s0 + q); cp_async16(&nxt[(4 + q) * MAXT], s1 + q); }
-            }
-        }
+        if (d > dstart) { mbar_wait(bar, parity); parity ^= 1u; }        // every warp has written step d-1
         const int r = d - cur.j;
         const int w0 = ph, w1 = (ph + 3) & 3, w2 = (ph + 2) & 3;        // steps d, d-1, d-2
         if (r >= cur.rlo && r <= cur.rhi)
         {
             const int ia = 2 * r + 1, ib = ia + 1;
-            const int ibc = min(ib, n0);                                 // row n0+1 of an odd event is never in a band
-            const LevelRec la = lev[REV ? n0 - ia : ia - 1];
-            const LevelRec lb = lev[REV ? n0 - ibc : ibc - 1];
-            const double lsa = REV ? la.lsd3 : lev[n0 - ia].lsd3;
-            const double lsb = REV ? lb.lsd3 : lev[n0 - ibc].lsd3;
+            const bool v0 = !INV || cur.sa >= 0, v1 = !INV || cur.sb >= 0;
+            if (INV) { if (!v0) { eA = 0.0; eC = 0.0; } if (!v1) { eB = 0.0; eD = 0.0; } }
             // the column left of the strip: left neighbour's second column, or the blank column 0
             double Lm = 0, La = 0, Lb = 0, LEm = 0, LEa = 0;             // rows ia-1, ia, ib
             if (cur.j > 0)
@@ -460,42 +533,34 @@ __device__ __forceinline__ void fill_wave(const Batch& b, const EvDesc& ev, cons
                 Lm = lfC[w2 * MAXT].y;
                 if (REV) { LEa = lfE[w1 * MAXT].x; LEm = lfE[w2 * MAXT].y; }
             }
-            const ColMeta c0 = cur.col[0], c1 = cur.col[1];
-            const bool okA = ia >= c0.i0 && ia <= c0.i1 && c0.s >= 0;
-            const bool okB = ia >= c1.i0 && ia <= c1.i1 && c1.s >= 0;
-            const bool okC = ib >= c0.i0 && ib <= c0.i1 && c0.s >= 0;
-            const bool okD = ib >= c1.i0 && ib <= c1.i1 && c1.s >= 0;
-            double eA = emission(la.mean, la.stdv, la.rstdv, lsa, p0, l2p, off);
-            double eB = emission(la.mean, la.stdv, la.rstdv, lsa, p1, l2p, off);
-            double eC = emission(lb.mean, lb.stdv, lb.rstdv, lsb, p0, l2p, off);
-            double eD = emission(lb.mean, lb.stdv, lb.rstdv, lsb, p1, l2p, off);
-            eA = okA ? eA : 0.0; eB = okB ? eB : 0.0; eC = okC ? eC : 0.0; eD = okD ? eD : 0.0;
+            const bool inA = ia >= cur.i0a && ia <= cur.i1a, inB = ia >= cur.i0b && ia <= cur.i1b;
+            const bool inC = ib >= cur.i0a && ib <= cur.i1a, inD = ib >= cur.i0b && ib <= cur.i1b;
             // band predicates of the horizontal / diagonal moves (previous column's band)
             const bool skA = ia >= cur.pp0 && ia <= cur.pp1, dgA = ia > cur.pp0 && ia <= cur.pp1;
             const bool skC = ib >= cur.pp0 && ib <= cur.pp1, dgC = ib > cur.pp0 && ib <= cur.pp1;
-            const bool skB = ia >= c0.i0 && ia <= c0.i1, dgB = ia > c0.i0 && ia <= c0.i1;
-            const bool skD = ib >= c0.i0 && ib <= c0.i1, dgD = ib > c0.i0 && ib <= c0.i1;
+            const bool skB = inA, dgB = ia > cur.i0a && ia <= cur.i1a;
+            const bool skD = inC, dgD = ib > cur.i0a && ib <= cur.i1a;
             double CA, CB, CC, CD, SA, SB, SC, SD, M;
             int kA, kB, kC, kD, qA, qB, qC, qD, m;
             // row ia
-            cell_pre(okA, ia == c0.i0, dgA, Lm, REV ? (dgA ? LEm : 0.0) : eA, REV ? upE0 : eA, upC0, upS0, tr, M, m, SA, qA);
-            cell_fin(skA && okA, La, M, m, tr, CA, kA);
-            cell_pre(okB, ia == c1.i0, dgB, upC0, REV ? (dgB ? upE0 : 0.0) : eB, REV ? upE1 : eB, upC1, upS1, tr, M, m, SB, qB);
-            cell_fin(skB && okB, CA, M, m, tr, CB, kB);
+            cell_pre<INV>(inA, v0, ia == cur.i0a, dgA, Lm, REV ? (dgA ? LEm : 0.0) : eA, REV ? upE0 : eA, upC0, upS0, tr, M, m, SA, qA);
+            cell_fin(skA && inA && v0, La, M, m, tr, CA, kA);
+            cell_pre<INV>(inB, v1, ia == cur.i0b, dgB, upC0, REV ? (dgB ? upE0 : 0.0) : eB, REV ? upE1 : eB, upC1, upS1, tr, M, m, SB, qB);
+            cell_fin(skB && inB && v1, CA, M, m, tr, CB, kB);
             // row ib
-            cell_pre(okC, ib == c0.i0, dgC, La, REV ? (dgC ? LEa : 0.0) : eC, REV ? eA : eC, CA, SA, tr, M, m, SC, qC);
-            cell_fin(skC && okC, Lb, M, m, tr, CC, kC);
-            cell_pre(okD, ib == c1.i0, dgD, CA, REV ? (dgD ? eA : 0.0) : eD, REV ? eB : eD, CB, SB, tr, M, m, SD, qD);
-            cell_fin(skD && okD, CC, M, m, tr, CD, kD);
-            if (okA && CA > best0) { best0 = CA; besti0 = ia; }
-            if (okC && CC > best0) { best0 = CC; besti0 = ib; }
-            if (okB && CB > best1) { best1 = CB; besti1 = ia; }
-            if (okD && CD > best1) { best1 = CD; besti1 = ib; }
-            upC0 = CC; upS0 = SC; upE0 = eC; upC1 = CD; upS1 = SD; upE1 = eD;
+            cell_pre<INV>(inC, v0, ib == cur.i0a, dgC, La, REV ? (dgC ? LEa : 0.0) : eC, REV ? eA : eC, CA, SA, tr, M, m, SC, qC);
+            cell_fin(skC && inC && v0, Lb, M, m, tr, CC, kC);
+            cell_pre<INV>(inD, v1, ib == cur.i0b, dgD, CA, REV ? (dgD ? eA : 0.0) : eD, REV ? eB : eD, CB, SB, tr, M, m, SD, qD);
+            cell_fin(skD && inD && v1, CC, M, m, tr, CD, kD);
             // the second column of the strip is what the right neighbour reads
             myC[w0 * MAXT] = make_double2(CB, CD);
             if (REV) myE[w0 * MAXT] = make_double2(eB, eD);
-            const long long a = ev.band_off + ((long long)d * ev.ts + (cur.j % ev.ts)) * 4;   // the tile's run
+            if (v0 && CA > best0) { best0 = CA; besti0 = ia; }
+            if (v0 && CC > best0) { best0 = CC; besti0 = ib; }
+            if (v1 && CB > best1) { best1 = CB; besti1 = ia; }
+            if (v1 && CD > best1) { best1 = CD; besti1 = ib; }
+            upC0 = CC; upS0 = SC; upE0 = eC; upC1 = CD; upS1 = SD; upE1 = eD;
+            const long long a = ev.band_off + (long long)d * ev.rs + cur.slot4;                 // the tile's run
             double2* pm = reinterpret_cast<double2*>(o.Mm + a);
             double2* ps = reinterpret_cast<double2*>(o.Ms + a);
             pm[0] = make_double2(CA, CB); pm[1] = make_double2(CC, CD);
@@ -504,19 +569,41 @@ __device__ __forceinline__ void fill_wave(const Batch& b, const EvDesc& ev, cons
                 *reinterpret_cast<unsigned*>(b.Fstep + a) = (unsigned)(kA | (qA << 3)) | ((unsigned)(kB | (qB << 3)) << 8) |
                                                            ((unsigned)(kC | (qC << 3)) << 16) | ((unsigned)(kD | (qD << 3)) << 24);
         }
-        __syncthreads();
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(bar);            // this warp's part of step d is in shared memory
         ph = (ph + 1) & 3;
-    }
-    if (cur.j < J)
-    {
-        const int k = CW * cur.j + 1;
-        const long long g = ev.col_off + k;
-        o.Mi0[g] = cur.col[0].i0; o.Mlen[g] = cur.col[0].i1 - cur.col[0].i0 + 1;
-        o.Mcb[g] = best0; o.Mcbi[g] = besti0;
-        if (k + 1 <= N)
+        // ---- preparation of step d+1: overlaps the other warps' step d ----
+        if (d + 1 > cur.j + cur.rhi)
         {
-            o.Mi0[g + 1] = cur.col[1].i0; o.Mlen[g + 1] = cur.col[1].i1 - cur.col[1].i0 + 1;
-            o.Mcb[g + 1] = best1; o.Mcbi[g + 1] = besti1;
+            // strip finished: publish the best cell of its columns, take the next strip from shared memory
+            // and request the one after it
+            if (cur.j < J)
+            {
+                const int k = CW * cur.j + 1;
+                const long long g = ev.col_off + k;
+                o.Mcb[g] = best0; o.Mcbi[g] = besti0;
+                if (k + 1 <= N) { o.Mcb[g + 1] = best1; o.Mcbi[g + 1] = besti1; }
+            }
+            best0 = NEG; best1 = NEG; besti0 = 0; besti1 = 0;
+            upC0 = NEG; upS0 = NEG; upC1 = NEG; upS1 = NEG;
+            const int jn = cur.j + T;
+            asm volatile("cp.async.wait_all;\n" ::: "memory");
+            strip_from_smem<MAXT>(nxt, cur, p0, p1);
+            cur.j = jn < J ? jn : 1 << 29;
+            strip_request<MAXT>(nxt, srec + min(jn + T, J));
+        }
+        {
+            const int rn = d + 1 - cur.j;
+            if (rn >= cur.rlo && rn <= cur.rhi)
+            {
+                eA = emission(rr.a.mean, rr.a.stdv, rr.a.rstdv, rr.a.lsd3, p0, l2p, off);
+                eB = emission(rr.a.mean, rr.a.stdv, rr.a.rstdv, rr.a.lsd3, p1, l2p, off);
+                eC = emission(rr.b.mean, rr.b.stdv, rr.b.rstdv, rr.b.lsd3, p0, l2p, off);
+                eD = emission(rr.b.mean, rr.b.stdv, rr.b.rstdv, rr.b.lsd3, p1, l2p, off);
+            }
+            // row records of step d+2, in flight across the wait
+            const int rnext = d + 2 - ((d + 2 > cur.j + cur.rhi) ? (cur.j + T < J ? cur.j + T : 1 << 29) : cur.j);
+            load_rows(rows, n0, rnext, rr);
         }
     }
     asm volatile("cp.async.wait_all;\n" ::: "memory");
@@ -577,12 +664,13 @@ __device__ void fill_serial(const Batch& b, const EvDesc& ev, const FillOut& o, 
 }
 
 template <int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB) k_fill(Batch b, int dir_base)
+__global__ void __launch_bounds__(MAXT, MINB) k_fill(Batch b, int list_off)
 {
     extern __shared__ double smem[];
     const int T = blockDim.x, tid = threadIdx.x;
-    const EvDesc ev = b.ev[blockIdx.x];
-    const bool rev = (dir_base + blockIdx.y) != 0;
+    const int e = b.fill_list[list_off + blockIdx.x];
+    const EvDesc ev = b.ev[e];
+    const bool rev = blockIdx.y != 0;
     if (!ev.usable || ev.N <= 0) return;
     const int N = ev.N;
     FillOut o;
@@ -590,9 +678,16 @@ __global__ void __launch_bounds__(MAXT, MINB) k_fill(Batch b, int dir_base)
     o.Mi0 = rev ? b.Bi0 : b.Fi0; o.Mlen = rev ? b.Blen : b.Flen;
     o.Mcb = rev ? b.Bcb : b.Fcb; o.Mcbi = rev ? b.Bcbi : b.Fcbi;
     double* Mcb = o.Mcb; int* Mcbi = o.Mcbi;
-    if (b.mono[blockIdx.x])
+    if (b.mono[e])
     {
-        if (rev) fill_wave<true, MAXT>(b, ev, o, smem); else fill_wave<false, MAXT>(b, ev, o, smem);
+        if (ev.inv)
+        {
+            if (rev) fill_wave<true, MAXT, true>(b, ev, o, smem); else fill_wave<false, MAXT, true>(b, ev, o, smem);
+        }
+        else
+        {
+            if (rev) fill_wave<true, MAXT, false>(b, ev, o, smem); else fill_wave<false, MAXT, false>(b, ev, o, smem);
+        }
     }
     else if (tid == 0)
     {

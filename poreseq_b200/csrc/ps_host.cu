@@ -162,11 +162,13 @@ int ps_ctx::init()
     sm_count = prop.multiProcessorCount;
     if (const char* fw = getenv("PORESEQ_B200_FILL_WARPS")) fill_warps = std::min(16, std::max(1, atoi(fw)));
     CU(cudaStreamCreate(&stream));
+    CU(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&join_ev, cudaEventDisableTiming));
     for (int i = 0; i <= PS_T_COUNT; i++) CU(cudaEventCreate(&tev[i]));
     CU(cudaFuncSetAttribute(k_backtrace, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
     CU(cudaFuncSetAttribute(k_fill<160, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CU(cudaFuncSetAttribute(k_fill<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    CU(cudaFuncSetAttribute(k_fill<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CU(cudaFuncSetAttribute(k_fill<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024));
     CU(cudaFuncSetAttribute(k_mutscore<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU(cudaFuncSetAttribute(k_mutscore<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU(cudaFuncSetAttribute(k_mutscore_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -227,6 +229,8 @@ ps_ctx::~ps_ctx()
     for (auto& kv : bufs) if (kv.second.p) cudaFree(kv.second.p);
     for (auto& kv : pins) if (kv.second.p) { if (kv.second.cap & 1) free(kv.second.p); else cudaFreeHost(kv.second.p); }
     for (int i = 0; i <= PS_T_COUNT; i++) cudaEventDestroy(tev[i]);
+    cudaEventDestroy(fork_ev); cudaEventDestroy(join_ev);
+    cudaStreamDestroy(side);
     cudaStreamDestroy(stream);
 }
 
@@ -360,10 +364,12 @@ struct Job
     PinVec<RegTab> regtab;
     std::vector<const HostModel*> model_src;
     std::vector<int> wave_need;
-    int wave_threads = 32;
+    // wide-fill launch classes: events whose wavefront fits 160 threads (3 CTAs per SM), wider ones, serial ones
+    PinVec<int> fill_list;
+    int fill_count[3] = {0, 0, 0}, fill_threads[3] = {160, 160, 32};
     double bias = -1e-6;                         // start value of every mutation's sum over events
     double wide_cells_fwd = 0, narrow_cells = 0;
-    long long n_levels, n_cols, n_cen, n_tasks, n_muts, n_band;
+    long long n_levels, n_cols, n_cen, n_tasks, n_muts, n_band, n_strips = 0;
     int cen_pad;
     Batch b;
     RegTab* d_regtab = nullptr;
@@ -376,6 +382,7 @@ struct Job
         ref_like = c->pinned<double>("ref_like"); ref_index = c->pinned<double>("ref_index");
         ri_empty = c->pinned<int>("ri_empty"); mono = c->pinned<int>("mono"); cen_old = c->pinned<int>("cen_old");
         mdev = c->pinned<MutDev>("mdev"); mut_str = c->pinned<char>("mut_str"); regtab = c->pinned<RegTab>("regtab");
+        fill_list = c->pinned<int>("fill_list");
     }
 
     void plan_event(const HostEvent& he, const EvDesc& d, int rw, int* cen, int* ok_out, int* need_out, double* cells_out);
@@ -539,6 +546,8 @@ int Job::build()
             }
         }
         const int nm = (int)(mdev.size() - mut_off);
+        int region_inv = 0;
+        for (int st : R->states) if (st < 0) { region_inv = 1; break; }
         RegTab rt; rt.mut_off = mut_off; rt.ev0 = ev0; rt.nev = (int)R->events.size();
         max_ev = std::max(max_ev, rt.nev);
         regtab.push_back(rt);
@@ -552,6 +561,7 @@ int Job::build()
             d.N = (int)R->states.size();
             d.L = (int)R->bases.size();
             d.usable = (!he.ri_empty && R->params.realign_width != 0 && he.n0 > 0) ? 1 : 0;
+            d.inv = region_inv;
             // model de-duplication across the whole batch (events usually share two models)
             const HostModel* hm = &R->models[he.model];
             int mi = -1;
@@ -598,33 +608,42 @@ int Job::build()
         ri_empty[e] = he.ri_empty ? 1 : 0;
         int ok = 1;
         plan_event(he, d, rw, cen_old.data() + d.cen_off, &ok, &wave_need[e], &ev_cells[e]);
-        // the wavefront fill assumes log(prob_skip) <= 0 (see fill_wave)
-        if (!(model_src[d.model]->trans[0] <= 1.0)) ok = 0;
+        // the wavefront fill assumes log(prob_skip) <= 0 and log(prob_insert) <= 0 (see fill_wave / cell_pre)
+        if (!(model_src[d.model]->trans[0] <= 1.0) || !(model_src[d.model]->trans[3] <= 1.0)) ok = 0;
         mono[e] = ok;
     });
+    // wavefront-major band storage: slots per step = wavefront width of the event's launch class (at
+    // most that many strips are live on one step), one slot per strip for the serially filled events
+    std::vector<int> cls(ne, -1);
+    int wide_t = 192;
     for (int e = 0; e < ne; e++)
     {
         const EvDesc& d = ev[e];
-        if (d.usable && mono[e])
-        {
-            wide_cells_fwd += ev_cells[e];
-            if (wave_need[e] <= 512) wave_threads = std::max(wave_threads, wave_need[e]);
-        }
         if (d.usable && want_muts) narrow_cells += ev_cols[e] * std::min(d.n0, 2 * P.scoring_width + 1);
+        if (!d.usable) continue;
+        if (mono[e] && wave_need[e] > 512) mono[e] = 0;
+        if (mono[e]) wide_cells_fwd += ev_cells[e];
+        cls[e] = !mono[e] ? 2 : wave_need[e] <= 160 ? 0 : 1;
+        if (cls[e] == 1) wide_t = std::max(wide_t, ((wave_need[e] + 31) / 32) * 32);
+        fill_count[cls[e]]++;
     }
-    // wavefront-major band storage: stride = wavefront width for monotone events (at most that many
-    // strips are live on one step), one slot per strip for the serially filled ones
-    wave_threads = std::min(std::max(((wave_threads + 31) / 32) * 32, 32), 512);
-    for (size_t e = 0; e < ev.size(); e++)
+    fill_threads[1] = wide_t;
+    if (!fill_list.resize((size_t)std::max(ne, 1))) { ps_set_error(ctx, "out of host memory staging the batch"); return PS_E_INTERNAL; }
+    {
+        int at[3] = {0, fill_count[0], fill_count[0] + fill_count[1]};
+        for (int e = 0; e < ne; e++) if (cls[e] >= 0) fill_list[at[cls[e]]++] = e;
+    }
+    for (int e = 0; e < ne; e++)
     {
         EvDesc& d = ev[e];
         if (!d.usable) { d.ts = 1; d.rs = 4; d.band_off = n_band; continue; }
-        if (mono[e] && wave_need[e] > wave_threads) mono[e] = 0;
         const int J = (d.N + CW - 1) / CW;
-        d.ts = mono[e] ? wave_threads : J + 1;
+        d.ts = cls[e] == 2 ? J + 1 : fill_threads[cls[e]];
         d.rs = d.ts * 4;                          // one 2x2 tile per slot
         d.band_off = n_band;                      // multiple of 4: keeps the 32-byte tiles aligned
         n_band += (long long)(J + (d.n0 + 1) / 2 + 2) * d.rs;
+        d.strip_off = n_strips;                   // forward strips 0..J, then reverse strips 0..J
+        n_strips += 2 * (J + 1);
     }
     return PS_OK;
 }
@@ -681,6 +700,7 @@ int Job::upload()
     TRY(up(ctx, "ref_index", ref_index.data(), ref_index.size(), &b.ref_index));
     TRY(up(ctx, "ri_empty", ri_empty.data(), ri_empty.size(), &b.ri_empty));
     TRY(up(ctx, "mono", mono.data(), mono.size(), &b.mono));
+    { int* fl; TRY(up(ctx, "fill_list", fill_list.data(), fill_list.size(), &fl)); b.fill_list = fl; }
     b.ev = d_ev; b.models = d_models; b.states = d_states; b.bases = d_bases;
     b.lev = d_lev;
     TRY(room(ctx, "bt_src", (size_t)n_levels, &b.bt_src));
@@ -693,6 +713,9 @@ int Job::upload()
     TRY(room(ctx, "Fm", cells, &b.Fm));
     TRY(room(ctx, "Fs", cells, &b.Fs));
     TRY(room(ctx, "Fstep", cells, &b.Fstep));
+    TRY(room(ctx, "strips", (size_t)std::max<long long>(n_strips, 1), &b.strips));
+    TRY(room(ctx, "rowF", (size_t)std::max<long long>(n_levels, 1), &b.rowF));
+    TRY(room(ctx, "rowB", (size_t)std::max<long long>(n_levels, 1), &b.rowB));
     TRY(room(ctx, "Fi0", (size_t)n_cols, &b.Fi0));
     TRY(room(ctx, "Flen", (size_t)n_cols, &b.Flen));
     TRY(room(ctx, "Fcb", (size_t)n_cols, &b.Fcb));
@@ -770,17 +793,43 @@ int Job::run(bool full)
     if (nev == 0) return PS_OK;
     MARK(PS_T_CENTRES);    // (pre-call band centres are planned on the host, see plan_event)
     MARK(PS_T_FORWARD);
-    // wavefront fill: one CTA per (event, direction), forward and reverse in one launch (grid.y = 2)
+    // wavefront fill: one CTA per (event, direction), forward and reverse in one launch (grid.y = 2),
+    // one launch per width class
     {
-        const int T = wave_threads;
-        if (getenv("PORESEQ_B200_TRACE")) fprintf(stderr, "[ps] fill: %d events, wavefront threads %d, band cells %lld\n", nev, T, n_band);
-        const int maxt = T <= 160 ? 160 : T <= 256 ? 256 : 512;
-        const size_t smem = std::max<size_t>(32 * maxt, 2 * b.RS) * sizeof(double);   // rings + next-strip parameters
-        dim3 grid(nev, full ? 2 : 1);
-        if (T <= 160) k_fill<160, 3><<<grid, T, smem, ctx->stream>>>(b, 0);
-        else if (T <= 256) k_fill<256, 1><<<grid, T, smem, ctx->stream>>>(b, 0);
-        else k_fill<512, 1><<<grid, T, smem, ctx->stream>>>(b, 0);
-        LAUNCHED();
+        if (getenv("PORESEQ_B200_TRACE"))
+            fprintf(stderr, "[ps] fill: %d events: %d at 160 threads, %d at %d, %d serial; band cells %lld\n", nev,
+                    fill_count[0], fill_count[1], fill_threads[1], fill_count[2], n_band);
+        const int dirs = full ? 2 : 1;
+        {
+            int maxn0 = 0;
+            for (const EvDesc& d : ev) maxn0 = std::max(maxn0, d.n0);
+            k_strips<<<dim3(((maxN + CW - 1) / CW + 1 + 127) / 128, nev, dirs), 128, 0, ctx->stream>>>(b);
+            LAUNCHED();
+            k_rows<<<dim3((maxn0 + 127) / 128, nev), 128, 0, ctx->stream>>>(b);
+            LAUNCHED();
+        }
+        // the majority class on the main stream, the others beside it on the side stream
+        const bool forked = fill_count[0] > 0 && fill_count[1] + fill_count[2] > 0;
+        cudaStream_t other = forked ? ctx->side : ctx->stream;
+        if (forked)
+        {
+            CU(cudaEventRecord(ctx->fork_ev, ctx->stream));
+            CU(cudaStreamWaitEvent(ctx->side, ctx->fork_ev, 0));
+        }
+        const size_t smem160 = std::max<size_t>(40 * 160, 2 * b.RS) * sizeof(double);   // rings + next strip record
+        if (fill_count[1])
+        {
+            const size_t smem = std::max<size_t>(40 * 512, 2 * b.RS) * sizeof(double);
+            k_fill<512, 1><<<dim3(fill_count[1], dirs), fill_threads[1], smem, other>>>(b, fill_count[0]);
+            LAUNCHED();
+        }
+        if (fill_count[2]) { k_fill<160, 3><<<dim3(fill_count[2], dirs), 32, smem160, other>>>(b, fill_count[0] + fill_count[1]); LAUNCHED(); }
+        if (fill_count[0]) { k_fill<160, 3><<<dim3(fill_count[0], dirs), 160, smem160, ctx->stream>>>(b, 0); LAUNCHED(); }
+        if (forked)
+        {
+            CU(cudaEventRecord(ctx->join_ev, ctx->side));
+            CU(cudaStreamWaitEvent(ctx->stream, ctx->join_ev, 0));
+        }
     }
     MARK(PS_T_BACKWARD);   // (reverse fill shares the launch above; kept as a phase marker)
     MARK(PS_T_BACKTRACE);

@@ -42,6 +42,8 @@ struct ps_ctx
     int precision = 0;                        // PS_PRECISION_EXACT / PS_PRECISION_FAST
     int fill_warps = 8;                       // warps per (event, direction) in the wide fill (PORESEQ_B200_FILL_WARPS)
     cudaStream_t stream = nullptr;
+    cudaStream_t side = nullptr;              // runs the minority launch classes of the wide fill beside the main one
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
     cudaEvent_t tev[PS_T_COUNT + 1];
     double timing[PS_T_COUNT] = {0};
     double wide_cells = 0, narrow_cells = 0;
