@@ -129,14 +129,31 @@ def cpu_checker_kind():
     return "oracle", "port"
 
 
-def run_cpu_baseline():
-    """One region on one host core, timed beside the GPU run (rank 0, N=1 only)."""
+def run_cpu_baseline(n_regions=4):
+    """A few of the step's regions on one host core, timed beside the GPU run (rank 0, N=1 only)."""
     which, kind = cpu_checker_kind()
-    reg = synth.make_region(REGION_LEN, COVERAGE, seed=1)
-    wide, narrow = algorithmic_cells(reg)
-    dt = cpu_score_points_worker((which, 1))
-    return {"value": (wide + narrow) / dt / 1e9, "unit": UNIT, "cores": 1, "kind": kind,
-            "sample": "ScorePoints on 1 of the step's 1 kb x 10x regions (%.0f M cells, %.1f s)" % ((wide + narrow) / 1e6, dt)}
+    cells, dt = 0.0, 0.0
+    for seed in range(1, n_regions + 1):
+        wide, narrow = algorithmic_cells(synth.make_region(REGION_LEN, COVERAGE, seed=seed))
+        cells += wide + narrow
+        dt += cpu_score_points_worker((which, seed))
+    return {"value": cells / dt / 1e9, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": "ScorePoints on %d of the step's 1 kb x 10x regions, one after the other on one core "
+                      "(%.0f M cells, %.1f s)" % (n_regions, cells / 1e6, dt)}
+
+
+def recorded_traffic(kernel, regions):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full
+    capture (profiles/r1_traffic.json), valid only for the batch size it was captured at."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            rec = json.load(f)
+        k = rec.get(kernel)
+        if k and int(k.get("regions", -1)) == int(regions):
+            return float(k["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
 
 
 def run_reference_arm(args, rank, world):
@@ -173,7 +190,7 @@ def run_reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--regions", type=int, default=22, help="1 kb regions per GPU per step (22 x 40 fill CTAs ~ 2 full waves of 148 SMs x 3)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -278,21 +295,29 @@ def main():
     props = torch.cuda.get_device_properties(local_rank)
     sms = props.multi_processor_count
     # dominant kernel: whichever phase took longest; its algorithmic cells / its own CUDA-event time
+    # (the phase events sit on the library's stream right around the phase's launches)
     phase_ms = {k: phase[k] / args.steps for k in kernel_keys}
     dom = max(phase_ms, key=phase_ms.get)
+    dom_kernel = {"forward": "k_fill", "mutscore": "k_mutscore_f32" if args.precision == "fast" else "k_mutscore"}.get(dom, dom)
     dom_cells = {"forward": wide_cells, "mutscore": narrow_cells}.get(dom, 0.0)
-    clock_hz = (clocks["sm_mhz"] or sm_max_mhz) * 1e6
-    peak_ops = sms * 128 * sm_max_mhz * 1e6 / 1e12                  # T lane-ops/s at max clock
-    achieved_ops = dom_cells * OPS_PER_CELL / (phase_ms[dom] * 1e-3) / 1e12 if phase_ms[dom] > 0 else 0.0
-    # algorithmic bytes of the dominant kernel: wide fill writes 2 matrices x 8 B + 1 step byte
-    # per cell (forward) / 16 B (reverse); the mutation kernel reads 8 B seed + 16 B join rows per band row
-    dom_bytes = {"forward": wide_cells * 16.5 + wide_cells / 2 * 0.0, "mutscore": narrow_cells / 5.875 * 24.0}.get(dom, 0.0)
+    dom_s = phase_ms[dom] * 1e-3
+    clock_mhz = clocks["sm_mhz"] or sm_max_mhz
+    peak_ops = sms * 128 * sm_max_mhz * 1e6 / 1e12                  # T lane-ops/s at max clock (SURVEY.md 8d)
+    achieved_ops = dom_cells * OPS_PER_CELL / dom_s / 1e12 if dom_s > 0 else 0.0
+    # algorithmic bytes of the dominant kernel: the wide fill writes 2 matrices x 8 B per
+    # cell plus 1 step byte per forward cell; the mutation kernel reads 8 B seed + 16 B join rows per band row
+    dom_bytes = {"forward": wide_cells * 16.5, "mutscore": narrow_cells / 5.875 * 24.0}.get(dom, 0.0)
+    # the fill is FP64 (exact): 45 FP64-pipe instructions per cell against the FP64 pipe of the SMs
+    # (64 lanes per SM; profiles/r1_fp64_ubench.txt measures 0.43 warp-instructions per cycle per scheduler)
+    fp64_peak = sms * 64 * sm_max_mhz * 1e6 / 1e12
+    fp64_per_cell = {"forward": 45, "mutscore": 0 if args.precision == "fast" else 46}.get(dom, 0)
+    fp64_achieved = dom_cells * fp64_per_cell / dom_s / 1e12 if dom_s > 0 else 0.0
     line = {
         "metric": METRIC, "value": total_cells / (dev_ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": wall_ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64" if args.precision == "fast" else "f64", "data": "synthetic",
         "config": {"workload": "ScorePoints (FindPointMutations+ScoreMutations) on 1 kb regions x 10x coverage, "
-                               "point_width 20, realign_width 300",
+                               "point_width 20, realign_width 300 (BASELINE.json configs[1])",
                    "regions_per_gpu_per_step": args.regions, "events_per_region": 2 * COVERAGE,
                    "mutations_per_region": 8 * (REGION_LEN - 4), "cells_per_step_per_gpu": step_cells,
                    "l2": "band working set %.0f MB per step exceeds the 126 MB L2" % (wide_cells * 16.5 / 1e6),
@@ -303,13 +328,22 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks,
         "phase_ms": phase_ms,
-        "roofline": {"bound": "fp32-issue", "kernel": {"forward": "k_fill", "mutscore": "k_mutscore"}.get(dom, dom),
+        "kernels": {"k_fill (forward+reverse wide fill, fp64)": {"ms": phase_ms["forward"], "cells": wide_cells,
+                                                                "gcups": wide_cells / phase_ms["forward"] / 1e6},
+                    dom_kernel if dom == "mutscore" else ("k_mutscore_f32 + exact re-score" if args.precision == "fast" else "k_mutscore"):
+                        {"ms": phase_ms["mutscore"], "cells": narrow_cells, "gcups": narrow_cells / phase_ms["mutscore"] / 1e6},
+                    "k_join": {"ms": phase_ms["join"]}, "k_backtrace": {"ms": phase_ms["backtrace"]}},
+        "roofline": {"bound": "fp32-issue", "kernel": dom_kernel,
                      "achieved": achieved_ops, "peak": peak_ops, "unit": "Tlane-op/s", "frac": achieved_ops / peak_ops,
-                     "ops_per_cell": OPS_PER_CELL, "clock_mhz_under_load": clock_hz / 1e6, "peak_source": peak_src,
-                     "traffic": None},
-        "roofline_hbm": {"bound": "hbm", "achieved": dom_bytes / (phase_ms[dom] * 1e-3) / 1e9 if phase_ms[dom] > 0 else 0.0,
-                         "peak": hbm_peak, "unit": "GB/s", "frac": dom_bytes / (phase_ms[dom] * 1e-3) / 1e9 / hbm_peak if phase_ms[dom] > 0 else 0.0,
-                         "peak_source": peak_src},
+                     "ops_per_cell": OPS_PER_CELL, "clock_mhz_under_load": clock_mhz, "peak_source": peak_src,
+                     "traffic": recorded_traffic(dom_kernel, args.regions),
+                     "note": "SURVEY.md 8d definition (24 FP32 lane-ops per cell); the dominant kernel computes in FP64, see roofline_fp64"},
+        "roofline_fp64": {"bound": "fp64-pipe", "kernel": dom_kernel, "achieved": fp64_achieved, "peak": fp64_peak,
+                          "unit": "T fp64-op/s", "frac": fp64_achieved / fp64_peak if fp64_peak else 0.0,
+                          "ops_per_cell": fp64_per_cell},
+        "roofline_hbm": {"bound": "hbm", "kernel": dom_kernel, "achieved": dom_bytes / dom_s / 1e9 if dom_s > 0 else 0.0,
+                         "peak": hbm_peak, "unit": "GB/s", "frac": dom_bytes / dom_s / 1e9 / hbm_peak if dom_s > 0 else 0.0,
+                         "peak_source": peak_src, "traffic": recorded_traffic(dom_kernel, args.regions)},
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:

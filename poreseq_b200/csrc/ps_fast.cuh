@@ -251,12 +251,267 @@ __global__ void __launch_bounds__(128) k_mutscore_f32(Batch b, int mask)
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// k_mutscore_rows_f32: the same FP32 scan, row-major.  A mutation that replaces at most one base
+// re-fills at most NC = 6 narrow columns.  Instead of finishing one column before the next (which
+// needs the previous column in a per-thread ring and re-reads the level records once per column),
+// the thread sweeps the rows once and keeps one (main, stay) pair per column in registers: cell
+// (i, c) reads (i, c-1) computed a moment ago, (i-1, c-1) and (i-1, c) from the registers of the
+// previous row.  Per row it loads one level record, one seed value and (for the last column) one
+// reverse cell pair, all one row ahead; the six emissions of a row are independent.
+// Arithmetic and operation order are those of k_mutscore_f32, so the two kernels agree bit for bit.
+// Mutations with longer replacement strings are left to the exact pass (k_flag sends them there).
+constexpr int NC = 6;
+
+struct ColState
+{
+    StateParamsF sp;
+    int i0, i1;
+    bool valid;
+};
+
+struct RowSweep               // everything the row loop carries, all in registers
+{
+    ColState col[NC];
+    float C[NC], S[NC];       // row i-1 of every narrow column
+    int ncol;
+    int p0, p1;               // band of the seed column
+    const double* seed;       // seed column (+ row_off), nullptr for the blank column 0
+    double a;                 // rebasing offset
+    const double* Bm; const double* Bs; int b0, b1; double dRa; bool joined;   // reverse column of the last narrow column
+    const LevelRecF* lev; int n0; long long rs;
+    float fl; float4 tr;
+    float best, joinmax;
+    // of the row about to be computed: emission of every column, seed value (rebased) at rows i and i-1
+    float em[NC];
+    float sd, sd_prev;
+};
+
+// seed column value of row i as stored (the rebasing offset itself outside its band / for the blank
+// column, so that it rebases to the floor)
+__device__ __forceinline__ double seed_raw(const RowSweep& q, int i)
+{
+    if (i < q.p0 || i > q.p1 || !q.seed) return 0.0;
+    return q.seed[row_off(q.rs, i)];
+}
+
+// rows [ia, ib].  FAST: every one of the first five columns (and the sixth, when there is one) is inside
+// its band and past its first row, the previous column covers rows i-1 and i, every state is valid
+// and (when joined) the reverse cell exists -- no predicate is left in the row body.  Otherwise the
+// general form with all edge cases.
+// Loads are issued at the top of a row and consumed at its bottom (the next row's emissions, the
+// join), so no loaded value is carried around the loop.
+template <bool FAST>
+__device__ __forceinline__ void sweep_rows(RowSweep& q, int ia, int ib, int rhi)
+{
+    for (int i = ia; i <= ib; i++)
+    {
+        // requests: level record and seed value of row i+1, reverse cells of row i
+        LevelRecF lrn; float eyn = 0.f; double sdn = 0.0;
+        lrn.x = lrn.y = lrn.ry = lrn.ey = 0.f;
+        if (i < rhi)
+        {
+            lrn = q.lev[i]; eyn = q.lev[q.n0 - i - 1].ey;
+            sdn = seed_raw(q, i + 1);
+        }
+        double bmr = 0.0, bsr = 0.0;
+        const int jb = q.n0 - i + 1;
+        const bool jin = jb >= q.b0 && jb <= q.b1;
+        if (q.joined && (FAST || jin)) { const long long ro = row_off(q.rs, jb); bmr = q.Bm[ro]; bsr = q.Bs[ro]; }
+        float left = q.sd, diag = q.sd_prev;                 // (i, c-1) and (i-1, c-1)
+        if (FAST)
+        {
+#pragma unroll
+            for (int c = 0; c < 5; c++)
+            {
+                const float upC = q.C[c], upS = q.S[c];
+                float Cn, Sn;
+                dp_cell_f(false, true, true, left, diag, q.em[c], upC, upS, q.fl, q.tr, Cn, Sn);
+                q.best = fmaxf(q.best, Cn);
+                q.C[c] = Cn; q.S[c] = Sn;
+                diag = upC; left = Cn;
+            }
+            if (q.ncol == 6)
+            {
+                // sixth column (every edit but a deletion), predicated instead of a second code path
+                const float upC = q.C[5], upS = q.S[5];
+                float Cn, Sn;
+                dp_cell_f(false, true, true, left, diag, q.em[5], upC, upS, q.fl, q.tr, Cn, Sn);
+                q.best = fmaxf(q.best, Cn);
+                q.C[5] = Cn; q.S[5] = Sn;
+            }
+            if (q.joined)
+            {
+                const float Cl = q.ncol == 6 ? q.C[5] : q.C[4], Sl = q.ncol == 6 ? q.S[5] : q.S[4];
+                q.joinmax = fmaxf(q.joinmax, fmaxf(Cl + (float)(bmr - q.dRa), Sl + (float)(bsr - q.dRa)));
+            }
+        }
+        else
+        {
+            int q0 = q.p0, q1 = q.p1;                        // band of column c-1
+#pragma unroll
+            for (int c = 0; c < NC; c++)
+            {
+                if (c < q.ncol)
+                {
+                    const bool act = i >= q.col[c].i0 && i <= q.col[c].i1;
+                    const float upC = q.C[c], upS = q.S[c];
+                    if (act)
+                    {
+                        float Cn = q.fl, Sn = q.fl;
+                        if (q.col[c].valid)
+                        {
+                            const bool skip_ok = i >= q0 && i <= q1;
+                            const bool diag_ok = i > q0 && i <= q1;
+                            dp_cell_f(i == q.col[c].i0, skip_ok, diag_ok, left, diag, q.em[c], upC, upS, q.fl, q.tr, Cn, Sn);
+                            q.best = fmaxf(q.best, Cn);
+                        }
+                        if (c == q.ncol - 1 && q.joined && jin)
+                            q.joinmax = fmaxf(q.joinmax, fmaxf(Cn + (float)(bmr - q.dRa), Sn + (float)(bsr - q.dRa)));
+                        q.C[c] = Cn; q.S[c] = Sn;
+                    }
+                    diag = upC;                              // (i-1, c) is the next column's diagonal
+                    left = q.C[c];
+                    q0 = q.col[c].i0; q1 = q.col[c].i1;
+                }
+            }
+        }
+        // bottom of the row: what row i+1 needs
+#pragma unroll
+        for (int c = 0; c < NC; c++) q.em[c] = emission_f(lrn, eyn, q.col[c].sp);
+        q.sd_prev = q.sd;
+        q.sd = (float)(sdn - q.a);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_mutscore_rows_f32(Batch b)
+{
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int W = b.scoring_width;
+    for (long long t = gtid; t < b.n_tasks; t += nthreads)
+    {
+        int e, m;
+        if (!task_decode(b, t, e, m)) continue;
+        const EvDesc ev = b.ev[e];
+        const MutDev mu = b.muts[ev.mut_off + m];
+        double result = 0.0;
+        if (ev.usable && !((unsigned)mu.start > (unsigned)ev.L) && mu.n_mut <= 1)
+        {
+            const int N = ev.N, n0 = ev.n0, L = ev.L;
+            MutView mv;
+            mv.bases = b.bases + ev.base_off; mv.L = L; mv.mstr = b.mut_str + mu.str_off;
+            mv.start = mu.start; mv.n_orig = mu.n_orig; mv.n_mut = mu.n_mut;
+            mv.applied = mu.start < L;
+            mv.Lm = mv.applied ? mu.start + mu.n_mut + max(0, L - mu.start - mu.n_orig) : L;
+            const int Nm = mv.Lm >= 5 ? mv.Lm - 4 : 0;
+            const int raf = max(mu.start - 3, 1);
+            const double R = raf <= N ? b.old[ev.col_off + raf] : thread_join(b, ev, raf, N - raf + 1);
+            const int startind = max(mu.start - 4, 0);
+            const int refind = mu.start + mu.n_mut + 1;
+            int last = min(min(refind, startind + mu.n_mut + 6), Nm);
+            if (W == 0) last = startind;
+            if (last <= startind)
+                result = thread_join(b, ev, startind, Nm - startind + 1) - R;     // boundary case: exact
+            else
+            {
+                RowSweep q;
+                q.ncol = last - startind;                                         // 1..NC
+                const StateParamsF* stf = b.stf + (size_t)ev.model * N_STATES;
+                const bool ri_empty = b.ri_empty[e] != 0;
+                q.rs = ev.rs; q.n0 = n0;
+                q.tr = b.trf[ev.model];
+                bool all_valid = true;
+#pragma unroll
+                for (int c = 0; c < NC; c++)
+                {
+                    q.col[c].i0 = 1; q.col[c].i1 = 0; q.col[c].valid = false;
+                    q.col[c].sp = stf[0];
+                    if (c < q.ncol)
+                    {
+                        band_of(ri_empty ? 1 : b.cen_new[ev.cen_off + startind + 1 + c], n0, W, q.col[c].i0, q.col[c].i1);
+                        const int s = mut_state(mv, startind + c);
+                        q.col[c].valid = s >= 0;
+                        all_valid = all_valid && s >= 0;
+                        q.col[c].sp = stf[max(s, 0)];
+                    }
+                }
+                // seed column (forward column startind, or the blank column 0) and the rebasing offset
+                q.p0 = 0; q.p1 = n0; q.seed = nullptr; q.a = 0.0;
+                double best_d = 0.0;
+                if (startind > 0)
+                {
+                    const long long gs = ev.col_off + startind;
+                    q.p0 = b.Fi0[gs]; q.p1 = q.p0 + b.Flen[gs] - 1;
+                    q.seed = b.Fm + col_base(ev, startind);
+                    best_d = b.Fbest[gs];
+                    const int mid = min(max((q.col[0].i0 + q.col[0].i1) >> 1, q.p0), q.p1);
+                    q.a = q.seed[row_off(q.rs, mid)];
+                }
+                q.fl = (float)(-q.a);
+                q.best = (float)(best_d - q.a);
+                // reverse column the last narrow column is joined with; values relative to R
+                const int rab = min(max(Nm - last + 1, 0), N);
+                q.dRa = R - q.a;
+                double mb = 0.0;
+                q.b0 = 1; q.b1 = 0; q.joined = rab > 0;
+                q.Bm = b.Bm; q.Bs = b.Bs;
+                if (rab > 0)
+                {
+                    const long long gb = ev.col_off + rab;
+                    q.b0 = b.Bi0[gb]; q.b1 = q.b0 + b.Blen[gb] - 1;
+                    mb = b.Bbest[gb];
+                    const long long bbase = col_base(ev, rab);
+                    q.Bm = b.Bm + bbase; q.Bs = b.Bs + bbase;
+                }
+                q.joinmax = NEGF;
+                q.lev = b.levf + ev.lev_off;
+                // rows swept: from the first row of the first column to the last row of the last one; the
+                // predicate-free rows are those every column treats as interior (see sweep_rows)
+                int rlo = q.col[0].i0, rhi = q.col[0].i1;
+                int flo = max(q.col[0].i0, q.p0) + 1, fhi = min(q.col[0].i1, q.p1);
+#pragma unroll
+                for (int c = 1; c < NC; c++)
+                    if (c < q.ncol)
+                    {
+                        rlo = min(rlo, q.col[c].i0); rhi = max(rhi, q.col[c].i1);
+                        flo = max(flo, max(q.col[c].i0, q.col[c - 1].i0) + 1);
+                        fhi = min(fhi, min(q.col[c].i1, q.col[c - 1].i1));
+                    }
+                if (q.joined) { flo = max(flo, n0 + 1 - q.b1); fhi = min(fhi, n0 + 1 - q.b0); }
+                if (!all_valid || q.ncol < 5 || flo > fhi) { flo = rhi + 1; fhi = rhi; }
+#pragma unroll
+                for (int c = 0; c < NC; c++) { q.C[c] = q.fl; q.S[c] = q.fl; }
+                q.sd_prev = (float)(seed_raw(q, rlo - 1) - q.a);
+                q.sd = (float)(seed_raw(q, rlo) - q.a);
+                {
+                    const LevelRecF lr = q.lev[rlo - 1];
+                    const float ey = q.lev[n0 - rlo].ey;
+#pragma unroll
+                    for (int c = 0; c < NC; c++) q.em[c] = emission_f(lr, ey, q.col[c].sp);
+                }
+                sweep_rows<false>(q, rlo, flo - 1, rhi);
+                sweep_rows<true>(q, flo, fhi, rhi);
+                sweep_rows<false>(q, fhi + 1, rhi, rhi);
+                float joinmax = q.joinmax;
+                // a blank reverse column (all zeros) adds nothing beyond the running best of the forward cells
+                if (rab == 0) joinmax = q.best - (float)q.dRa;
+                // new - old = max(join, best, reverse best, 0) - R, all relative to R
+                const float rel = fmaxf(fmaxf(joinmax, q.best - (float)q.dRa), fmaxf((float)(mb - R), (float)(-R)));
+                result = (double)rel;
+            }
+        }
+        b.delta[t] = result;
+    }
+}
+
 // mutations whose FP32 total is not clearly negative go to the exact pass
-__global__ void k_flag(Batch b, long long n_muts)
+// (and so do the mutations the FP32 scan does not handle: replacement strings longer than max_mut bases)
+__global__ void k_flag(Batch b, long long n_muts, int max_mut)
 {
     long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_muts) return;
-    if (b.scores[g] > -b.tau)
+    if (b.scores[g] > -b.tau || b.muts[g].n_mut > max_mut)
     {
         const int q = atomicAdd(b.flag_count, 1);
         b.flag_list[q] = (int)g;

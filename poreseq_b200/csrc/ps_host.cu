@@ -172,6 +172,9 @@ int ps_ctx::init()
     CU(cudaFuncSetAttribute(k_mutscore<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU(cudaFuncSetAttribute(k_mutscore<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU(cudaFuncSetAttribute(k_mutscore_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    // the per-thread rings of the exact mutation kernel are what limits its occupancy: ask for the largest shared-memory carve-out
+    CU(cudaFuncSetAttribute(k_mutscore<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_mutscore<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     ready = true;
     return PS_OK;
 }
@@ -863,17 +866,26 @@ int Job::run(bool full)
             int mask = 1;
             while (mask + 1 < 2 * b.scoring_width + 2) mask = 2 * mask + 1;     // power-of-two ring >= 2W+2 rows
             const size_t ringf_bytes = (size_t)(mask + 1) * 128 * sizeof(float);
-            if (fast && in_smem && ringf_bytes <= 96 * 1024)
+            static const bool old_scan = getenv("PORESEQ_B200_MUT_OLD") != nullptr;   // column-major FP32 scan, kept for A/B runs
+            if (fast && (!old_scan || (in_smem && ringf_bytes <= 96 * 1024)))
             {
                 // pass 1: every pair in rebased FP32; pass 2: exact FP64 for the mutations that matter
-                k_mutscore_f32<<<(unsigned)blocks, threads, ringf_bytes, ctx->stream>>>(b, mask);
+                if (old_scan) k_mutscore_f32<<<(unsigned)blocks, threads, ringf_bytes, ctx->stream>>>(b, mask);
+                else k_mutscore_rows_f32<<<(unsigned)blocks, threads, 0, ctx->stream>>>(b);
                 LAUNCHED();
                 k_reduce<<<(unsigned)((n_muts + 127) / 128), 128, 0, ctx->stream>>>(b, (const RegTabDev*)d_regtab, (int)regs.size(), n_muts, bias, 0);
                 LAUNCHED();
                 CU(cudaMemsetAsync(b.flag_count, 0, sizeof(int), ctx->stream));
-                k_flag<<<(unsigned)((n_muts + 127) / 128), 128, 0, ctx->stream>>>(b, n_muts);
+                k_flag<<<(unsigned)((n_muts + 127) / 128), 128, 0, ctx->stream>>>(b, n_muts, old_scan ? 1 << 30 : 1);
                 LAUNCHED();
-                k_mutscore<true, true><<<(unsigned)std::min<long long>(blocks, (long long)ctx->sm_count * 4), threads, ring * 128, ctx->stream>>>(b);
+                const unsigned rblocks = (unsigned)std::min<long long>(blocks, (long long)ctx->sm_count * 4);
+                if (in_smem) k_mutscore<true, true><<<rblocks, threads, ring * 128, ctx->stream>>>(b);
+                else
+                {
+                    b.scratch_slots = (long long)rblocks * threads;
+                    TRY(room(ctx, "scratch", (size_t)b.scratch_slots * (2 * b.scoring_width + 2), &b.scratch));
+                    k_mutscore<false, true><<<rblocks, threads, 0, ctx->stream>>>(b);
+                }
                 LAUNCHED();
                 MARK(PS_T_REDUCE);
                 k_reduce<<<(unsigned)((n_muts + 127) / 128), 128, 0, ctx->stream>>>(b, (const RegTabDev*)d_regtab, (int)regs.size(), n_muts, bias, 1);
