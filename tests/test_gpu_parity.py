@@ -274,3 +274,115 @@ def test_fast_mode_decisions_exact(orc, name):
         assert same_aligns([nr.event_align(e) for e in range(len(reg.events))], want_a)
     finally:
         c2.close()
+
+
+# ---- launch classes, odd shapes, batching API, full-size configs ---------------------------------
+@pytest.mark.parametrize("kw", [
+    dict(length=401, coverage=3, seed=31, draft_error=0.03, params=dict(realign_width=60, scoring_width=15, point_width=8)),   # odd N
+    dict(length=230, coverage=3, seed=32, draft_error=0.02, params=dict(realign_width=450, scoring_width=30, point_width=12)),  # band wider than the event
+    dict(length=900, coverage=2, seed=33, draft_error=0.02, params=dict(realign_width=420, scoring_width=20, point_width=9)),   # wavefront wider than 160 threads
+    dict(length=60, coverage=3, seed=34, params=dict(realign_width=7, scoring_width=3, point_width=2)),                        # tiny band
+], ids=["odd", "band_gt_event", "wide_class", "tiny_band"])
+def test_fill_shapes(ctx, orc, kw):
+    """Odd column / row counts (2x2 tiles with a half-empty last strip or row pair), bands clipped by
+    the event, the wide wavefront class and very narrow bands."""
+    reg = synth.make_region(**kw)
+    want_s, want_l, want_a = orc.score_alignments(reg, True)
+    nr = native(ctx, reg)
+    got_s, got_l = nr.score_alignments(True)
+    assert np.array_equal(got_s, want_s)
+    assert np.array_equal(got_l, want_l)
+    assert same_aligns(native_aligns(nr, reg), want_a)
+    want, want_a = orc.score_points(reg)
+    nr = native(ctx, reg, "point_width")
+    st, og, mu, sc = nr.score_points()
+    assert np.array_equal(sc, np.array([w[3] for w in want]))
+    assert same_aligns(native_aligns(nr, reg), want_a)
+
+
+def test_short_events(ctx, orc):
+    """Events of 1..6 levels (single row pairs, strips that end on their first step)."""
+    reg = synth.make_region(120, 3, seed=35, params=dict(realign_width=10, scoring_width=4, point_width=3))
+    for k, ev in enumerate(reg.events):
+        n = 1 + k
+        ev.mean, ev.stdv = ev.mean[:n].copy(), ev.stdv[:n].copy()
+        ev.ref_align, ev.ref_like = ev.ref_align[:n].copy(), ev.ref_like[:n].copy()
+    want_s, _, want_a = orc.score_alignments(reg)
+    nr = native(ctx, reg)
+    got_s, _ = nr.score_alignments()
+    assert np.array_equal(got_s, want_s)
+    assert same_aligns(native_aligns(nr, reg), want_a)
+    want, _ = orc.score_points(reg)
+    st, og, mu, sc = native(ctx, reg, "point_width").score_points()
+    assert np.array_equal(sc, np.array([w[3] for w in want]))
+
+
+def test_packed_and_async_batches(orc):
+    """ps_region_add_events + ps_score_points_batch_begin/_end on two contexts: same scores as the
+    per-event, synchronous path (and as the checker)."""
+    regs = [region("clean"), region("draft_partial"), region("ragged")]
+    packs = [poreseqcpp.PackedRegion(r.sequence, r.events, r.params) for r in regs]
+    want = [np.array([w[3] for w in orc.score_points(r)[0]]) for r in regs]
+    ctxs = [poreseqcpp.Context(0), poreseqcpp.Context(0)]
+    try:
+        pend = []
+        for c in ctxs:                       # two batches in flight, one per context
+            nrs = [poreseqcpp.NativeRegion.from_packed(c, p, "point_width") for p in packs]
+            pend.append(poreseqcpp.score_points_batch_begin(c, nrs))
+        for p in pend:
+            out = p.end()
+            for (st, og, mu, sc), w in zip(out, want):
+                assert np.array_equal(sc, w)
+        # a second _begin on a busy context is refused, _end without _begin too
+        nrs = [poreseqcpp.NativeRegion.from_packed(ctxs[0], packs[0], "point_width")]
+        p = poreseqcpp.score_points_batch_begin(ctxs[0], nrs)
+        with pytest.raises(RuntimeError):
+            poreseqcpp.score_points_batch_begin(ctxs[0], nrs)
+        p.end()
+        with pytest.raises(RuntimeError):
+            p.end()
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def test_config2_full_size(ctx, ref):
+    """BASELINE.json configs[1] at full size (1 kb x 10x, default widths): every one of the 7968 point
+    mutation scores bit-identical to the compiled reference (about 4 s of CPU)."""
+    reg = synth.make_region(1000, 10, seed=101)
+    want, want_a = ref.score_points(reg)
+    nr = native(ctx, reg, "point_width")
+    st, og, mu, sc = nr.score_points()
+    assert len(sc) == 8 * (1000 - 4)
+    assert np.array_equal(sc, np.array([w[3] for w in want]))
+    assert same_aligns(native_aligns(nr, reg), want_a)
+
+
+def test_config3_size_properties(ref):
+    """BASELINE.json configs[2] size (10 kb, 30x = 60 events): ScoreEvents bit-identical to the compiled
+    reference (one CPU pass, ~6 s); the full point scan (1157 s on one CPU core) is checked through
+    properties: fast vs exact mode agree (decisions identical, scores within 1e-4 relative), 300
+    sampled mutations match the reference bit for bit, and re-scoring the realigned region is stable."""
+    reg = synth.make_region(10000, 30, seed=102, draft_error=0.01)
+    want_s, _, want_a = ref.score_alignments(reg)
+    cx, cf = poreseqcpp.Context(0), poreseqcpp.Context(0)
+    cf.set_precision("fast")
+    try:
+        nr = native(cx, reg)
+        got_s, _ = nr.score_alignments()
+        assert np.array_equal(got_s, want_s)
+        assert same_aligns(native_aligns(nr, reg), want_a)
+        st, og, mu, sc = native(cx, reg, "point_width").score_points()
+        st2, og2, mu2, sf = native(cf, reg, "point_width").score_points()
+        assert len(sc) == 8 * (len(reg.sequence) - 4)
+        assert np.array_equal(sc >= 0, sf >= 0)
+        assert np.array_equal(sc[sc > -0.02], sf[sc > -0.02])
+        assert np.all(np.abs(sf - sc) <= 1e-4 * np.abs(sc) + 1e-3), float(np.max(np.abs(sf - sc)))
+        rng = np.random.default_rng(5)
+        pick = np.sort(rng.choice(len(sc), 300, replace=False))
+        reg.params = dict(reg.params, scoring_width=reg.params["point_width"])
+        w, _ = ref.score_mutations(reg, [int(st[i]) for i in pick], [chr(og[i]) if og[i] else "" for i in pick],
+                                   [chr(mu[i]) if mu[i] else "" for i in pick])
+        assert np.array_equal(sc[pick], w)
+    finally:
+        cx.close(); cf.close()

@@ -87,3 +87,29 @@ def test_swalign_matches_reference(ref):
     acc, pairs = poreseqcpp.swalign("AAAAAAAAAACCCCCCCCCC", "AAAAACCCCCCCCCCCCAAAAA")
     want_acc, _, want_pairs = ref.swfull("AAAAAAAAAACCCCCCCCCC", "AAAAACCCCCCCCCCCCAAAAA")
     assert pairs == want_pairs and acc == want_acc
+
+
+def test_packed_marshalling_equals_per_event():
+    """ps_region_add_events (one call per region) builds the same native region as one
+    ps_region_add_event per event: same sequence, same per-event alignments, same event count.
+    No compute call, so this runs without a GPU."""
+    import numpy as np
+    from poreseq_b200 import poreseqcpp, synth
+    reg = synth.make_region(300, 3, seed=9, draft_error=0.05, partial=0.4)
+    ctx = poreseqcpp.Context(0)
+    a = poreseqcpp.NativeRegion(ctx, reg.sequence, reg.events, reg.params, "point_width")
+    pack = poreseqcpp.PackedRegion(reg.sequence, reg.events, reg.params)
+    b = poreseqcpp.NativeRegion.from_packed(ctx, pack, "point_width")
+    assert a.sequence() == b.sequence() == reg.sequence
+    assert ctx.lib.ps_region_num_events(a.handle) == ctx.lib.ps_region_num_events(b.handle) == len(reg.events)
+    for e in range(len(reg.events)):
+        ra, rl = a.event_align(e)
+        rb, lb = b.event_align(e)
+        assert np.array_equal(ra, rb) and np.array_equal(rl, lb)
+        assert np.array_equal(ra, reg.events[e].ref_align)
+    # a model index outside the table is refused and leaves the region unchanged
+    bad = poreseqcpp.PackedRegion(reg.sequence, reg.events, reg.params)
+    bad.model_index = bad.model_index + 7
+    with pytest.raises(RuntimeError):
+        poreseqcpp.NativeRegion.from_packed(ctx, bad, "point_width")
+    assert pack.nbytes() > 0
