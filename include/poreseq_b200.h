@@ -185,6 +185,12 @@ int         ps_seq_to_states(const char* seq, int len, int* states);
 int         ps_swfull(const char* seq1, const char* seq2, int* inds1, int* inds2, int cap,
                       int* n, int* score, double* accuracy);
 
+/* The same alignment computed on the GPU (ps_sw.cu: int32 scores, one byte of traceback per cell,
+ * anti-diagonal wavefront, the reference's tie order), for sequences of 1..16384 bases.  FindMutations
+ * uses the batched form of this internally for its seed realignments (cpp/EventUtil.cpp:16). */
+int         ps_swfull_device(ps_ctx* ctx, const char* seq1, const char* seq2, int* inds1, int* inds2, int cap,
+                             int* n, int* score, double* accuracy);
+
 #ifdef __cplusplus
 }
 #endif

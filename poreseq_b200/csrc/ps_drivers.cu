@@ -3,6 +3,7 @@
 // Find/Score/Make iteration of PSAlign.Mutate.  All DP over events runs on the GPU through
 // ps_run_job(); what stays here is sequential glue the reference also runs on one core.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -86,7 +87,11 @@ void psi_fillinds(SWResult& al)
 // every level's ref_align across: value v -> inds2[lower_bound(inds1, v)], 0 outside the aligned span.
 SWResult psi_map_alignments(ps_region* R, const std::string& newseq)
 {
-    SWResult al = psi_swfull(R->bases, newseq);
+    return psi_map_alignments_with(R, newseq, psi_swfull(R->bases, newseq));
+}
+
+SWResult psi_map_alignments_with(ps_region* R, const std::string& newseq, SWResult al)
+{
     psi_fillinds(al);
     R->set_sequence(newseq);
     const std::vector<int>& a = al.inds1;
@@ -114,6 +119,9 @@ int ps_find_mutation_list(ps_region* R, const std::vector<std::string>& seeds, s
     found.clear();
     ps_ctx* ctx = R->ctx;
     const size_t L = R->bases.size();
+    const bool trace = getenv("PORESEQ_B200_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_start = now();
     // 1. realign to the current sequence, keep its per-base likelihood profile
     std::vector<double> base(L, 0.0);
     {
@@ -127,16 +135,27 @@ int ps_find_mutation_list(ps_region* R, const std::vector<std::string>& seeds, s
     std::vector<SWResult> als(S);
     std::vector<ps_region*> shadows;
     std::vector<std::string> shadow_key;
-    for (size_t s = 0; s < S; s++)
-    {
+    const double t_base = now();
+    // the SW maps (O(L^2) each, the host-side cost of FindMutations) are independent per seed: worker threads
+    // on the GPU (ps_sw.cu) for sequences up to 16 k bases, else on the host worker threads
+    std::vector<ps_region*> nds(S, nullptr);
+    std::vector<SWResult> sw;
+    const bool sw_gpu = !getenv("PORESEQ_B200_SW_HOST") && psi_swfull_batch(ctx, R->bases, seeds, sw) == PS_OK;
+    ps_parallel_for((int)S, [&](int s) {
         ps_region* nd = new ps_region(*R);
         nd->seqlikes.clear();
-        als[s] = psi_map_alignments(nd, seeds[s]);
+        als[s] = sw_gpu ? psi_map_alignments_with(nd, seeds[s], sw[s]) : psi_map_alignments(nd, seeds[s]);
+        nds[s] = nd;
+    });
+    for (size_t s = 0; s < S; s++)
+    {
+        ps_region* nd = nds[s];
         const bool cached = R->seqlikes.count(seeds[s]) && !R->seqlikes[seeds[s]].empty();
         const bool queued = std::find(shadow_key.begin(), shadow_key.end(), seeds[s]) != shadow_key.end();
         if (!cached && !queued && seeds[s].size() >= 5) { shadows.push_back(nd); shadow_key.push_back(seeds[s]); }
         else delete nd;
     }
+    const double t_sw = now();
     if (!shadows.empty())
     {
         std::vector<std::vector<double>> likes;
@@ -148,6 +167,8 @@ int ps_find_mutation_list(ps_region* R, const std::vector<std::string>& seeds, s
         }
         if (rc) return rc;
     }
+    if (trace) fprintf(stderr, "[ps] FindMutations: base realign %.1f ms, %zu SW maps %.1f ms, %zu shadow regions realigned %.1f ms\n",
+                       t_base - t_start, S, t_sw - t_base, shadows.size(), now() - t_sw);
     // 3. CUSUM of the profile difference along each SW alignment (:51-94)
     std::vector<std::vector<double>> dl(S);
     for (size_t s = 0; s < S; s++)
@@ -176,17 +197,22 @@ int ps_find_mutation_list(ps_region* R, const std::vector<std::string>& seeds, s
         }
     }
     // 4. greedy peak picking (:111-183)
+    std::vector<long> peak_at(S, -1);              // cached first argmax of every seed's curve, -1 = stale
     while (found.size() < L / 3)
     {
         int smax = -1, ind = 0;
         double vmax = 0;
+        // (the reference rescans every seed's curve per pick; only the curve the previous pick zeroed can have
+        // a new first maximum, so the others keep their cached one -- same picks, same tie order)
         for (size_t s = 0; s < S; s++)
         {
             if (dl[s].empty()) continue;
-            const size_t at = std::max_element(dl[s].begin(), dl[s].end()) - dl[s].begin();
+            if (peak_at[s] < 0) peak_at[s] = (long)(std::max_element(dl[s].begin(), dl[s].end()) - dl[s].begin());
+            const size_t at = (size_t)peak_at[s];
             if (smax < 0 || dl[s][at] > vmax) { smax = (int)s; ind = (int)at; vmax = dl[s][at]; }
         }
         if (smax < 0 || vmax < 0.25) break;
+        peak_at[smax] = -1;
         std::vector<double>& d = dl[smax];
         const int n = (int)d.size();
         int i1 = ind;
@@ -221,11 +247,18 @@ int ps_mutate_loop(ps_region* R, const std::vector<std::string>& seeds, int reps
     int total = 0;
     for (int rep = 0; rep < reps; rep++)
     {
+        const bool trace = getenv("PORESEQ_B200_TRACE") != nullptr;
+        auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        const double t0 = now();
         std::vector<HostMut> cand;
         TRY(ps_find_mutation_list(R, seeds, cand));
+        const double t1 = now();
         TRY(ps_score_mutation_list(R, cand));
+        const double t2 = now();
         int nb = 0;
         TRY(ps_make_mutation_list(R, cand, &nb));
+        if (trace) fprintf(stderr, "[ps] Mutate rep %d: FindMutations %.1f ms (%zu candidates), ScoreMutations %.1f ms, MakeMutations %.1f ms (%d bases)\n",
+                           rep, t1 - t0, cand.size(), t2 - t1, now() - t2, nb);
         if (nb == 0) break;
         total += nb;
     }
@@ -240,6 +273,22 @@ int ps_swfull(const char* seq1, const char* seq2, int* inds1, int* inds2, int ca
 {
     if (!seq1 || !seq2) return PS_E_ARG;
     SWResult r = psi_swfull(std::string(seq1), std::string(seq2));
+    if (n) *n = (int)r.inds1.size();
+    if (score) *score = r.score;
+    if (accuracy) *accuracy = r.accuracy;
+    if ((int)r.inds1.size() > cap) return PS_E_CAPACITY;
+    for (size_t k = 0; k < r.inds1.size(); k++) { if (inds1) inds1[k] = r.inds1[k]; if (inds2) inds2[k] = r.inds2[k]; }
+    return PS_OK;
+}
+
+int ps_swfull_device(ps_ctx* ctx, const char* seq1, const char* seq2, int* inds1, int* inds2, int cap, int* n, int* score, double* accuracy)
+{
+    if (!ctx || !seq1 || !seq2) return PS_E_ARG;
+    std::vector<SWResult> out;
+    int rc = psi_swfull_batch(ctx, std::string(seq1), std::vector<std::string>(1, std::string(seq2)), out);
+    if (rc == PS_E_ARG) { ps_set_error(ctx, "ps_swfull_device: sequences of 1..16384 bases only"); return rc; }
+    if (rc) return rc;
+    const SWResult& r = out[0];
     if (n) *n = (int)r.inds1.size();
     if (score) *score = r.score;
     if (accuracy) *accuracy = r.accuracy;

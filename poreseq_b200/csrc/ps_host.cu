@@ -160,6 +160,7 @@ int ps_ctx::init()
         return PS_E_CUDA;
     }
     sm_count = prop.multiProcessorCount;
+    total_mem = prop.totalGlobalMem;
     if (const char* fw = getenv("PORESEQ_B200_FILL_WARPS")) fill_warps = std::min(16, std::max(1, atoi(fw)));
     CU(cudaStreamCreate(&stream));
     CU(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
@@ -1040,11 +1041,51 @@ static int job_end(ps_ctx* ctx, std::vector<double>* align_scores, std::vector<d
     return rc;
 }
 
+// Band storage a region's events need (upper estimate: widest common wavefront class, both directions
+// when mutations are scored).  Decides how a large job is cut into consecutive sub-batches.
+static double region_band_bytes(const ps_region* R, bool full)
+{
+    const double J = (R->states.size() + 1) / 2;
+    double cells = 0;
+    for (const HostEvent& he : R->events) cells += (J + (he.n0 + 1) / 2 + 2) * 192.0 * 4.0;
+    return cells * (full ? 33.0 : 17.0);
+}
+
 static int run_job(ps_ctx* ctx, const std::vector<ps_region*>& regs, const std::vector<MutSpec>* muts,
                    std::vector<double>* align_scores, std::vector<double>* mut_scores, double bias = -1e-6)
 {
-    TRY(job_begin(ctx, regs, muts, bias));
-    return job_end(ctx, align_scores, mut_scores);
+    TRY(ctx->init());
+    // a job whose band matrices would not fit (e.g. FindMutations: seeds x events wide fills of a 10 kb
+    // region) runs as consecutive sub-batches of whole regions; results are concatenated in region order
+    double budget = 0.40 * (double)ctx->total_mem;
+    if (const char* e = getenv("PORESEQ_B200_BAND_BUDGET")) budget = atof(e);      // bytes; tests force the split path with it
+    double total = 0;
+    for (const ps_region* R : regs) total += region_band_bytes(R, muts != nullptr);
+    if (total <= budget || regs.size() <= 1)
+    {
+        TRY(job_begin(ctx, regs, muts, bias));
+        return job_end(ctx, align_scores, mut_scores);
+    }
+    if (align_scores) align_scores->clear();
+    if (mut_scores) mut_scores->clear();
+    size_t a = 0;
+    while (a < regs.size())
+    {
+        size_t b = a;
+        double acc = 0;
+        while (b < regs.size() && (b == a || acc + region_band_bytes(regs[b], muts != nullptr) <= budget))
+            acc += region_band_bytes(regs[b++], muts != nullptr);
+        std::vector<ps_region*> sub(regs.begin() + a, regs.begin() + b);
+        std::vector<MutSpec> subm;
+        if (muts) subm.assign(muts->begin() + a, muts->begin() + b);
+        std::vector<double> as, ms;
+        TRY(job_begin(ctx, sub, muts ? &subm : nullptr, bias));
+        TRY(job_end(ctx, align_scores ? &as : nullptr, mut_scores ? &ms : nullptr));
+        if (align_scores) align_scores->insert(align_scores->end(), as.begin(), as.end());
+        if (mut_scores) mut_scores->insert(mut_scores->end(), ms.begin(), ms.end());
+        a = b;
+    }
+    return PS_OK;
 }
 
 int ps_run_alignments(ps_ctx* ctx, const std::vector<ps_region*>& regs,

@@ -39,6 +39,7 @@ struct ps_ctx
     int device = 0;
     bool ready = false;
     int sm_count = 0;
+    size_t total_mem = 0;
     int precision = 0;                        // PS_PRECISION_EXACT / PS_PRECISION_FAST
     int fill_warps = 8;                       // warps per (event, direction) in the wide fill (PORESEQ_B200_FILL_WARPS)
     cudaStream_t stream = nullptr;
@@ -119,6 +120,9 @@ struct SWResult                               // cpp/swlib.h:25-33
 };
 
 SWResult psi_swfull(const std::string& s1, const std::string& s2);
+// the same on the GPU for one sequence against many (ps_sw.cu); PS_E_ARG when a sequence is too long for it
+int psi_swfull_batch(ps_ctx* ctx, const std::string& s1, const std::vector<std::string>& others, std::vector<SWResult>& out);
+SWResult psi_map_alignments_with(ps_region* R, const std::string& newseq, SWResult al);
 void psi_fillinds(SWResult& al);
 SWResult psi_map_alignments(ps_region* R, const std::string& newseq);
 // forward fill + backtrace of every event of every region (ScoreAlignments); per-region score

@@ -77,6 +77,7 @@ def lib():
     L.ps_refine.argtypes = [C.c_void_p, _c_int_p]
     L.ps_seq_to_states.argtypes = [C.c_char_p, C.c_int, _c_int_p]
     L.ps_swfull.argtypes = [C.c_char_p, C.c_char_p, _c_int_p, _c_int_p, C.c_int, _c_int_p, _c_int_p, _c_double_p]
+    L.ps_swfull_device.argtypes = [C.c_void_p] + L.ps_swfull.argtypes
     L.ps_map_alignments.argtypes = [C.c_void_p, C.c_char_p]
     L.ps_find_mutations.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), _c_int_p]
     L.ps_found_mutation_sizes.argtypes = [C.c_void_p, C.c_int, _c_int_p, _c_int_p]
@@ -461,6 +462,19 @@ def swalign(seq1, seq2):
     if rc != 0:
         raise RuntimeError("ps_swfull failed (%d)" % rc)
     return (acc.value, list(zip(i1[:n.value].tolist(), i2[:n.value].tolist())))
+
+
+def swalign_device(ctx, seq1, seq2):
+    """swalign computed on the GPU (ps_swfull_device); returns (score, accuracy, index pairs)."""
+    a = seq1.encode("ascii") if isinstance(seq1, str) else bytes(seq1)
+    b = seq2.encode("ascii") if isinstance(seq2, str) else bytes(seq2)
+    cap = len(a) + len(b) + 8
+    i1 = np.zeros(cap, dtype=np.int32)
+    i2 = np.zeros(cap, dtype=np.int32)
+    n, score, acc = C.c_int(0), C.c_int(0), C.c_double(0)
+    ctx.check(ctx.lib.ps_swfull_device(ctx.handle, a, b, i1.ctypes.data_as(_c_int_p), i2.ctypes.data_as(_c_int_p), cap,
+                                       C.byref(n), C.byref(score), C.byref(acc)))
+    return score.value, acc.value, list(zip(i1[:n.value].tolist(), i2[:n.value].tolist()))
 
 
 def seqtostates(seq):

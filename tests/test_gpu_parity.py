@@ -386,3 +386,42 @@ def test_config3_size_properties(ref):
         assert np.array_equal(sc[pick], w)
     finally:
         cx.close(); cf.close()
+
+
+def test_oversized_job_is_split(orc, monkeypatch):
+    """A job whose band matrices exceed the memory budget runs as consecutive sub-batches of whole
+    regions (FindMutations on a 10 kb region at 30x needs ~190 GB otherwise): same results."""
+    monkeypatch.setenv("PORESEQ_B200_BAND_BUDGET", "3e6")      # ~ one small region per sub-batch
+    c = poreseqcpp.Context(0)
+    try:
+        regs = [region("clean"), region("draft_partial"), region("ragged")]
+        nrs = [native(c, r, "point_width") for r in regs]
+        out = poreseqcpp.score_points_batch(c, nrs)
+        for r, nr, (st, og, mu, sc) in zip(regs, nrs, out):
+            want, want_a = orc.score_points(r)
+            assert np.array_equal(sc, np.array([w[3] for w in want]))
+            assert same_aligns(native_aligns(nr, r), want_a)
+    finally:
+        c.close()
+
+
+def test_swfull_device_matches_host(ctx, ref):
+    """GPU Smith-Waterman (ps_sw.cu) vs the reference's swfull: score, accuracy and every aligned index
+    pair identical, including tie-heavy low-complexity sequences and sizes that are not multiples of
+    the thread strip."""
+    rng = np.random.default_rng(17)
+    cases = []
+    for n in (1, 5, 37, 400, 1025, 3000):
+        a = "".join(rng.choice(list("ACGT"), n))
+        b, _ = synth.corrupt_sequence(a, 0.12, rng) if n > 4 else (a, None)
+        cases.append((a, b))
+    cases.append(("A" * 300, "A" * 280))                                   # every path ties
+    cases.append(("ACACACACAC" * 40, "CACACACA" * 45))                     # periodic: many equal maxima
+    cases.append(("".join(rng.choice(list("AC"), 700)), "".join(rng.choice(list("AC"), 650))))   # unrelated, two letters
+    cases.append(("ACGT" * 50, "TTTT"))
+    for a, b in cases:
+        want_acc, want_score, want_pairs = ref.swfull(a, b)
+        score, acc, pairs = poreseqcpp.swalign_device(ctx, a, b)
+        assert [tuple(p) for p in pairs] == [tuple(p) for p in want_pairs], (len(a), len(b))
+        assert score == want_score
+        assert (acc == want_acc) or (np.isnan(acc) and np.isnan(want_acc))
