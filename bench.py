@@ -142,6 +142,58 @@ def run_cpu_baseline(n_regions=4):
                       "(%.0f M cells, %.1f s)" % (n_regions, cells / 1e6, dt)}
 
 
+def libc_srand(seed):
+    import ctypes
+    ctypes.CDLL("libc.so.6").srand(seed)
+
+
+def consensus_gpu(length, coverage, seed):
+    """Secondary headline (BASELINE.json: consensus kb/s): the whole Mutate.py policy -- Mutate('self'), then
+    rounds of Mutate('viterbi') + Refine until nothing changes -- on one synthetic region through the PSAlign
+    mirror.  A throw-away region runs first so that CUDA initialisation is not inside the timed loop."""
+    from poreseq_b200 import drivers, poreseqcpp
+    poreseqcpp.default_context().set_precision("fast")
+    drivers.consensus(drivers.make_psalign(synth.make_region(300, 5, seed=99, draft_error=0.05)), reps=1)
+    reg = synth.make_region(length, coverage, seed=seed, draft_error=0.10)
+    pa = drivers.make_psalign(reg)
+    libc_srand(1)                       # ViterbiMutate draws from the process-global rand() stream on both sides
+    t0 = time.perf_counter()
+    seq, acc = drivers.consensus(pa, refseq=reg.truth, reps=4)
+    dt = time.perf_counter() - t0
+    return {"value": length / 1000.0 / dt, "unit": "kb/s", "seconds": dt, "accuracy_pct": acc,
+            "draft_accuracy_pct": poreseqcpp.swalign(reg.sequence, reg.truth)[0],
+            "config": "consensus loop on a %d b region at %dx coverage (draft with 10%% errors), fast precision" % (length, coverage)}, seq
+
+
+def consensus_cpu(length, coverage, seed):
+    """The same policy driven through the reference's own C++ (oracle/_ref) on one host core."""
+    import copy
+    from oracle import binding
+    ref = binding.load("ref")
+    rr = copy.deepcopy(synth.make_region(length, coverage, seed=seed, draft_error=0.10))
+
+    def sync(al):
+        for ev, (ra, rl) in zip(rr.events, al):
+            ev.ref_align, ev.ref_like = ra, rl
+
+    libc_srand(1)
+    t0 = time.perf_counter()
+    seq, _, al = ref.mutate(rr, [ev.sequence for ev in rr.events[::2]], reps=4)
+    rr.sequence = seq; sync(al)
+    for _ in range(4):
+        seeds = ref.viterbi_mutate(rr, nkeep=16, seed=None)
+        seq, _, al = ref.mutate(rr, seeds, reps=4)
+        rr.sequence = seq; sync(al)
+        seq, nb, al = ref.refine(rr)
+        rr.sequence = seq; sync(al)
+        if nb == 0:
+            break
+    dt = time.perf_counter() - t0
+    t = int(rr.params.get("end_trim", 0))
+    out = rr.sequence[t:-t] if t and len(rr.sequence) > 2 * t else rr.sequence
+    return {"value": length / 1000.0 / dt, "unit": "kb/s", "seconds": dt, "cores": 1, "kind": "reference"}, out
+
+
 def recorded_traffic(kernel, regions):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full
     capture (profiles/r1_traffic.json), valid only for the batch size it was captured at."""
@@ -195,6 +247,7 @@ def main():
     ap.add_argument("--regions", type=int, default=22, help="1 kb regions per GPU per step (22 x 40 fill CTAs ~ 2 full waves of 148 SMs x 3)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-consensus", action="store_true", help="skip the secondary consensus kb/s measurement")
     ap.add_argument("--precision", default="fast", choices=["fast", "exact"],
                     help="fast: FP32 mutation scan + exact FP64 re-score of every candidate (decisions and accepted scores "
                          "bit-identical, other scores within 1e-4 relative); exact: everything FP64 bit-identical")
@@ -348,6 +401,20 @@ def main():
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = run_cpu_baseline()
+        if world == 1 and not args.no_consensus:
+            # consensus kb/s beside the GCUPS headline: configs[2] size on the GPU, the README's own 1 kb x 10x case
+            # on both sides (the reference needs ~25 s for it; 10 kb x 30x would take it the better part of an hour)
+            for c in ctxs:
+                c.close()
+            big, _ = consensus_gpu(10000, 30, seed=7)
+            small, seq_gpu = consensus_gpu(1000, 10, seed=7)
+            line["consensus"] = {"configs[2] 10 kb x 30x": big, "1 kb x 10x": small}
+            if not args.no_cpu_baseline:
+                from oracle import binding
+                if binding.available("ref"):
+                    cpu, seq_cpu = consensus_cpu(1000, 10, seed=7)
+                    cpu["identical_consensus"] = bool(seq_cpu == seq_gpu)
+                    line["consensus"]["1 kb x 10x"]["cpu_baseline"] = cpu
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
