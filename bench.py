@@ -298,7 +298,7 @@ def main():
     packs = [poreseqcpp.PackedRegion(r.sequence, r.events, r.params) for r in regions]
 
     def begin(c):
-        nrs = [poreseqcpp.NativeRegion.from_packed(c, p, "point_width") for p in packs]
+        nrs = poreseqcpp.native_regions_from_packed(c, packs, "point_width")
         return poreseqcpp.score_points_batch_begin(c, nrs)
 
     def end(p, record):
@@ -319,15 +319,28 @@ def main():
             pending = p
         return end(pending, record)
 
+    def run_steps_serial(count, record):
+        out = None
+        for k in range(count):
+            out = end(begin(ctxs[0]), record)
+        return out
+
     out = run_steps(max(args.warmup, 3), False)
     d2h = sum(8 * len(o[3]) for o in out) + sum(2 * 8 * len(ev.mean) for r in regions for ev in r.events)
 
     sampler = ClockSampler(local_rank)
     sampler.start()
+    # timed region 1 (`value`): K steps one after the other on one context; the kernel phases are timed with
+    # CUDA events on the library's stream, nothing else runs on the GPU, the inputs of a phase are in HBM
+    barrier()
+    run_steps_serial(args.steps, True)
+    barrier()
+    # timed region 2 (`e2e`): K steps through the C-ABI from host buffers, two contexts in flight so that the
+    # host staging and H2D of step k+1 overlap the kernels of step k; wall clock around barrier + synchronize
     launches0 = sum(c.launch_count() for c in ctxs)
     barrier()
     t0 = time.perf_counter()
-    run_steps(args.steps, True)
+    run_steps(args.steps, False)
     barrier()
     wall = time.perf_counter() - t0
     launches = sum(c.launch_count() for c in ctxs) - launches0

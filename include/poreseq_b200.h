@@ -106,6 +106,20 @@ int         ps_region_add_events(ps_region* r, int n_events, const int* n0,
                                  const double* ref_align, const double* ref_like,
                                  const int* model_index, int n_models, const double* models,
                                  const double* probs, const int* complement, const char* const* seq2d);
+/* Many regions in one call: out[k] = ps_region_create(bases, len, params) + ps_region_add_events(...) for every
+ * descriptor, built on the library's host worker threads.  On failure nothing is returned (out[] all NULL). */
+typedef struct ps_region_desc
+{
+    const char*   bases;       int len;
+    ps_params     params;
+    int           n_events;    const int* n0;
+    const double* mean;        const double* stdv;
+    const double* ref_align;   const double* ref_like;
+    const int*    model_index; int n_models;
+    const double* models;      const double* probs;
+    const int*    complement;  const char* const* seq2d;
+} ps_region_desc;
+int         ps_regions_create(ps_ctx* ctx, int n_regions, const ps_region_desc* desc, ps_region** out);
 int         ps_region_set_params(ps_region* r, const ps_params* params);
 int         ps_region_num_events(ps_region* r);
 int         ps_region_sequence_length(ps_region* r);

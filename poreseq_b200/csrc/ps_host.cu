@@ -1342,6 +1342,30 @@ int ps_region_add_events(ps_region* R, int n_events, const int* n0, const double
     return PS_OK;
 }
 
+int ps_regions_create(ps_ctx* ctx, int n_regions, const ps_region_desc* desc, ps_region** out)
+{
+    if (!ctx || n_regions < 0 || (n_regions > 0 && (!desc || !out))) return PS_E_ARG;
+    std::vector<int> rc(n_regions, PS_OK);
+    for (int k = 0; k < n_regions; k++) out[k] = nullptr;
+    ps_parallel_for(n_regions, [&](int k) {
+        const ps_region_desc& d = desc[k];
+        ps_region* R = ps_region_create(ctx, d.bases, d.len, &d.params);
+        if (!R) { rc[k] = PS_E_ARG; return; }
+        rc[k] = ps_region_add_events(R, d.n_events, d.n0, d.mean, d.stdv, d.ref_align, d.ref_like, d.model_index,
+                                     d.n_models, d.models, d.probs, d.complement, d.seq2d);
+        if (rc[k]) { delete R; return; }
+        out[k] = R;
+    });
+    for (int k = 0; k < n_regions; k++)
+        if (rc[k])
+        {
+            for (int q = 0; q < n_regions; q++) { delete out[q]; out[q] = nullptr; }
+            ps_set_error(ctx, "ps_regions_create: region %d was refused", k);
+            return rc[k];
+        }
+    return PS_OK;
+}
+
 int ps_region_set_params(ps_region* R, const ps_params* p)
 {
     if (!R || !p) return PS_E_ARG;

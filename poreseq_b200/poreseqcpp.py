@@ -29,6 +29,13 @@ class PSParams(C.Structure):
     _fields_ = [("lik_offset", C.c_double), ("scoring_width", C.c_int), ("realign_width", C.c_int), ("verbose", C.c_int)]
 
 
+class PSRegionDesc(C.Structure):
+    _fields_ = [("bases", C.c_char_p), ("len", C.c_int), ("params", PSParams), ("n_events", C.c_int), ("n0", C.c_void_p),
+                ("mean", C.c_void_p), ("stdv", C.c_void_p), ("ref_align", C.c_void_p), ("ref_like", C.c_void_p),
+                ("model_index", C.c_void_p), ("n_models", C.c_int), ("models", C.c_void_p), ("probs", C.c_void_p),
+                ("complement", C.c_void_p), ("seq2d", C.c_void_p)]
+
+
 _lib = None
 
 
@@ -58,6 +65,7 @@ def lib():
     L.ps_region_add_event.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 8 + [C.c_int] + [C.c_double] * 4 + [C.c_char_p]
     L.ps_region_add_events.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                                                                    C.c_void_p, C.c_void_p]
+    L.ps_regions_create.argtypes = [C.c_void_p, C.c_int, C.POINTER(PSRegionDesc), C.POINTER(C.c_void_p)]
     L.ps_region_set_params.argtypes = [C.c_void_p, C.POINTER(PSParams)]
     L.ps_region_num_events.argtypes = [C.c_void_p]
     L.ps_region_sequence_length.argtypes = [C.c_void_p]
@@ -377,6 +385,28 @@ class NativeRegion(object):
         tot = C.c_int(0)
         self.ctx.check(self.ctx.lib.ps_mutate(self.handle, len(seeds), _cstrs(seeds), int(reps), C.byref(tot)))
         return tot.value
+
+
+def native_regions_from_packed(ctx, packs, width_key=None):
+    """ps_regions_create: fresh native regions for a batch of PackedRegion host buffers in ONE C-ABI call
+    (the library copies them in on its worker threads)."""
+    n = len(packs)
+    desc = (PSRegionDesc * n)()
+    for k, p in enumerate(packs):
+        d = desc[k]
+        d.bases, d.len, d.params = p.sequence, len(p.sequence), _ps_params(p.params, width_key)
+        d.n_events, d.n0 = len(p.n0), p.n0.ctypes.data
+        d.mean, d.stdv, d.ref_align, d.ref_like = p.mean.ctypes.data, p.stdv.ctypes.data, p.ref_align.ctypes.data, p.ref_like.ctypes.data
+        d.model_index, d.n_models, d.models, d.probs = p.model_index.ctypes.data, len(p.models), p.models.ctypes.data, p.probs.ctypes.data
+        d.complement, d.seq2d = p.complement.ctypes.data, C.cast(p._seq2d_c, C.c_void_p)
+    out = (C.c_void_p * n)()
+    ctx.check(ctx.lib.ps_regions_create(ctx.handle, n, desc, out))
+    regs = []
+    for k, p in enumerate(packs):
+        r = NativeRegion.__new__(NativeRegion)
+        r.ctx, r.handle, r.n_levels = ctx, out[k], p.n0.tolist()
+        regs.append(r)
+    return regs
 
 
 def score_points_batch(ctx, regions):
