@@ -169,6 +169,7 @@ int ps_ctx::init()
     for (int i = 0; i <= PS_T_COUNT; i++) CU(cudaEventCreate(&tev[i]));
     CU(cudaFuncSetAttribute(k_backtrace, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
     CU(cudaFuncSetAttribute(k_fill<160, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CU(cudaFuncSetAttribute(k_fill<192, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CU(cudaFuncSetAttribute(k_fill<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024));
     CU(cudaFuncSetAttribute(k_mutscore<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU(cudaFuncSetAttribute(k_mutscore<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -370,7 +371,7 @@ struct Job
     std::vector<int> wave_need;
     // wide-fill launch classes: events whose wavefront fits 160 threads (3 CTAs per SM), wider ones, serial ones
     PinVec<int> fill_list;
-    int fill_count[3] = {0, 0, 0}, fill_threads[3] = {160, 160, 32};
+    int fill_count[4] = {0, 0, 0, 0}, fill_threads[4] = {160, 192, 224, 32};
     double bias = -1e-6;                         // start value of every mutation's sum over events
     double wide_cells_fwd = 0, narrow_cells = 0;
     long long n_levels, n_cols, n_cen, n_tasks, n_muts, n_band, n_strips = 0;
@@ -619,7 +620,7 @@ int Job::build()
     // wavefront-major band storage: slots per step = wavefront width of the event's launch class (at
     // most that many strips are live on one step), one slot per strip for the serially filled events
     std::vector<int> cls(ne, -1);
-    int wide_t = 192;
+    int wide_t = 224;
     for (int e = 0; e < ne; e++)
     {
         const EvDesc& d = ev[e];
@@ -627,14 +628,14 @@ int Job::build()
         if (!d.usable) continue;
         if (mono[e] && wave_need[e] > 512) mono[e] = 0;
         if (mono[e]) wide_cells_fwd += ev_cells[e];
-        cls[e] = !mono[e] ? 2 : wave_need[e] <= 160 ? 0 : 1;
-        if (cls[e] == 1) wide_t = std::max(wide_t, ((wave_need[e] + 31) / 32) * 32);
+        cls[e] = !mono[e] ? 3 : wave_need[e] <= 160 ? 0 : wave_need[e] <= 192 ? 1 : 2;
+        if (cls[e] == 2) wide_t = std::max(wide_t, ((wave_need[e] + 31) / 32) * 32);
         fill_count[cls[e]]++;
     }
-    fill_threads[1] = wide_t;
+    fill_threads[2] = wide_t;
     if (!fill_list.resize((size_t)std::max(ne, 1))) { ps_set_error(ctx, "out of host memory staging the batch"); return PS_E_INTERNAL; }
     {
-        int at[3] = {0, fill_count[0], fill_count[0] + fill_count[1]};
+        int at[4] = {0, fill_count[0], fill_count[0] + fill_count[1], fill_count[0] + fill_count[1] + fill_count[2]};
         for (int e = 0; e < ne; e++) if (cls[e] >= 0) fill_list[at[cls[e]]++] = e;
     }
     for (int e = 0; e < ne; e++)
@@ -642,7 +643,7 @@ int Job::build()
         EvDesc& d = ev[e];
         if (!d.usable) { d.ts = 1; d.rs = 4; d.band_off = n_band; continue; }
         const int J = (d.N + CW - 1) / CW;
-        d.ts = cls[e] == 2 ? J + 1 : fill_threads[cls[e]];
+        d.ts = cls[e] == 3 ? J + 1 : fill_threads[cls[e]];
         d.rs = d.ts * 4;                          // one 2x2 tile per slot
         d.band_off = n_band;                      // multiple of 4: keeps the 32-byte tiles aligned
         n_band += (long long)(J + (d.n0 + 1) / 2 + 2) * d.rs;
@@ -801,8 +802,8 @@ int Job::run(bool full)
     // one launch per width class
     {
         if (getenv("PORESEQ_B200_TRACE"))
-            fprintf(stderr, "[ps] fill: %d events: %d at 160 threads, %d at %d, %d serial; band cells %lld\n", nev,
-                    fill_count[0], fill_count[1], fill_threads[1], fill_count[2], n_band);
+            fprintf(stderr, "[ps] fill: %d events: %d at 160 threads, %d at 192, %d at %d, %d serial; band cells %lld\n", nev,
+                    fill_count[0], fill_count[1], fill_count[2], fill_threads[2], fill_count[3], n_band);
         const int dirs = full ? 2 : 1;
         {
             int maxn0 = 0;
@@ -813,7 +814,8 @@ int Job::run(bool full)
             LAUNCHED();
         }
         // the majority class on the main stream, the others beside it on the side stream
-        const bool forked = fill_count[0] > 0 && fill_count[1] + fill_count[2] > 0;
+        const int off1 = fill_count[0], off2 = off1 + fill_count[1], off3 = off2 + fill_count[2];
+        const bool forked = fill_count[0] > 0 && fill_count[1] + fill_count[2] + fill_count[3] > 0;
         cudaStream_t other = forked ? ctx->side : ctx->stream;
         if (forked)
         {
@@ -821,13 +823,15 @@ int Job::run(bool full)
             CU(cudaStreamWaitEvent(ctx->side, ctx->fork_ev, 0));
         }
         const size_t smem160 = std::max<size_t>(40 * 160, 2 * b.RS) * sizeof(double);   // rings + next strip record
-        if (fill_count[1])
+        const size_t smem192 = std::max<size_t>(40 * 192, 2 * b.RS) * sizeof(double);
+        if (fill_count[2])
         {
             const size_t smem = std::max<size_t>(40 * 512, 2 * b.RS) * sizeof(double);
-            k_fill<512, 1><<<dim3(fill_count[1], dirs), fill_threads[1], smem, other>>>(b, fill_count[0]);
+            k_fill<512, 1><<<dim3(fill_count[2], dirs), fill_threads[2], smem, other>>>(b, off2);
             LAUNCHED();
         }
-        if (fill_count[2]) { k_fill<160, 3><<<dim3(fill_count[2], dirs), 32, smem160, other>>>(b, fill_count[0] + fill_count[1]); LAUNCHED(); }
+        if (fill_count[1]) { k_fill<192, 2><<<dim3(fill_count[1], dirs), 192, smem192, other>>>(b, off1); LAUNCHED(); }
+        if (fill_count[3]) { k_fill<160, 3><<<dim3(fill_count[3], dirs), 32, smem160, other>>>(b, off3); LAUNCHED(); }
         if (fill_count[0]) { k_fill<160, 3><<<dim3(fill_count[0], dirs), 160, smem160, ctx->stream>>>(b, 0); LAUNCHED(); }
         if (forked)
         {
