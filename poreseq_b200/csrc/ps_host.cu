@@ -132,7 +132,11 @@ void ps_parallel_for(int n, const std::function<void(int)>& fn)
             g_pool = new Pool(threads - 1);
         }
     }
-    if (g_pool->workers.empty()) { for (int i = 0; i < n; i++) fn(i); return; }
+    // one parallel loop at a time: a caller that finds the workers busy (several host threads driving
+    // their own contexts, or a nested loop) runs its loop inline
+    static std::mutex busy;
+    std::unique_lock<std::mutex> turn(busy, std::try_to_lock);
+    if (g_pool->workers.empty() || !turn.owns_lock()) { for (int i = 0; i < n; i++) fn(i); return; }
     g_pool->run(n, fn);
 }
 

@@ -524,10 +524,17 @@ class PSAlign(object):
         self.sequence = ""
         self.events = []
         self.params = {}
+        self.ctx = None          # optional Context of its own (one per host thread); default: the process-wide one
 
     # -- plumbing --------------------------------------------------------------------------
     def _native(self, width_key=None):
-        return NativeRegion(default_context(), self.sequence, self.events, self.params, width_key)
+        return NativeRegion(self.ctx or default_context(), self.sequence, self.events, self.params, width_key)
+
+    def __deepcopy__(self, memo):
+        other = PSAlign()
+        other.sequence, other.params, other.ctx = self.sequence, dict(self.params), self.ctx
+        other.events = copy.deepcopy(self.events, memo)
+        return other
 
     def Copy(self):
         return copy.deepcopy(self)
