@@ -276,7 +276,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--regions", type=int, default=22, help="1 kb regions per GPU per step (22 x 40 fill CTAs ~ 2 full waves of 148 SMs x 3)")
+    ap.add_argument("--regions", type=int, default=44, help="1 kb regions per GPU per step (44 x 40 fill CTAs ~ 4 waves of 148 SMs x 3)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-consensus", action="store_true", help="skip the secondary consensus kb/s measurement")

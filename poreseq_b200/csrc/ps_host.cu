@@ -165,7 +165,6 @@ int ps_ctx::init()
     }
     sm_count = prop.multiProcessorCount;
     total_mem = prop.totalGlobalMem;
-    if (const char* fw = getenv("PORESEQ_B200_FILL_WARPS")) fill_warps = std::min(16, std::max(1, atoi(fw)));
     CU(cudaStreamCreate(&stream));
     CU(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));

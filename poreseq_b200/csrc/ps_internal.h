@@ -41,7 +41,6 @@ struct ps_ctx
     int sm_count = 0;
     size_t total_mem = 0;
     int precision = 0;                        // PS_PRECISION_EXACT / PS_PRECISION_FAST
-    int fill_warps = 8;                       // warps per (event, direction) in the wide fill (PORESEQ_B200_FILL_WARPS)
     cudaStream_t stream = nullptr;
     cudaStream_t side = nullptr;              // runs the minority launch classes of the wide fill beside the main one
     cudaEvent_t fork_ev = nullptr, join_ev = nullptr;

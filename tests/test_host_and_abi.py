@@ -113,3 +113,26 @@ def test_packed_marshalling_equals_per_event():
     with pytest.raises(RuntimeError):
         poreseqcpp.NativeRegion.from_packed(ctx, bad, "point_width")
     assert pack.nbytes() > 0
+
+
+def test_bulk_region_creation_equals_per_region():
+    """ps_regions_create (one call, worker threads) == ps_region_create + ps_region_add_events per region."""
+    import numpy as np
+    from poreseq_b200 import poreseqcpp, synth
+    regs = [synth.make_region(200 + 37 * k, 2 + k % 3, seed=40 + k, draft_error=0.04, partial=0.3) for k in range(9)]
+    ctx = poreseqcpp.Context(0)
+    packs = [poreseqcpp.PackedRegion(r.sequence, r.events, r.params) for r in regs]
+    many = poreseqcpp.native_regions_from_packed(ctx, packs, "point_width")
+    assert len(many) == len(regs)
+    for r, p, m in zip(regs, packs, many):
+        one = poreseqcpp.NativeRegion.from_packed(ctx, p, "point_width")
+        assert m.sequence() == one.sequence() == r.sequence
+        assert m.n_levels == one.n_levels
+        for e in range(len(r.events)):
+            a, b = m.event_align(e), one.event_align(e)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    # one bad descriptor refuses the whole batch
+    bad = poreseqcpp.PackedRegion(regs[0].sequence, regs[0].events, regs[0].params)
+    bad.model_index = bad.model_index + 3
+    with pytest.raises(RuntimeError):
+        poreseqcpp.native_regions_from_packed(ctx, packs[:2] + [bad], "point_width")

@@ -39,7 +39,7 @@ def test_event_shard_allreduce_world2():
     from oracle import binding
     binding.build("oracle")
     world, port = 2, 29517 + os.getpid() % 500
-    with mp.Manager() as mgr:
+    with mp.get_context("spawn").Manager() as mgr:      # (the test process may already own worker threads: no fork)
         out = mgr.dict()
         mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
         res = dict(out)
