@@ -301,9 +301,18 @@ __device__ __forceinline__ double seed_raw(const RowSweep& q, int i)
 // general form with all edge cases.
 // Loads are issued at the top of a row and consumed at its bottom (the next row's emissions, the
 // join), so no loaded value is carried around the loop.
-template <bool FAST>
+// MASKED (edge rows, all states valid): the same predicate-free arithmetic for every cell, made right by
+// sentinels instead of branches -- a cell outside its band leaves NEGF in the column registers, which
+// (a) makes stay / extend / insert lose on the column's first row and puts the stay matrix's floor at
+// NEGF there (min(upC, fl)), and (b) reads as the floor fl through max(., fl) when the next column
+// looks left or diagonally; a column's last row is replaced by NEGF after use so that the diagonal
+// move out of it is implicit (cpp/Alignment.cpp:213-225 tests i <= p1, not i-1 <= p1).
+enum { ROWS_GENERAL = 0, ROWS_FAST = 1, ROWS_MASKED = 2 };
+
+template <int MODE>
 __device__ __forceinline__ void sweep_rows(RowSweep& q, int ia, int ib, int rhi)
 {
+    constexpr bool FAST = MODE == ROWS_FAST;
     for (int i = ia; i <= ib; i++)
     {
         // requests: level record and seed value of row i+1, reverse cells of row i
@@ -346,6 +355,34 @@ __device__ __forceinline__ void sweep_rows(RowSweep& q, int ia, int ib, int rhi)
                 q.joinmax = fmaxf(q.joinmax, fmaxf(Cl + (float)(bmr - q.dRa), Sl + (float)(bsr - q.dRa)));
             }
         }
+        else if (MODE == ROWS_MASKED)
+        {
+            const float bmf = jin ? (float)(bmr - q.dRa) : NEGF, bsf = jin ? (float)(bsr - q.dRa) : NEGF;
+            float jv4 = NEGF, jv5 = NEGF;
+#pragma unroll
+            for (int c = 0; c < NC; c++)
+            {
+                const float upC = q.C[c], upS = q.S[c], em = q.em[c];
+                const float skip = left + q.tr.x;
+                const float match = diag + em;
+                const float ignore = diag + q.tr.w;
+                const float stay = upC + em + q.tr.y;
+                const float ins = upC + q.tr.w;
+                const float ext = upS + em + q.tr.z;
+                const float Sn = fmaxf(fminf(upC, q.fl), fmaxf(stay, ext));
+                const float Cn = fmaxf(fmaxf(fmaxf(q.fl, skip), fmaxf(match, ins)), fmaxf(ignore, Sn));
+                const bool act = i >= q.col[c].i0 && i <= q.col[c].i1;
+                const float Cm = act ? Cn : NEGF, Sm = act ? Sn : NEGF;
+                q.best = fmaxf(q.best, Cm);
+                if (c == 4) jv4 = fmaxf(Cm + bmf, Sm + bsf);
+                if (c == 5) jv5 = fmaxf(Cm + bmf, Sm + bsf);
+                left = fmaxf(Cm, q.fl);
+                diag = fmaxf(upC, q.fl);                     // (i-1, c) as the next column's diagonal
+                q.C[c] = i == q.col[c].i1 ? NEGF : Cm;
+                q.S[c] = Sm;
+            }
+            if (q.joined) q.joinmax = fmaxf(q.joinmax, q.ncol == 6 ? jv5 : jv4);
+        }
         else
         {
             int q0 = q.p0, q1 = q.p1;                        // band of column c-1
@@ -379,7 +416,8 @@ __device__ __forceinline__ void sweep_rows(RowSweep& q, int ia, int ib, int rhi)
         // bottom of the row: what row i+1 needs
 #pragma unroll
         for (int c = 0; c < NC; c++) q.em[c] = emission_f(lrn, eyn, q.col[c].sp);
-        q.sd_prev = q.sd;
+        q.sd_prev = (MODE == ROWS_MASKED && i == q.p1) ? q.fl : q.sd;   // the diagonal out of the seed column's last row is implicit
+                                                                          // (fast rows end before any column's last row)
         q.sd = (float)(sdn - q.a);
     }
 }
@@ -422,6 +460,15 @@ __global__ void __launch_bounds__(128) k_mutscore_rows_f32(Batch b)
                 q.rs = ev.rs; q.n0 = n0;
                 q.tr = b.trf[ev.model];
                 bool all_valid = true;
+                // 5-mer states of the narrow columns: one rolling window over the mutated bases when the region
+                // and the replacement base are plain ACGT (cpp/Sequence.h:79-98 without its reset cases)
+                const bool plain = !ev.inv && (mu.n_mut == 0 || base_code(mv.mstr[0]) < 4);
+                int win = 0;
+                if (plain)
+                {
+#pragma unroll
+                    for (int t = 0; t < 4; t++) win = (win << 2) | mut_base(mv, startind + t);
+                }
 #pragma unroll
                 for (int c = 0; c < NC; c++)
                 {
@@ -430,7 +477,9 @@ __global__ void __launch_bounds__(128) k_mutscore_rows_f32(Batch b)
                     if (c < q.ncol)
                     {
                         band_of(ri_empty ? 1 : b.cen_new[ev.cen_off + startind + 1 + c], n0, W, q.col[c].i0, q.col[c].i1);
-                        const int s = mut_state(mv, startind + c);
+                        int s;
+                        if (plain) { win = ((win << 2) | mut_base(mv, startind + c + 4)) & (N_STATES - 1); s = win; }
+                        else s = mut_state(mv, startind + c);
                         q.col[c].valid = s >= 0;
                         all_valid = all_valid && s >= 0;
                         q.col[c].sp = stf[max(s, 0)];
@@ -469,17 +518,17 @@ __global__ void __launch_bounds__(128) k_mutscore_rows_f32(Batch b)
                 // rows swept: from the first row of the first column to the last row of the last one; the
                 // predicate-free rows are those every column treats as interior (see sweep_rows)
                 int rlo = q.col[0].i0, rhi = q.col[0].i1;
-                int flo = max(q.col[0].i0, q.p0) + 1, fhi = min(q.col[0].i1, q.p1);
+                int flo = max(q.col[0].i0, q.p0) + 1, fhi = min(q.col[0].i1, q.p1) - 1;   // (last rows: sentinel handling)
 #pragma unroll
                 for (int c = 1; c < NC; c++)
                     if (c < q.ncol)
                     {
                         rlo = min(rlo, q.col[c].i0); rhi = max(rhi, q.col[c].i1);
                         flo = max(flo, max(q.col[c].i0, q.col[c - 1].i0) + 1);
-                        fhi = min(fhi, min(q.col[c].i1, q.col[c - 1].i1));
+                        fhi = min(fhi, min(q.col[c].i1, q.col[c - 1].i1) - 1);
                     }
                 if (q.joined) { flo = max(flo, n0 + 1 - q.b1); fhi = min(fhi, n0 + 1 - q.b0); }
-                if (!all_valid || q.ncol < 5 || flo > fhi) { flo = rhi + 1; fhi = rhi; }
+                if (flo > fhi) { flo = rhi + 1; fhi = rhi; }
 #pragma unroll
                 for (int c = 0; c < NC; c++) { q.C[c] = q.fl; q.S[c] = q.fl; }
                 q.sd_prev = (float)(seed_raw(q, rlo - 1) - q.a);
@@ -490,9 +539,17 @@ __global__ void __launch_bounds__(128) k_mutscore_rows_f32(Batch b)
 #pragma unroll
                     for (int c = 0; c < NC; c++) q.em[c] = emission_f(lr, ey, q.col[c].sp);
                 }
-                sweep_rows<false>(q, rlo, flo - 1, rhi);
-                sweep_rows<true>(q, flo, fhi, rhi);
-                sweep_rows<false>(q, fhi + 1, rhi, rhi);
+                if (all_valid && q.ncol >= 5)
+                {
+                    // edge rows with sentinels, interior rows with nothing: the column registers start as "outside"
+#pragma unroll
+                    for (int c = 0; c < NC; c++) { q.C[c] = NEGF; q.S[c] = NEGF; }
+                    sweep_rows<ROWS_MASKED>(q, rlo, flo - 1, rhi);
+                    sweep_rows<ROWS_FAST>(q, flo, fhi, rhi);
+                    sweep_rows<ROWS_MASKED>(q, fhi + 1, rhi, rhi);
+                }
+                else
+                    sweep_rows<ROWS_GENERAL>(q, rlo, rhi, rhi);
                 float joinmax = q.joinmax;
                 // a blank reverse column (all zeros) adds nothing beyond the running best of the forward cells
                 if (rab == 0) joinmax = q.best - (float)q.dRa;

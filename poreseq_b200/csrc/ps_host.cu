@@ -554,8 +554,8 @@ int Job::build()
             }
         }
         const int nm = (int)(mdev.size() - mut_off);
-        int region_inv = 0;
-        for (int st : R->states) if (st < 0) { region_inv = 1; break; }
+        int region_inv = 0;               // any base that is not ACGT (an invalid state, or a polluted one near the end)
+        for (char ch : R->bases) if (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T') { region_inv = 1; break; }
         RegTab rt; rt.mut_off = mut_off; rt.ev0 = ev0; rt.nev = (int)R->events.size();
         max_ev = std::max(max_ev, rt.nev);
         regtab.push_back(rt);
