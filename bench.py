@@ -280,6 +280,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-consensus", action="store_true", help="skip the secondary consensus kb/s measurement")
+    ap.add_argument("--contexts", type=int, default=4, help="library contexts (streams + staging areas) per GPU in the e2e pipeline")
     ap.add_argument("--precision", default="fast", choices=["fast", "exact"],
                     help="fast: FP32 mutation scan + exact FP64 re-score of every candidate (decisions and accepted scores "
                          "bit-identical, other scores within 1e-4 relative); exact: everything FP64 bit-identical")
@@ -313,7 +314,7 @@ def main():
 
     # two contexts (two streams, two sets of staging / device buffers) on this rank's GPU: while the GPU
     # works on step k the host marshals and stages step k+1 (ps_score_points_batch_begin / _end)
-    ctxs = [poreseqcpp.Context(local_rank), poreseqcpp.Context(local_rank)]
+    ctxs = [poreseqcpp.Context(local_rank) for _ in range(max(2, args.contexts))]
     for c in ctxs:
         c.set_precision(args.precision)
     ctx = ctxs[0]
@@ -343,13 +344,15 @@ def main():
         return out
 
     def run_steps(count, record):
-        pending, out = None, None
+        out = None
+        inflight = []
         for k in range(count):
-            p = begin(ctxs[k % 2])
-            if pending is not None:
-                out = end(pending, record)
-            pending = p
-        return end(pending, record)
+            inflight.append(begin(ctxs[k % len(ctxs)]))
+            if len(inflight) == len(ctxs):
+                out = end(inflight.pop(0), record)
+        while inflight:
+            out = end(inflight.pop(0), record)
+        return out
 
     def run_steps_serial(count, record):
         out = None
@@ -419,7 +422,7 @@ def main():
                    "regions_per_gpu_per_step": args.regions, "events_per_region": 2 * COVERAGE,
                    "mutations_per_region": 8 * (REGION_LEN - 4), "cells_per_step_per_gpu": step_cells,
                    "l2": "band working set %.0f MB per step exceeds the 126 MB L2" % (wide_cells * 16.5 / 1e6),
-                   "pipelining": "2 contexts: host staging of step k+1 overlaps kernels of step k",
+                   "pipelining": "%d contexts: host staging and H2D of the next steps overlap the kernels of step k" % len(ctxs),
                    "precision": ("fp32 mutation scan + exact fp64 re-score of all candidates > -tau; wide fills/backtrace fp64"
                                  if args.precision == "fast" else "fp64 exact (bit-identical to the reference)")},
         "e2e": {"value": total_cells / (wall_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -78,7 +78,7 @@ struct Batch                  // everything the kernels need, passed by value
     // band storage, wavefront-major: the cells of one anti-diagonal d = k+i of an event are
     // contiguous (slot k % ts), so the fill's per-step stores and the join's loads coalesce
     int               RS;            // 2*realign_width+1 rounded up (serial-fallback smem strips)
-    double*           Fm; double* Fs; double* Bm; double* Bs;
+    double*           Fm; double* Fs; double* Bm;    // no reverse stay matrix: main >= stay, joins read B's main only
     uint8_t*          Fstep;
     int*              Fi0; int* Flen; int* Bi0; int* Blen;
     double*           Fcb; int* Fcbi;          // per-column best (score, row) before the running max
@@ -472,17 +472,33 @@ __device__ __forceinline__ void fill_wave(const Batch& b, const EvDesc& ev, cons
     const int T = blockDim.x, tid = threadIdx.x;
     const int n0 = ev.n0, N = ev.N;
     const int J = (N + CW - 1) / CW;                      // strips
-    // [4][MAXT] rings of the last four steps: second-column main values (and, reverse pass, emissions)
-    // of both rows of the tile; then the [11][MAXT] 16-byte chunks of the thread's next strip record
+    // [RD][MAXT] rings of the last RD steps: second-column main values (and, reverse pass, emissions)
+    // of both rows of the tile; then the [11][MAXT] 16-byte chunks of the thread's next strip record.
+    //
+    // Step synchronisation.  A tile only looks at the left neighbour's previous two steps, so a warp only
+    // has to wait for the warp left of it (warp 0: the last warp, whose last thread owns the strip before
+    // thread 0's next one).  P2P (classes of at most 6 warps): warp w signals "step q written" on its own
+    // mbarrier [w][q & 7] (one arrival per phase) and warp w+1 waits for it before its step q+1 -- no
+    // CTA-wide barrier in the sweep; the warps run as a pipeline skewed by their own pace.  Around the ring
+    // of nw warps a warp can get nw-1 steps ahead of the warp that reads it, hence 8-deep data rings (the
+    // reader still needs up to nw+1 <= 7 older slots) and 8 barriers per warp (the second arrival on a slot
+    // comes 8 steps later, never before the reader has passed, so the parity wait is unambiguous).
+    // Wider classes keep the split-phase CTA barrier with 4-deep rings.
+    constexpr bool P2P = MAXT <= 192;
+    constexpr int RD = P2P ? 8 : 4;
     double2* myC = reinterpret_cast<double2*>(smem) + tid;
-    double2* myE = myC + 4 * MAXT;
+    double2* myE = myC + RD * MAXT;
     const int left = tid == 0 ? T - 1 : tid - 1;
     const double2* lfC = reinterpret_cast<const double2*>(smem) + left;
-    const double2* lfE = lfC + 4 * MAXT;
-    double2* nxt = reinterpret_cast<double2*>(smem) + 8 * MAXT + tid;    // chunk q at nxt[q * MAXT]
-    __shared__ unsigned long long step_bar;
-    const unsigned bar = (unsigned)__cvta_generic_to_shared(&step_bar);
-    if (tid == 0) mbar_init(bar, T >> 5);                 // one arrival per warp and step
+    const double2* lfE = lfC + RD * MAXT;
+    double2* nxt = reinterpret_cast<double2*>(smem) + 2 * RD * MAXT + tid;    // chunk q at nxt[q * MAXT]
+    __shared__ unsigned long long step_bar[P2P ? 64 : 1];
+    const int wrp = tid >> 5, nwarps = T >> 5;
+    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(&step_bar[0]);
+    const unsigned bar_mine = bar0 + (P2P ? wrp * 64 : 0);                              // + 8 * (q & 7)
+    const unsigned bar_left = bar0 + (P2P ? (wrp == 0 ? nwarps - 1 : wrp - 1) * 64 : 0);
+    if (P2P) { if (tid < 8 * nwarps) mbar_init(bar0 + 8 * tid, 1); }
+    else if (tid == 0) mbar_init(bar0, nwarps);           // one arrival per warp and step
     const LevelRec* rows = (REV ? b.rowB : b.rowF) + ev.lev_off;
     const StripRec* srec = b.strips + ev.strip_off + (REV ? J + 1 : 0);  // strips 0..J-1, sentinel J
     const ModelDev& md = b.models[ev.model];
@@ -500,7 +516,7 @@ __device__ __forceinline__ void fill_wave(const Batch& b, const EvDesc& ev, cons
     double upC0 = NEG, upS0 = NEG, upE0 = 0, upC1 = NEG, upS1 = NEG, upE1 = 0;
     double best0 = NEG, best1 = NEG;
     int besti0 = 0, besti1 = 0;
-    int ph = dstart & 3;
+    int ph = dstart & (RD - 1);
     unsigned parity = 0;
     RowRecs rr;
     double eA = 0, eB = 0, eC = 0, eD = 0;                // emissions of the tile of the coming step
@@ -516,9 +532,17 @@ __device__ __forceinline__ void fill_wave(const Batch& b, const EvDesc& ev, cons
     __syncthreads();                                      // the barrier object is initialised
     for (int d = dstart; d <= dend; d++)
     {
-        if (d > dstart) { mbar_wait(bar, parity); parity ^= 1u; }        // every warp has written step d-1
+        if (d > dstart)
+        {
+            if (P2P)
+            {
+                const int q1 = d - 1 - dstart;                           // the left warp has written step d-1
+                mbar_wait(bar_left + 8 * (q1 & 7), (unsigned)(q1 >> 3) & 1u);
+            }
+            else { mbar_wait(bar0, parity); parity ^= 1u; }              // every warp has written step d-1
+        }
         const int r = d - cur.j;
-        const int w0 = ph, w1 = (ph + 3) & 3, w2 = (ph + 2) & 3;        // steps d, d-1, d-2
+        const int w0 = ph, w1 = (ph + RD - 1) & (RD - 1), w2 = (ph + RD - 2) & (RD - 1);   // steps d, d-1, d-2
         if (r >= cur.rlo && r <= cur.rhi)
         {
             const int ia = 2 * r + 1, ib = ia + 1;
@@ -564,14 +588,15 @@ __device__ __forceinline__ void fill_wave(const Batch& b, const EvDesc& ev, cons
             double2* pm = reinterpret_cast<double2*>(o.Mm + a);
             double2* ps = reinterpret_cast<double2*>(o.Ms + a);
             pm[0] = make_double2(CA, CB); pm[1] = make_double2(CC, CD);
-            ps[0] = make_double2(SA, SB); ps[1] = make_double2(SC, SD);
+            // the reverse stay matrix is never read (main >= stay in every cell: the joins need B's main only)
+            if (!REV) { ps[0] = make_double2(SA, SB); ps[1] = make_double2(SC, SD); }
             if (!REV)
                 *reinterpret_cast<unsigned*>(b.Fstep + a) = (unsigned)(kA | (qA << 3)) | ((unsigned)(kB | (qB << 3)) << 8) |
                                                            ((unsigned)(kC | (qC << 3)) << 16) | ((unsigned)(kD | (qD << 3)) << 24);
         }
         __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(bar);            // this warp's part of step d is in shared memory
-        ph = (ph + 1) & 3;
+        if ((tid & 31) == 0) mbar_arrive(P2P ? bar_mine + 8 * ((d - dstart) & 7) : bar0);   // this warp's part of step d is in shared memory
+        ph = (ph + 1) & (RD - 1);
         // ---- preparation of step d+1: overlaps the other warps' step d ----
         if (d + 1 > cur.j + cur.rhi)
         {
@@ -651,7 +676,8 @@ __device__ void fill_serial(const Batch& b, const EvDesc& ev, const FillOut& o, 
                 if (C > best) { best = C; besti = i; }
             }
             const long long a = cell_at(ev, k, i);
-            o.Mm[a] = C; o.Ms[a] = S;
+            o.Mm[a] = C;
+            if (!REV) o.Ms[a] = S;
             if (!REV) b.Fstep[a] = (uint8_t)step;
             Ecur[i - i0] = e;
             upC = C; upS = S; upE = e;
@@ -674,7 +700,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_fill(Batch b, int list_off)
     if (!ev.usable || ev.N <= 0) return;
     const int N = ev.N;
     FillOut o;
-    o.Mm = rev ? b.Bm : b.Fm; o.Ms = rev ? b.Bs : b.Fs;
+    o.Mm = rev ? b.Bm : b.Fm; o.Ms = rev ? nullptr : b.Fs;
     o.Mi0 = rev ? b.Bi0 : b.Fi0; o.Mlen = rev ? b.Blen : b.Flen;
     o.Mcb = rev ? b.Bcb : b.Fcb; o.Mcbi = rev ? b.Bcbi : b.Fcbi;
     double* Mcb = o.Mcb; int* Mcbi = o.Mcbi;
@@ -948,7 +974,7 @@ __global__ void __launch_bounds__(256) k_join(Batch b)
             {
                 const long long af = fb + (long long)r * rs + 2 * h;
                 const long long ab = bb + row_off(rs, n0 - jf + 1);
-                m = fmax(m, fmax(b.Fm[af] + b.Bm[ab], b.Fs[af] + b.Bs[ab]));
+                m = fmax(m, b.Fm[af] + b.Bm[ab]);
             }
         }
     }
@@ -1039,9 +1065,8 @@ __device__ double thread_join(const Batch& b, const EvDesc& ev, int raf, int rab
     {
         int jb = n0 - jf + 1;
         const long long af = cell_at(ev, raf, jf), ab = cell_at(ev, rab, jb);
-        double fm = raf > 0 ? b.Fm[af] : 0.0, fs = raf > 0 ? b.Fs[af] : 0.0;
-        double bm = rab > 0 ? b.Bm[ab] : 0.0, bs = rab > 0 ? b.Bs[ab] : 0.0;
-        m = fmax(m, fmax(fm + bm, fs + bs));
+        const double fm = raf > 0 ? b.Fm[af] : 0.0, bm = rab > 0 ? b.Bm[ab] : 0.0;
+        m = fmax(m, fm + bm);
     }
     return m;
 }
@@ -1136,7 +1161,6 @@ __global__ void __launch_bounds__(128) k_mutscore(Batch b)
                 if (rab > 0) { b0 = b.Bi0[gb]; blen = b.Blen[gb]; mb = b.Bbest[gb]; }
                 const long long bbase = col_base(ev, rab);            // + reverse row * rs
                 const double* Bm = b.Bm + bbase;
-                const double* Bs = b.Bs + bbase;
                 const long long ts = ev.rs;
                 double joinmax = 0.0;
                 for (int c = startind + 1; c <= last; c++)
@@ -1165,15 +1189,15 @@ __global__ void __launch_bounds__(128) k_mutscore(Batch b)
                         LevelRec lr = *lv;
                         double lsd3 = lq->lsd3;
                         double sv = (sd && i0 >= p0 && i0 <= p1) ? sd[row_off(ts, i0)] : 0.0;
-                        double bmv = 0.0, bsv = 0.0;
+                        double bmv = 0.0;
                         {
                             const int jb = n0 - i0 + 1;
-                            if (joinB && jb >= b0 && jb < b0 + blen) { const long long ro = row_off(ts, jb); bmv = Bm[ro]; bsv = Bs[ro]; }
+                            if (joinB && jb >= b0 && jb < b0 + blen) bmv = Bm[row_off(ts, jb)];
                         }
                         for (int i = i0; i <= i1; i++)
                         {
                             const LevelRec lr_c = lr;
-                            const double lsd3_c = lsd3, sv_c = sv, bm_c = bmv, bs_c = bsv;
+                            const double lsd3_c = lsd3, sv_c = sv, bm_c = bmv;
                             if (i < i1)
                             {
                                 lv++; lq--;
@@ -1182,8 +1206,8 @@ __global__ void __launch_bounds__(128) k_mutscore(Batch b)
                                 if (joinB)
                                 {
                                     const int jn = n0 - i;
-                                    bmv = 0.0; bsv = 0.0;
-                                    if (jn >= b0 && jn < b0 + blen) { const long long ro = row_off(ts, jn); bmv = Bm[ro]; bsv = Bs[ro]; }
+                                    bmv = 0.0;
+                                    if (jn >= b0 && jn < b0 + blen) bmv = Bm[row_off(ts, jn)];
                                 }
                             }
                             const double e_i = emission(lr_c.mean, lr_c.stdv, lr_c.rstdv, lsd3_c, sp, b.log2pi, b.lik_offset);
@@ -1197,7 +1221,7 @@ __global__ void __launch_bounds__(128) k_mutscore(Batch b)
                             if (last_col)
                             {
                                 const int jb = n0 - i + 1;
-                                if (jb >= b0 && jb < b0 + blen) joinmax = fmax(joinmax, fmax(C + bm_c, Sv + bs_c));
+                                if (jb >= b0 && jb < b0 + blen) joinmax = fmax(joinmax, C + bm_c);
                             }
                             else ring[(long long)slot * rstride] = C;
                             diag = Pi;
@@ -1215,8 +1239,7 @@ __global__ void __launch_bounds__(128) k_mutscore(Batch b)
                                 const int jb = n0 - i + 1;
                                 if (jb >= b0 && jb < b0 + blen)
                                 {
-                                    const double bm = rab > 0 ? Bm[row_off(ts, jb)] : 0.0, bs = rab > 0 ? Bs[row_off(ts, jb)] : 0.0;
-                                    joinmax = fmax(joinmax, fmax(bm, bs));
+                                    joinmax = fmax(joinmax, rab > 0 ? Bm[row_off(ts, jb)] : 0.0);
                                 }
                             }
                             else ring[(long long)slot * rstride] = 0.0;

@@ -55,7 +55,8 @@ struct ColF
 {
     float* ringC;                // + (row & mask) * 128
     const LevelRecF* lev;        // event levels
-    const double* Bm; const double* Bs;   // reverse column (last narrow column only): + row_off(ts, jb)
+    const double* Bm;            // reverse column, main matrix (last narrow column only): + row_off(ts, jb); main >= stay
+                                 // in every cell, so the stay matrices never decide a join
     long long ts;
     double dRa;
     int n0, mask;
@@ -69,10 +70,10 @@ struct ColF
 template <bool EDGE, bool LAST>
 __device__ __forceinline__ void row_f(ColF& q, const StateParamsF& sp, int i, int i0, int i1,
                                       const LevelRecF*& lv, const LevelRecF*& lq, LevelRecF& lr, float& ey,
-                                      float& bm, float& bs, float& diag, float& upC, float& upS)
+                                      float& bm, float& diag, float& upC, float& upS)
 {
     const LevelRecF lr_c = lr;
-    const float ey_c = ey, bm_c = bm, bs_c = bs;
+    const float ey_c = ey, bm_c = bm;
     if (!EDGE || i < i1)
     {
         // next row: level i (mean/stdv) and level n0-i-1 (its -1.5 log stdv, quirk A.3-1), reverse row jb-1
@@ -82,10 +83,7 @@ __device__ __forceinline__ void row_f(ColF& q, const StateParamsF& sp, int i, in
         {
             const int jn = q.n0 - i;
             if (!EDGE || (jn >= q.b0 && jn <= q.b1))
-            {
-                const long long ro = row_off(q.ts, jn);
-                bm = (float)(q.Bm[ro] - q.dRa); bs = (float)(q.Bs[ro] - q.dRa);
-            }
+                bm = (float)(q.Bm[row_off(q.ts, jn)] - q.dRa);
         }
     }
     const float e = emission_f(lr_c, ey_c, sp);
@@ -101,7 +99,7 @@ __device__ __forceinline__ void row_f(ColF& q, const StateParamsF& sp, int i, in
     if (LAST)
     {
         const int jb = q.n0 - i + 1;
-        if (!EDGE || (jb >= q.b0 && jb <= q.b1)) q.joinmax = fmaxf(q.joinmax, fmaxf(C + bm_c, Sv + bs_c));
+        if (!EDGE || (jb >= q.b0 && jb <= q.b1)) q.joinmax = fmaxf(q.joinmax, C + bm_c);
     }
     else *slot = C;
     diag = Pi;
@@ -123,16 +121,16 @@ __device__ __forceinline__ void column_f(ColF& q, const StateParamsF& sp, int i0
     const LevelRecF* lq = q.lev + (q.n0 - i0);
     LevelRecF lr = *lv;
     float ey = lq->ey;
-    float bm = 0.f, bs = 0.f;
+    float bm = 0.f;
     if (LAST)
     {
         const int jb = q.n0 - i0 + 1;
-        if (jb >= q.b0 && jb <= q.b1) { const long long ro = row_off(q.ts, jb); bm = (float)(q.Bm[ro] - q.dRa); bs = (float)(q.Bs[ro] - q.dRa); }
+        if (jb >= q.b0 && jb <= q.b1) bm = (float)(q.Bm[row_off(q.ts, jb)] - q.dRa);
     }
     int i = i0;
-    for (; i < lo; i++) row_f<true, LAST>(q, sp, i, i0, i1, lv, lq, lr, ey, bm, bs, diag, upC, upS);
-    for (; i <= hi; i++) row_f<false, LAST>(q, sp, i, i0, i1, lv, lq, lr, ey, bm, bs, diag, upC, upS);
-    for (; i <= i1; i++) row_f<true, LAST>(q, sp, i, i0, i1, lv, lq, lr, ey, bm, bs, diag, upC, upS);
+    for (; i < lo; i++) row_f<true, LAST>(q, sp, i, i0, i1, lv, lq, lr, ey, bm, diag, upC, upS);
+    for (; i <= hi; i++) row_f<false, LAST>(q, sp, i, i0, i1, lv, lq, lr, ey, bm, diag, upC, upS);
+    for (; i <= i1; i++) row_f<true, LAST>(q, sp, i, i0, i1, lv, lq, lr, ey, bm, diag, upC, upS);
 }
 
 __global__ void __launch_bounds__(128) k_mutscore_f32(Batch b, int mask)
@@ -207,14 +205,14 @@ __global__ void __launch_bounds__(128) k_mutscore_f32(Batch b, int mask)
                 q.dRa = dRa;
                 q.joinmax = NEGF;
                 q.b0 = 1; q.b1 = 0;
-                q.Bm = b.Bm; q.Bs = b.Bs;
+                q.Bm = b.Bm;
                 if (rab > 0)
                 {
                     const long long gb = ev.col_off + rab;
                     q.b0 = b.Bi0[gb]; q.b1 = q.b0 + b.Blen[gb] - 1;
                     mb = b.Bbest[gb];
                     const long long bbase = col_base(ev, rab);
-                    q.Bm = b.Bm + bbase; q.Bs = b.Bs + bbase;
+                    q.Bm = b.Bm + bbase;
                 }
                 int i0 = f0, i1 = f1;
                 for (int c = startind + 1; c <= last; c++)
@@ -234,7 +232,7 @@ __global__ void __launch_bounds__(128) k_mutscore_f32(Batch b, int mask)
                             for (int i = max(i0, n0 + 1 - q.b1); i <= min(i1, n0 + 1 - q.b0); i++)
                             {
                                 const long long jb = n0 - i + 1;
-                                q.joinmax = fmaxf(q.joinmax, q.fl + fmaxf((float)(q.Bm[row_off(ts, (int)jb)] - dRa), (float)(q.Bs[row_off(ts, (int)jb)] - dRa)));
+                                q.joinmax = fmaxf(q.joinmax, q.fl + (float)(q.Bm[row_off(ts, (int)jb)] - dRa));
                             }
                     }
                     q.p0 = i0; q.p1 = i1;
@@ -278,7 +276,7 @@ struct RowSweep               // everything the row loop carries, all in registe
     int p0, p1;               // band of the seed column
     const double* seed;       // seed column (+ row_off), nullptr for the blank column 0
     double a;                 // rebasing offset
-    const double* Bm; const double* Bs; int b0, b1; double dRa; bool joined;   // reverse column of the last narrow column
+    const double* Bm; int b0, b1; double dRa; bool joined;   // reverse column of the last narrow column
     const LevelRecF* lev; int n0; long long rs;
     float fl; float4 tr;
     float best, joinmax;
@@ -323,10 +321,10 @@ __device__ __forceinline__ void sweep_rows(RowSweep& q, int ia, int ib, int rhi)
             lrn = q.lev[i]; eyn = q.lev[q.n0 - i - 1].ey;
             sdn = seed_raw(q, i + 1);
         }
-        double bmr = 0.0, bsr = 0.0;
+        double bmr = 0.0;
         const int jb = q.n0 - i + 1;
         const bool jin = jb >= q.b0 && jb <= q.b1;
-        if (q.joined && (FAST || jin)) { const long long ro = row_off(q.rs, jb); bmr = q.Bm[ro]; bsr = q.Bs[ro]; }
+        if (q.joined && (FAST || jin)) bmr = q.Bm[row_off(q.rs, jb)];
         float left = q.sd, diag = q.sd_prev;                 // (i, c-1) and (i-1, c-1)
         if (FAST)
         {
@@ -351,13 +349,13 @@ __device__ __forceinline__ void sweep_rows(RowSweep& q, int ia, int ib, int rhi)
             }
             if (q.joined)
             {
-                const float Cl = q.ncol == 6 ? q.C[5] : q.C[4], Sl = q.ncol == 6 ? q.S[5] : q.S[4];
-                q.joinmax = fmaxf(q.joinmax, fmaxf(Cl + (float)(bmr - q.dRa), Sl + (float)(bsr - q.dRa)));
+                const float Cl = q.ncol == 6 ? q.C[5] : q.C[4];
+                q.joinmax = fmaxf(q.joinmax, Cl + (float)(bmr - q.dRa));
             }
         }
         else if (MODE == ROWS_MASKED)
         {
-            const float bmf = jin ? (float)(bmr - q.dRa) : NEGF, bsf = jin ? (float)(bsr - q.dRa) : NEGF;
+            const float bmf = jin ? (float)(bmr - q.dRa) : NEGF;
             float jv4 = NEGF, jv5 = NEGF;
 #pragma unroll
             for (int c = 0; c < NC; c++)
@@ -374,8 +372,8 @@ __device__ __forceinline__ void sweep_rows(RowSweep& q, int ia, int ib, int rhi)
                 const bool act = i >= q.col[c].i0 && i <= q.col[c].i1;
                 const float Cm = act ? Cn : NEGF, Sm = act ? Sn : NEGF;
                 q.best = fmaxf(q.best, Cm);
-                if (c == 4) jv4 = fmaxf(Cm + bmf, Sm + bsf);
-                if (c == 5) jv5 = fmaxf(Cm + bmf, Sm + bsf);
+                if (c == 4) jv4 = Cm + bmf;
+                if (c == 5) jv5 = Cm + bmf;
                 left = fmaxf(Cm, q.fl);
                 diag = fmaxf(upC, q.fl);                     // (i-1, c) as the next column's diagonal
                 q.C[c] = i == q.col[c].i1 ? NEGF : Cm;
@@ -404,7 +402,7 @@ __device__ __forceinline__ void sweep_rows(RowSweep& q, int ia, int ib, int rhi)
                             q.best = fmaxf(q.best, Cn);
                         }
                         if (c == q.ncol - 1 && q.joined && jin)
-                            q.joinmax = fmaxf(q.joinmax, fmaxf(Cn + (float)(bmr - q.dRa), Sn + (float)(bsr - q.dRa)));
+                            q.joinmax = fmaxf(q.joinmax, Cn + (float)(bmr - q.dRa));
                         q.C[c] = Cn; q.S[c] = Sn;
                     }
                     diag = upC;                              // (i-1, c) is the next column's diagonal
@@ -504,14 +502,14 @@ __global__ void __launch_bounds__(128) k_mutscore_rows_f32(Batch b)
                 q.dRa = R - q.a;
                 double mb = 0.0;
                 q.b0 = 1; q.b1 = 0; q.joined = rab > 0;
-                q.Bm = b.Bm; q.Bs = b.Bs;
+                q.Bm = b.Bm;
                 if (rab > 0)
                 {
                     const long long gb = ev.col_off + rab;
                     q.b0 = b.Bi0[gb]; q.b1 = q.b0 + b.Blen[gb] - 1;
                     mb = b.Bbest[gb];
                     const long long bbase = col_base(ev, rab);
-                    q.Bm = b.Bm + bbase; q.Bs = b.Bs + bbase;
+                    q.Bm = b.Bm + bbase;
                 }
                 q.joinmax = NEGF;
                 q.lev = b.levf + ev.lev_off;

@@ -171,8 +171,8 @@ int ps_ctx::init()
     CU(cudaEventCreateWithFlags(&join_ev, cudaEventDisableTiming));
     for (int i = 0; i <= PS_T_COUNT; i++) CU(cudaEventCreate(&tev[i]));
     CU(cudaFuncSetAttribute(k_backtrace, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
-    CU(cudaFuncSetAttribute(k_fill<160, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CU(cudaFuncSetAttribute(k_fill<192, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CU(cudaFuncSetAttribute(k_fill<160, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    CU(cudaFuncSetAttribute(k_fill<192, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU(cudaFuncSetAttribute(k_fill<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024));
     CU(cudaFuncSetAttribute(k_mutscore<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU(cudaFuncSetAttribute(k_mutscore<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -734,7 +734,6 @@ int Job::upload()
     if (want_muts)
     {
         TRY(room(ctx, "Bm", cells, &b.Bm));
-        TRY(room(ctx, "Bs", cells, &b.Bs));
         TRY(room(ctx, "Bi0", (size_t)n_cols, &b.Bi0));
         TRY(room(ctx, "Blen", (size_t)n_cols, &b.Blen));
         TRY(room(ctx, "Bcb", (size_t)n_cols, &b.Bcb));
@@ -825,8 +824,9 @@ int Job::run(bool full)
             CU(cudaEventRecord(ctx->fork_ev, ctx->stream));
             CU(cudaStreamWaitEvent(ctx->side, ctx->fork_ev, 0));
         }
-        const size_t smem160 = std::max<size_t>(40 * 160, 2 * b.RS) * sizeof(double);   // rings + next strip record
-        const size_t smem192 = std::max<size_t>(40 * 192, 2 * b.RS) * sizeof(double);
+        // 8-deep rings (2 x 8 x 16 B per thread) + next strip record (11 x 16 B) for the point-to-point classes
+        const size_t smem160 = std::max<size_t>(54 * 160, 2 * b.RS) * sizeof(double);
+        const size_t smem192 = std::max<size_t>(54 * 192, 2 * b.RS) * sizeof(double);
         if (fill_count[2])
         {
             const size_t smem = std::max<size_t>(40 * 512, 2 * b.RS) * sizeof(double);
