@@ -339,8 +339,7 @@ def main():
         if record:
             for k, v in p.ctx.last_timing().items():
                 phase[k] = phase.get(k, 0.0) + v
-        for nr in p.regions:
-            nr.close()
+        poreseqcpp.close_regions(p.regions)
         return out
 
     def run_steps(count, record):

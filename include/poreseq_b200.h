@@ -120,6 +120,8 @@ typedef struct ps_region_desc
     const int*    complement;  const char* const* seq2d;
 } ps_region_desc;
 int         ps_regions_create(ps_ctx* ctx, int n_regions, const ps_region_desc* desc, ps_region** out);
+/* Releases a batch of regions in one call (the frees run on the library's worker threads); NULL entries are skipped. */
+void        ps_regions_destroy(ps_region* const* regions, int n_regions);
 int         ps_region_set_params(ps_region* r, const ps_params* params);
 int         ps_region_num_events(ps_region* r);
 int         ps_region_sequence_length(ps_region* r);

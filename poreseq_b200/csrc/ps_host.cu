@@ -402,6 +402,7 @@ struct Job
     PinVec<int> rs, re;
     PinVec<double> best, msc;
     bool have_scores = false;
+    double* raw_scores = nullptr;
 };
 
 // Band centres of the wide fill (cpp/EventData.h:172-183: lower_bound over ref_index; 1 when the
@@ -509,9 +510,11 @@ int Job::build()
     }
     mut_str.append("ACGT", 4);                  // single-base replacement strings live at offsets 0..3
 
-    // pass 1 (serial, cheap): region tables, mutation tables, event descriptors and offsets
+    // pass 1 (serial, cheap): region tables, list-mutation tables, event descriptors and offsets.  The
+    // point-mutation tables (8-9 entries per state) are only sized here and written in pass 2.
     std::vector<const HostEvent*> hev;
     std::vector<double> ev_cols;                  // per event: narrow columns of its region's mutations
+    std::vector<long long> reg_mut_off(regs.size(), 0);
     hev.reserve(tot_events); ev_cols.reserve(tot_events);
     for (size_t r = 0; r < regs.size(); r++)
     {
@@ -521,25 +524,25 @@ int Job::build()
         states.append(R->states.data(), R->states.size());
         bases.append(R->bases.data(), R->bases.size());
         const long long mut_off = (long long)mdev.size();
+        reg_mut_off[r] = mut_off;
         const int ev0 = (int)ev.size();
         double cols = 0;
+        int region_inv = 0;               // any base that is not ACGT (an invalid state, or a polluted one near the end)
+        long long odd = 0;                // non-ACGT bases that start a 5-mer window (4 substitutions instead of 3)
+        {
+            const size_t ns = R->states.size();
+            for (size_t i = 0; i < R->bases.size(); i++)
+            {
+                const char ch = R->bases[i];
+                if (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T') { region_inv = 1; if (i < ns) odd++; }
+            }
+        }
         if (want_muts && muts[r].points)
         {
-            // FindPointMutations order (cpp/FindMutations.cpp:191-234): del, 3 subs, 4 ins per state
-            for (int i = 0; i < (int)R->states.size(); i++)
-            {
-                const char here = R->bases[i];
-                MutDev d;
-                d.start = i; d.n_orig = 1; d.n_mut = 0; d.str_off = 0;
-                mdev.push_back(d);
-                d.n_mut = 1;
-                int nsub = 0;                    // 3, or 4 for a non-ACGT base
-                for (int j = 0; j < 4; j++)
-                    if ("ACGT"[j] != here) { d.str_off = j; mdev.push_back(d); nsub++; }
-                d.n_orig = 0;
-                for (int j = 0; j < 4; j++) { d.str_off = j; mdev.push_back(d); }
-                cols += 5 + 6.0 * nsub + 6.0 * 4;
-            }
+            // FindPointMutations (cpp/FindMutations.cpp:191-234): del, 3 subs (4 for a non-ACGT base), 4 ins per state
+            const long long ns = (long long)R->states.size();
+            mdev.resize((size_t)(mut_off + 8 * ns + odd));
+            cols = (double)(ns - odd) * (5 + 6.0 * 3 + 6.0 * 4) + (double)odd * (5 + 6.0 * 4 + 6.0 * 4);
         }
         else if (want_muts)
         {
@@ -554,11 +557,12 @@ int Job::build()
             }
         }
         const int nm = (int)(mdev.size() - mut_off);
-        int region_inv = 0;               // any base that is not ACGT (an invalid state, or a polluted one near the end)
-        for (char ch : R->bases) if (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T') { region_inv = 1; break; }
         RegTab rt; rt.mut_off = mut_off; rt.ev0 = ev0; rt.nev = (int)R->events.size();
         max_ev = std::max(max_ev, rt.nev);
         regtab.push_back(rt);
+        // model de-duplication across the whole batch (events usually share two models): once per
+        // (region, model), not per event
+        std::vector<int> model_of(R->models.size(), -1);
         for (size_t k = 0; k < R->events.size(); k++)
         {
             const HostEvent& he = R->events[k];
@@ -570,12 +574,14 @@ int Job::build()
             d.L = (int)R->bases.size();
             d.usable = (!he.ri_empty && R->params.realign_width != 0 && he.n0 > 0) ? 1 : 0;
             d.inv = region_inv;
-            // model de-duplication across the whole batch (events usually share two models)
-            const HostModel* hm = &R->models[he.model];
-            int mi = -1;
-            for (size_t q = 0; q < model_src.size(); q++)
-                if (model_src[q] == hm || memcmp(model_src[q], hm, sizeof(HostModel)) == 0) { mi = (int)q; break; }
-            if (mi < 0) { mi = (int)model_src.size(); model_src.push_back(hm); }
+            int& mi = model_of[he.model];
+            if (mi < 0)
+            {
+                const HostModel* hm = &R->models[he.model];
+                for (size_t q = 0; q < model_src.size(); q++)
+                    if (model_src[q] == hm || memcmp(model_src[q], hm, sizeof(HostModel)) == 0) { mi = (int)q; break; }
+                if (mi < 0) { mi = (int)model_src.size(); model_src.push_back(hm); }
+            }
             d.model = mi;
             d.n_muts = nm;
             d.lev_off = n_levels;
@@ -597,7 +603,26 @@ int Job::build()
     n_cols += 1;                                  // index 0 of the first event is never used
     n_muts = (long long)mdev.size();
 
-    // pass 2 (parallel over events): level records, alignment arrays, band centres, wavefront plan
+    // pass 2a (parallel over regions): the implicit point-mutation tables in FindPointMutations order
+    if (want_muts)
+        ps_parallel_for((int)regs.size(), [&](int r) {
+            if (!muts[r].points) return;
+            const ps_region* R = regs[r];
+            MutDev* out = mdev.data() + reg_mut_off[r];
+            for (int i = 0; i < (int)R->states.size(); i++)
+            {
+                const char here = R->bases[i];
+                MutDev d;
+                d.start = i; d.n_orig = 1; d.n_mut = 0; d.str_off = 0;
+                *out++ = d;
+                d.n_mut = 1;
+                for (int j = 0; j < 4; j++)
+                    if ("ACGT"[j] != here) { d.str_off = j; *out++ = d; }
+                d.n_orig = 0;
+                for (int j = 0; j < 4; j++) { d.str_off = j; *out++ = d; }
+            }
+        });
+    // pass 2b (parallel over events): level records, alignment arrays, band centres, wavefront plan
     const int ne = (int)ev.size();
     wave_need.assign(ne, 32);
     std::vector<double> ev_cells(ne, 0.0);
@@ -983,6 +1008,11 @@ int Job::finish(std::vector<double>* align_scores, std::vector<double>* mut_scor
         if (have_scores) mut_scores->assign(msc.data(), msc.data() + n_muts);
         else mut_scores->assign((size_t)n_muts, bias);
     }
+    if (raw_scores)                               // straight into the caller's array
+    {
+        if (have_scores) memcpy(raw_scores, msc.data(), (size_t)n_muts * sizeof(double));
+        else std::fill(raw_scores, raw_scores + n_muts, bias);
+    }
     // timings + algorithmic cell counts (wide = band cells of the usable events, both
     // directions when the reverse fill ran; narrow = (|mut|+5) x band rows per (mutation, usable event))
     for (int i = 0; i < PS_T_TOTAL; i++)
@@ -1034,10 +1064,11 @@ static int job_begin(ps_ctx* ctx, const std::vector<ps_region*>& regs, const std
     return PS_OK;
 }
 
-static int job_end(ps_ctx* ctx, std::vector<double>* align_scores, std::vector<double>* mut_scores)
+static int job_end(ps_ctx* ctx, std::vector<double>* align_scores, std::vector<double>* mut_scores, double* raw_scores = nullptr)
 {
     Job* job = (Job*)ctx->pending;
     if (!job) { ps_set_error(ctx, "no batch in flight on this context"); return PS_E_ARG; }
+    job->raw_scores = raw_scores;
     CU(cudaSetDevice(ctx->device));
     ctx->pending = nullptr;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -1259,6 +1290,12 @@ ps_region* ps_region_create(ps_ctx* ctx, const char* bases, int len, const ps_pa
 }
 
 void ps_region_destroy(ps_region* r) { delete r; }
+
+void ps_regions_destroy(ps_region* const* regions, int n_regions)
+{
+    if (!regions || n_regions <= 0) return;
+    ps_parallel_for(n_regions, [&](int k) { delete regions[k]; });
+}
 
 int ps_region_add_event(ps_region* R, int n0, const double* mean, const double* stdv, const double* ref_align,
                         const double* ref_like, const double* level_mean, const double* level_stdv,
@@ -1494,26 +1531,34 @@ int ps_score_points_batch_begin(ps_region* const* regions, int n_regions, int ca
     std::vector<ps_region*> regs(regions, regions + n_regions);
     std::vector<MutSpec> per(n_regions);
     long long at = 0;
+    std::vector<long long> offs(n_regions), cnt(n_regions);
     for (int r = 0; r < n_regions; r++)
     {
         if (!regs[r] || regs[r]->ctx != ctx) { ps_set_error(ctx, "all regions of a batch must belong to one context"); return PS_E_ARG; }
         per[r].points = true;
-        const long long n = write_points(regs[r], at, cap, start, orig, mut);
+        // 8 edits per state, 9 where the base is not ACGT (no substitution is skipped)
+        const ps_region* R = regs[r];
+        long long n = 8 * (long long)R->states.size();
+        for (size_t i = 0; i < R->states.size(); i++)
+        {
+            const char ch = R->bases[i];
+            if (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T') n++;
+        }
+        offs[r] = at; cnt[r] = n;
         if (n_out) n_out[r] = (int)n;
         if (off_out) off_out[r] = at;
         at += n;
     }
     if (at > cap) { ps_set_error(ctx, "output capacity %d < %lld point mutations", cap, at); return PS_E_CAPACITY; }
+    if (start || orig || mut)
+        ps_parallel_for(n_regions, [&](int r) { write_points(regs[r], offs[r], cap, start, orig, mut); });
     return job_begin(ctx, regs, &per, -1e-6);
 }
 
 int ps_score_points_batch_end(ps_ctx* ctx, double* scores)
 {
     if (!ctx) return PS_E_ARG;
-    std::vector<double> sc;
-    TRY(job_end(ctx, nullptr, &sc));
-    if (scores) std::copy(sc.begin(), sc.end(), scores);
-    return PS_OK;
+    return job_end(ctx, nullptr, nullptr, scores);
 }
 
 int ps_score_points_batch(ps_region* const* regions, int n_regions, int cap, int* n_out, long long* off_out,

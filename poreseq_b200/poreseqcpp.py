@@ -66,6 +66,7 @@ def lib():
     L.ps_region_add_events.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                                                                    C.c_void_p, C.c_void_p]
     L.ps_regions_create.argtypes = [C.c_void_p, C.c_int, C.POINTER(PSRegionDesc), C.POINTER(C.c_void_p)]
+    L.ps_regions_destroy.argtypes = [C.POINTER(C.c_void_p), C.c_int]
     L.ps_region_set_params.argtypes = [C.c_void_p, C.POINTER(PSParams)]
     L.ps_region_num_events.argtypes = [C.c_void_p]
     L.ps_region_sequence_length.argtypes = [C.c_void_p]
@@ -409,6 +410,17 @@ def native_regions_from_packed(ctx, packs, width_key=None):
     return regs
 
 
+def close_regions(regions):
+    """ps_regions_destroy: release a batch of NativeRegion objects in one C-ABI call."""
+    live = [r for r in regions if r.handle]
+    if not live:
+        return
+    handles = (C.c_void_p * len(live))(*[r.handle for r in live])
+    live[0].ctx.lib.ps_regions_destroy(handles, len(live))
+    for r in live:
+        r.handle = None
+
+
 def score_points_batch(ctx, regions):
     """ps_score_points_batch over NativeRegion objects: one launch sequence for all of them.
     Returns a list of (start, orig bytes, mut bytes, score) tuples of arrays, one per region."""
@@ -423,9 +435,10 @@ def score_points_batch(ctx, regions):
     sc = np.zeros(cap)
     ctx.check(ctx.lib.ps_score_points_batch(handles, n, cap, n_out, off, st.ctypes.data_as(_c_int_p), og, mu, _dp(sc)))
     out = []
+    ogr, mur = og.raw, mu.raw
     for k in range(n):
         a, b = off[k], off[k] + n_out[k]
-        out.append((st[a:b], og.raw[a:b], mu.raw[a:b], sc[a:b]))
+        out.append((st[a:b], ogr[a:b], mur[a:b], sc[a:b]))
     return out
 
 
@@ -450,9 +463,10 @@ class PendingBatch(object):
         """Wait for the batch; returns [(start, orig bytes, mut bytes, score)] per region."""
         self.ctx.check(self.ctx.lib.ps_score_points_batch_end(self.ctx.handle, _dp(self.sc)))
         out = []
+        og, mu = self.og.raw, self.mu.raw                 # one copy of each buffer, not one per region
         for k in range(len(self.regions)):
             a, b = self.off[k], self.off[k] + self.n_out[k]
-            out.append((self.st[a:b], self.og.raw[a:b], self.mu.raw[a:b], self.sc[a:b]))
+            out.append((self.st[a:b], og[a:b], mu[a:b], self.sc[a:b]))
         return out
 
 
