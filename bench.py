@@ -398,7 +398,7 @@ def main():
     # (the phase events sit on the library's stream right around the phase's launches)
     phase_ms = {k: phase[k] / args.steps for k in kernel_keys}
     dom = max(phase_ms, key=phase_ms.get)
-    dom_kernel = {"forward": "k_fill", "mutscore": "k_mutscore_f32" if args.precision == "fast" else "k_mutscore"}.get(dom, dom)
+    dom_kernel = {"forward": "k_fill", "mutscore": "k_mutscore_rows_f32" if args.precision == "fast" else "k_mutscore"}.get(dom, dom)
     dom_cells = {"forward": wide_cells, "mutscore": narrow_cells}.get(dom, 0.0)
     dom_s = phase_ms[dom] * 1e-3
     clock_mhz = clocks["sm_mhz"] or sm_max_mhz
@@ -430,7 +430,7 @@ def main():
         "phase_ms": phase_ms,
         "kernels": {"k_fill (forward+reverse wide fill, fp64)": {"ms": phase_ms["forward"], "cells": wide_cells,
                                                                 "gcups": wide_cells / phase_ms["forward"] / 1e6},
-                    dom_kernel if dom == "mutscore" else ("k_mutscore_f32 + exact re-score" if args.precision == "fast" else "k_mutscore"):
+                    dom_kernel if dom == "mutscore" else ("k_mutscore_rows_f32 + exact re-score" if args.precision == "fast" else "k_mutscore"):
                         {"ms": phase_ms["mutscore"], "cells": narrow_cells, "gcups": narrow_cells / phase_ms["mutscore"] / 1e6},
                     "k_join": {"ms": phase_ms["join"]}, "k_backtrace": {"ms": phase_ms["backtrace"]}},
         "roofline": {"bound": "fp32-issue", "kernel": dom_kernel,

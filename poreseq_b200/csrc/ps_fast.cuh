@@ -2,7 +2,7 @@
 //
 // The exact FP64 kernels of ps_device.cuh stay the source of truth for everything a decision hangs
 // on.  In PS_PRECISION_FAST mode the mutation scan runs in two passes:
-//   1. k_mutscore_f32 scores EVERY (mutation, event) pair in log-space FP32.  Path scores grow
+//   1. k_mutscore_rows_f32 scores EVERY (mutation, event) pair in log-space FP32.  Path scores grow
 //      with the region (~2.3 per level), so each task works on values rebased to its own seed
 //      column: forward values carry x - a (a = seed value at the band centre), the reverse join
 //      values B - (R - a) with R the task's old score, so the numbers the FP32 units see are O(10)
@@ -21,10 +21,10 @@ namespace psdev {
 
 constexpr float NEGF = -3.0e38f;
 
-__device__ __forceinline__ float emission_f(const LevelRecF& l, float ey, const StateParamsF& p)
+__device__ __forceinline__ float emission_f(const LevelRecF& l, const StateParamsF& p)
 {
     const float d1 = l.x - p.mu, d2 = l.y - p.mu2;
-    return __fmaf_rn(p.a_s, d1 * d1, p.c_s) + __fmaf_rn(p.f_s * l.ry, d2 * d2, ey);
+    return __fmaf_rn(p.a_s, d1 * d1, p.c_s) + __fmaf_rn(p.f_s * l.ry, d2 * d2, l.ey);
 }
 
 // one cell in rebased FP32: `fl` is the rebased 0 floor (cpp/Alignment.cpp:194-271 with 0 -> fl)
@@ -45,219 +45,15 @@ __device__ __forceinline__ void dp_cell_f(bool first_row, bool skip_ok, bool dia
     C = fmaxf(fmaxf(fmaxf(fl, skip), fmaxf(match, ins)), fmaxf(ignore, S));
 }
 
-// Per-thread strip in shared memory, indexed by (row & mask) so no wrap logic is needed: the
-// main-matrix values of the previous column, updated in place (see ps_device.cuh).  The seed
-// column is staged into it (rebased, FP32) before the first narrow column, so the column routine
-// has one form for every column but the last, whose rows are joined with the reverse column on the
-// fly.  Interior rows carry no band predicate; the level record (and the reverse cells) of row i+1
-// are requested while row i is computed.
-struct ColF
-{
-    float* ringC;                // + (row & mask) * 128
-    const LevelRecF* lev;        // event levels
-    const double* Bm;            // reverse column, main matrix (last narrow column only): + row_off(ts, jb); main >= stay
-                                 // in every cell, so the stay matrices never decide a join
-    long long ts;
-    double dRa;
-    int n0, mask;
-    int p0, p1;                  // previous column's band
-    int b0, b1;                  // reverse column's band (rows jb, inclusive); empty when there is none
-    float fl;
-    float4 tr;
-    float best, joinmax;
-};
-
-template <bool EDGE, bool LAST>
-__device__ __forceinline__ void row_f(ColF& q, const StateParamsF& sp, int i, int i0, int i1,
-                                      const LevelRecF*& lv, const LevelRecF*& lq, LevelRecF& lr, float& ey,
-                                      float& bm, float& diag, float& upC, float& upS)
-{
-    const LevelRecF lr_c = lr;
-    const float ey_c = ey, bm_c = bm;
-    if (!EDGE || i < i1)
-    {
-        // next row: level i (mean/stdv) and level n0-i-1 (its -1.5 log stdv, quirk A.3-1), reverse row jb-1
-        lv++; lq--;
-        lr = *lv; ey = lq->ey;
-        if (LAST)
-        {
-            const int jn = q.n0 - i;
-            if (!EDGE || (jn >= q.b0 && jn <= q.b1))
-                bm = (float)(q.Bm[row_off(q.ts, jn)] - q.dRa);
-        }
-    }
-    const float e = emission_f(lr_c, ey_c, sp);
-    const bool skip_ok = EDGE ? (i >= q.p0 && i <= q.p1) : true;
-    const bool diag_ok = EDGE ? (i > q.p0 && i <= q.p1) : true;
-    const bool first = EDGE ? (i == i0) : false;
-    float* slot = q.ringC + (i & q.mask) * 128;
-    float Pi = q.fl;
-    if (skip_ok) Pi = *slot;
-    float C, Sv;
-    dp_cell_f(first, skip_ok, diag_ok, Pi, diag, e, upC, upS, q.fl, q.tr, C, Sv);
-    q.best = fmaxf(q.best, C);
-    if (LAST)
-    {
-        const int jb = q.n0 - i + 1;
-        if (!EDGE || (jb >= q.b0 && jb <= q.b1)) q.joinmax = fmaxf(q.joinmax, C + bm_c);
-    }
-    else *slot = C;
-    diag = Pi;
-    upC = C; upS = Sv;
-}
-
-template <bool LAST>
-__device__ __forceinline__ void column_f(ColF& q, const StateParamsF& sp, int i0, int i1)
-{
-    float diag = q.fl;
-    if (i0 > q.p0 && i0 <= q.p1) diag = q.ringC[((i0 - 1) & q.mask) * 128];
-    float upC = q.fl, upS = q.fl;
-    // interior: rows i-1 and i of the previous column exist and (last column) so does the reverse cell,
-    // also for the row after (its values are requested one row ahead)
-    int lo = max(i0 + 1, q.p0 + 1), hi = min(i1 - 1, q.p1);
-    if (LAST) { lo = max(lo, q.n0 + 1 - q.b1); hi = min(hi, q.n0 - q.b0); }
-    if (lo > hi) { lo = i1 + 1; hi = i1; }
-    const LevelRecF* lv = q.lev + (i0 - 1);
-    const LevelRecF* lq = q.lev + (q.n0 - i0);
-    LevelRecF lr = *lv;
-    float ey = lq->ey;
-    float bm = 0.f;
-    if (LAST)
-    {
-        const int jb = q.n0 - i0 + 1;
-        if (jb >= q.b0 && jb <= q.b1) bm = (float)(q.Bm[row_off(q.ts, jb)] - q.dRa);
-    }
-    int i = i0;
-    for (; i < lo; i++) row_f<true, LAST>(q, sp, i, i0, i1, lv, lq, lr, ey, bm, diag, upC, upS);
-    for (; i <= hi; i++) row_f<false, LAST>(q, sp, i, i0, i1, lv, lq, lr, ey, bm, diag, upC, upS);
-    for (; i <= i1; i++) row_f<true, LAST>(q, sp, i, i0, i1, lv, lq, lr, ey, bm, diag, upC, upS);
-}
-
-__global__ void __launch_bounds__(128) k_mutscore_f32(Batch b, int mask)
-{
-    extern __shared__ float ringf[];
-    const long long nthreads = (long long)gridDim.x * blockDim.x;
-    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int W = b.scoring_width;
-    for (long long t = gtid; t < b.n_tasks; t += nthreads)
-    {
-        int e, m;
-        if (!task_decode(b, t, e, m)) continue;
-        const EvDesc ev = b.ev[e];
-        const MutDev mu = b.muts[ev.mut_off + m];
-        double result = 0.0;
-        if (ev.usable && !((unsigned)mu.start > (unsigned)ev.L))
-        {
-            const int N = ev.N, n0 = ev.n0, L = ev.L;
-            MutView mv;
-            mv.bases = b.bases + ev.base_off; mv.L = L; mv.mstr = b.mut_str + mu.str_off;
-            mv.start = mu.start; mv.n_orig = mu.n_orig; mv.n_mut = mu.n_mut;
-            mv.applied = mu.start < L;
-            mv.Lm = mv.applied ? mu.start + mu.n_mut + max(0, L - mu.start - mu.n_orig) : L;
-            const int Nm = mv.Lm >= 5 ? mv.Lm - 4 : 0;
-            const int raf = max(mu.start - 3, 1);
-            const double R = raf <= N ? b.old[ev.col_off + raf] : thread_join(b, ev, raf, N - raf + 1);
-            const int startind = max(mu.start - 4, 0);
-            const int refind = mu.start + mu.n_mut + 1;
-            int last = min(min(refind, startind + mu.n_mut + 6), Nm);
-            if (W == 0) last = startind;
-            if (last <= startind)
-                result = thread_join(b, ev, startind, Nm - startind + 1) - R;     // boundary case: exact
-            else
-            {
-                const StateParamsF* stf = b.stf + (size_t)ev.model * N_STATES;
-                const bool ri_empty = b.ri_empty[e] != 0;
-                const long long ts = ev.rs;
-                ColF q;
-                q.ringC = ringf + threadIdx.x;
-                q.lev = b.levf + ev.lev_off;
-                q.n0 = n0; q.mask = mask; q.ts = ts;
-                q.tr = b.trf[ev.model];
-                q.p0 = 0; q.p1 = n0;
-                double best_d = 0.0, a = 0.0;
-                // band of the first narrow column: the seed rows it can touch are [i0-1, i1]
-                int f0, f1;
-                band_of(ri_empty ? 1 : b.cen_new[ev.cen_off + startind + 1], n0, W, f0, f1);
-                if (startind > 0)
-                {
-                    const long long gs = ev.col_off + startind;
-                    q.p0 = b.Fi0[gs]; q.p1 = q.p0 + b.Flen[gs] - 1;
-                    const double* seed = b.Fm + col_base(ev, startind);
-                    best_d = b.Fbest[gs];
-                    // rebase to the seed value on the band centre of the first narrow column
-                    const int mid = min(max((f0 + f1) >> 1, q.p0), q.p1);
-                    a = seed[row_off(ts, mid)];
-                    // stage the seed rows the first column reads, rebased, into the ring
-                    const int s0 = max(f0 - 1, q.p0), s1 = min(f1, q.p1);
-                    for (int i = s0; i <= s1; i++) q.ringC[(i & mask) * 128] = (float)(seed[row_off(ts, i)] - a);
-                }
-                q.fl = (float)(-a);
-                q.best = (float)(best_d - a);
-                if (startind == 0)
-                {
-                    // blank column 0: rows 0..n0, all zeros
-                    for (int i = max(f0 - 1, 0); i <= f1; i++) q.ringC[(i & mask) * 128] = q.fl;
-                }
-                // reverse column the last narrow column is joined with; values relative to R
-                const int rab = min(max(Nm - last + 1, 0), N);
-                const double dRa = R - a;
-                double mb = 0.0;
-                q.dRa = dRa;
-                q.joinmax = NEGF;
-                q.b0 = 1; q.b1 = 0;
-                q.Bm = b.Bm;
-                if (rab > 0)
-                {
-                    const long long gb = ev.col_off + rab;
-                    q.b0 = b.Bi0[gb]; q.b1 = q.b0 + b.Blen[gb] - 1;
-                    mb = b.Bbest[gb];
-                    const long long bbase = col_base(ev, rab);
-                    q.Bm = b.Bm + bbase;
-                }
-                int i0 = f0, i1 = f1;
-                for (int c = startind + 1; c <= last; c++)
-                {
-                    if (c > startind + 1) band_of(ri_empty ? 1 : b.cen_new[ev.cen_off + c], n0, W, i0, i1);
-                    const int s = mut_state(mv, c - 1);
-                    if (s >= 0)
-                    {
-                        const StateParamsF sp = stf[s];
-                        if (c == last && rab > 0) column_f<true>(q, sp, i0, i1); else column_f<false>(q, sp, i0, i1);
-                    }
-                    else
-                    {
-                        // invalid state (cpp/Alignment.cpp:162-163): all-zero column inheriting the running best
-                        for (int i = i0; i <= i1; i++) q.ringC[(i & mask) * 128] = q.fl;
-                        if (c == last && rab > 0)
-                            for (int i = max(i0, n0 + 1 - q.b1); i <= min(i1, n0 + 1 - q.b0); i++)
-                            {
-                                const long long jb = n0 - i + 1;
-                                q.joinmax = fmaxf(q.joinmax, q.fl + (float)(q.Bm[row_off(ts, (int)jb)] - dRa));
-                            }
-                    }
-                    q.p0 = i0; q.p1 = i1;
-                }
-                float joinmax = q.joinmax;
-                // a blank reverse column (all zeros) adds nothing beyond the running best of the forward cells
-                if (rab == 0) joinmax = q.best - (float)dRa;
-                // new - old = max(join, best, reverse best, 0) - R, all relative to R
-                const float rel = fmaxf(fmaxf(joinmax, q.best - (float)dRa), fmaxf((float)(mb - R), (float)(-R)));
-                result = (double)rel;
-            }
-        }
-        b.delta[t] = result;
-    }
-}
-
 // ------------------------------------------------------------------------------------------
-// k_mutscore_rows_f32: the same FP32 scan, row-major.  A mutation that replaces at most one base
+// k_mutscore_rows_f32: the FP32 scan, row-major.  A mutation that replaces at most one base
 // re-fills at most NC = 6 narrow columns.  Instead of finishing one column before the next (which
 // needs the previous column in a per-thread ring and re-reads the level records once per column),
 // the thread sweeps the rows once and keeps one (main, stay) pair per column in registers: cell
 // (i, c) reads (i, c-1) computed a moment ago, (i-1, c-1) and (i-1, c) from the registers of the
-// previous row.  Per row it loads one level record, one seed value and (for the last column) one
-// reverse cell pair, all one row ahead; the six emissions of a row are independent.
-// Arithmetic and operation order are those of k_mutscore_f32, so the two kernels agree bit for bit.
+// previous row.  Per row it loads one 16-byte row record (mean, stdv, 1/stdv of level i-1 and the
+// -1.5 log stdv of level n0-i the forward pass pairs with them, quirk A.3-1; built by the host), one seed
+// value and (for the last column) one reverse cell; the six emissions of a row are independent.
 // Mutations with longer replacement strings are left to the exact pass (k_flag sends them there).
 constexpr int NC = 6;
 
@@ -311,20 +107,36 @@ template <int MODE>
 __device__ __forceinline__ void sweep_rows(RowSweep& q, int ia, int ib, int rhi)
 {
     constexpr bool FAST = MODE == ROWS_FAST;
+    // FAST rows lie strictly inside every band (and before the last row), so their loads need no range test
+    // and walk with running pointers: the row record of row i+1, the seed cell of row i+1 (a row pair shares
+    // a 2x2 tile: +2 inside the pair, +rs-2 to the next pair) and the reverse cell of row i (rows run backwards)
+    const float4* plev = reinterpret_cast<const float4*>(q.lev + ia);
+    const double* pseed = q.seed ? q.seed + row_off(q.rs, ia + 1) : nullptr;
+    const double* pB = q.Bm + (q.joined ? row_off(q.rs, max(q.n0 - ia + 1, 1)) : 0);
+    const long long hop = q.rs - 2;
     for (int i = ia; i <= ib; i++)
     {
-        // requests: level record and seed value of row i+1, reverse cells of row i
-        LevelRecF lrn; float eyn = 0.f; double sdn = 0.0;
-        lrn.x = lrn.y = lrn.ry = lrn.ey = 0.f;
-        if (i < rhi)
-        {
-            lrn = q.lev[i]; eyn = q.lev[q.n0 - i - 1].ey;
-            sdn = seed_raw(q, i + 1);
-        }
-        double bmr = 0.0;
+        // requests: row record and seed value of row i+1, reverse cell of row i
+        LevelRecF lrn; double sdn = 0.0, bmr = 0.0;
         const int jb = q.n0 - i + 1;
         const bool jin = jb >= q.b0 && jb <= q.b1;
-        if (q.joined && (FAST || jin)) bmr = q.Bm[row_off(q.rs, jb)];
+        if (FAST)
+        {
+            const float4 v = *plev++;
+            lrn.x = v.x; lrn.y = v.y; lrn.ry = v.z; lrn.ey = v.w;
+            if (pseed) { sdn = *pseed; pseed += (i & 1) ? hop : 2; }            // row i+1 -> i+2: i+1 even ends a pair
+            if (q.joined) { bmr = *pB; pB -= (jb & 1) ? hop : 2; }              // row jb -> jb-1: jb odd starts a pair
+        }
+        else
+        {
+            lrn.x = lrn.y = lrn.ry = lrn.ey = 0.f;
+            if (i < rhi)
+            {
+                lrn = q.lev[i];
+                sdn = seed_raw(q, i + 1);
+            }
+            if (q.joined && jin) bmr = q.Bm[row_off(q.rs, jb)];
+        }
         float left = q.sd, diag = q.sd_prev;                 // (i, c-1) and (i-1, c-1)
         if (FAST)
         {
@@ -413,7 +225,7 @@ __device__ __forceinline__ void sweep_rows(RowSweep& q, int ia, int ib, int rhi)
         }
         // bottom of the row: what row i+1 needs
 #pragma unroll
-        for (int c = 0; c < NC; c++) q.em[c] = emission_f(lrn, eyn, q.col[c].sp);
+        for (int c = 0; c < NC; c++) q.em[c] = emission_f(lrn, q.col[c].sp);
         q.sd_prev = (MODE == ROWS_MASKED && i == q.p1) ? q.fl : q.sd;   // the diagonal out of the seed column's last row is implicit
                                                                           // (fast rows end before any column's last row)
         q.sd = (float)(sdn - q.a);
@@ -533,9 +345,8 @@ __global__ void __launch_bounds__(128) k_mutscore_rows_f32(Batch b)
                 q.sd = (float)(seed_raw(q, rlo) - q.a);
                 {
                     const LevelRecF lr = q.lev[rlo - 1];
-                    const float ey = q.lev[n0 - rlo].ey;
 #pragma unroll
-                    for (int c = 0; c < NC; c++) q.em[c] = emission_f(lr, ey, q.col[c].sp);
+                    for (int c = 0; c < NC; c++) q.em[c] = emission_f(lr, q.col[c].sp);
                 }
                 if (all_valid && q.ncol >= 5)
                 {

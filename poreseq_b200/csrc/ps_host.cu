@@ -176,7 +176,6 @@ int ps_ctx::init()
     CU(cudaFuncSetAttribute(k_fill<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024));
     CU(cudaFuncSetAttribute(k_mutscore<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU(cudaFuncSetAttribute(k_mutscore<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    CU(cudaFuncSetAttribute(k_mutscore_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     // the per-thread rings of the exact mutation kernel are what limits its occupancy: ask for the largest shared-memory carve-out
     CU(cudaFuncSetAttribute(k_mutscore<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_mutscore<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -633,7 +632,17 @@ int Job::build()
         he.ensure_levrec();
         const size_t at = (size_t)d.lev_off, n = (size_t)he.n0;
         memcpy(lev.data() + at, he.levrec.data(), n * sizeof(LevelRec));
-        if (fast) memcpy(levf.data() + at, he.levrecf.data(), n * sizeof(LevelRecF));
+        if (fast)
+        {
+            // row records of the FP32 scan: row i reads level i-1 and the log stdv term of level n0-i
+            LevelRecF* out = levf.data() + at;
+            const float* src = he.levrecf.data();
+            for (size_t k = 0; k < n; k++)
+            {
+                out[k].x = src[4 * k]; out[k].y = src[4 * k + 1]; out[k].ry = src[4 * k + 2];
+                out[k].ey = src[4 * (n - 1 - k) + 3];
+            }
+        }
         memcpy(ref_align.data() + at, he.ref_align.data(), n * sizeof(double));
         memcpy(ref_like.data() + at, he.ref_like.data(), n * sizeof(double));
         if (he.ri_empty) std::fill(ref_index.data() + at, ref_index.data() + at + n, 0.0);
@@ -896,20 +905,15 @@ int Job::run(bool full)
             const int threads = 128;
             const bool in_smem = ring * 128 <= 96 * 1024;            // the smem ring is laid out for 128 threads
             long long blocks = std::min<long long>((n_tasks + threads - 1) / threads, (long long)ctx->sm_count * 16);
-            int mask = 1;
-            while (mask + 1 < 2 * b.scoring_width + 2) mask = 2 * mask + 1;     // power-of-two ring >= 2W+2 rows
-            const size_t ringf_bytes = (size_t)(mask + 1) * 128 * sizeof(float);
-            static const bool old_scan = getenv("PORESEQ_B200_MUT_OLD") != nullptr;   // column-major FP32 scan, kept for A/B runs
-            if (fast && (!old_scan || (in_smem && ringf_bytes <= 96 * 1024)))
+            if (fast)
             {
                 // pass 1: every pair in rebased FP32; pass 2: exact FP64 for the mutations that matter
-                if (old_scan) k_mutscore_f32<<<(unsigned)blocks, threads, ringf_bytes, ctx->stream>>>(b, mask);
-                else k_mutscore_rows_f32<<<(unsigned)blocks, threads, 0, ctx->stream>>>(b);
+                k_mutscore_rows_f32<<<(unsigned)blocks, threads, 0, ctx->stream>>>(b);
                 LAUNCHED();
                 k_reduce<<<(unsigned)((n_muts + 127) / 128), 128, 0, ctx->stream>>>(b, (const RegTabDev*)d_regtab, (int)regs.size(), n_muts, bias, 0);
                 LAUNCHED();
                 CU(cudaMemsetAsync(b.flag_count, 0, sizeof(int), ctx->stream));
-                k_flag<<<(unsigned)((n_muts + 127) / 128), 128, 0, ctx->stream>>>(b, n_muts, old_scan ? 1 << 30 : 1);
+                k_flag<<<(unsigned)((n_muts + 127) / 128), 128, 0, ctx->stream>>>(b, n_muts, 1);
                 LAUNCHED();
                 const unsigned rblocks = (unsigned)std::min<long long>(blocks, (long long)ctx->sm_count * 4);
                 if (in_smem) k_mutscore<true, true><<<rblocks, threads, ring * 128, ctx->stream>>>(b);

@@ -34,8 +34,8 @@ struct StateParamsF           // FP32 fused emission coefficients of one state (
     float pad0, pad1, pad2;
 };
 
-struct LevelRecF              // FP32 level record: mean, stdv, 1/stdv, -1.5 log(stdv)
-{
+struct __align__(16) LevelRecF // FP32 row record of the forward scan, row i (1-based) at index i-1: mean, stdv, 1/stdv of
+{                              // level i-1 and -1.5 log(stdv) of level n0-i (quirk A.3-1: cpp/Alignment.cpp:171-172)
     float x, y, ry, ey;
 };
 

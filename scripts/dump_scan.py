@@ -1,4 +1,5 @@
-"""A/B check of the two FP32 mutation scans: run with and without PORESEQ_B200_MUT_OLD=1, compare dumps."""
+"""Dump the FAST-mode ScorePoints scores of three fixed synthetic regions (regression check of the FP32 scan:
+compare the dump of a new build with the dump of the previous one, they must be bit-identical)."""
 import sys
 import numpy as np
 sys.path.insert(0, ".")
@@ -15,4 +16,7 @@ for seed, kw in ((1, {}), (2, dict(draft_error=0.03)), (3, dict(partial=0.3))):
     res.append(sc.copy())
     nr.close()
 np.save(out, np.concatenate(res))
+if len(sys.argv) > 2:
+    ref = np.load(sys.argv[2])
+    print("identical to %s:" % sys.argv[2], np.array_equal(ref, np.concatenate(res)))
 print(out, len(np.concatenate(res)), ctx.last_timing()["mutscore"])
