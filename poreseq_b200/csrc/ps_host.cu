@@ -165,7 +165,7 @@ int ps_ctx::init()
     }
     sm_count = prop.multiProcessorCount;
     total_mem = prop.totalGlobalMem;
-    CU(cudaStreamCreate(&stream));
+    CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));   // never waits for (or holds up) the legacy default stream of the host program
     CU(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&join_ev, cudaEventDisableTiming));

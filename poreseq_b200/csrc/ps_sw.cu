@@ -212,17 +212,30 @@ int psi_swfull_batch(ps_ctx* ctx, const std::string& s1, const std::vector<std::
         TRY(dev_room(ctx, "sw_best", np, &d_best));
         TRY(dev_room(ctx, "sw_o1", (size_t)out_off, &d_o1));
         TRY(dev_room(ctx, "sw_o2", (size_t)out_off, &d_o2));
-        CU(cudaMemcpyAsync(d_s1, s1.data(), (size_t)n1, cudaMemcpyHostToDevice, ctx->stream));
-        if (!cat.empty()) CU(cudaMemcpyAsync(d_s2, cat.data(), cat.size(), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(d_pairs, pairs.data(), np * sizeof(SwPair), cudaMemcpyHostToDevice, ctx->stream));
+        // host sides of all copies in pinned memory of the context (a pageable copy waits for the stream inside
+        // the driver call and holds up the CUDA calls of other host threads meanwhile)
+        PinVec<char> h_s1 = ctx->pinned<char>("sw_s1_h"), h_s2 = ctx->pinned<char>("sw_s2_h");
+        PinVec<SwPair> h_pairs = ctx->pinned<SwPair>("sw_pairs_h");
+        PinVec<SwBest> best = ctx->pinned<SwBest>("sw_best_h");
+        PinVec<int> o1 = ctx->pinned<int>("sw_o1_h"), o2 = ctx->pinned<int>("sw_o2_h");
+        if (!h_s1.resize((size_t)n1) || !h_s2.resize(std::max<size_t>(cat.size(), 1)) || !h_pairs.resize(np) || !best.resize(np) ||
+            !o1.resize((size_t)out_off) || !o2.resize((size_t)out_off))
+        {
+            ps_set_error(ctx, "out of host memory staging the alignments");
+            return PS_E_INTERNAL;
+        }
+        memcpy(h_s1.data(), s1.data(), (size_t)n1);
+        memcpy(h_s2.data(), cat.data(), cat.size());
+        std::copy(pairs.begin(), pairs.end(), h_pairs.data());
+        CU(cudaMemcpyAsync(d_s1, h_s1.data(), (size_t)n1, cudaMemcpyHostToDevice, ctx->stream));
+        if (!cat.empty()) CU(cudaMemcpyAsync(d_s2, h_s2.data(), cat.size(), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(d_pairs, h_pairs.data(), np * sizeof(SwPair), cudaMemcpyHostToDevice, ctx->stream));
         k_sw_fill<<<(unsigned)np, SW_T, 0, ctx->stream>>>(d_s1, n1, d_s2, d_pairs, d_mv, d_best, K);
         ctx->launches++;
         CU(cudaGetLastError());
         k_sw_trace<<<(unsigned)np, 32, 0, ctx->stream>>>(d_s1, n1, d_s2, d_pairs, d_mv, d_best, d_o1, d_o2);
         ctx->launches++;
         CU(cudaGetLastError());
-        std::vector<SwBest> best(np);
-        std::vector<int> o1((size_t)out_off), o2((size_t)out_off);
         CU(cudaMemcpyAsync(best.data(), d_best, np * sizeof(SwBest), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaMemcpyAsync(o1.data(), d_o1, (size_t)out_off * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaMemcpyAsync(o2.data(), d_o2, (size_t)out_off * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

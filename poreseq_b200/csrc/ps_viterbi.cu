@@ -346,8 +346,20 @@ int ps_viterbi_list(ps_region* R, int nkeep, double skip_prob, double stay_prob,
     if (n_pos == 0) { ps_set_error(ctx, "ViterbiMutate: no position is covered by the events"); return PS_E_ARG; }
 
     // ---- device ------------------------------------------------------------------------------
-    std::vector<ModelDev> models(R->models.size());
+    // every host side of a copy is pinned memory owned by the context: a copy from or to pageable memory
+    // waits for the stream inside the driver call, which stalls the CUDA calls of the other host threads
+    // (other regions in flight on their own contexts) for as long as the chain kernel runs
+    PinVec<ModelDev> models = ctx->pinned<ModelDev>("vit_models_h");
+    PinVec<VitSlot> h_slots = ctx->pinned<VitSlot>("vit_slots_h");
+    PinVec<int> h_off = ctx->pinned<int>("vit_off_h");
+    if (!models.resize(R->models.size()) || !h_slots.resize(slots.size()) || !h_off.resize(slot_off.size()))
+    {
+        ps_set_error(ctx, "out of host memory staging ViterbiMutate");
+        return PS_E_INTERNAL;
+    }
     for (size_t q = 0; q < models.size(); q++) ps_build_model(R->models[q], models[q]);
+    std::copy(slots.begin(), slots.end(), h_slots.data());
+    std::copy(slot_off.begin(), slot_off.end(), h_off.data());
     ModelDev* d_models; VitSlot* d_slots; int* d_off;
     double *d_obs, *d_eobs, *d_fwd, *d_last, *d_rnd;
     int *d_bp, *d_paths;
@@ -360,8 +372,8 @@ int ps_viterbi_list(ps_region* R, int nkeep, double skip_prob, double stay_prob,
     TRY(vroom(ctx, "vit_bp", (size_t)n_pos * N_STATES, &d_bp));
     TRY(vroom(ctx, "vit_last", (size_t)N_STATES, &d_last));
     CU(cudaMemcpyAsync(d_models, models.data(), models.size() * sizeof(ModelDev), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(d_slots, slots.data(), slots.size() * sizeof(VitSlot), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(d_off, slot_off.data(), slot_off.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_slots, h_slots.data(), slots.size() * sizeof(VitSlot), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_off, h_off.data(), slot_off.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     {
         int threads = 128;
         while (threads > 32 && (size_t)threads * max_lik * sizeof(double) > 200 * 1024) threads >>= 1;
@@ -385,7 +397,8 @@ int ps_viterbi_list(ps_region* R, int nkeep, double skip_prob, double stay_prob,
     k_vit_chain<<<1, N_STATES, 0, ctx->stream>>>(d_obs, d_eobs, n_pos, vc, d_fwd, d_bp, d_last);
     ctx->launches++;
     CU(cudaGetLastError());
-    std::vector<double> last(N_STATES);
+    PinVec<double> last = ctx->pinned<double>("vit_last_h");
+    if (!last.resize(N_STATES)) { ps_set_error(ctx, "out of host memory staging ViterbiMutate"); return PS_E_INTERNAL; }
     CU(cudaMemcpyAsync(last.data(), d_last, N_STATES * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     const int startst = (int)(std::max_element(last.begin(), last.end()) - last.begin());
@@ -393,15 +406,23 @@ int ps_viterbi_list(ps_region* R, int nkeep, double skip_prob, double stay_prob,
     std::vector<int> path(n_pos);
     if (nkeep == 0)
     {
-        std::vector<int> bp((size_t)n_pos * N_STATES);
-        CU(cudaMemcpy(bp.data(), d_bp, bp.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        PinVec<int> bp = ctx->pinned<int>("vit_bp_h");
+        if (!bp.resize((size_t)n_pos * N_STATES)) { ps_set_error(ctx, "out of host memory staging ViterbiMutate"); return PS_E_INTERNAL; }
+        CU(cudaMemcpyAsync(bp.data(), d_bp, bp.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
         int cur = startst;
         for (int t = n_pos - 1; t >= 0; t--) { path[t] = cur; cur = bp[(size_t)t * N_STATES + cur]; }
         out.push_back(states_to_sequence(path));
         return PS_OK;
     }
     // glibc rand() stream in the reference's call order: sample-major, positions from the end
-    std::vector<double> rnd((size_t)nkeep * n_pos);
+    PinVec<double> rnd = ctx->pinned<double>("vit_rnd_h");
+    PinVec<int> paths = ctx->pinned<int>("vit_paths_h");
+    if (!rnd.resize((size_t)nkeep * n_pos) || !paths.resize((size_t)nkeep * n_pos))
+    {
+        ps_set_error(ctx, "out of host memory staging ViterbiMutate");
+        return PS_E_INTERNAL;
+    }
     for (size_t q = 0; q < rnd.size(); q++) rnd[q] = rand() / (double(RAND_MAX) + 1);
     TRY(vroom(ctx, "vit_rnd", rnd.size(), &d_rnd));
     TRY(vroom(ctx, "vit_paths", rnd.size(), &d_paths));
@@ -409,7 +430,6 @@ int ps_viterbi_list(ps_region* R, int nkeep, double skip_prob, double stay_prob,
     k_vit_sample<<<nkeep, N_STATES, 0, ctx->stream>>>(d_fwd, n_pos, startst, d_rnd, skip_prob, stay_prob, mut_min, mut_max, nkeep, d_paths);
     ctx->launches++;
     CU(cudaGetLastError());
-    std::vector<int> paths((size_t)nkeep * n_pos);
     CU(cudaMemcpyAsync(paths.data(), d_paths, paths.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     for (int k = 0; k < nkeep; k++)
