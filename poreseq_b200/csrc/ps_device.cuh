@@ -75,6 +75,7 @@ struct Batch                  // everything the kernels need, passed by value
     int*              cen_old;
     int*              cen_new;
     int               cen_pad;
+    long long         warp_limit;               // exact pass: up to this many tasks go to k_mutscore_warp (0: never)
     // band storage, wavefront-major: the cells of one anti-diagonal d = k+i of an event are
     // contiguous (slot k % ts), so the fill's per-step stores and the join's loads coalesce
     int               RS;            // 2*realign_width+1 rounded up (serial-fallback smem strips)
@@ -1105,6 +1106,7 @@ __global__ void __launch_bounds__(128) k_mutscore(Batch b)
     double* ring = SMEM ? ring_smem + threadIdx.x : b.scratch + gtid;
     const long long rstride = SMEM ? 128 : nthreads;              // element r at ring[r * rstride]
     const long long n_total = LIST ? (long long)(*b.flag_count) * b.max_ev : b.n_tasks;
+    if (LIST && n_total <= b.warp_limit) return;                   // few flagged pairs: k_mutscore_warp does them
     for (long long t = gtid; t < n_total; t += nthreads)
     {
         int e, m;
@@ -1253,6 +1255,191 @@ __global__ void __launch_bounds__(128) k_mutscore(Batch b)
             result = neu - old;
         }
         b.delta[LIST ? ev.task_off + m : t] = result;
+    }
+}
+
+// k_mutscore_warp: the exact FP64 task of k_mutscore with ONE WARP per (mutation, event) pair, for jobs
+// with few pairs (FindMutations' candidate lists at scoring_width, the flagged re-scores of the FAST mode):
+// a thread-per-pair launch leaves the machine empty there and its run time is the latency of one thread
+// walking (|mut| + 6) x (2W + 1) cells.  Lane c owns narrow column startind + 1 + c and the warp runs the
+// anti-diagonal wavefront: at step s lane c computes row rmin + s - c, its left neighbour (row i of column
+// c-1) is what lane c-1 computed one step earlier and arrives by __shfl_up_sync, the diagonal (row i-1) is
+// the value received the step before, the cell above is the lane's own previous result.  Lane 0 reads the
+// seed column, the last lane joins with the reverse column; level records, seed and reverse cells are
+// requested one step ahead.  Same cell arithmetic (dp_cell, emission) as the thread form: bit-identical.
+// Longer replacement strings run as chunks of 32 columns.  With more than b.warp_limit tasks the kernel is a
+// no-op and the thread form launched beside it does the work, and vice versa (the flagged count only exists
+// on the device).
+template <bool LIST>
+__global__ void __launch_bounds__(128) k_mutscore_warp(Batch b)
+{
+    extern __shared__ double wbuf[];                               // [warps][2][S] hand-over strips (see below)
+    const int S = 2 * b.scoring_width + 2;
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int W = b.scoring_width;
+    const long long n_total = LIST ? (long long)(*b.flag_count) * b.max_ev : b.n_tasks;
+    if (n_total > b.warp_limit) return;
+    for (long long t = gw; t < n_total; t += nwarps)
+    {
+        int e, m;
+        if (LIST ? !list_task(b, t, e, m) : !task_decode(b, t, e, m)) continue;
+        const EvDesc ev = b.ev[e];
+        const MutDev mu = b.muts[ev.mut_off + m];
+        double result = 0.0;
+        if (ev.usable && !((unsigned)mu.start > (unsigned)ev.L))        // cpp/MakeMutations.cpp:46
+        {
+            const int N = ev.N, n0 = ev.n0, L = ev.L;
+            MutView mv;
+            mv.bases = b.bases + ev.base_off; mv.L = L; mv.mstr = b.mut_str + mu.str_off;
+            mv.start = mu.start; mv.n_orig = mu.n_orig; mv.n_mut = mu.n_mut;
+            mv.applied = mu.start < L;
+            mv.Lm = mv.applied ? mu.start + mu.n_mut + max(0, L - mu.start - mu.n_orig) : L;
+            const int Nm = mv.Lm >= 5 ? mv.Lm - 4 : 0;
+            const int raf = max(mu.start - 3, 1);
+            double old;
+            if (raf <= N) old = b.old[ev.col_off + raf];
+            else old = thread_join(b, ev, raf, N - raf + 1);
+            const int startind = max(mu.start - 4, 0);
+            const int refind = mu.start + mu.n_mut + 1;
+            int last = min(min(refind, startind + mu.n_mut + 6), Nm);
+            if (W == 0) last = startind;
+            const int ncol = last - startind;
+            double neu;
+            if (ncol <= 0) neu = thread_join(b, ev, startind, Nm - startind + 1);     // cpp/Alignment.cpp:483-499
+            else
+            {
+                const LevelRec* lev = b.lev + ev.lev_off;
+                const ModelDev& md = b.models[ev.model];
+                const Trans tr = {md.lskip, md.lstay, md.lext, md.lins};
+                const bool ri_empty = b.ri_empty[e] != 0;
+                const long long ts = ev.rs;
+                // reverse column joined with the last narrow column
+                const int rab = min(max(Nm - last + 1, 0), N);
+                const long long gb = ev.col_off + rab;
+                int b0 = 0, blen = n0 + 1;
+                double mb = 0.0;
+                if (rab > 0) { b0 = b.Bi0[gb]; blen = b.Blen[gb]; mb = b.Bbest[gb]; }
+                const double* Bm = b.Bm + col_base(ev, rab);
+                // the column left of the first chunk: the seed column, or the blank column 0
+                int pb0 = 0, pb1 = n0;
+                const double* seed = nullptr;
+                double best = lane == 0 ? 0.0 : NEG, joinmax = 0.0;
+                if (startind > 0)
+                {
+                    const long long gs = ev.col_off + startind;
+                    pb0 = b.Fi0[gs]; pb1 = pb0 + b.Flen[gs] - 1;
+                    seed = b.Fm + col_base(ev, startind);
+                    if (lane == 0) best = b.Fbest[gs];
+                }
+                // more than 32 narrow columns: chunks of 32, the last column of a chunk is handed to the next chunk's
+                // lane 0 through a per-warp strip of shared memory (two strips, alternating)
+                double* bin = wbuf + (size_t)(threadIdx.x >> 5) * 2 * S;
+                double* bout = bin + S;
+                for (int c0 = 0; c0 < ncol; c0 += 32)
+                {
+                    const int ncq = min(32, ncol - c0);
+                    const bool first_chunk = c0 == 0, final_chunk = c0 + 32 >= ncol;
+                    const bool mine = lane < ncq, lastl = final_chunk && lane == ncq - 1, handl = !final_chunk && lane == 31;
+                    // this lane's column
+                    int i0 = 1 << 29, i1 = -(1 << 29), st = -1;
+                    StateParams sp;
+                    if (mine)
+                    {
+                        const int k = startind + 1 + c0 + lane;
+                        band_of(ri_empty ? 1 : b.cen_new[ev.cen_off + k], n0, W, i0, i1);
+                        st = mut_state(mv, k - 1);
+                        sp = md.st[max(st, 0)];
+                    }
+                    else sp = md.st[0];
+                    const bool valid = st >= 0;
+                    // band of the column before: the left lane's, or (lane 0) the column left of the chunk
+                    int p0 = __shfl_up_sync(0xffffffffu, i0, 1), p1 = __shfl_up_sync(0xffffffffu, i1, 1);
+                    if (lane == 0) { p0 = pb0; p1 = pb1; }
+                    const bool have_left = !first_chunk || seed != nullptr;      // lane 0: a stored column exists
+                    int rmin = mine ? i0 : 1 << 29, rmax = mine ? i1 : -(1 << 29);
+                    for (int o = 16; o; o >>= 1)
+                    {
+                        rmin = min(rmin, __shfl_xor_sync(0xffffffffu, rmin, o));
+                        rmax = max(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+                    }
+                    const int nsteps = rmax - rmin + ncq;
+                    double upC = 0.0, upS = 0.0, recv = 0.0, recv_prev = 0.0, Cpub = 0.0;
+                    // requests of the first step; lane 0 follows the column left of the chunk on every step (its
+                    // diagonal is that column's cell of the row before)
+                    int i = rmin - lane;
+                    bool act = mine && i >= i0 && i <= i1;
+                    LevelRec lr = lev[0]; double lsd3 = 0.0, sv = 0.0, bmv = 0.0;
+                    if (lane == 0 && have_left)
+                    {
+                        if (i >= p0 && i <= p1) sv = first_chunk ? seed[row_off(ts, i)] : bin[i - p0];
+                        if (i - 1 >= p0 && i - 1 <= p1) recv_prev = first_chunk ? seed[row_off(ts, i - 1)] : bin[i - 1 - p0];
+                    }
+                    if (act)
+                    {
+                        lr = lev[i - 1]; lsd3 = lev[n0 - i].lsd3;
+                        const int jb = n0 - i + 1;
+                        if (lastl && rab > 0 && jb >= b0 && jb < b0 + blen) bmv = Bm[row_off(ts, jb)];
+                    }
+                    for (int s = 0; s < nsteps; s++)
+                    {
+                        const bool act_c = act;
+                        const int i_c = i;
+                        const LevelRec lr_c = lr;
+                        const double lsd3_c = lsd3, sv_c = sv, bm_c = bmv;
+                        // next step's row: requested now, consumed after this step's cell
+                        i = i_c + 1;
+                        act = mine && i >= i0 && i <= i1;
+                        sv = 0.0; bmv = 0.0;
+                        if (lane == 0 && have_left && i >= p0 && i <= p1) sv = first_chunk ? seed[row_off(ts, i)] : bin[i - p0];
+                        if (act)
+                        {
+                            lr = lev[i - 1]; lsd3 = lev[n0 - i].lsd3;
+                            const int jb = n0 - i + 1;
+                            if (lastl && rab > 0 && jb >= b0 && jb < b0 + blen) bmv = Bm[row_off(ts, jb)];
+                        }
+                        if (act_c)
+                        {
+                            double C = 0.0, Sv = 0.0;
+                            if (valid)
+                            {
+                                const double e_i = emission(lr_c.mean, lr_c.stdv, lr_c.rstdv, lsd3_c, sp, b.log2pi, b.lik_offset);
+                                const bool skip_ok = i_c >= p0 && i_c <= p1;
+                                const bool diag_ok = i_c > p0 && i_c <= p1;
+                                const double Pi = skip_ok ? (lane == 0 ? sv_c : recv) : 0.0;
+                                const double Pd = diag_ok ? recv_prev : 0.0;
+                                int step;
+                                dp_cell(i_c == i0, skip_ok, diag_ok, Pi, Pd, e_i, e_i, upC, upS, tr, C, Sv, step);
+                                if (C > best) best = C;
+                            }
+                            if (lastl)
+                            {
+                                const int jb = n0 - i_c + 1;
+                                if (jb >= b0 && jb < b0 + blen) joinmax = fmax(joinmax, C + bm_c);
+                            }
+                            if (handl) bout[i_c - i0] = C;
+                            upC = C; upS = Sv;
+                            Cpub = C;
+                        }
+                        // hand this step's cell to the right neighbour; what it held becomes its diagonal
+                        recv_prev = lane == 0 ? sv_c : recv;
+                        const double got = __shfl_up_sync(0xffffffffu, Cpub, 1);
+                        if (lane > 0) recv = got;
+                    }
+                    // the chunk's last column becomes the column left of the next chunk
+                    pb0 = __shfl_sync(0xffffffffu, i0, 31); pb1 = __shfl_sync(0xffffffffu, i1, 31);
+                    __syncwarp();
+                    double* tmp = bin; bin = bout; bout = tmp;
+                }
+                // the warp's best cell and the last lane's join
+                for (int o = 16; o; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
+                joinmax = __shfl_sync(0xffffffffu, joinmax, (ncol - 1) & 31);
+                neu = fmax(fmax(joinmax, 0.0), fmax(best, mb));
+            }
+            result = neu - old;
+        }
+        if (lane == 0) b.delta[LIST ? ev.task_off + m : t] = result;
     }
 }
 

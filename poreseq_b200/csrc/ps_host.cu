@@ -174,6 +174,8 @@ int ps_ctx::init()
     CU(cudaFuncSetAttribute(k_fill<160, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     CU(cudaFuncSetAttribute(k_fill<192, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU(cudaFuncSetAttribute(k_fill<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024));
+    CU(cudaFuncSetAttribute(k_mutscore_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CU(cudaFuncSetAttribute(k_mutscore_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU(cudaFuncSetAttribute(k_mutscore<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU(cudaFuncSetAttribute(k_mutscore<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     // the per-thread rings of the exact mutation kernel are what limits its occupancy: ask for the largest shared-memory carve-out
@@ -401,6 +403,7 @@ struct Job
     PinVec<int> rs, re;
     PinVec<double> best, msc;
     bool have_scores = false;
+    int max_nmut = 1;                            // longest replacement string of the job (1 for point edits)
     double* raw_scores = nullptr;
 };
 
@@ -491,7 +494,10 @@ int Job::build()
     for (size_t r = 0; r < regs.size(); r++)
         if (want_muts && muts[r].list)
             for (const HostMut& m : *muts[r].list)
+            {
                 cen_pad = std::max(cen_pad, (int)m.mut.size() - (int)m.orig.size() + 8);
+                max_nmut = std::max(max_nmut, (int)m.mut.size());
+            }
     for (size_t r = 0; r < regs.size(); r++)
     {
         for (const HostEvent& he : regs[r]->events) tot_levels += he.n0;
@@ -723,6 +729,9 @@ int Job::upload()
     b.realign_width = P.realign_width;
     b.scoring_width = P.scoring_width;
     b.cen_pad = cen_pad;
+    // exact pass with one warp per (mutation, event) pair when the pairs are few and no replacement string needs
+    // more than 32 narrow columns (k_mutscore_warp)
+    b.warp_limit = ((size_t)(2 * P.scoring_width + 2) * 8 * sizeof(double) <= 96 * 1024 && !getenv("PORESEQ_B200_NO_WARP")) ? 32768 : 0;
     b.RS = ((2 * P.realign_width + 1) + 3) & ~3;
     b.n_tasks = n_tasks;
 
@@ -916,6 +925,13 @@ int Job::run(bool full)
                 k_flag<<<(unsigned)((n_muts + 127) / 128), 128, 0, ctx->stream>>>(b, n_muts, 1);
                 LAUNCHED();
                 const unsigned rblocks = (unsigned)std::min<long long>(blocks, (long long)ctx->sm_count * 4);
+                // few flagged pairs (the usual case): one warp per pair; many: one thread per pair.  The count only
+                // exists on the device, so both are launched and one of them returns at once.
+                if (b.warp_limit > 0)
+                {
+                    k_mutscore_warp<true><<<(unsigned)ctx->sm_count * 8, threads, ring * 8, ctx->stream>>>(b);
+                    LAUNCHED();
+                }
                 if (in_smem) k_mutscore<true, true><<<rblocks, threads, ring * 128, ctx->stream>>>(b);
                 else
                 {
@@ -930,7 +946,9 @@ int Job::run(bool full)
             }
             else
             {
-                if (in_smem) k_mutscore<true, false><<<(unsigned)blocks, threads, ring * 128, ctx->stream>>>(b);
+                if (b.warp_limit > 0 && n_tasks <= b.warp_limit)
+                    k_mutscore_warp<false><<<(unsigned)std::min<long long>((n_tasks + 3) / 4, (long long)ctx->sm_count * 8), threads, ring * 8, ctx->stream>>>(b);
+                else if (in_smem) k_mutscore<true, false><<<(unsigned)blocks, threads, ring * 128, ctx->stream>>>(b);
                 else
                 {
                     b.scratch_slots = blocks * threads;

@@ -425,3 +425,34 @@ def test_swfull_device_matches_host(ctx, ref):
         assert [tuple(p) for p in pairs] == [tuple(p) for p in want_pairs], (len(a), len(b))
         assert score == want_score
         assert (acc == want_acc) or (np.isnan(acc) and np.isnan(want_acc))
+
+
+@pytest.mark.parametrize("precision", ["exact", "fast"])
+def test_long_replacements_warp_and_thread_forms(orc, monkeypatch, precision):
+    """The exact mutation pass has two forms: one warp per (mutation, event) pair (k_mutscore_warp, chunks of 32
+    narrow columns for long replacement strings) and one thread per pair (k_mutscore).  Both must give the
+    checker's scores bit for bit, for replacement strings from 0 to 100 bases, also at region ends."""
+    reg = region("draft_partial")
+    rng = np.random.default_rng(5)
+    L = len(reg.sequence)
+    st, og, mu = [], [], []
+    for n in (0, 1, 2, 7, 26, 27, 31, 32, 33, 58, 59, 64, 70, 100):
+        for s in (0, 3, int(rng.integers(10, L - 120)), int(rng.integers(10, L - 120)), L - 30, L - 6):
+            k = int(rng.integers(0, 4))
+            st.append(s); og.append(reg.sequence[s:s + k]); mu.append("".join(rng.choice(list("ACGT"), n)))
+    want, want_a = orc.score_mutations(reg, st, og, mu)
+    for no_warp in ("", "1"):
+        if no_warp:
+            monkeypatch.setenv("PORESEQ_B200_NO_WARP", "1")
+        else:
+            monkeypatch.delenv("PORESEQ_B200_NO_WARP", raising=False)
+        c = poreseqcpp.Context(0)
+        c.set_precision(precision)
+        nr = native(c, reg)
+        got = nr.score_mutations(st, og, mu)
+        if precision == "exact":
+            bad = np.nonzero(got != want)[0]
+        else:   # FP32 scan for the single-base edits that are clearly negative, exact for everything else
+            bad = np.nonzero((got != want) & ~((np.array([len(m) for m in mu]) <= 1) & (np.abs(got - want) <= 1e-4 * np.abs(want))))[0]
+        assert len(bad) == 0, (no_warp, [(int(i), st[i], og[i], mu[i], got[i], want[i]) for i in bad[:8]])
+        assert same_aligns(native_aligns(nr, reg), want_a)
