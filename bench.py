@@ -53,26 +53,38 @@ def measured_peaks():
     return 6650.0, 1965.0, "fallback"
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+class ClockSampler(object):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe): ONE nvidia-smi
+    process looping with -lms 200, started before the timed region and stopped after it (a fresh nvidia-smi
+    per sample re-initialises NVML every time, which holds up the CUDA calls of every process on the box)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.samples, self.proc = index, [], None
 
-    def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 6:
-                    self.samples.append(f)
-            except Exception:
-                pass
-            time.sleep(0.1)
+    def start(self):
+        if os.environ.get("BENCH_NO_SAMPLER"):
+            return
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return
+        try:
+            self.proc.terminate()
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            out = ""
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 6:
+                self.samples.append(f)
 
     def summary(self):
         if not self.samples:
@@ -359,7 +371,10 @@ def main():
             out = end(begin(ctxs[0]), record)
         return out
 
-    out = run_steps(max(args.warmup, 3), False)
+    # warm-up: at least W steps and at least two on every context (each context owns its staging and device buffers,
+    # which grow on first use)
+    n_warm = max(args.warmup, 3, 2 * len(ctxs))
+    out = run_steps(n_warm, False)
     d2h = sum(8 * len(o[3]) for o in out) + sum(2 * 8 * len(ev.mean) for r in regions for ev in r.events)
 
     sampler = ClockSampler(local_rank)
@@ -378,8 +393,7 @@ def main():
     barrier()
     wall = time.perf_counter() - t0
     launches = sum(c.launch_count() for c in ctxs) - launches0
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
+    sampler.stop()
 
     kernel_keys = ["centres", "forward", "backward", "backtrace", "join", "mutscore", "reduce"]
     dev_ms = sum(phase[k] for k in kernel_keys) / args.steps
@@ -414,7 +428,7 @@ def main():
     fp64_achieved = dom_cells * fp64_per_cell / dom_s / 1e12 if dom_s > 0 else 0.0
     line = {
         "metric": METRIC, "value": total_cells / (dev_ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": wall_ms, "higher_is_better": True,
+        "steps": args.steps, "warmup": n_warm, "ms_per_step": wall_ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64" if args.precision == "fast" else "f64", "data": "synthetic",
         "config": {"workload": "ScorePoints (FindPointMutations+ScoreMutations) on 1 kb regions x 10x coverage, "
                                "point_width 20, realign_width 300 (BASELINE.json configs[1])",
