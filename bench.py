@@ -308,6 +308,12 @@ def main():
         run_reference_arm(args, rank, world)
         return
 
+    # the library's host worker threads (marshalling, per-level logs, band planning): share the box's cores between
+    # the ranks of this node instead of 8 per rank (PORESEQ_B200_THREADS is the library's own knob)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    if "PORESEQ_B200_THREADS" not in os.environ:
+        os.environ["PORESEQ_B200_THREADS"] = str(max(1, min(8, (os.cpu_count() or 8) // max(local_world, 1))))
+
     import torch
     import torch.distributed as dist
     from poreseq_b200 import build, poreseqcpp
@@ -435,6 +441,7 @@ def main():
                    "regions_per_gpu_per_step": args.regions, "events_per_region": 2 * COVERAGE,
                    "mutations_per_region": 8 * (REGION_LEN - 4), "cells_per_step_per_gpu": step_cells,
                    "l2": "band working set %.0f MB per step exceeds the 126 MB L2" % (wide_cells * 16.5 / 1e6),
+                   "host_threads_per_rank": int(os.environ["PORESEQ_B200_THREADS"]),
                    "pipelining": "%d contexts: host staging and H2D of the next steps overlap the kernels of step k" % len(ctxs),
                    "precision": ("fp32 mutation scan + exact fp64 re-score of all candidates > -tau; wide fills/backtrace fp64"
                                  if args.precision == "fast" else "fp64 exact (bit-identical to the reference)")},

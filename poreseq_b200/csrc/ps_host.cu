@@ -635,18 +635,41 @@ int Job::build()
     ps_parallel_for(ne, [&](int e) {
         HostEvent& he = *const_cast<HostEvent*>(hev[e]);
         const EvDesc& d = ev[e];
-        he.ensure_levrec();
         const size_t at = (size_t)d.lev_off, n = (size_t)he.n0;
-        memcpy(lev.data() + at, he.levrec.data(), n * sizeof(LevelRec));
-        if (fast)
+        if (he.staged++ == 0 && he.levrec.empty())
         {
-            // row records of the FP32 scan: row i reads level i-1 and the log stdv term of level n0-i
-            LevelRecF* out = levf.data() + at;
-            const float* src = he.levrecf.data();
+            // first batch of this event: level records (log(stdv), cpp/EventData.h:218-220) straight into the staging
+            // buffers; an event that comes back (Refine's recursion, the consensus loop) caches them next time
+            LevelRec* out = lev.data() + at;
+            LevelRecF* outf = fast ? levf.data() + at : nullptr;
+            const double* mean = he.mean.data();
+            const double* stdv = he.stdv.data();
             for (size_t k = 0; k < n; k++)
             {
-                out[k].x = src[4 * k]; out[k].y = src[4 * k + 1]; out[k].ry = src[4 * k + 2];
-                out[k].ey = src[4 * (n - 1 - k) + 3];
+                const double lsd = std::log(stdv[k]);
+                const double r = 1.0 / stdv[k];
+                out[k].mean = mean[k]; out[k].stdv = stdv[k]; out[k].rstdv = r; out[k].lsd3 = 3 * lsd;
+                if (outf)
+                {
+                    // row records of the FP32 scan: row i reads level i-1 and the log stdv term of level n0-i
+                    outf[k].x = (float)mean[k]; outf[k].y = (float)stdv[k]; outf[k].ry = (float)r;
+                    outf[n - 1 - k].ey = (float)(-1.5 * lsd);
+                }
+            }
+        }
+        else
+        {
+            he.ensure_levrec();
+            memcpy(lev.data() + at, he.levrec.data(), n * sizeof(LevelRec));
+            if (fast)
+            {
+                LevelRecF* out = levf.data() + at;
+                const float* src = he.levrecf.data();
+                for (size_t k = 0; k < n; k++)
+                {
+                    out[k].x = src[4 * k]; out[k].y = src[4 * k + 1]; out[k].ry = src[4 * k + 2];
+                    out[k].ey = src[4 * (n - 1 - k) + 3];
+                }
             }
         }
         memcpy(ref_align.data() + at, he.ref_align.data(), n * sizeof(double));

@@ -75,6 +75,7 @@ struct HostEvent                              // cpp/EventData.h:78-229
     std::vector<double> mean, stdv, ref_align, ref_like, ref_index;
     std::vector<double> levrec;               // 4 doubles per level, the device LevelRec layout (built on first use)
     std::vector<float> levrecf;               // 4 floats per level, the device LevelRecF layout
+    int staged = 0;                           // batches this event was staged for (the level records are cached from the second on)
     std::string seq2d;
     void update_refs();
     void ensure_levrec();                     // log(stdv) etc. (cpp/EventData.h:218-220), cached
