@@ -177,6 +177,9 @@ def consensus_gpu(length, coverage, seed):
             "config": "consensus loop on a %d b region at %dx coverage (draft with 10%% errors), fast precision" % (length, coverage)}, seq
 
 
+CONS_REGIONS = 64          # per GPU (32 left the tail of the last regions in flight visible: 17-23 kb/s run to run)
+
+
 def consensus_throughput(ctxs, n_regions, length, coverage, seed0):
     """Consensus loops of several regions at once on one GPU: one host thread and one context (stream) per
     region in flight -- the reference's own scaling model (one process per region file, README.md:48-54)
@@ -424,9 +427,10 @@ def main():
     clock_mhz = clocks["sm_mhz"] or sm_max_mhz
     peak_ops = sms * 128 * sm_max_mhz * 1e6 / 1e12                  # T lane-ops/s at max clock
     achieved_ops = dom_cells * OPS_PER_CELL / dom_s / 1e12 if dom_s > 0 else 0.0
-    # algorithmic bytes of the dominant kernel: the wide fill writes 2 matrices x 8 B per
-    # cell plus 1 step byte per forward cell; the mutation kernel reads 8 B seed + 16 B join rows per band row
-    dom_bytes = {"forward": wide_cells * 16.5, "mutscore": narrow_cells / 5.875 * 24.0}.get(dom, 0.0)
+    # algorithmic bytes of the dominant kernel: the wide fill writes main + stay matrix and a step
+    # byte per forward cell (16.5 B) and the main matrix per reverse cell (8 B): 12.25 B per cell over both directions;
+    # the mutation kernel reads 8 B seed + 8 B reverse cell per band row
+    dom_bytes = {"forward": wide_cells * 12.25, "mutscore": narrow_cells / 5.875 * 16.0}.get(dom, 0.0)
     # the fill is FP64 (exact): 45 FP64-pipe instructions per cell against the FP64 pipe of the SMs
     # (64 lanes per SM; profiles/r1_fp64_ubench.txt measures 0.43 warp-instructions per cycle per scheduler)
     fp64_peak = sms * 64 * sm_max_mhz * 1e6 / 1e12
@@ -440,7 +444,7 @@ def main():
                                "point_width 20, realign_width 300 (BASELINE.json configs[1])",
                    "regions_per_gpu_per_step": args.regions, "events_per_region": 2 * COVERAGE,
                    "mutations_per_region": 8 * (REGION_LEN - 4), "cells_per_step_per_gpu": step_cells,
-                   "l2": "band working set %.0f MB per step exceeds the 126 MB L2" % (wide_cells * 16.5 / 1e6),
+                   "l2": "band working set %.0f MB per step exceeds the 126 MB L2" % (wide_cells * 12.25 / 1e6),
                    "host_threads_per_rank": int(os.environ["PORESEQ_B200_THREADS"]),
                    "pipelining": "%d contexts: host staging and H2D of the next steps overlap the kernels of step k" % len(ctxs),
                    "precision": ("fp32 mutation scan + exact fp64 re-score of all candidates > -tau; wide fills/backtrace fp64"
@@ -467,7 +471,7 @@ def main():
                          "peak_source": peak_src, "traffic": recorded_traffic(dom_kernel, args.regions)},
     }
     if not args.no_consensus:
-        # consensus kb/s, throughput form, on every rank: 32 regions of 1 kb x 10x per GPU, 8 in flight
+        # consensus kb/s, throughput form, on every rank: CONS_REGIONS regions of 1 kb x 10x per GPU, 8 in flight
         for c in ctxs:
             c.close()
         cons_ctxs = [poreseqcpp.Context(local_rank) for _ in range(8)]
@@ -475,17 +479,17 @@ def main():
             c.set_precision("fast")
         consensus_throughput(cons_ctxs, 8, 1000, 10, seed0=9000)       # untimed: every context allocates its buffers
         barrier()
-        dt, acc = consensus_throughput(cons_ctxs, 32, 1000, 10, seed0=500 + 32 * rank)
+        dt, acc = consensus_throughput(cons_ctxs, CONS_REGIONS, 1000, 10, seed0=500 + CONS_REGIONS * rank)
         for c in cons_ctxs:
             c.close()
         tt = torch.tensor([dt, acc], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tt[0:1], op=dist.ReduceOp.MAX)
             dist.all_reduce(tt[1:2], op=dist.ReduceOp.SUM)
-        line["consensus"] = {"throughput": {"value": 32.0 * world / tt[0].item(), "unit": "kb/s", "n_gpus": world,
+        line["consensus"] = {"throughput": {"value": float(CONS_REGIONS) * world / tt[0].item(), "unit": "kb/s", "n_gpus": world,
                                             "seconds": tt[0].item(), "mean_accuracy_pct": tt[1].item() / world,
-                                            "config": "consensus loop (Mutate.py policy) on 32 regions of 1 kb x 10x per GPU "
-                                                      "(drafts with 10% errors), 8 regions in flight per GPU, fast precision"}}
+                                            "config": "consensus loop (Mutate.py policy) on %d regions of 1 kb x 10x per GPU "
+                                                      "(drafts with 10%% errors), 8 regions in flight per GPU, fast precision" % CONS_REGIONS}}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = run_cpu_baseline()
