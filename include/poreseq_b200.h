@@ -82,6 +82,8 @@ long long   ps_launch_count(ps_ctx* ctx);
 int         ps_set_precision(ps_ctx* ctx, int mode);
 int         ps_last_timing(ps_ctx* ctx, double* ms /*PS_T_COUNT*/);
 int         ps_last_cells(ps_ctx* ctx, double* wide_cells, double* narrow_cells);
+/* Bytes the last batch copied host->device and device->host (cudaMemcpyAsync payloads). */
+int         ps_last_bytes(ps_ctx* ctx, long long* h2d_bytes, long long* d2h_bytes);
 
 /* ---- region = AlignData (cpp/AlignData.h:24-34) ------------------------------------------ */
 ps_region*  ps_region_create(ps_ctx* ctx, const char* bases, int len, const ps_params* params);

@@ -57,7 +57,8 @@ struct Batch                  // everything the kernels need, passed by value
     const int*        states;
     const char*       bases;
     // per level
-    const LevelRec*   lev;
+    LevelRec*         lev;
+    const LevIn*       lev_in;                  // staged by the host; k_rows builds lev / rowF / rowB / levf from it
     double*           ref_align;
     double*           ref_like;
     double*           ref_index;
@@ -103,7 +104,7 @@ struct Batch                  // everything the kernels need, passed by value
     int               scoring_width;
     // FP32 fast pass + exact re-score of the candidates that matter (ps_fast.cuh)
     const StateParamsF* stf;                    // [models][1024]
-    const LevelRecF*  levf;                     // per level
+    LevelRecF*        levf;                     // per level
     const float4*     trf;                      // per model: log skip, stay, extend, insert
     const RegTabDev*  regs;                     // per region
     int               n_regs;
@@ -334,19 +335,32 @@ __global__ void k_strips(Batch b)
     b.strips[ev.strip_off + (rev ? J + 1 : 0) + j] = r;
 }
 
-// k_rows: the level record each fill row reads, per direction (quirk A.3-1: the forward pass pairs
-// stdv[i-1] with log_stdv[n0-i], cpp/Alignment.cpp:171-172)
+// k_rows: expands the staged (mean, stdv, 3 log stdv) of every level into the records the kernels read: the level
+// record with RN(1/stdv), the record each fill row reads per direction (quirk A.3-1: the forward pass pairs
+// stdv[i-1] with log_stdv[n0-i], cpp/Alignment.cpp:171-172) and the FP32 row record of the mutation scan
 __global__ void k_rows(Batch b)
 {
     const EvDesc ev = b.ev[blockIdx.y];
     if (!ev.usable) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;       // row 1..n0
     if (i > ev.n0) return;
-    const LevelRec* lev = b.lev + ev.lev_off;
-    LevelRec f = lev[i - 1];
-    f.lsd3 = lev[ev.n0 - i].lsd3;
+    const LevIn* in = b.lev_in + ev.lev_off;
+    const LevIn a = in[i - 1], q = in[ev.n0 - i];
+    LevelRec f;
+    f.mean = a.mean; f.stdv = a.stdv; f.rstdv = 1.0 / a.stdv; f.lsd3 = a.lsd3;     // IEEE division: RN(1 / stdv)
+    b.lev[ev.lev_off + i - 1] = f;
+    LevelRec r;
+    r.mean = q.mean; r.stdv = q.stdv; r.rstdv = 1.0 / q.stdv; r.lsd3 = q.lsd3;
+    b.rowB[ev.lev_off + i - 1] = r;
+    f.lsd3 = q.lsd3;
     b.rowF[ev.lev_off + i - 1] = f;
-    b.rowB[ev.lev_off + i - 1] = lev[ev.n0 - i];
+    if (b.levf)
+    {
+        // FP32 row record of the scan: -1.5 log(stdv) = -0.5 * (3 log stdv), exact halving
+        LevelRecF g;
+        g.x = (float)f.mean; g.y = (float)f.stdv; g.ry = (float)f.rstdv; g.ey = (float)(-0.5 * q.lsd3);
+        b.levf[ev.lev_off + i - 1] = g;
+    }
 }
 
 struct FillOut               // where one direction's band columns go

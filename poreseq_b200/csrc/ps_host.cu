@@ -306,18 +306,12 @@ void HostEvent::update_refs()                                // cpp/EventData.h:
 
 void HostEvent::ensure_levrec()
 {
-    if (levrec.size() == (size_t)n0 * 4) return;
-    levrec.resize((size_t)n0 * 4);
-    levrecf.resize((size_t)n0 * 4);
+    if (levrec.size() == (size_t)n0 * 3) return;
+    levrec.resize((size_t)n0 * 3);
     for (int i = 0; i < n0; i++)
     {
-        const double lsd = std::log(stdv[i]);                                // cpp/EventData.h:218-220
-        const double r = 1.0 / stdv[i];
-        // device level record: mean, stdv, RN(1/stdv), 3*log(stdv)  (psdev::LevelRec)
-        levrec[4 * i] = mean[i]; levrec[4 * i + 1] = stdv[i]; levrec[4 * i + 2] = r; levrec[4 * i + 3] = 3 * lsd;
-        // FP32 twin (psdev::LevelRecF): mean, stdv, 1/stdv, -1.5 log(stdv)
-        levrecf[4 * i] = (float)mean[i]; levrecf[4 * i + 1] = (float)stdv[i];
-        levrecf[4 * i + 2] = (float)r; levrecf[4 * i + 3] = (float)(-1.5 * lsd);
+        // staged level record (psdev::LevIn): mean, stdv, 3*log(stdv)  (cpp/EventData.h:218-220)
+        levrec[3 * i] = mean[i]; levrec[3 * i + 1] = stdv[i]; levrec[3 * i + 2] = 3 * std::log(stdv[i]);
     }
 }
 
@@ -362,8 +356,7 @@ struct Job
     PinVec<EvDesc> ev;
     PinVec<int> states;
     PinVec<char> bases;
-    PinVec<LevelRec> lev;
-    PinVec<LevelRecF> levf;
+    PinVec<LevIn> lev;
     bool fast = false;                           // FP32 pass + exact re-score (PS_PRECISION_FAST)
     int max_ev = 1;
     PinVec<double> ref_align, ref_like, ref_index;
@@ -387,7 +380,7 @@ struct Job
     Job(ps_ctx* c) : ctx(c), want_muts(false), n_levels(0), n_cols(0), n_cen(0), n_tasks(0), n_muts(0), n_band(0), cen_pad(8)
     {
         ev = c->pinned<EvDesc>("ev"); states = c->pinned<int>("states"); bases = c->pinned<char>("bases");
-        lev = c->pinned<LevelRec>("lev"); levf = c->pinned<LevelRecF>("levf"); ref_align = c->pinned<double>("ref_align");
+        lev = c->pinned<LevIn>("lev"); ref_align = c->pinned<double>("ref_align");
         ref_like = c->pinned<double>("ref_like"); ref_index = c->pinned<double>("ref_index");
         ri_empty = c->pinned<int>("ri_empty"); mono = c->pinned<int>("mono"); cen_old = c->pinned<int>("cen_old");
         mdev = c->pinned<MutDev>("mdev"); mut_str = c->pinned<char>("mut_str"); regtab = c->pinned<RegTab>("regtab");
@@ -505,7 +498,7 @@ int Job::build()
         tot_cen += regs[r]->events.size() * (regs[r]->states.size() + cen_pad + 1);
         if (want_muts) tot_muts += muts[r].points ? regs[r]->states.size() * 9 : muts[r].list->size();
     }
-    if (!lev.resize(tot_levels) || !(fast ? levf.resize(tot_levels) : true) || !ref_align.resize(tot_levels) ||
+    if (!lev.resize(tot_levels) || !ref_align.resize(tot_levels) ||
         !ref_like.resize(tot_levels) || !ref_index.resize(tot_levels) || !states.reserve(tot_states) ||
         !bases.reserve(tot_bases) || !ev.reserve(tot_events) || !mdev.reserve(tot_muts) || !ri_empty.resize(tot_events) ||
         !mono.resize(tot_events) || !cen_old.resize(tot_cen) || !regtab.reserve(regs.size()))
@@ -638,45 +631,22 @@ int Job::build()
         const size_t at = (size_t)d.lev_off, n = (size_t)he.n0;
         if (he.staged++ == 0 && he.levrec.empty())
         {
-            // first batch of this event: level records (log(stdv), cpp/EventData.h:218-220) straight into the staging
-            // buffers; an event that comes back (Refine's recursion, the consensus loop) caches them next time
-            LevelRec* out = lev.data() + at;
-            LevelRecF* outf = fast ? levf.data() + at : nullptr;
+            // first batch of this event: (mean, stdv, 3 log stdv) straight into the staging buffer (the log is the only
+            // transcendental of the path, cpp/EventData.h:218-220); an event that comes back (Refine's recursion, the
+            // consensus loop) caches them next time.  1/stdv and the FP32 records are derived on the device (k_rows).
+            LevIn* out = lev.data() + at;
             const double* mean = he.mean.data();
             const double* stdv = he.stdv.data();
-            for (size_t k = 0; k < n; k++)
-            {
-                const double lsd = std::log(stdv[k]);
-                const double r = 1.0 / stdv[k];
-                out[k].mean = mean[k]; out[k].stdv = stdv[k]; out[k].rstdv = r; out[k].lsd3 = 3 * lsd;
-                if (outf)
-                {
-                    // row records of the FP32 scan: row i reads level i-1 and the log stdv term of level n0-i
-                    outf[k].x = (float)mean[k]; outf[k].y = (float)stdv[k]; outf[k].ry = (float)r;
-                    outf[n - 1 - k].ey = (float)(-1.5 * lsd);
-                }
-            }
+            for (size_t k = 0; k < n; k++) { out[k].mean = mean[k]; out[k].stdv = stdv[k]; out[k].lsd3 = 3 * std::log(stdv[k]); }
         }
         else
         {
             he.ensure_levrec();
-            memcpy(lev.data() + at, he.levrec.data(), n * sizeof(LevelRec));
-            if (fast)
-            {
-                LevelRecF* out = levf.data() + at;
-                const float* src = he.levrecf.data();
-                for (size_t k = 0; k < n; k++)
-                {
-                    out[k].x = src[4 * k]; out[k].y = src[4 * k + 1]; out[k].ry = src[4 * k + 2];
-                    out[k].ey = src[4 * (n - 1 - k) + 3];
-                }
-            }
+            memcpy(lev.data() + at, he.levrec.data(), n * sizeof(LevIn));
         }
-        memcpy(ref_align.data() + at, he.ref_align.data(), n * sizeof(double));
-        memcpy(ref_like.data() + at, he.ref_like.data(), n * sizeof(double));
-        if (he.ri_empty) std::fill(ref_index.data() + at, ref_index.data() + at + n, 0.0);
-        else memcpy(ref_index.data() + at, he.ref_index.data(), n * sizeof(double));
-        ri_empty[e] = he.ri_empty ? 1 : 0;
+        // ref_align / ref_like / ref_index are outputs of the device (k_backtrace rewrites them for every usable
+        // event, the band centres of the fill are planned here on the host): nothing to stage or upload
+        ri_empty[e] = (he.ri_empty || !d.usable) ? 1 : 0;
         int ok = 1;
         plan_event(he, d, rw, cen_old.data() + d.cen_off, &ok, &wave_need[e], &ev_cells[e]);
         // the wavefront fill assumes log(prob_skip) <= 0 and log(prob_insert) <= 0 (see fill_wave / cell_pre)
@@ -726,6 +696,7 @@ static int up(ps_ctx* ctx, const char* name, const T* src, size_t count, T** out
     int rc = ctx->ensure(buf, std::max<size_t>(count, 1) * sizeof(T));
     if (rc) return rc;
     if (count) CU(cudaMemcpyAsync(buf.p, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h2d_bytes += (long long)(count * sizeof(T));
     *out = (T*)buf.p;
     return PS_OK;
 }
@@ -763,20 +734,21 @@ int Job::upload()
     ps_parallel_for((int)model_src.size(), [&](int q) { ps_build_model(*model_src[q], models[q]); });
 
     EvDesc* d_ev; ModelDev* d_models; int* d_states; char* d_bases;
-    LevelRec* d_lev;
+    LevIn* d_lev;
     TRY(up(ctx, "ev", ev.data(), ev.size(), &d_ev));
     TRY(up(ctx, "models", models.data(), models.size(), &d_models));
     TRY(up(ctx, "states", states.data(), states.size(), &d_states));
     TRY(up(ctx, "bases", bases.data(), bases.size(), &d_bases));
     TRY(up(ctx, "lev", lev.data(), lev.size(), &d_lev));
-    TRY(up(ctx, "ref_align", ref_align.data(), ref_align.size(), &b.ref_align));
-    TRY(up(ctx, "ref_like", ref_like.data(), ref_like.size(), &b.ref_like));
-    TRY(up(ctx, "ref_index", ref_index.data(), ref_index.size(), &b.ref_index));
+    TRY(room(ctx, "ref_align", ref_align.size(), &b.ref_align));
+    TRY(room(ctx, "ref_like", ref_like.size(), &b.ref_like));
+    TRY(room(ctx, "ref_index", ref_index.size(), &b.ref_index));
     TRY(up(ctx, "ri_empty", ri_empty.data(), ri_empty.size(), &b.ri_empty));
     TRY(up(ctx, "mono", mono.data(), mono.size(), &b.mono));
     { int* fl; TRY(up(ctx, "fill_list", fill_list.data(), fill_list.size(), &fl)); b.fill_list = fl; }
     b.ev = d_ev; b.models = d_models; b.states = d_states; b.bases = d_bases;
-    b.lev = d_lev;
+    b.lev_in = d_lev;
+    TRY(room(ctx, "lev_rec", (size_t)std::max<long long>(n_levels, 1), &b.lev));
     TRY(room(ctx, "bt_src", (size_t)n_levels, &b.bt_src));
     TRY(room(ctx, "refstart", ev.size(), &b.refstart));
     TRY(room(ctx, "refend", ev.size(), &b.refend));
@@ -844,11 +816,11 @@ int Job::upload()
                 }
                 trf[q] = make_float4((float)md.lskip, (float)md.lstay, (float)md.lext, (float)md.lins);
             }
-            StateParamsF* d_stf; float4* d_trf; LevelRecF* d_levf;
+            StateParamsF* d_stf; float4* d_trf;
             TRY(up(ctx, "stf", stf.data(), stf.size(), &d_stf));
             TRY(up(ctx, "trf", trf.data(), trf.size(), &d_trf));
-            TRY(up(ctx, "levf", levf.data(), levf.size(), &d_levf));
-            b.stf = d_stf; b.trf = d_trf; b.levf = d_levf;
+            TRY(room(ctx, "levf", (size_t)std::max<long long>(n_levels, 1), &b.levf));
+            b.stf = d_stf; b.trf = d_trf;
             b.tau = 0.02 + 5e-4 * max_ev;
         }
     }
@@ -1016,7 +988,9 @@ int Job::download_enqueue()
         CU(cudaMemcpyAsync(re.data(), b.refend, ne * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaMemcpyAsync(best.data(), d_evbest, ne * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     }
+    ctx->d2h_bytes += (long long)(3 * nl * sizeof(double) + ne * (3 * sizeof(int) + sizeof(double)));
     have_scores = want_muts && n_muts && n_tasks;
+    if (have_scores) ctx->d2h_bytes += (long long)((size_t)n_muts * sizeof(double));
     if (have_scores)
         CU(cudaMemcpyAsync(msc.data(), b.scores, (size_t)n_muts * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     MARK(PS_T_TOTAL);
@@ -1095,6 +1069,7 @@ static int job_begin(ps_ctx* ctx, const std::vector<ps_region*>& regs, const std
     const bool trace = getenv("PORESEQ_B200_TRACE") != nullptr;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = now();
+    ctx->h2d_bytes = 0; ctx->d2h_bytes = 0;
     int rc = job->build();
     const double t1 = now();
     if (!rc) rc = (cudaEventRecord(ctx->tev[PS_T_H2D], ctx->stream) == cudaSuccess) ? PS_OK : PS_E_CUDA;
@@ -1312,6 +1287,14 @@ int ps_last_timing(ps_ctx* ctx, double* ms)
 {
     if (!ctx || !ms) return PS_E_ARG;
     for (int i = 0; i < PS_T_COUNT; i++) ms[i] = ctx->timing[i];
+    return PS_OK;
+}
+
+int ps_last_bytes(ps_ctx* ctx, long long* h2d, long long* d2h)
+{
+    if (!ctx) return PS_E_ARG;
+    if (h2d) *h2d = ctx->h2d_bytes;
+    if (d2h) *d2h = ctx->d2h_bytes;
     return PS_OK;
 }
 

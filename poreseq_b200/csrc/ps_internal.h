@@ -47,6 +47,7 @@ struct ps_ctx
     cudaEvent_t tev[PS_T_COUNT + 1];
     double timing[PS_T_COUNT] = {0};
     double wide_cells = 0, narrow_cells = 0;
+    long long h2d_bytes = 0, d2h_bytes = 0;   // bytes the last batch copied to / from the device
     long long launches = 0;
     void* pending = nullptr;                  // the batch in flight between *_begin and *_end (a Job)
     std::string error;
@@ -73,8 +74,7 @@ struct HostEvent                              // cpp/EventData.h:78-229
     bool ri_empty = true;
     int refstart = -1, refend = -1;
     std::vector<double> mean, stdv, ref_align, ref_like, ref_index;
-    std::vector<double> levrec;               // 4 doubles per level, the device LevelRec layout (built on first use)
-    std::vector<float> levrecf;               // 4 floats per level, the device LevelRecF layout
+    std::vector<double> levrec;               // 3 doubles per level, the staged LevIn layout (mean, stdv, 3 log stdv), cached
     int staged = 0;                           // batches this event was staged for (the level records are cached from the second on)
     std::string seq2d;
     void update_refs();

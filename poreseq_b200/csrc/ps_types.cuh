@@ -24,6 +24,12 @@ struct LevelRec               // one 32-byte record per event level (cpp/EventDa
     double lsd3;                       // 3 * log(stdv)
 };
 
+struct LevIn                  // what the host stages per level: 24 bytes; k_rows expands it into the records above/below
+{
+    double mean, stdv;
+    double lsd3;                       // 3 * log(stdv), host libm (the only transcendental of the path, cpp/EventData.h:220)
+};
+
 struct StateParamsF           // FP32 fused emission coefficients of one state (ps_fast.cuh)
 {
     float mu;                          // lev_mean

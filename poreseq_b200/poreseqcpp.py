@@ -59,6 +59,7 @@ def lib():
     L.ps_set_precision.argtypes = [C.c_void_p, C.c_int]
     L.ps_last_timing.argtypes = [C.c_void_p, _c_double_p]
     L.ps_last_cells.argtypes = [C.c_void_p, _c_double_p, _c_double_p]
+    L.ps_last_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     L.ps_region_create.restype = C.c_void_p
     L.ps_region_create.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(PSParams)]
     L.ps_region_destroy.argtypes = [C.c_void_p]
@@ -134,6 +135,12 @@ class Context(object):
         ms = (C.c_double * len(PS_T_NAMES))()
         self.check(self.lib.ps_last_timing(self.handle, ms))
         return dict(zip(PS_T_NAMES, list(ms)))
+
+    def last_bytes(self):
+        """(host->device, device->host) bytes copied by the last batch on this context."""
+        h, d = C.c_longlong(0), C.c_longlong(0)
+        self.check(self.lib.ps_last_bytes(self.handle, C.byref(h), C.byref(d)))
+        return h.value, d.value
 
     def last_cells(self):
         w, n = C.c_double(0), C.c_double(0)
