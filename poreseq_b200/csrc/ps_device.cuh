@@ -820,119 +820,112 @@ __device__ void dev_updaterefs(const double* ra, double* ri, int n0, int& empty,
     }
 }
 
-// k_backtrace: one CTA per event.  The best path is followed from the best cell through the packed
-// step bytes (cpp/Alignment.cpp:516-605).  A pointer chase through global memory costs one L2 round
-// trip per move, so the CTA stages a window of step bytes (BT_D anti-diagonals x BT_C columns
-// ending at the current cell) into shared memory with coalesced loads, thread 0 walks inside it,
-// and the window is re-staged where the walk leaves it.  Every visited level records its column
-// and matrix; the CTA then gathers ref_like in parallel and thread 0 rebuilds ref_index.
-constexpr int BT_D = 128, BT_C = 64;
+// k_backtrace: one WARP per event.  The best path is followed from the best cell through the packed step
+// bytes (cpp/Alignment.cpp:516-605).  A pointer chase through global memory costs one memory round trip
+// per move, so the warp fetches a block of 8 columns x 16 rows below and left of the current cell in one
+// go -- in the wavefront-major layout a 2x2 tile is one 32-bit word of step bytes, lane l takes the tile of
+// (strip s_hi - (l & 3), row pair r_hi - (l >> 2)) -- walks inside the block with the words handed around
+// by __shfl_sync (the walk itself is uniform across the warp), and fetches the next block where the walk
+// leaves this one: one round trip per ~10 moves.  Every visited level records its column and matrix; the
+// warp then gathers ref_like in parallel and lane 0 rebuilds ref_index.  BT_WARPS events per CTA, their
+// per-level scratch in shared memory when the events fit.
+constexpr int BT_WARPS = 4;
 
-__global__ void __launch_bounds__(256) k_backtrace(Batch b, int smem_levels)
+__global__ void __launch_bounds__(32 * BT_WARPS) k_backtrace(Batch b, int smem_levels, int warps_per_cta)
 {
     extern __shared__ double bt_dyn[];
-    const EvDesc ev = b.ev[blockIdx.x];
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int e = blockIdx.x * warps_per_cta + wrp;
+    if (wrp >= warps_per_cta || e >= b.n_events) return;
+    const EvDesc ev = b.ev[e];
     if (!ev.usable) return;
-    const int n0 = ev.n0, N = ev.N, tid = threadIdx.x;
+    const int n0 = ev.n0, N = ev.N;
     double* ra = b.ref_align + ev.lev_off;
     double* rl = b.ref_like + ev.lev_off;
     double* ri = b.ref_index + ev.lev_off;
     // the per-level scratch of the walk lives in shared memory when the event fits
     const bool in_smem = n0 <= smem_levels;
-    double* val = in_smem ? bt_dyn : ra;
-    int* src = in_smem ? (int*)(bt_dyn + smem_levels) : b.bt_src + ev.lev_off;
-    __shared__ uint8_t win[BT_D][BT_C];
-    __shared__ int w_i0[BT_C], w_i1[BT_C];
-    __shared__ int s_i, s_j, s_arr, s_go, s_empty;
-    for (int i = tid; i < n0; i += blockDim.x) { val[i] = 0.0; src[i] = 0; }
-    if (tid == 0)
+    double* val = in_smem ? bt_dyn + (size_t)wrp * smem_levels : ra;
+    int* src = in_smem ? (int*)(bt_dyn + (size_t)warps_per_cta * smem_levels) + (size_t)wrp * smem_levels : b.bt_src + ev.lev_off;
+    for (int i = lane; i < n0; i += 32) { val[i] = 0.0; src[i] = 0; }
+    __syncwarp();
+    int i = N > 0 ? b.Fbi[ev.col_off + N] : 0, j = N > 0 ? b.Fbj[ev.col_off + N] : 0, arr = 0;
+    bool go = i > 0 && j > 0;
+    const int ts = ev.ts;
+    while (go)
     {
-        s_i = N > 0 ? b.Fbi[ev.col_off + N] : 0;
-        s_j = N > 0 ? b.Fbj[ev.col_off + N] : 0;
-        s_arr = 0;
-        s_go = (s_i > 0 && s_j > 0) ? 1 : 0;
-    }
-    __syncthreads();
-    while (s_go)
-    {
-        const int ktop = s_j, dtop = s_j + s_i;
-        const int kbot = ktop - BT_C + 1;                 // columns kbot..ktop, diagonals dtop-BT_D+1..dtop
-        __syncthreads();                                  // everyone has read the walk position
-        for (int q = tid; q < BT_C; q += blockDim.x)
+        // block of strips s_hi-3 .. s_hi and row pairs r_hi-7 .. r_hi around the current cell (its top right corner)
+        const int s_hi = (j - 1) >> 1, r_hi = (i - 1) >> 1;
+        const int s = s_hi - (lane & 3), r = r_hi - (lane >> 2);
+        unsigned word = (unsigned)ST_STOP * 0x01010101u;
+        if (s >= 0 && r >= 0)
+            word = *reinterpret_cast<const unsigned*>(b.Fstep + ev.band_off + ((long long)(s + r) * ts + (s % ts)) * 4);
+        // bands of the block's 8 columns: lane c holds column 2 (s_hi - 3) + 1 + c
+        const int kcol0 = 2 * (s_hi - 3) + 1;
+        int ci0 = 1, ci1 = 0;
+        if (lane < 8)
         {
-            const int k = kbot + q;
-            int a0 = 1, a1 = 0;
-            if (k >= 1) { const long long g = ev.col_off + k; a0 = b.Fi0[g]; a1 = a0 + b.Flen[g] - 1; }
-            w_i0[q] = a0; w_i1[q] = a1;
+            const int k = kcol0 + lane;
+            if (k >= 1 && k <= N) { const long long g = ev.col_off + k; ci0 = b.Fi0[g]; ci1 = ci0 + b.Flen[g] - 1; }
         }
-        __syncthreads();
-        for (int idx = tid; idx < BT_D * BT_C; idx += blockDim.x)
+        const int jlo = kcol0, ilo = 2 * (r_hi - 7) + 1;         // the block covers columns >= jlo and rows >= ilo
+        while (true)
         {
-            const int r = idx / BT_C, q = idx % BT_C;
-            const int k = kbot + q, i = dtop - r - k;
-            uint8_t v = ST_STOP;
-            if (i >= w_i0[q] && i <= w_i1[q]) v = b.Fstep[cell_at(ev, k, i)];
-            win[r][q] = v;
-        }
-        __syncthreads();
-        if (tid == 0)
-        {
-            int i = s_i, j = s_j, arr = s_arr, go = 1;
-            while (i > 0 && j > 0)
+            if (!(i > 0 && j > 0)) { go = false; break; }
+            if (j < jlo || i < ilo) break;                       // left the block: fetch the next one
+            const int sj = (j - 1) >> 1, rix = (i - 1) >> 1;
+            const unsigned w = __shfl_sync(0xffffffffu, word, (s_hi - sj) + 4 * (r_hi - rix));
+            const int b0 = __shfl_sync(0xffffffffu, ci0, j - kcol0), b1 = __shfl_sync(0xffffffffu, ci1, j - kcol0);
+            int st = ST_STOP;
+            if (i >= b0 && i <= b1) st = (int)((w >> (8 * ((((i - 1) & 1) << 1) + ((j - 1) & 1)))) & 0xffu);
+            const int mv = arr ? ((st >> 3) & 3) : (st & 7);
+            if (arr == 0)
             {
-                const int r = dtop - (j + i), q = j - kbot;
-                if (r >= BT_D || q < 0) break;            // left the window: re-stage
-                const int st = win[r][q];
-                const int mv = arr ? ((st >> 3) & 3) : (st & 7);
-                if (arr == 0)
-                {
-                    if (mv == ST_STOP || mv == ST_IMPLICIT || mv == 5) { go = 0; break; }
-                    if (mv == ST_SKIP) { j--; }
-                    else if (mv == ST_MATCH) { val[i - 1] = (double)j; src[i - 1] = 2 * j; i--; j--; }
-                    else if (mv == ST_IGNORE) { val[i - 1] = -1.0; src[i - 1] = 2 * j; i--; j--; }
-                    else if (mv == ST_INSERT) { val[i - 1] = -1.0; src[i - 1] = 2 * j; i--; }
-                    else /* ST_STAY: hop to the stay matrix, same cell */ arr = 1;
-                }
-                else
-                {
-                    if (mv == 0) { go = 0; break; }
-                    val[i - 1] = (double)j; src[i - 1] = 2 * j + 1;
-                    i--;
-                    if (mv == 1) arr = 0;                 // stay: back to the main matrix one row up
-                }
+                if (mv == ST_STOP || mv == ST_IMPLICIT || mv == 5) { go = false; break; }
+                if (mv == ST_SKIP) { j--; }
+                else if (mv == ST_MATCH) { if (lane == 0) { val[i - 1] = (double)j; src[i - 1] = 2 * j; } i--; j--; }
+                else if (mv == ST_IGNORE) { if (lane == 0) { val[i - 1] = -1.0; src[i - 1] = 2 * j; } i--; j--; }
+                else if (mv == ST_INSERT) { if (lane == 0) { val[i - 1] = -1.0; src[i - 1] = 2 * j; } i--; }
+                else /* ST_STAY: hop to the stay matrix, same cell */ arr = 1;
             }
-            if (!(i > 0 && j > 0)) go = 0;
-            s_i = i; s_j = j; s_arr = arr; s_go = go;
+            else
+            {
+                if (mv == 0) { go = false; break; }
+                if (lane == 0) { val[i - 1] = (double)j; src[i - 1] = 2 * j + 1; }
+                i--;
+                if (mv == 1) arr = 0;                             // stay: back to the main matrix one row up
+            }
         }
-        __syncthreads();
     }
+    __syncwarp();
     // ref_align out, ref_like gathered from the recorded (column, matrix) of every aligned level
-    for (int i = tid; i < n0; i += blockDim.x)
+    for (int q = lane; q < n0; q += 32)
     {
-        if (in_smem) ra[i] = val[i];
-        const int s = src[i];
+        if (in_smem) ra[q] = val[q];
+        const int sc = src[q];
         double like = 0.0;
-        if (s)
+        if (sc)
         {
-            const long long a = cell_at(ev, s >> 1, i + 1);
-            like = (s & 1) ? b.Fs[a] : b.Fm[a];
+            const long long a = cell_at(ev, sc >> 1, q + 1);
+            like = (sc & 1) ? b.Fs[a] : b.Fm[a];
         }
-        rl[i] = like;
+        rl[q] = like;
     }
-    __syncthreads();
-    if (tid == 0)
+    __syncwarp();
+    int empty = 0;
+    if (lane == 0)
     {
-        int empty, rs, re;
+        int rs, re;
         // in shared memory the interpolation runs in place (every entry is read before it is rewritten)
         dev_updaterefs(val, in_smem ? val : ri, n0, empty, rs, re);
-        b.ri_empty[blockIdx.x] = empty;
-        b.refstart[blockIdx.x] = rs;
-        b.refend[blockIdx.x] = re;
-        s_empty = empty;
+        b.ri_empty[e] = empty;
+        b.refstart[e] = rs;
+        b.refend[e] = re;
     }
-    __syncthreads();
-    if (in_smem && !s_empty)
-        for (int i = tid; i < n0; i += blockDim.x) ri[i] = val[i];
+    empty = __shfl_sync(0xffffffffu, empty, 0);
+    __syncwarp();
+    if (in_smem && !empty)
+        for (int q = lane; q < n0; q += 32) ri[q] = val[q];
 }
 
 // ------------------------------------------------------------------------------------------

@@ -885,8 +885,12 @@ int Job::run(bool full)
     {
         int max_n0 = 0;
         for (const EvDesc& d : ev) max_n0 = std::max(max_n0, d.n0);
-        int smem_levels = std::min((max_n0 + 1) & ~1, (int)(160 * 1024 / 12) & ~1);   // 8 B value + 4 B source per level
-        k_backtrace<<<nev, 256, (size_t)smem_levels * 12, ctx->stream>>>(b, smem_levels);
+        // one warp per event, up to BT_WARPS events per CTA: 8 B value + 4 B source per level and event in shared memory
+        const int budget = 160 * 1024 / 12;
+        int wpc = BT_WARPS;
+        while (wpc > 1 && (long long)wpc * ((max_n0 + 1) & ~1) > budget) wpc >>= 1;
+        int smem_levels = std::min((max_n0 + 1) & ~1, (budget / wpc) & ~1);
+        k_backtrace<<<(nev + wpc - 1) / wpc, 32 * BT_WARPS, (size_t)wpc * smem_levels * 12, ctx->stream>>>(b, smem_levels, wpc);
     }
     LAUNCHED();
     MARK(PS_T_JOIN);
