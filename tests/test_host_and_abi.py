@@ -136,3 +136,23 @@ def test_bulk_region_creation_equals_per_region():
     bad.model_index = bad.model_index + 3
     with pytest.raises(RuntimeError):
         poreseqcpp.native_regions_from_packed(ctx, packs[:2] + [bad], "point_width")
+
+
+def test_bulk_create_and_destroy_without_gpu():
+    """ps_regions_create / ps_regions_destroy are host-only (no CUDA call): a batch of regions can be marshalled and
+    released on a box without a GPU; NULL entries and empty batches are ignored."""
+    import ctypes as C
+    from poreseq_b200 import poreseqcpp, synth
+    ctx = poreseqcpp.Context(0)
+    regs = [synth.make_region(200, 3, seed=s + 1) for s in range(6)]
+    packs = [poreseqcpp.PackedRegion(r.sequence, r.events, r.params) for r in regs]
+    nrs = poreseqcpp.native_regions_from_packed(ctx, packs, "point_width")
+    assert [ctx.lib.ps_region_num_events(n.handle) for n in nrs] == [len(r.events) for r in regs]
+    assert [n.sequence() for n in nrs] == [r.sequence for r in regs]
+    poreseqcpp.close_regions(nrs)
+    assert all(n.handle is None for n in nrs)
+    poreseqcpp.close_regions(nrs)                      # already released: nothing to do
+    ctx.lib.ps_regions_destroy((C.c_void_p * 2)(None, None), 2)
+    ctx.lib.ps_regions_destroy(None, 0)
+    h, d = ctx.last_bytes()
+    assert (h, d) == (0, 0)                            # no batch has run on this context
