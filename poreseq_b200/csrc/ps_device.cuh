@@ -1450,6 +1450,30 @@ __global__ void __launch_bounds__(128) k_mutscore_warp(Batch b)
     }
 }
 
+// k_points: the implicit point-mutation table of a region whose sequence is plain ACGT, in FindPointMutations order
+// (cpp/FindMutations.cpp:191-234): per state one deletion, the 3 substitutions by the other bases, 4 insertions.
+// Regions with other characters (a fourth substitution where the base is not ACGT) get their table from the host.
+__global__ void k_points(Batch b)
+{
+    const RegTabDev rt = b.regs[blockIdx.y];
+    if (!rt.plain_points || rt.nev == 0) return;
+    const EvDesc ev = b.ev[rt.ev0];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ev.N) return;
+    const char here = b.bases[ev.base_off + i];
+    MutDev* out = const_cast<MutDev*>(b.muts) + rt.mut_off + 8LL * i;
+    MutDev d;
+    d.start = i; d.n_orig = 1; d.n_mut = 0; d.str_off = 0;
+    *out++ = d;
+    d.n_mut = 1;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        if ("ACGT"[j] != here) { d.str_off = j; *out++ = d; }
+    d.n_orig = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) { d.str_off = j; *out++ = d; }
+}
+
 // k_reduce: score[m] = -1e-6 + sum_e delta(e, m), events in order (cpp/MakeMutations.cpp:38-52,
 // cpp/AlignUtil.h:84-90).  One thread per mutation; the region table gives its events.
 __global__ void k_reduce(Batch b, const RegTabDev* regs, int n_regs, long long n_muts, double start, int from_list)

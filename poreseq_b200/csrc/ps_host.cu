@@ -279,6 +279,7 @@ std::string ps_apply_mutation(const std::string& bases, int start, const std::st
 void HostEvent::update_refs()                                // cpp/EventData.h:110-169
 {
     const int n = n0;
+    ri_stale = false;
     refstart = refend = -1;
     int lo = 0, hi = n - 1;
     while (lo < n && !(ref_align[lo] > 0)) lo++;
@@ -397,6 +398,7 @@ struct Job
     PinVec<double> best, msc;
     bool have_scores = false;
     int max_nmut = 1;                            // longest replacement string of the job (1 for point edits)
+    bool host_muts = false, dev_points = false;   // some mutation tables come from the host / are written by k_points
     double* raw_scores = nullptr;
 };
 
@@ -499,7 +501,7 @@ int Job::build()
         if (want_muts) tot_muts += muts[r].points ? regs[r]->states.size() * 9 : muts[r].list->size();
     }
     if (!lev.resize(tot_levels) || !ref_align.resize(tot_levels) ||
-        !ref_like.resize(tot_levels) || !ref_index.resize(tot_levels) || !states.reserve(tot_states) ||
+        !ref_like.resize(tot_levels) || !states.reserve(tot_states) ||
         !bases.reserve(tot_bases) || !ev.reserve(tot_events) || !mdev.reserve(tot_muts) || !ri_empty.resize(tot_events) ||
         !mono.resize(tot_events) || !cen_old.resize(tot_cen) || !regtab.reserve(regs.size()))
     {
@@ -556,6 +558,9 @@ int Job::build()
         }
         const int nm = (int)(mdev.size() - mut_off);
         RegTab rt; rt.mut_off = mut_off; rt.ev0 = ev0; rt.nev = (int)R->events.size();
+        rt.plain_points = (want_muts && muts[r].points && odd == 0) ? 1 : 0; rt.pad = 0;
+        if (want_muts && !rt.plain_points) host_muts = true;
+        if (rt.plain_points) dev_points = true;
         max_ev = std::max(max_ev, rt.nev);
         regtab.push_back(rt);
         // model de-duplication across the whole batch (events usually share two models): once per
@@ -604,7 +609,7 @@ int Job::build()
     // pass 2a (parallel over regions): the implicit point-mutation tables in FindPointMutations order
     if (want_muts)
         ps_parallel_for((int)regs.size(), [&](int r) {
-            if (!muts[r].points) return;
+            if (!muts[r].points || regtab[r].plain_points) return;      // plain ACGT regions: k_points on the device
             const ps_region* R = regs[r];
             MutDev* out = mdev.data() + reg_mut_off[r];
             for (int i = 0; i < (int)R->states.size(); i++)
@@ -628,6 +633,7 @@ int Job::build()
     ps_parallel_for(ne, [&](int e) {
         HostEvent& he = *const_cast<HostEvent*>(hev[e]);
         const EvDesc& d = ev[e];
+        he.ensure_refs();
         const size_t at = (size_t)d.lev_off, n = (size_t)he.n0;
         if (he.staged++ == 0 && he.levrec.empty())
         {
@@ -742,7 +748,7 @@ int Job::upload()
     TRY(up(ctx, "lev", lev.data(), lev.size(), &d_lev));
     TRY(room(ctx, "ref_align", ref_align.size(), &b.ref_align));
     TRY(room(ctx, "ref_like", ref_like.size(), &b.ref_like));
-    TRY(room(ctx, "ref_index", ref_index.size(), &b.ref_index));
+    TRY(room(ctx, "ref_index", ref_align.size(), &b.ref_index));
     TRY(up(ctx, "ri_empty", ri_empty.data(), ri_empty.size(), &b.ri_empty));
     TRY(up(ctx, "mono", mono.data(), mono.size(), &b.mono));
     { int* fl; TRY(up(ctx, "fill_list", fill_list.data(), fill_list.size(), &fl)); b.fill_list = fl; }
@@ -779,7 +785,8 @@ int Job::upload()
         TRY(room(ctx, "Bbest", (size_t)n_cols, &b.Bbest));
         TRY(room(ctx, "old", (size_t)n_cols, &b.old));
         MutDev* d_m; char* d_ms; RegTab* d_rt;
-        TRY(up(ctx, "muts", mdev.data(), mdev.size(), &d_m));
+        if (host_muts) TRY(up(ctx, "muts", mdev.data(), mdev.size(), &d_m));
+        else TRY(room(ctx, "muts", mdev.size(), &d_m));
         TRY(up(ctx, "mut_str", mut_str.data(), mut_str.size(), &d_ms));
         TRY(up(ctx, "regtab", regtab.data(), regtab.size(), &d_rt));
         b.muts = d_m; b.mut_str = d_ms;
@@ -901,6 +908,11 @@ int Job::run(bool full)
             k_centres<<<grid, 128, 0, ctx->stream>>>(b, b.cen_new, 0);
             LAUNCHED();
         }
+        if (dev_points)
+        {
+            k_points<<<dim3((maxN + 127) / 128, (unsigned)regs.size()), 128, 0, ctx->stream>>>(b);
+            LAUNCHED();
+        }
         {
             dim3 grid((maxN + 31) / 32, nev);
             k_join<<<grid, 256, 0, ctx->stream>>>(b);
@@ -983,7 +995,6 @@ int Job::download_enqueue()
     {
         CU(cudaMemcpyAsync(ref_align.data(), b.ref_align, nl * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaMemcpyAsync(ref_like.data(), b.ref_like, nl * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaMemcpyAsync(ref_index.data(), b.ref_index, nl * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     }
     if (ne)
     {
@@ -992,7 +1003,7 @@ int Job::download_enqueue()
         CU(cudaMemcpyAsync(re.data(), b.refend, ne * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaMemcpyAsync(best.data(), d_evbest, ne * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     }
-    ctx->d2h_bytes += (long long)(3 * nl * sizeof(double) + ne * (3 * sizeof(int) + sizeof(double)));
+    ctx->d2h_bytes += (long long)(2 * nl * sizeof(double) + ne * (3 * sizeof(int) + sizeof(double)));
     have_scores = want_muts && n_muts && n_tasks;
     if (have_scores) ctx->d2h_bytes += (long long)((size_t)n_muts * sizeof(double));
     if (have_scores)
@@ -1018,8 +1029,10 @@ int Job::finish(std::vector<double>* align_scores, std::vector<double>* mut_scor
         std::copy(ref_like.data() + d.lev_off, ref_like.data() + d.lev_off + d.n0, he.ref_like.begin());
         he.ri_empty = ri_empty[e] != 0;
         he.refstart = rs[e]; he.refend = re[e];
-        if (he.ri_empty) he.ref_index.clear();
-        else he.ref_index.assign(ref_index.data() + d.lev_off, ref_index.data() + d.lev_off + d.n0);
+        // ref_index stays on the device; the host rebuilds it from ref_align (same arithmetic, cpp/EventData.h:110-169)
+        // if this event is staged again or ViterbiMutate looks at it
+        if (he.ri_empty) { he.ref_index.clear(); he.ri_stale = false; }
+        else he.ri_stale = true;
     });
     if (align_scores)
     {

@@ -75,9 +75,11 @@ struct HostEvent                              // cpp/EventData.h:78-229
     int refstart = -1, refend = -1;
     std::vector<double> mean, stdv, ref_align, ref_like, ref_index;
     std::vector<double> levrec;               // 3 doubles per level, the staged LevIn layout (mean, stdv, 3 log stdv), cached
+    bool ri_stale = false;                    // ref_align was rewritten by a batch; ref_index is rebuilt from it on first use
     int staged = 0;                           // batches this event was staged for (the level records are cached from the second on)
     std::string seq2d;
     void update_refs();
+    void ensure_refs() { if (ri_stale) update_refs(); }
     void ensure_levrec();                     // log(stdv) etc. (cpp/EventData.h:218-220), cached
 };
 

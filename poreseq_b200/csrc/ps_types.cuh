@@ -45,7 +45,11 @@ struct __align__(16) LevelRecF // FP32 row record of the forward scan, row i (1-
     float x, y, ry, ey;
 };
 
-struct RegTabDev { long long mut_off; int ev0, nev; };   // per region: first mutation, its events
+struct RegTabDev              // per region: first mutation, its events
+{
+    long long mut_off; int ev0, nev;
+    int plain_points, pad;             // the region's mutations are the implicit point edits of an all-ACGT sequence: k_points writes them
+};
 
 struct ModelDev               // cpp/EventData.h:21-74
 {

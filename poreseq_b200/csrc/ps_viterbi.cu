@@ -277,6 +277,7 @@ int ps_viterbi_list(ps_region* R, int nkeep, double skip_prob, double stay_prob,
     CU(cudaSetDevice(ctx->device));
     const int E = (int)R->events.size();
     if (E == 0) { ps_set_error(ctx, "ViterbiMutate needs at least one event"); return PS_E_ARG; }
+    for (HostEvent& ev : R->events) ev.ensure_refs();
     for (const HostEvent& ev : R->events)
         if (ev.ri_empty)
         {
