@@ -295,6 +295,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-consensus", action="store_true", help="skip the secondary consensus kb/s measurement")
+    ap.add_argument("--driver", default="threads", choices=["threads", "pipeline"],
+                    help="e2e region: --drivers host threads with two contexts each (threads) or one host thread pipelining "
+                         "--contexts contexts (pipeline)")
+    ap.add_argument("--drivers", type=int, default=3, help="host threads of the e2e region (driver threads)")
     ap.add_argument("--contexts", type=int, default=4, help="library contexts (streams + staging areas) per GPU in the e2e pipeline")
     ap.add_argument("--precision", default="fast", choices=["fast", "exact"],
                     help="fast: FP32 mutation scan + exact FP64 re-score of every candidate (decisions and accepted scores "
@@ -315,7 +319,10 @@ def main():
     # the ranks of this node instead of 8 per rank (PORESEQ_B200_THREADS is the library's own knob)
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     if "PORESEQ_B200_THREADS" not in os.environ:
-        os.environ["PORESEQ_B200_THREADS"] = str(max(1, min(8, (os.cpu_count() or 8) // max(local_world, 1))))
+        share = (os.cpu_count() or 8) // max(local_world, 1)
+        if args.driver == "threads":
+            share -= max(1, args.drivers) - 1                 # the driver threads marshal too
+        os.environ["PORESEQ_B200_THREADS"] = str(max(1, min(8, share)))
 
     import torch
     import torch.distributed as dist
@@ -335,7 +342,8 @@ def main():
 
     # two contexts (two streams, two sets of staging / device buffers) on this rank's GPU: while the GPU
     # works on step k the host marshals and stages step k+1 (ps_score_points_batch_begin / _end)
-    ctxs = [poreseqcpp.Context(local_rank) for _ in range(max(2, args.contexts))]
+    n_ctx = 2 * max(1, args.drivers) if args.driver == "threads" else max(2, args.contexts)
+    ctxs = [poreseqcpp.Context(local_rank) for _ in range(n_ctx)]
     for c in ctxs:
         c.set_precision(args.precision)
     ctx = ctxs[0]
@@ -374,6 +382,43 @@ def main():
             out = end(inflight.pop(0), record)
         return out
 
+    def run_steps_threads(count, record):
+        """A few host threads, each pipelining whole steps (create, begin ... end, destroy) over its own two contexts:
+        the host work of different steps runs on different cores (ctypes releases the GIL inside the library) and
+        every thread keeps one batch queued behind the one it waits for, so the GPU never runs dry while the
+        threads marshal (with one batch per thread the threads fall into lock-step: all wait, then all marshal)."""
+        nxt = [0]
+        lock = threading.Lock()
+        last = [None]
+
+        def take():
+            with lock:
+                k = nxt[0]
+                nxt[0] += 1
+            return k
+
+        def drive(mine):
+            pending = None                                   # (step index, batch in flight)
+            turn = 0
+            while True:
+                k = take()
+                cur = (k, begin(mine[turn])) if k < count else None
+                turn ^= 1
+                if pending is not None:
+                    o = end(pending[1], record)
+                    if pending[0] == count - 1:
+                        last[0] = o
+                pending = cur
+                if cur is None:
+                    return
+
+        ths = [threading.Thread(target=drive, args=(ctxs[2 * t:2 * t + 2],)) for t in range(len(ctxs) // 2)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        return last[0]
+
     def run_steps_serial(count, record):
         out = None
         for k in range(count):
@@ -401,7 +446,7 @@ def main():
     launches0 = sum(c.launch_count() for c in ctxs)
     barrier()
     t0 = time.perf_counter()
-    run_steps(args.steps, False)
+    (run_steps_threads if args.driver == "threads" else run_steps)(args.steps, False)
     barrier()
     wall = time.perf_counter() - t0
     launches = sum(c.launch_count() for c in ctxs) - launches0
@@ -449,7 +494,9 @@ def main():
                    "mutations_per_region": 8 * (REGION_LEN - 4), "cells_per_step_per_gpu": step_cells,
                    "l2": "band working set %.0f MB per step exceeds the 126 MB L2" % (wide_cells * 12.25 / 1e6),
                    "host_threads_per_rank": int(os.environ["PORESEQ_B200_THREADS"]),
-                   "pipelining": "%d contexts: host staging and H2D of the next steps overlap the kernels of step k" % len(ctxs),
+                   "pipelining": ("%d host threads x 2 contexts: host staging and H2D of the other steps overlap the kernels of step k" % (len(ctxs) // 2)
+                                  if args.driver == "threads" else
+                                  "%d contexts, one host thread: host staging and H2D of the next steps overlap the kernels of step k" % len(ctxs)),
                    "precision": ("fp32 mutation scan + exact fp64 re-score of all candidates > -tau; wide fills/backtrace fp64"
                                  if args.precision == "fast" else "fp64 exact (bit-identical to the reference)")},
         "e2e": {"value": total_cells / (wall_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -510,6 +510,9 @@ int Job::build()
     }
     mut_str.append("ACGT", 4);                  // single-base replacement strings live at offsets 0..3
 
+    const bool trace_b = getenv("PORESEQ_B200_TRACE") != nullptr;
+    auto nowb = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double tb0 = nowb();
     // pass 1 (serial, cheap): region tables, list-mutation tables, event descriptors and offsets.  The
     // point-mutation tables (8-9 entries per state) are only sized here and written in pass 2.
     std::vector<const HostEvent*> hev;
@@ -606,6 +609,7 @@ int Job::build()
     n_cols += 1;                                  // index 0 of the first event is never used
     n_muts = (long long)mdev.size();
 
+    const double tb1 = nowb();
     // pass 2a (parallel over regions): the implicit point-mutation tables in FindPointMutations order
     if (want_muts)
         ps_parallel_for((int)regs.size(), [&](int r) {
@@ -625,6 +629,7 @@ int Job::build()
                 for (int j = 0; j < 4; j++) { d.str_off = j; *out++ = d; }
             }
         });
+    const double tb2 = nowb();
     // pass 2b (parallel over events): level records, alignment arrays, band centres, wavefront plan
     const int ne = (int)ev.size();
     wave_need.assign(ne, 32);
@@ -659,6 +664,7 @@ int Job::build()
         if (!(model_src[d.model]->trans[0] <= 1.0) || !(model_src[d.model]->trans[3] <= 1.0)) ok = 0;
         mono[e] = ok;
     });
+    const double tb3 = nowb();
     // wavefront-major band storage: slots per step = wavefront width of the event's launch class (at
     // most that many strips are live on one step), one slot per strip for the serially filled events
     std::vector<int> cls(ne, -1);
@@ -692,6 +698,7 @@ int Job::build()
         d.strip_off = n_strips;                   // forward strips 0..J, then reverse strips 0..J
         n_strips += 2 * (J + 1);
     }
+    if (trace_b) fprintf(stderr, "[ps] build: tables %.2f ms, point tables %.2f, per-event staging %.2f, layout %.2f\n", tb1 - tb0, tb2 - tb1, tb3 - tb2, nowb() - tb3);
     return PS_OK;
 }
 
