@@ -521,10 +521,17 @@ def main():
                          "peak": hbm_peak, "unit": "GB/s", "frac": dom_bytes / dom_s / 1e9 / hbm_peak if dom_s > 0 else 0.0,
                          "peak_source": peak_src, "traffic": recorded_traffic(dom_kernel, args.regions)},
     }
+    single = None
     if not args.no_consensus:
         # consensus kb/s, throughput form, on every rank: CONS_REGIONS regions of 1 kb x 10x per GPU, 8 in flight
         for c in ctxs:
             c.close()
+        if rank == 0 and world == 1:
+            # consensus kb/s beside the GCUPS headline: configs[2] size on the GPU, the README's own 1 kb x 10x case
+            # on both sides (the reference needs ~25 s for it; 10 kb x 30x would take it the better part of an hour)
+            big, _ = consensus_gpu(10000, 30, seed=7)
+            small, seq_gpu = consensus_gpu(1000, 10, seed=7)
+            single = (big, small, seq_gpu)
         cons_ctxs = [poreseqcpp.Context(local_rank) for _ in range(8)]
         for c in cons_ctxs:
             c.set_precision("fast")
@@ -544,11 +551,8 @@ def main():
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = run_cpu_baseline()
-        if world == 1 and not args.no_consensus:
-            # consensus kb/s beside the GCUPS headline: configs[2] size on the GPU, the README's own 1 kb x 10x case
-            # on both sides (the reference needs ~25 s for it; 10 kb x 30x would take it the better part of an hour)
-            big, _ = consensus_gpu(10000, 30, seed=7)
-            small, seq_gpu = consensus_gpu(1000, 10, seed=7)
+        if world == 1 and not args.no_consensus and single is not None:
+            big, small, seq_gpu = single
             line["consensus"].update({"configs[2] 10 kb x 30x": big, "1 kb x 10x": small})
             if not args.no_cpu_baseline:
                 from oracle import binding
