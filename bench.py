@@ -340,8 +340,8 @@ def main():
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize()
 
-    # two contexts (two streams, two sets of staging / device buffers) on this rank's GPU: while the GPU
-    # works on step k the host marshals and stages step k+1 (ps_score_points_batch_begin / _end)
+    # several contexts (stream + staging / device buffers each) on this rank's GPU: while the GPU works on step k
+    # the host marshals and stages the next steps (ps_score_points_batch_begin / _end)
     n_ctx = 2 * max(1, args.drivers) if args.driver == "threads" else max(2, args.contexts)
     ctxs = [poreseqcpp.Context(local_rank) for _ in range(n_ctx)]
     for c in ctxs:
@@ -441,7 +441,7 @@ def main():
     barrier()
     run_steps_serial(args.steps, True)
     barrier()
-    # timed region 2 (`e2e`): K steps through the C-ABI from host buffers, two contexts in flight so that the
+    # timed region 2 (`e2e`): K steps through the C-ABI from host buffers, several contexts in flight so that the
     # host staging and H2D of step k+1 overlap the kernels of step k; wall clock around barrier + synchronize
     launches0 = sum(c.launch_count() for c in ctxs)
     barrier()

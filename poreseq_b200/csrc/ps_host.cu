@@ -397,7 +397,6 @@ struct Job
     PinVec<int> rs, re;
     PinVec<double> best, msc;
     bool have_scores = false;
-    int max_nmut = 1;                            // longest replacement string of the job (1 for point edits)
     bool host_muts = false, dev_points = false;   // some mutation tables come from the host / are written by k_points
     double* raw_scores = nullptr;
 };
@@ -489,10 +488,7 @@ int Job::build()
     for (size_t r = 0; r < regs.size(); r++)
         if (want_muts && muts[r].list)
             for (const HostMut& m : *muts[r].list)
-            {
                 cen_pad = std::max(cen_pad, (int)m.mut.size() - (int)m.orig.size() + 8);
-                max_nmut = std::max(max_nmut, (int)m.mut.size());
-            }
     for (size_t r = 0; r < regs.size(); r++)
     {
         for (const HostEvent& he : regs[r]->events) tot_levels += he.n0;
