@@ -9,6 +9,10 @@
  * (tests/golden/make_golden.py).  The reference itself ships no tests or golden vectors
  * (SURVEY.md section 4), so the compiled reference is the pin.
  *
+ * Restated here: the DP path (fills, join, backtrace, scoreMutation, ScoreAlignments, ScoreMutations,
+ * FindPointMutations, MakeMutations) and its drivers (swfull, fillinds, MapAlignments, FindMutations, the Mutate
+ * loop).  ViterbiMutate is not restated: its checker is the compiled reference.
+ *
  * The restatement is written dense-array style (one flat band buffer per event, one shared cell
  * routine for both directions) rather than the reference's column-object style.  Each routine
  * cites the reference lines whose behaviour it restates.  Arithmetic is IEEE double, evaluated
@@ -515,6 +519,182 @@ int make_mutations(Region& R, std::vector<Mut> muts)
     return changed;
 }
 
+/* ------------------------------------------------------------- sequence alignment (cpp/swlib.cpp) */
+
+/* cpp/swlib.h:21-33 */
+struct Pairing { int score; double accuracy; std::vector<int> a, b; Pairing() : score(0), accuracy(0) {} };
+
+/* swfull, cpp/swlib.cpp:211-340, restated with two rolling score rows and one byte per cell that holds the
+ * move (1 = gap in seq1, 2 = gap in seq2, 3 = pair) and whether the cell's score is 0 (where the reference's
+ * traceback stops, :299-301; scores are never negative).  Compare order and ties as in :246-268: the gap moves
+ * win only when strictly better, the pairing move wins ties (also the tie with 0); the first maximum in
+ * (seq2 position, seq1 position) order is the end of the alignment (:273-278). */
+Pairing sw_align(const std::string& s1, const std::string& s2)
+{
+    const int n1 = (int)s1.size(), n2 = (int)s2.size();
+    const int match = 5, mismatch = -4, gap = -8;                      /* cpp/swlib.h:21-23 */
+    std::vector<unsigned char> cell((size_t)(n1 + 1) * (n2 + 1), 4);   /* border: score 0 */
+    std::vector<int> before(n1 + 1, 0), now(n1 + 1, 0);
+    int top = 0, ti = 0, tj = 0;
+    for (int j = 1; j <= n2; j++)
+    {
+        now[0] = 0;
+        unsigned char* row = &cell[(size_t)j * (n1 + 1)];
+        for (int i = 1; i <= n1; i++)
+        {
+            int best = 0, how = 0;
+            const int from_j = before[i] + gap, from_i = now[i - 1] + gap;
+            const int both = before[i - 1] + (s1[i - 1] == s2[j - 1] ? match : mismatch);
+            if (from_j > best) { best = from_j; how = 1; }
+            if (from_i > best) { best = from_i; how = 2; }
+            if (both >= best) { best = both; how = 3; }
+            now[i] = best;
+            row[i] = (unsigned char)(how | (best <= 0 ? 4 : 0));
+            if (best > top) { top = best; ti = i; tj = j; }
+        }
+        before.swap(now);
+    }
+    Pairing out;
+    out.score = top;
+    int i = ti, j = tj, same = 0;
+    while (i > 0 && j > 0)
+    {
+        const unsigned char c = cell[(size_t)j * (n1 + 1) + i];
+        if (c & 4) break;
+        const int how = c & 3;
+        if (how == 1) { out.a.push_back(0); out.b.push_back(j); j--; }
+        else if (how == 2) { out.a.push_back(i); out.b.push_back(0); i--; }
+        else { out.a.push_back(i); out.b.push_back(j); if (s1[i - 1] == s2[j - 1]) same++; i--; j--; }
+    }
+    std::reverse(out.a.begin(), out.a.end());
+    std::reverse(out.b.begin(), out.b.end());
+    out.accuracy = 100.0 * same / (double)out.a.size();
+    return out;
+}
+
+/* fillinds, cpp/swlib.cpp:342-364: a gap repeats the last index seen on its side (the first entry as it is) */
+void fill_gaps(Pairing& p)
+{
+    if (p.a.empty()) return;
+    int ka = p.a[0], kb = p.b[0];
+    for (size_t k = 0; k < p.a.size(); k++)
+    {
+        if (p.a[k] > 0) ka = p.a[k]; else p.a[k] = ka;
+        if (p.b[k] > 0) kb = p.b[k]; else p.b[k] = kb;
+    }
+}
+
+/* forward declarations of the region-level routines further down */
+struct Region;
+std::vector<double> score_alignments(Region& R, double* likes);
+
+/* MapAlignments, cpp/EventUtil.cpp:12-55: every level's column is sent through the pairing of the old and the
+ * new sequence -- the first pairing entry whose old-side index is not below it (std::lower_bound, :41) -- levels
+ * outside the paired stretch lose their alignment; then updaterefs. */
+Pairing map_alignments(Region& R, const std::string& newseq)
+{
+    Pairing p = sw_align(R.bases, newseq);
+    fill_gaps(p);
+    R.set_sequence(newseq);
+    for (size_t e = 0; e < R.events.size(); e++)
+    {
+        Event& ev = R.events[e];
+        for (size_t j = 0; j < ev.ref_align.size(); j++)
+        {
+            const int col = (int)ev.ref_align[j];
+            if (p.a.empty() || col < p.a.front() || col > p.a.back()) { ev.ref_align[j] = 0; continue; }
+            const size_t at = std::lower_bound(p.a.begin(), p.a.end(), col) - p.a.begin();
+            ev.ref_align[j] = at < p.b.size() ? p.b[at] : 0;
+        }
+        ev.updaterefs();
+    }
+    return p;
+}
+
+typedef std::map<std::string, std::vector<double> > ProfileCache;     /* cpp/AlignData.h:34 */
+
+/* FindMutations, cpp/FindMutations.cpp:24-186.  Per-base likelihood profiles of the current sequence and of every
+ * seed (events remapped onto the seed, realigned; cached by seed string, :44-49), compared along the pairing of
+ * the two sequences: differences of consecutive profile values, a CUSUM of (seed - current) clamped at 0 and
+ * zeroed where the two differences agree to 1e-5 (:83-94); then the greedy peak picking of :111-183. */
+std::vector<Mut> find_mutations(Region& R, const std::vector<std::string>& seeds, ProfileCache& cache)
+{
+    std::vector<double> mine(R.bases.size(), 0.0);
+    score_alignments(R, mine.data());
+    std::vector<std::vector<double> > gain;
+    std::vector<Pairing> pairs;
+    for (size_t s = 0; s < seeds.size(); s++)
+    {
+        Region other(R);
+        Pairing p = map_alignments(other, seeds[s]);
+        std::vector<double>& prof = cache[seeds[s]];
+        if (prof.empty())
+        {
+            prof.assign(seeds[s].size(), 0.0);
+            score_alignments(other, prof.data());
+        }
+        /* "because i did it in matlab code" (:51-63): both index lists minus 2, leading negatives dropped */
+        for (size_t k = 0; k < p.a.size(); k++) { p.a[k] -= 2; p.b[k] -= 2; }
+        size_t drop = 0;
+        while (drop < p.a.size() && (p.a[drop] < 0 || p.b[drop] < 0)) drop++;
+        p.a.erase(p.a.begin(), p.a.begin() + drop);
+        p.b.erase(p.b.begin(), p.b.begin() + drop);
+        const size_t n = p.a.size();
+        std::vector<double> d1(n), d2(n), g(n);
+        for (size_t k = 0; k < n; k++) { d1[k] = mine[p.a[k]]; d2[k] = prof[p.b[k]]; }
+        for (size_t k = n; k-- > 1;) { d1[k] -= d1[k - 1]; d2[k] -= d2[k - 1]; }
+        if (n) { d1[0] = 0; d2[0] = 0; }
+        double run = 0;
+        for (size_t k = 0; k < n; k++)
+        {
+            run += d2[k] - d1[k];
+            if (run < 0) run = 0;
+            g[k] = std::fabs(d1[k] - d2[k]) < 1e-5 ? 0.0 : run;
+        }
+        gain.push_back(g);
+        pairs.push_back(p);
+    }
+    std::vector<Mut> found;
+    while (found.size() < R.bases.size() / 3)
+    {
+        /* the seed with the highest peak (first on ties), the first position of that peak */
+        size_t who = 0, where = 0;
+        double peak = 0;
+        bool any = false;
+        for (size_t s = 0; s < gain.size(); s++)
+        {
+            if (gain[s].empty()) continue;
+            const size_t at = std::max_element(gain[s].begin(), gain[s].end()) - gain[s].begin();
+            if (!any || gain[s][at] > peak) { any = true; peak = gain[s][at]; who = s; where = at; }
+        }
+        if (!any) break;
+        std::vector<double>& g = gain[who];
+        if (g[where] < 0.25) break;
+        /* the stretch between the exact zeros around the peak (:134-145) */
+        long right = (long)where;
+        while (right < (long)g.size() && g[right] != 0) right++;
+        long left = (long)where;
+        while (left >= 0 && g[left] != 0) left--;
+        if (left < 0) left = 0;
+        if (right >= (long)g.size()) right = (long)g.size() - 1;
+        const Pairing& p = pairs[who];
+        const int from1 = p.a[left], from2 = p.b[left], to1 = p.a[where], to2 = p.b[where];
+        Mut m;
+        m.start = from1;
+        m.orig = R.bases.substr(from1, to1 - from1);
+        m.mut = seeds[who].substr(from2, to2 - from2);
+        m.score = -1e-6;
+        while (!m.orig.empty() && !m.mut.empty() && m.orig[0] == m.mut[0]) { m.orig.erase(0, 1); m.mut.erase(0, 1); m.start++; }
+        while (!m.orig.empty() && !m.mut.empty() && m.orig[m.orig.size() - 1] == m.mut[m.mut.size() - 1])
+        {
+            m.orig.erase(m.orig.size() - 1); m.mut.erase(m.mut.size() - 1);
+        }
+        if (!m.orig.empty() || !m.mut.empty()) found.push_back(m);
+        std::fill(g.begin() + left, g.begin() + right + 1, 0.0);
+    }
+    return found;
+}
+
 std::string dot(const std::string& s) { return s.empty() ? std::string(".") : s; }
 
 std::string text_of(const std::vector<Mut>& v, bool scored)
@@ -599,6 +779,60 @@ int orc_refine(orc_region* r, char* seq_out, int cap, int* nbases)
     *nbases = make_mutations(R, m);
     R.store(r);
     return put(R.bases, seq_out, cap);
+}
+
+/* FindMutations with a fresh profile cache (one call = one AlignData, _poreseqcpp.pyx:408) */
+int orc_find_mutations(orc_region* r, int n_seeds, const char* const* seeds, char* out, int cap)
+{
+    Region R(r);
+    ProfileCache cache;
+    std::vector<std::string> sd(seeds, seeds + n_seeds);
+    std::vector<Mut> m = find_mutations(R, sd, cache);
+    R.store(r);
+    return put(text_of(m, false), out, cap);
+}
+
+/* PSAlign.Mutate's loop (_poreseqcpp.pyx:424-431): the profile cache lives across the repetitions although the
+ * sequence changes under it */
+int orc_mutate(orc_region* r, int n_seeds, const char* const* seeds, int reps, char* seq_out, int cap, int* totbases)
+{
+    Region R(r);
+    ProfileCache cache;
+    std::vector<std::string> sd(seeds, seeds + n_seeds);
+    int total = 0;
+    for (int k = 0; k < reps; k++)
+    {
+        std::vector<Mut> m = find_mutations(R, sd, cache);
+        score_mutations(R, m);
+        const int nb = make_mutations(R, m);
+        if (nb == 0) break;
+        total += nb;
+    }
+    *totbases = total;
+    R.store(r);
+    return put(R.bases, seq_out, cap);
+}
+
+/* not restated: the checker for ViterbiMutate is the compiled reference (oracle/_ref) */
+int orc_viterbi_mutate(orc_region*, int, double, double, double, double, char*, int) { return -2; }
+
+int orc_swfull(const char* seq1, const char* seq2, int* inds1, int* inds2, int cap, int* n, int* score, double* accuracy)
+{
+    Pairing p = sw_align(seq1, seq2);
+    *n = (int)p.a.size();
+    *score = p.score;
+    *accuracy = p.accuracy;
+    if (*n > cap) return -1;
+    for (int k = 0; k < *n; k++) { inds1[k] = p.a[k]; inds2[k] = p.b[k]; }
+    return 0;
+}
+
+int orc_map_alignments(orc_region* r, const char* newseq)
+{
+    Region R(r);
+    map_alignments(R, newseq);
+    R.store(r);
+    return 0;
 }
 
 int orc_seq_to_states(const char* seq, int len, int* states)

@@ -52,3 +52,48 @@ def test_restatement_matches_reference(orc, ref, name):
 def test_states_with_invalid_bases(orc, ref):
     for seq in ["ACGTACGTNACGTACGGTNNACGTTGCA", "NACGT", "ACGT", "ACGTN", "ACG-TACGTAC", "TTTTTTTTTT"]:
         assert orc.seq_to_states(seq).tolist() == ref.seq_to_states(seq).tolist()
+
+
+def _noisy(seq, rng, rate):
+    out = []
+    for ch in seq:
+        u = rng.random()
+        if u < rate / 3:
+            continue
+        if u < 2 * rate / 3:
+            out.append("ACGT"[rng.integers(4)])
+            continue
+        out.append(ch)
+        if u < rate:
+            out.append("ACGT"[rng.integers(4)])
+    return "".join(out)
+
+
+def test_swfull_restatement_matches_reference(orc, ref):
+    """swfull (cpp/swlib.cpp:211-340): score, accuracy and the aligned index pairs, incl. empty overlaps, one-base
+    sequences, homopolymers (ties between the gap moves and the pairing move) and unrelated sequences."""
+    rng = np.random.default_rng(3)
+    pairs = [("ACGT", "ACGT"), ("A", "A"), ("A", "C"), ("AAAAAAAAAA", "AAAAAAA"), ("ACGTACGT", "TTTT"),
+             ("ACGTTTTTACGT", "ACGTTTACGT"), ("GATTACA", "GCATGCT"), ("ACACACACAC", "CACACACA")]
+    for n in (30, 120, 400):
+        base = "".join(rng.choice(list("ACGT"), n))
+        pairs += [(base, _noisy(base, rng, 0.15)), (_noisy(base, rng, 0.3), base), (base, "".join(rng.choice(list("ACGT"), n)))]
+    for a, b in pairs:
+        x, y = orc.swfull(a, b), ref.swfull(a, b)
+        assert x[1:] == y[1:] and (x[0] == y[0] or (np.isnan(x[0]) and np.isnan(y[0]))), (a, b)   # 0/0 on an empty alignment
+
+
+@pytest.mark.parametrize("name", ["draft_partial", "ragged"])
+def test_find_and_map_restatements_match_reference(orc, ref, name):
+    """MapAlignments, FindMutations and the Mutate loop of the restatement against the reference's own C++: remapped
+    alignments, candidate lists in order, final sequence, bases changed and every event's alignment."""
+    reg = region(name)
+    rng = np.random.default_rng(17)
+    seeds = [ev.sequence for ev in reg.events[::2]][:4] + [_noisy(reg.sequence, rng, 0.08)]
+    seeds.append(seeds[0])                                        # a repeated seed takes the cached profile
+    assert same_aligns(orc.map_alignments(reg, seeds[-2]), ref.map_alignments(reg, seeds[-2]))
+    f1, a1 = ref.find_mutations(reg, seeds)
+    f2, a2 = orc.find_mutations(reg, seeds)
+    assert f1 == f2 and len(f1) > 0 and same_aligns(a1, a2)
+    m1, m2 = ref.mutate(reg, seeds, reps=3), orc.mutate(reg, seeds, reps=3)
+    assert m1[0] == m2[0] and m1[1] == m2[1] and same_aligns(m1[2], m2[2])
