@@ -11,7 +11,7 @@
  *
  * Restated here: the DP path (fills, join, backtrace, scoreMutation, ScoreAlignments, ScoreMutations,
  * FindPointMutations, MakeMutations) and its drivers (swfull, fillinds, MapAlignments, FindMutations, the Mutate
- * loop).  ViterbiMutate is not restated: its checker is the compiled reference.
+ * loop, ViterbiMutate).
  *
  * The restatement is written dense-array style (one flat band buffer per event, one shared cell
  * routine for both directions) rather than the reference's column-object style.  Each routine
@@ -695,6 +695,199 @@ std::vector<Mut> find_mutations(Region& R, const std::vector<std::string>& seeds
     return found;
 }
 
+/* ------------------------------------------------------------- ViterbiMutate (cpp/Viterbi.cpp) */
+
+/* One position of the 1024-state chain: Viterbi scores with back pointers and normalised forward probabilities. */
+struct Layer { std::vector<double> lik, fwd; std::vector<int> from; Layer() : lik(NS), fwd(NS), from(NS) {} };
+
+/* V_LIK::V_LIK, cpp/Viterbi.cpp:39-102: a state is entered by an advance of 1, 2 or 3 bases -- predecessor
+ * (d >> 2j) + (k << (10 - 2j)), cpp/Viterbi.h:28-29, weight .25^j skip^(j-1), in that order, the first best wins --
+ * or by staying; the forward sum runs over the same terms, is multiplied by exp(obs) and normalised by the
+ * reciprocal of the plain sum (cpp/Viterbi.h:56-64). */
+void chain_step(const Layer& prev, const std::vector<double>& obs, double skip, double stay, Layer& out)
+{
+    const double lskip = std::log(skip), lstay = std::log(stay);
+    for (int d = 0; d < NS; d++)
+    {
+        double top = NEG, mass = 0.0;
+        int arg = -1;
+        double w = 0.25, lw = std::log(0.25);
+        for (int j = 1; j <= 3; j++)
+        {
+            for (int k = 0; k < (1 << (2 * j)); k++)
+            {
+                const int p = (d >> (2 * j)) + (k << (10 - 2 * j));
+                double l = obs[d] + lw;
+                l += prev.lik[p];
+                mass += w * prev.fwd[p];
+                if (l > top) { top = l; arg = p; }
+            }
+            w = w * 0.25 * skip;
+            lw = lw + std::log(0.25) + lskip;
+        }
+        const double l = obs[d] + lstay + prev.lik[d];
+        if (l > top) { top = l; arg = d; }
+        mass += stay * prev.fwd[d];
+        mass *= std::exp(obs[d]);
+        out.lik[d] = top; out.from[d] = arg; out.fwd[d] = mass;
+    }
+    double tot = 0;
+    for (int d = 0; d < NS; d++) tot += out.fwd[d];
+    tot = 1.0 / tot;
+    for (int d = 0; d < NS; d++) out.fwd[d] *= tot;
+}
+
+/* StatesToSequence, cpp/Viterbi.cpp:171-237: first base of the first state; a change of state emits the bases the
+ * smallest advance (1..4, then smallest index) that explains it has shifted out, or, if none does, the first base
+ * of the new state; repeats are stays; finally the last four bases of the last state. */
+std::string path_to_bases(const std::vector<int>& path)
+{
+    /* base `at` (0 = leftmost) of a 5-mer state, cpp/Viterbi.h:35-39 */
+    struct { char operator()(int st, int at) const { return "ACGT"[3 & (st >> (2 * (4 - at)))]; } } base;
+    std::string seq;
+    int cur = path[0];
+    seq.push_back(base(cur, 0));
+    for (size_t i = 1; i < path.size(); i++)
+    {
+        if (path[i] == cur) continue;
+        int adv = 0;
+        for (int n = 1; n <= 4 && !adv; n++)
+            for (int k = 0; k < (1 << (2 * n)); k++)
+                if ((((cur << (2 * n)) & (NS - 1)) + k) == path[i]) { adv = n; break; }
+        if (adv) for (int j = 1; j <= adv; j++) seq.push_back(base(cur, j));
+        else seq.push_back(base(path[i], 0));
+        cur = path[i];
+    }
+    for (int j = 1; j <= 4; j++) seq.push_back(base(cur, j));
+    return seq;
+}
+
+/* ViterbiMutate, cpp/Viterbi.cpp:239-426.  Positions run from the smallest refstart; per position
+ * every read contributes the pdf of the MEAN of its levels aligned there (getrefstates, cpp/EventData.h:187-204: the
+ * first level whose ref_index equals the position exactly, then the following levels while ref_align <= position,
+ * keeping the aligned ones), without lik_offset; per state the lowest quarter of the reads is dropped and the rest
+ * averaged (:327-343); positions with too few reads are skipped, the chain ends where no read is left (:310-325).
+ * nkeep = 0: the best path; otherwise nkeep sampled paths, drawn backwards with rand() from
+ * T[cur][i] * fwd_i^atten (:105-131, T with FOUR advance lengths and the diagonal overwritten by stay, :134-169). */
+std::vector<std::string> viterbi_mutate(Region& R, int nkeep, double skip, double stay, double mut_min, double mut_max)
+{
+    const int E = (int)R.events.size();
+    std::vector<Layer> layers(1);
+    for (int d = 0; d < NS; d++) { layers[0].lik[d] = 0; layers[0].from[d] = -1; layers[0].fwd[d] = 1.0 / NS; }
+    int pos = R.events[0].refstart;
+    for (int e = 0; e < E; e++) pos = std::min(pos, R.events[e].refstart);
+    std::vector<double> pool((size_t)NS * E), obs(NS);
+    for (;;)
+    {
+        int used = 0;
+        for (int e = 0; e < E; e++)
+        {
+            const Event& ev = R.events[e];
+            std::vector<int> at;
+            for (size_t i = 0; i < ev.ref_index.size(); i++)
+                if (ev.ref_index[i] == pos)
+                {
+                    at.push_back((int)i);
+                    for (int q = (int)i + 1; q < ev.n0 && ev.ref_align[q] <= pos; q++)
+                        if (ev.ref_align[q] > 0) at.push_back(q);
+                    break;
+                }
+            if (at.empty()) continue;
+            used++;
+            double lvl = 0, sd = 0;
+            for (size_t q = 0; q < at.size(); q++) { lvl += ev.mean[at[q]]; sd += ev.stdv[at[q]]; }
+            lvl = lvl / at.size();
+            sd = sd / at.size();
+            const Model& m = ev.model;
+            const double lsd = std::log(sd);
+            for (int st = 0; st < NS; st++)
+            {
+                const double d = (lvl - m.lev_mean[st]) / m.lev_stdv[st];
+                double l = -0.5 * (d * d + LOG2PI) - m.log_lev[st];
+                const double g = (sd - m.sd_mean[st]) / m.sd_mean[st];
+                l += 0.5 * (m.log_lambda[st] - 3 * lsd - LOG2PI - g * g * m.sd_lambda[st] / sd);
+                pool[(size_t)st * E + used - 1] = l;
+            }
+        }
+        int covering = 0;
+        for (int e = 0; e < E; e++)
+            if (pos >= R.events[e].refstart && pos <= R.events[e].refend) covering++;
+        if (used <= covering * 0.2)
+        {
+            if (covering == 0) break;
+            pos++;
+            continue;
+        }
+        if (used > 1)
+        {
+            int drop = (int)std::floor(used * 0.25);
+            if (drop > used - 2) drop = 0;
+            for (int st = 0; st < NS; st++)
+            {
+                double* v = &pool[(size_t)st * E];
+                std::sort(v, v + used);
+                double sum = 0.0;
+                for (int q = drop; q < used; q++) sum += v[q];
+                obs[st] = sum / (used - drop);
+            }
+        }
+        else
+            for (int st = 0; st < NS; st++) obs[st] = pool[(size_t)st * E];
+        layers.push_back(Layer());
+        chain_step(layers[layers.size() - 2], obs, skip, stay, layers.back());
+        pos++;
+    }
+    std::vector<std::string> out;
+    const Layer& last = layers.back();
+    const int head = (int)(std::max_element(last.lik.begin(), last.lik.end()) - last.lik.begin());
+    const int n = (int)layers.size() - 1;
+    std::vector<int> path;
+    if (nkeep == 0)
+    {
+        int cur = head;
+        for (int i = n - 1; i >= 0; i--) { path.push_back(cur); cur = layers[i + 1].from[cur]; }
+        std::reverse(path.begin(), path.end());
+        out.push_back(path_to_bases(path));
+        return out;
+    }
+    std::vector<double> T((size_t)NS * NS, 0.0);
+    for (int d = 0; d < NS; d++)
+    {
+        double w = 0.25;
+        for (int j = 1; j <= 4; j++)
+        {
+            for (int k = 0; k < (1 << (2 * j)); k++) T[(size_t)d * NS + (d >> (2 * j)) + (k << (10 - 2 * j))] += w;
+            w = w * 0.25 * skip;
+        }
+    }
+    for (int d = 0; d < NS; d++) T[(size_t)d * (NS + 1)] = stay;
+    std::vector<double> pr(NS);
+    for (int s = 0; s < nkeep; s++)
+    {
+        const double atten = mut_min + (mut_max - mut_min) * s / (double)nkeep;
+        path.clear();
+        int cur = head;
+        for (int i = n - 1; i >= 0; i--)
+        {
+            path.push_back(cur);
+            const Layer& L = layers[i + 1];
+            const double r = rand() / (double(RAND_MAX) + 1);
+            for (int q = 0; q < NS; q++) pr[q] = T[(size_t)cur * NS + q] * std::pow(L.fwd[q], atten);
+            double tot = 0;
+            for (int q = 0; q < NS; q++) tot += pr[q];
+            tot = 1.0 / tot;
+            for (int q = 0; q < NS; q++) pr[q] *= tot;
+            double run = 0;
+            int pick = NS - 1;
+            for (int q = 0; q < NS; q++) { run += pr[q]; if (r < run) { pick = q; break; } }
+            cur = pick;
+        }
+        std::reverse(path.begin(), path.end());
+        out.push_back(path_to_bases(path));
+    }
+    return out;
+}
+
 std::string dot(const std::string& s) { return s.empty() ? std::string(".") : s; }
 
 std::string text_of(const std::vector<Mut>& v, bool scored)
@@ -813,8 +1006,15 @@ int orc_mutate(orc_region* r, int n_seeds, const char* const* seeds, int reps, c
     return put(R.bases, seq_out, cap);
 }
 
-/* not restated: the checker for ViterbiMutate is the compiled reference (oracle/_ref) */
-int orc_viterbi_mutate(orc_region*, int, double, double, double, double, char*, int) { return -2; }
+int orc_viterbi_mutate(orc_region* r, int nkeep, double skip_prob, double stay_prob, double mut_min, double mut_max,
+                       char* out, int cap)
+{
+    Region R(r);
+    std::vector<std::string> seqs = viterbi_mutate(R, nkeep, skip_prob, stay_prob, mut_min, mut_max);
+    std::string s;
+    for (size_t i = 0; i < seqs.size(); i++) { s += seqs[i]; s += '\n'; }
+    return put(s, out, cap);
+}
 
 int orc_swfull(const char* seq1, const char* seq2, int* inds1, int* inds2, int cap, int* n, int* score, double* accuracy)
 {

@@ -97,3 +97,19 @@ def test_find_and_map_restatements_match_reference(orc, ref, name):
     assert f1 == f2 and len(f1) > 0 and same_aligns(a1, a2)
     m1, m2 = ref.mutate(reg, seeds, reps=3), orc.mutate(reg, seeds, reps=3)
     assert m1[0] == m2[0] and m1[1] == m2[1] and same_aligns(m1[2], m2[2])
+
+
+@pytest.mark.parametrize("name", ["clean", "draft_partial", "ragged"])
+def test_viterbi_restatement_matches_reference(orc, ref, name):
+    """ViterbiMutate of the restatement against the reference's own C++: the best path (nkeep = 0) and sixteen
+    sampled paths on the same rand() stream (both sides are reseeded before the call)."""
+    reg = region(name)
+    a, _, al = ref.refine(reg)                      # aligned events (ViterbiMutate needs every event aligned)
+    import copy
+    rr = copy.deepcopy(reg)
+    rr.sequence = a
+    for ev, (ra, rl) in zip(rr.events, al):
+        ev.ref_align, ev.ref_like = ra, rl
+    assert orc.viterbi_mutate(rr, nkeep=0) == ref.viterbi_mutate(rr, nkeep=0)
+    got, want = orc.viterbi_mutate(rr, nkeep=16, seed=1), ref.viterbi_mutate(rr, nkeep=16, seed=1)
+    assert got == want and len(want) == 16
