@@ -33,6 +33,19 @@ def ref():
 
 
 @pytest.fixture(scope="session")
+def drv():
+    """Checker for the driver-level tests (FindMutations, Mutate, MapAlignments, ViterbiMutate, swfull): the compiled
+    reference where it is available, else the restatement (which is pinned against it by the CPU tests)."""
+    from oracle import binding
+    if os.path.isdir("/root/reference/cpp"):
+        binding.build("ref")
+    if binding.available("ref") and os.environ.get("PORESEQ_TEST_CHECKER", "ref") != "oracle":
+        return binding.load("ref")
+    binding.build("oracle")
+    return binding.load("oracle")
+
+
+@pytest.fixture(scope="session")
 def ctx():
     from poreseq_b200 import build, poreseqcpp
     if not os.path.exists(build.LIB):

@@ -112,11 +112,11 @@ def test_unusable_and_invalid_bases(ctx, orc):
 
 
 @pytest.mark.parametrize("name", ["draft_partial", "ragged"])
-def test_find_mutations(ctx, ref, name):
+def test_find_mutations(ctx, drv, name):
     """Seed-based candidate discovery (cpp/FindMutations.cpp:24-186): same candidates, same order."""
     reg = region(name)
     seeds = [ev.sequence for ev in reg.events[::2]]
-    want, want_a = ref.find_mutations(reg, seeds)
+    want, want_a = drv.find_mutations(reg, seeds)
     nr = native(ctx, reg)
     got = nr.find_mutations(seeds)
     assert got == want
@@ -124,11 +124,11 @@ def test_find_mutations(ctx, ref, name):
 
 
 @pytest.mark.parametrize("name", ["draft_partial", "ragged"])
-def test_mutate_self(ctx, ref, name):
+def test_mutate_self(ctx, drv, name):
     """PSAlign.Mutate('self') loop: reps x (FindMutations, ScoreMutations, MakeMutations)."""
     reg = region(name)
     seeds = [ev.sequence for ev in reg.events[::2]]
-    want_seq, want_nb, want_a = ref.mutate(reg, seeds, reps=4)
+    want_seq, want_nb, want_a = drv.mutate(reg, seeds, reps=4)
     pa = poreseqcpp.PSAlign()
     pa.sequence, pa.events, pa.params = reg.sequence, [e.copy() for e in reg.events], dict(reg.params)
     nb = pa.Mutate(reps=4)
@@ -136,50 +136,50 @@ def test_mutate_self(ctx, ref, name):
     assert same_aligns([(e.ref_align, e.ref_like) for e in pa.events], want_a)
 
 
-def test_map_alignments_and_realign(ctx, ref):
+def test_map_alignments_and_realign(ctx, drv):
     reg = region("draft_partial")
     rng = np.random.default_rng(3)
     newseq, _ = synth.corrupt_sequence(reg.sequence, 0.08, rng)
-    want_a = ref.map_alignments(reg, newseq)
+    want_a = drv.map_alignments(reg, newseq)
     nr = native(ctx, reg)
     nr.map_alignments(newseq)
     assert same_aligns(native_aligns(nr, reg), want_a)
 
 
 @pytest.mark.parametrize("name", ["clean", "draft_partial", "ragged"])
-def test_viterbi_best_path(ctx, ref, name):
+def test_viterbi_best_path(ctx, drv, name):
     """nkeep=0: Viterbi liks/backptrs are IEEE-exact, so the best-path sequence is identical."""
     reg = region(name)
-    want = ref.viterbi_mutate(reg, nkeep=0)
+    want = drv.viterbi_mutate(reg, nkeep=0)
     got = native(ctx, reg).viterbi_mutate(0)
     assert got == want
 
 
 @pytest.mark.parametrize("name", ["draft_partial", "ragged"])
-def test_viterbi_samples(ctx, ref, name):
+def test_viterbi_samples(ctx, drv, name):
     """nkeep=16 forward-weighted samples on the same libc rand() stream (srand(1) before each side)."""
     reg = region(name)
-    want = ref.viterbi_mutate(reg, nkeep=16, seed=1)
-    ref.srand(1)
+    want = drv.viterbi_mutate(reg, nkeep=16, seed=1)
+    drv.srand(1)
     got = native(ctx, reg).viterbi_mutate(16)
     assert len(got) == 16
     assert got == want
 
 
-def test_mutate_viterbi(ctx, ref):
+def test_mutate_viterbi(ctx, drv):
     """PSAlign.Mutate('viterbi') = ViterbiMutate seeds + Find/Score/Make loop (pyx:415-431)."""
     reg = region("draft_partial")
-    seeds = ref.viterbi_mutate(reg, nkeep=16, seed=1)
-    want_seq, want_nb, want_a = ref.mutate(reg, seeds, reps=4)
+    seeds = drv.viterbi_mutate(reg, nkeep=16, seed=1)
+    want_seq, want_nb, want_a = drv.mutate(reg, seeds, reps=4)
     pa = poreseqcpp.PSAlign()
     pa.sequence, pa.events, pa.params = reg.sequence, [e.copy() for e in reg.events], dict(reg.params)
-    ref.srand(1)
+    drv.srand(1)
     nb = pa.Mutate(seqs='viterbi')
     assert (nb, pa.sequence) == (want_nb, want_seq)
     assert same_aligns([(e.ref_align, e.ref_like) for e in pa.events], want_a)
 
 
-def test_consensus_loop(ctx, ref):
+def test_consensus_loop(ctx, drv):
     """The whole Mutate.py policy on the CUDA path vs the same policy driven through the reference:
     final consensus sequence identical, and better than the draft."""
     from poreseq_b200 import drivers
@@ -193,19 +193,19 @@ def test_consensus_loop(ctx, ref):
         for ev, (ra, rl) in zip(rr.events, al):
             ev.ref_align, ev.ref_like = ra, rl
 
-    ref.srand(1)
-    seq, _, al = ref.mutate(rr, [ev.sequence for ev in rr.events[::2]], reps=4)
+    drv.srand(1)
+    seq, _, al = drv.mutate(rr, [ev.sequence for ev in rr.events[::2]], reps=4)
     rr.sequence = seq; sync(al)
     for _ in range(4):
-        seeds = ref.viterbi_mutate(rr, nkeep=16, seed=None)
-        seq, _, al = ref.mutate(rr, seeds, reps=4)
+        seeds = drv.viterbi_mutate(rr, nkeep=16, seed=None)
+        seq, _, al = drv.mutate(rr, seeds, reps=4)
         rr.sequence = seq; sync(al)
-        seq, nb, al = ref.refine(rr)
+        seq, nb, al = drv.refine(rr)
         rr.sequence = seq; sync(al)
         if nb == 0:
             break
     want = rr.sequence[20:-20]
-    ref.srand(1)
+    drv.srand(1)
     pa = drivers.make_psalign(reg)
     got, acc = drivers.consensus(pa, refseq=reg.truth, reps=4)
     assert got == want
@@ -346,11 +346,11 @@ def test_packed_and_async_batches(orc):
             c.close()
 
 
-def test_config2_full_size(ctx, ref):
+def test_config2_full_size(ctx, drv):
     """BASELINE.json configs[1] at full size (1 kb x 10x, default widths): every one of the 7968 point
     mutation scores bit-identical to the compiled reference (about 4 s of CPU)."""
     reg = synth.make_region(1000, 10, seed=101)
-    want, want_a = ref.score_points(reg)
+    want, want_a = drv.score_points(reg)
     nr = native(ctx, reg, "point_width")
     st, og, mu, sc = nr.score_points()
     assert len(sc) == 8 * (1000 - 4)
@@ -358,13 +358,13 @@ def test_config2_full_size(ctx, ref):
     assert same_aligns(native_aligns(nr, reg), want_a)
 
 
-def test_config3_size_properties(ref):
+def test_config3_size_properties(drv):
     """BASELINE.json configs[2] size (10 kb, 30x = 60 events): ScoreEvents bit-identical to the compiled
     reference (one CPU pass, ~6 s); the full point scan (1157 s on one CPU core) is checked through
     properties: fast vs exact mode agree (decisions identical, scores within 1e-4 relative), 300
     sampled mutations match the reference bit for bit, and re-scoring the realigned region is stable."""
     reg = synth.make_region(10000, 30, seed=102, draft_error=0.01)
-    want_s, _, want_a = ref.score_alignments(reg)
+    want_s, _, want_a = drv.score_alignments(reg)
     cx, cf = poreseqcpp.Context(0), poreseqcpp.Context(0)
     cf.set_precision("fast")
     try:
@@ -381,7 +381,7 @@ def test_config3_size_properties(ref):
         rng = np.random.default_rng(5)
         pick = np.sort(rng.choice(len(sc), 300, replace=False))
         reg.params = dict(reg.params, scoring_width=reg.params["point_width"])
-        w, _ = ref.score_mutations(reg, [int(st[i]) for i in pick], [chr(og[i]) if og[i] else "" for i in pick],
+        w, _ = drv.score_mutations(reg, [int(st[i]) for i in pick], [chr(og[i]) if og[i] else "" for i in pick],
                                    [chr(mu[i]) if mu[i] else "" for i in pick])
         assert np.array_equal(sc[pick], w)
     finally:
@@ -405,7 +405,7 @@ def test_oversized_job_is_split(orc, monkeypatch):
         c.close()
 
 
-def test_swfull_device_matches_host(ctx, ref):
+def test_swfull_device_matches_host(ctx, drv):
     """GPU Smith-Waterman (ps_sw.cu) vs the reference's swfull: score, accuracy and every aligned index
     pair identical, including tie-heavy low-complexity sequences and sizes that are not multiples of
     the thread strip."""
@@ -420,7 +420,7 @@ def test_swfull_device_matches_host(ctx, ref):
     cases.append(("".join(rng.choice(list("AC"), 700)), "".join(rng.choice(list("AC"), 650))))   # unrelated, two letters
     cases.append(("ACGT" * 50, "TTTT"))
     for a, b in cases:
-        want_acc, want_score, want_pairs = ref.swfull(a, b)
+        want_acc, want_score, want_pairs = drv.swfull(a, b)
         score, acc, pairs = poreseqcpp.swalign_device(ctx, a, b)
         assert [tuple(p) for p in pairs] == [tuple(p) for p in want_pairs], (len(a), len(b))
         assert score == want_score
