@@ -67,6 +67,65 @@ def aligns_array(al):
     return np.concatenate([np.stack(a) for a in al], axis=1) if al else np.zeros((2, 0))
 
 
+def noisy(seq, rng, rate):
+    """Deterministic corruption of a sequence (substitutions, deletions, insertions at rate/3 each)."""
+    out = []
+    for ch in seq:
+        u = rng.random()
+        if u < rate / 3:
+            continue
+        if u < 2 * rate / 3:
+            out.append("ACGT"[rng.integers(4)])
+            continue
+        out.append(ch)
+        if u < rate:
+            out.append("ACGT"[rng.integers(4)])
+    return "".join(out)
+
+
+def aligned_copy(reg, seq, al):
+    """The region with a new sequence and the given per-event alignments."""
+    import copy
+    rr = copy.deepcopy(reg)
+    rr.sequence = seq
+    for ev, (ra, rl) in zip(rr.events, al):
+        ev.ref_align, ev.ref_like = ra, rl
+    return rr
+
+
+def driver_fixture(ref, reg):
+    """Outputs of the reference's driver-level entry points (swfull, MapAlignments, FindMutations, the Mutate loop,
+    ViterbiMutate) on a region of the g_*.npz files: the d_*.npz files."""
+    rng = np.random.default_rng(23)
+    seeds = [ev.sequence for ev in reg.events[::2]] + [noisy(reg.sequence, rng, 0.08)]
+    seeds.append(seeds[0])
+    d = {"seeds": np.array(seeds)}
+    acc, score, pairs = ref.swfull(reg.sequence, seeds[-2])
+    d["sw_acc"], d["sw_score"], d["sw_pairs"] = np.array(acc), np.array(score), np.array(pairs, dtype=np.int32).reshape(-1, 2)
+    d["ma_aligns"] = aligns_array(ref.map_alignments(reg, seeds[-2]))
+    fm, a = ref.find_mutations(reg, seeds)
+    d["fm_start"] = np.array([m[0] for m in fm], dtype=np.int32)
+    d["fm_orig"], d["fm_mut"] = np.array([m[1] for m in fm]), np.array([m[2] for m in fm])
+    d["fm_aligns"] = aligns_array(a)
+    seq, nb, a = ref.mutate(reg, seeds, reps=3)
+    d["mu_seq"], d["mu_nbases"], d["mu_aligns"] = np.array(seq), np.array(nb), aligns_array(a)
+    rseq, _, ral = ref.refine(reg)                    # ViterbiMutate needs every event aligned
+    rr = aligned_copy(reg, rseq, ral)
+    d["vit_best"] = np.array(ref.viterbi_mutate(rr, nkeep=0))
+    d["vit_samples"] = np.array(ref.viterbi_mutate(rr, nkeep=4, seed=1))
+    return d
+
+
+def split_aligns(arr, reg):
+    """Inverse of aligns_array for a region: [(ref_align, ref_like)] per event."""
+    out, at = [], 0
+    for ev in reg.events:
+        n = len(ev.mean)
+        out.append((arr[0, at:at + n], arr[1, at:at + n]))
+        at += n
+    return out
+
+
 def main():
     ref = binding.load("ref")
     for name, kw in GOLDEN:
@@ -84,6 +143,9 @@ def main():
         d["rf_seq"], d["rf_nbases"], d["rf_aligns"] = np.array(seq), np.array(nb), aligns_array(a)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
         print(name, "events", len(reg.events), "points", len(pts), "refine", nb)
+        dd = driver_fixture(ref, reg)
+        np.savez_compressed(os.path.join(HERE, name.replace("g_", "d_") + ".npz"), **dd)
+        print("  drivers: found", len(dd["fm_start"]), "mutate", int(dd["mu_nbases"]), "viterbi", len(str(dd["vit_best"][0])))
 
 
 if __name__ == "__main__":

@@ -456,3 +456,52 @@ def test_long_replacements_warp_and_thread_forms(orc, monkeypatch, precision):
             bad = np.nonzero((got != want) & ~((np.array([len(m) for m in mu]) <= 1) & (np.abs(got - want) <= 1e-4 * np.abs(want))))[0]
         assert len(bad) == 0, (no_warp, [(int(i), st[i], og[i], mu[i], got[i], want[i]) for i in bad[:8]])
         assert same_aligns(native_aligns(nr, reg), want_a)
+
+
+def _golden_paths():
+    import glob
+    import os
+    return sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "g_*.npz")))
+
+
+@pytest.mark.parametrize("path", _golden_paths(), ids=lambda p: p.split("/")[-1])
+def test_native_matches_golden(ctx, path):
+    """The CUDA path against the committed outputs of the reference's own C++ (tests/golden/g_*.npz for the DP entry
+    points, d_*.npz for the drivers) with no CPU checker in the loop: every number bit for bit."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden import aligned_copy, aligns_array, split_aligns, unpack_region
+    import ctypes
+    z, d = np.load(path), np.load(path.replace("g_", "d_"))
+    reg = unpack_region(z)
+    nr = native(ctx, reg)
+    s, l = nr.score_alignments(True)
+    assert np.array_equal(s, z["sa_scores"]) and np.array_equal(l, z["sa_likes"])
+    assert np.array_equal(aligns_array(native_aligns(nr, reg)), z["sa_aligns"])
+    nr = native(ctx, reg, "point_width")
+    assert np.array_equal(nr.score_points()[3], z["sp_scores"])
+    assert np.array_equal(aligns_array(native_aligns(nr, reg)), z["sp_aligns"])
+    sm = native(ctx, reg).score_mutations(z["sm_start"].tolist(), z["sm_orig"].tolist(), z["sm_mut"].tolist())
+    assert np.array_equal(sm, z["sm_scores"])
+    nr = native(ctx, reg, "point_width")
+    assert nr.refine() == int(z["rf_nbases"]) and nr.sequence() == str(z["rf_seq"])
+    assert np.array_equal(aligns_array(native_aligns(nr, reg)), z["rf_aligns"])
+    # drivers
+    seeds = d["seeds"].tolist()
+    score, acc, pairs = poreseqcpp.swalign_device(ctx, reg.sequence, seeds[-2])
+    assert (acc, score) == (float(d["sw_acc"]), int(d["sw_score"])) and pairs == [tuple(p) for p in d["sw_pairs"].tolist()]
+    assert poreseqcpp.swalign(reg.sequence, seeds[-2]) == (float(d["sw_acc"]), [tuple(p) for p in d["sw_pairs"].tolist()])
+    nr = native(ctx, reg)
+    nr.map_alignments(seeds[-2])
+    assert np.array_equal(aligns_array(native_aligns(nr, reg)), d["ma_aligns"])
+    nr = native(ctx, reg)
+    assert nr.find_mutations(seeds) == list(zip(d["fm_start"].tolist(), d["fm_orig"].tolist(), d["fm_mut"].tolist()))
+    assert np.array_equal(aligns_array(native_aligns(nr, reg)), d["fm_aligns"])
+    nr = native(ctx, reg)
+    assert nr.mutate(seeds, reps=3) == int(d["mu_nbases"]) and nr.sequence() == str(d["mu_seq"])
+    assert np.array_equal(aligns_array(native_aligns(nr, reg)), d["mu_aligns"])
+    rr = aligned_copy(reg, str(z["rf_seq"]), split_aligns(z["rf_aligns"], reg))
+    assert native(ctx, rr).viterbi_mutate(0) == d["vit_best"].tolist()
+    ctypes.CDLL(None).srand(ctypes.c_uint(1))          # ViterbiMutate draws from the process-global rand() stream
+    assert native(ctx, rr).viterbi_mutate(4) == d["vit_samples"].tolist()

@@ -9,10 +9,10 @@ import numpy as np
 import pytest
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
-from make_golden import aligns_array, unpack_region  # noqa: E402
+from make_golden import aligned_copy, aligns_array, split_aligns, unpack_region  # noqa: E402
 from util import CASES, edge_mutations, region, same_aligns  # noqa: E402
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")))
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "g_*.npz")))
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
@@ -113,3 +113,24 @@ def test_viterbi_restatement_matches_reference(orc, ref, name):
     assert orc.viterbi_mutate(rr, nkeep=0) == ref.viterbi_mutate(rr, nkeep=0)
     got, want = orc.viterbi_mutate(rr, nkeep=16, seed=1), ref.viterbi_mutate(rr, nkeep=16, seed=1)
     assert got == want and len(want) == 16
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_restatement_matches_driver_golden(orc, path):
+    """The driver-level restatements against the committed outputs of the reference (tests/golden/d_*.npz): swfull,
+    MapAlignments, FindMutations (candidates in order), the Mutate loop, ViterbiMutate (best path and 4 samples)."""
+    z = np.load(path)
+    d = np.load(path.replace("g_", "d_"))
+    reg = unpack_region(z)
+    seeds = d["seeds"].tolist()
+    acc, score, pairs = orc.swfull(reg.sequence, seeds[-2])
+    assert (acc, score) == (float(d["sw_acc"]), int(d["sw_score"])) and pairs == [tuple(p) for p in d["sw_pairs"].tolist()]
+    assert np.array_equal(aligns_array(orc.map_alignments(reg, seeds[-2])), d["ma_aligns"])
+    fm, a = orc.find_mutations(reg, seeds)
+    assert fm == list(zip(d["fm_start"].tolist(), d["fm_orig"].tolist(), d["fm_mut"].tolist()))
+    assert np.array_equal(aligns_array(a), d["fm_aligns"])
+    seq, nb, a = orc.mutate(reg, seeds, reps=3)
+    assert seq == str(d["mu_seq"]) and nb == int(d["mu_nbases"]) and np.array_equal(aligns_array(a), d["mu_aligns"])
+    rr = aligned_copy(reg, str(z["rf_seq"]), split_aligns(z["rf_aligns"], reg))
+    assert orc.viterbi_mutate(rr, nkeep=0) == d["vit_best"].tolist()
+    assert orc.viterbi_mutate(rr, nkeep=4, seed=1) == d["vit_samples"].tolist()
