@@ -210,6 +210,23 @@ class PackedRegion(object):
         self.seq2d = [(getattr(ev, "sequence", "") or "") for ev in events]
         self._seq2d_c = _cstrs(self.seq2d)
 
+    @classmethod
+    def from_arrays(cls, sequence, params, n0, mean, stdv, ref_align, ref_like, model_index, models, probs, complement, seq2d):
+        """A PackedRegion over arrays that already have the packed layout (e.g. views into an event-pack file,
+        poreseq_b200/eventpack.py): nothing is copied, the arrays must stay alive as long as the object."""
+        self = cls.__new__(cls)
+        self.sequence = sequence.encode("ascii") if isinstance(sequence, str) else bytes(sequence)
+        self.params = dict(params)
+        self.n0 = np.ascontiguousarray(n0, dtype=np.int32)
+        self.mean, self.stdv, self.ref_align, self.ref_like = (np.ascontiguousarray(a, dtype="f8") for a in (mean, stdv, ref_align, ref_like))
+        self.model_index = np.ascontiguousarray(model_index, dtype=np.int32)
+        self.models = np.ascontiguousarray(models, dtype="f8").reshape(-1, 4, 1024)
+        self.probs = np.ascontiguousarray(probs, dtype="f8").reshape(-1, 4)
+        self.complement = np.ascontiguousarray(complement, dtype=np.int32)
+        self.seq2d = list(seq2d)
+        self._seq2d_c = _cstrs(self.seq2d)
+        return self
+
     def nbytes(self):
         return (self.mean.nbytes + self.stdv.nbytes + self.ref_align.nbytes + self.ref_like.nbytes + self.models.nbytes +
                 self.probs.nbytes + self.n0.nbytes + self.model_index.nbytes + self.complement.nbytes + len(self.sequence))

@@ -505,3 +505,18 @@ def test_native_matches_golden(ctx, path):
     assert native(ctx, rr).viterbi_mutate(0) == d["vit_best"].tolist()
     ctypes.CDLL(None).srand(ctypes.c_uint(1))          # ViterbiMutate draws from the process-global rand() stream
     assert native(ctx, rr).viterbi_mutate(4) == d["vit_samples"].tolist()
+
+
+def test_event_pack_regions_score_like_in_memory_ones(ctx, orc, tmp_path):
+    """Regions read back from an event-pack file (memory-mapped views, poreseq_b200/eventpack.py) go through the batched
+    entry point and give the checker's scores."""
+    from poreseq_b200 import eventpack
+    regs = [region("clean"), region("draft_partial"), region("ragged")]
+    path = str(tmp_path / "regions.psep")
+    eventpack.write_pack(path, regs)
+    nrs = poreseqcpp.native_regions_from_packed(ctx, list(eventpack.read_pack(path)), "point_width")
+    out = poreseqcpp.score_points_batch(ctx, nrs)
+    for reg, o in zip(regs, out):
+        want, _ = orc.score_points(reg)
+        assert np.array_equal(o[3], np.array([w[3] for w in want]))
+    poreseqcpp.close_regions(nrs)

@@ -156,3 +156,31 @@ def test_bulk_create_and_destroy_without_gpu():
     ctx.lib.ps_regions_destroy(None, 0)
     h, d = ctx.last_bytes()
     assert (h, d) == (0, 0)                            # no batch has run on this context
+
+
+def test_event_pack_round_trip(tmp_path):
+    """Event-pack files (poreseq_b200/eventpack.py): regions written to one flat file come back as PackedRegion views with
+    identical contents, and marshal into native regions like the in-memory ones (host only)."""
+    from poreseq_b200 import eventpack, poreseqcpp, synth
+    regs = [synth.make_region(150 + 30 * k, 2 + k, seed=40 + k, draft_error=0.05 * k, partial=0.2 * k,
+                              params=dict(realign_width=40, scoring_width=12, point_width=6, lik_offset=4.5)) for k in range(3)]
+    path = str(tmp_path / "regions.psep")
+    eventpack.write_pack(path, regs)
+    pack = eventpack.read_pack(path)
+    assert len(pack) == 3
+    for reg, got in zip(regs, pack):
+        want = poreseqcpp.PackedRegion(reg.sequence, reg.events, reg.params)
+        assert got.sequence == want.sequence and got.params == {k: want.params[k] for k in want.params}
+        for name in ("n0", "mean", "stdv", "ref_align", "ref_like", "model_index", "models", "probs", "complement"):
+            a, b = getattr(got, name), getattr(want, name)
+            assert a.dtype == b.dtype and np.array_equal(a, b), name
+        assert got.seq2d == want.seq2d
+    ctx = poreseqcpp.Context(0)
+    nrs = poreseqcpp.native_regions_from_packed(ctx, list(pack), "point_width")
+    assert [n.sequence() for n in nrs] == [r.sequence for r in regs]
+    assert [ctx.lib.ps_region_num_events(n.handle) for n in nrs] == [len(r.events) for r in regs]
+    poreseqcpp.close_regions(nrs)
+    with open(path, "r+b") as f:
+        f.write(b"XXXX")
+    with pytest.raises(ValueError):
+        eventpack.read_pack(path)
