@@ -64,3 +64,82 @@ def variant(pa, muts=None, var_seqs=None, region_start=0):
     for ms in scores:
         ms.start += region_start
     return scores
+
+
+# ---------------------------------------------------------------------------------------------------------
+# `poreseq train` (poreseq/cmdline.py:246-267, poreseq/Params.py:31-60): every iteration tries 16
+# random variations of the transition parameters, runs the consensus loop with each, keeps the most accurate.  The
+# reference gives every variant its own process; here the variants are regions in flight on one GPU (one host thread
+# and one context each), like the consensus throughput mode.
+
+def vary_params(params, rng, count=16):
+    """VaryParams (Params.py:31-60): `count` copies of params, each with 3 randomly chosen `_t` / `_c` parameters multiplied
+    by gauss(1, 0.15).  `rng` is a random.Random (the reference uses the module-level generator)."""
+    names = [k for k in params.keys() if k[-2:] == '_t' or k[-2:] == '_c']
+    out = []
+    for _ in range(count):
+        p = dict(params)
+        for k in rng.sample(names, 3):
+            p[k] *= rng.gauss(1.0, 0.15)
+        out.append(p)
+    return out
+
+
+def set_params(events, params):
+    """PSEvent.setparams (poreseq/EventData.py:286-312): `skip_t` sets model.prob_skip of the template events, `skip_c` of
+    the complement ones, likewise stay / extend / insert."""
+    for ev in events:
+        for k, v in params.items():
+            name = 'prob_' + k[:-2]
+            if not hasattr(ev.model, name):
+                continue
+            if (k[-2:] == '_t' and not ev.model.complement) or (k[-2:] == '_c' and ev.model.complement):
+                setattr(ev.model, name, v)
+
+
+def train(region, params, iters=1, variants=16, in_flight=8, reps=4, seed=None, device=None, log=None):
+    """The training loop on one loaded region with known truth (`region.truth`): returns (best params, [best accuracy per
+    iteration]).  Every variant starts from the region's draft sequence and seed alignments."""
+    import copy
+    import queue
+    import random
+    import threading
+    rng = random.Random(seed)
+    params = dict(params)
+    ctxs = [poreseqcpp.Context(device if device is not None else poreseqcpp.default_context().device) for _ in range(in_flight)]
+    history = []
+    try:
+        for it in range(iters):
+            plist = vary_params(params, rng, variants)
+            accs = [None] * len(plist)
+            todo = queue.Queue()
+            for k in range(len(plist)):
+                todo.put(k)
+
+            def worker(ctx):
+                while True:
+                    try:
+                        k = todo.get_nowait()
+                    except queue.Empty:
+                        return
+                    reg = copy.deepcopy(region)
+                    set_params(reg.events, plist[k])
+                    reg.params = dict(reg.params, **{q: v for q, v in plist[k].items() if q in ("lik_offset",)})
+                    pa = make_psalign(reg)
+                    pa.ctx = ctx
+                    accs[k] = consensus(pa, refseq=region.truth, reps=reps)[1]
+
+            ths = [threading.Thread(target=worker, args=(c,)) for c in ctxs]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+            best = int(np.argmax(accs))                    # cmdline.py:261: first maximum
+            params = plist[best]
+            history.append(accs[best])
+            if log is not None:
+                log.write('Best at iter {}: {}\n'.format(it + 1, accs[best]))
+    finally:
+        for c in ctxs:
+            c.close()
+    return params, history

@@ -520,3 +520,16 @@ def test_event_pack_regions_score_like_in_memory_ones(ctx, orc, tmp_path):
         want, _ = orc.score_points(reg)
         assert np.array_equal(o[3], np.array([w[3] for w in want]))
     poreseqcpp.close_regions(nrs)
+
+
+def test_train_loop_runs_variants_in_flight():
+    """`poreseq train` restated over a loaded region (drivers.train): every iteration scores the variants with several
+    consensus loops in flight on one GPU and keeps the most accurate parameter set."""
+    from poreseq_b200 import drivers
+    reg = synth.make_region(300, 3, seed=21, draft_error=0.08, params=dict(realign_width=60, scoring_width=15, point_width=8))
+    base = dict(skip_t=0.141, skip_c=0.088, stay_t=0.043, stay_c=0.057, extend_t=0.072, extend_c=0.046,
+                insert_t=0.020, insert_c=0.025, lik_offset=4.5)
+    best, hist = drivers.train(reg, base, iters=2, variants=4, in_flight=2, reps=2, seed=9, device=0)
+    assert len(hist) == 2 and all(90.0 <= a <= 100.0 for a in hist)
+    assert set(best) == set(base) and best["lik_offset"] == 4.5
+    assert 1 <= sum(best[k] != base[k] for k in base) <= 6

@@ -184,3 +184,24 @@ def test_event_pack_round_trip(tmp_path):
         f.write(b"XXXX")
     with pytest.raises(ValueError):
         eventpack.read_pack(path)
+
+
+def test_train_parameter_variation():
+    """vary_params / set_params of the training driver (poreseq/Params.py:31-60, poreseq/EventData.py:286-312)."""
+    import random
+    from poreseq_b200 import drivers, synth
+    base = dict(realign_width=300, lik_offset=4.5, skip_t=0.141, skip_c=0.088, stay_t=0.043, stay_c=0.057,
+                extend_t=0.072, extend_c=0.046, insert_t=0.020, insert_c=0.025)
+    vs = drivers.vary_params(base, random.Random(5), 16)
+    assert len(vs) == 16
+    for v in vs:
+        changed = [k for k in base if v[k] != base[k]]
+        assert len(changed) == 3 and all(k[-2:] in ("_t", "_c") for k in changed)
+        assert v["lik_offset"] == 4.5 and v["realign_width"] == 300
+    assert vs == drivers.vary_params(base, random.Random(5), 16)          # reproducible from the generator
+    reg = synth.make_region(120, 2, seed=3)
+    drivers.set_params(reg.events, dict(skip_t=0.3, skip_c=0.4, insert_c=0.5, lik_offset=9.0))
+    for ev in reg.events:
+        assert ev.model.prob_skip == (0.4 if ev.model.complement else 0.3)
+        if ev.model.complement:
+            assert ev.model.prob_insert == 0.5
