@@ -822,11 +822,11 @@ __device__ void dev_updaterefs(const double* ra, double* ri, int n0, int& empty,
 
 // k_backtrace: one WARP per event.  The best path is followed from the best cell through the packed step
 // bytes (cpp/Alignment.cpp:516-605).  A pointer chase through global memory costs one memory round trip
-// per move, so the warp fetches a block of 8 columns x 16 rows below and left of the current cell in one
-// go -- in the wavefront-major layout a 2x2 tile is one 32-bit word of step bytes, lane l takes the tile of
-// (strip s_hi - (l & 3), row pair r_hi - (l >> 2)) -- walks inside the block with the words handed around
+// per move, so the warp fetches a block of 16 columns x 16 rows below and left of the current cell in one
+// go -- in the wavefront-major layout a 2x2 tile is one 32-bit word of step bytes, lane l takes the tiles of
+// (strips s_hi - (l & 3) and s_hi - 4 - (l & 3), row pair r_hi - (l >> 2)) -- walks inside the block with the words handed around
 // by __shfl_sync (the walk itself is uniform across the warp), and fetches the next block where the walk
-// leaves this one: one round trip per ~10 moves.  Every visited level records its column and matrix; the
+// leaves this one: one round trip per ~16 moves.  Every visited level records its column and matrix; the
 // warp then gathers ref_like in parallel and lane 0 rebuilds ref_index.  BT_WARPS events per CTA, their
 // per-level scratch in shared memory when the events fit.
 constexpr int BT_WARPS = 4;
@@ -854,16 +854,19 @@ __global__ void __launch_bounds__(32 * BT_WARPS) k_backtrace(Batch b, int smem_l
     const int ts = ev.ts;
     while (go)
     {
-        // block of strips s_hi-3 .. s_hi and row pairs r_hi-7 .. r_hi around the current cell (its top right corner)
+        // block of strips s_hi-7 .. s_hi and row pairs r_hi-7 .. r_hi around the current cell (its top right corner):
+        // 16 columns x 16 rows, two tile words per lane (strips s and s - 4 of row pair r)
         const int s_hi = (j - 1) >> 1, r_hi = (i - 1) >> 1;
         const int s = s_hi - (lane & 3), r = r_hi - (lane >> 2);
-        unsigned word = (unsigned)ST_STOP * 0x01010101u;
+        unsigned word = (unsigned)ST_STOP * 0x01010101u, word2 = word;
         if (s >= 0 && r >= 0)
             word = *reinterpret_cast<const unsigned*>(b.Fstep + ev.band_off + ((long long)(s + r) * ts + (s % ts)) * 4);
-        // bands of the block's 8 columns: lane c holds column 2 (s_hi - 3) + 1 + c
-        const int kcol0 = 2 * (s_hi - 3) + 1;
+        if (s >= 4 && r >= 0)
+            word2 = *reinterpret_cast<const unsigned*>(b.Fstep + ev.band_off + ((long long)(s - 4 + r) * ts + ((s - 4) % ts)) * 4);
+        // bands of the block's 16 columns: lane c holds column 2 (s_hi - 7) + 1 + c
+        const int kcol0 = 2 * (s_hi - 7) + 1;
         int ci0 = 1, ci1 = 0;
-        if (lane < 8)
+        if (lane < 16)
         {
             const int k = kcol0 + lane;
             if (k >= 1 && k <= N) { const long long g = ev.col_off + k; ci0 = b.Fi0[g]; ci1 = ci0 + b.Flen[g] - 1; }
@@ -874,7 +877,9 @@ __global__ void __launch_bounds__(32 * BT_WARPS) k_backtrace(Batch b, int smem_l
             if (!(i > 0 && j > 0)) { go = false; break; }
             if (j < jlo || i < ilo) break;                       // left the block: fetch the next one
             const int sj = (j - 1) >> 1, rix = (i - 1) >> 1;
-            const unsigned w = __shfl_sync(0xffffffffu, word, (s_hi - sj) + 4 * (r_hi - rix));
+            const int ds = s_hi - sj, owner = (ds & 3) + 4 * (r_hi - rix);
+            const unsigned wa = __shfl_sync(0xffffffffu, word, owner), wb = __shfl_sync(0xffffffffu, word2, owner);
+            const unsigned w = ds < 4 ? wa : wb;
             const int b0 = __shfl_sync(0xffffffffu, ci0, j - kcol0), b1 = __shfl_sync(0xffffffffu, ci1, j - kcol0);
             int st = ST_STOP;
             if (i >= b0 && i <= b1) st = (int)((w >> (8 * ((((i - 1) & 1) << 1) + ((j - 1) & 1)))) & 0xffu);
