@@ -230,7 +230,7 @@ def make_region(length=1000, coverage=10, seed=1, draft_error=0.0, read_error=0.
         for model in models:
             ev = simulate_event(truth_states, model, rng, first, last, p_unaligned=p_unaligned, jitter=jitter)
             al = ev.ref_align > 0
-            idx = (ev.ref_align[al] - 1).astype(np.int64)
+            idx = np.clip((ev.ref_align[al] - 1).astype(np.int64), 0, len(pos_map) - 1)   # jitter may step past the end
             ev.ref_align[al] = np.minimum(pos_map[idx] + 1, n_draft_states).astype("f8")
             ev.sequence = read_seq
             ev.makecontiguous()
