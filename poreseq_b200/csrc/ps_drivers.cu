@@ -283,7 +283,7 @@ int ps_swfull(const char* seq1, const char* seq2, int* inds1, int* inds2, int ca
 
 int ps_swfull_device(ps_ctx* ctx, const char* seq1, const char* seq2, int* inds1, int* inds2, int cap, int* n, int* score, double* accuracy)
 {
-    if (!ctx || !seq1 || !seq2) return PS_E_ARG;
+    if (!ctx || !seq1 || !seq2) return PS_BAD_ARGS(ctx, "ps_swfull_device");
     std::vector<SWResult> out;
     int rc = psi_swfull_batch(ctx, std::string(seq1), std::vector<std::string>(1, std::string(seq2)), out);
     if (rc == PS_E_ARG) { ps_set_error(ctx, "ps_swfull_device: sequences of 1..16384 bases only"); return rc; }
@@ -299,14 +299,14 @@ int ps_swfull_device(ps_ctx* ctx, const char* seq1, const char* seq2, int* inds1
 
 int ps_map_alignments(ps_region* R, const char* newseq)
 {
-    if (!R || !newseq) return PS_E_ARG;
+    if (!R || !newseq) return PS_BAD_ARGS(R ? R->ctx : nullptr, "ps_map_alignments");
     psi_map_alignments(R, std::string(newseq));
     return PS_OK;
 }
 
 int ps_find_mutations(ps_region* R, int n_seeds, const char* const* seeds, int* n_found)
 {
-    if (!R || n_seeds < 0 || (n_seeds > 0 && !seeds)) return PS_E_ARG;
+    if (!R || n_seeds < 0 || (n_seeds > 0 && !seeds)) return PS_BAD_ARGS(R ? R->ctx : nullptr, "ps_find_mutations");
     std::vector<std::string> sv(n_seeds);
     for (int i = 0; i < n_seeds; i++) sv[i] = seeds[i] ? seeds[i] : "";
     TRY(ps_find_mutation_list(R, sv, R->found));
@@ -316,7 +316,7 @@ int ps_find_mutations(ps_region* R, int n_seeds, const char* const* seeds, int* 
 
 int ps_get_found_mutation(ps_region* R, int i, int* start, char* orig, int orig_cap, char* mut, int mut_cap)
 {
-    if (!R || i < 0 || i >= (int)R->found.size()) return PS_E_ARG;
+    if (!R || i < 0 || i >= (int)R->found.size()) return PS_BAD_ARGS(R ? R->ctx : nullptr, "ps_get_found_mutation");
     const HostMut& m = R->found[i];
     if ((int)m.orig.size() + 1 > orig_cap || (int)m.mut.size() + 1 > mut_cap) return PS_E_CAPACITY;
     if (start) *start = m.start;
@@ -327,7 +327,7 @@ int ps_get_found_mutation(ps_region* R, int i, int* start, char* orig, int orig_
 
 int ps_found_mutation_sizes(ps_region* R, int i, int* n_orig, int* n_mut)
 {
-    if (!R || i < 0 || i >= (int)R->found.size()) return PS_E_ARG;
+    if (!R || i < 0 || i >= (int)R->found.size()) return PS_BAD_ARGS(R ? R->ctx : nullptr, "ps_found_mutation_sizes");
     if (n_orig) *n_orig = (int)R->found[i].orig.size();
     if (n_mut) *n_mut = (int)R->found[i].mut.size();
     return PS_OK;
@@ -335,7 +335,7 @@ int ps_found_mutation_sizes(ps_region* R, int i, int* n_orig, int* n_mut)
 
 int ps_mutate(ps_region* R, int n_seeds, const char* const* seeds, int reps, int* totbases)
 {
-    if (!R || n_seeds < 0 || (n_seeds > 0 && !seeds)) return PS_E_ARG;
+    if (!R || n_seeds < 0 || (n_seeds > 0 && !seeds)) return PS_BAD_ARGS(R ? R->ctx : nullptr, "ps_mutate");
     std::vector<std::string> sv(n_seeds);
     for (int i = 0; i < n_seeds; i++) sv[i] = seeds[i] ? seeds[i] : "";
     int tot = 0;

@@ -1298,21 +1298,21 @@ long long ps_launch_count(ps_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int ps_set_precision(ps_ctx* ctx, int mode)
 {
-    if (!ctx || (mode != PS_PRECISION_EXACT && mode != PS_PRECISION_FAST)) return PS_E_ARG;
+    if (!ctx || (mode != PS_PRECISION_EXACT && mode != PS_PRECISION_FAST)) return PS_BAD_ARGS(ctx, "ps_set_precision");
     ctx->precision = mode;
     return PS_OK;
 }
 
 int ps_last_timing(ps_ctx* ctx, double* ms)
 {
-    if (!ctx || !ms) return PS_E_ARG;
+    if (!ctx || !ms) return PS_BAD_ARGS(ctx, "ps_last_timing");
     for (int i = 0; i < PS_T_COUNT; i++) ms[i] = ctx->timing[i];
     return PS_OK;
 }
 
 int ps_last_bytes(ps_ctx* ctx, long long* h2d, long long* d2h)
 {
-    if (!ctx) return PS_E_ARG;
+    if (!ctx) return PS_BAD_ARGS(ctx, "ps_last_bytes");
     if (h2d) *h2d = ctx->h2d_bytes;
     if (d2h) *d2h = ctx->d2h_bytes;
     return PS_OK;
@@ -1320,7 +1320,7 @@ int ps_last_bytes(ps_ctx* ctx, long long* h2d, long long* d2h)
 
 int ps_last_cells(ps_ctx* ctx, double* wide, double* narrow)
 {
-    if (!ctx) return PS_E_ARG;
+    if (!ctx) return PS_BAD_ARGS(ctx, "ps_last_cells");
     if (wide) *wide = ctx->wide_cells;
     if (narrow) *narrow = ctx->narrow_cells;
     return PS_OK;
@@ -1350,7 +1350,7 @@ int ps_region_add_event(ps_region* R, int n0, const double* mean, const double* 
                         const double* sd_mean, const double* sd_stdv, int complement, double prob_skip,
                         double prob_stay, double prob_extend, double prob_insert, const char* seq2d)
 {
-    if (!R) return PS_E_ARG;
+    if (!R) return PS_BAD_ARGS(R ? R->ctx : nullptr, "ps_region_add_event");
     ps_ctx* ctx = R->ctx;
     if (n0 < 0 || (n0 > 0 && (!mean || !stdv || !ref_align || !ref_like)) || !level_mean || !level_stdv || !sd_mean || !sd_stdv)
     {
@@ -1386,7 +1386,7 @@ int ps_region_add_events(ps_region* R, int n_events, const int* n0, const double
                          const double* ref_align, const double* ref_like, const int* model_index, int n_models,
                          const double* models, const double* probs, const int* complement, const char* const* seq2d)
 {
-    if (!R) return PS_E_ARG;
+    if (!R) return PS_BAD_ARGS(R ? R->ctx : nullptr, "ps_region_add_events");
     ps_ctx* ctx = R->ctx;
     if (n_events < 0 || n_models < 0 || (n_events > 0 && (!n0 || !model_index || !models || !probs || n_models == 0)))
     {
@@ -1436,7 +1436,7 @@ int ps_region_add_events(ps_region* R, int n_events, const int* n0, const double
 
 int ps_regions_create(ps_ctx* ctx, int n_regions, const ps_region_desc* desc, ps_region** out)
 {
-    if (!ctx || n_regions < 0 || (n_regions > 0 && (!desc || !out))) return PS_E_ARG;
+    if (!ctx || n_regions < 0 || (n_regions > 0 && (!desc || !out))) return PS_BAD_ARGS(ctx, "ps_regions_create");
     std::vector<int> rc(n_regions, PS_OK);
     for (int k = 0; k < n_regions; k++) out[k] = nullptr;
     ps_parallel_for(n_regions, [&](int k) {
@@ -1460,7 +1460,7 @@ int ps_regions_create(ps_ctx* ctx, int n_regions, const ps_region_desc* desc, ps
 
 int ps_region_set_params(ps_region* R, const ps_params* p)
 {
-    if (!R || !p) return PS_E_ARG;
+    if (!R || !p) return PS_BAD_ARGS(R ? R->ctx : nullptr, "ps_region_set_params");
     R->params = *p;
     return PS_OK;
 }
@@ -1470,7 +1470,7 @@ int ps_region_sequence_length(ps_region* R) { return R ? (int)R->bases.size() : 
 
 int ps_region_get_sequence(ps_region* R, char* out, int cap)
 {
-    if (!R || !out) return PS_E_ARG;
+    if (!R || !out) return PS_BAD_ARGS(R ? R->ctx : nullptr, "ps_region_get_sequence");
     if ((int)R->bases.size() + 1 > cap) { ps_set_error(R->ctx, "sequence buffer too small"); return PS_E_CAPACITY; }
     memcpy(out, R->bases.c_str(), R->bases.size() + 1);
     return PS_OK;
@@ -1478,7 +1478,7 @@ int ps_region_get_sequence(ps_region* R, char* out, int cap)
 
 int ps_region_get_event_align(ps_region* R, int e, double* ref_align, double* ref_like)
 {
-    if (!R || e < 0 || e >= (int)R->events.size()) return PS_E_ARG;
+    if (!R || e < 0 || e >= (int)R->events.size()) return PS_BAD_ARGS(R ? R->ctx : nullptr, "ps_region_get_event_align");
     const HostEvent& he = R->events[e];
     if (ref_align) std::copy(he.ref_align.begin(), he.ref_align.end(), ref_align);
     if (ref_like) std::copy(he.ref_like.begin(), he.ref_like.end(), ref_like);
@@ -1487,7 +1487,7 @@ int ps_region_get_event_align(ps_region* R, int e, double* ref_align, double* re
 
 int ps_score_alignments(ps_region* R, double* scores, double* likes)
 {
-    if (!R || !scores) return PS_E_ARG;
+    if (!R || !scores) return PS_BAD_ARGS(R ? R->ctx : nullptr, "ps_score_alignments");
     std::vector<std::vector<double>> sc, lk;
     TRY(ps_run_alignments(R->ctx, std::vector<ps_region*>(1, R), &sc, likes ? &lk : nullptr));
     std::copy(sc[0].begin(), sc[0].end(), scores);
@@ -1511,7 +1511,7 @@ static std::vector<HostMut> gather_muts(int n, const int* start, const char* con
 
 int ps_score_mutations(ps_region* R, int n, const int* start, const char* const* orig, const char* const* mut, double* scores)
 {
-    if (!R || n < 0 || (n > 0 && (!start || !orig || !mut || !scores))) return PS_E_ARG;
+    if (!R || n < 0 || (n > 0 && (!start || !orig || !mut || !scores))) return PS_BAD_ARGS(R ? R->ctx : nullptr, "ps_score_mutations");
     std::vector<HostMut> v = gather_muts(n, start, orig, mut, nullptr);
     TRY(ps_score_mutation_list(R, v));
     for (int i = 0; i < n; i++) scores[i] = v[i].score;
@@ -1520,7 +1520,7 @@ int ps_score_mutations(ps_region* R, int n, const int* start, const char* const*
 
 int ps_score_mutations_partial(ps_region* R, int n, const int* start, const char* const* orig, const char* const* mut, double* partial)
 {
-    if (!R || n < 0 || (n > 0 && (!start || !orig || !mut || !partial))) return PS_E_ARG;
+    if (!R || n < 0 || (n > 0 && (!start || !orig || !mut || !partial))) return PS_BAD_ARGS(R ? R->ctx : nullptr, "ps_score_mutations_partial");
     std::vector<HostMut> v = gather_muts(n, start, orig, mut, nullptr);
     TRY(ps_score_mutation_list(R, v, 0.0));
     for (int i = 0; i < n; i++) partial[i] = v[i].score;
@@ -1543,7 +1543,7 @@ static int emit_points(ps_ctx* ctx, const std::vector<HostMut>& v, int cap, int*
 
 int ps_find_point_mutations(ps_region* R, int cap, int* n, int* start, char* orig, char* mut)
 {
-    if (!R) return PS_E_ARG;
+    if (!R) return PS_BAD_ARGS(R ? R->ctx : nullptr, "ps_find_point_mutations");
     return emit_points(R->ctx, ps_point_mutations(R), cap, n, start, orig, mut, nullptr);
 }
 
@@ -1605,7 +1605,7 @@ int ps_score_points_batch_begin(ps_region* const* regions, int n_regions, int ca
 
 int ps_score_points_batch_end(ps_ctx* ctx, double* scores)
 {
-    if (!ctx) return PS_E_ARG;
+    if (!ctx) return PS_BAD_ARGS(ctx, "ps_score_points_batch_end");
     return job_end(ctx, nullptr, nullptr, scores);
 }
 
@@ -1618,7 +1618,7 @@ int ps_score_points_batch(ps_region* const* regions, int n_regions, int cap, int
 
 int ps_score_points(ps_region* R, int cap, int* n, int* start, char* orig, char* mut, double* scores)
 {
-    if (!R) return PS_E_ARG;
+    if (!R) return PS_BAD_ARGS(R ? R->ctx : nullptr, "ps_score_points");
     int count = 0;
     long long off = 0;
     ps_region* one = R;
@@ -1630,7 +1630,7 @@ int ps_score_points(ps_region* R, int cap, int* n, int* start, char* orig, char*
 int ps_make_mutations(ps_region* R, int n, const int* start, const char* const* orig, const char* const* mut,
                       const double* scores, int* nbases)
 {
-    if (!R || n < 0 || (n > 0 && (!start || !orig || !mut || !scores))) return PS_E_ARG;
+    if (!R || n < 0 || (n > 0 && (!start || !orig || !mut || !scores))) return PS_BAD_ARGS(R ? R->ctx : nullptr, "ps_make_mutations");
     int nb = 0;
     TRY(ps_make_mutation_list(R, gather_muts(n, start, orig, mut, scores), &nb));
     if (nbases) *nbases = nb;
@@ -1639,7 +1639,7 @@ int ps_make_mutations(ps_region* R, int n, const int* start, const char* const* 
 
 int ps_refine(ps_region* R, int* nbases)
 {
-    if (!R) return PS_E_ARG;
+    if (!R) return PS_BAD_ARGS(R ? R->ctx : nullptr, "ps_refine");
     std::vector<HostMut> v = ps_point_mutations(R);
     TRY(ps_score_mutation_list(R, v));
     int nb = 0;

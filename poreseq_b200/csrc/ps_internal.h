@@ -105,6 +105,8 @@ struct ps_region                              // cpp/AlignData.h:24-34
 };
 
 void ps_set_error(ps_ctx* ctx, const char* fmt, ...);
+// PS_E_ARG with a message naming the entry point (ctx may be null: the message is then what ps_last_error(NULL) returns)
+#define PS_BAD_ARGS(ctx_, fn_) (ps_set_error((ctx_), "%s: bad arguments", (fn_)), PS_E_ARG)
 // fn(i) for i in [0, n) on the library's host worker threads (PORESEQ_B200_THREADS, default
 // min(cores, 8)); the caller takes part.  Used for the per-event staging work of a batch.
 void ps_parallel_for(int n, const std::function<void(int)>& fn);

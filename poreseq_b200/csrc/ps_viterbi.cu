@@ -446,7 +446,7 @@ extern "C" {
 
 int ps_viterbi_mutate(ps_region* R, int nkeep, double skip_prob, double stay_prob, double mut_min, double mut_max, int* n_seqs)
 {
-    if (!R || nkeep < 0) return PS_E_ARG;
+    if (!R || nkeep < 0) return PS_BAD_ARGS(R ? R->ctx : nullptr, "ps_viterbi_mutate");
     TRY(ps_viterbi_list(R, nkeep, skip_prob, stay_prob, mut_min, mut_max, R->viterbi));
     if (n_seqs) *n_seqs = (int)R->viterbi.size();
     return PS_OK;
@@ -454,7 +454,7 @@ int ps_viterbi_mutate(ps_region* R, int nkeep, double skip_prob, double stay_pro
 
 int ps_get_viterbi_sequence(ps_region* R, int i, char* out, int cap)
 {
-    if (!R || i < 0 || i >= (int)R->viterbi.size()) return PS_E_ARG;
+    if (!R || i < 0 || i >= (int)R->viterbi.size()) return PS_BAD_ARGS(R ? R->ctx : nullptr, "ps_get_viterbi_sequence");
     const std::string& s = R->viterbi[i];
     if (!out) return (int)s.size();
     if ((int)s.size() + 1 > cap) return PS_E_CAPACITY;

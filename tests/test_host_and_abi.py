@@ -205,3 +205,48 @@ def test_train_parameter_variation():
         assert ev.model.prob_skip == (0.4 if ev.model.complement else 0.3)
         if ev.model.complement:
             assert ev.model.prob_insert == 0.5
+
+
+def test_bad_arguments_are_reported_not_dereferenced():
+    """Error convention of the C-ABI (include/poreseq_b200.h): null handles, null arrays, negative sizes and
+    too-small output buffers return PS_E_ARG / PS_E_CAPACITY with a message naming the entry point; nothing is
+    dereferenced.  (The reference never reports errors from C++; these are the boundary's own.)"""
+    C = ctypes
+    L = poreseqcpp.lib()
+    c = poreseqcpp.Context(0)
+    reg = synth.make_region(30, 1, seed=4)
+    nr = poreseqcpp.NativeRegion(c, reg.sequence, reg.events, reg.params)
+    vp = C.c_void_p
+
+    def call(name, *args):
+        fn = getattr(L, name)
+        saved = fn.argtypes
+        fn.argtypes = None                                 # raw call: let None through as NULL
+        try:
+            return fn(*args)
+        finally:
+            fn.argtypes = saved
+
+    h = vp(nr.handle) if not isinstance(nr.handle, vp) else nr.handle
+    assert call("ps_score_alignments", h, None, None) == -1
+    assert b"ps_score_alignments" in L.ps_last_error(c.handle)
+    assert call("ps_score_mutations", h, C.c_int(3), None, None, None, None) == -1
+    assert b"ps_score_mutations" in L.ps_last_error(c.handle)
+    assert call("ps_make_mutations", h, C.c_int(-1), None, None, None, None, None) == -1
+    assert call("ps_mutate", h, C.c_int(2), None, C.c_int(1), None) == -1
+    assert call("ps_find_mutations", h, C.c_int(2), None, None) == -1
+    assert call("ps_map_alignments", h, None) == -1
+    assert call("ps_region_get_event_align", h, C.c_int(99), None, None) == -1
+    buf = C.create_string_buffer(4)
+    assert call("ps_region_get_sequence", h, buf, C.c_int(4)) == -3
+    n = C.c_int(0)
+    assert call("ps_find_point_mutations", h, C.c_int(3), C.byref(n), None, None, None) == -3 and n.value == 8 * 26
+    for name, args in [("ps_score_alignments", (None, None, None)), ("ps_refine", (None, None)),
+                       ("ps_region_get_sequence", (None, None, C.c_int(0))), ("ps_mutate", (None, C.c_int(0), None, C.c_int(1), None)),
+                       ("ps_viterbi_mutate", (None, C.c_int(0), C.c_double(.1), C.c_double(.1), C.c_double(.1), C.c_double(.1), None)),
+                       ("ps_seq_to_states", (None, C.c_int(5), None)), ("ps_last_timing", (None, None)),
+                       ("ps_score_points_batch", (None, C.c_int(2), C.c_int(10), None, None, None, None, None, None))]:
+        assert call(name, *args) == -1, name
+    call("ps_region_destroy", None)
+    call("ps_destroy", None)
+    nr.close()
