@@ -11,6 +11,7 @@
 #include <cmath>
 #include <condition_variable>
 #include <mutex>
+#include <new>
 #include <thread>
 #include <pthread.h>
 #include <cstdarg>
@@ -54,6 +55,105 @@ void ps_set_error(ps_ctx* ctx, const char* fmt, ...)
             return PS_E_CUDA;                                                                     \
         }                                                                                         \
     } while (0)
+
+// ------------------------------------------------------------------------------------------
+// recycling allocator of the level arrays (ps_internal.h)
+namespace
+{
+constexpr size_t PS_POOL_GRAIN = 1024, PS_POOL_CLASSES = 256, PS_POOL_CAP = (size_t)768 << 20;
+constexpr int PS_POOL_SHARDS = 16;              // a thread works on the shard its id hashes to, and steals from the others
+struct alignas(64) PoolShard
+{
+    std::mutex mu;
+    std::vector<void*> free_list[PS_POOL_CLASSES + 1];
+};
+struct LevelPool
+{
+    PoolShard shard[PS_POOL_SHARDS];
+    std::atomic<size_t> held{0};
+};
+std::atomic<LevelPool*> g_level_pool{nullptr};
+// after fork() the child starts with fresh free lists: a shard mutex may have been held by a thread that does not
+// exist in the child (the parent's blocks stay valid memory, they are just not recycled there)
+void level_pool_forget() { g_level_pool.store(new LevelPool(), std::memory_order_release); }
+LevelPool& level_pool()
+{
+    LevelPool* p = g_level_pool.load(std::memory_order_acquire);
+    if (!p)
+    {
+        static std::once_flag once;
+        std::call_once(once, [] {
+            g_level_pool.store(new LevelPool(), std::memory_order_release);   // never destroyed: regions may be released during process exit
+            pthread_atfork(nullptr, nullptr, level_pool_forget);
+        });
+        p = g_level_pool.load(std::memory_order_acquire);
+    }
+    return *p;
+}
+inline size_t pool_class(size_t bytes) { return (bytes + PS_POOL_GRAIN - 1) / PS_POOL_GRAIN; }
+inline int pool_home()
+{
+    static std::atomic<int> next{0};
+    thread_local int home = next.fetch_add(1, std::memory_order_relaxed) % PS_POOL_SHARDS;
+    return home;
+}
+}
+
+void* ps_pool_alloc(size_t bytes)
+{
+    if (bytes == 0) bytes = 1;
+    const size_t c = pool_class(bytes);
+    if (c <= PS_POOL_CLASSES)
+    {
+        LevelPool& P = level_pool();
+        const int h = pool_home();
+        for (int k = 0; k < PS_POOL_SHARDS; k++)
+        {
+            PoolShard& S = P.shard[(h + k) % PS_POOL_SHARDS];
+            std::unique_lock<std::mutex> g(S.mu, std::defer_lock);
+            if (k == 0) g.lock();
+            else if (!g.try_lock()) continue;
+            std::vector<void*>& f = S.free_list[c];
+            if (!f.empty())
+            {
+                void* p = f.back();
+                f.pop_back();
+                P.held.fetch_sub(c * PS_POOL_GRAIN, std::memory_order_relaxed);
+                return p;
+            }
+        }
+        bytes = c * PS_POOL_GRAIN;
+    }
+    void* p = malloc(bytes);
+    if (!p) throw std::bad_alloc();
+    return p;
+}
+
+void ps_pool_free(void* p, size_t bytes) noexcept
+{
+    if (!p) return;
+    if (bytes == 0) bytes = 1;
+    const size_t c = pool_class(bytes);
+    if (c <= PS_POOL_CLASSES)
+    {
+        LevelPool& P = level_pool();
+        if (P.held.load(std::memory_order_relaxed) + c * PS_POOL_GRAIN <= PS_POOL_CAP)
+        {
+            PoolShard& S = P.shard[pool_home()];
+            std::lock_guard<std::mutex> g(S.mu);
+            try
+            {
+                S.free_list[c].push_back(p);
+                P.held.fetch_add(c * PS_POOL_GRAIN, std::memory_order_relaxed);
+                return;
+            }
+            catch (...) {}
+        }
+    }
+    free(p);
+}
+
+size_t ps_pool_held() { return level_pool().held.load(); }
 
 // ------------------------------------------------------------------------------------------
 // host worker threads: the per-event staging of a batch (log(stdv), band planning, copies into the
@@ -413,7 +513,7 @@ void Job::plan_event(const HostEvent& he, const EvDesc& d, int rw, int* cen, int
     double cells = 0;
     if (!he.ri_empty)
     {
-        const std::vector<double>& ri = he.ref_index;
+        const LevelVec& ri = he.ref_index;
         bool sorted = true;
         for (int i = 1; i < n0 && sorted; i++) sorted = !(ri[i] < ri[i - 1]);
         if (sorted)

@@ -66,6 +66,27 @@ struct HostModel                              // raw inputs of ModelData::setDat
     double trans[4];                          // prob_skip, prob_stay, prob_extend, prob_insert
 };
 
+// Recycling allocator of the per-event level arrays.  A batch of regions is created, scored and destroyed per
+// step; with the default allocator the 30-60 MB of level arrays freed by a destroyed batch are trimmed from the heap
+// and faulted in again by the next one (2/3 of the time of ps_regions_create).  Blocks of up to 256 KB are kept on
+// per-size free lists instead (1 KB size classes, at most PS_POOL_CAP bytes held), larger ones go to malloc.
+void* ps_pool_alloc(size_t bytes);
+void  ps_pool_free(void* p, size_t bytes) noexcept;
+size_t ps_pool_held();                           // bytes on the free lists (tests)
+
+template <class T>
+struct PoolAlloc
+{
+    using value_type = T;
+    PoolAlloc() = default;
+    template <class U> PoolAlloc(const PoolAlloc<U>&) {}
+    T* allocate(size_t n) { return static_cast<T*>(ps_pool_alloc(n * sizeof(T))); }
+    void deallocate(T* p, size_t n) noexcept { ps_pool_free(p, n * sizeof(T)); }
+    template <class U> bool operator==(const PoolAlloc<U>&) const { return true; }
+    template <class U> bool operator!=(const PoolAlloc<U>&) const { return false; }
+};
+typedef std::vector<double, PoolAlloc<double>> LevelVec;
+
 struct HostEvent                              // cpp/EventData.h:78-229
 {
     int n0 = 0;
@@ -73,8 +94,8 @@ struct HostEvent                              // cpp/EventData.h:78-229
     bool complement = false;
     bool ri_empty = true;
     int refstart = -1, refend = -1;
-    std::vector<double> mean, stdv, ref_align, ref_like, ref_index;
-    std::vector<double> levrec;               // 3 doubles per level, the staged LevIn layout (mean, stdv, 3 log stdv), cached
+    LevelVec mean, stdv, ref_align, ref_like, ref_index;
+    LevelVec levrec;               // 3 doubles per level, the staged LevIn layout (mean, stdv, 3 log stdv), cached
     bool ri_stale = false;                    // ref_align was rewritten by a batch; ref_index is rebuilt from it on first use
     int staged = 0;                           // batches this event was staged for (the level records are cached from the second on)
     std::string seq2d;

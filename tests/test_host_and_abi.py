@@ -250,3 +250,40 @@ def test_bad_arguments_are_reported_not_dereferenced():
     call("ps_region_destroy", None)
     call("ps_destroy", None)
     nr.close()
+
+
+def test_recycled_level_arrays_keep_their_contents():
+    """The per-event level arrays come from a recycling allocator (csrc/ps_internal.h PoolAlloc): batches of regions
+    created, read back and destroyed over many cycles, from several threads at once, always hold the caller's data."""
+    import threading
+    from poreseq_b200 import poreseqcpp, synth
+    regs = [synth.make_region(120 + 40 * s, 1 + s % 3, seed=60 + s, partial=0.3, p_unaligned=0.2) for s in range(8)]
+    packs = [poreseqcpp.PackedRegion(r.sequence, r.events, r.params) for r in regs]
+    errors = []
+
+    def cycle(tid):
+        try:
+            ctx = poreseqcpp.Context(0)
+            for it in range(12):
+                pick = [(tid + it + k) % len(regs) for k in range(1 + (tid + it) % 5)]
+                nrs = poreseqcpp.native_regions_from_packed(ctx, [packs[i] for i in pick], "point_width")
+                for i, nr in zip(pick, nrs):
+                    for e, ev in enumerate(regs[i].events):
+                        ra, rl = nr.event_align(e)
+                        if not (np.array_equal(ra, ev.ref_align) and np.array_equal(rl, ev.ref_like)):
+                            errors.append((tid, it, i, e))
+                if it % 2:
+                    poreseqcpp.close_regions(nrs)
+                else:
+                    for nr in nrs:
+                        nr.close()
+            ctx.close()
+        except Exception as ex:                        # noqa: BLE001
+            errors.append(repr(ex))
+
+    threads = [threading.Thread(target=cycle, args=(t,)) for t in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:4]
