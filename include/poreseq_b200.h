@@ -195,6 +195,25 @@ int         ps_get_viterbi_sequence(ps_region* r, int i, char* out, int cap);
  * swfull + fillinds, then every level's ref_align is carried over to newseq. */
 int         ps_map_alignments(ps_region* r, const char* newseq);
 
+/* ---- event-pack files ------------------------------------------------------------------------- */
+/* A flat binary file of many regions (layout: poreseq_b200/eventpack.py) that is memory-mapped and marshalled without
+ * Python objects.  Stands in for the per-region loading of LoadAlignedEvents (poreseq/LoadData.py:10-65: h5py + pysam
+ * into PSEvent objects, then PythonToAlignData poreseq/_poreseqcpp.pyx:139-153 on every call).  Host only. */
+typedef struct ps_pack ps_pack;
+ps_pack*    ps_pack_open(const char* path);        /* NULL on failure: ps_last_error(NULL) has the reason          */
+void        ps_pack_close(ps_pack* pack);
+int         ps_pack_num_regions(ps_pack* pack);
+/* Region k as a descriptor whose pointers are views into the mapping (valid until ps_pack_close; seq2d is NULL).
+ * width_key names the parameter that overrides scoring_width ("point_width", pyx:293,361,465) or is NULL. */
+int         ps_pack_region_desc(ps_pack* pack, int k, const char* width_key, ps_region_desc* out);
+/* A named parameter of region k (the pack keeps every key of the .conf); PS_E_ARG when absent. */
+int         ps_pack_region_param(ps_pack* pack, int k, const char* name, double* value);
+/* The 2D read sequence of event e of region k (PSEvent.sequence, the seeds of PSAlign.Mutate('self'), pyx:412-414):
+ * a view of *len bytes, not NUL-terminated. */
+int         ps_pack_event_sequence(ps_pack* pack, int k, int e, const char** seq, int* len);
+/* ps_regions_create over regions [first, first + count) of the pack, straight from the mapping. */
+int         ps_pack_regions_create(ps_ctx* ctx, ps_pack* pack, int first, int count, const char* width_key, ps_region** out);
+
 /* ---- helpers that stay on the host ---------------------------------------------------------- */
 /* Sequence::populateStates (cpp/Sequence.h:69-100); returns the number of states written. */
 int         ps_seq_to_states(const char* seq, int len, int* states);

@@ -122,3 +122,67 @@ class Pack(object):
 
 def read_pack(path):
     return Pack(path)
+
+
+class NativePack(object):
+    """The same file opened below the C-ABI (`ps_pack_open`, csrc/ps_pack.cu): the library maps it and builds its
+    regions straight from the mapping -- `regions(ctx, first, count)` is ONE call, with no per-region Python object
+    and no numpy view in between.  This is the form a C5-sized job uses (hundreds of regions per pack)."""
+
+    def __init__(self, path):
+        import ctypes as C
+        self.lib = poreseqcpp.lib()
+        self.handle = self.lib.ps_pack_open(str(path).encode())
+        if not self.handle:
+            raise ValueError(self.lib.ps_last_error(None).decode())
+        self._C = C
+
+    def close(self):
+        if self.handle:
+            self.lib.ps_pack_close(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return self.lib.ps_pack_num_regions(self.handle)
+
+    def desc(self, k, width_key=None):
+        """ps_region_desc of region k (pointers into the mapping)."""
+        d = poreseqcpp.PSRegionDesc()
+        rc = self.lib.ps_pack_region_desc(self.handle, int(k), width_key.encode() if width_key else None, self._C.byref(d))
+        if rc:
+            raise IndexError("region %d: %s" % (k, self.lib.ps_last_error(None).decode()))
+        return d
+
+    def param(self, k, name, default=None):
+        v = self._C.c_double(0)
+        if self.lib.ps_pack_region_param(self.handle, int(k), name.encode(), self._C.byref(v)):
+            return default
+        return v.value
+
+    def event_sequence(self, k, e):
+        ptr, ln = self._C.c_void_p(), self._C.c_int(0)
+        if self.lib.ps_pack_event_sequence(self.handle, int(k), int(e), self._C.byref(ptr), self._C.byref(ln)):
+            raise IndexError("region %d event %d" % (k, e))
+        return self._C.string_at(ptr.value, ln.value).decode("ascii") if ln.value else ""
+
+    def regions(self, ctx, first=0, count=None, width_key=None):
+        """ps_pack_regions_create: NativeRegion objects for regions [first, first + count)."""
+        C = self._C
+        n = len(self) - first if count is None else count
+        out = (C.c_void_p * max(n, 1))()
+        ctx.check(self.lib.ps_pack_regions_create(ctx.handle, self.handle, int(first), int(n),
+                                                  width_key.encode() if width_key else None, out))
+        regs = []
+        for k in range(n):
+            d = self.desc(first + k)
+            r = poreseqcpp.NativeRegion.__new__(poreseqcpp.NativeRegion)
+            r.ctx, r.handle = ctx, out[k]
+            r.n_levels = np.ctypeslib.as_array(C.cast(d.n0, C.POINTER(C.c_int)), shape=(d.n_events,)).tolist() if d.n_events else []
+            regs.append(r)
+        return regs

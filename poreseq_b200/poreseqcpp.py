@@ -95,6 +95,14 @@ def lib():
     L.ps_mutate.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.c_int, _c_int_p]
     L.ps_viterbi_mutate.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, _c_int_p]
     L.ps_get_viterbi_sequence.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
+    L.ps_pack_open.restype = C.c_void_p
+    L.ps_pack_open.argtypes = [C.c_char_p]
+    L.ps_pack_close.argtypes = [C.c_void_p]
+    L.ps_pack_num_regions.argtypes = [C.c_void_p]
+    L.ps_pack_region_desc.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.POINTER(PSRegionDesc)]
+    L.ps_pack_region_param.argtypes = [C.c_void_p, C.c_int, C.c_char_p, _c_double_p]
+    L.ps_pack_event_sequence.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), _c_int_p]
+    L.ps_pack_regions_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]
     _lib = L
     return L
 

@@ -533,3 +533,20 @@ def test_train_loop_runs_variants_in_flight():
     assert len(hist) == 2 and all(90.0 <= a <= 100.0 for a in hist)
     assert set(best) == set(base) and best["lik_offset"] == 4.5
     assert 1 <= sum(best[k] != base[k] for k in base) <= 6
+
+
+def test_native_pack_regions_score_like_in_memory_ones(ctx, orc, tmp_path):
+    """The same pack opened below the C-ABI (ps_pack_open / ps_pack_regions_create, csrc/ps_pack.cu): regions built
+    straight from the mapping give the checker's scores."""
+    from poreseq_b200 import eventpack
+    regs = [region("clean"), region("draft_partial"), region("ragged")]
+    path = str(tmp_path / "regions.psep")
+    eventpack.write_pack(path, regs)
+    pack = eventpack.NativePack(path)
+    nrs = pack.regions(ctx, width_key="point_width")
+    out = poreseqcpp.score_points_batch(ctx, nrs)
+    for reg, o in zip(regs, out):
+        want, _ = orc.score_points(reg)
+        assert np.array_equal(o[3], np.array([w[3] for w in want]))
+    poreseqcpp.close_regions(nrs)
+    pack.close()

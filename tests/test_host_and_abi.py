@@ -287,3 +287,92 @@ def test_recycled_level_arrays_keep_their_contents():
     for t in threads:
         t.join()
     assert not errors, errors[:4]
+
+
+def test_native_event_pack_reader(tmp_path):
+    """ps_pack_* (csrc/ps_pack.cu): the library maps an event-pack file itself; every block of every region is where the
+    Python reader finds it, parameters and 2D sequences come back, regions marshal straight from the mapping."""
+    import ctypes as C
+    from poreseq_b200 import eventpack
+    regs = [synth.make_region(150 + 30 * k, 2 + k, seed=40 + k, draft_error=0.05 * k, partial=0.2 * k,
+                              params=dict(realign_width=40, scoring_width=12, point_width=6, lik_offset=4.5)) for k in range(3)]
+    regs.append(synth.make_region(40, 1, seed=50))
+    regs[-1].events = []                                   # a region without events
+    path = str(tmp_path / "regions.psep")
+    eventpack.write_pack(path, regs)
+    views = eventpack.read_pack(path)
+    pack = eventpack.NativePack(path)
+    assert len(pack) == len(regs) == len(views)
+
+    def arr(ptr, ctype, n):
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(n,)).copy() if n else np.zeros(0)
+
+    for k, (reg, v) in enumerate(zip(regs, views)):
+        d = pack.desc(k, "point_width")
+        assert C.string_at(d.bases, d.len) == v.sequence and d.n_events == len(v.n0) and d.n_models == len(v.models)
+        assert (d.params.lik_offset, d.params.scoring_width, d.params.realign_width) == (
+            reg.params["lik_offset"], reg.params["point_width"], reg.params["realign_width"])
+        assert pack.desc(k).params.scoring_width == reg.params["scoring_width"]
+        n_lev = int(v.n0.sum())
+        assert np.array_equal(arr(d.n0, C.c_int, d.n_events), v.n0)
+        assert np.array_equal(arr(d.model_index, C.c_int, d.n_events), v.model_index)
+        assert np.array_equal(arr(d.complement, C.c_int, d.n_events), v.complement)
+        for name in ("mean", "stdv", "ref_align", "ref_like"):
+            assert np.array_equal(arr(getattr(d, name), C.c_double, n_lev), getattr(v, name)), name
+        assert np.array_equal(arr(d.models, C.c_double, d.n_models * 4096), v.models.ravel())
+        assert np.array_equal(arr(d.probs, C.c_double, d.n_models * 4), v.probs.ravel())
+        assert pack.param(k, "point_width") == reg.params["point_width"] and pack.param(k, "no_such_key") is None
+        assert [pack.event_sequence(k, e) for e in range(d.n_events)] == v.seq2d
+    ctx = poreseqcpp.Context(0)
+    nrs = pack.regions(ctx, first=1, count=3, width_key="point_width")
+    for reg, nr in zip(regs[1:], nrs):
+        assert nr.sequence() == reg.sequence and ctx.lib.ps_region_num_events(nr.handle) == len(reg.events)
+        for e, ev in enumerate(reg.events):
+            ra, rl = nr.event_align(e)
+            assert np.array_equal(ra, ev.ref_align) and np.array_equal(rl, ev.ref_like)
+    poreseqcpp.close_regions(nrs)
+    with pytest.raises(RuntimeError, match="ps_pack_regions_create"):
+        pack.regions(ctx, first=3, count=2)
+    with pytest.raises(IndexError):
+        pack.desc(9)
+    pack.close()
+
+
+def test_native_event_pack_reader_refuses_damaged_files(tmp_path):
+    """Truncated, re-labelled or internally inconsistent packs are refused at ps_pack_open with a reason (nothing is
+    dereferenced outside the mapping)."""
+    import struct
+    from poreseq_b200 import eventpack
+    regs = [synth.make_region(80, 2, seed=70), synth.make_region(90, 1, seed=71)]
+    good = str(tmp_path / "good.psep")
+    eventpack.write_pack(good, regs)
+    data = open(good, "rb").read()
+    n, index_at = struct.unpack("<QQ", data[8:24])
+    off1 = struct.unpack("<Q", data[index_at + 16:index_at + 24])[0]
+
+    def patched(at, raw):
+        b = bytearray(data)
+        b[at:at + len(raw)] = raw
+        return bytes(b)
+
+    damaged = {
+        "missing": None,
+        "empty": b"",
+        "magic": b"PSEP0002" + data[8:],
+        "truncated": data[:len(data) // 2],
+        "no_index": data[:index_at + 8],
+        "count": patched(8, struct.pack("<Q", 1 << 40)),
+        "index_offset": patched(16, struct.pack("<Q", len(data) + 64)),
+        "region_offset": patched(index_at, struct.pack("<Q", len(data) - 8)),
+        "region_size": patched(index_at + 8, struct.pack("<Q", 1 << 50)),
+        "levels": patched(off1 + 16, struct.pack("<I", 7)),                 # n_levels disagrees with sum(n0)
+        "events": patched(off1 + 4, struct.pack("<I", 1 << 30)),            # n_events far beyond the block
+        "model_index": patched(off1 + 32 + 24 * len(regs[1].params) + ((len(regs[1].sequence) + 7) & ~7) + 4 * 2 + 4, struct.pack("<i", 5)),
+    }
+    for name, raw in damaged.items():
+        path = str(tmp_path / (name + ".psep"))
+        if raw is not None:
+            open(path, "wb").write(raw)
+        with pytest.raises(ValueError, match="ps_pack_open"):
+            eventpack.NativePack(path)
+    assert len(eventpack.NativePack(good)) == 2
