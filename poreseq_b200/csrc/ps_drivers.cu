@@ -14,63 +14,6 @@
 
 #define TRY(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
 
-// ------------------------------------------------------------------------------------------
-// swfull: full-matrix local alignment, +5 match / -4 mismatch / -8 gap (cpp/swlib.h:21-23,
-// cpp/swlib.cpp:211-340).  Tie rules: left and up must beat the running best strictly, the
-// diagonal wins ties; the best cell is the first maximum in (column of seq2, row of seq1) order.
-// Only one byte per cell is kept: the move (0..3) plus a flag for "score is zero", which is all the
-// traceback ever asks of the score matrix; scores themselves roll over two columns.
-SWResult psi_swfull(const std::string& s1, const std::string& s2)
-{
-    const int n1 = (int)s1.size(), n2 = (int)s2.size();
-    const size_t stride = (size_t)n1 + 1;
-    std::vector<uint8_t> move(stride * ((size_t)n2 + 1), 0);
-    std::vector<int> prev(stride, 0), cur(stride, 0);
-    int best = 0, bi = 0, bj = 0;
-    for (int j = 1; j <= n2; j++)
-    {
-        uint8_t* mv = move.data() + (size_t)j * stride;
-        const char cj = s2[j - 1];
-        cur[0] = 0;
-        for (int i = 1; i <= n1; i++)
-        {
-            int sc = 0, m = 0;
-            int v = prev[i] - 8;
-            if (v > sc) { sc = v; m = 1; }
-            v = cur[i - 1] - 8;
-            if (v > sc) { sc = v; m = 2; }
-            v = prev[i - 1] + (s1[i - 1] == cj ? 5 : -4);
-            if (v >= sc) { sc = v; m = 3; }
-            cur[i] = sc;
-            mv[i] = (uint8_t)(m | (sc <= 0 ? 4 : 0));
-            if (sc > best) { best = sc; bi = i; bj = j; }
-        }
-        prev.swap(cur);
-    }
-    SWResult r;
-    r.score = best;
-    int i = bi, j = bj, nmatch = 0;
-    while (i > 0 && j > 0)
-    {
-        const uint8_t mv = move[(size_t)j * stride + i];
-        if (mv & 4) break;
-        const int m = mv & 3;
-        if (m == 1) { r.inds1.push_back(0); r.inds2.push_back(j); j--; }
-        else if (m == 2) { r.inds1.push_back(i); r.inds2.push_back(0); i--; }
-        else if (m == 3)
-        {
-            r.inds1.push_back(i); r.inds2.push_back(j);
-            if (s1[i - 1] == s2[j - 1]) nmatch++;
-            i--; j--;
-        }
-        else break;      // cannot happen for a positive score
-    }
-    std::reverse(r.inds1.begin(), r.inds1.end());
-    std::reverse(r.inds2.begin(), r.inds2.end());
-    r.accuracy = 100.0 * nmatch / (double)r.inds1.size();
-    return r;
-}
-
 // fillinds (cpp/swlib.cpp:342-365): gaps take the previous aligned index of their own sequence
 void psi_fillinds(SWResult& al)
 {
