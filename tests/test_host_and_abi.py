@@ -376,3 +376,35 @@ def test_native_event_pack_reader_refuses_damaged_files(tmp_path):
         with pytest.raises(ValueError, match="ps_pack_open"):
             eventpack.NativePack(path)
     assert len(eventpack.NativePack(good)) == 2
+
+
+def test_swalign_fuzz_against_reference(ref):
+    """The anti-diagonal host swfull (csrc/ps_swhost.cpp) against cpp/swlib.cpp:211-340 on ~900 pairs: small alphabets
+    (ties everywhere), shifted / truncated / unrelated sequences, one-base inputs, both argument orders."""
+    rng = np.random.default_rng(11)
+
+    def same(a, b):
+        x, y = poreseqcpp.swalign(a, b), ref.swfull(a, b)
+        return (x[0] == y[0] or (np.isnan(x[0]) and np.isnan(y[0]))) and [tuple(p) for p in x[1]] == [tuple(p) for p in y[2]]
+
+    fixed = [("A", "A"), ("A", "C"), ("AAAAAAAAAA", "AAAAAAA"), ("ACGTACGT", "TTTT"), ("A", "AAAAAAAA"), ("ACGT" * 50, "ACGT" * 37),
+             ("AC" * 100, "CA" * 100), ("A" * 300, "A" * 299), ("ACGTN", "ACGTN"), ("NNNN", "NNNN")]
+    for a, b in fixed:
+        assert same(a, b) and same(b, a), (a, b)
+    alph = [list("ACGT"), list("AC"), list("A")]
+    for it in range(800):
+        k = int(rng.integers(0, 3))
+        la, lb = int(rng.integers(1, 120)), int(rng.integers(1, 120))
+        a = "".join(rng.choice(alph[k], la))
+        mode = it % 4
+        if mode == 0:
+            b = "".join(rng.choice(alph[k], lb))
+        elif mode == 1:
+            b = synth.corrupt_sequence(a, float(rng.choice([0.02, 0.1, 0.3])), rng)[0] or "A"
+        elif mode == 2:
+            b = (a[int(rng.integers(0, la)):] + "".join(rng.choice(alph[k], int(rng.integers(0, 20))))) or "C"
+        else:
+            b = ("".join(rng.choice(alph[k], int(rng.integers(0, 30)))) + a)[:max(1, lb)]
+        assert same(a, b), (a, b)
+    a = synth.random_sequence(2500, rng)
+    assert same(a, synth.corrupt_sequence(a, 0.1, rng)[0]) and same(synth.random_sequence(2000, rng), a)
