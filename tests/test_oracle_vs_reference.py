@@ -134,3 +134,17 @@ def test_restatement_matches_driver_golden(orc, path):
     rr = aligned_copy(reg, str(z["rf_seq"]), split_aligns(z["rf_aligns"], reg))
     assert orc.viterbi_mutate(rr, nkeep=0) == d["vit_best"].tolist()
     assert orc.viterbi_mutate(rr, nkeep=4, seed=1) == d["vit_samples"].tolist()
+
+
+def test_baseline_configs_0_and_1_at_full_size(orc, ref):
+    """BASELINE.json configs[0] (PSAlign.ScoreEvents, 1 kb x 10x) and configs[1] (the full single-base scan of the same
+    region: 7968 edits x 20 events at the default widths) on the restatement and on the reference's own C++: event
+    scores, likelihood profile, all 7968 mutation scores and every event's alignment, bit for bit."""
+    from poreseq_b200 import synth
+    reg = synth.make_region(1000, 10, seed=1)
+    s1, l1, a1 = ref.score_alignments(reg, True)
+    s2, l2, a2 = orc.score_alignments(reg, True)
+    assert len(s1) == 20 and np.array_equal(s1, s2) and np.array_equal(l1, l2) and same_aligns(a1, a2)
+    p1, a1 = ref.score_points(reg)
+    p2, a2 = orc.score_points(reg)
+    assert len(p1) == 7968 and p1 == p2 and same_aligns(a1, a2)
