@@ -148,3 +148,18 @@ def test_baseline_configs_0_and_1_at_full_size(orc, ref):
     p1, a1 = ref.score_points(reg)
     p2, a2 = orc.score_points(reg)
     assert len(p1) == 7968 and p1 == p2 and same_aligns(a1, a2)
+
+
+def test_baseline_config_3_shape_reduced(orc, ref):
+    """BASELINE.json configs[3] (`poreseq variant -m`: known multi-base mutations scored at scoring_width 100 against
+    deep coverage) at a size the CPU finishes in seconds: 2 kb, 40 events, 600 random sub / ins / del edits of up to 6
+    bases plus the boundary edits, default widths."""
+    from poreseq_b200 import synth
+    reg = synth.make_region(2000, 20, seed=4, draft_error=0.01, partial=0.3, params=dict(scoring_width=100))
+    rng = np.random.default_rng(44)
+    st, og, mu = synth.random_mutations(reg.sequence, 600, rng, max_len=6)
+    e_st, e_og, e_mu = edge_mutations(reg.sequence, 45, count=0)
+    st, og, mu = st + e_st, og + e_og, mu + e_mu
+    m1, a1 = ref.score_mutations(reg, st, og, mu)
+    m2, a2 = orc.score_mutations(reg, st, og, mu)
+    assert np.array_equal(m1, m2) and same_aligns(a1, a2) and (m1 > 0).any() and (m1 < -1).any()
