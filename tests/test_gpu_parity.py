@@ -550,3 +550,31 @@ def test_native_pack_regions_score_like_in_memory_ones(ctx, orc, tmp_path):
         assert np.array_equal(o[3], np.array([w[3] for w in want]))
     poreseqcpp.close_regions(nrs)
     pack.close()
+
+
+@pytest.mark.parametrize("precision", ["exact", "fast"])
+def test_baseline_config_3_shape_reduced(orc, precision):
+    """BASELINE.json configs[3] (`poreseq variant -m`: known multi-base mutations at scoring_width 100 against deep
+    coverage) at the size of the CPU test of the same name: 2 kb, 40 events, 600 random edits of up to 6 bases plus the
+    boundary edits.  Exact mode: every score bit-identical; fast mode: scores >= 0 bit-identical, the rest within 1e-4 relative
+    (+ 1e-3 absolute near zero, as in test_fast_mode_decisions_exact)."""
+    reg = synth.make_region(2000, 20, seed=4, draft_error=0.01, partial=0.3, params=dict(scoring_width=100))
+    rng = np.random.default_rng(44)
+    st, og, mu = synth.random_mutations(reg.sequence, 600, rng, max_len=6)
+    e_st, e_og, e_mu = edge_mutations(reg.sequence, 45, count=0)
+    st, og, mu = st + e_st, og + e_og, mu + e_mu
+    want, want_a = orc.score_mutations(reg, st, og, mu)
+    c2 = poreseqcpp.Context(0)
+    try:
+        c2.set_precision(precision)
+        nr = native(c2, reg)
+        got = nr.score_mutations(st, og, mu)
+        if precision == "exact":
+            bad = np.nonzero(got != want)[0]
+            assert len(bad) == 0, [(int(i), st[i], og[i], mu[i], got[i], want[i]) for i in bad[:8]]
+        else:
+            assert np.array_equal(got[want >= 0], want[want >= 0]) and np.array_equal(got >= 0, want >= 0)
+            assert np.all(np.abs(got - want) <= 1e-4 * np.abs(want) + 1e-3), float(np.max(np.abs(got - want)))
+        assert same_aligns(native_aligns(nr, reg), want_a)
+    finally:
+        c2.close()
