@@ -4,7 +4,7 @@
  * replaces one native function the reference's Cython module binds through `cdef extern`
  * (poreseq/_poreseqcpp.pyx:63-83); the citation beside each declaration is the reference
  * interface it stands in for.  INTEGRATION.md shows the Cython stub a PoreSeq maintainer would
- * add to call these instead of cpp/*.cpp.
+ * add to call these instead of the sources under cpp/.
  *
  * Model: a `ps_ctx` owns one CUDA device/stream and its scratch memory; a `ps_region` is the
  * native twin of the reference's `AlignData` (cpp/AlignData.h:24-34): one sequence, its events

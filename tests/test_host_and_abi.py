@@ -408,3 +408,26 @@ def test_swalign_fuzz_against_reference(ref):
         assert same(a, b), (a, b)
     a = synth.random_sequence(2500, rng)
     assert same(a, synth.corrupt_sequence(a, 0.1, rng)[0]) and same(synth.random_sequence(2000, rng), a)
+
+
+def test_header_is_plain_c_and_the_c_example_links(tmp_path):
+    """include/poreseq_b200.h is a C header (gcc -std=c99 -pedantic), and examples/score_points.c -- a caller with no
+    Python and no C++ in it -- builds against it, opens an event pack and marshals its regions through the library."""
+    import subprocess
+    from poreseq_b200 import eventpack
+    build.build()
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-x", "c",
+                    os.path.join(inc, "poreseq_b200.h")], check=True)
+    exe = str(tmp_path / "score_points")
+    libdir = os.path.dirname(build.LIB)
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I" + inc, os.path.join(ROOT, "examples", "score_points.c"),
+                    "-L" + libdir, "-lporeseq_b200", "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    regs = [synth.make_region(120, 2, seed=80 + k) for k in range(3)]
+    path = str(tmp_path / "regions.psep")
+    eventpack.write_pack(path, regs)
+    out = subprocess.run([exe, path], capture_output=True, text=True)
+    assert "3 regions" in out.stdout, out.stdout + out.stderr
+    import torch
+    if not torch.cuda.is_available():
+        assert out.returncode == 0 and "no CPU fallback" in out.stdout
