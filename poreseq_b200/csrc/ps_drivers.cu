@@ -84,20 +84,33 @@ int ps_find_mutation_list(ps_region* R, const std::vector<std::string>& seeds, s
     std::vector<ps_region*> nds(S, nullptr);
     std::vector<SWResult> sw;
     const bool sw_gpu = !getenv("PORESEQ_B200_SW_HOST") && psi_swfull_batch(ctx, R->bases, seeds, sw) == PS_OK;
-    ps_parallel_for((int)S, [&](int s) {
-        ps_region* nd = new ps_region(*R);
-        nd->seqlikes.clear();
-        als[s] = sw_gpu ? psi_map_alignments_with(nd, seeds[s], sw[s]) : psi_map_alignments(nd, seeds[s]);
-        nds[s] = nd;
-    });
+    // Only the first occurrence of a seed whose profile is not cached yet needs a shadow region (a copy of every
+    // event, 36 MB for 10 kb x 30x); for the others the SW alignment with its gaps filled (what MapAlignments returns)
+    // is all the CUSUM below reads.
+    std::vector<char> need(S, 0);
     for (size_t s = 0; s < S; s++)
     {
-        ps_region* nd = nds[s];
-        const bool cached = R->seqlikes.count(seeds[s]) && !R->seqlikes[seeds[s]].empty();
+        const auto hit = R->seqlikes.find(seeds[s]);
+        const bool cached = hit != R->seqlikes.end() && !hit->second.empty();
         const bool queued = std::find(shadow_key.begin(), shadow_key.end(), seeds[s]) != shadow_key.end();
-        if (!cached && !queued && seeds[s].size() >= 5) { shadows.push_back(nd); shadow_key.push_back(seeds[s]); }
-        else delete nd;
+        if (!cached && !queued && seeds[s].size() >= 5) { need[s] = 1; shadow_key.push_back(seeds[s]); }
     }
+    ps_parallel_for((int)S, [&](int s) {
+        if (need[s])
+        {
+            ps_region* nd = new ps_region(*R);
+            nd->seqlikes.clear();
+            als[s] = sw_gpu ? psi_map_alignments_with(nd, seeds[s], sw[s]) : psi_map_alignments(nd, seeds[s]);
+            nds[s] = nd;
+        }
+        else
+        {
+            als[s] = sw_gpu ? sw[s] : psi_swfull(R->bases, seeds[s]);
+            psi_fillinds(als[s]);
+        }
+    });
+    for (size_t s = 0; s < S; s++)
+        if (need[s]) shadows.push_back(nds[s]);        // same order as shadow_key
     const double t_sw = now();
     if (!shadows.empty())
     {
