@@ -95,6 +95,9 @@ int ps_find_mutation_list(ps_region* R, const std::vector<std::string>& seeds, s
         const bool queued = std::find(shadow_key.begin(), shadow_key.end(), seeds[s]) != shadow_key.end();
         if (!cached && !queued && seeds[s].size() >= 5) { need[s] = 1; shadow_key.push_back(seeds[s]); }
     }
+    // the shadow regions inherit the level records (3 log(stdv) per level) instead of each computing its own
+    if (!shadow_key.empty())
+        ps_parallel_for((int)R->events.size(), [&](int e) { R->events[e].ensure_levrec(); });
     ps_parallel_for((int)S, [&](int s) {
         if (need[s])
         {
