@@ -578,3 +578,26 @@ def test_baseline_config_3_shape_reduced(orc, precision):
         assert same_aligns(native_aligns(nr, reg), want_a)
     finally:
         c2.close()
+
+
+def test_cython_stub_is_a_drop_in(orc, tmp_path):
+    """The Cython binding a PoreSeq maintainer would add (examples/cython_stub) run for real:
+    PSAlign.ScoreEvents and PSAlign.Refine through the compiled stub -> C-ABI -> CUDA give the checker's scores,
+    sequence, bases changed and per-level alignments, written back into the Python events in place (pyx:131-137)."""
+    import sys
+    from util import build_cython_stub
+    where, log = build_cython_stub(tmp_path)
+    if not where:
+        pytest.skip("cannot build the Cython stub here: " + log[-300:])
+    sys.path.insert(0, where)
+    try:
+        import poreseqcpp_b200 as m
+    finally:
+        sys.path.remove(where)
+    reg = region("draft_partial")
+    pa = m.PSAlign()
+    pa.sequence, pa.events, pa.params = reg.sequence, [e.copy() for e in reg.events], dict(reg.params)
+    assert np.array_equal(np.array(pa.ScoreEvents()), orc.score_alignments(reg)[0])
+    want_seq, want_nb, want_a = orc.refine(reg)
+    assert (pa.Refine(), pa.sequence) == (want_nb, want_seq)
+    assert same_aligns([(e.ref_align, e.ref_like) for e in pa.events], want_a)

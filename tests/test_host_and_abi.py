@@ -431,3 +431,39 @@ def test_header_is_plain_c_and_the_c_example_links(tmp_path):
     import torch
     if not torch.cuda.is_available():
         assert out.returncode == 0 and "no CPU fallback" in out.stdout
+
+
+def test_cython_stub_of_integration_md_builds_and_binds(tmp_path):
+    """The reference-side binding of INTEGRATION.md section 2 is a real module (examples/cython_stub): Cython compiles it
+    against include/poreseq_b200.h, it links to the library, its host-only entry points give the product's answers, the
+    PSAlign marshalling reaches the library, and a compute call without a GPU raises the 'no CPU fallback' error."""
+    import subprocess
+    import sys
+    from util import build_cython_stub
+    build.build()
+    where, log = build_cython_stub(tmp_path)
+    assert where, log
+    code = r"""
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import poreseqcpp_b200 as m
+from poreseq_b200 import synth, poreseqcpp
+for a, b in [("ACGTTTTTACGT", "ACGTTTACGT"), ("GATTACA", "GCATGCT"), ("AAAAAAAAAA", "AAAAAAA")]:
+    x, y = m.swalign(a, b), poreseqcpp.swalign(a, b)
+    assert x[0] == y[0] and [tuple(p) for p in x[1]] == [tuple(p) for p in y[1]], (a, b)
+assert m.seqtostates("ACGTACGTNACGT") == poreseqcpp.seqtostates("ACGTACGTNACGT")
+reg = synth.make_region(80, 2, seed=3)
+pa = m.PSAlign(); pa.sequence, pa.events, pa.params = reg.sequence, reg.events, reg.params
+assert pa.NumEvents() == 4
+import torch
+if not torch.cuda.is_available():
+    try:
+        pa.Refine()
+    except RuntimeError as e:
+        assert "no CPU fallback" in str(e)
+    else:
+        raise AssertionError("Refine returned without a GPU")
+print("stub ok")
+""" % (where, ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.returncode == 0 and "stub ok" in out.stdout, out.stdout + out.stderr

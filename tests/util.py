@@ -34,3 +34,20 @@ def edge_mutations(seq, seed, count=200, max_len=5):
 
 def same_aligns(a, b):
     return all(np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1]) for x, y in zip(a, b))
+
+
+def build_cython_stub(tmp_dir):
+    """Builds examples/cython_stub (the binding of INTEGRATION.md section 2) in a scratch directory; returns the
+    directory to put on sys.path, or None when the toolchain refuses (reported by the caller)."""
+    import os
+    import shutil
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dst = os.path.join(str(tmp_dir), "cython_stub")
+    shutil.copytree(os.path.join(root, "examples", "cython_stub"), dst)
+    env = dict(os.environ, PORESEQ_B200_ROOT=root)
+    proc = subprocess.run([sys.executable, "setup.py", "build_ext", "--inplace"], cwd=dst, env=env, capture_output=True, text=True)
+    if proc.returncode != 0:
+        return None, proc.stdout[-2000:] + proc.stderr[-2000:]
+    return dst, ""
