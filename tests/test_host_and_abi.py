@@ -467,3 +467,47 @@ print("stub ok")
 """ % (where, ROOT)
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert out.returncode == 0 and "stub ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_make_mutations_accept_loop_matches_reference(ref):
+    """The product's host-side MakeMutations (cpp/MakeMutations.cpp:74-146: std::sort by score with its tie placement,
+    drop the negative tail, apply in order, invalidate neighbours within mutspc = 10, shift later starts) against the
+    reference's own C++ on crafted score lists: random positives, exact ties, all-equal scores, -1e-6 entries, edits at
+    and past the end.  Lists that defer more than 10 edits need the GPU scorer for the recursion and are skipped here
+    (they run in the GPU tests through Refine / Mutate)."""
+    ctx = poreseqcpp.Context(0)
+    compared = 0
+    for seed in range(240):
+        rng = np.random.default_rng(seed)
+        reg = synth.make_region(int(rng.integers(30, 300)), 1, seed=seed + 1, params=dict(realign_width=20, scoring_width=8, point_width=4))
+        L = len(reg.sequence)
+        st, og, mu = synth.point_mutations(reg.sequence)
+        s2, o2, m2 = synth.random_mutations(reg.sequence, int(rng.integers(0, 40)), rng, max_len=6)
+        st, og, mu = st + s2 + [L, L + 3, 0], og + o2 + ["", "", reg.sequence[:7]], mu + m2 + ["AC", "G", ""]
+        n = len(st)
+        sc = -np.abs(rng.normal(3, 2, n)) - 0.01
+        pos = rng.choice(n, size=int(rng.integers(0, 18)), replace=False)
+        mode = seed % 4
+        if mode == 0:
+            sc[pos] = rng.uniform(0, 5, len(pos))
+        elif mode == 1:
+            sc[pos] = rng.integers(0, 3, len(pos)).astype(float)       # exact ties, zeros included
+        elif mode == 2:
+            sc[pos] = 1.0
+        else:
+            sc[pos] = rng.uniform(0, 5, len(pos))
+            sc[rng.choice(n, 5)] = -1e-6
+        want_seq, want_nb, _ = ref.make_mutations(reg, st, og, mu, sc.tolist())
+        nr = poreseqcpp.NativeRegion(ctx, reg.sequence, reg.events, reg.params, "point_width")
+        try:
+            nb = nr.make_mutations(st, og, mu, sc.tolist())
+        except RuntimeError as e:
+            assert "no CPU fallback" in str(e)
+            continue
+        finally:
+            seq = nr.sequence()
+            nr.close()
+        compared += 1
+        assert (seq, nb) == (want_seq, want_nb), seed
+    import torch
+    assert compared >= (240 if torch.cuda.is_available() else 120)
