@@ -511,3 +511,32 @@ def test_make_mutations_accept_loop_matches_reference(ref):
         assert (seq, nb) == (want_seq, want_nb), seed
     import torch
     assert compared >= (240 if torch.cuda.is_available() else 120)
+
+
+def test_map_alignments_host_path_matches_reference(ref):
+    """ps_map_alignments is host-only (cpp/EventUtil.cpp:12-55: swfull + fillinds, then every level's ref_align carried
+    over through lower_bound): against the reference's own C++ on 150 random regions -- drafts with 0-30 % errors, partial
+    and unaligned reads, jittered seed alignments, new sequences that are shifted, truncated or unrelated."""
+    ctx = poreseqcpp.Context(0)
+    for seed in range(150):
+        rng = np.random.default_rng(300 + seed)
+        reg = synth.make_region(int(rng.integers(12, 260)), int(rng.integers(1, 4)), seed=seed + 1,
+                                draft_error=float(rng.choice([0, 0.05, 0.2])), partial=float(rng.choice([0, 0.5])),
+                                p_unaligned=float(rng.choice([0, 0.3])), jitter=int(rng.choice([0, 3])))
+        mode = seed % 4
+        if mode == 0:
+            newseq = synth.corrupt_sequence(reg.sequence, float(rng.choice([0.02, 0.1, 0.3])), rng)[0]
+        elif mode == 1:
+            newseq = reg.sequence[int(rng.integers(0, len(reg.sequence) // 2)):] + synth.random_sequence(int(rng.integers(0, 30)), rng)
+        elif mode == 2:
+            newseq = synth.random_sequence(int(rng.integers(0, 20)), rng) + reg.sequence[:int(rng.integers(6, len(reg.sequence) + 1))]
+        else:
+            newseq = synth.random_sequence(int(rng.integers(5, 200)), rng)
+        if len(newseq) < 5:
+            continue
+        want = ref.map_alignments(reg, newseq)
+        nr = poreseqcpp.NativeRegion(ctx, reg.sequence, reg.events, reg.params)
+        nr.map_alignments(newseq)
+        got = [nr.event_align(e) for e in range(len(reg.events))]
+        assert nr.sequence() == newseq and all(np.array_equal(g[0], w[0]) and np.array_equal(g[1], w[1]) for g, w in zip(got, want)), seed
+        nr.close()
