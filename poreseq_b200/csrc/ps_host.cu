@@ -1235,7 +1235,11 @@ static int run_job(ps_ctx* ctx, const std::vector<ps_region*>& regs, const std::
     TRY(ctx->init());
     // a job whose band matrices would not fit (e.g. FindMutations: seeds x events wide fills of a 10 kb
     // region) runs as consecutive sub-batches of whole regions; results are concatenated in region order
-    double budget = 0.40 * (double)ctx->total_mem;
+    // At most 32 GB of band storage per sub-batch: growing the band buffers is a synchronous cudaFree + cudaMalloc whose
+    // cost rises with the size -- the 30 seed realignments of a 10 kb x 30x region (1800 events) took 1411 ms as three
+    // sub-batches of 76 GB and 432 ms as eight of 30 GB (240 events = one wave of the 192-thread fill class each),
+    // measured on a B200 (gpurun_out -> profiles/r1_consensus_10kb_trace.txt).
+    double budget = std::min(0.40 * (double)ctx->total_mem, 32e9);
     if (const char* e = getenv("PORESEQ_B200_BAND_BUDGET")) budget = atof(e);      // bytes; tests force the split path with it
     double total = 0;
     for (const ps_region* R : regs) total += region_band_bytes(R, muts != nullptr);
