@@ -178,6 +178,13 @@ int         ps_score_points_batch_end(ps_ctx* ctx, double* scores);
  * cpp/FindMutations.cpp:24-186.  The result is held by the region; fetch entry i with
  * ps_get_found_mutation (sizes first with ps_found_mutation_sizes). */
 int         ps_find_mutations(ps_region* r, int n_seeds, const char* const* seeds, int* n_found);
+/* The host-only second half of FindMutations (cpp/FindMutations.cpp:51-186) for callers that already hold the per-base
+ * likelihood profiles ScoreAlignments accumulates (cpp/MakeMutations.cpp:168-189) -- e.g. summed over event shards on
+ * several GPUs: swfull of the region's sequence against every seed, CUSUM of the profile differences along the alignments,
+ * greedy peak picking.  base_profile has len(sequence) entries, seed_profiles[s] strlen(seeds[s]).  The result is read
+ * like that of ps_find_mutations. */
+int         ps_pick_candidates(ps_region* r, int n_seeds, const char* const* seeds, const double* base_profile,
+                               const double* const* seed_profiles, int* n_found);
 int         ps_found_mutation_sizes(ps_region* r, int i, int* n_orig, int* n_mut);
 int         ps_get_found_mutation(ps_region* r, int i, int* start, char* orig, int orig_cap, char* mut, int mut_cap);
 /* Loop body of PSAlign.Mutate (poreseq/_poreseqcpp.pyx:424-431): reps x (FindMutations,

@@ -53,6 +53,86 @@ SWResult psi_map_alignments_with(ps_region* R, const std::string& newseq, SWResu
     return al;
 }
 
+// FindMutations, second half (cpp/FindMutations.cpp:51-186): given the per-base likelihood profile of the current
+// sequence (`base`), of every seed (`profs[s]`, one value per seed base) and the SW alignment of the sequence to every
+// seed with its gaps filled (`als[s]`, consumed), the CUSUM of the profile difference along each alignment and the
+// greedy peak picking that turns its maxima into candidate edits.  Host only.
+void psi_pick_candidates(const std::string& bases, const std::vector<double>& base, const std::vector<std::string>& seeds,
+                         const std::vector<const std::vector<double>*>& profs, std::vector<SWResult>& als,
+                         std::vector<HostMut>& found)
+{
+    found.clear();
+    const size_t L = bases.size(), S = seeds.size();
+    // 3. CUSUM of the profile difference along each SW alignment (:51-94)
+    std::vector<std::vector<double>> dl(S);
+    for (size_t s = 0; s < S; s++)
+    {
+        const std::vector<double>& prof = *profs[s];
+        std::vector<int>& i1 = als[s].inds1;
+        std::vector<int>& i2 = als[s].inds2;
+        for (size_t j = 0; j < i1.size(); j++) { i1[j] -= 2; i2[j] -= 2; }
+        size_t drop = 0;
+        while (drop < i1.size() && (i1[drop] < 0 || i2[drop] < 0)) drop++;
+        i1.erase(i1.begin(), i1.begin() + drop);
+        i2.erase(i2.begin(), i2.begin() + drop);
+        const size_t n = i1.size();
+        std::vector<double> a1(n), a2(n);
+        for (size_t j = 0; j < n; j++) { a1[j] = base[i1[j]]; a2[j] = prof[i2[j]]; }
+        for (size_t j = n; j-- > 1;) { a1[j] -= a1[j - 1]; a2[j] -= a2[j - 1]; }
+        if (n) { a1[0] = 0; a2[0] = 0; }
+        dl[s].resize(n);
+        double cus = 0;
+        for (size_t j = 0; j < n; j++)
+        {
+            cus += a2[j] - a1[j];
+            if (cus < 0) cus = 0;
+            dl[s][j] = std::fabs(a1[j] - a2[j]) < 1e-5 ? 0.0 : cus;
+        }
+    }
+    // 4. greedy peak picking (:111-183)
+    std::vector<long> peak_at(S, -1);              // cached first argmax of every seed's curve, -1 = stale
+    while (found.size() < L / 3)
+    {
+        int smax = -1, ind = 0;
+        double vmax = 0;
+        // (the reference rescans every seed's curve per pick; only the curve the previous pick zeroed can have
+        // a new first maximum, so the others keep their cached one -- same picks, same tie order)
+        for (size_t s = 0; s < S; s++)
+        {
+            if (dl[s].empty()) continue;
+            if (peak_at[s] < 0) peak_at[s] = (long)(std::max_element(dl[s].begin(), dl[s].end()) - dl[s].begin());
+            const size_t at = (size_t)peak_at[s];
+            if (smax < 0 || dl[s][at] > vmax) { smax = (int)s; ind = (int)at; vmax = dl[s][at]; }
+        }
+        if (smax < 0 || vmax < 0.25) break;
+        peak_at[smax] = -1;
+        std::vector<double>& d = dl[smax];
+        const int n = (int)d.size();
+        int i1 = ind;
+        while (i1 < n && d[i1] != 0) i1++;
+        int i0 = ind;
+        while (i0 >= 0 && d[i0] != 0) i0--;
+        if (i0 < 0) i0 = 0;
+        if (i1 >= n) i1 = n - 1;
+        const int start1 = als[smax].inds1[i0], start2 = als[smax].inds2[i0];
+        const int end1 = als[smax].inds1[ind], end2 = als[smax].inds2[ind];
+        HostMut m;
+        m.start = start1;
+        m.orig = bases.substr(start1, end1 - start1);
+        m.mut = seeds[smax].substr(start2, end2 - start2);
+        while (!m.orig.empty() && !m.mut.empty() && m.orig.front() == m.mut.front())
+        {
+            m.orig.erase(0, 1); m.mut.erase(0, 1); m.start++;
+        }
+        while (!m.orig.empty() && !m.mut.empty() && m.orig.back() == m.mut.back())
+        {
+            m.orig.pop_back(); m.mut.pop_back();
+        }
+        if (!m.orig.empty() || !m.mut.empty()) found.push_back(m);
+        std::fill(d.begin() + i0, d.begin() + i1 + 1, 0.0);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // FindMutations (cpp/FindMutations.cpp:24-186).  The S seed realignments (S x E wide forward
 // fills + backtraces) that dominate it are submitted as ONE batched GPU job: every distinct,
@@ -128,75 +208,15 @@ int ps_find_mutation_list(ps_region* R, const std::vector<std::string>& seeds, s
     }
     if (trace) fprintf(stderr, "[ps] FindMutations: base realign %.1f ms, %zu SW maps %.1f ms, %zu shadow regions realigned %.1f ms\n",
                        t_base - t_start, S, t_sw - t_base, shadows.size(), now() - t_sw);
-    // 3. CUSUM of the profile difference along each SW alignment (:51-94)
-    std::vector<std::vector<double>> dl(S);
+    // 3./4. CUSUM of the profile differences and greedy peak picking
+    std::vector<const std::vector<double>*> profs(S);
     for (size_t s = 0; s < S; s++)
     {
         std::vector<double>& prof = R->seqlikes[seeds[s]];
         if (prof.empty()) prof.assign(seeds[s].size(), 0.0);
-        std::vector<int>& i1 = als[s].inds1;
-        std::vector<int>& i2 = als[s].inds2;
-        for (size_t j = 0; j < i1.size(); j++) { i1[j] -= 2; i2[j] -= 2; }
-        size_t drop = 0;
-        while (drop < i1.size() && (i1[drop] < 0 || i2[drop] < 0)) drop++;
-        i1.erase(i1.begin(), i1.begin() + drop);
-        i2.erase(i2.begin(), i2.begin() + drop);
-        const size_t n = i1.size();
-        std::vector<double> a1(n), a2(n);
-        for (size_t j = 0; j < n; j++) { a1[j] = base[i1[j]]; a2[j] = prof[i2[j]]; }
-        for (size_t j = n; j-- > 1;) { a1[j] -= a1[j - 1]; a2[j] -= a2[j - 1]; }
-        if (n) { a1[0] = 0; a2[0] = 0; }
-        dl[s].resize(n);
-        double cus = 0;
-        for (size_t j = 0; j < n; j++)
-        {
-            cus += a2[j] - a1[j];
-            if (cus < 0) cus = 0;
-            dl[s][j] = std::fabs(a1[j] - a2[j]) < 1e-5 ? 0.0 : cus;
-        }
+        profs[s] = &prof;
     }
-    // 4. greedy peak picking (:111-183)
-    std::vector<long> peak_at(S, -1);              // cached first argmax of every seed's curve, -1 = stale
-    while (found.size() < L / 3)
-    {
-        int smax = -1, ind = 0;
-        double vmax = 0;
-        // (the reference rescans every seed's curve per pick; only the curve the previous pick zeroed can have
-        // a new first maximum, so the others keep their cached one -- same picks, same tie order)
-        for (size_t s = 0; s < S; s++)
-        {
-            if (dl[s].empty()) continue;
-            if (peak_at[s] < 0) peak_at[s] = (long)(std::max_element(dl[s].begin(), dl[s].end()) - dl[s].begin());
-            const size_t at = (size_t)peak_at[s];
-            if (smax < 0 || dl[s][at] > vmax) { smax = (int)s; ind = (int)at; vmax = dl[s][at]; }
-        }
-        if (smax < 0 || vmax < 0.25) break;
-        peak_at[smax] = -1;
-        std::vector<double>& d = dl[smax];
-        const int n = (int)d.size();
-        int i1 = ind;
-        while (i1 < n && d[i1] != 0) i1++;
-        int i0 = ind;
-        while (i0 >= 0 && d[i0] != 0) i0--;
-        if (i0 < 0) i0 = 0;
-        if (i1 >= n) i1 = n - 1;
-        const int start1 = als[smax].inds1[i0], start2 = als[smax].inds2[i0];
-        const int end1 = als[smax].inds1[ind], end2 = als[smax].inds2[ind];
-        HostMut m;
-        m.start = start1;
-        m.orig = R->bases.substr(start1, end1 - start1);
-        m.mut = seeds[smax].substr(start2, end2 - start2);
-        while (!m.orig.empty() && !m.mut.empty() && m.orig.front() == m.mut.front())
-        {
-            m.orig.erase(0, 1); m.mut.erase(0, 1); m.start++;
-        }
-        while (!m.orig.empty() && !m.mut.empty() && m.orig.back() == m.mut.back())
-        {
-            m.orig.pop_back(); m.mut.pop_back();
-        }
-        if (!m.orig.empty() || !m.mut.empty()) found.push_back(m);
-        std::fill(d.begin() + i0, d.begin() + i1 + 1, 0.0);
-    }
+    psi_pick_candidates(R->bases, base, seeds, profs, als, found);
     return PS_OK;
 }
 
@@ -269,6 +289,29 @@ int ps_find_mutations(ps_region* R, int n_seeds, const char* const* seeds, int* 
     std::vector<std::string> sv(n_seeds);
     for (int i = 0; i < n_seeds; i++) sv[i] = seeds[i] ? seeds[i] : "";
     TRY(ps_find_mutation_list(R, sv, R->found));
+    if (n_found) *n_found = (int)R->found.size();
+    return PS_OK;
+}
+
+int ps_pick_candidates(ps_region* R, int n_seeds, const char* const* seeds, const double* base_profile,
+                       const double* const* seed_profiles, int* n_found)
+{
+    if (!R || n_seeds < 0 || (n_seeds > 0 && (!seeds || !seed_profiles)) || !base_profile)
+        return PS_BAD_ARGS(R ? R->ctx : nullptr, "ps_pick_candidates");
+    std::vector<std::string> sv(n_seeds);
+    std::vector<std::vector<double>> pv(n_seeds);
+    std::vector<const std::vector<double>*> profs(n_seeds);
+    std::vector<SWResult> als(n_seeds);
+    for (int s = 0; s < n_seeds; s++)
+    {
+        if (!seeds[s] || !seed_profiles[s]) return PS_BAD_ARGS(R->ctx, "ps_pick_candidates");
+        sv[s] = seeds[s];
+        pv[s].assign(seed_profiles[s], seed_profiles[s] + sv[s].size());
+        profs[s] = &pv[s];
+    }
+    ps_parallel_for(n_seeds, [&](int s) { als[s] = psi_swfull(R->bases, sv[s]); psi_fillinds(als[s]); });
+    const std::vector<double> base(base_profile, base_profile + R->bases.size());
+    psi_pick_candidates(R->bases, base, sv, profs, als, R->found);
     if (n_found) *n_found = (int)R->found.size();
     return PS_OK;
 }

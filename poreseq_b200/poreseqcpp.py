@@ -92,6 +92,7 @@ def lib():
     L.ps_find_mutations.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), _c_int_p]
     L.ps_found_mutation_sizes.argtypes = [C.c_void_p, C.c_int, _c_int_p, _c_int_p]
     L.ps_get_found_mutation.argtypes = [C.c_void_p, C.c_int, _c_int_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+    L.ps_pick_candidates.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), _c_double_p, C.POINTER(_c_double_p), _c_int_p]
     L.ps_mutate.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.c_int, _c_int_p]
     L.ps_viterbi_mutate.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, _c_int_p]
     L.ps_get_viterbi_sequence.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
@@ -391,9 +392,22 @@ class NativeRegion(object):
     def map_alignments(self, newseq):
         self.ctx.check(self.ctx.lib.ps_map_alignments(self.handle, newseq.encode("ascii")))
 
+    def pick_candidates(self, seeds, base_profile, seed_profiles):
+        """ps_pick_candidates: the host-only second half of FindMutations over profiles the caller already holds."""
+        n = C.c_int(0)
+        base = np.ascontiguousarray(base_profile, dtype="f8")
+        profs = [np.ascontiguousarray(p, dtype="f8") for p in seed_profiles]
+        arr = (_c_double_p * max(len(profs), 1))(*[_dp(p) for p in profs])
+        self.ctx.check(self.ctx.lib.ps_pick_candidates(self.handle, len(seeds), _cstrs(seeds), _dp(base), arr, C.byref(n)))
+        return self._found(n.value)
+
     def find_mutations(self, seeds):
         n = C.c_int(0)
         self.ctx.check(self.ctx.lib.ps_find_mutations(self.handle, len(seeds), _cstrs(seeds), C.byref(n)))
+        return self._found(n.value)
+
+    def _found(self, count):
+        n = C.c_int(count)
         out = []
         for i in range(n.value):
             no, nm, st = C.c_int(0), C.c_int(0), C.c_int(0)

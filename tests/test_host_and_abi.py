@@ -540,3 +540,38 @@ def test_map_alignments_host_path_matches_reference(ref):
         got = [nr.event_align(e) for e in range(len(reg.events))]
         assert nr.sequence() == newseq and all(np.array_equal(g[0], w[0]) and np.array_equal(g[1], w[1]) for g, w in zip(got, want)), seed
         nr.close()
+
+
+def test_find_mutations_host_half_matches_reference(ref):
+    """ps_pick_candidates = the host-only second half of the product's FindMutations (swfull per seed, CUSUM of the profile
+    differences, greedy peak picking; cpp/FindMutations.cpp:51-186).  Fed with the likelihood profiles of the reference's
+    own ScoreAlignments (realign, MapAlignments per seed, realign the mapped copy -- what the GPU half computes), it must
+    return the reference's FindMutations candidate list, in order, incl. a repeated seed."""
+    import copy
+    ctx = poreseqcpp.Context(0)
+
+    def aligned(reg, seq, aligns):
+        rr = copy.deepcopy(reg)
+        rr.sequence = seq
+        for ev, (ra, rl) in zip(rr.events, aligns):
+            ev.ref_align, ev.ref_like = ra, rl
+        return rr
+
+    nonempty = 0
+    for seed in range(40):
+        rng = np.random.default_rng(seed)
+        reg = synth.make_region(int(rng.integers(40, 400)), int(rng.integers(1, 4)), seed=seed + 1,
+                                draft_error=float(rng.choice([0.03, 0.1])), partial=float(rng.choice([0, 0.4])),
+                                params=dict(realign_width=40, scoring_width=12, point_width=6))
+        seeds = [ev.sequence for ev in reg.events[::2]] + [synth.corrupt_sequence(reg.sequence, 0.08, rng)[0]]
+        seeds.append(seeds[0])
+        want, _ = ref.find_mutations(reg, seeds)
+        _, base, a1 = ref.score_alignments(reg, True)
+        reg1 = aligned(reg, reg.sequence, a1)
+        profs = [ref.score_alignments(aligned(reg1, sd, ref.map_alignments(reg1, sd)), True)[1] if len(sd) >= 5 else np.zeros(len(sd))
+                 for sd in seeds]
+        nr = poreseqcpp.NativeRegion(ctx, reg.sequence, reg.events, reg.params)
+        assert nr.pick_candidates(seeds, base, profs) == want, seed
+        nonempty += len(want) > 0
+        nr.close()
+    assert nonempty >= 30
