@@ -91,16 +91,44 @@ void psi_pick_candidates(const std::string& bases, const std::vector<double>& ba
     }
     // 4. greedy peak picking (:111-183)
     std::vector<long> peak_at(S, -1);              // cached first argmax of every seed's curve, -1 = stale
+    // The reference rescans every seed's curve per pick (std::max_element over ~L values, up to L/3 picks).  Only the
+    // curve the previous pick zeroed can have a new first maximum, so the others keep their cached one; and that
+    // curve's first maximum is found through per-block maxima (blocks of 64, refreshed where the pick zeroed):
+    // the first block holding the largest block maximum contains the first occurrence of the largest value.  Same
+    // picks, same tie order.
+    constexpr int PB = 64;
+    std::vector<std::vector<double>> bmax(S);
+    auto refresh_block = [&](size_t s, int b) {
+        const std::vector<double>& d = dl[s];
+        const int lo = b * PB, hi = std::min((int)d.size(), lo + PB);
+        double m = d[lo];
+        for (int k = lo + 1; k < hi; k++) m = d[k] > m ? d[k] : m;
+        bmax[s][b] = m;
+    };
+    auto first_argmax = [&](size_t s) -> long {
+        const std::vector<double>& d = dl[s];
+        const std::vector<double>& bm = bmax[s];
+        int bb = 0;
+        for (int b = 1; b < (int)bm.size(); b++) if (bm[b] > bm[bb]) bb = b;
+        const int lo = bb * PB, hi = std::min((int)d.size(), lo + PB);
+        int at = lo;
+        for (int k = lo + 1; k < hi; k++) if (d[k] > d[at]) at = k;
+        return at;
+    };
+    for (size_t s = 0; s < S; s++)
+    {
+        if (dl[s].empty()) continue;
+        bmax[s].resize((dl[s].size() + PB - 1) / PB);
+        for (int b = 0; b < (int)bmax[s].size(); b++) refresh_block(s, b);
+    }
     while (found.size() < L / 3)
     {
         int smax = -1, ind = 0;
         double vmax = 0;
-        // (the reference rescans every seed's curve per pick; only the curve the previous pick zeroed can have
-        // a new first maximum, so the others keep their cached one -- same picks, same tie order)
         for (size_t s = 0; s < S; s++)
         {
             if (dl[s].empty()) continue;
-            if (peak_at[s] < 0) peak_at[s] = (long)(std::max_element(dl[s].begin(), dl[s].end()) - dl[s].begin());
+            if (peak_at[s] < 0) peak_at[s] = first_argmax(s);
             const size_t at = (size_t)peak_at[s];
             if (smax < 0 || dl[s][at] > vmax) { smax = (int)s; ind = (int)at; vmax = dl[s][at]; }
         }
@@ -130,6 +158,7 @@ void psi_pick_candidates(const std::string& bases, const std::vector<double>& ba
         }
         if (!m.orig.empty() || !m.mut.empty()) found.push_back(m);
         std::fill(d.begin() + i0, d.begin() + i1 + 1, 0.0);
+        for (int b = i0 / PB; b <= i1 / PB; b++) refresh_block((size_t)smax, b);
     }
 }
 
@@ -309,9 +338,14 @@ int ps_pick_candidates(ps_region* R, int n_seeds, const char* const* seeds, cons
         pv[s].assign(seed_profiles[s], seed_profiles[s] + sv[s].size());
         profs[s] = &pv[s];
     }
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     ps_parallel_for(n_seeds, [&](int s) { als[s] = psi_swfull(R->bases, sv[s]); psi_fillinds(als[s]); });
     const std::vector<double> base(base_profile, base_profile + R->bases.size());
+    const double t1 = now();
     psi_pick_candidates(R->bases, base, sv, profs, als, R->found);
+    if (getenv("PORESEQ_B200_TRACE"))
+        fprintf(stderr, "[ps] pick_candidates: %d SW maps %.1f ms, CUSUM + peak picking %.1f ms (%zu candidates)\n", n_seeds, t1 - t0, now() - t1, R->found.size());
     if (n_found) *n_found = (int)R->found.size();
     return PS_OK;
 }
