@@ -1348,11 +1348,14 @@ int ps_make_mutation_list(ps_region* R, std::vector<HostMut> muts, int* nbases)
     *nbases = 0;
     if (muts.empty()) return PS_OK;
     std::vector<HostMut> deferred;
+    // the accepted edits are applied to a working copy of the bases; the region's sequence (and its 5-mer states) is
+    // replaced once after the loop -- nothing inside the loop reads the states (0.08 ms per accept at 10 kb otherwise)
+    std::string seq = R->bases;
     for (size_t i = 0; i < muts.size(); i++)
     {
         HostMut& a = muts[i];
         if (a.score < 0) { deferred.push_back(a); continue; }
-        R->set_sequence(ps_apply_mutation(R->bases, a.start, a.orig, a.mut));
+        seq = ps_apply_mutation(seq, a.start, a.orig, a.mut);
         changed += (int)std::max(a.orig.size(), a.mut.size());
         for (size_t j = i + 1; j < muts.size(); j++)
         {
@@ -1364,6 +1367,7 @@ int ps_make_mutation_list(ps_region* R, std::vector<HostMut> muts, int* nbases)
                 c.start += (int)(a.mut.size() - a.orig.size());
         }
     }
+    R->set_sequence(seq);
     if (deferred.size() > 10)
     {
         int more = 0;
