@@ -39,13 +39,26 @@ SWResult psi_map_alignments_with(ps_region* R, const std::string& newseq, SWResu
     R->set_sequence(newseq);
     const std::vector<int>& a = al.inds1;
     const std::vector<int>& b = al.inds2;
+    // lower_bound(a, v) for every v in [a.front(), a.back()] in one sweep (a is non-decreasing once its gaps are
+    // filled): the per-level search of the reference becomes a table look-up
+    std::vector<int> first_ge;
+    if (!a.empty() && a.back() >= a.front())
+    {
+        first_ge.resize((size_t)(a.back() - a.front()) + 1);
+        size_t idx = 0;
+        for (int v = a.front(); v <= a.back(); v++)
+        {
+            while (idx < a.size() && a[idx] < v) idx++;
+            first_ge[(size_t)(v - a.front())] = (int)idx;
+        }
+    }
     for (HostEvent& ev : R->events)
     {
         for (int j = 0; j < ev.n0; j++)
         {
             const int v = (int)ev.ref_align[j];
             if (a.empty() || v < a.front() || v > a.back()) { ev.ref_align[j] = 0; continue; }
-            const size_t at = std::lower_bound(a.begin(), a.end(), v) - a.begin();
+            const size_t at = (size_t)first_ge[(size_t)(v - a.front())];
             ev.ref_align[j] = at < b.size() ? b[at] : 0;
         }
         ev.update_refs();
