@@ -220,6 +220,9 @@ int ps_find_mutation_list(ps_region* R, const std::vector<std::string>& seeds, s
     // the shadow regions inherit the level records (3 log(stdv) per level) instead of each computing its own
     if (!shadow_key.empty())
         ps_parallel_for((int)R->events.size(), [&](int e) { R->events[e].ensure_levrec(); });
+    // (the profile cache stays out of the copies: up to one L-long profile per seed ever seen)
+    std::map<std::string, std::vector<double>> cache;
+    cache.swap(R->seqlikes);
     ps_parallel_for((int)S, [&](int s) {
         if (need[s])
         {
@@ -234,6 +237,7 @@ int ps_find_mutation_list(ps_region* R, const std::vector<std::string>& seeds, s
             psi_fillinds(als[s]);
         }
     });
+    R->seqlikes.swap(cache);
     for (size_t s = 0; s < S; s++)
         if (need[s]) shadows.push_back(nds[s]);        // same order as shadow_key
     const double t_sw = now();
