@@ -137,6 +137,12 @@ int         ps_region_get_event_align(ps_region* r, int e, double* ref_align, do
  * cpp/MakeMutations.cpp:148-195.  scores[n_events]; likes[len(sequence)] is accumulated into
  * when non-NULL.  Realigns every event in place. */
 int         ps_score_alignments(ps_region* r, double* scores, double* likes);
+/* PSAlign.ScoreEvents   poreseq/_poreseqcpp.pyx:263-276 (= ScoreAlignments(data, NULL) whose realignment is dropped,
+ * pyx:273-276): scores[n_events], the region's events keep their alignments.  PS_PRECISION_FAST: score-only log-space
+ * FP32 fill (k_score_f32, nothing stored), scores within 1e-4 relative; PS_PRECISION_EXACT: the FP64 fill, bit-identical.
+ * _batch: the events of n regions of ONE context in one launch sequence, scores concatenated in region order. */
+int         ps_score_events(ps_region* r, double* scores);
+int         ps_score_events_batch(ps_region* const* regions, int n_regions, double* scores);
 /* vector<MutScore> ScoreMutations(AlignData&, const vector<MutInfo>&)   cpp/Mutations.h:23,
  * cpp/MakeMutations.cpp:23-69.  orig[i]/mut[i] are NUL-terminated. */
 int         ps_score_mutations(ps_region* r, int n, const int* start, const char* const* orig,

@@ -26,23 +26,27 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines / out: experiment builds (kernel A/Bs, ablations) beside the shipped library; loaded through
+    PORESEQ_B200_LIB (poreseqcpp.lib)."""
+    if out is None and not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    target = LIB if out is None else os.path.join(HERE, out)
+    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", target]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     log = proc.stdout + proc.stderr
-    with open(os.path.join(HERE, "build.log"), "w") as f:
+    with open(os.path.join(HERE, "build.log" if out is None else out + ".log"), "w") as f:
         f.write(" ".join(cmd) + "\n" + log)
     if proc.returncode != 0:
         sys.stderr.write(log)
         raise RuntimeError("nvcc failed building %s" % LIB)
     if verbose:
         sys.stderr.write(log)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose=True)
-    print(LIB)
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="--quiet" not in sys.argv, defines=defs, out=outs[0] if outs else None))

@@ -184,7 +184,7 @@ int ps_find_mutation_list(ps_region* R, const std::vector<std::string>& seeds, s
     found.clear();
     ps_ctx* ctx = R->ctx;
     const size_t L = R->bases.size();
-    const bool trace = getenv("PORESEQ_B200_TRACE") != nullptr;
+    const bool trace = ctx->trace;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_start = now();
     // 1. realign to the current sequence, keep its per-base likelihood profile
@@ -205,7 +205,7 @@ int ps_find_mutation_list(ps_region* R, const std::vector<std::string>& seeds, s
     // on the GPU (ps_sw.cu) for sequences up to 16 k bases, else on the host worker threads
     std::vector<ps_region*> nds(S, nullptr);
     std::vector<SWResult> sw;
-    const bool sw_gpu = !getenv("PORESEQ_B200_SW_HOST") && psi_swfull_batch(ctx, R->bases, seeds, sw) == PS_OK;
+    const bool sw_gpu = !ctx->sw_host && psi_swfull_batch(ctx, R->bases, seeds, sw) == PS_OK;
     // Only the first occurrence of a seed whose profile is not cached yet needs a shadow region (a copy of every
     // event, 36 MB for 10 kb x 30x); for the others the SW alignment with its gaps filled (what MapAlignments returns)
     // is all the CUSUM below reads.
@@ -272,7 +272,7 @@ int ps_mutate_loop(ps_region* R, const std::vector<std::string>& seeds, int reps
     int total = 0;
     for (int rep = 0; rep < reps; rep++)
     {
-        const bool trace = getenv("PORESEQ_B200_TRACE") != nullptr;
+        const bool trace = R->ctx->trace;
         auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         const double t0 = now();
         std::vector<HostMut> cand;
@@ -334,7 +334,10 @@ int ps_find_mutations(ps_region* R, int n_seeds, const char* const* seeds, int* 
     if (!R || n_seeds < 0 || (n_seeds > 0 && !seeds)) return PS_BAD_ARGS(R ? R->ctx : nullptr, "ps_find_mutations");
     std::vector<std::string> sv(n_seeds);
     for (int i = 0; i < n_seeds; i++) sv[i] = seeds[i] ? seeds[i] : "";
-    TRY(ps_find_mutation_list(R, sv, R->found));
+    R->seqlikes.clear();               // a stand-alone FindMutations starts from an empty profile cache (fresh AlignData)
+    const int rc = ps_find_mutation_list(R, sv, R->found);
+    R->seqlikes.clear();
+    if (rc) return rc;
     if (n_found) *n_found = (int)R->found.size();
     return PS_OK;
 }
@@ -361,7 +364,7 @@ int ps_pick_candidates(ps_region* R, int n_seeds, const char* const* seeds, cons
     const std::vector<double> base(base_profile, base_profile + R->bases.size());
     const double t1 = now();
     psi_pick_candidates(R->bases, base, sv, profs, als, R->found);
-    if (getenv("PORESEQ_B200_TRACE"))
+    if (R->ctx && R->ctx->trace)
         fprintf(stderr, "[ps] pick_candidates: %d SW maps %.1f ms, CUSUM + peak picking %.1f ms (%zu candidates)\n", n_seeds, t1 - t0, now() - t1, R->found.size());
     if (n_found) *n_found = (int)R->found.size();
     return PS_OK;
@@ -392,7 +395,9 @@ int ps_mutate(ps_region* R, int n_seeds, const char* const* seeds, int reps, int
     std::vector<std::string> sv(n_seeds);
     for (int i = 0; i < n_seeds; i++) sv[i] = seeds[i] ? seeds[i] : "";
     int tot = 0;
+    R->seqlikes.clear();               // the reference's profile cache lives for ONE Mutate call (fresh AlignData, pyx:407-408; A.3-14)
     TRY(ps_mutate_loop(R, sv, reps, &tot));
+    R->seqlikes.clear();
     if (totbases) *totbases = tot;
     return PS_OK;
 }

@@ -377,7 +377,14 @@ __global__ void k_flag(Batch b, long long n_muts, int max_mut)
 {
     long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_muts) return;
-    if (b.scores[g] > -b.tau || b.muts[g].n_mut > max_mut)
+    // tau is per event of the mutation's region: an FP32 total over E events carries at most E times the per-pair error
+    int lo = 0, hi = b.n_regs - 1;
+    while (lo < hi)
+    {
+        const int mid = (lo + hi + 1) >> 1;
+        if (b.regs[mid].mut_off <= g) lo = mid; else hi = mid - 1;
+    }
+    if (b.scores[g] > -b.tau * (double)b.regs[lo].nev || b.muts[g].n_mut > max_mut)
     {
         const int q = atomicAdd(b.flag_count, 1);
         b.flag_list[q] = (int)g;

@@ -27,6 +27,7 @@
 #include "../../include/poreseq_b200.h"
 #include "ps_device.cuh"
 #include "ps_fast.cuh"
+#include "ps_score32.cuh"
 #include "ps_internal.h"
 
 using namespace psdev;
@@ -42,6 +43,9 @@ void ps_set_error(ps_ctx* ctx, const char* fmt, ...)
     va_start(ap, fmt);
     vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
+    // several library threads may refuse their regions at once (ps_regions_create, ps_pack_regions_create)
+    static std::mutex error_lock;
+    std::lock_guard<std::mutex> hold(error_lock);
     if (ctx) ctx->error = buf; else g_create_error = buf;
 }
 
@@ -278,6 +282,10 @@ int ps_ctx::init()
     CU(cudaFuncSetAttribute(k_mutscore_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU(cudaFuncSetAttribute(k_mutscore<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU(cudaFuncSetAttribute(k_mutscore<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CU(cudaFuncSetAttribute(k_score_f32<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CU(cudaFuncSetAttribute(k_score_f32<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CU(cudaFuncSetAttribute(k_score_f32<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CU(cudaFuncSetAttribute(k_score_f32<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     // the per-thread rings of the exact mutation kernel are what limits its occupancy: ask for the largest shared-memory carve-out
     CU(cudaFuncSetAttribute(k_mutscore<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_mutscore<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -446,6 +454,9 @@ struct MutSpec                      // the mutations of one region: an explicit 
 
 typedef RegTabDev RegTab;
 
+// absolute error bound of one FP32 (mutation, event) delta of k_mutscore_rows_f32, see Job::upload
+constexpr double PS_FAST_PAIR_ERR = 5e-5;     // 3x the largest error seen (1.55e-5 per event, profiles/r2_fast_error.txt)
+
 struct Job
 {
     ps_ctx* ctx;
@@ -459,6 +470,9 @@ struct Job
     PinVec<char> bases;
     PinVec<LevIn> lev;
     bool fast = false;                           // FP32 pass + exact re-score (PS_PRECISION_FAST)
+    bool score32 = false;                        // ScoreEvents in FAST mode: k_score_f32, no matrices, no backtrace, events untouched
+    PinVec<int> s32_list;                        // events by launch class of k_score_f32: (staged, plain), (staged, inv), (global, plain), (global, inv)
+    int s32_count[4] = {0, 0, 0, 0}, s32_max_n0 = 0;
     int max_ev = 1;
     PinVec<double> ref_align, ref_like, ref_index;
     PinVec<int> ri_empty, mono, cen_old;
@@ -476,6 +490,7 @@ struct Job
     int cen_pad;
     Batch b;
     RegTab* d_regtab = nullptr;
+    int* d_s32_list = nullptr;
     double* d_evbest = nullptr;
 
     Job(ps_ctx* c) : ctx(c), want_muts(false), n_levels(0), n_cols(0), n_cen(0), n_tasks(0), n_muts(0), n_band(0), cen_pad(8)
@@ -485,7 +500,7 @@ struct Job
         ref_like = c->pinned<double>("ref_like"); ref_index = c->pinned<double>("ref_index");
         ri_empty = c->pinned<int>("ri_empty"); mono = c->pinned<int>("mono"); cen_old = c->pinned<int>("cen_old");
         mdev = c->pinned<MutDev>("mdev"); mut_str = c->pinned<char>("mut_str"); regtab = c->pinned<RegTab>("regtab");
-        fill_list = c->pinned<int>("fill_list");
+        fill_list = c->pinned<int>("fill_list"); s32_list = c->pinned<int>("s32_list");
     }
 
     void plan_event(const HostEvent& he, const EvDesc& d, int rw, int* cen, int* ok_out, int* need_out, double* cells_out);
@@ -606,7 +621,7 @@ int Job::build()
     }
     mut_str.append("ACGT", 4);                  // single-base replacement strings live at offsets 0..3
 
-    const bool trace_b = getenv("PORESEQ_B200_TRACE") != nullptr;
+    const bool trace_b = ctx->trace;
     auto nowb = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double tb0 = nowb();
     // pass 1 (serial, cheap): region tables, list-mutation tables, event descriptors and offsets.  The
@@ -834,7 +849,7 @@ int Job::upload()
     b.cen_pad = cen_pad;
     // exact pass with one warp per (mutation, event) pair when the pairs are few and no replacement string needs
     // more than 32 narrow columns (k_mutscore_warp)
-    b.warp_limit = ((size_t)(2 * P.scoring_width + 2) * 8 * sizeof(double) <= 96 * 1024 && !getenv("PORESEQ_B200_NO_WARP")) ? 32768 : 0;
+    b.warp_limit = ((size_t)(2 * P.scoring_width + 2) * 8 * sizeof(double) <= 96 * 1024 && !ctx->no_warp) ? 32768 : 0;
     b.RS = ((2 * P.realign_width + 1) + 3) & ~3;
     b.n_tasks = n_tasks;
 
@@ -864,7 +879,7 @@ int Job::upload()
     TRY(up(ctx, "cen_old", cen_old.data(), cen_old.size(), &b.cen_old));
     TRY(room(ctx, "cen_new", (size_t)n_cen, &b.cen_new));
 
-    const size_t cells = (size_t)std::max<long long>(n_band, 1);
+    const size_t cells = score32 ? 1 : (size_t)std::max<long long>(n_band, 1);     // k_score_f32 stores no band matrices
     TRY(room(ctx, "Fm", cells, &b.Fm));
     TRY(room(ctx, "Fs", cells, &b.Fs));
     TRY(room(ctx, "Fstep", cells, &b.Fstep));
@@ -899,40 +914,65 @@ int Job::upload()
         b.regs = d_rt; b.n_regs = (int)regs.size(); b.max_ev = max_ev;
         TRY(room(ctx, "flag_list", (size_t)n_muts + 1, &b.flag_list));
         TRY(room(ctx, "flag_count", 1, &b.flag_count));
-        if (fast)
+    }
+    if (fast || score32)
+    {
+        // FP32 twins: fused emission coefficients per state, log transition costs per model
+        PinVec<StateParamsF> stf = ctx->pinned<StateParamsF>("stf");
+        PinVec<float4> trf = ctx->pinned<float4>("trf");
+        if (!stf.resize(model_src.size() * N_STATES) || !trf.resize(model_src.size()))
         {
-            // FP32 twins: fused emission coefficients per state, log transition costs per model
-            PinVec<StateParamsF> stf = ctx->pinned<StateParamsF>("stf");
-            PinVec<float4> trf = ctx->pinned<float4>("trf");
-            if (!stf.resize(model_src.size() * N_STATES) || !trf.resize(model_src.size()))
-            {
-                ps_set_error(ctx, "out of host memory staging the models");
-                return PS_E_INTERNAL;
-            }
-            const double l2p = std::log(2 * M_PI);
-            for (size_t q = 0; q < model_src.size(); q++)
-            {
-                const ModelDev& md = models[q];
-                for (int st = 0; st < N_STATES; st++)
-                {
-                    const StateParams& sp = md.st[st];
-                    StateParamsF& f = stf[q * N_STATES + st];
-                    f.mu = (float)sp.lev_mean;
-                    f.a_s = (float)(-0.5 / (sp.lev_stdv * sp.lev_stdv));
-                    f.c_s = (float)(-0.5 * l2p - sp.log_lev + 0.5 * (sp.log_lambda - l2p) + P.lik_offset);
-                    f.mu2 = (float)sp.sd_mean;
-                    f.f_s = (float)(-0.5 * sp.sd_lambda / (sp.sd_mean * sp.sd_mean));
-                    f.pad0 = f.pad1 = f.pad2 = 0.f;
-                }
-                trf[q] = make_float4((float)md.lskip, (float)md.lstay, (float)md.lext, (float)md.lins);
-            }
-            StateParamsF* d_stf; float4* d_trf;
-            TRY(up(ctx, "stf", stf.data(), stf.size(), &d_stf));
-            TRY(up(ctx, "trf", trf.data(), trf.size(), &d_trf));
-            TRY(room(ctx, "levf", (size_t)std::max<long long>(n_levels, 1), &b.levf));
-            b.stf = d_stf; b.trf = d_trf;
-            b.tau = 0.02 + 5e-4 * max_ev;
+            ps_set_error(ctx, "out of host memory staging the models");
+            return PS_E_INTERNAL;
         }
+        const double l2p = std::log(2 * M_PI);
+        for (size_t q = 0; q < model_src.size(); q++)
+        {
+            const ModelDev& md = models[q];
+            for (int st = 0; st < N_STATES; st++)
+            {
+                const StateParams& sp = md.st[st];
+                StateParamsF& f = stf[q * N_STATES + st];
+                f.mu = (float)sp.lev_mean;
+                f.a_s = (float)(-0.5 / (sp.lev_stdv * sp.lev_stdv));
+                f.c_s = (float)(-0.5 * l2p - sp.log_lev + 0.5 * (sp.log_lambda - l2p) + P.lik_offset);
+                f.mu2 = (float)sp.sd_mean;
+                f.f_s = (float)(-0.5 * sp.sd_lambda / (sp.sd_mean * sp.sd_mean));
+                f.pad0 = f.pad1 = f.pad2 = 0.f;
+            }
+            trf[q] = make_float4((float)md.lskip, (float)md.lstay, (float)md.lext, (float)md.lins);
+        }
+        StateParamsF* d_stf; float4* d_trf;
+        TRY(up(ctx, "stf", stf.data(), stf.size(), &d_stf));
+        TRY(up(ctx, "trf", trf.data(), trf.size(), &d_trf));
+        TRY(room(ctx, "levf", (size_t)std::max<long long>(n_levels, 1) + 1, &b.levf));   // + 1: k_score_f32 requests one row ahead
+        b.stf = d_stf; b.trf = d_trf;
+        // Re-score threshold of the FAST mode, per EVENT of the mutation's region (k_flag multiplies by the region's
+        // event count).  PS_FAST_PAIR_ERR bounds the absolute error of one rebased FP32 (mutation, event) delta
+        // (measured: scripts/fast_error.py -> profiles/r2_fast_error.txt); a total over E events is then off by at
+        // most E * PS_FAST_PAIR_ERR, and every mutation whose FP32 total is above -tau = -E * PS_FAST_PAIR_ERR / 1e-4
+        // is re-scored exactly -- so what keeps its FP32 value is within 1e-4 RELATIVE of the reference
+        // (BASELINE.json north_star), with no absolute slack.
+        b.tau = ctx->tau_override >= 0 ? ctx->tau_override : PS_FAST_PAIR_ERR * 1e4;
+    }
+    if (score32)
+    {
+        // launch classes of k_score_f32: level records staged whole by one TMA bulk copy (short events) or read through
+        // L1, plain ACGT regions or regions with invalid states
+        const int ne = (int)ev.size();
+        if (!s32_list.resize((size_t)std::max(ne, 1))) { ps_set_error(ctx, "out of host memory staging the batch"); return PS_E_INTERNAL; }
+        auto cls = [&](const EvDesc& d) { return ((d.n0 <= PS_SCORE32_STAGE_LEVELS && !ctx->no_stage) ? 0 : 2) + (d.inv ? 1 : 0); };
+        for (int e = 0; e < ne; e++) s32_count[cls(ev[e])]++;
+        int at[4] = {0, s32_count[0], s32_count[0] + s32_count[1], s32_count[0] + s32_count[1] + s32_count[2]};
+        for (int e = 0; e < ne; e++)
+        {
+            const int c = cls(ev[e]);
+            s32_list[at[c]++] = e;
+            if (c < 2) s32_max_n0 = std::max(s32_max_n0, ev[e].n0);
+        }
+        int* d_list;
+        TRY(up(ctx, "s32_list", s32_list.data(), s32_list.size(), &d_list));
+        d_s32_list = d_list;
     }
     return PS_OK;
 }
@@ -948,10 +988,36 @@ int Job::run(bool full)
     if (nev == 0) return PS_OK;
     MARK(PS_T_CENTRES);    // (pre-call band centres are planned on the host, see plan_event)
     MARK(PS_T_FORWARD);
+    if (score32)
+    {
+        int maxn0 = 0;
+        for (const EvDesc& d : ev) maxn0 = std::max(maxn0, d.n0);
+        k_rows<<<dim3((maxn0 + 127) / 128, nev), 128, 0, ctx->stream>>>(b);
+        LAUNCHED();
+        TRY(room(ctx, "evbest", ev.size(), &d_evbest));
+        Score32Args a;
+        a.out = d_evbest;
+        a.strip = 64;
+        while (a.strip < 2 * b.realign_width + 64) a.strip <<= 1;
+        const size_t strips = (size_t)PS_SCORE32_WARPS * a.strip * sizeof(float);
+        const size_t staged = strips + (size_t)(s32_max_n0 + 1) * sizeof(LevelRecF);
+        const int threads = 32 * PS_SCORE32_WARPS;
+        int off = 0;
+        a.list = d_s32_list + off;
+        if (s32_count[0]) { k_score_f32<true, false><<<s32_count[0], threads, staged, ctx->stream>>>(b, a); LAUNCHED(); }
+        off += s32_count[0]; a.list = d_s32_list + off;
+        if (s32_count[1]) { k_score_f32<true, true><<<s32_count[1], threads, staged, ctx->stream>>>(b, a); LAUNCHED(); }
+        off += s32_count[1]; a.list = d_s32_list + off;
+        if (s32_count[2]) { k_score_f32<false, false><<<s32_count[2], threads, strips, ctx->stream>>>(b, a); LAUNCHED(); }
+        off += s32_count[2]; a.list = d_s32_list + off;
+        if (s32_count[3]) { k_score_f32<false, true><<<s32_count[3], threads, strips, ctx->stream>>>(b, a); LAUNCHED(); }
+        MARK(PS_T_BACKWARD); MARK(PS_T_BACKTRACE); MARK(PS_T_JOIN); MARK(PS_T_MUTSCORE); MARK(PS_T_REDUCE); MARK(PS_T_D2H);
+        return PS_OK;
+    }
     // wavefront fill: one CTA per (event, direction), forward and reverse in one launch (grid.y = 2),
     // one launch per width class
     {
-        if (getenv("PORESEQ_B200_TRACE"))
+        if (ctx->trace)
             fprintf(stderr, "[ps] fill: %d events: %d at 160 threads, %d at 192, %d at %d, %d serial; band cells %lld\n", nev,
                     fill_count[0], fill_count[1], fill_count[2], fill_threads[2], fill_count[3], n_band);
         const int dirs = full ? 2 : 1;
@@ -1094,6 +1160,15 @@ int Job::download_enqueue()
         ps_set_error(ctx, "out of host memory staging the results");
         return PS_E_INTERNAL;
     }
+    if (score32)
+    {
+        // scores only: the events keep their alignments (poreseq/_poreseqcpp.pyx:273-276)
+        if (ne) CU(cudaMemcpyAsync(best.data(), d_evbest, ne * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->d2h_bytes += (long long)(ne * sizeof(double));
+        have_scores = false;
+        MARK(PS_T_TOTAL);
+        return PS_OK;
+    }
     if (nl)
     {
         CU(cudaMemcpyAsync(ref_align.data(), b.ref_align, nl * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1124,7 +1199,7 @@ int Job::finish(std::vector<double>* align_scores, std::vector<double>* mut_scor
     hev.reserve(ne);
     for (ps_region* R : regs)
         for (HostEvent& he : R->events) hev.push_back(&he);
-    ps_parallel_for((int)ne, [&](int e) {
+    if (!score32) ps_parallel_for((int)ne, [&](int e) {
         const EvDesc& d = ev[e];
         if (!d.usable) return;
         HostEvent& he = *hev[e];
@@ -1173,7 +1248,7 @@ int Job::finish(std::vector<double>* align_scores, std::vector<double>* mut_scor
 // One job = build (host staging) + upload + kernels + result copies, all enqueued on the context's
 // stream by job_begin; job_end waits for the stream and scatters the results into the regions.
 // Between the two the host is free (e.g. to stage the next batch on another context).
-static int job_begin(ps_ctx* ctx, const std::vector<ps_region*>& regs, const std::vector<MutSpec>* muts, double bias)
+static int job_begin(ps_ctx* ctx, const std::vector<ps_region*>& regs, const std::vector<MutSpec>* muts, double bias, bool score32 = false)
 {
     TRY(ctx->init());
     CU(cudaSetDevice(ctx->device));
@@ -1185,8 +1260,11 @@ static int job_begin(ps_ctx* ctx, const std::vector<ps_region*>& regs, const std
     job->want_muts = muts != nullptr;
     if (muts) job->muts = *muts;
     job->bias = bias;
-    job->fast = ctx->precision == PS_PRECISION_FAST && muts != nullptr;
-    const bool trace = getenv("PORESEQ_B200_TRACE") != nullptr;
+    job->score32 = score32 && muts == nullptr;
+    // FAST flags mutations by their TOTAL over all events; an event shard (bias 0, ps_score_mutations_partial) only has
+    // its part of the sum, so partial sums are always exact
+    job->fast = ctx->precision == PS_PRECISION_FAST && muts != nullptr && bias != 0.0;
+    const bool trace = ctx->trace;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = now();
     ctx->h2d_bytes = 0; ctx->d2h_bytes = 0;
@@ -1214,7 +1292,7 @@ static int job_end(ps_ctx* ctx, std::vector<double>* align_scores, std::vector<d
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = now();
     int rc = job->finish(align_scores, mut_scores);
-    if (getenv("PORESEQ_B200_TRACE")) fprintf(stderr, "[ps] host: wait+scatter %.2f ms (device total %.2f)\n", now() - t0, ctx->timing[PS_T_TOTAL]);
+    if (ctx->trace) fprintf(stderr, "[ps] host: wait+scatter %.2f ms (device total %.2f)\n", now() - t0, ctx->timing[PS_T_TOTAL]);
     delete job;
     return rc;
 }
@@ -1240,7 +1318,7 @@ static int run_job(ps_ctx* ctx, const std::vector<ps_region*>& regs, const std::
     // sub-batches of 76 GB and 432 ms as eight of 30 GB (240 events = one wave of the 192-thread fill class each),
     // measured on a B200 (gpurun_out -> profiles/r1_consensus_10kb_trace.txt).
     double budget = std::min(0.40 * (double)ctx->total_mem, 32e9);
-    if (const char* e = getenv("PORESEQ_B200_BAND_BUDGET")) budget = atof(e);      // bytes; tests force the split path with it
+    if (ctx->band_budget > 0) budget = ctx->band_budget;      // bytes; tests force the split path with it
     double total = 0;
     for (const ps_region* R : regs) total += region_band_bytes(R, muts != nullptr);
     if (total <= budget || regs.size() <= 1)
@@ -1305,6 +1383,44 @@ int ps_run_alignments(ps_ctx* ctx, const std::vector<ps_region*>& regs,
     return PS_OK;
 }
 
+// PSAlign.ScoreEvents (poreseq/_poreseqcpp.pyx:263-276): ScoreAlignments(data, NULL) -- one score per event, nothing else
+// leaves the call (the realignment is not propagated, A.3-10), so the regions' events are left as they were.
+// FAST precision: k_score_f32 (log-space FP32, no matrices, no backtrace); EXACT: the FP64 forward fill.
+int ps_run_event_scores(ps_ctx* ctx, const std::vector<ps_region*>& regs, std::vector<double>* flat)
+{
+    TRY(ctx->init());
+    bool f32 = ctx->precision == PS_PRECISION_FAST;
+    for (const ps_region* R : regs)
+        for (const HostModel& hm : R->models)                       // k_score_f32 folds implicit moves into the floor: needs log p <= 0
+            if (!(hm.trans[0] <= 1.0) || !(hm.trans[3] <= 1.0)) f32 = false;
+    if (f32)
+    {
+        TRY(job_begin(ctx, regs, nullptr, -1e-6, true));
+        return job_end(ctx, flat, nullptr);
+    }
+    // exact: the job realigns the events in place; put the alignments back afterwards
+    struct Keep { LevelVec ref_align, ref_like; bool ri_empty; int refstart, refend; };
+    std::vector<Keep> keep;
+    for (ps_region* R : regs)
+        for (HostEvent& he : R->events)
+        {
+            he.ensure_refs();
+            keep.push_back(Keep{he.ref_align, he.ref_like, he.ri_empty, he.refstart, he.refend});
+        }
+    const int rc = run_job(ctx, regs, nullptr, flat, nullptr);
+    size_t k = 0;
+    for (ps_region* R : regs)
+        for (HostEvent& he : R->events)
+        {
+            Keep& q = keep[k++];
+            he.ref_align.swap(q.ref_align); he.ref_like.swap(q.ref_like);
+            he.ri_empty = q.ri_empty; he.refstart = q.refstart; he.refend = q.refend;
+            he.ri_stale = !he.ri_empty;
+            if (he.ri_empty) he.ref_index.clear();
+        }
+    return rc;
+}
+
 std::vector<HostMut> ps_point_mutations(const ps_region* R)      // cpp/FindMutations.cpp:191-234
 {
     static const char acgt[] = "ACGT";
@@ -1330,7 +1446,47 @@ int ps_score_mutation_list(ps_region* R, std::vector<HostMut>& muts, double bias
     std::vector<MutSpec> per(1);
     per[0].list = &muts;
     std::vector<double> sc;
-    TRY(run_job(R->ctx, std::vector<ps_region*>(1, R), &per, nullptr, &sc, bias));
+    ps_ctx* ctx = R->ctx;
+    const bool fast = ctx->precision == PS_PRECISION_FAST && bias != 0.0;
+    // FAST keeps approximate values for the clearly negative scores.  MakeMutations sorts the whole list with an UNSTABLE
+    // std::sort (cpp/MakeMutations.cpp:83) before it drops the negative ones, so where two exactly tied non-negative
+    // scores end up can depend on the negative keys around them.  Such ties get the whole list re-scored exactly, from
+    // the alignments the first pass started from (the pass realigns the events in place).
+    struct Seed { LevelVec ref_align; bool ri_empty; int refstart, refend; };
+    std::vector<Seed> seeds;
+    if (fast)
+    {
+        seeds.resize(R->events.size());
+        for (size_t e = 0; e < R->events.size(); e++)
+        {
+            const HostEvent& he = R->events[e];
+            seeds[e].ref_align = he.ref_align; seeds[e].ri_empty = he.ri_empty;
+            seeds[e].refstart = he.refstart; seeds[e].refend = he.refend;
+        }
+    }
+    TRY(run_job(ctx, std::vector<ps_region*>(1, R), &per, nullptr, &sc, bias));
+    if (fast)
+    {
+        std::vector<double> keep;
+        for (double v : sc) if (v >= 0) keep.push_back(v);
+        std::sort(keep.begin(), keep.end());
+        if (std::adjacent_find(keep.begin(), keep.end()) != keep.end())
+        {
+            for (size_t e = 0; e < R->events.size(); e++)
+            {
+                HostEvent& he = R->events[e];
+                he.ref_align = seeds[e].ref_align; he.ri_empty = seeds[e].ri_empty;
+                he.refstart = seeds[e].refstart; he.refend = seeds[e].refend;
+                he.ri_stale = !he.ri_empty;
+                if (he.ri_empty) he.ref_index.clear();
+            }
+            ctx->precision = PS_PRECISION_EXACT;
+            const int rc = run_job(ctx, std::vector<ps_region*>(1, R), &per, nullptr, &sc, bias);
+            ctx->precision = PS_PRECISION_FAST;
+            if (rc) return rc;
+            ctx->exact_reruns++;
+        }
+    }
     for (size_t i = 0; i < muts.size(); i++) muts[i].score = sc[i];
     return PS_OK;
 }
@@ -1395,6 +1551,12 @@ ps_ctx* ps_create(int device)
 {
     ps_ctx* ctx = new ps_ctx();
     ctx->device = device;
+    ctx->trace = getenv("PORESEQ_B200_TRACE") != nullptr;
+    ctx->no_warp = getenv("PORESEQ_B200_NO_WARP") != nullptr;
+    ctx->sw_host = getenv("PORESEQ_B200_SW_HOST") != nullptr;
+    ctx->no_stage = getenv("PORESEQ_B200_NO_STAGE") != nullptr;
+    if (const char* e = getenv("PORESEQ_B200_BAND_BUDGET")) ctx->band_budget = atof(e);
+    if (const char* e = getenv("PORESEQ_B200_TAU")) ctx->tau_override = atof(e);
     return ctx;                       // CUDA is initialised lazily (fork-safe)
 }
 
@@ -1600,6 +1762,27 @@ int ps_score_alignments(ps_region* R, double* scores, double* likes)
     TRY(ps_run_alignments(R->ctx, std::vector<ps_region*>(1, R), &sc, likes ? &lk : nullptr));
     std::copy(sc[0].begin(), sc[0].end(), scores);
     if (likes) for (size_t k = 0; k < lk[0].size(); k++) likes[k] += lk[0][k];
+    return PS_OK;
+}
+
+int ps_score_events(ps_region* R, double* scores)
+{
+    if (!R || !scores) return PS_BAD_ARGS(R ? R->ctx : nullptr, "ps_score_events");
+    std::vector<double> flat;
+    TRY(ps_run_event_scores(R->ctx, std::vector<ps_region*>(1, R), &flat));
+    std::copy(flat.begin(), flat.end(), scores);
+    return PS_OK;
+}
+
+int ps_score_events_batch(ps_region* const* regions, int n_regions, double* scores)
+{
+    if (n_regions < 0 || (n_regions > 0 && (!regions || !scores))) return PS_BAD_ARGS(nullptr, "ps_score_events_batch");
+    if (n_regions == 0) return PS_OK;
+    for (int k = 0; k < n_regions; k++)
+        if (!regions[k] || regions[k]->ctx != regions[0]->ctx) return PS_BAD_ARGS(regions[0] ? regions[0]->ctx : nullptr, "ps_score_events_batch");
+    std::vector<double> flat;
+    TRY(ps_run_event_scores(regions[0]->ctx, std::vector<ps_region*>(regions, regions + n_regions), &flat));
+    std::copy(flat.begin(), flat.end(), scores);
     return PS_OK;
 }
 

@@ -49,7 +49,16 @@ struct ps_ctx
     double wide_cells = 0, narrow_cells = 0;
     long long h2d_bytes = 0, d2h_bytes = 0;   // bytes the last batch copied to / from the device
     long long launches = 0;
+    long long exact_reruns = 0;               // FAST-mode lists re-scored exactly because of tied non-negative scores
     void* pending = nullptr;                  // the batch in flight between *_begin and *_end (a Job)
+    // environment knobs, read ONCE when the context is created (ps_create): a per-call getenv() races with a
+    // setenv() of the host program
+    bool trace = false;                       // PORESEQ_B200_TRACE: phase timings on stderr
+    bool no_warp = false;                     // PORESEQ_B200_NO_WARP: never use the warp-per-pair exact kernel
+    bool sw_host = false;                     // PORESEQ_B200_SW_HOST: FindMutations' Smith-Waterman maps on the host
+    double band_budget = 0;                   // PORESEQ_B200_BAND_BUDGET: bytes of band storage per sub-batch (0: default)
+    bool no_stage = false;                    // PORESEQ_B200_NO_STAGE: k_score_f32 reads level records through L1 instead of a TMA-staged copy (A/B)
+    double tau_override = -1;                 // PORESEQ_B200_TAU: FAST-mode re-score threshold (diagnostics; < 0: derived)
     std::string error;
     std::map<std::string, DevBuf> bufs;       // grow-only named device buffers, reused across calls
     std::map<std::string, PinBuf> pins;       // grow-only named pinned host buffers

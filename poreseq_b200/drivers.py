@@ -20,19 +20,27 @@ def make_psalign(region):
     return pa
 
 
-def consensus(pa, refseq=None, reps=4, verbose=0, log=sys.stderr):
+def consensus(pa, refseq=None, reps=4, verbose=0, log=sys.stderr, stages=None):
     """Consensus error correction of one region: Mutate('self') then up to `reps` rounds of
     (Mutate('viterbi'), Refine) until Refine changes nothing, then end trimming
-    (poreseq/Mutate.py:47-99).  Returns (sequence, accuracy vs refseq or None)."""
+    (poreseq/Mutate.py:47-99).  Returns (sequence, accuracy vs refseq or None).
+    `stages`: a list that receives (stage name, sequence, bases changed, [ref_align per event]) after every stage
+    (the parity tests compare them with the reference's)."""
     params = pa.params
     if len(pa.events) < 5:                       # Mutate.py:50-53
         return pa.sequence, 100
-    pa.Mutate(reps=reps)
+
+    def note(name, nb):
+        if stages is not None:
+            stages.append((name, pa.sequence, int(nb), [np.array(ev.ref_align, dtype="f8") for ev in pa.events]))
+
+    note("mutate_self", pa.Mutate(reps=reps))
     if verbose and refseq:
         log.write("Accuracy: %.1f%%\n" % poreseqcpp.swalign(pa.sequence, refseq)[0])
-    for _ in range(reps):
-        pa.Mutate(seqs='viterbi')
+    for k in range(reps):
+        note("mutate_viterbi_%d" % k, pa.Mutate(seqs='viterbi'))
         nbases = pa.Refine()
+        note("refine_%d" % k, nbases)
         if verbose and refseq:
             log.write("Accuracy: %.1f%%\n" % poreseqcpp.swalign(pa.sequence, refseq)[0])
         if nbases == 0:

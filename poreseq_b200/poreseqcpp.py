@@ -18,7 +18,8 @@ import numpy as np
 from .Util import MutationInfo, MutationScore  # noqa: F401  (re-exported like the reference)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libporeseq_b200.so")
+# PORESEQ_B200_LIB: an experiment build of the same library (python -m poreseq_b200.build -D... --out=...), never a fallback
+_LIB_PATH = os.environ.get("PORESEQ_B200_LIB") or os.path.join(_HERE, "libporeseq_b200.so")
 _c_double_p = C.POINTER(C.c_double)
 _c_int_p = C.POINTER(C.c_int)
 
@@ -74,6 +75,8 @@ def lib():
     L.ps_region_get_sequence.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     L.ps_region_get_event_align.argtypes = [C.c_void_p, C.c_int, _c_double_p, _c_double_p]
     L.ps_score_alignments.argtypes = [C.c_void_p, _c_double_p, _c_double_p]
+    L.ps_score_events.argtypes = [C.c_void_p, _c_double_p]
+    L.ps_score_events_batch.argtypes = [C.POINTER(C.c_void_p), C.c_int, _c_double_p]
     L.ps_score_mutations.argtypes = [C.c_void_p, C.c_int, _c_int_p, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), _c_double_p]
     L.ps_score_mutations_partial.argtypes = L.ps_score_mutations.argtypes
     L.ps_find_point_mutations.argtypes = [C.c_void_p, C.c_int, _c_int_p, _c_int_p, C.c_char_p, C.c_char_p]
@@ -347,6 +350,13 @@ class NativeRegion(object):
         self.ctx.check(self.ctx.lib.ps_score_alignments(self.handle, _dp(scores), _dp(likes) if want_likes else None))
         return scores, likes
 
+    def score_events(self):
+        """PSAlign.ScoreEvents: one score per event, alignments untouched (ps_score_events)."""
+        n = self.ctx.lib.ps_region_num_events(self.handle)
+        out = np.zeros(max(n, 1))
+        self.ctx.check(self.ctx.lib.ps_score_events(self.handle, _dp(out)))
+        return out[:n]
+
     def score_mutations(self, starts, origs, muts):
         n = len(starts)
         st = np.ascontiguousarray(starts, dtype=np.int32)
@@ -365,7 +375,7 @@ class NativeRegion(object):
         return out
 
     def score_points(self):
-        cap = 8 * max(self.ctx.lib.ps_region_sequence_length(self.handle), 1)
+        cap = 9 * max(self.ctx.lib.ps_region_sequence_length(self.handle), 1)   # 8 per state, 9 where the base is not ACGT
         n = C.c_int(0)
         st = np.zeros(cap, dtype=np.int32)
         og = C.create_string_buffer(cap)
@@ -472,7 +482,7 @@ def score_points_batch(ctx, regions):
     Returns a list of (start, orig bytes, mut bytes, score) tuples of arrays, one per region."""
     n = len(regions)
     handles = (C.c_void_p * n)(*[r.handle for r in regions])
-    cap = sum(8 * max(ctx.lib.ps_region_sequence_length(r.handle), 1) for r in regions)
+    cap = sum(9 * max(ctx.lib.ps_region_sequence_length(r.handle), 1) for r in regions)
     n_out = (C.c_int * n)()
     off = (C.c_longlong * n)()
     st = np.zeros(cap, dtype=np.int32)
@@ -488,6 +498,20 @@ def score_points_batch(ctx, regions):
     return out
 
 
+def score_events_batch(ctx, regions):
+    """ps_score_events_batch over NativeRegion objects: [scores per event] per region, one launch sequence."""
+    n = len(regions)
+    handles = (C.c_void_p * n)(*[r.handle for r in regions])
+    counts = [ctx.lib.ps_region_num_events(r.handle) for r in regions]
+    out = np.zeros(max(sum(counts), 1))
+    ctx.check(ctx.lib.ps_score_events_batch(handles, n, _dp(out)))
+    res, at = [], 0
+    for c in counts:
+        res.append(out[at:at + c])
+        at += c
+    return res
+
+
 class PendingBatch(object):
     """A ps_score_points_batch in flight (ps_score_points_batch_begin / _end)."""
 
@@ -495,7 +519,7 @@ class PendingBatch(object):
         self.ctx, self.regions = ctx, regions
         n = len(regions)
         handles = (C.c_void_p * n)(*[r.handle for r in regions])
-        cap = sum(8 * max(ctx.lib.ps_region_sequence_length(r.handle), 1) for r in regions)
+        cap = sum(9 * max(ctx.lib.ps_region_sequence_length(r.handle), 1) for r in regions)
         self.n_out = (C.c_int * n)()
         self.off = (C.c_longlong * n)()
         self.st = np.zeros(cap, dtype=np.int32)
@@ -626,7 +650,7 @@ class PSAlign(object):
         not propagated back to the Python events."""
         reg = self._native()
         try:
-            scores, _ = reg.score_alignments()
+            scores = reg.score_events()
         finally:
             reg.close()
         return scores.tolist()

@@ -9,6 +9,9 @@ from util import CASES, edge_mutations, region, same_aligns
 
 pytestmark = pytest.mark.gpu
 
+# BASELINE.json north_star: per-mutation log-likelihoods within 1e-4 RELATIVE (pure: no absolute term)
+REL_TOL = 1e-4
+
 
 def native(ctx, reg, width_key=None):
     return poreseqcpp.NativeRegion(ctx, reg.sequence, reg.events, reg.params, width_key)
@@ -228,26 +231,39 @@ def test_variant_modes(ctx, orc):
     assert [g.start for g in got] == [s + 1000 for s in st]
 
 
-def test_event_sharded_partials(ctx, orc):
-    """Two event shards scored separately on the GPU (partial sums from 0) add up to the full score."""
+@pytest.mark.parametrize("precision", ["exact", "fast"])
+def test_event_sharded_partials(orc, precision):
+    """Two event shards scored separately on the GPU (partial sums from 0) add up to the full score.  A shard's partial
+    says nothing about the sign of the total, so partial sums are exact FP64 in both precision modes (FAST flags by
+    totals): the two modes must give the same bits."""
     from poreseq_b200 import sharding
     reg = region("draft_partial")
     st, og, mu = edge_mutations(reg.sequence, 4, count=120)
     want, _ = orc.score_mutations(reg, st, og, mu)
-    fn = sharding.cuda_partial(ctx)
-    total = np.zeros(len(st))
-    for rank in range(2):
-        total += fn(sharding.RegionShard(reg, rank, 2), st, og, mu)
-    got = -1e-6 + total
-    assert np.allclose(got, want, rtol=1e-12, atol=1e-12)
-    assert np.array_equal(got >= 0, want >= 0)
+    c2 = poreseqcpp.Context(0)
+    try:
+        c2.set_precision(precision)
+        fn = sharding.cuda_partial(c2)
+        parts = [fn(sharding.RegionShard(reg, rank, 2), st, og, mu) for rank in range(2)]
+        got = -1e-6 + (parts[0] + parts[1])
+        assert np.allclose(got, want, rtol=1e-12, atol=1e-12)
+        assert np.array_equal(got >= 0, want >= 0)
+        # each shard alone is the exact ordered FP64 sum over its events
+        for rank in range(2):
+            shard = sharding.RegionShard(reg, rank, 2)
+            if shard.events:
+                w, _ = orc.score_mutations(shard, st, og, mu)
+                assert np.array_equal(parts[rank], w + 1e-6) or np.allclose(parts[rank], w + 1e-6, rtol=0, atol=1e-12)
+    finally:
+        c2.close()
 
 
 @pytest.mark.parametrize("name", [c[0] for c in CASES])
 def test_fast_mode_decisions_exact(orc, name):
     """PS_PRECISION_FAST: FP32 scan + exact re-score.  Every score above -tau (in particular every
-    accepted mutation) is bit-identical; the rest is within 1e-4 relative (BASELINE.json tolerance,
-    plus 1e-3 absolute for scores near zero magnitude); Refine gives the identical sequence."""
+    accepted mutation) is bit-identical; the rest is within 1e-4 RELATIVE (BASELINE.json north_star; no
+    absolute slack: tau = 0.5 x events is derived from the measured FP32 error, profiles/r2_fast_error.txt);
+    Refine gives the identical sequence."""
     c2 = poreseqcpp.Context(0)
     c2.set_precision("fast")
     try:
@@ -256,17 +272,17 @@ def test_fast_mode_decisions_exact(orc, name):
         w = np.array([x[3] for x in want])
         nr = poreseqcpp.NativeRegion(c2, reg.sequence, reg.events, reg.params, "point_width")
         st, og, mu, sc = nr.score_points()
-        keep = w > -0.02
+        keep = w > -0.4 * len(reg.events)                     # inside the library's -tau = -0.5 x events
         assert np.array_equal(sc[keep], w[keep])
         assert np.array_equal(sc >= 0, w >= 0)
-        assert np.all(np.abs(sc - w) <= 1e-4 * np.abs(w) + 1e-3), float(np.max(np.abs(sc - w)))
+        assert np.all(np.abs(sc - w) <= REL_TOL * np.abs(w)), float(np.max(np.abs(sc - w) / np.abs(w)))
         assert same_aligns([nr.event_align(e) for e in range(len(reg.events))], want_a)
         st2, og2, mu2 = edge_mutations(reg.sequence, 11)
         w2, _ = orc.score_mutations(reg, st2, og2, mu2)
         nr = poreseqcpp.NativeRegion(c2, reg.sequence, reg.events, reg.params)
         s2 = nr.score_mutations(st2, og2, mu2)
         assert np.array_equal(s2 >= 0, w2 >= 0)
-        assert np.all(np.abs(s2 - w2) <= 1e-4 * np.abs(w2) + 1e-3), float(np.max(np.abs(s2 - w2)))
+        assert np.all(np.abs(s2 - w2) <= REL_TOL * np.abs(w2)), float(np.max(np.abs(s2 - w2) / np.abs(w2)))
         nr = poreseqcpp.NativeRegion(c2, reg.sequence, reg.events, reg.params, "point_width")
         nb = nr.refine()
         seq, want_nb, want_a = orc.refine(reg)
@@ -376,8 +392,8 @@ def test_config3_size_properties(drv):
         st2, og2, mu2, sf = native(cf, reg, "point_width").score_points()
         assert len(sc) == 8 * (len(reg.sequence) - 4)
         assert np.array_equal(sc >= 0, sf >= 0)
-        assert np.array_equal(sc[sc > -0.02], sf[sc > -0.02])
-        assert np.all(np.abs(sf - sc) <= 1e-4 * np.abs(sc) + 1e-3), float(np.max(np.abs(sf - sc)))
+        assert np.array_equal(sc[sc > -0.4 * len(reg.events)], sf[sc > -0.4 * len(reg.events)])
+        assert np.all(np.abs(sf - sc) <= REL_TOL * np.abs(sc)), float(np.max(np.abs(sf - sc) / np.abs(sc)))
         rng = np.random.default_rng(5)
         pick = np.sort(rng.choice(len(sc), 300, replace=False))
         reg.params = dict(reg.params, scoring_width=reg.params["point_width"])
@@ -556,8 +572,8 @@ def test_native_pack_regions_score_like_in_memory_ones(ctx, orc, tmp_path):
 def test_baseline_config_3_shape_reduced(orc, precision):
     """BASELINE.json configs[3] (`poreseq variant -m`: known multi-base mutations at scoring_width 100 against deep
     coverage) at the size of the CPU test of the same name: 2 kb, 40 events, 600 random edits of up to 6 bases plus the
-    boundary edits.  Exact mode: every score bit-identical; fast mode: scores >= 0 bit-identical, the rest within 1e-4 relative
-    (+ 1e-3 absolute near zero, as in test_fast_mode_decisions_exact)."""
+    boundary edits.  Exact mode: every score bit-identical; fast mode: scores >= 0 bit-identical, the rest within 1e-4
+    relative, no absolute slack (as in test_fast_mode_decisions_exact)."""
     reg = synth.make_region(2000, 20, seed=4, draft_error=0.01, partial=0.3, params=dict(scoring_width=100))
     rng = np.random.default_rng(44)
     st, og, mu = synth.random_mutations(reg.sequence, 600, rng, max_len=6)
@@ -574,7 +590,7 @@ def test_baseline_config_3_shape_reduced(orc, precision):
             assert len(bad) == 0, [(int(i), st[i], og[i], mu[i], got[i], want[i]) for i in bad[:8]]
         else:
             assert np.array_equal(got[want >= 0], want[want >= 0]) and np.array_equal(got >= 0, want >= 0)
-            assert np.all(np.abs(got - want) <= 1e-4 * np.abs(want) + 1e-3), float(np.max(np.abs(got - want)))
+            assert np.all(np.abs(got - want) <= REL_TOL * np.abs(want)), float(np.max(np.abs(got - want) / np.abs(want)))
         assert same_aligns(native_aligns(nr, reg), want_a)
     finally:
         c2.close()
