@@ -282,10 +282,10 @@ int ps_ctx::init()
     CU(cudaFuncSetAttribute(k_mutscore_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU(cudaFuncSetAttribute(k_mutscore<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU(cudaFuncSetAttribute(k_mutscore<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    CU(cudaFuncSetAttribute(k_score_f32<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CU(cudaFuncSetAttribute(k_score_f32<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CU(cudaFuncSetAttribute(k_score_f32<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CU(cudaFuncSetAttribute(k_score_f32<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CU(cudaFuncSetAttribute(k_score_f32<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(k_score_f32<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(k_score_f32<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(k_score_f32<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     // the per-thread rings of the exact mutation kernel are what limits its occupancy: ask for the largest shared-memory carve-out
     CU(cudaFuncSetAttribute(k_mutscore<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_mutscore<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -997,20 +997,23 @@ int Job::run(bool full)
         TRY(room(ctx, "evbest", ev.size(), &d_evbest));
         Score32Args a;
         a.out = d_evbest;
-        a.strip = 64;
-        while (a.strip < 2 * b.realign_width + 64) a.strip <<= 1;
-        const size_t strips = (size_t)PS_SCORE32_WARPS * a.strip * sizeof(float);
-        const size_t staged = strips + (size_t)(s32_max_n0 + 1) * sizeof(LevelRecF);
-        const int threads = 32 * PS_SCORE32_WARPS;
+        a.strip = (2 * b.realign_width + 1 + 8 + 3) & ~3;            // a band's rows + the row requested one step ahead, 16-byte multiple
+        // warps per CTA = blocks (of 64 columns) of one event in flight: few events -> more warps per event (the sweep of
+        // one event is a pipeline of blocks ~90 steps apart), many events -> 4 warps and more CTAs per SM
+        const int warps = nev >= 4 * ctx->sm_count ? 4 : nev >= 2 * ctx->sm_count ? 8 : 16;
+        const int warps_long = nev >= 4 * ctx->sm_count ? 4 : nev >= 2 * ctx->sm_count ? 8 : nev >= ctx->sm_count ? 16 : PS_SCORE32_MAX_WARPS;
+        const size_t staged = (size_t)(warps + 1) * a.strip * sizeof(float) + (size_t)(s32_max_n0 + 1) * sizeof(LevelRecF);
+        const size_t strips = (size_t)(warps_long + 1) * a.strip * sizeof(float);
+        const int threads = 32 * warps, threads_long = 32 * warps_long;
         int off = 0;
         a.list = d_s32_list + off;
         if (s32_count[0]) { k_score_f32<true, false><<<s32_count[0], threads, staged, ctx->stream>>>(b, a); LAUNCHED(); }
         off += s32_count[0]; a.list = d_s32_list + off;
         if (s32_count[1]) { k_score_f32<true, true><<<s32_count[1], threads, staged, ctx->stream>>>(b, a); LAUNCHED(); }
         off += s32_count[1]; a.list = d_s32_list + off;
-        if (s32_count[2]) { k_score_f32<false, false><<<s32_count[2], threads, strips, ctx->stream>>>(b, a); LAUNCHED(); }
+        if (s32_count[2]) { k_score_f32<false, false><<<s32_count[2], threads_long, strips, ctx->stream>>>(b, a); LAUNCHED(); }
         off += s32_count[2]; a.list = d_s32_list + off;
-        if (s32_count[3]) { k_score_f32<false, true><<<s32_count[3], threads, strips, ctx->stream>>>(b, a); LAUNCHED(); }
+        if (s32_count[3]) { k_score_f32<false, true><<<s32_count[3], threads_long, strips, ctx->stream>>>(b, a); LAUNCHED(); }
         MARK(PS_T_BACKWARD); MARK(PS_T_BACKTRACE); MARK(PS_T_JOIN); MARK(PS_T_MUTSCORE); MARK(PS_T_REDUCE); MARK(PS_T_D2H);
         return PS_OK;
     }

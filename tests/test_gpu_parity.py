@@ -617,3 +617,67 @@ def test_cython_stub_is_a_drop_in(orc, tmp_path):
     want_seq, want_nb, want_a = orc.refine(reg)
     assert (pa.Refine(), pa.sequence) == (want_nb, want_seq)
     assert same_aligns([(e.ref_align, e.ref_like) for e in pa.events], want_a)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# PSAlign.ScoreEvents (BASELINE.json configs[0]): scores only, the events keep their alignments
+
+SCORE_EVENT_CASES = [c[0] for c in CASES] + ["1kb", "n_bases", "unaligned", "10kb"]
+
+
+def score_events_region(name):
+    if name == "1kb":
+        return synth.make_region(1000, 10, seed=31, draft_error=0.02)             # configs[0]
+    if name == "10kb":
+        return synth.make_region(10000, 2, seed=32, draft_error=0.02, partial=0.5)
+    if name == "n_bases":
+        reg = synth.make_region(500, 3, seed=33, draft_error=0.02)
+        s = list(reg.sequence)
+        for q in (0, 17, 18, 250, 251, 252, 253, 254, 400, len(s) - 1):
+            s[q] = "N"
+        reg.sequence = "".join(s)
+        return reg
+    if name == "unaligned":
+        reg = synth.make_region(400, 3, seed=34, params=dict(realign_width=60))
+        reg.events[1].ref_align[:] = 0.0                                           # no alignment at all: unusable event
+        reg.events[2].ref_align[5:] = 0.0                                          # a stub of an alignment
+        return reg
+    return region(name)
+
+
+@pytest.mark.parametrize("name", SCORE_EVENT_CASES)
+def test_score_events_exact(ctx, drv, name):
+    """ps_score_events in EXACT mode = ScoreAlignments(data, NULL) bit for bit, and the handle's events are untouched."""
+    reg = score_events_region(name)
+    want, _, _ = drv.score_alignments(reg)
+    nr = native(ctx, reg)
+    before = native_aligns(nr, reg)
+    got = nr.score_events()
+    assert np.array_equal(got, want)
+    assert same_aligns(native_aligns(nr, reg), before)
+    nr.close()
+
+
+@pytest.mark.parametrize("name", SCORE_EVENT_CASES)
+def test_score_events_fast(drv, name):
+    """FAST mode: the score-only FP32 fill (k_score_f32).  Scores within 1e-4 relative of the reference's (north_star);
+    exactly 0 where the reference gives 0 (unusable events); the handle's events untouched; batch = one by one."""
+    reg = score_events_region(name)
+    want, _, _ = drv.score_alignments(reg)
+    c2 = poreseqcpp.Context(0)
+    try:
+        c2.set_precision("fast")
+        nr = native(c2, reg)
+        before = native_aligns(nr, reg)
+        got = nr.score_events()
+        assert got.shape == want.shape
+        assert np.all(np.abs(got - want) <= REL_TOL * np.abs(want)), (got, want)
+        assert same_aligns(native_aligns(nr, reg), before)
+        oreg = synth.make_region(300, 3, seed=35, draft_error=0.03, params=reg.params)   # (a batch shares the band widths)
+        other = native(c2, oreg)
+        both = poreseqcpp.score_events_batch(c2, [nr, other, nr])
+        assert np.array_equal(both[0], got) and np.array_equal(both[2], got)
+        assert np.array_equal(both[1], other.score_events())
+        nr.close(); other.close()
+    finally:
+        c2.close()
