@@ -140,7 +140,8 @@ int         ps_score_alignments(ps_region* r, double* scores, double* likes);
 /* PSAlign.ScoreEvents   poreseq/_poreseqcpp.pyx:263-276 (= ScoreAlignments(data, NULL) whose realignment is dropped,
  * pyx:273-276): scores[n_events], the region's events keep their alignments.  PS_PRECISION_FAST: score-only log-space
  * FP32 fill (k_score_f32, nothing stored), scores within 1e-4 relative; PS_PRECISION_EXACT: the FP64 fill, bit-identical.
- * _batch: the events of n regions of ONE context in one launch sequence, scores concatenated in region order. */
+ * _batch: the events of n DISTINCT regions of ONE context in one launch sequence, scores concatenated in region order
+ * (like every batched entry point: PS_E_ARG when a handle appears twice). */
 int         ps_score_events(ps_region* r, double* scores);
 int         ps_score_events_batch(ps_region* const* regions, int n_regions, double* scores);
 /* vector<MutScore> ScoreMutations(AlignData&, const vector<MutInfo>&)   cpp/Mutations.h:23,

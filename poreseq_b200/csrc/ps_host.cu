@@ -282,10 +282,12 @@ int ps_ctx::init()
     CU(cudaFuncSetAttribute(k_mutscore_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU(cudaFuncSetAttribute(k_mutscore<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU(cudaFuncSetAttribute(k_mutscore<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    CU(cudaFuncSetAttribute(k_score_f32<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CU(cudaFuncSetAttribute(k_score_f32<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CU(cudaFuncSetAttribute(k_score_f32<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CU(cudaFuncSetAttribute(k_score_f32<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(k_score_f32<true, false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(k_score_f32<true, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(k_score_f32<false, false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(k_score_f32<false, false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(k_score_f32<false, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(k_score_f32<false, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     // the per-thread rings of the exact mutation kernel are what limits its occupancy: ask for the largest shared-memory carve-out
     CU(cudaFuncSetAttribute(k_mutscore<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_mutscore<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -994,26 +996,63 @@ int Job::run(bool full)
         for (const EvDesc& d : ev) maxn0 = std::max(maxn0, d.n0);
         k_rows<<<dim3((maxn0 + 127) / 128, nev), 128, 0, ctx->stream>>>(b);
         LAUNCHED();
-        TRY(room(ctx, "evbest", ev.size(), &d_evbest));
         Score32Args a;
-        a.out = d_evbest;
+        float* d_out32;
+        TRY(room(ctx, "evbest32", ev.size(), &d_out32));
+        CU(cudaMemsetAsync(d_out32, 0, ev.size() * sizeof(float), ctx->stream));
+        a.out32 = d_out32;
         a.strip = (2 * b.realign_width + 1 + 8 + 3) & ~3;            // a band's rows + the row requested one step ahead, 16-byte multiple
-        // warps per CTA = blocks (of 64 columns) of one event in flight: few events -> more warps per event (the sweep of
-        // one event is a pipeline of blocks ~90 steps apart), many events -> 4 warps and more CTAs per SM
-        const int warps = nev >= 4 * ctx->sm_count ? 4 : nev >= 2 * ctx->sm_count ? 8 : 16;
-        const int warps_long = nev >= 4 * ctx->sm_count ? 4 : nev >= 2 * ctx->sm_count ? 8 : nev >= ctx->sm_count ? 16 : PS_SCORE32_MAX_WARPS;
-        const size_t staged = (size_t)(warps + 1) * a.strip * sizeof(float) + (size_t)(s32_max_n0 + 1) * sizeof(LevelRecF);
+        // Staged form (level records of one event brought into shared memory by one TMA bulk copy; one event per CTA): few
+        // events, many warps per event -- the sweep of one event is a pipeline of blocks ~90 steps apart.  Persistent form
+        // (level records through L1; a CTA walks through its events without a barrier): many events, 4 warps per CTA.
+        // Measured equal per cell (profiles/r2_score32_stage_ab.txt); the persistent form saves the pipeline's fill and
+        // drain per event, the staged form is kept for the small batches where an event has a CTA to itself anyway.
+        const bool persist = nev >= 4 * ctx->sm_count || ctx->no_stage;
+        int warps = persist ? 4 : nev >= 2 * ctx->sm_count ? 8 : 16;
+        int warps_long = nev >= 4 * ctx->sm_count ? 4 : nev >= 2 * ctx->sm_count ? 8 : 16;
+        if (ctx->s32_warps) { warps = ctx->s32_warps; warps_long = ctx->s32_warps; }
+        const size_t strips_s = (size_t)(warps + 1) * a.strip * sizeof(float);
+        const size_t staged = strips_s + (size_t)(s32_max_n0 + 1) * sizeof(LevelRecF);
         const size_t strips = (size_t)(warps_long + 1) * a.strip * sizeof(float);
         const int threads = 32 * warps, threads_long = 32 * warps_long;
+        auto grid_for = [&](int count, int thr, size_t smem) {
+            // persistent: as many CTAs as fit at once (registers: 64 per thread; shared memory), never more than events
+            const int by_regs = 65536 / (80 * thr), by_smem = (int)((220 * 1024) / (smem + 1024));
+            return std::max(1, std::min(count, ctx->sm_count * std::max(1, std::min(by_regs, by_smem))));
+        };
         int off = 0;
-        a.list = d_s32_list + off;
-        if (s32_count[0]) { k_score_f32<true, false><<<s32_count[0], threads, staged, ctx->stream>>>(b, a); LAUNCHED(); }
-        off += s32_count[0]; a.list = d_s32_list + off;
-        if (s32_count[1]) { k_score_f32<true, true><<<s32_count[1], threads, staged, ctx->stream>>>(b, a); LAUNCHED(); }
-        off += s32_count[1]; a.list = d_s32_list + off;
-        if (s32_count[2]) { k_score_f32<false, false><<<s32_count[2], threads_long, strips, ctx->stream>>>(b, a); LAUNCHED(); }
-        off += s32_count[2]; a.list = d_s32_list + off;
-        if (s32_count[3]) { k_score_f32<false, true><<<s32_count[3], threads_long, strips, ctx->stream>>>(b, a); LAUNCHED(); }
+        for (int c = 0; c < 4; c++)
+        {
+            a.list = d_s32_list + off; a.count = s32_count[c];
+            off += s32_count[c];
+            if (!a.count) continue;
+            const bool inv = c & 1, short_ev = c < 2;
+            if (short_ev && !persist)
+            {
+                if (inv) k_score_f32<true, true, 512><<<a.count, threads, staged, ctx->stream>>>(b, a);
+                else k_score_f32<true, false, 512><<<a.count, threads, staged, ctx->stream>>>(b, a);
+            }
+            else
+            {
+                const int thr = short_ev ? threads : threads_long;
+                const size_t sm = short_ev ? strips_s : strips;
+                const int g = grid_for(a.count, thr, sm);
+                if (thr <= 256)
+                {
+                    if (inv) k_score_f32<false, true, 256><<<g, thr, sm, ctx->stream>>>(b, a);
+                    else k_score_f32<false, false, 256><<<g, thr, sm, ctx->stream>>>(b, a);
+                }
+                else
+                {
+                    if (inv) k_score_f32<false, true, 512><<<g, thr, sm, ctx->stream>>>(b, a);
+                    else k_score_f32<false, false, 512><<<g, thr, sm, ctx->stream>>>(b, a);
+                }
+            }
+            LAUNCHED();
+        }
+        TRY(room(ctx, "evbest", ev.size(), &d_evbest));
+        k_score_f32_out<<<(nev + 127) / 128, 128, 0, ctx->stream>>>(d_out32, d_evbest, nev);
+        LAUNCHED();
         MARK(PS_T_BACKWARD); MARK(PS_T_BACKTRACE); MARK(PS_T_JOIN); MARK(PS_T_MUTSCORE); MARK(PS_T_REDUCE); MARK(PS_T_D2H);
         return PS_OK;
     }
@@ -1258,6 +1297,16 @@ static int job_begin(ps_ctx* ctx, const std::vector<ps_region*>& regs, const std
     if (ctx->pending) { ps_set_error(ctx, "a batch is already in flight on this context"); return PS_E_ARG; }
     for (ps_region* R : regs)
         if (R->bases.size() < 5) { ps_set_error(ctx, "sequences shorter than 5 bases are not supported"); return PS_E_ARG; }
+    {
+        // the events of a batch are staged (and realigned) in parallel: a region can be in a batch only once
+        std::vector<ps_region*> seen(regs);
+        std::sort(seen.begin(), seen.end());
+        if (std::adjacent_find(seen.begin(), seen.end()) != seen.end())
+        {
+            ps_set_error(ctx, "the same region handle appears twice in one batch");
+            return PS_E_ARG;
+        }
+    }
     Job* job = new Job(ctx);
     job->regs = regs;
     job->want_muts = muts != nullptr;
@@ -1558,6 +1607,7 @@ ps_ctx* ps_create(int device)
     ctx->no_warp = getenv("PORESEQ_B200_NO_WARP") != nullptr;
     ctx->sw_host = getenv("PORESEQ_B200_SW_HOST") != nullptr;
     ctx->no_stage = getenv("PORESEQ_B200_NO_STAGE") != nullptr;
+    if (const char* e = getenv("PORESEQ_B200_S32_WARPS")) ctx->s32_warps = std::max(2, std::min(atoi(e), PS_SCORE32_MAX_WARPS));
     if (const char* e = getenv("PORESEQ_B200_BAND_BUDGET")) ctx->band_budget = atof(e);
     if (const char* e = getenv("PORESEQ_B200_TAU")) ctx->tau_override = atof(e);
     return ctx;                       // CUDA is initialised lazily (fork-safe)

@@ -58,6 +58,7 @@ struct ps_ctx
     bool sw_host = false;                     // PORESEQ_B200_SW_HOST: FindMutations' Smith-Waterman maps on the host
     double band_budget = 0;                   // PORESEQ_B200_BAND_BUDGET: bytes of band storage per sub-batch (0: default)
     bool no_stage = false;                    // PORESEQ_B200_NO_STAGE: k_score_f32 reads level records through L1 instead of a TMA-staged copy (A/B)
+    int s32_warps = 0;                        // PORESEQ_B200_S32_WARPS: warps per CTA of k_score_f32 (0: chosen by batch size)
     double tau_override = -1;                 // PORESEQ_B200_TAU: FAST-mode re-score threshold (diagnostics; < 0: derived)
     std::string error;
     std::map<std::string, DevBuf> bufs;       // grow-only named device buffers, reused across calls

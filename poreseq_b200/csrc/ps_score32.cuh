@@ -35,8 +35,8 @@
 
 namespace psdev {
 
-constexpr int   PS_SCORE32_MAX_WARPS = 32;            // warps per CTA = blocks of one event in flight (4 for big batches;
-                                                      // the staged form keeps to 16: it needs more than 64 registers)
+constexpr int   PS_SCORE32_MAX_WARPS = 16;            // warps per CTA = blocks of one event in flight (4 for big batches);
+                                                      // 32 warps were slower on long events (64 registers, spills): 190 vs 215 GCUPS
 constexpr int   PS_SCORE32_STAGE_LEVELS = 2048;       // events up to this many levels are staged whole (32 KB)
 constexpr float S32_BIG = 1.0e30f;                    // "never wins" (cpp/AlignUtil.h:20 uses 1e300)
 
@@ -71,8 +71,9 @@ __device__ __forceinline__ void sts_volatile(unsigned addr, float v)
 
 struct Score32Args
 {
-    const int* list;              // event indices, grid.x indexes it
-    double*    out;               // per event: best main-matrix cell, floor 0
+    const int* list;              // event indices of this launch
+    int        count;
+    float*     out32;             // per event (indexed by event): best main-matrix cell, floor 0; zeroed before the launch
     int        strip;             // slots per hand-over strip: 2 * realign_width + 1 rows of a band, padded
 };
 
@@ -94,24 +95,36 @@ __device__ __forceinline__ float emis32(const float4 l, const StateParamsF& p)
     return __fmaf_rn(p.a_s, d1 * d1, p.c_s) + __fmaf_rn(p.f_s * l.z, d2 * d2, l.w);
 }
 
-template <bool STAGE, bool INV>
-__global__ void __launch_bounds__(STAGE ? 512 : 1024) k_score_f32(Batch b, Score32Args a)
+template <bool STAGE, bool INV, int MAXT>
+__global__ void __launch_bounds__(MAXT) k_score_f32(Batch b, Score32Args a)
 {
     extern __shared__ __align__(16) unsigned char s32_smem[];
     const int W = blockDim.x >> 5;
-    const int e = a.list[blockIdx.x];
-    const EvDesc ev = b.ev[e];
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-    const int N = ev.N, n0 = ev.n0;
-    __shared__ float warp_best[PS_SCORE32_MAX_WARPS];
     __shared__ int rdone[PS_SCORE32_MAX_WARPS];            // strip q: last block whose hand-over through it was read to the end
     __shared__ unsigned long long stage_bar;
-    if (!ev.usable || N <= 0)
-    {
-        if (threadIdx.x == 0) a.out[e] = 0.0;
-        return;
-    }
     float* strips = reinterpret_cast<float*>(s32_smem);                   // [W + 1][strip]; strip W = the blank column 0
+    for (int q = threadIdx.x; q < (W + 1) * a.strip; q += blockDim.x) strips[q] = q < W * a.strip ? -1.f : 0.f;
+    if (threadIdx.x < W) rdone[threadIdx.x] = -1;
+    if (STAGE && threadIdx.x == 0)
+    {
+        mbar_init(smem_u32(&stage_bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    const int rw = b.realign_width;
+    // A CTA takes the events list[blockIdx.x], list[blockIdx.x + gridDim.x], ... one after the other WITHOUT a barrier
+    // between them: its warps share out the blocks of the whole sequence round robin (block G of the sequence goes to
+    // warp G mod W), so a warp that has finished its last block of one event starts on the next event while the others
+    // are still busy -- the pipeline of blocks is filled once per CTA, not once per event.  (STAGE: one event per CTA,
+    // the grid is the list.)
+    int gbase = 0;                                                       // blocks of the events this CTA has been through
+    for (int q = blockIdx.x; q < a.count; q += gridDim.x)
+    {
+    const int e = a.list[q];
+    const EvDesc ev = b.ev[e];
+    const int N = ev.N, n0 = ev.n0;
+    if (!ev.usable || N <= 0) continue;                                  // its score stays 0
     const LevelRecF* glev = b.levf + ev.lev_off;
     const float4* lev = reinterpret_cast<const float4*>(glev);           // row i at lev[i - 1]
     if (STAGE)
@@ -120,32 +133,26 @@ __global__ void __launch_bounds__(STAGE ? 512 : 1024) k_score_f32(Batch b, Score
         const unsigned bar = smem_u32(&stage_bar);
         if (threadIdx.x == 0)
         {
-            mbar_init(bar, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-        }
-        __syncthreads();
-        if (threadIdx.x == 0)
-        {
             const unsigned bytes = (unsigned)n0 * (unsigned)sizeof(LevelRecF);
             mbar_expect_tx(bar, bytes);
             bulk_load(slev, glev, bytes, bar);
         }
         lev = slev;
+        mbar_wait(bar, 0);
     }
-    for (int q = threadIdx.x; q < (W + 1) * a.strip; q += blockDim.x) strips[q] = q < W * a.strip ? -1.f : 0.f;
-    if (threadIdx.x < W) rdone[threadIdx.x] = -1;
-    __syncthreads();
-    if (STAGE) mbar_wait(smem_u32(&stage_bar), 0);
     const StateParamsF* stf = b.stf + (size_t)ev.model * N_STATES;
     const float4 tr = b.trf[ev.model];
     const int* cen = b.cen_old + ev.cen_off;
     const int* states = b.states + ev.state_off;
-    const int rw = b.realign_width;
     const int nblocks = (N + 63) >> 6;
     float best = 0.f;
+    bool any = false;
 
-    for (int blk = wrp; blk < nblocks; blk += W)
+    for (int blk = ((wrp - gbase) % W + W) % W; blk < nblocks; blk += W)
     {
+        const int G = gbase + blk;                                       // the block's number in the CTA's sequence
+        any = true;
+
         // this lane's two columns
         const int kA = (blk << 6) + 2 * lane + 1, kB = kA + 1;
         const bool mineA = kA <= N, mineB = kB <= N;
@@ -165,8 +172,8 @@ __global__ void __launch_bounds__(STAGE ? 512 : 1024) k_score_f32(Batch b, Score
         }
         const int l0p0 = __shfl_sync(0xffffffffu, p0, 0), l0p1 = __shfl_sync(0xffffffffu, p1, 0);
         // strips are indexed by (row - first band row of their column); the blank column 0 is one zero that never moves
-        const unsigned sin = smem_u32(strips + (size_t)(from_strip ? (blk + W - 1) % W : W) * a.strip);
-        const unsigned sout = smem_u32(strips + (size_t)(blk % W) * a.strip);
+        const unsigned sin = smem_u32(strips + (size_t)(from_strip ? (G + W - 1) % W : W) * a.strip);
+        const unsigned sout = smem_u32(strips + (size_t)(G % W) * a.strip);
         const unsigned sin_step = from_strip ? 4u : 0u;
         const int nslot = a.strip - 1;
         const bool hand = blk + 1 < nblocks;                             // (then the block is full: lane 31's second column is its last)
@@ -187,8 +194,8 @@ __global__ void __launch_bounds__(STAGE ? 512 : 1024) k_score_f32(Batch b, Score
         if (s_lo > s_hi) { s_lo = nsteps; s_hi = nsteps - 1; }           // (a partial last block has none: some lane owns no column)
         // the output strip was last used by block blk - W; wait for its reader (the warp of block blk - W + 1, which
         // finished about a block's worth of steps ago in any regular schedule) to say so
-        if (hand && blk >= W)
-            while (*(volatile int*)&rdone[blk % W] < blk - W) __nanosleep(64);
+        if (hand && G >= W)
+            while (*(volatile int*)&rdone[G % W] < G - W) __nanosleep(64);
         float upCA = 0.f, upSA = 0.f, upCB = 0.f, upSB = 0.f, recv = 0.f, recv_prev = 0.f, pub = 0.f;
         int i = R0 - lane;                                               // this lane's row of step 0
         int il0 = R0;                                                    // lane 0's row
@@ -304,19 +311,26 @@ __global__ void __launch_bounds__(STAGE ? 512 : 1024) k_score_f32(Batch b, Score
             for (int q = lane; q <= l0p1 - l0p0; q += 32) sts_volatile(sin + ((unsigned)q << 2), -1.f);
             __threadfence_block();
             __syncwarp();
-            if (lane == 0) *(volatile int*)&rdone[(blk + W - 1) % W] = blk - 1;
+            if (lane == 0) *(volatile int*)&rdone[(G + W - 1) % W] = G - 1;
         }
+        if (!hand && lane == 0) *(volatile int*)&rdone[G % W] = G;       // nobody reads the last block of an event
         __syncwarp();
     }
-    for (int o = 16; o; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
-    if (lane == 0) warp_best[wrp] = best;
-    __syncthreads();
-    if (threadIdx.x == 0)
+    if (any)
     {
-        float m = 0.f;
-        for (int q = 0; q < W; q++) m = fmaxf(m, warp_best[q]);
-        a.out[e] = (double)m;
+        for (int o = 16; o; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+        // scores are >= 0: their order as floats is their order as ints
+        if (lane == 0) atomicMax(reinterpret_cast<int*>(a.out32) + e, __float_as_int(best));
     }
+    gbase += nblocks;
+    }
+}
+
+// the per-event maxima as doubles (the C-ABI's type)
+__global__ void k_score_f32_out(const float* in, double* out, int n)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) out[e] = (double)in[e];
 }
 
 } // namespace psdev

@@ -675,9 +675,12 @@ def test_score_events_fast(drv, name):
         assert same_aligns(native_aligns(nr, reg), before)
         oreg = synth.make_region(300, 3, seed=35, draft_error=0.03, params=reg.params)   # (a batch shares the band widths)
         other = native(c2, oreg)
-        both = poreseqcpp.score_events_batch(c2, [nr, other, nr])
+        twin = native(c2, reg)
+        both = poreseqcpp.score_events_batch(c2, [nr, other, twin])
         assert np.array_equal(both[0], got) and np.array_equal(both[2], got)
         assert np.array_equal(both[1], other.score_events())
-        nr.close(); other.close()
+        with pytest.raises(RuntimeError):                              # a handle can be in a batch only once
+            poreseqcpp.score_events_batch(c2, [nr, other, nr])
+        nr.close(); other.close(); twin.close()
     finally:
         c2.close()
