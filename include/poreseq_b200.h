@@ -153,6 +153,27 @@ int         ps_score_mutations(ps_region* r, int n, const int* start, const char
  * (the reference's comment at cpp/MakeMutations.cpp:19-22 anticipates exactly that split). */
 int         ps_score_mutations_partial(ps_region* r, int n, const int* start, const char* const* orig,
                                        const char* const* mut, double* partial);
+
+/* ---- one region's events split across the GPUs of a box ---------------------------------------
+ * score[m] = -1e-6 + sum over events of delta(m, e)   (cpp/MakeMutations.cpp:19-22, 38-52; the caller is
+ * poreseq/Variant.py:71-76 on deep coverage).  Every rank (one process / context per GPU) holds a contiguous block of
+ * the region's events in a handle of its own, rank 0 the first block; ps_score_mutations_sharded scores all mutations
+ * against the local block and combines the sums over NCCL (NVLink / NVSwitch) on the context's stream, inside the
+ * library: no host round trip, no torch.  Every rank passes the same mutations and receives the complete scores.
+ *   ordered != 0  rank r continues the running sums of the ranks before it in event order: bit-identical to the
+ *                 single-GPU call and to the reference (n_ranks - 1 small messages in sequence, then a broadcast);
+ *   ordered == 0  one ncclAllReduce(sum, float64, n) of partial sums: scores agree to ~1e-16 relative.
+ * PS_PRECISION_FAST works as on one GPU (FP32 scan, mutations whose TOTAL is above the threshold re-scored exactly).
+ * ps_comm_unique_id: rank 0 makes the 128-byte NCCL id, the caller carries it to the other ranks by its own means
+ * (MPI, a file, torch.distributed ...); ps_comm_init is collective over the n_ranks contexts.  NCCL is loaded with
+ * dlopen("libnccl.so.2") at that point (PORESEQ_B200_NCCL overrides the path). */
+#define PS_COMM_ID_BYTES 128
+int         ps_comm_unique_id(void* id, int bytes);
+int         ps_comm_init(ps_ctx* ctx, const void* id, int bytes, int rank, int n_ranks, int ordered);
+int         ps_comm_destroy(ps_ctx* ctx);
+int         ps_comm_rank(ps_ctx* ctx, int* rank, int* n_ranks);
+int         ps_score_mutations_sharded(ps_region* r, int n, const int* start, const char* const* orig,
+                                       const char* const* mut, double* scores);
 /* vector<MutInfo> FindPointMutations(AlignData&)   cpp/Mutations.h:19, cpp/FindMutations.cpp:191-234.
  * Writes up to cap single-base edits (orig/mut as one char, 0 = empty); *n = 8 per state. */
 int         ps_find_point_mutations(ps_region* r, int cap, int* n, int* start, char* orig, char* mut);

@@ -112,6 +112,7 @@ struct Batch                  // everything the kernels need, passed by value
     int*              flag_list;                // global indices of the mutations to re-score exactly
     int*              flag_count;
     double            tau;                      // re-score when the FP32 total is above -tau * (events of the region)
+    int               tau_events;               // > 0: the region's events over ALL ranks of an event-sharded job
 };
 
 // ------------------------------------------------------------------------------------------
@@ -1488,7 +1489,8 @@ __global__ void k_points(Batch b)
 
 // k_reduce: score[m] = -1e-6 + sum_e delta(e, m), events in order (cpp/MakeMutations.cpp:38-52,
 // cpp/AlignUtil.h:84-90).  One thread per mutation; the region table gives its events.
-__global__ void k_reduce(Batch b, const RegTabDev* regs, int n_regs, long long n_muts, double start, int from_list)
+__global__ void k_reduce(Batch b, const RegTabDev* regs, int n_regs, long long n_muts, double start, int from_list,
+                         const double* start_arr, double* out)
 {
     long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (from_list)
@@ -1504,9 +1506,26 @@ __global__ void k_reduce(Batch b, const RegTabDev* regs, int n_regs, long long n
         if (regs[mid].mut_off <= g) lo = mid; else hi = mid - 1;
     }
     const int m = (int)(g - regs[lo].mut_off);
-    double s = start;                      // -1e-6 (cpp/AlignUtil.h:86), or 0 for a partial sum over an event shard
+    // -1e-6 (cpp/AlignUtil.h:86); 0 for a partial sum over an event shard; the running sum of the ranks before this one
+    // when the events of the region are split across GPUs in order (ps_comm.cu)
+    double s = start_arr ? start_arr[g] : start;
     for (int e = regs[lo].ev0; e < regs[lo].ev0 + regs[lo].nev; e++) s += b.delta[b.ev[e].task_off + m];
-    b.scores[g] = s;
+    out[g] = s;
+}
+
+// event-sharded FAST mode: the exactly re-scored totals of the flagged mutations replace the FP32 ones
+__global__ void k_merge_flagged(Batch b, const double* exact, double add)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= *b.flag_count) return;
+    const int g = b.flag_list[k];
+    b.scores[g] = exact[g] + add;
+}
+
+__global__ void k_add_scalar(double* v, long long n, double add)
+{
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n) v[g] += add;
 }
 
 // per-event alignment score = running best of the last forward column (cpp/Alignment.h:127-130)

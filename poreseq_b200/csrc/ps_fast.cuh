@@ -384,7 +384,8 @@ __global__ void k_flag(Batch b, long long n_muts, int max_mut)
         const int mid = (lo + hi + 1) >> 1;
         if (b.regs[mid].mut_off <= g) lo = mid; else hi = mid - 1;
     }
-    if (b.scores[g] > -b.tau * (double)b.regs[lo].nev || b.muts[g].n_mut > max_mut)
+    const int nev = b.tau_events > 0 ? b.tau_events : b.regs[lo].nev;
+    if (b.scores[g] > -b.tau * (double)nev || b.muts[g].n_mut > max_mut)
     {
         const int q = atomicAdd(b.flag_count, 1);
         b.flag_list[q] = (int)g;

@@ -345,6 +345,7 @@ ps_ctx::~ps_ctx()
 {
     if (!ready) return;
     cudaSetDevice(device);
+    ps_comm_destroy(this);
     for (auto& kv : bufs) if (kv.second.p) cudaFree(kv.second.p);
     for (auto& kv : pins) if (kv.second.p) { if (kv.second.cap & 1) free(kv.second.p); else cudaFreeHost(kv.second.p); }
     for (int i = 0; i <= PS_T_COUNT; i++) cudaEventDestroy(tev[i]);
@@ -472,6 +473,9 @@ struct Job
     PinVec<char> bases;
     PinVec<LevIn> lev;
     bool fast = false;                           // FP32 pass + exact re-score (PS_PRECISION_FAST)
+    bool sharded = false;                        // this job scores ONE rank's block of a region's events (ps_comm.cu): sums combined over NCCL
+    int total_events = 0;                        // events of the region over all ranks (sharded FAST: the re-score threshold counts them all)
+    double* d_scores2 = nullptr;                 // sharded FAST: totals of the exact pass (dense, only the flagged entries mean anything)
     bool score32 = false;                        // ScoreEvents in FAST mode: k_score_f32, no matrices, no backtrace, events untouched
     PinVec<int> s32_list;                        // events by launch class of k_score_f32: (staged, plain), (staged, inv), (global, plain), (global, inv)
     int s32_count[4] = {0, 0, 0, 0}, s32_max_n0 = 0;
@@ -956,6 +960,7 @@ int Job::upload()
         // is re-scored exactly -- so what keeps its FP32 value is within 1e-4 RELATIVE of the reference
         // (BASELINE.json north_star), with no absolute slack.
         b.tau = ctx->tau_override >= 0 ? ctx->tau_override : PS_FAST_PAIR_ERR * 1e4;
+        b.tau_events = sharded ? total_events : 0;
     }
     if (score32)
     {
@@ -1129,6 +1134,39 @@ int Job::run(bool full)
             k_join<<<grid, 256, 0, ctx->stream>>>(b);
             LAUNCHED();
         }
+        // the sum over events: score[m] = bias + sum_e delta(m, e) in event order.  Event-sharded jobs combine the ranks'
+        // sums on the stream: ordered (rank r continues the running sums of the ranks before it: bit-identical to one
+        // GPU) or by one all-reduce of partial sums.
+        const unsigned rblk = (unsigned)((n_muts + 127) / 128);
+        auto reduce_stage = [&](int from_list, double* out) -> int {
+            const RegTabDev* rt = (const RegTabDev*)d_regtab;
+            const int nr = (int)regs.size();
+            if (!sharded || ctx->comm_ranks <= 1)
+            {
+                k_reduce<<<rblk, 128, 0, ctx->stream>>>(b, rt, nr, n_muts, bias, from_list, nullptr, out);
+                LAUNCHED();
+                return PS_OK;
+            }
+            if (ctx->comm_ordered)
+            {
+                const bool first = ctx->comm_rank == 0, last = ctx->comm_rank == ctx->comm_ranks - 1;
+                if (!first) TRY(psi_comm_recv_prev(ctx, out, (size_t)n_muts));
+                k_reduce<<<rblk, 128, 0, ctx->stream>>>(b, rt, nr, n_muts, bias, from_list, first ? nullptr : out, out);
+                LAUNCHED();
+                if (!last) TRY(psi_comm_send_next(ctx, out, (size_t)n_muts));
+                TRY(psi_comm_bcast_last(ctx, out, (size_t)n_muts));
+            }
+            else
+            {
+                if (from_list) CU(cudaMemsetAsync(out, 0, (size_t)n_muts * sizeof(double), ctx->stream));
+                k_reduce<<<rblk, 128, 0, ctx->stream>>>(b, rt, nr, n_muts, 0.0, from_list, nullptr, out);
+                LAUNCHED();
+                TRY(psi_comm_allreduce_sum(ctx, out, (size_t)n_muts));
+                k_add_scalar<<<rblk, 128, 0, ctx->stream>>>(out, n_muts, bias);
+                LAUNCHED();
+            }
+            return PS_OK;
+        };
         MARK(PS_T_MUTSCORE);
         {
             // previous-column ring: shared memory when 2W+2 doubles per thread fit, else global scratch
@@ -1141,8 +1179,7 @@ int Job::run(bool full)
                 // pass 1: every pair in rebased FP32; pass 2: exact FP64 for the mutations that matter
                 k_mutscore_rows_f32<<<(unsigned)blocks, threads, 0, ctx->stream>>>(b);
                 LAUNCHED();
-                k_reduce<<<(unsigned)((n_muts + 127) / 128), 128, 0, ctx->stream>>>(b, (const RegTabDev*)d_regtab, (int)regs.size(), n_muts, bias, 0);
-                LAUNCHED();
+                TRY(reduce_stage(0, b.scores));
                 CU(cudaMemsetAsync(b.flag_count, 0, sizeof(int), ctx->stream));
                 k_flag<<<(unsigned)((n_muts + 127) / 128), 128, 0, ctx->stream>>>(b, n_muts, 1);
                 LAUNCHED();
@@ -1163,8 +1200,16 @@ int Job::run(bool full)
                 }
                 LAUNCHED();
                 MARK(PS_T_REDUCE);
-                k_reduce<<<(unsigned)((n_muts + 127) / 128), 128, 0, ctx->stream>>>(b, (const RegTabDev*)d_regtab, (int)regs.size(), n_muts, bias, 1);
-                LAUNCHED();
+                if (sharded && ctx->comm_ranks > 1)
+                {
+                    // every rank flagged the same mutations (the totals are the same everywhere); their exact sums travel
+                    // through a second dense array and replace the FP32 totals
+                    TRY(room(ctx, "scores2", (size_t)n_muts, &d_scores2));
+                    TRY(reduce_stage(1, d_scores2));
+                    k_merge_flagged<<<rblk, 128, 0, ctx->stream>>>(b, d_scores2, 0.0);
+                    LAUNCHED();
+                }
+                else TRY(reduce_stage(1, b.scores));
             }
             else
             {
@@ -1179,8 +1224,7 @@ int Job::run(bool full)
                 }
                 LAUNCHED();
                 MARK(PS_T_REDUCE);
-                k_reduce<<<(unsigned)((n_muts + 127) / 128), 128, 0, ctx->stream>>>(b, (const RegTabDev*)d_regtab, (int)regs.size(), n_muts, bias, 0);
-                LAUNCHED();
+                TRY(reduce_stage(0, b.scores));
             }
         }
     }
@@ -1290,7 +1334,8 @@ int Job::finish(std::vector<double>* align_scores, std::vector<double>* mut_scor
 // One job = build (host staging) + upload + kernels + result copies, all enqueued on the context's
 // stream by job_begin; job_end waits for the stream and scatters the results into the regions.
 // Between the two the host is free (e.g. to stage the next batch on another context).
-static int job_begin(ps_ctx* ctx, const std::vector<ps_region*>& regs, const std::vector<MutSpec>* muts, double bias, bool score32 = false)
+static int job_begin(ps_ctx* ctx, const std::vector<ps_region*>& regs, const std::vector<MutSpec>* muts, double bias, bool score32 = false,
+                     int shard_total_events = 0)
 {
     TRY(ctx->init());
     CU(cudaSetDevice(ctx->device));
@@ -1313,6 +1358,8 @@ static int job_begin(ps_ctx* ctx, const std::vector<ps_region*>& regs, const std
     if (muts) job->muts = *muts;
     job->bias = bias;
     job->score32 = score32 && muts == nullptr;
+    job->sharded = shard_total_events > 0 && muts != nullptr;
+    job->total_events = shard_total_events;
     // FAST flags mutations by their TOTAL over all events; an event shard (bias 0, ps_score_mutations_partial) only has
     // its part of the sum, so partial sums are always exact
     job->fast = ctx->precision == PS_PRECISION_FAST && muts != nullptr && bias != 0.0;
@@ -1360,7 +1407,7 @@ static double region_band_bytes(const ps_region* R, bool full)
 }
 
 static int run_job(ps_ctx* ctx, const std::vector<ps_region*>& regs, const std::vector<MutSpec>* muts,
-                   std::vector<double>* align_scores, std::vector<double>* mut_scores, double bias = -1e-6)
+                   std::vector<double>* align_scores, std::vector<double>* mut_scores, double bias = -1e-6, int shard_total_events = 0)
 {
     TRY(ctx->init());
     // a job whose band matrices would not fit (e.g. FindMutations: seeds x events wide fills of a 10 kb
@@ -1375,7 +1422,7 @@ static int run_job(ps_ctx* ctx, const std::vector<ps_region*>& regs, const std::
     for (const ps_region* R : regs) total += region_band_bytes(R, muts != nullptr);
     if (total <= budget || regs.size() <= 1)
     {
-        TRY(job_begin(ctx, regs, muts, bias));
+        TRY(job_begin(ctx, regs, muts, bias, false, shard_total_events));
         return job_end(ctx, align_scores, mut_scores);
     }
     if (align_scores) align_scores->clear();
@@ -1493,7 +1540,7 @@ std::vector<HostMut> ps_point_mutations(const ps_region* R)      // cpp/FindMuta
     return v;
 }
 
-int ps_score_mutation_list(ps_region* R, std::vector<HostMut>& muts, double bias)
+int ps_score_mutation_list(ps_region* R, std::vector<HostMut>& muts, double bias, int shard_total_events)
 {
     std::vector<MutSpec> per(1);
     per[0].list = &muts;
@@ -1516,7 +1563,7 @@ int ps_score_mutation_list(ps_region* R, std::vector<HostMut>& muts, double bias
             seeds[e].refstart = he.refstart; seeds[e].refend = he.refend;
         }
     }
-    TRY(run_job(ctx, std::vector<ps_region*>(1, R), &per, nullptr, &sc, bias));
+    TRY(run_job(ctx, std::vector<ps_region*>(1, R), &per, nullptr, &sc, bias, shard_total_events));
     if (fast)
     {
         std::vector<double> keep;
@@ -1533,7 +1580,7 @@ int ps_score_mutation_list(ps_region* R, std::vector<HostMut>& muts, double bias
                 if (he.ri_empty) he.ref_index.clear();
             }
             ctx->precision = PS_PRECISION_EXACT;
-            const int rc = run_job(ctx, std::vector<ps_region*>(1, R), &per, nullptr, &sc, bias);
+            const int rc = run_job(ctx, std::vector<ps_region*>(1, R), &per, nullptr, &sc, bias, shard_total_events);
             ctx->precision = PS_PRECISION_FAST;
             if (rc) return rc;
             ctx->exact_reruns++;
@@ -1868,6 +1915,31 @@ int ps_score_mutations_partial(ps_region* R, int n, const int* start, const char
     std::vector<HostMut> v = gather_muts(n, start, orig, mut, nullptr);
     TRY(ps_score_mutation_list(R, v, 0.0));
     for (int i = 0; i < n; i++) partial[i] = v[i].score;
+    return PS_OK;
+}
+
+// The events of ONE region split across the ranks of ps_comm_init: this handle holds this rank's block of the events (in
+// event order: rank 0 the first block, and so on), every rank passes the same mutations and gets the same, complete
+// scores back.  The sums over events are combined on the GPUs (ps_comm.cu).  poreseq/Variant.py:71-76.
+int ps_score_mutations_sharded(ps_region* R, int n, const int* start, const char* const* orig, const char* const* mut, double* scores)
+{
+    if (!R || n < 0 || (n > 0 && (!start || !orig || !mut || !scores))) return PS_BAD_ARGS(R ? R->ctx : nullptr, "ps_score_mutations_sharded");
+    ps_ctx* ctx = R->ctx;
+    if (!ctx->comm) { ps_set_error(ctx, "ps_score_mutations_sharded: the context has no communicator (ps_comm_init)"); return PS_E_ARG; }
+    if (R->events.empty()) { ps_set_error(ctx, "ps_score_mutations_sharded: every rank must hold at least one event"); return PS_E_ARG; }
+    TRY(ctx->init());
+    CU(cudaSetDevice(ctx->device));
+    // events of the region over all ranks (the FAST mode's re-score threshold is per event of the TOTAL)
+    double* d_count;
+    TRY(room(ctx, "shard_count", 1, &d_count));
+    double local = (double)R->events.size(), total = 0;
+    CU(cudaMemcpyAsync(d_count, &local, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    TRY(psi_comm_allreduce_sum(ctx, d_count, 1));
+    CU(cudaMemcpyAsync(&total, d_count, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    std::vector<HostMut> v = gather_muts(n, start, orig, mut, nullptr);
+    TRY(ps_score_mutation_list(R, v, -1e-6, (int)total));
+    for (int i = 0; i < n; i++) scores[i] = v[i].score;
     return PS_OK;
 }
 

@@ -51,6 +51,10 @@ struct ps_ctx
     long long launches = 0;
     long long exact_reruns = 0;               // FAST-mode lists re-scored exactly because of tied non-negative scores
     void* pending = nullptr;                  // the batch in flight between *_begin and *_end (a Job)
+    // event-shard communicator (ps_comm.cu): the ranks of one box that share the events of a region
+    void* comm = nullptr;                     // ncclComm_t
+    int comm_rank = 0, comm_ranks = 1;
+    bool comm_ordered = true;                 // ordered chain (bit-exact) or one all-reduce
     // environment knobs, read ONCE when the context is created (ps_create): a per-call getenv() races with a
     // setenv() of the host program
     bool trace = false;                       // PORESEQ_B200_TRACE: phase timings on stderr
@@ -144,7 +148,7 @@ void ps_parallel_for(int n, const std::function<void(int)>& fn);
 std::vector<int> ps_states_of(const std::string& bases);
 std::string ps_apply_mutation(const std::string& bases, int start, const std::string& orig, const std::string& mut);
 std::vector<HostMut> ps_point_mutations(const ps_region* R);
-int ps_score_mutation_list(ps_region* R, std::vector<HostMut>& muts, double bias = -1e-6);
+int ps_score_mutation_list(ps_region* R, std::vector<HostMut>& muts, double bias = -1e-6, int shard_total_events = 0);
 int ps_make_mutation_list(ps_region* R, std::vector<HostMut> muts, int* nbases);
 
 struct SWResult                               // cpp/swlib.h:25-33
@@ -166,3 +170,8 @@ int ps_run_alignments(ps_ctx* ctx, const std::vector<ps_region*>& regs,
                       std::vector<std::vector<double>>* scores, std::vector<std::vector<double>>* likes);
 int ps_find_mutation_list(ps_region* R, const std::vector<std::string>& seeds, std::vector<HostMut>& found);
 int ps_mutate_loop(ps_region* R, const std::vector<std::string>& seeds, int reps, int* totbases);
+// NCCL steps of the event-sharded sum, enqueued on the context's stream (ps_comm.cu)
+int psi_comm_allreduce_sum(ps_ctx* ctx, double* buf, size_t count);
+int psi_comm_recv_prev(ps_ctx* ctx, double* buf, size_t count);
+int psi_comm_send_next(ps_ctx* ctx, const double* buf, size_t count);
+int psi_comm_bcast_last(ps_ctx* ctx, double* buf, size_t count);

@@ -79,6 +79,11 @@ def lib():
     L.ps_score_events_batch.argtypes = [C.POINTER(C.c_void_p), C.c_int, _c_double_p]
     L.ps_score_mutations.argtypes = [C.c_void_p, C.c_int, _c_int_p, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), _c_double_p]
     L.ps_score_mutations_partial.argtypes = L.ps_score_mutations.argtypes
+    L.ps_score_mutations_sharded.argtypes = L.ps_score_mutations.argtypes
+    L.ps_comm_unique_id.argtypes = [C.c_char_p, C.c_int]
+    L.ps_comm_init.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.ps_comm_destroy.argtypes = [C.c_void_p]
+    L.ps_comm_rank.argtypes = [C.c_void_p, _c_int_p, _c_int_p]
     L.ps_find_point_mutations.argtypes = [C.c_void_p, C.c_int, _c_int_p, _c_int_p, C.c_char_p, C.c_char_p]
     L.ps_score_points.argtypes = [C.c_void_p, C.c_int, _c_int_p, _c_int_p, C.c_char_p, C.c_char_p, _c_double_p]
     L.ps_score_points_batch.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, _c_int_p, C.POINTER(C.c_longlong),
@@ -140,6 +145,14 @@ class Context(object):
         """'exact' (default, bit-identical FP64) or 'fast' (FP32 scan + exact re-score of candidates)."""
         self.check(self.lib.ps_set_precision(self.handle, {"exact": 0, "fast": 1}[mode]))
 
+    def comm_init(self, unique_id, rank, n_ranks, ordered=True):
+        """Joins the event-shard communicator of `n_ranks` contexts (one per GPU): ps_comm_init.  `unique_id` is what
+        rank 0 got from comm_unique_id(), carried to the other ranks by the caller."""
+        self.check(self.lib.ps_comm_init(self.handle, unique_id, len(unique_id), int(rank), int(n_ranks), 1 if ordered else 0))
+
+    def comm_destroy(self):
+        self.check(self.lib.ps_comm_destroy(self.handle))
+
     def launch_count(self):
         return int(self.lib.ps_launch_count(self.handle))
 
@@ -161,6 +174,15 @@ class Context(object):
 
 
 _default_ctx = {}
+
+
+def comm_unique_id():
+    """The 128-byte NCCL id rank 0 creates for ps_comm_init (ps_comm_unique_id)."""
+    buf = C.create_string_buffer(128)
+    rc = lib().ps_comm_unique_id(buf, 128)
+    if rc != 0:
+        raise RuntimeError("poreseq_b200 error %d: %s" % (rc, lib().ps_last_error(None).decode()))
+    return buf.raw
 
 
 def default_context(device=None):
@@ -371,6 +393,16 @@ class NativeRegion(object):
         st = np.ascontiguousarray(starts, dtype=np.int32)
         out = np.zeros(n)
         self.ctx.check(self.ctx.lib.ps_score_mutations_partial(self.handle, n, st.ctypes.data_as(_c_int_p), _cstrs(origs),
+                                                               _cstrs(muts), _dp(out)))
+        return out
+
+    def score_mutations_sharded(self, starts, origs, muts):
+        """This handle holds this rank's block of the region's events; complete scores come back on every rank
+        (ps_score_mutations_sharded, sums combined over NCCL inside the library)."""
+        n = len(starts)
+        st = np.ascontiguousarray(starts, dtype=np.int32)
+        out = np.zeros(n)
+        self.ctx.check(self.ctx.lib.ps_score_mutations_sharded(self.handle, n, st.ctypes.data_as(_c_int_p), _cstrs(origs),
                                                                _cstrs(muts), _dp(out)))
         return out
 

@@ -7,7 +7,10 @@ Three nested levels, all independent except one sum:
                 with ONE all_reduce(sum, float64, n_mutations) (`score_mutations_event_sharded`);
   mutations  -> not needed once events are split.
 
-`torch.distributed` is plumbing only: NCCL over NVLink on the GPUs, gloo in the CPU test.  The sum over
+On the GPUs the combine step lives INSIDE the library (`score_mutations_sharded` -> ps_score_mutations_sharded,
+csrc/ps_comm.cu: NCCL on the library's stream, ordered = bit-identical to one GPU, or one all-reduce).  The
+`torch.distributed` form below (`score_mutations_event_sharded`) is the same host logic over any backend: gloo in the
+CPU test.  The sum over
 a rank's own events stays the ordered FP64 sum of the kernel; across ranks the order of the (few)
 partials is fixed by the reduction, so scores agree with the single-GPU path to ~1e-16 relative
 (not bit for bit) while accept/reject decisions on clearly signed scores are unchanged.
@@ -55,6 +58,19 @@ def score_mutations_event_sharded(region, starts, origs, muts, partial_fn, rank,
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return -1e-6 + t.cpu().numpy()
+
+
+def score_mutations_sharded(ctx, region, starts, origs, muts, rank, world, width_key=None):
+    """The product path: this rank's block of the region's events goes into a native region on this rank's GPU and
+    ps_score_mutations_sharded combines the per-mutation sums over NCCL inside the library (ctx.comm_init first).
+    Returns the complete scores (identical on every rank)."""
+    from . import poreseqcpp
+    shard = RegionShard(region, rank, world)
+    nr = poreseqcpp.NativeRegion(ctx, shard.sequence, shard.events, shard.params, width_key)
+    try:
+        return nr.score_mutations_sharded(starts, origs, muts)
+    finally:
+        nr.close()
 
 
 def cuda_partial(ctx, width_key=None):
