@@ -154,6 +154,23 @@ int         ps_score_mutations(ps_region* r, int n, const int* start, const char
 int         ps_score_mutations_partial(ps_region* r, int n, const int* start, const char* const* orig,
                                        const char* const* mut, double* partial);
 
+/* ---- the consensus loop ----------------------------------------------------------------------
+ * poreseq/Mutate.py:47-99 below the boundary: Mutate('self', reps), then up to `reps` rounds of (Mutate('viterbi'),
+ * Refine at point_width) until Refine changes nothing.  The handle is the PSAlign object of the loop: its sequence and
+ * its events' alignments are what pa.sequence / pa.events hold afterwards (end_trim, Mutate.py:84-88, is left to the
+ * caller: it is a slice of the returned string).  Regions with fewer than 5 events are left untouched (Mutate.py:50-53).
+ * ViterbiMutate draws from a rand() stream of the region's own that starts at glibc's default seed -- what the
+ * reference's one process per region sees (cpp/Viterbi.cpp:108; the stream is never seeded).
+ * *n_stages: stages run; ps_region_get_stage(k) gives the stage's name ("mutate_self", "mutate_viterbi_0", "refine_0",
+ * ...), the sequence after it and the bases it changed (returns the sequence length; buffers may be NULL).
+ * ps_consensus_batch: n regions, `in_flight` of them side by side on ctx's device (host threads and streams of the
+ * library: the reference's one-process-per-region scaling, README.md:48-54, inside one process). */
+int         ps_consensus(ps_region* r, int reps, int point_width, int* n_stages);
+int         ps_consensus_batch(ps_ctx* ctx, ps_region* const* regions, int n_regions, int reps, int point_width,
+                               int in_flight);
+int         ps_region_num_stages(ps_region* r);
+int         ps_region_get_stage(ps_region* r, int k, char* name, int name_cap, char* seq, int seq_cap, int* nbases);
+
 /* ---- one region's events split across the GPUs of a box ---------------------------------------
  * score[m] = -1e-6 + sum over events of delta(m, e)   (cpp/MakeMutations.cpp:19-22, 38-52; the caller is
  * poreseq/Variant.py:71-76 on deep coverage).  Every rank (one process / context per GPU) holds a contiguous block of

@@ -9,6 +9,8 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <thread>
+#include <atomic>
 
 #include "ps_internal.h"
 
@@ -387,6 +389,110 @@ int ps_found_mutation_sizes(ps_region* R, int i, int* n_orig, int* n_mut)
     if (n_orig) *n_orig = (int)R->found[i].orig.size();
     if (n_mut) *n_mut = (int)R->found[i].mut.size();
     return PS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// The consensus loop of one region below the C-ABI (poreseq/Mutate.py:47-99): Mutate('self', reps) then up to `reps`
+// rounds of (Mutate('viterbi'), Refine) until Refine changes nothing.  One region handle for the whole loop: nothing is
+// re-marshalled between the steps (the Python policy builds a fresh native region for every PSAlign method, like the
+// reference does, pyx:139-153) and the per-level log(stdv) records are computed once.  The handle's own state after each
+// step is exactly what the reference writes back to Python and marshals again for the next one (sequence, ref_align,
+// ref_like); ref_index is rebuilt from ref_align with the same arithmetic (HostEvent::update_refs).
+static int consensus_one(ps_region* R, int reps, int point_width)
+{
+    R->stage_log.clear(); R->stage_nbases.clear();
+    if (R->events.size() < 5) return PS_OK;                          // Mutate.py:50-53
+    if (!R->own_rng) R->rng_seed(1);                                 // one process per region in the reference: rand() starts at seed 1
+    auto note = [&](const std::string& name, int nb) { R->stage_log.emplace_back(name, R->bases); R->stage_nbases.push_back(nb); };
+    const int scoring_width = R->params.scoring_width;
+    std::vector<std::string> seeds;
+    for (size_t e = 0; e < R->events.size(); e += 2) seeds.push_back(R->events[e].seq2d);     // pyx:412-414
+    int nb = 0;
+    R->seqlikes.clear();
+    TRY(ps_mutate_loop(R, seeds, reps, &nb));
+    R->seqlikes.clear();
+    note("mutate_self", nb);
+    for (int k = 0; k < reps; k++)
+    {
+        std::vector<std::string> vit;
+        TRY(ps_viterbi_list(R, 16, 0.05, 0.01, 0.33, 0.75, vit));      // pyx:417
+        R->seqlikes.clear();
+        TRY(ps_mutate_loop(R, vit, 4, &nb));                          // Mutate.py:76: pa.Mutate(seqs='viterbi'), reps defaults to 4
+        R->seqlikes.clear();
+        note("mutate_viterbi_" + std::to_string(k), nb);
+        R->params.scoring_width = point_width;                         // pyx:464-465
+        const int rc = ps_refine_region(R, &nb);
+        R->params.scoring_width = scoring_width;
+        if (rc) return rc;
+        note("refine_" + std::to_string(k), nb);
+        if (nb == 0) break;
+    }
+    return PS_OK;
+}
+
+extern "C" int ps_consensus(ps_region* R, int reps, int point_width, int* n_stages)
+{
+    if (!R || reps < 0 || point_width < 0) return PS_BAD_ARGS(R ? R->ctx : nullptr, "ps_consensus");
+    TRY(consensus_one(R, reps, point_width));
+    if (n_stages) *n_stages = (int)R->stage_log.size();
+    return PS_OK;
+}
+
+// Many regions at once: `in_flight` regions are worked on side by side, each by a host thread of the library with a
+// context of its own (stream, staging and device buffers) on ctx's device -- the reference's scaling model (one process
+// per region, README.md:48-54) folded into one process, below the C-ABI: no interpreter, no marshalling between the
+// steps.  The loop of one region is ~400 small dependent launches; regions in flight is what fills the GPU.
+extern "C" int ps_consensus_batch(ps_ctx* ctx, ps_region* const* regions, int n_regions, int reps, int point_width, int in_flight)
+{
+    if (!ctx || n_regions < 0 || (n_regions > 0 && !regions) || reps < 0 || point_width < 0) return PS_BAD_ARGS(ctx, "ps_consensus_batch");
+    for (int k = 0; k < n_regions; k++) if (!regions[k]) return PS_BAD_ARGS(ctx, "ps_consensus_batch");
+    if (n_regions == 0) return PS_OK;
+    TRY(ctx->init());
+    in_flight = std::max(1, std::min(std::min(in_flight, n_regions), 64));
+    while ((int)ctx->helpers.size() < in_flight - 1)
+    {
+        ps_ctx* h = ps_create(ctx->device);
+        if (!h) { ps_set_error(ctx, "ps_consensus_batch: out of memory"); return PS_E_INTERNAL; }
+        ctx->helpers.push_back(h);
+    }
+    std::vector<ps_ctx*> lanes(1, ctx);
+    for (int k = 0; k + 1 < in_flight; k++) { ctx->helpers[k]->precision = ctx->precision; lanes.push_back(ctx->helpers[k]); }
+    std::atomic<int> next(0);
+    std::vector<int> rcs(in_flight, PS_OK);
+    std::vector<std::string> errs(in_flight);
+    auto work = [&](int lane) {
+        ps_ctx* mine = lanes[lane];
+        for (;;)
+        {
+            const int k = next.fetch_add(1);
+            if (k >= n_regions) return;
+            ps_region* R = regions[k];
+            ps_ctx* home = R->ctx;
+            R->ctx = mine;                                               // the region's jobs run on this lane's stream and buffers
+            const int rc = consensus_one(R, reps, point_width);
+            R->ctx = home;
+            if (rc && !rcs[lane]) { rcs[lane] = rc; errs[lane] = mine->error; }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int lane = 1; lane < in_flight; lane++) th.emplace_back(work, lane);
+    work(0);
+    for (std::thread& t : th) t.join();
+    for (int lane = 0; lane < in_flight; lane++)
+        if (rcs[lane]) { ps_set_error(ctx, "ps_consensus_batch: %s", errs[lane].c_str()); return rcs[lane]; }
+    return PS_OK;
+}
+
+extern "C" int ps_region_num_stages(ps_region* R) { return R ? (int)R->stage_log.size() : PS_E_ARG; }
+
+extern "C" int ps_region_get_stage(ps_region* R, int k, char* name, int name_cap, char* seq, int seq_cap, int* nbases)
+{
+    if (!R || k < 0 || k >= (int)R->stage_log.size()) return PS_BAD_ARGS(R ? R->ctx : nullptr, "ps_region_get_stage");
+    const auto& st = R->stage_log[k];
+    if (nbases) *nbases = R->stage_nbases[k];
+    if (name) { if ((int)st.first.size() + 1 > name_cap) return PS_E_CAPACITY; memcpy(name, st.first.c_str(), st.first.size() + 1); }
+    if (seq) { if ((int)st.second.size() + 1 > seq_cap) return PS_E_CAPACITY; memcpy(seq, st.second.c_str(), st.second.size() + 1); }
+    return (int)st.second.size();
 }
 
 int ps_mutate(ps_region* R, int n_seeds, const char* const* seeds, int reps, int* totbases)

@@ -343,6 +343,8 @@ bool ps_pin_reserve(PinBuf* b, size_t bytes, size_t keep)
 
 ps_ctx::~ps_ctx()
 {
+    for (ps_ctx* h : helpers) delete h;
+    helpers.clear();
     if (!ready) return;
     cudaSetDevice(device);
     ps_comm_destroy(this);
@@ -1520,6 +1522,16 @@ int ps_run_event_scores(ps_ctx* ctx, const std::vector<ps_region*>& regs, std::v
     return rc;
 }
 
+int ps_refine_region(ps_region* R, int* nbases)                  // PSAlign.Refine, poreseq/_poreseqcpp.pyx:437-472
+{
+    std::vector<HostMut> v = ps_point_mutations(R);
+    TRY(ps_score_mutation_list(R, v));
+    int nb = 0;
+    TRY(ps_make_mutation_list(R, v, &nb));
+    if (nbases) *nbases = nb;
+    return PS_OK;
+}
+
 std::vector<HostMut> ps_point_mutations(const ps_region* R)      // cpp/FindMutations.cpp:191-234
 {
     static const char acgt[] = "ACGT";
@@ -1632,6 +1644,21 @@ int ps_make_mutation_list(ps_region* R, std::vector<HostMut> muts, int* nbases)
     }
     *nbases = changed;
     return PS_OK;
+}
+
+void ps_region::rng_seed(unsigned seed)
+{
+    memset(&rng_data, 0, sizeof rng_data);
+    memset(rng_state, 0, sizeof rng_state);
+    initstate_r(seed, rng_state, sizeof rng_state, &rng_data);
+    own_rng = true;
+}
+
+double ps_region::next_uniform()
+{
+    int32_t v = 0;
+    random_r(&rng_data, &v);
+    return v / (double(RAND_MAX) + 1);
 }
 
 void ps_region::set_sequence(const std::string& s)
@@ -2056,12 +2083,7 @@ int ps_make_mutations(ps_region* R, int n, const int* start, const char* const* 
 int ps_refine(ps_region* R, int* nbases)
 {
     if (!R) return PS_BAD_ARGS(R ? R->ctx : nullptr, "ps_refine");
-    std::vector<HostMut> v = ps_point_mutations(R);
-    TRY(ps_score_mutation_list(R, v));
-    int nb = 0;
-    TRY(ps_make_mutation_list(R, v, &nb));
-    if (nbases) *nbases = nb;
-    return PS_OK;
+    return ps_refine_region(R, nbases);
 }
 
 int ps_seq_to_states(const char* seq, int len, int* states)

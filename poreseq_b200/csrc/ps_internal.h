@@ -1,5 +1,6 @@
 // ps_internal.h -- host-side objects behind the opaque handles of include/poreseq_b200.h.
 #pragma once
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -69,6 +70,7 @@ struct ps_ctx
     std::map<std::string, PinBuf> pins;       // grow-only named pinned host buffers
     template <class T> PinVec<T> pinned(const char* name) { PinVec<T> v; v.buf = &pins[name]; v.n = 0; return v; }
 
+    std::vector<ps_ctx*> helpers;             // ps_consensus_batch: further contexts (stream + buffers) on the same device, one per region in flight
     int init();                               // lazy CUDA initialisation
     int ensure(DevBuf& b, size_t bytes);
     ~ps_ctx();
@@ -136,6 +138,17 @@ struct ps_region                              // cpp/AlignData.h:24-34
     std::map<std::string, std::vector<double>> seqlikes;   // FindMutations cache (cpp/AlignData.h:34)
     std::vector<HostMut> found;                            // result of the last ps_find_mutations
     std::vector<std::string> viterbi;                      // result of the last ps_viterbi_mutate
+    // ps_consensus: the reference runs one process per region, so every region's ViterbiMutate calls draw from a
+    // rand() stream of their own that starts at glibc's default seed 1 (cpp/Viterbi.cpp:108, never seeded).  A region
+    // with `own_rng` draws from a private copy of that generator (random_r: the same TYPE_3 sequence as rand()) instead
+    // of the process-global one, so regions in flight side by side do not interleave their draws.
+    bool own_rng = false;
+    char rng_state[128];
+    struct random_data rng_data;
+    void rng_seed(unsigned seed);
+    double next_uniform();                                 // rand() / (RAND_MAX + 1.0)
+    std::vector<std::pair<std::string, std::string>> stage_log;   // ps_consensus: (stage, sequence after it)
+    std::vector<int> stage_nbases;
     void set_sequence(const std::string& s);
 };
 
@@ -170,6 +183,9 @@ int ps_run_alignments(ps_ctx* ctx, const std::vector<ps_region*>& regs,
                       std::vector<std::vector<double>>* scores, std::vector<std::vector<double>>* likes);
 int ps_find_mutation_list(ps_region* R, const std::vector<std::string>& seeds, std::vector<HostMut>& found);
 int ps_mutate_loop(ps_region* R, const std::vector<std::string>& seeds, int reps, int* totbases);
+int ps_viterbi_list(ps_region* R, int nkeep, double skip_prob, double stay_prob, double mut_min, double mut_max,
+                    std::vector<std::string>& out);
+int ps_refine_region(ps_region* R, int* nbases);
 // NCCL steps of the event-sharded sum, enqueued on the context's stream (ps_comm.cu)
 int psi_comm_allreduce_sum(ps_ctx* ctx, double* buf, size_t count);
 int psi_comm_recv_prev(ps_ctx* ctx, double* buf, size_t count);

@@ -424,7 +424,8 @@ int ps_viterbi_list(ps_region* R, int nkeep, double skip_prob, double stay_prob,
         ps_set_error(ctx, "out of host memory staging ViterbiMutate");
         return PS_E_INTERNAL;
     }
-    for (size_t q = 0; q < rnd.size(); q++) rnd[q] = rand() / (double(RAND_MAX) + 1);
+    if (R->own_rng) for (size_t q = 0; q < rnd.size(); q++) rnd[q] = R->next_uniform();
+    else for (size_t q = 0; q < rnd.size(); q++) rnd[q] = rand() / (double(RAND_MAX) + 1);
     TRY(vroom(ctx, "vit_rnd", rnd.size(), &d_rnd));
     TRY(vroom(ctx, "vit_paths", rnd.size(), &d_paths));
     CU(cudaMemcpyAsync(d_rnd, rnd.data(), rnd.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));

@@ -52,6 +52,31 @@ def consensus(pa, refseq=None, reps=4, verbose=0, log=sys.stderr, stages=None):
     return pa.sequence, acc
 
 
+def consensus_native(regions, ctx=None, reps=4, in_flight=16, refseqs=None):
+    """The same policy run below the C-ABI (ps_consensus_batch): one native region per input region for the whole loop,
+    `in_flight` regions side by side on the GPU.  `regions`: objects with .sequence/.events/.params (PSAlign, synthetic
+    regions) or poreseqcpp.PackedRegion views of an event-pack file.  Returns [(sequence after end_trim, accuracy or None,
+    stages)] per region."""
+    ctx = ctx or poreseqcpp.default_context()
+    packs = [r if isinstance(r, poreseqcpp.PackedRegion) else poreseqcpp.PackedRegion(r.sequence, r.events, r.params) for r in regions]
+    nrs = poreseqcpp.native_regions_from_packed(ctx, packs)
+    try:
+        pw = int(packs[0].params.get("point_width", packs[0].params.get("scoring_width", 20))) if packs else 20
+        poreseqcpp.consensus_batch(ctx, nrs, reps=reps, point_width=pw, in_flight=in_flight)
+        out = []
+        for k, nr in enumerate(nrs):
+            seq = nr.sequence()
+            params = packs[k].params
+            if 'end_trim' in params and len(seq) > 2 * params['end_trim']:
+                t = int(params['end_trim'])
+                seq = seq[t:-t]
+            acc = poreseqcpp.swalign(seq, refseqs[k])[0] if refseqs else None
+            out.append((seq, acc, nr.stages()))
+        return out
+    finally:
+        poreseqcpp.close_regions(nrs)
+
+
 def variant(pa, muts=None, var_seqs=None, region_start=0):
     """Variant scoring of one region (poreseq/Variant.py:44-95).
 

@@ -80,6 +80,10 @@ def lib():
     L.ps_score_mutations.argtypes = [C.c_void_p, C.c_int, _c_int_p, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), _c_double_p]
     L.ps_score_mutations_partial.argtypes = L.ps_score_mutations.argtypes
     L.ps_score_mutations_sharded.argtypes = L.ps_score_mutations.argtypes
+    L.ps_consensus.argtypes = [C.c_void_p, C.c_int, C.c_int, _c_int_p]
+    L.ps_consensus_batch.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int]
+    L.ps_region_num_stages.argtypes = [C.c_void_p]
+    L.ps_region_get_stage.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int, _c_int_p]
     L.ps_comm_unique_id.argtypes = [C.c_char_p, C.c_int]
     L.ps_comm_init.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]
     L.ps_comm_destroy.argtypes = [C.c_void_p]
@@ -396,6 +400,21 @@ class NativeRegion(object):
                                                                _cstrs(muts), _dp(out)))
         return out
 
+    def consensus(self, reps=4, point_width=20):
+        """The whole Mutate.py loop on this handle (ps_consensus); returns the stages [(name, sequence, bases changed)]."""
+        n = C.c_int(0)
+        self.ctx.check(self.ctx.lib.ps_consensus(self.handle, int(reps), int(point_width), C.byref(n)))
+        return self.stages()
+
+    def stages(self):
+        out = []
+        for k in range(self.ctx.lib.ps_region_num_stages(self.handle)):
+            ln = self.ctx.lib.ps_region_get_stage(self.handle, k, None, 0, None, 0, None)
+            name, seq, nb = C.create_string_buffer(64), C.create_string_buffer(ln + 1), C.c_int(0)
+            self.ctx.lib.ps_region_get_stage(self.handle, k, name, 64, seq, ln + 1, C.byref(nb))
+            out.append((name.value.decode(), seq.value.decode(), nb.value))
+        return out
+
     def score_mutations_sharded(self, starts, origs, muts):
         """This handle holds this rank's block of the region's events; complete scores come back on every rank
         (ps_score_mutations_sharded, sums combined over NCCL inside the library)."""
@@ -542,6 +561,14 @@ def score_events_batch(ctx, regions):
         res.append(out[at:at + c])
         at += c
     return res
+
+
+def consensus_batch(ctx, regions, reps=4, point_width=20, in_flight=16):
+    """ps_consensus_batch over NativeRegion objects of `ctx`: the Mutate.py loop of every region, `in_flight` regions side
+    by side on the GPU.  Afterwards every region's .sequence() / .event_align() / .stages() hold its result."""
+    n = len(regions)
+    handles = (C.c_void_p * n)(*[r.handle for r in regions])
+    ctx.check(ctx.lib.ps_consensus_batch(ctx.handle, handles, n, int(reps), int(point_width), int(in_flight)))
 
 
 class PendingBatch(object):

@@ -101,3 +101,25 @@ def test_variant_region_matches_reference(precision):
         assert np.array_equal(ev_scores, z["event_scores"])
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("precision", ["exact", "fast"])
+@pytest.mark.parametrize("name", ["c2s", "c2", "c4"])
+def test_native_consensus_matches_reference(name, precision):
+    """The same loop below the C-ABI (ps_consensus: one region handle for the whole loop, the region's own rand()
+    stream): every stage's sequence and bases changed equal the reference's, and so do the final alignments."""
+    z, reg = load(name)
+    c = poreseqcpp.Context(0)
+    try:
+        c.set_precision(precision)
+        nr = poreseqcpp.NativeRegion(c, reg.sequence, reg.events, reg.params)
+        stages = nr.consensus(reps=4, point_width=int(reg.params["point_width"]))
+        assert [s[0] for s in stages] == z["stage_names"].tolist()
+        for k, (nm, seq, nb) in enumerate(stages):
+            assert nb == int(z["stage_nbases"][k]), (nm, nb, int(z["stage_nbases"][k]))
+            assert seq == str(z["stage_seqs"][k]), "sequence differs after %s" % nm
+        al = [nr.event_align(e)[0] for e in range(len(reg.events))]
+        assert align_digest(al) == str(z["stage_aligns"][-1])
+        nr.close()
+    finally:
+        c.close()

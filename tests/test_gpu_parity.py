@@ -684,3 +684,37 @@ def test_score_events_fast(drv, name):
         nr.close(); other.close(); twin.close()
     finally:
         c2.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the consensus loop below the C-ABI (ps_consensus / ps_consensus_batch) against the Python policy over PSAlign
+
+@pytest.mark.parametrize("precision", ["exact", "fast"])
+def test_native_consensus_equals_python_policy(precision):
+    """drivers.consensus (a fresh native region per PSAlign method, like the reference) and ps_consensus (one handle for
+    the whole loop) must walk through the same stages; a batch of regions in flight gives what one by one gives."""
+    import ctypes
+    from poreseq_b200 import drivers
+    regs = [synth.make_region(500, 5, seed=60 + k, draft_error=0.08) for k in range(5)]
+    regs.append(synth.make_region(300, 2, seed=70, draft_error=0.05))             # fewer than 5 events: left untouched
+    c = poreseqcpp.Context(0)
+    try:
+        c.set_precision(precision)
+        want = []
+        for reg in regs:
+            pa = drivers.make_psalign(reg)
+            pa.ctx = c
+            ctypes.CDLL("libc.so.6").srand(1)
+            st = []
+            seq, _ = drivers.consensus(pa, reps=4, stages=st)
+            want.append((seq, [(s[0], s[1], s[2]) for s in st], [np.array(ev.ref_align) for ev in pa.events]))
+        got = drivers.consensus_native(regs, ctx=c, reps=4, in_flight=4)
+        for k, reg in enumerate(regs):
+            assert got[k][2] == want[k][1], "stages of region %d differ" % k
+            assert got[k][0] == want[k][0]
+        one = poreseqcpp.NativeRegion(c, regs[0].sequence, regs[0].events, regs[0].params)
+        assert one.consensus(4, int(regs[0].params["point_width"])) == want[0][1]
+        assert all(np.array_equal(one.event_align(e)[0], want[0][2][e]) for e in range(len(regs[0].events)))
+        one.close()
+    finally:
+        c.close()
