@@ -35,6 +35,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# the consensus legs keep 16 regions (streams) in flight per GPU: with the default 8 hardware queues streams share a
+# connection and serialise behind each other (25 -> 40 kb/s); must be set before CUDA initialises
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 from poreseq_b200 import synth  # noqa: E402
 
@@ -159,57 +162,8 @@ def libc_srand(seed):
     ctypes.CDLL("libc.so.6").srand(seed)
 
 
-def consensus_gpu(length, coverage, seed):
-    """Secondary headline (BASELINE.json: consensus kb/s): the whole Mutate.py policy -- Mutate('self'), then
-    rounds of Mutate('viterbi') + Refine until nothing changes -- on one synthetic region through the PSAlign
-    mirror.  A throw-away region runs first so that CUDA initialisation is not inside the timed loop."""
-    from poreseq_b200 import drivers, poreseqcpp
-    poreseqcpp.default_context().set_precision("fast")
-    drivers.consensus(drivers.make_psalign(synth.make_region(300, 5, seed=99, draft_error=0.05)), reps=1)
-    reg = synth.make_region(length, coverage, seed=seed, draft_error=0.10)
-    pa = drivers.make_psalign(reg)
-    libc_srand(1)                       # ViterbiMutate draws from the process-global rand() stream on both sides
-    t0 = time.perf_counter()
-    seq, acc = drivers.consensus(pa, refseq=reg.truth, reps=4)
-    dt = time.perf_counter() - t0
-    return {"value": length / 1000.0 / dt, "unit": "kb/s", "seconds": dt, "accuracy_pct": acc,
-            "draft_accuracy_pct": poreseqcpp.swalign(reg.sequence, reg.truth)[0],
-            "config": "consensus loop on a %d b region at %dx coverage (draft with 10%% errors), fast precision" % (length, coverage)}, seq
-
-
 CONS_REGIONS = 64          # per GPU (32 left the tail of the last regions in flight visible: 17-23 kb/s run to run)
-
-
-def consensus_throughput(ctxs, n_regions, length, coverage, seed0):
-    """Consensus loops of several regions at once on one GPU: one host thread and one context (stream) per
-    region in flight -- the reference's own scaling model (one process per region file, README.md:48-54)
-    folded into one process.  Returns (seconds, mean accuracy)."""
-    import queue
-    import threading
-    from poreseq_b200 import drivers, poreseqcpp
-    regs = [synth.make_region(length, coverage, seed=seed0 + k, draft_error=0.10) for k in range(n_regions)]
-    q = queue.Queue()
-    for r in regs:
-        q.put(r)
-    accs = []
-
-    def worker(ctx):
-        while True:
-            try:
-                reg = q.get_nowait()
-            except queue.Empty:
-                break
-            pa = drivers.make_psalign(reg)
-            pa.ctx = ctx
-            accs.append(drivers.consensus(pa, refseq=reg.truth, reps=4)[1])
-
-    t0 = time.perf_counter()
-    ths = [threading.Thread(target=worker, args=(c,)) for c in ctxs]
-    for t in ths:
-        t.start()
-    for t in ths:
-        t.join()
-    return time.perf_counter() - t0, sum(accs) / max(len(accs), 1)
+CONS_IN_FLIGHT = 16        # regions side by side per GPU (library threads + streams)
 
 
 def consensus_cpu(length, coverage, seed):
@@ -239,6 +193,199 @@ def consensus_cpu(length, coverage, seed):
     t = int(rr.params.get("end_trim", 0))
     out = rr.sequence[t:-t] if t and len(rr.sequence) > 2 * t else rr.sequence
     return {"value": length / 1000.0 / dt, "unit": "kb/s", "seconds": dt, "cores": 1, "kind": "reference"}, out
+
+
+def golden(name):
+    """tests/golden/f_<name>.npz (outputs of the reference's own C++ at full size), or None."""
+    path = os.path.join(ROOT, "tests", "golden", "f_%s.npz" % name)
+    return np.load(path) if os.path.exists(path) else None
+
+
+def fast_mode_error(ctx_fast, device):
+    """Largest relative error the FAST mode leaves against the EXACT (bit-identical) mode, measured in this run on one
+    of the step's regions; scores >= -tau are re-scored exactly, so they must be equal."""
+    from poreseq_b200 import poreseqcpp
+    reg = synth.make_region(REGION_LEN, COVERAGE, seed=1, draft_error=0.03)
+    cx = poreseqcpp.Context(device)
+    try:
+        ex = poreseqcpp.NativeRegion(cx, reg.sequence, reg.events, reg.params, "point_width").score_points()[3].copy()
+        fa = poreseqcpp.NativeRegion(ctx_fast, reg.sequence, reg.events, reg.params, "point_width").score_points()[3].copy()
+    finally:
+        cx.close()
+    rel = np.abs(fa - ex) / np.maximum(np.abs(ex), 1e-300)
+    return {"max_rel_err": float(rel.max()), "tolerance": 1e-4, "edits": int(len(ex)),
+            "accept_reject_identical": bool(np.array_equal(fa >= 0, ex >= 0)),
+            "bit_identical_above_threshold": bool(np.array_equal(fa[ex > -0.4 * len(reg.events)], ex[ex > -0.4 * len(reg.events)])),
+            "sample": "ScorePoints of one 1 kb x 10x region with a 3% draft error, FAST vs EXACT"}
+
+
+def leg_score_events(device, sms, sm_max_mhz, cpu=True):
+    """BASELINE.json configs[0]: PSAlign.ScoreEvents on a 1 kb region at 10x -- FAST mode = k_score_f32 (score-only FP32
+    fill).  One region (latency) and 44 regions per call (throughput, the kernel's roofline)."""
+    from poreseq_b200 import poreseqcpp
+    ctx = poreseqcpp.Context(device)
+    ctx.set_precision("fast")
+    cx = poreseqcpp.Context(device)
+    try:
+        regs = [synth.make_region(REGION_LEN, COVERAGE, seed=1 + k) for k in range(44)]
+        nrs = [poreseqcpp.NativeRegion(ctx, r.sequence, r.events, r.params) for r in regs]
+        one = nrs[:1]
+        exact = poreseqcpp.NativeRegion(cx, regs[0].sequence, regs[0].events, regs[0].params).score_events()
+        for _ in range(3):
+            got = poreseqcpp.score_events_batch(ctx, one)[0]
+            poreseqcpp.score_events_batch(ctx, nrs)
+        t0 = time.perf_counter()
+        kern = []
+        for _ in range(20):
+            poreseqcpp.score_events_batch(ctx, one)
+            kern.append(ctx.last_timing()["forward"])
+        lat = (time.perf_counter() - t0) / 20
+        cells1, _ = ctx.last_cells()
+        kb = []
+        t0 = time.perf_counter()
+        for _ in range(20):
+            poreseqcpp.score_events_batch(ctx, nrs)
+            kb.append(ctx.last_timing()["forward"])
+        wall44 = (time.perf_counter() - t0) / 20
+        cells44, _ = ctx.last_cells()
+        kb.sort(); kern.sort()
+        k44 = kb[len(kb) // 2] * 1e-3
+        peak = sms * 128 * sm_max_mhz * 1e6 / 1e12
+        ach = cells44 * OPS_PER_CELL / k44 / 1e12
+        out = {"config": "PSAlign.ScoreEvents, 1 kb region x 10x coverage (BASELINE.json configs[0]), fast precision: score-only FP32 fill",
+               "one_region": {"seconds_per_call": lat, "kernel_ms": kern[len(kern) // 2], "gcups_call": cells1 / lat / 1e9,
+                              "gcups_kernel": cells1 / (kern[len(kern) // 2] * 1e-3) / 1e9, "cells": cells1},
+               "batch_44_regions": {"kernel_ms": k44 * 1e3, "gcups_kernel": cells44 / k44 / 1e9, "gcups_call": cells44 / wall44 / 1e9,
+                                    "cells": cells44},
+               "roofline": {"bound": "fp32-issue", "kernel": "k_score_f32", "achieved": ach, "peak": peak, "unit": "Tlane-op/s",
+                            "frac": ach / peak, "ops_per_cell": OPS_PER_CELL, "traffic": None,
+                            "note": "44 regions per launch; nothing is stored: HBM traffic is the 16 B level records, read once per CTA"},
+               "max_rel_err_vs_exact": float(np.max(np.abs(got - exact) / exact)), "tolerance": 1e-4}
+        if cpu:
+            from oracle import binding
+            which, kind = cpu_checker_kind()
+            chk = binding.load(which)
+            t0 = time.perf_counter()
+            want, _, _ = chk.score_alignments(regs[0])
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": cells1 / dt / 1e9, "unit": UNIT, "cores": 1, "kind": kind, "seconds": dt,
+                                   "sample": "the same region, ScoreAlignments of the reference on one core",
+                                   "exact_mode_bit_identical": bool(np.array_equal(want, exact))}
+        poreseqcpp.close_regions(nrs)
+        return out
+    finally:
+        ctx.close(); cx.close()
+
+
+def leg_variant(rank, world, device, dist, torch):
+    """BASELINE.json configs[3], ONE of its six regions: ScoreMutations (poreseq variant -m) of 1200 single / multi-base
+    edits at scoring_width 100 against a 10 kb region at 100x coverage (200 events).  With N GPUs the region's events are
+    split across the ranks and the per-mutation sums are combined over NCCL inside the library, in event order
+    (ps_score_mutations_sharded: bit-identical to one GPU).  This is the problem of tests/golden/f_c3.npz."""
+    from poreseq_b200 import poreseqcpp, sharding
+    kw = dict(length=10000, coverage=100, seed=17)
+    reg = synth.make_region(**kw)
+    st, og, mu = synth.random_mutations(reg.sequence, 1200, np.random.default_rng(4242), max_len=4)
+    ctx = poreseqcpp.Context(device)
+    ctx.set_precision("fast")
+    try:
+        if world > 1:
+            uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                uid = torch.frombuffer(bytearray(poreseqcpp.comm_unique_id()), dtype=torch.uint8).cuda()
+            dist.broadcast(uid, 0)
+            ctx.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world, ordered=True)
+            shard = sharding.RegionShard(reg, rank, world)
+            nr = poreseqcpp.NativeRegion(ctx, shard.sequence, shard.events, shard.params)
+            call = lambda: nr.score_mutations_sharded(st, og, mu)
+        else:
+            nr = poreseqcpp.NativeRegion(ctx, reg.sequence, reg.events, reg.params)
+            call = lambda: nr.score_mutations(st, og, mu)
+        call()                                               # buffers grow on the first call
+        nr.close()
+        if world > 1:
+            nr = poreseqcpp.NativeRegion(ctx, shard.sequence, shard.events, shard.params)
+        else:
+            nr = poreseqcpp.NativeRegion(ctx, reg.sequence, reg.events, reg.params)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        got = call()
+        dt = time.perf_counter() - t0
+        wide, narrow = ctx.last_cells()
+        t = torch.tensor([dt, wide + narrow], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t[0:1], op=dist.ReduceOp.MAX)
+            dist.all_reduce(t[1:2], op=dist.ReduceOp.SUM)
+        out = {"config": "poreseq variant -m: ScoreMutations of 1200 edits (<= 4 bases) at scoring_width 100, one 10 kb region x 100x "
+                         "(200 events) = one of the six regions of BASELINE.json configs[3]; events split over %d GPU(s), sums "
+                         "combined in event order over NCCL inside the library" % world,
+               "seconds": t[0].item(), "mutations_per_s": 1200 / t[0].item(), "gcups": t[1].item() / t[0].item() / 1e9,
+               "n_gpus": world, "events_per_rank": len(nr.n_levels), "precision": "fast"}
+        z = golden("c3")
+        if z is not None:
+            want = z["scores"]
+            rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-300)
+            out["parity_vs_reference"] = {"accept_reject_identical": bool(np.array_equal(got >= 0, want >= 0)),
+                                          "scores_ge0_bit_identical": bool(np.array_equal(got[want >= 0], want[want >= 0])),
+                                          "max_rel_err": float(rel.max()), "tolerance": 1e-4,
+                                          "golden": "tests/golden/f_c3.npz (reference C++, %.0f s on one core incl. input generation)" % float(z["seconds"])}
+            out["cpu_baseline"] = {"seconds": float(z["seconds"]), "cores": 1, "kind": "reference",
+                                   "sample": "recorded when the golden was generated (not timed in this run): the reference's ScoreMutations + ScoreAlignments on the same region"}
+        nr.close()
+        if world > 1:
+            ctx.comm_destroy()
+        return out
+    finally:
+        ctx.close()
+
+
+def leg_polish(rank, world, device, dist, torch, per_rank=2, in_flight=2):
+    """BASELINE.json configs[4] in small: consensus polish of 10 kb regions at 50x coverage (100 events each) read from an
+    event-pack file, `per_rank` regions per GPU through ps_consensus_batch (the whole Mutate.py loop below the C-ABI),
+    regions dealt out to the ranks round robin.  Region 0 is the problem of tests/golden/f_c4.npz."""
+    import tempfile
+    from poreseq_b200 import drivers, eventpack, poreseqcpp
+    seeds = [11 + 100 * k for k in range(world * per_rank)][rank::world]
+    regs = [synth.make_region(10000, 50, seed=sd, draft_error=0.10) for sd in seeds]
+    path = os.path.join(tempfile.gettempdir(), "poreseq_b200_polish_%d_%d.pack" % (os.getpid(), rank))
+    eventpack.write_pack(path, regs)
+    ctx = poreseqcpp.Context(device)
+    ctx.set_precision("fast")
+    try:
+        warm = synth.make_region(2000, 50, seed=5, draft_error=0.05)
+        drivers.consensus_native([warm] * 1, ctx=ctx, in_flight=1)
+        packs = list(eventpack.read_pack(path))
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = drivers.consensus_native(packs, ctx=ctx, reps=4, in_flight=in_flight)
+        dt = time.perf_counter() - t0
+        accs = [poreseqcpp.swalign(r[0], g.truth[150:-150])[0] for r, g in zip(res, regs)]
+        t = torch.tensor([dt, float(sum(accs)), float(len(regs))], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t[0:1], op=dist.ReduceOp.MAX)
+            dist.all_reduce(t[1:3], op=dist.ReduceOp.SUM)
+        out = {"config": "consensus polish (Mutate.py loop, ps_consensus_batch) of %d regions of 10 kb x 50x per GPU from an event-pack "
+                         "file, %d in flight, fast precision (BASELINE.json configs[4] is ~512 such regions)" % (per_rank, in_flight),
+               "value": 10.0 * t[2].item() / t[0].item(), "unit": "kb/s", "seconds": t[0].item(), "regions": int(t[2].item()),
+               "n_gpus": world, "mean_accuracy_pct": t[1].item() / t[2].item()}
+        z = golden("c4")
+        if z is not None and rank == 0:
+            want = str(z["stage_seqs"][-1])
+            out["parity_vs_reference"] = {"region": "seed 11", "identical_final_sequence": bool(res[0][2][-1][1] == want),
+                                          "identical_stages": bool([s[1] for s in res[0][2]] == z["stage_seqs"].tolist())}
+            out["cpu_baseline"] = {"value": 10.0 / float(z["seconds"]), "unit": "kb/s", "seconds": float(z["seconds"]), "cores": 1,
+                                   "kind": "reference", "sample": "recorded when the golden was generated (not timed in this run): the same loop on region seed 11"}
+        return out
+    finally:
+        ctx.close()
+        try:
+            os.remove(path)
+        except OSError:
+            pass
 
 
 def recorded_traffic(kernel, regions):
@@ -291,10 +438,12 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--min-seconds", type=float, default=2.0, help="each timed region repeats its block of --steps steps until this much time has been measured")
     ap.add_argument("--regions", type=int, default=44, help="1 kb regions per GPU per step (44 x 40 fill CTAs ~ 4 waves of 148 SMs x 3)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-consensus", action="store_true", help="skip the secondary consensus kb/s measurement")
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs[0] / configs[3] / configs[4] legs")
     ap.add_argument("--driver", default="threads", choices=["threads", "pipeline"],
                     help="e2e region: --drivers host threads with two contexts each (threads) or one host thread pipelining "
                          "--contexts contexts (pipeline)")
@@ -425,10 +574,13 @@ def main():
             out = end(begin(ctxs[0]), record)
         return out
 
-    # warm-up: at least W steps and at least two on every context (each context owns its staging and device buffers,
-    # which grow on first use)
-    n_warm = max(args.warmup, 3, 2 * len(ctxs))
-    out = run_steps(n_warm, False)
+    # priming (not counted as warm-up): two steps on every context -- each context owns its staging and device buffers,
+    # which grow on first use; then exactly --warmup warm-up steps
+    n_prime = 2 * len(ctxs)
+    out = run_steps(n_prime, False)
+    n_warm = max(args.warmup, 0)
+    if n_warm:
+        out = run_steps(n_warm, False)
     # bytes the library copied for one step: staged level records, band centres, mutation tables, models ... up;
     # realigned events (ref_align, ref_like, ref_index) and scores down
     host_in = h2d
@@ -436,25 +588,60 @@ def main():
 
     sampler = ClockSampler(local_rank)
     sampler.start()
+    # Both timed regions run BLOCKS of exactly K steps, each block bracketed by barrier + synchronize, until at least
+    # --min-seconds have been timed (at most 25 blocks); the reported step time is the MEDIAN block, the spread is kept.
     # timed region 1 (`value`): K steps one after the other on one context; the kernel phases are timed with
     # CUDA events on the library's stream, nothing else runs on the GPU, the inputs of a phase are in HBM
-    barrier()
-    run_steps_serial(args.steps, True)
-    barrier()
+    kernel_keys = ["centres", "forward", "backward", "backtrace", "join", "mutscore", "reduce"]
+    dev_blocks, phase_blocks = [], []
+
+    def blocks_wanted(first_seconds):
+        """How many blocks every rank runs in all: enough for --min-seconds, the same number everywhere (max over ranks)."""
+        n = int(min(25, max(1, -(-args.min_seconds // max(first_seconds, 1e-4)))))
+        if world > 1:
+            t = torch.tensor([n], dtype=torch.int64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            n = int(t.item())
+        return n
+
+    def device_block():
+        phase.clear()
+        barrier()
+        t0 = time.perf_counter()
+        run_steps_serial(args.steps, True)
+        barrier()
+        dev_blocks.append(sum(phase[k] for k in kernel_keys) / args.steps)
+        phase_blocks.append(dict(phase))
+        return time.perf_counter() - t0
+
+    for _ in range(blocks_wanted(device_block()) - 1):
+        device_block()
     # timed region 2 (`e2e`): K steps through the C-ABI from host buffers, several contexts in flight so that the
     # host staging and H2D of step k+1 overlap the kernels of step k; wall clock around barrier + synchronize
+    wall_blocks = []
     launches0 = sum(c.launch_count() for c in ctxs)
-    barrier()
-    t0 = time.perf_counter()
-    (run_steps_threads if args.driver == "threads" else run_steps)(args.steps, False)
-    barrier()
-    wall = time.perf_counter() - t0
-    launches = sum(c.launch_count() for c in ctxs) - launches0
+
+    def e2e_block():
+        barrier()
+        t0 = time.perf_counter()
+        (run_steps_threads if args.driver == "threads" else run_steps)(args.steps, False)
+        barrier()
+        wall_blocks.append((time.perf_counter() - t0) / args.steps * 1e3)
+        return time.perf_counter() - t0
+
+    for _ in range(blocks_wanted(e2e_block()) - 1):
+        e2e_block()
+    launches = (sum(c.launch_count() for c in ctxs) - launches0) // len(wall_blocks)
     sampler.stop()
 
-    kernel_keys = ["centres", "forward", "backward", "backtrace", "join", "mutscore", "reduce"]
-    dev_ms = sum(phase[k] for k in kernel_keys) / args.steps
-    wall_ms = wall / args.steps * 1e3
+    def median(v):
+        v = sorted(v)
+        return v[len(v) // 2]
+
+    mid = sorted(range(len(dev_blocks)), key=lambda k: dev_blocks[k])[len(dev_blocks) // 2]
+    phase = phase_blocks[mid]
+    dev_ms = dev_blocks[mid]
+    wall_ms = median(wall_blocks)
     times = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -487,6 +674,9 @@ def main():
     line = {
         "metric": METRIC, "value": total_cells / (dev_ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": n_warm, "ms_per_step": wall_ms, "higher_is_better": True,
+        "timing": {"blocks_of_steps": {"device": len(dev_blocks), "e2e": len(wall_blocks)}, "priming_steps": n_prime,
+                   "device_ms_per_step": {"median": dev_ms, "min": min(dev_blocks), "max": max(dev_blocks)},
+                   "e2e_ms_per_step": {"median": wall_ms, "min": min(wall_blocks), "max": max(wall_blocks)}},
         "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64" if args.precision == "fast" else "f64", "data": "synthetic",
         "config": {"workload": "ScorePoints (FindPointMutations+ScoreMutations) on 1 kb regions x 10x coverage, "
                                "point_width 20, realign_width 300 (BASELINE.json configs[1])",
@@ -513,6 +703,7 @@ def main():
                      "achieved": achieved_ops, "peak": peak_ops, "unit": "Tlane-op/s", "frac": achieved_ops / peak_ops,
                      "ops_per_cell": OPS_PER_CELL, "clock_mhz_under_load": clock_mhz, "peak_source": peak_src,
                      "traffic": recorded_traffic(dom_kernel, args.regions),
+                     "traffic_source": "recorded: dram__bytes_read+write per launch from the committed ncu --set full capture of this batch size (profiles/r1_traffic.json), not sampled in this run",
                      "note": "SURVEY.md 8d definition (24 FP32 lane-ops per cell); the dominant kernel computes in FP64, see roofline_fp64"},
         "roofline_fp64": {"bound": "fp64-pipe", "kernel": dom_kernel, "achieved": fp64_achieved, "peak": fp64_peak,
                           "unit": "T fp64-op/s", "frac": fp64_achieved / fp64_peak if fp64_peak else 0.0,
@@ -521,45 +712,108 @@ def main():
                          "peak": hbm_peak, "unit": "GB/s", "frac": dom_bytes / dom_s / 1e9 / hbm_peak if dom_s > 0 else 0.0,
                          "peak_source": peak_src, "traffic": recorded_traffic(dom_kernel, args.regions)},
     }
-    single = None
+    for c in ctxs[1:]:
+        c.close()
+    extras_errors = {}
+
+    def attempt(name, fn):
+        try:
+            return fn()
+        except Exception as ex:                                   # an extra leg must not cost the headline line
+            extras_errors[name] = "%s: %s" % (type(ex).__name__, ex)
+            return None
+
+    if rank == 0:
+        line["fast_mode_parity"] = attempt("fast_mode_parity", lambda: fast_mode_error(ctxs[0], local_rank))
+    ctxs[0].close()
+    if rank == 0 and not args.no_extras:
+        line["score_events"] = attempt("score_events", lambda: leg_score_events(local_rank, sms, sm_max_mhz, cpu=not args.no_cpu_baseline))
     if not args.no_consensus:
-        # consensus kb/s, throughput form, on every rank: CONS_REGIONS regions of 1 kb x 10x per GPU, 8 in flight
-        for c in ctxs:
-            c.close()
+        from poreseq_b200 import drivers
+        # consensus kb/s (BASELINE.json's second headline): the Mutate.py loop below the C-ABI (ps_consensus_batch),
+        # CONS_REGIONS regions of 1 kb x 10x per GPU, CONS_IN_FLIGHT of them side by side on every rank
+        def cons_throughput():
+            cctx = poreseqcpp.Context(local_rank)
+            cctx.set_precision("fast")
+            try:
+                warm = [synth.make_region(1000, 10, seed=9000 + k, draft_error=0.10) for k in range(CONS_IN_FLIGHT)]
+                drivers.consensus_native(warm, ctx=cctx, in_flight=CONS_IN_FLIGHT)          # untimed: every lane allocates its buffers
+                regs = [synth.make_region(1000, 10, seed=500 + CONS_REGIONS * rank + k, draft_error=0.10) for k in range(CONS_REGIONS)]
+                times = []
+                for _ in range(3):
+                    barrier()
+                    t0 = time.perf_counter()
+                    res = drivers.consensus_native(regs, ctx=cctx, in_flight=CONS_IN_FLIGHT)
+                    barrier()
+                    times.append(time.perf_counter() - t0)
+                acc = sum(poreseqcpp.swalign(r[0], g.truth)[0] for r, g in zip(res, regs)) / len(regs)
+                return times, acc
+            finally:
+                cctx.close()
+        got = attempt("consensus_throughput", cons_throughput)
+        if got is not None:
+            times, acc = got
+            tt = torch.tensor(times + [acc], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tt[0:3], op=dist.ReduceOp.MAX)
+                dist.all_reduce(tt[3:4], op=dist.ReduceOp.SUM)
+            tl = sorted(tt[0:3].tolist())
+            line["consensus"] = {"throughput": {"value": float(CONS_REGIONS) * world / tl[1], "unit": "kb/s", "n_gpus": world,
+                                                "seconds": {"median": tl[1], "min": tl[0], "max": tl[2]},
+                                                "mean_accuracy_pct": tt[3].item() / world,
+                                                "config": "consensus loop (Mutate.py policy below the C-ABI, ps_consensus_batch) on %d regions of 1 kb x 10x "
+                                                          "per GPU (drafts with 10%% errors), %d regions in flight per GPU, fast precision; "
+                                                          "3 passes, max over ranks each" % (CONS_REGIONS, CONS_IN_FLIGHT)}}
+        else:
+            line["consensus"] = {}
         if rank == 0 and world == 1:
-            # consensus kb/s beside the GCUPS headline: configs[2] size on the GPU, the README's own 1 kb x 10x case
-            # on both sides (the reference needs ~25 s for it; 10 kb x 30x would take it the better part of an hour)
-            big, _ = consensus_gpu(10000, 30, seed=7)
-            small, seq_gpu = consensus_gpu(1000, 10, seed=7)
-            single = (big, small, seq_gpu)
-        cons_ctxs = [poreseqcpp.Context(local_rank) for _ in range(8)]
-        for c in cons_ctxs:
-            c.set_precision("fast")
-        consensus_throughput(cons_ctxs, 8, 1000, 10, seed0=9000)       # untimed: every context allocates its buffers
-        barrier()
-        dt, acc = consensus_throughput(cons_ctxs, CONS_REGIONS, 1000, 10, seed0=500 + CONS_REGIONS * rank)
-        for c in cons_ctxs:
-            c.close()
-        tt = torch.tensor([dt, acc], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt[0:1], op=dist.ReduceOp.MAX)
-            dist.all_reduce(tt[1:2], op=dist.ReduceOp.SUM)
-        line["consensus"] = {"throughput": {"value": float(CONS_REGIONS) * world / tt[0].item(), "unit": "kb/s", "n_gpus": world,
-                                            "seconds": tt[0].item(), "mean_accuracy_pct": tt[1].item() / world,
-                                            "config": "consensus loop (Mutate.py policy) on %d regions of 1 kb x 10x per GPU "
-                                                      "(drafts with 10%% errors), 8 regions in flight per GPU, fast precision" % CONS_REGIONS}}
+            def cons_single(length, coverage, seed, gold):
+                cctx = poreseqcpp.Context(local_rank)
+                cctx.set_precision("fast")
+                try:
+                    drivers.consensus_native([synth.make_region(300, 5, seed=99, draft_error=0.05)], ctx=cctx, in_flight=1)
+                    reg = synth.make_region(length, coverage, seed=seed, draft_error=0.10)
+                    t0 = time.perf_counter()
+                    seq, acc, stages = drivers.consensus_native([reg], ctx=cctx, in_flight=1, refseqs=[reg.truth])[0]
+                    dt = time.perf_counter() - t0
+                    out = {"value": length / 1000.0 / dt, "unit": "kb/s", "seconds": dt, "accuracy_pct": acc,
+                           "draft_accuracy_pct": poreseqcpp.swalign(reg.sequence, reg.truth)[0],
+                           "config": "consensus loop (ps_consensus) on a %d b region at %dx coverage (draft with 10%% errors), fast precision" % (length, coverage)}
+                    z = golden(gold) if gold else None
+                    if z is not None:
+                        out["parity_vs_reference"] = {"identical_stages": bool([st[1] for st in stages] == z["stage_seqs"].tolist()),
+                                                      "golden": "tests/golden/f_%s.npz" % gold}
+                        out["cpu_baseline"] = {"value": length / 1000.0 / float(z["seconds"]), "unit": "kb/s", "seconds": float(z["seconds"]),
+                                               "cores": 1, "kind": "reference",
+                                               "sample": "recorded when the golden was generated (not timed in this run): the same loop, same region"}
+                    return out, seq
+                finally:
+                    cctx.close()
+            big = attempt("consensus_10kb", lambda: cons_single(10000, 30, 7, "c2"))
+            small = attempt("consensus_1kb", lambda: cons_single(1000, 10, 7, None))
+            if big is not None:
+                line["consensus"]["configs[2] 10 kb x 30x"] = big[0]
+            if small is not None:
+                line["consensus"]["1 kb x 10x"] = small[0]
+                if not args.no_cpu_baseline:
+                    from oracle import binding
+                    if binding.available("ref"):
+                        def cpu_small():
+                            cpu, seq_cpu = consensus_cpu(1000, 10, seed=7)
+                            cpu["identical_consensus"] = bool(seq_cpu == small[1])
+                            return cpu
+                        line["consensus"]["1 kb x 10x"]["cpu_baseline"] = attempt("consensus_1kb_cpu", cpu_small)
+    if not args.no_extras:
+        v = attempt("variant", lambda: leg_variant(rank, world, local_rank, dist, torch))
+        pl = attempt("polish", lambda: leg_polish(rank, world, local_rank, dist, torch))
+        if rank == 0:
+            line["variant_configs3"] = v
+            line["polish_configs4"] = pl
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = run_cpu_baseline()
-        if world == 1 and not args.no_consensus and single is not None:
-            big, small, seq_gpu = single
-            line["consensus"].update({"configs[2] 10 kb x 30x": big, "1 kb x 10x": small})
-            if not args.no_cpu_baseline:
-                from oracle import binding
-                if binding.available("ref"):
-                    cpu, seq_cpu = consensus_cpu(1000, 10, seed=7)
-                    cpu["identical_consensus"] = bool(seq_cpu == seq_gpu)
-                    line["consensus"]["1 kb x 10x"]["cpu_baseline"] = cpu
+            line["cpu_baseline"] = attempt("cpu_baseline", run_cpu_baseline)
+        if extras_errors:
+            line["extras_errors"] = extras_errors
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
