@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libporeseq_b200.so")
-SOURCES = ["ps_host.cu", "ps_drivers.cu", "ps_viterbi.cu", "ps_sw.cu", "ps_pack.cu", "ps_comm.cu", "ps_swhost.cpp"]
+SOURCES = ["ps_host.cu", "ps_drivers.cu", "ps_viterbi.cu", "ps_sw.cu", "ps_pack.cu", "ps_comm.cu", "ps_lockstep.cu", "ps_swhost.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-fmad=false", "--shared", "-Xcompiler", "-fPIC,-ffp-contract=off,-O3",
               "-Xptxas", "-v", "-ldl"]

@@ -345,6 +345,8 @@ ps_ctx::~ps_ctx()
 {
     for (ps_ctx* h : helpers) delete h;
     helpers.clear();
+    for (ps_ctx* h : group_ctx) delete h;
+    group_ctx.clear();
     if (!ready) return;
     cudaSetDevice(device);
     ps_comm_destroy(this);
@@ -1602,26 +1604,88 @@ int ps_score_mutation_list(ps_region* R, std::vector<HostMut>& muts, double bias
     return PS_OK;
 }
 
+// The same for several regions in ONE job (the consensus loop in lockstep over regions, ps_lockstep.cu): lists[r] is
+// scored against regs[r].  FAST precision: a region whose list ends up with exactly tied non-negative scores is re-scored
+// exactly from the alignments it started with (see ps_score_mutation_list), in one second job for all such regions.
+int ps_score_mutation_lists(ps_ctx* ctx, const std::vector<ps_region*>& regs, const std::vector<std::vector<HostMut>*>& lists)
+{
+    if (regs.empty()) return PS_OK;
+    std::vector<MutSpec> per(regs.size());
+    for (size_t r = 0; r < regs.size(); r++) per[r].list = lists[r];
+    const bool fast = ctx->precision == PS_PRECISION_FAST;
+    struct Seed { LevelVec ref_align; bool ri_empty; int refstart, refend; };
+    std::vector<std::vector<Seed>> seeds;
+    if (fast)
+    {
+        seeds.resize(regs.size());
+        ps_parallel_for((int)regs.size(), [&](int r) {
+            seeds[r].resize(regs[r]->events.size());
+            for (size_t e = 0; e < regs[r]->events.size(); e++)
+            {
+                const HostEvent& he = regs[r]->events[e];
+                seeds[r][e].ref_align = he.ref_align; seeds[r][e].ri_empty = he.ri_empty;
+                seeds[r][e].refstart = he.refstart; seeds[r][e].refend = he.refend;
+            }
+        });
+    }
+    std::vector<double> sc;
+    TRY(run_job(ctx, regs, &per, nullptr, &sc));
+    size_t at = 0;
+    std::vector<ps_region*> again;
+    std::vector<std::vector<HostMut>*> again_lists;
+    for (size_t r = 0; r < regs.size(); r++)
+    {
+        std::vector<HostMut>& v = *lists[r];
+        for (size_t i = 0; i < v.size(); i++) v[i].score = sc[at + i];
+        at += v.size();
+        if (!fast) continue;
+        std::vector<double> keep;
+        for (const HostMut& m : v) if (m.score >= 0) keep.push_back(m.score);
+        std::sort(keep.begin(), keep.end());
+        if (std::adjacent_find(keep.begin(), keep.end()) == keep.end()) continue;
+        for (size_t e = 0; e < regs[r]->events.size(); e++)
+        {
+            HostEvent& he = regs[r]->events[e];
+            he.ref_align = seeds[r][e].ref_align; he.ri_empty = seeds[r][e].ri_empty;
+            he.refstart = seeds[r][e].refstart; he.refend = seeds[r][e].refend;
+            he.ri_stale = !he.ri_empty;
+            if (he.ri_empty) he.ref_index.clear();
+        }
+        again.push_back(regs[r]); again_lists.push_back(lists[r]);
+    }
+    if (!again.empty())
+    {
+        ctx->precision = PS_PRECISION_EXACT;
+        const int rc = ps_score_mutation_lists(ctx, again, again_lists);
+        ctx->precision = PS_PRECISION_FAST;
+        if (rc) return rc;
+        ctx->exact_reruns += (long long)again.size();
+    }
+    return PS_OK;
+}
+
 static bool by_score_desc(const HostMut& a, const HostMut& b) { return a.score > b.score; }
 
 // cpp/MakeMutations.cpp:74-146.  std::sort with the same ordering predicate on the same element
 // order reproduces the reference's (unstable) tie placement.
-int ps_make_mutation_list(ps_region* R, std::vector<HostMut> muts, int* nbases)
+// One pass (:83-139): accepts in score order, invalidates neighbours, shifts later starts; `deferred` receives the
+// mutations the reference would score again (:104-108, :142-143) -- the caller does so when there are more than ten.
+void ps_make_mutation_pass(ps_region* R, std::vector<HostMut> muts, int* changed_out, std::vector<HostMut>* deferred)
 {
     const int spacing = 10;
     int changed = 0;
+    deferred->clear();
     std::sort(muts.begin(), muts.end(), by_score_desc);
     while (!muts.empty() && muts.back().score < 0) muts.pop_back();
-    *nbases = 0;
-    if (muts.empty()) return PS_OK;
-    std::vector<HostMut> deferred;
+    *changed_out = 0;
+    if (muts.empty()) return;
     // the accepted edits are applied to a working copy of the bases; the region's sequence (and its 5-mer states) is
     // replaced once after the loop -- nothing inside the loop reads the states (0.08 ms per accept at 10 kb otherwise)
     std::string seq = R->bases;
     for (size_t i = 0; i < muts.size(); i++)
     {
         HostMut& a = muts[i];
-        if (a.score < 0) { deferred.push_back(a); continue; }
+        if (a.score < 0) { deferred->push_back(a); continue; }
         seq = ps_apply_mutation(seq, a.start, a.orig, a.mut);
         changed += (int)std::max(a.orig.size(), a.mut.size());
         for (size_t j = i + 1; j < muts.size(); j++)
@@ -1635,6 +1699,14 @@ int ps_make_mutation_list(ps_region* R, std::vector<HostMut> muts, int* nbases)
         }
     }
     R->set_sequence(seq);
+    *changed_out = changed;
+}
+
+int ps_make_mutation_list(ps_region* R, std::vector<HostMut> muts, int* nbases)
+{
+    int changed = 0;
+    std::vector<HostMut> deferred;
+    ps_make_mutation_pass(R, std::move(muts), &changed, &deferred);
     if (deferred.size() > 10)
     {
         int more = 0;
@@ -1681,6 +1753,8 @@ ps_ctx* ps_create(int device)
     ctx->no_warp = getenv("PORESEQ_B200_NO_WARP") != nullptr;
     ctx->sw_host = getenv("PORESEQ_B200_SW_HOST") != nullptr;
     ctx->no_stage = getenv("PORESEQ_B200_NO_STAGE") != nullptr;
+    if (const char* e = getenv("PORESEQ_B200_CONSENSUS")) ctx->threads_consensus = std::string(e) == "threads";
+    if (const char* e = getenv("PORESEQ_B200_GROUPS")) ctx->consensus_groups = std::max(1, atoi(e));
     if (const char* e = getenv("PORESEQ_B200_S32_WARPS")) ctx->s32_warps = std::max(2, std::min(atoi(e), PS_SCORE32_MAX_WARPS));
     if (const char* e = getenv("PORESEQ_B200_BAND_BUDGET")) ctx->band_budget = atof(e);
     if (const char* e = getenv("PORESEQ_B200_TAU")) ctx->tau_override = atof(e);

@@ -62,6 +62,8 @@ struct ps_ctx
     bool no_warp = false;                     // PORESEQ_B200_NO_WARP: never use the warp-per-pair exact kernel
     bool sw_host = false;                     // PORESEQ_B200_SW_HOST: FindMutations' Smith-Waterman maps on the host
     double band_budget = 0;                   // PORESEQ_B200_BAND_BUDGET: bytes of band storage per sub-batch (0: default)
+    int consensus_groups = 0;                 // PORESEQ_B200_GROUPS: lockstep groups of ps_consensus_batch running side by side (0: chosen by batch size)
+    bool threads_consensus = false;           // PORESEQ_B200_CONSENSUS=threads: ps_consensus_batch as regions in flight on threads instead of lockstep (A/B)
     bool no_stage = false;                    // PORESEQ_B200_NO_STAGE: k_score_f32 reads level records through L1 instead of a TMA-staged copy (A/B)
     int s32_warps = 0;                        // PORESEQ_B200_S32_WARPS: warps per CTA of k_score_f32 (0: chosen by batch size)
     double tau_override = -1;                 // PORESEQ_B200_TAU: FAST-mode re-score threshold (diagnostics; < 0: derived)
@@ -70,6 +72,7 @@ struct ps_ctx
     std::map<std::string, PinBuf> pins;       // grow-only named pinned host buffers
     template <class T> PinVec<T> pinned(const char* name) { PinVec<T> v; v.buf = &pins[name]; v.n = 0; return v; }
 
+    std::vector<ps_ctx*> group_ctx;           // ps_consensus_batch: the contexts of the lockstep groups 1.. (group 0 is this context); each has helpers of its own
     std::vector<ps_ctx*> helpers;             // ps_consensus_batch: further contexts (stream + buffers) on the same device, one per region in flight
     int init();                               // lazy CUDA initialisation
     int ensure(DevBuf& b, size_t bytes);
@@ -163,6 +166,9 @@ std::string ps_apply_mutation(const std::string& bases, int start, const std::st
 std::vector<HostMut> ps_point_mutations(const ps_region* R);
 int ps_score_mutation_list(ps_region* R, std::vector<HostMut>& muts, double bias = -1e-6, int shard_total_events = 0);
 int ps_make_mutation_list(ps_region* R, std::vector<HostMut> muts, int* nbases);
+void ps_make_mutation_pass(ps_region* R, std::vector<HostMut> muts, int* changed_out, std::vector<HostMut>* deferred);
+int ps_score_mutation_lists(ps_ctx* ctx, const std::vector<ps_region*>& regs, const std::vector<std::vector<HostMut>*>& lists);
+int ps_consensus_lockstep(ps_ctx* ctx, ps_region* const* regions, int n_regions, int reps, int point_width, int in_flight);
 
 struct SWResult                               // cpp/swlib.h:25-33
 {
@@ -176,6 +182,8 @@ SWResult psi_swfull(const std::string& s1, const std::string& s2);
 int psi_swfull_batch(ps_ctx* ctx, const std::string& s1, const std::vector<std::string>& others, std::vector<SWResult>& out);
 SWResult psi_map_alignments_with(ps_region* R, const std::string& newseq, SWResult al);
 void psi_fillinds(SWResult& al);
+void psi_pick_candidates(const std::string& bases, const std::vector<double>& base, const std::vector<std::string>& seeds,
+                         const std::vector<const std::vector<double>*>& profs, std::vector<SWResult>& als, std::vector<HostMut>& found);
 SWResult psi_map_alignments(ps_region* R, const std::string& newseq);
 // forward fill + backtrace of every event of every region (ScoreAlignments); per-region score
 // vectors and per-base likelihood profiles on request
