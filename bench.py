@@ -402,7 +402,7 @@ def recorded_traffic(kernel, regions):
     return None
 
 
-def run_reference_arm(args, rank, world):
+def run_reference_arm(args, rank, world, out=sys.stdout):
     """--impl reference: the reference CPU path on all host cores, one process per region."""
     if rank != 0:
         return
@@ -429,11 +429,23 @@ def run_reference_arm(args, rank, world):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 # ------------------------------------------------------------------------------------------------
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner on the
+    first communicator when NCCL_DEBUG asks for it): point fd 1 at stderr for the whole run and keep the real stdout
+    for the line itself."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    real_stdout = claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
@@ -461,7 +473,7 @@ def main():
         # bounded: each step is `cores` regions (~5 s); cap the step count so the run ends in minutes
         args.steps_ref = max(1, min(args.steps, 6))
         args.warmup_ref = max(0, min(args.warmup, 1))
-        run_reference_arm(args, rank, world)
+        run_reference_arm(args, rank, world, real_stdout)
         return
 
     # the library's host worker threads (marshalling, per-level logs, band planning): share the box's cores between
@@ -814,7 +826,8 @@ def main():
             line["cpu_baseline"] = attempt("cpu_baseline", run_cpu_baseline)
         if extras_errors:
             line["extras_errors"] = extras_errors
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 
