@@ -455,6 +455,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-consensus", action="store_true", help="skip the secondary consensus kb/s measurement")
+    ap.add_argument("--e2e-path", default="direct", choices=["direct", "handles"],
+                    help="direct: ps_score_points_direct from the host buffers (scores only, like PSAlign.ScorePoints); handles: native region objects per step")
     ap.add_argument("--no-extras", action="store_true", help="skip the configs[0] / configs[3] / configs[4] legs")
     ap.add_argument("--driver", default="threads", choices=["threads", "pipeline"],
                     help="e2e region: --drivers host threads with two contexts each (threads) or one host thread pipelining "
@@ -480,7 +482,7 @@ def main():
     # the ranks of this node instead of 8 per rank (PORESEQ_B200_THREADS is the library's own knob)
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     if "PORESEQ_B200_THREADS" not in os.environ:
-        share = (os.cpu_count() or 8) // max(local_world, 1)
+        share = (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 8)) // max(local_world, 1)
         if args.driver == "threads":
             share -= max(1, args.drivers) - 1                 # the driver threads marshal too
         os.environ["PORESEQ_B200_THREADS"] = str(max(1, min(8, share)))
@@ -520,7 +522,12 @@ def main():
     # every step marshals them into fresh native regions: 1 ps_region_create + 1 ps_region_add_events each
     packs = [poreseqcpp.PackedRegion(r.sequence, r.events, r.params) for r in regions]
 
+    # --e2e-path direct (default): ps_score_points_direct -- PSAlign.ScorePoints straight from the host buffers, scores out
+    # (the reference drops ScorePoints' realignment too, pyx:278-308); handles: ps_regions_create + ps_score_points_batch
+    # + ps_regions_destroy per step (native region objects, realigned events copied back into them)
     def begin(c):
+        if args.e2e_path == "direct":
+            return poreseqcpp.PendingDirect(c, packs, "point_width")
         nrs = poreseqcpp.native_regions_from_packed(c, packs, "point_width")
         return poreseqcpp.score_points_batch_begin(c, nrs)
 
@@ -529,7 +536,8 @@ def main():
         if record:
             for k, v in p.ctx.last_timing().items():
                 phase[k] = phase.get(k, 0.0) + v
-        poreseqcpp.close_regions(p.regions)
+        if args.e2e_path != "direct":
+            poreseqcpp.close_regions(p.regions)
         return out
 
     def run_steps(count, record):
@@ -696,6 +704,7 @@ def main():
                    "mutations_per_region": 8 * (REGION_LEN - 4), "cells_per_step_per_gpu": step_cells,
                    "l2": "band working set %.0f MB per step exceeds the 126 MB L2" % (wide_cells * 12.25 / 1e6),
                    "host_threads_per_rank": int(os.environ["PORESEQ_B200_THREADS"]),
+                   "entry_point": "ps_score_points_direct_begin/_end (host arrays in, scores out; no region handles)" if args.e2e_path == "direct" else "ps_regions_create + ps_score_points_batch_begin/_end + ps_regions_destroy",
                    "pipelining": ("%d host threads x 2 contexts: host staging and H2D of the other steps overlap the kernels of step k" % (len(ctxs) // 2)
                                   if args.driver == "threads" else
                                   "%d contexts, one host thread: host staging and H2D of the next steps overlap the kernels of step k" % len(ctxs)),

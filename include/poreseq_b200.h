@@ -217,6 +217,16 @@ int         ps_score_points_batch(ps_region* const* regions, int n_regions, int 
 int         ps_score_points_batch_begin(ps_region* const* regions, int n_regions, int cap,
                                         int* n_out, long long* off_out, int* start, char* orig, char* mut);
 int         ps_score_points_batch_end(ps_ctx* ctx, double* scores);
+/* PSAlign.ScorePoints of n regions straight from the caller's arrays -- poreseq/_poreseqcpp.pyx:278-308: PythonToAlignData,
+ * FindPointMutations, ScoreMutations, the scores; the realignment is dropped there (no UpdatePythonEvents), so nothing but
+ * the scores comes back here either.  No region handles are made: the level arrays of `desc` are read where they lie (they
+ * must stay valid until _end returns), nothing is copied, no alignment travels back from the device.  Outputs as in
+ * ps_score_points_batch.  _begin / _end: the asynchronous halves, one batch in flight per context. */
+int         ps_score_points_direct(ps_ctx* ctx, int n_regions, const ps_region_desc* desc, int cap, int* n_out,
+                                   long long* off_out, int* start, char* orig, char* mut, double* scores);
+int         ps_score_points_direct_begin(ps_ctx* ctx, int n_regions, const ps_region_desc* desc, int cap, int* n_out,
+                                         long long* off_out, int* start, char* orig, char* mut);
+int         ps_score_points_direct_end(ps_ctx* ctx, double* scores);
 
 /* ---- candidate discovery and the consensus iteration ------------------------------------------- */
 /* vector<MutInfo> FindMutations(AlignData&, const vector<Sequence>&)   cpp/Mutations.h:18,

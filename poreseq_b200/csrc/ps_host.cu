@@ -391,7 +391,9 @@ std::string ps_apply_mutation(const std::string& bases, int start, const std::st
     return out;
 }
 
-void HostEvent::update_refs()                                // cpp/EventData.h:110-169
+void HostEvent::update_refs() { update_refs_from(ref_align.data()); }
+
+void HostEvent::update_refs_from(const double* ref_align)     // cpp/EventData.h:110-169
 {
     const int n = n0;
     ri_stale = false;
@@ -403,7 +405,7 @@ void HostEvent::update_refs()                                // cpp/EventData.h:
     ri_empty = false;
     refstart = (int)ref_align[lo];
     refend = (int)ref_align[hi];
-    ref_index = ref_align;
+    ref_index.assign(ref_align, ref_align + n);
     const double slope = (ref_align[hi] - ref_align[lo]) / (double)(hi - lo);
     const double icpt = ref_align[lo] - slope * lo;
     int anchor = -1;
@@ -477,6 +479,10 @@ struct Job
     PinVec<char> bases;
     PinVec<LevIn> lev;
     bool fast = false;                           // FP32 pass + exact re-score (PS_PRECISION_FAST)
+    bool scores_only = false;                    // PSAlign.ScorePoints / ScoreMutations semantics (pyx:278-342): scores out, the realignment is dropped --
+                                                 // no D2H of the alignments, nothing scattered into the regions
+    std::vector<ps_region*> owned;               // regions built for this job alone (ps_score_points_direct), deleted with it
+    ~Job() { for (ps_region* r : owned) delete r; }
     bool sharded = false;                        // this job scores ONE rank's block of a region's events (ps_comm.cu): sums combined over NCCL
     int total_events = 0;                        // events of the region over all ranks (sharded FAST: the re-score threshold counts them all)
     double* d_scores2 = nullptr;                 // sharded FAST: totals of the exact pass (dense, only the flagged entries mean anything)
@@ -761,14 +767,14 @@ int Job::build()
         const EvDesc& d = ev[e];
         he.ensure_refs();
         const size_t at = (size_t)d.lev_off, n = (size_t)he.n0;
-        if (he.staged++ == 0 && he.levrec.empty())
+        if ((he.staged++ == 0 && he.levrec.empty()) || he.ext_mean)
         {
             // first batch of this event: (mean, stdv, 3 log stdv) straight into the staging buffer (the log is the only
             // transcendental of the path, cpp/EventData.h:218-220); an event that comes back (Refine's recursion, the
             // consensus loop) caches them next time.  1/stdv and the FP32 records are derived on the device (k_rows).
             LevIn* out = lev.data() + at;
-            const double* mean = he.mean.data();
-            const double* stdv = he.stdv.data();
+            const double* mean = he.ext_mean ? he.ext_mean : he.mean.data();
+            const double* stdv = he.ext_stdv ? he.ext_stdv : he.stdv.data();
             for (size_t k = 0; k < n; k++) { out[k].mean = mean[k]; out[k].stdv = stdv[k]; out[k].lsd3 = 3 * std::log(stdv[k]); }
         }
         else
@@ -1259,7 +1265,7 @@ int Job::download_enqueue()
         MARK(PS_T_TOTAL);
         return PS_OK;
     }
-    if (nl)
+    if (nl && !scores_only)
     {
         CU(cudaMemcpyAsync(ref_align.data(), b.ref_align, nl * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaMemcpyAsync(ref_like.data(), b.ref_like, nl * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1271,7 +1277,7 @@ int Job::download_enqueue()
         CU(cudaMemcpyAsync(re.data(), b.refend, ne * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaMemcpyAsync(best.data(), d_evbest, ne * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     }
-    ctx->d2h_bytes += (long long)(2 * nl * sizeof(double) + ne * (3 * sizeof(int) + sizeof(double)));
+    ctx->d2h_bytes += (long long)((scores_only ? 0 : 2 * nl * sizeof(double)) + ne * (3 * sizeof(int) + sizeof(double)));
     have_scores = want_muts && n_muts && n_tasks;
     if (have_scores) ctx->d2h_bytes += (long long)((size_t)n_muts * sizeof(double));
     if (have_scores)
@@ -1289,7 +1295,7 @@ int Job::finish(std::vector<double>* align_scores, std::vector<double>* mut_scor
     hev.reserve(ne);
     for (ps_region* R : regs)
         for (HostEvent& he : R->events) hev.push_back(&he);
-    if (!score32) ps_parallel_for((int)ne, [&](int e) {
+    if (!score32 && !scores_only) ps_parallel_for((int)ne, [&](int e) {
         const EvDesc& d = ev[e];
         if (!d.usable) return;
         HostEvent& he = *hev[e];
@@ -1339,7 +1345,7 @@ int Job::finish(std::vector<double>* align_scores, std::vector<double>* mut_scor
 // stream by job_begin; job_end waits for the stream and scatters the results into the regions.
 // Between the two the host is free (e.g. to stage the next batch on another context).
 static int job_begin(ps_ctx* ctx, const std::vector<ps_region*>& regs, const std::vector<MutSpec>* muts, double bias, bool score32 = false,
-                     int shard_total_events = 0)
+                     int shard_total_events = 0, bool scores_only = false, bool owns_regions = false)
 {
     TRY(ctx->init());
     CU(cudaSetDevice(ctx->device));
@@ -1362,6 +1368,7 @@ static int job_begin(ps_ctx* ctx, const std::vector<ps_region*>& regs, const std
     if (muts) job->muts = *muts;
     job->bias = bias;
     job->score32 = score32 && muts == nullptr;
+    job->scores_only = scores_only;
     job->sharded = shard_total_events > 0 && muts != nullptr;
     job->total_events = shard_total_events;
     // FAST flags mutations by their TOTAL over all events; an event shard (bias 0, ps_score_mutations_partial) only has
@@ -1381,6 +1388,7 @@ static int job_begin(ps_ctx* ctx, const std::vector<ps_region*>& regs, const std
     const double t3 = now();
     if (trace) fprintf(stderr, "[ps] host: build %.2f ms, upload(enqueue) %.2f, kernels+d2h(enqueue) %.2f\n", t1 - t0, t2 - t1, t3 - t2);
     if (rc) { delete job; return rc; }
+    if (owns_regions) job->owned = regs;               // (only a job that was enqueued takes the regions over)
     ctx->pending = job;
     return PS_OK;
 }
@@ -2118,6 +2126,92 @@ int ps_score_points_batch_begin(ps_region* const* regions, int n_regions, int ca
     if (start || orig || mut)
         ps_parallel_for(n_regions, [&](int r) { write_points(regs[r], offs[r], cap, start, orig, mut); });
     return job_begin(ctx, regs, &per, -1e-6);
+}
+
+// PSAlign.ScorePoints straight from the caller's arrays (poreseq/_poreseqcpp.pyx:278-308: PythonToAlignData ->
+// FindPointMutations -> ScoreMutations -> the scores; the realignment is dropped, nothing is written back).  No region
+// handles: the level arrays are read where they lie (mean, stdv once into the pinned staging records, ref_align once for
+// the band centres), no copy of them is kept, no alignment comes back from the device.
+static ps_region* borrowed_region(ps_ctx* ctx, const ps_region_desc& d)
+{
+    if (!d.bases || d.len < 5 || d.n_events < 0 || d.n_models <= 0 || !d.n0 || !d.model_index || !d.models || !d.probs) return nullptr;
+    ps_region* R = new ps_region();
+    R->ctx = ctx;
+    R->params = d.params;
+    R->set_sequence(std::string(d.bases, d.len));
+    std::vector<int> map(d.n_models, -1);
+    for (int q = 0; q < d.n_models; q++)
+    {
+        HostModel hm;
+        memcpy(hm.raw, d.models + (size_t)q * 4 * PS_N_STATES, sizeof hm.raw);
+        memcpy(hm.trans, d.probs + (size_t)q * 4, sizeof hm.trans);
+        for (size_t k = 0; k < R->models.size() && map[q] < 0; k++)
+            if (memcmp(&R->models[k], &hm, sizeof hm) == 0) map[q] = (int)k;
+        if (map[q] < 0) { map[q] = (int)R->models.size(); R->models.push_back(hm); }
+    }
+    R->events.resize(d.n_events);
+    size_t at = 0;
+    for (int e = 0; e < d.n_events; e++)
+    {
+        const int n = d.n0[e];
+        if (n < 0 || d.model_index[e] < 0 || d.model_index[e] >= d.n_models || (n > 0 && (!d.mean || !d.stdv || !d.ref_align))) { delete R; return nullptr; }
+        HostEvent& he = R->events[e];
+        he.n0 = n;
+        he.model = map[d.model_index[e]];
+        he.complement = d.complement ? d.complement[e] != 0 : false;
+        he.ext_mean = d.mean + at; he.ext_stdv = d.stdv + at;
+        he.update_refs_from(d.ref_align + at);
+        at += (size_t)n;
+    }
+    return R;
+}
+
+int ps_score_points_direct_begin(ps_ctx* ctx, int n_regions, const ps_region_desc* desc, int cap, int* n_out, long long* off_out,
+                                 int* start, char* orig, char* mut)
+{
+    if (!ctx || n_regions <= 0 || !desc) return PS_BAD_ARGS(ctx, "ps_score_points_direct_begin");
+    std::vector<ps_region*> regs(n_regions, nullptr);
+    ps_parallel_for(n_regions, [&](int r) { regs[r] = borrowed_region(ctx, desc[r]); });
+    auto drop = [&] { for (ps_region* R : regs) delete R; };
+    for (int r = 0; r < n_regions; r++)
+        if (!regs[r]) { drop(); ps_set_error(ctx, "ps_score_points_direct: region %d was refused", r); return PS_E_ARG; }
+    std::vector<MutSpec> per(n_regions);
+    long long at = 0;
+    std::vector<long long> offs(n_regions);
+    for (int r = 0; r < n_regions; r++)
+    {
+        per[r].points = true;
+        const ps_region* R = regs[r];
+        long long n = 8 * (long long)R->states.size();
+        for (size_t i = 0; i < R->states.size(); i++)
+        {
+            const char ch = R->bases[i];
+            if (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T') n++;
+        }
+        offs[r] = at;
+        if (n_out) n_out[r] = (int)n;
+        if (off_out) off_out[r] = at;
+        at += n;
+    }
+    if (at > cap) { drop(); ps_set_error(ctx, "output capacity %d < %lld point mutations", cap, at); return PS_E_CAPACITY; }
+    if (start || orig || mut)
+        ps_parallel_for(n_regions, [&](int r) { write_points(regs[r], offs[r], cap, start, orig, mut); });
+    const int rc = job_begin(ctx, regs, &per, -1e-6, false, 0, /*scores_only=*/true, /*owns_regions=*/true);
+    if (rc) drop();
+    return rc;
+}
+
+int ps_score_points_direct_end(ps_ctx* ctx, double* scores)
+{
+    if (!ctx) return PS_BAD_ARGS(ctx, "ps_score_points_direct_end");
+    return job_end(ctx, nullptr, nullptr, scores);
+}
+
+int ps_score_points_direct(ps_ctx* ctx, int n_regions, const ps_region_desc* desc, int cap, int* n_out, long long* off_out,
+                           int* start, char* orig, char* mut, double* scores)
+{
+    TRY(ps_score_points_direct_begin(ctx, n_regions, desc, cap, n_out, off_out, start, orig, mut));
+    return ps_score_points_direct_end(ctx, scores);
 }
 
 int ps_score_points_batch_end(ps_ctx* ctx, double* scores)

@@ -118,7 +118,12 @@ struct HostEvent                              // cpp/EventData.h:78-229
     bool ri_stale = false;                    // ref_align was rewritten by a batch; ref_index is rebuilt from it on first use
     int staged = 0;                           // batches this event was staged for (the level records are cached from the second on)
     std::string seq2d;
+    // borrowed level arrays (ps_score_points_direct: the caller's buffers for the duration of one call, nothing copied);
+    // mean / stdv / ref_align / ref_like above stay empty then
+    const double* ext_mean = nullptr;
+    const double* ext_stdv = nullptr;
     void update_refs();
+    void update_refs_from(const double* ra);  // the same from an array that is not this event's own
     void ensure_refs() { if (ri_stale) update_refs(); }
     void ensure_levrec();                     // log(stdv) etc. (cpp/EventData.h:218-220), cached
 };

@@ -95,6 +95,9 @@ def lib():
     L.ps_score_points_batch_begin.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, _c_int_p, C.POINTER(C.c_longlong),
                                               _c_int_p, C.c_char_p, C.c_char_p]
     L.ps_score_points_batch_end.argtypes = [C.c_void_p, _c_double_p]
+    L.ps_score_points_direct_begin.argtypes = [C.c_void_p, C.c_int, C.POINTER(PSRegionDesc), C.c_int, _c_int_p, C.POINTER(C.c_longlong),
+                                               _c_int_p, C.c_char_p, C.c_char_p]
+    L.ps_score_points_direct_end.argtypes = [C.c_void_p, _c_double_p]
     L.ps_make_mutations.argtypes = [C.c_void_p, C.c_int, _c_int_p, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), _c_double_p, _c_int_p]
     L.ps_refine.argtypes = [C.c_void_p, _c_int_p]
     L.ps_seq_to_states.argtypes = [C.c_char_p, C.c_int, _c_int_p]
@@ -495,9 +498,7 @@ class NativeRegion(object):
         return tot.value
 
 
-def native_regions_from_packed(ctx, packs, width_key=None):
-    """ps_regions_create: fresh native regions for a batch of PackedRegion host buffers in ONE C-ABI call
-    (the library copies them in on its worker threads)."""
+def _region_descs(packs, width_key=None):
     n = len(packs)
     desc = (PSRegionDesc * n)()
     for k, p in enumerate(packs):
@@ -507,6 +508,14 @@ def native_regions_from_packed(ctx, packs, width_key=None):
         d.mean, d.stdv, d.ref_align, d.ref_like = p.mean.ctypes.data, p.stdv.ctypes.data, p.ref_align.ctypes.data, p.ref_like.ctypes.data
         d.model_index, d.n_models, d.models, d.probs = p.model_index.ctypes.data, len(p.models), p.models.ctypes.data, p.probs.ctypes.data
         d.complement, d.seq2d = p.complement.ctypes.data, C.cast(p._seq2d_c, C.c_void_p)
+    return desc
+
+
+def native_regions_from_packed(ctx, packs, width_key=None):
+    """ps_regions_create: fresh native regions for a batch of PackedRegion host buffers in ONE C-ABI call
+    (the library copies them in on its worker threads)."""
+    n = len(packs)
+    desc = _region_descs(packs, width_key)
     out = (C.c_void_p * n)()
     ctx.check(ctx.lib.ps_regions_create(ctx.handle, n, desc, out))
     regs = []
@@ -515,6 +524,38 @@ def native_regions_from_packed(ctx, packs, width_key=None):
         r.ctx, r.handle, r.n_levels = ctx, out[k], p.n0.tolist()
         regs.append(r)
     return regs
+
+
+class PendingDirect(object):
+    """PSAlign.ScorePoints of many regions straight from host buffers (ps_score_points_direct_begin / _end): no native
+    region objects, scores only (the reference drops the realignment of ScorePoints too, pyx:278-308)."""
+
+    def __init__(self, ctx, packs, width_key="point_width"):
+        self.ctx, self.packs = ctx, packs                         # (the host buffers must outlive the call)
+        n = len(packs)
+        self.desc = _region_descs(packs, width_key)
+        cap = sum(9 * max(len(p.sequence), 1) for p in packs)
+        self.n_out = (C.c_int * n)()
+        self.off = (C.c_longlong * n)()
+        self.st = np.zeros(cap, dtype=np.int32)
+        self.og = C.create_string_buffer(cap)
+        self.mu = C.create_string_buffer(cap)
+        self.sc = np.zeros(cap)
+        ctx.check(ctx.lib.ps_score_points_direct_begin(ctx.handle, n, self.desc, cap, self.n_out, self.off,
+                                                       self.st.ctypes.data_as(_c_int_p), self.og, self.mu))
+
+    def end(self):
+        self.ctx.check(self.ctx.lib.ps_score_points_direct_end(self.ctx.handle, _dp(self.sc)))
+        out = []
+        og, mu = self.og.raw, self.mu.raw
+        for k in range(len(self.packs)):
+            a, b = self.off[k], self.off[k] + self.n_out[k]
+            out.append((self.st[a:b], og[a:b], mu[a:b], self.sc[a:b]))
+        return out
+
+
+def score_points_direct(ctx, packs, width_key="point_width"):
+    return PendingDirect(ctx, packs, width_key).end()
 
 
 def close_regions(regions):

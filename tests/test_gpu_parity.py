@@ -718,3 +718,29 @@ def test_native_consensus_equals_python_policy(precision):
         one.close()
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("precision", ["exact", "fast"])
+def test_score_points_direct(orc, precision):
+    """ps_score_points_direct: PSAlign.ScorePoints from the caller's arrays without region handles -- the same scores as
+    the handle path (bit-identical to the checker in exact mode), for a ragged batch; the inputs stay untouched."""
+    regs = [region(c[0]) for c in CASES[:3]]                          # (one batch shares the band widths)
+    packs = [poreseqcpp.PackedRegion(r.sequence, r.events, r.params) for r in regs]
+    keep = [(p.mean.copy(), p.ref_align.copy(), p.ref_like.copy()) for p in packs]
+    c2 = poreseqcpp.Context(0)
+    try:
+        c2.set_precision(precision)
+        got = poreseqcpp.score_points_direct(c2, packs)
+        for k, reg in enumerate(regs):
+            nr = native(c2, reg, "point_width")
+            st, og, mu, sc = nr.score_points()
+            assert np.array_equal(got[k][0], st) and got[k][1] == og and got[k][2] == mu
+            assert np.array_equal(got[k][3], sc)
+            if precision == "exact":
+                want, _ = orc.score_points(reg)
+                assert np.array_equal(got[k][3], np.array([w[3] for w in want]))
+            assert np.array_equal(packs[k].mean, keep[k][0]) and np.array_equal(packs[k].ref_align, keep[k][1])
+            assert np.array_equal(packs[k].ref_like, keep[k][2])
+            nr.close()
+    finally:
+        c2.close()
