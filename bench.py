@@ -390,9 +390,9 @@ def leg_polish(rank, world, device, dist, torch, per_rank=2, in_flight=2):
 
 def recorded_traffic(kernel, regions):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full
-    capture (profiles/r1_traffic.json), valid only for the batch size it was captured at."""
+    capture (profiles/r2_traffic.json), valid only for the batch size it was captured at."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             rec = json.load(f)
         k = rec.get(kernel)
         if k and int(k.get("regions", -1)) == int(regions):
@@ -724,7 +724,7 @@ def main():
                      "achieved": achieved_ops, "peak": peak_ops, "unit": "Tlane-op/s", "frac": achieved_ops / peak_ops,
                      "ops_per_cell": OPS_PER_CELL, "clock_mhz_under_load": clock_mhz, "peak_source": peak_src,
                      "traffic": recorded_traffic(dom_kernel, args.regions),
-                     "traffic_source": "recorded: dram__bytes_read+write per launch from the committed ncu --set full capture of this batch size (profiles/r1_traffic.json), not sampled in this run",
+                     "traffic_source": "recorded: dram__bytes_read+write per launch from the committed ncu --set full capture of this batch size (profiles/r2_traffic.json), not sampled in this run",
                      "note": "SURVEY.md 8d definition (24 FP32 lane-ops per cell); the dominant kernel computes in FP64, see roofline_fp64"},
         "roofline_fp64": {"bound": "fp64-pipe", "kernel": dom_kernel, "achieved": fp64_achieved, "peak": fp64_peak,
                           "unit": "T fp64-op/s", "frac": fp64_achieved / fp64_peak if fp64_peak else 0.0,

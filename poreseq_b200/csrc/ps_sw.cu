@@ -12,6 +12,8 @@
 // The best cell is the first maximum in the reference's (j outer, i inner) order.  A second kernel
 // walks the traceback (one thread per pair) and returns the aligned index pairs.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -29,7 +31,7 @@ struct SwPair
 {
     int n2;
     long long s2_off;             // into the concatenated seed bases
-    long long mv_off;             // into the move matrices, (n1+1) x (n2+1) bytes each, row j at j*(n1+1)
+    long long mv_off;             // into the move records (16 bytes each): (n2 + T) x T per pair, record (step s, thread t) at s*T + t
     long long out_off;            // into the index outputs (n1 + n2 entries reserved per pair)
 };
 
@@ -42,8 +44,11 @@ __global__ void __launch_bounds__(SW_T) k_sw_fill(const char* __restrict__ s1, i
     const SwPair pr = pairs[blockIdx.x];
     const int n2 = pr.n2, t = threadIdx.x, T = blockDim.x;
     const char* s2 = s2all + pr.s2_off;
-    uint8_t* mv = move + pr.mv_off;
-    const long long stride = (long long)n1 + 1;
+    // Move bytes, step-major: the K moves a thread produces in one step are ONE 16-byte record, and the records of one
+    // step lie next to each other (thread t at step s: record s * T + t), so a warp's stores are one contiguous 512-byte
+    // run.  (Row-major bytes -- row j at j * (n1 + 1) -- made every thread store K single bytes into a row of its own per
+    // step: 10 240 scattered byte stores per step at 10 kb, 104 ms per batch of 10 kb x 10 kb pairs however many pairs.)
+    uint4* mv = reinterpret_cast<uint4*>(move) + pr.mv_off;
     const int i0 = t * K + 1;                                    // first column (1-based) of this thread
     const int ncols = min(K, n1 - t * K);                        // <= 0: nothing to do
     __shared__ int ring[3][SW_T];
@@ -67,7 +72,7 @@ __global__ void __launch_bounds__(SW_T) k_sw_fill(const char* __restrict__ s1, i
                 diag = j > 1 ? ring[w2][t - 1] : 0;
             }
             const char cj = s2[j - 1];
-            uint8_t* row = mv + (long long)j * stride + i0;
+            unsigned pk[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
             for (int c = 0; c < SW_KMAX; c++)
             {
@@ -81,11 +86,12 @@ __global__ void __launch_bounds__(SW_T) k_sw_fill(const char* __restrict__ s1, i
                     if (v > sc) { sc = v; m = 2; }
                     v = diag + (c1[c] == cj ? 5 : -4);
                     if (v >= sc) { sc = v; m = 3; }
-                    row[c] = (uint8_t)(m | (sc <= 0 ? 4 : 0));
+                    pk[c >> 2] |= (unsigned)(m | (sc <= 0 ? 4 : 0)) << (8 * (c & 3));
                     if (sc > bs) { bs = sc; bi = i0 + c; bj = j; }
                     diag = up; left = sc; H[c] = sc;
                 }
             }
+            mv[(long long)s * T + t] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             ring[w0][t] = left;
         }
         __syncthreads();
@@ -115,20 +121,21 @@ __global__ void __launch_bounds__(SW_T) k_sw_fill(const char* __restrict__ s1, i
 // traceback (cpp/swlib.cpp:296-333): index pairs from the best cell back to the first cell with score <= 0,
 // written in walk order (the host reverses them)
 __global__ void k_sw_trace(const char* __restrict__ s1, int n1, const char* __restrict__ s2all, const SwPair* __restrict__ pairs,
-                           const uint8_t* __restrict__ move, SwBest* __restrict__ best, int* __restrict__ o1, int* __restrict__ o2)
+                           const uint8_t* __restrict__ move, SwBest* __restrict__ best, int* __restrict__ o1, int* __restrict__ o2,
+                           int K, int T)
 {
     if (threadIdx.x != 0) return;
     const SwPair pr = pairs[blockIdx.x];
     const char* s2 = s2all + pr.s2_off;
-    const uint8_t* mv = move + pr.mv_off;
-    const long long stride = (long long)n1 + 1;
+    const uint8_t* mv = move + pr.mv_off * 16;
     SwBest b = best[blockIdx.x];
     int i = b.i, j = b.j, n = 0, nmatch = 0;
     int* a1 = o1 + pr.out_off;
     int* a2 = o2 + pr.out_off;
     while (i > 0 && j > 0)
     {
-        const uint8_t x = mv[(long long)j * stride + i];
+        const int t = (i - 1) / K, c = (i - 1) - t * K;             // cell (j, i): thread t, its column c, step j + t - 1
+        const uint8_t x = mv[((long long)(j + t - 1) * T + t) * 16 + c];
         if (x & 4) break;
         const int m = x & 3;
         if (m == 1) { a1[n] = 0; a2[n] = j; j--; }
@@ -176,7 +183,10 @@ int psi_swfull_batch(ps_ctx* ctx, const std::string& s1, const std::vector<std::
     if (n1 == 0 || n1 > SW_T * SW_KMAX) return PS_E_ARG;
     TRY(ctx->init());
     CU(cudaSetDevice(ctx->device));
-    const int K = (n1 + SW_T - 1) / SW_T;
+    // columns per thread and threads per pair: at least 8 columns per thread (short sequences take fewer threads: a
+    // cheaper barrier, a shorter skew), at most SW_T threads
+    const int K = std::max(8, (n1 + SW_T - 1) / SW_T);
+    const int T = std::min(SW_T, (((n1 + K - 1) / K) + 31) & ~31);
     // pairs in sub-batches whose move matrices fit a quarter of the device memory
     const double budget = 0.25 * (double)ctx->total_mem;
     size_t a = 0;
@@ -189,7 +199,7 @@ int psi_swfull_batch(ps_ctx* ctx, const std::string& s1, const std::vector<std::
         long long mv_off = 0, out_off = 0;
         while (b < P)
         {
-            const double need = ((double)n1 + 1) * ((double)others[b].size() + 1);
+            const double need = ((double)others[b].size() + T) * (double)T * 16.0;
             if (b > a && bytes + need > budget) break;
             SwPair p;
             p.n2 = (int)others[b].size();
@@ -197,7 +207,7 @@ int psi_swfull_batch(ps_ctx* ctx, const std::string& s1, const std::vector<std::
             p.mv_off = mv_off;
             p.out_off = out_off;
             cat += others[b];
-            mv_off += ((long long)n1 + 1) * ((long long)p.n2 + 1);
+            mv_off += ((long long)p.n2 + T) * (long long)T;        // 16-byte records
             out_off += (long long)n1 + p.n2 + 2;
             bytes += need;
             pairs.push_back(p);
@@ -208,7 +218,7 @@ int psi_swfull_batch(ps_ctx* ctx, const std::string& s1, const std::vector<std::
         TRY(dev_room(ctx, "sw_s1", (size_t)n1, &d_s1));
         TRY(dev_room(ctx, "sw_s2", cat.size(), &d_s2));
         TRY(dev_room(ctx, "sw_pairs", np, &d_pairs));
-        TRY(dev_room(ctx, "sw_move", (size_t)mv_off, &d_mv));
+        TRY(dev_room(ctx, "sw_move", (size_t)mv_off * 16, &d_mv));
         TRY(dev_room(ctx, "sw_best", np, &d_best));
         TRY(dev_room(ctx, "sw_o1", (size_t)out_off, &d_o1));
         TRY(dev_room(ctx, "sw_o2", (size_t)out_off, &d_o2));
@@ -230,12 +240,21 @@ int psi_swfull_batch(ps_ctx* ctx, const std::string& s1, const std::vector<std::
         CU(cudaMemcpyAsync(d_s1, h_s1.data(), (size_t)n1, cudaMemcpyHostToDevice, ctx->stream));
         if (!cat.empty()) CU(cudaMemcpyAsync(d_s2, h_s2.data(), cat.size(), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(d_pairs, h_pairs.data(), np * sizeof(SwPair), cudaMemcpyHostToDevice, ctx->stream));
-        k_sw_fill<<<(unsigned)np, SW_T, 0, ctx->stream>>>(d_s1, n1, d_s2, d_pairs, d_mv, d_best, K);
+        auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        double t0 = 0, t1 = 0;
+        if (ctx->trace) { CU(cudaStreamSynchronize(ctx->stream)); t0 = now(); }
+        k_sw_fill<<<(unsigned)np, T, 0, ctx->stream>>>(d_s1, n1, d_s2, d_pairs, d_mv, d_best, K);
         ctx->launches++;
         CU(cudaGetLastError());
-        k_sw_trace<<<(unsigned)np, 32, 0, ctx->stream>>>(d_s1, n1, d_s2, d_pairs, d_mv, d_best, d_o1, d_o2);
+        if (ctx->trace) { CU(cudaStreamSynchronize(ctx->stream)); t1 = now(); }
+        k_sw_trace<<<(unsigned)np, 32, 0, ctx->stream>>>(d_s1, n1, d_s2, d_pairs, d_mv, d_best, d_o1, d_o2, K, T);
         ctx->launches++;
         CU(cudaGetLastError());
+        if (ctx->trace)
+        {
+            CU(cudaStreamSynchronize(ctx->stream));
+            fprintf(stderr, "[ps] swfull batch: %zu pairs of %d x ~%zu: fill %.2f ms, traceback %.2f ms\n", np, n1, cat.size() / np, t1 - t0, now() - t1);
+        }
         CU(cudaMemcpyAsync(best.data(), d_best, np * sizeof(SwBest), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaMemcpyAsync(o1.data(), d_o1, (size_t)out_off * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaMemcpyAsync(o2.data(), d_o2, (size_t)out_off * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
