@@ -163,7 +163,7 @@ def libc_srand(seed):
 
 
 CONS_REGIONS = 64          # per GPU (32 left the tail of the last regions in flight visible: 17-23 kb/s run to run)
-CONS_IN_FLIGHT = 16        # regions side by side per GPU (library threads + streams)
+CONS_IN_FLIGHT = 32        # lanes (library threads + streams) per GPU: 16 lockstep groups of 4 regions with 2 lanes each
 
 
 def consensus_cpu(length, coverage, seed):

@@ -462,8 +462,9 @@ extern "C" int ps_consensus_batch(ps_ctx* ctx, ps_region* const* regions, int n_
     {
         // A few lockstep groups side by side (a host thread + context each, with lanes of their own): while one group's
         // host step runs (staging a job, picking candidates, the accept loops) the GPU works on another group's job.
-        // Measured on 64 regions of 1 kb x 10x: 1 group 27 kb/s, 2: 34, 4: 40, 8: 46 (regions in flight on threads: 25-43, unstable).
-        int groups = ctx->consensus_groups > 0 ? ctx->consensus_groups : std::max(1, std::min(8, n_regions / 8));
+        // Measured on 64 regions of 1 kb x 10x: 1 group 27 kb/s, 2: 34, 4: 40, 8: 46-49, 16: 53 (regions in flight on
+        // threads: 25-43, unstable).
+        int groups = ctx->consensus_groups > 0 ? ctx->consensus_groups : std::max(1, std::min(16, n_regions / 4));
         groups = std::max(1, std::min(groups, n_regions));
         if (groups == 1) return ps_consensus_lockstep(ctx, regions, n_regions, reps, point_width, in_flight);
         while ((int)ctx->group_ctx.size() < groups - 1)

@@ -19,6 +19,8 @@
 // glibc in the last ulps, which can move an inverse-CDF boundary by ~1e-16 -- a sampled state flips
 // with probability ~1e-13 per draw.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -275,6 +277,8 @@ int ps_viterbi_list(ps_region* R, int nkeep, double skip_prob, double stay_prob,
     ps_ctx* ctx = R->ctx;
     TRY(ctx->init());
     CU(cudaSetDevice(ctx->device));
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
     const int E = (int)R->events.size();
     if (E == 0) { ps_set_error(ctx, "ViterbiMutate needs at least one event"); return PS_E_ARG; }
     for (HostEvent& ev : R->events) ev.ensure_refs();
@@ -395,6 +399,8 @@ int ps_viterbi_list(ps_region* R, int nkeep, double skip_prob, double stay_prob,
         vc.stay_lik = std::log(stay_prob);
         vc.stay_prob = stay_prob;
     }
+    double t_obs = 0;
+    if (ctx->trace) { CU(cudaStreamSynchronize(ctx->stream)); t_obs = now(); }
     k_vit_chain<<<1, N_STATES, 0, ctx->stream>>>(d_obs, d_eobs, n_pos, vc, d_fwd, d_bp, d_last);
     ctx->launches++;
     CU(cudaGetLastError());
@@ -402,6 +408,7 @@ int ps_viterbi_list(ps_region* R, int nkeep, double skip_prob, double stay_prob,
     if (!last.resize(N_STATES)) { ps_set_error(ctx, "out of host memory staging ViterbiMutate"); return PS_E_INTERNAL; }
     CU(cudaMemcpyAsync(last.data(), d_last, N_STATES * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    const double t_chain = now();
     const int startst = (int)(std::max_element(last.begin(), last.end()) - last.begin());
 
     std::vector<int> path(n_pos);
@@ -434,6 +441,9 @@ int ps_viterbi_list(ps_region* R, int nkeep, double skip_prob, double stay_prob,
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(paths.data(), d_paths, paths.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->trace)
+        fprintf(stderr, "[ps] ViterbiMutate: %d positions, %d reads: host + emission pooling %.1f ms, chain %.1f ms, %d sampled walks %.1f ms\n",
+                n_pos, E, t_obs - t_begin, t_chain - t_obs, nkeep, now() - t_chain);
     for (int k = 0; k < nkeep; k++)
     {
         // paths are stored end-first (as walked); flip to chain order
