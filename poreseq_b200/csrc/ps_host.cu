@@ -1761,6 +1761,7 @@ ps_ctx* ps_create(int device)
     ctx->no_warp = getenv("PORESEQ_B200_NO_WARP") != nullptr;
     ctx->sw_host = getenv("PORESEQ_B200_SW_HOST") != nullptr;
     ctx->no_stage = getenv("PORESEQ_B200_NO_STAGE") != nullptr;
+    if (const char* e = getenv("PORESEQ_B200_VIT_CLUSTER")) ctx->vit_cluster = atoi(e) != 0;
     if (const char* e = getenv("PORESEQ_B200_CONSENSUS")) ctx->threads_consensus = std::string(e) == "threads";
     if (const char* e = getenv("PORESEQ_B200_GROUPS")) ctx->consensus_groups = std::max(1, atoi(e));
     if (const char* e = getenv("PORESEQ_B200_S32_WARPS")) ctx->s32_warps = std::max(2, std::min(atoi(e), PS_SCORE32_MAX_WARPS));

@@ -29,6 +29,7 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 
 #include "ps_internal.h"
 #include "ps_types.cuh"
@@ -154,6 +155,104 @@ __global__ void __launch_bounds__(1024) k_vit_chain(const double* obs, const dou
         __syncthreads();
     }
     last_liks[d] = lk[n_pos & 1][d];
+}
+
+// The same chain on a CLUSTER of 8 CTAs (thread-block clusters + distributed shared memory): the 1024 destination states
+// are split over 8 SMs (128 threads each), every CTA keeps a full copy of the previous position's Viterbi scores and
+// forward probabilities in its own shared memory, writes its 128 new values into all eight copies (st.shared::cluster
+// through cluster.map_shared_rank) and the cluster meets once per position.  The single-CTA form is bound by ONE SM's FP64
+// pipe (336 FP64 instructions per state and position x 32 warps: 6.5 us per position measured); here a position costs one
+// warp per scheduler's worth of that plus the cluster barrier.  Per-state arithmetic and its order are unchanged; the
+// normalising sum is the sum of the eight CTAs' tree sums (the forward probabilities were never bit-identical to the
+// reference's index-order sum).
+constexpr int VIT_CL = 8;
+
+__global__ void __cluster_dims__(VIT_CL, 1, 1) __launch_bounds__(N_STATES / VIT_CL)
+k_vit_chain_cluster(const double* obs, const double* eobs, int n_pos, VitConst vc, double* fwd, int* backptr, double* last_liks)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    constexpr int PER = N_STATES / VIT_CL;                    // states per CTA = threads per CTA
+    __shared__ double lk[2][N_STATES];
+    __shared__ double fw[2][N_STATES];
+    __shared__ double part[2][VIT_CL];
+    __shared__ double red[PER / 32];
+    const int rank = (int)cluster.block_rank();
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int d = rank * PER + tid;                           // this thread's destination state
+    for (int i = tid; i < N_STATES; i += PER) { lk[0][i] = 0.0; fw[0][i] = 1.0 / N_STATES; }
+    // the eight copies of every array, as this thread sees them
+    double* r_lk[VIT_CL]; double* r_fw[VIT_CL]; double* r_part[VIT_CL];
+#pragma unroll
+    for (int q = 0; q < VIT_CL; q++)
+    {
+        r_lk[q] = cluster.map_shared_rank(&lk[0][0], q);
+        r_fw[q] = cluster.map_shared_rank(&fw[0][0], q);
+        r_part[q] = cluster.map_shared_rank(&part[0][0], q);
+    }
+    cluster.sync();
+    for (int t = 0; t < n_pos; t++)
+    {
+        const int cur = t & 1, nxt = cur ^ 1;
+        const double* pl = lk[cur];
+        const double* pf = fw[cur];
+        const double o = obs[(size_t)t * N_STATES + d];
+        double best = NEG, f = 0.0;
+        int ptr = -1;
+#pragma unroll
+        for (int j = 1; j <= 3; j++)
+        {
+            const double lsp = vc.lsp[j - 1], sp = vc.sp[j - 1];
+            const double base = o + lsp;
+            const int lowbits = d >> (2 * j), shift = 10 - 2 * j;
+#pragma unroll 4
+            for (int k = 0; k < (1 << (2 * j)); k++)
+            {
+                const int p = lowbits + (k << shift);
+                const double l = base + pl[p];
+                f += sp * pf[p];
+                if (l > best) { best = l; ptr = p; }
+            }
+        }
+        {
+            const double l = o + vc.stay_lik + pl[d];
+            if (l > best) { best = l; ptr = d; }
+            f += vc.stay_prob * pf[d];
+        }
+        f *= eobs[(size_t)t * N_STATES + d];
+        // this CTA's part of the normalising sum
+        double s = f;
+        for (int o2 = 16; o2; o2 >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2);
+        if (lane == 0) red[wid] = s;
+        __syncthreads();
+        // new values (forward probability not yet normalised) and the partial sum into all eight copies
+#pragma unroll
+        for (int q = 0; q < VIT_CL; q++)
+        {
+            r_lk[q][nxt * N_STATES + d] = best;
+            r_fw[q][nxt * N_STATES + d] = f;
+        }
+        if (tid < VIT_CL)
+        {
+            double w = 0.0;
+#pragma unroll
+            for (int k = 0; k < PER / 32; k++) w += red[k];
+            r_part[tid][cur * VIT_CL + rank] = w;
+        }
+        cluster.sync();
+        double w = 0.0;
+#pragma unroll
+        for (int q = 0; q < VIT_CL; q++) w += part[cur][q];
+        const double inv = 1.0 / w;
+        // every CTA normalises its own copy (the same products everywhere)
+#pragma unroll
+        for (int q = 0; q < VIT_CL; q++) fw[nxt][q * PER + tid] *= inv;
+        fwd[(size_t)t * N_STATES + d] = f * inv;
+        backptr[(size_t)t * N_STATES + d] = ptr;
+        __syncthreads();
+    }
+    last_liks[d] = lk[n_pos & 1][d];
+    cluster.sync();                                           // nobody leaves while its shared memory may still be written
 }
 
 // ------------------------------------------------------------------------------------------
@@ -401,7 +500,8 @@ int ps_viterbi_list(ps_region* R, int nkeep, double skip_prob, double stay_prob,
     }
     double t_obs = 0;
     if (ctx->trace) { CU(cudaStreamSynchronize(ctx->stream)); t_obs = now(); }
-    k_vit_chain<<<1, N_STATES, 0, ctx->stream>>>(d_obs, d_eobs, n_pos, vc, d_fwd, d_bp, d_last);
+    if (ctx->vit_cluster) k_vit_chain_cluster<<<VIT_CL, N_STATES / VIT_CL, 0, ctx->stream>>>(d_obs, d_eobs, n_pos, vc, d_fwd, d_bp, d_last);
+    else k_vit_chain<<<1, N_STATES, 0, ctx->stream>>>(d_obs, d_eobs, n_pos, vc, d_fwd, d_bp, d_last);
     ctx->launches++;
     CU(cudaGetLastError());
     PinVec<double> last = ctx->pinned<double>("vit_last_h");
