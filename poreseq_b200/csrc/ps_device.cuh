@@ -566,6 +566,19 @@ __device__ __forceinline__ void fill_wave(const Batch& b, const EvDesc& ev, cons
         }
         const int r = d - cur.j;
         const int w0 = ph, w1 = (ph + RD - 1) & (RD - 1), w2 = (ph + RD - 2) & (RD - 1);   // steps d, d-1, d-2
+#ifndef PS_NO_LEAN
+        // Is every tile of this warp's step an interior one (all four cells inside their bands and past their first
+        // rows, every predecessor inside the band of the column before, valid states)?  Then the warp runs the same
+        // arithmetic with every mask a compile-time `true`: the selects that only apply masks fold away.
+        bool warp_lean;
+        {
+            const int ia = 2 * r + 1, ib = ia + 1;
+            const bool act = r >= cur.rlo && r <= cur.rhi;
+            const bool mine = (!INV || (cur.sa >= 0 && cur.sb >= 0)) && ia > cur.i0a && ia > cur.i0b && ib <= cur.i1a && ib <= cur.i1b &&
+                              ia > cur.pp0 && ib <= cur.pp1 && cur.j > 0;
+            warp_lean = __all_sync(0xffffffffu, !act || mine);
+        }
+#endif
         if (r >= cur.rlo && r <= cur.rhi)
         {
             const int ia = 2 * r + 1, ib = ia + 1;
@@ -589,6 +602,22 @@ __device__ __forceinline__ void fill_wave(const Batch& b, const EvDesc& ev, cons
             const bool skD = inC, dgD = ib > cur.i0a && ib <= cur.i1a;
             double CA, CB, CC, CD, SA, SB, SC, SD, M;
             int kA, kB, kC, kD, qA, qB, qC, qD, m;
+#ifndef PS_NO_LEAN
+            const bool lean = warp_lean;
+            if (lean)
+            {
+                cell_pre<false>(true, true, false, true, Lm, REV ? LEm : eA, REV ? upE0 : eA, upC0, upS0, tr, M, m, SA, qA);
+                cell_fin(true, La, M, m, tr, CA, kA);
+                cell_pre<false>(true, true, false, true, upC0, REV ? upE0 : eB, REV ? upE1 : eB, upC1, upS1, tr, M, m, SB, qB);
+                cell_fin(true, CA, M, m, tr, CB, kB);
+                cell_pre<false>(true, true, false, true, La, REV ? LEa : eC, REV ? eA : eC, CA, SA, tr, M, m, SC, qC);
+                cell_fin(true, Lb, M, m, tr, CC, kC);
+                cell_pre<false>(true, true, false, true, CA, REV ? eA : eD, REV ? eB : eD, CB, SB, tr, M, m, SD, qD);
+                cell_fin(true, CC, M, m, tr, CD, kD);
+            }
+            else
+#endif
+            {
             // row ia
             cell_pre<INV>(inA, v0, ia == cur.i0a, dgA, Lm, REV ? (dgA ? LEm : 0.0) : eA, REV ? upE0 : eA, upC0, upS0, tr, M, m, SA, qA);
             cell_fin(skA && inA && v0, La, M, m, tr, CA, kA);
@@ -599,6 +628,7 @@ __device__ __forceinline__ void fill_wave(const Batch& b, const EvDesc& ev, cons
             cell_fin(skC && inC && v0, Lb, M, m, tr, CC, kC);
             cell_pre<INV>(inD, v1, ib == cur.i0b, dgD, CA, REV ? (dgD ? eA : 0.0) : eD, REV ? eB : eD, CB, SB, tr, M, m, SD, qD);
             cell_fin(skD && inD && v1, CC, M, m, tr, CD, kD);
+            }
             // the second column of the strip is what the right neighbour reads
             myC[w0 * MAXT] = make_double2(CB, CD);
             if (REV) myE[w0 * MAXT] = make_double2(eB, eD);
