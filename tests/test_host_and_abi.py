@@ -575,3 +575,39 @@ def test_find_mutations_host_half_matches_reference(ref):
         nonempty += len(want) > 0
         nr.close()
     assert nonempty >= 30
+
+
+def test_round2_entry_points_refuse_bad_arguments_and_have_no_cpu_path():
+    """The entry points added in round 2 (ScoreEvents, the direct ScorePoints path, the consensus loop, the event-shard
+    communicator): bad arguments come back as PS_E_ARG with a message, and on a machine without a GPU the compute calls
+    fail with PS_E_CUDA -- there is no CPU path behind them either."""
+    import ctypes as C
+    L = poreseqcpp.lib()
+    assert L.ps_score_events(None, None) == -1
+    assert L.ps_score_events_batch(None, 3, None) == -1
+    assert L.ps_consensus(None, 4, 20, None) == -1
+    assert L.ps_consensus_batch(None, None, 1, 4, 20, 4) == -1
+    assert L.ps_score_points_direct_begin(None, 1, None, 0, None, None, None, None, None) == -1
+    assert L.ps_comm_init(None, None, 0, 0, 1, 1) == -1
+    assert L.ps_region_get_stage(None, 0, None, 0, None, 0, None) == -1
+    ctx = poreseqcpp.Context(0)
+    try:
+        reg = synth.make_region(80, 3, seed=11)
+        nr = poreseqcpp.NativeRegion(ctx, reg.sequence, reg.events, reg.params)
+        assert L.ps_region_num_stages(nr.handle) == 0
+        # a sharded call without a communicator is an argument error, whatever the machine
+        st = np.zeros(1, dtype=np.int32)
+        out = np.zeros(1)
+        o = (C.c_char_p * 1)(b"A"); m = (C.c_char_p * 1)(b"C")
+        rc = L.ps_score_mutations_sharded(nr.handle, 1, st.ctypes.data_as(C.POINTER(C.c_int)), o, m, out.ctypes.data_as(C.POINTER(C.c_double)))
+        assert rc == -1 and b"communicator" in L.ps_last_error(ctx.handle)
+        # the same handle twice in one batch
+        import torch
+        if not torch.cuda.is_available():
+            for call in (lambda: nr.score_events(), lambda: nr.consensus(1, 8),
+                         lambda: poreseqcpp.score_points_direct(ctx, [poreseqcpp.PackedRegion(reg.sequence, reg.events, reg.params)])):
+                with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+                    call()
+        nr.close()
+    finally:
+        ctx.close()
