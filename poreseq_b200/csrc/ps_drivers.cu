@@ -458,7 +458,14 @@ extern "C" int ps_consensus_batch(ps_ctx* ctx, ps_region* const* regions, int n_
         }
     }
     // default: every step of the loop as one job over all regions that are at it (ps_lockstep.cu)
-    if (!ctx->threads_consensus && n_regions > 1)
+    // lockstep needs one set of band widths for all regions (they share jobs); otherwise regions in flight on threads
+    bool uniform = true;
+    for (int k = 1; k < n_regions; k++)
+    {
+        const ps_params &p = regions[k]->params, &q = regions[0]->params;
+        if (p.lik_offset != q.lik_offset || p.realign_width != q.realign_width || p.scoring_width != q.scoring_width) uniform = false;
+    }
+    if (!ctx->threads_consensus && n_regions > 1 && uniform)
     {
         // A few lockstep groups side by side (a host thread + context each, with lanes of their own): while one group's
         // host step runs (staging a job, picking candidates, the accept loops) the GPU works on another group's job.

@@ -28,6 +28,7 @@
 #include "ps_device.cuh"
 #include "ps_fast.cuh"
 #include "ps_score32.cuh"
+#include "ps_fill2.cuh"
 #include "ps_internal.h"
 
 using namespace psdev;
@@ -282,6 +283,8 @@ int ps_ctx::init()
     CU(cudaFuncSetAttribute(k_mutscore_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU(cudaFuncSetAttribute(k_mutscore<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU(cudaFuncSetAttribute(k_mutscore<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CU(cudaFuncSetAttribute(k_fill2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(k_fill2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(k_score_f32<true, false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(k_score_f32<true, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(k_score_f32<false, false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -1098,6 +1101,27 @@ int Job::run(bool full)
         // 8-deep rings (2 x 8 x 16 B per thread) + next strip record (11 x 16 B) for the point-to-point classes
         const size_t smem160 = std::max<size_t>(54 * 160, 2 * b.RS) * sizeof(double);
         const size_t smem192 = std::max<size_t>(54 * 192, 2 * b.RS) * sizeof(double);
+        if (ctx->fill2 && off3 > 0)
+        {
+            // every wavefront-capable event (the three width classes are one list: k_fill2 has no width classes)
+            Fill2Args fa;
+            fa.list = b.fill_list; fa.count = off3; fa.dirs = dirs;
+            fa.slots = (2 * b.realign_width + 1 + 8 + 3) & ~3;
+            const int warps = 4;
+            const size_t smem = (size_t)(warps + 1) * fa.slots * sizeof(double2);
+            const int per_sm = std::max(1, std::min(4, (int)((220 * 1024) / (smem + 1024))));
+            const int grid = std::max(1, std::min(off3 * dirs, ctx->sm_count * per_sm));
+            bool any_inv = false;
+            for (const EvDesc& d : ev) any_inv = any_inv || d.inv;
+            if (any_inv) k_fill2<true><<<grid, 32 * warps, smem, ctx->stream>>>(b, fa);
+            else k_fill2<false><<<grid, 32 * warps, smem, ctx->stream>>>(b, fa);
+            LAUNCHED();
+            k_fill_best<<<dim3(off3, dirs), 256, 0, ctx->stream>>>(b, fa);
+            LAUNCHED();
+            if (fill_count[3]) { k_fill<160, 3><<<dim3(fill_count[3], dirs), 32, smem160, ctx->stream>>>(b, off3); LAUNCHED(); }
+        }
+        else
+        {
         if (fill_count[2])
         {
             const size_t smem = std::max<size_t>(40 * 512, 2 * b.RS) * sizeof(double);
@@ -1107,6 +1131,7 @@ int Job::run(bool full)
         if (fill_count[1]) { k_fill<192, 2><<<dim3(fill_count[1], dirs), 192, smem192, other>>>(b, off1); LAUNCHED(); }
         if (fill_count[3]) { k_fill<160, 3><<<dim3(fill_count[3], dirs), 32, smem160, other>>>(b, off3); LAUNCHED(); }
         if (fill_count[0]) { k_fill<160, 3><<<dim3(fill_count[0], dirs), 160, smem160, ctx->stream>>>(b, 0); LAUNCHED(); }
+        }
         if (forked)
         {
             CU(cudaEventRecord(ctx->join_ev, ctx->side));
@@ -1762,6 +1787,7 @@ ps_ctx* ps_create(int device)
     ctx->sw_host = getenv("PORESEQ_B200_SW_HOST") != nullptr;
     ctx->no_stage = getenv("PORESEQ_B200_NO_STAGE") != nullptr;
     if (const char* e = getenv("PORESEQ_B200_VIT_CLUSTER")) ctx->vit_cluster = atoi(e) != 0;
+    if (const char* e = getenv("PORESEQ_B200_FILL2")) ctx->fill2 = atoi(e) != 0;
     if (const char* e = getenv("PORESEQ_B200_CONSENSUS")) ctx->threads_consensus = std::string(e) == "threads";
     if (const char* e = getenv("PORESEQ_B200_GROUPS")) ctx->consensus_groups = std::max(1, atoi(e));
     if (const char* e = getenv("PORESEQ_B200_S32_WARPS")) ctx->s32_warps = std::max(2, std::min(atoi(e), PS_SCORE32_MAX_WARPS));

@@ -65,6 +65,7 @@ struct ps_ctx
     int consensus_groups = 0;                 // PORESEQ_B200_GROUPS: lockstep groups of ps_consensus_batch running side by side (0: chosen by batch size)
     bool threads_consensus = false;           // PORESEQ_B200_CONSENSUS=threads: ps_consensus_batch as regions in flight on threads instead of lockstep (A/B)
     bool no_stage = false;                    // PORESEQ_B200_NO_STAGE: k_score_f32 reads level records through L1 instead of a TMA-staged copy (A/B)
+    bool fill2 = false;                       // PORESEQ_B200_FILL2=1: the wide fill on the warp-block schedule (k_fill2) instead of k_fill (A/B)
     bool vit_cluster = true;                  // PORESEQ_B200_VIT_CLUSTER=0: the Viterbi chain on one CTA instead of a cluster of 8 (A/B)
     int s32_warps = 0;                        // PORESEQ_B200_S32_WARPS: warps per CTA of k_score_f32 (0: chosen by batch size)
     double tau_override = -1;                 // PORESEQ_B200_TAU: FAST-mode re-score threshold (diagnostics; < 0: derived)
