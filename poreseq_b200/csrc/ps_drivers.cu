@@ -486,11 +486,13 @@ extern "C" int ps_consensus_batch(ps_ctx* ctx, ps_region* const* regions, int n_
         const int lanes = std::max(1, in_flight / groups);
         // every group's context grows band buffers of its own: share the device memory between them
         const double keep_budget = ctx->band_budget;
+        const bool keep_wait = ctx->blocking_wait;
         const double group_budget = std::min(keep_budget > 0 ? keep_budget : 32e9, 0.6 * (double)ctx->total_mem / groups);
         auto run = [&](int g) {
             ps_ctx* c = g == 0 ? ctx : ctx->group_ctx[g - 1];
             c->precision = ctx->precision;
             c->band_budget = group_budget;
+            c->blocking_wait = true;                                     // (restored for ctx below)
             rcs[g] = ps_consensus_lockstep(c, part[g].data(), (int)part[g].size(), reps, point_width, lanes);
         };
         std::vector<std::thread> th;
@@ -498,6 +500,7 @@ extern "C" int ps_consensus_batch(ps_ctx* ctx, ps_region* const* regions, int n_
         run(0);
         for (std::thread& t : th) t.join();
         ctx->band_budget = keep_budget;
+        ctx->blocking_wait = keep_wait;
         for (int g = 0; g < groups; g++)
             if (rcs[g]) { if (g) ps_set_error(ctx, "ps_consensus_batch: %s", ctx->group_ctx[g - 1]->error.c_str()); return rcs[g]; }
         return PS_OK;
@@ -510,7 +513,7 @@ extern "C" int ps_consensus_batch(ps_ctx* ctx, ps_region* const* regions, int n_
         ctx->helpers.push_back(h);
     }
     std::vector<ps_ctx*> lanes(1, ctx);
-    for (int k = 0; k + 1 < in_flight; k++) { ctx->helpers[k]->precision = ctx->precision; lanes.push_back(ctx->helpers[k]); }
+    for (int k = 0; k + 1 < in_flight; k++) { ctx->helpers[k]->precision = ctx->precision; ctx->helpers[k]->blocking_wait = true; lanes.push_back(ctx->helpers[k]); }
     std::atomic<int> next(0);
     std::vector<int> rcs(in_flight, PS_OK);
     std::vector<std::string> errs(in_flight);

@@ -37,6 +37,17 @@ using namespace psdev;
 // errors
 static std::string g_create_error;
 
+// cudaStreamSynchronize spins on a host core; with more driving threads than cores (the lanes and groups of
+// ps_consensus_batch: 16-48 threads on the 4 cores a rank gets on an 8-GPU box) the spinning takes the cores from the
+// threads that have work.  A blocking-sync event puts the waiting thread to sleep instead.
+int ps_stream_wait(ps_ctx* ctx)
+{
+    if (!ctx->blocking_wait) return (int)cudaStreamSynchronize(ctx->stream);
+    cudaError_t e = cudaEventRecord(ctx->wait_ev, ctx->stream);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaEventSynchronize(ctx->wait_ev);
+}
+
 void ps_set_error(ps_ctx* ctx, const char* fmt, ...)
 {
     char buf[1024];
@@ -275,6 +286,7 @@ int ps_ctx::init()
     CU(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&join_ev, cudaEventDisableTiming));
     for (int i = 0; i <= PS_T_COUNT; i++) CU(cudaEventCreate(&tev[i]));
+    CU(cudaEventCreateWithFlags(&wait_ev, cudaEventBlockingSync | cudaEventDisableTiming));
     CU(cudaFuncSetAttribute(k_backtrace, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
     CU(cudaFuncSetAttribute(k_fill<160, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     CU(cudaFuncSetAttribute(k_fill<192, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -356,7 +368,7 @@ ps_ctx::~ps_ctx()
     for (auto& kv : bufs) if (kv.second.p) cudaFree(kv.second.p);
     for (auto& kv : pins) if (kv.second.p) { if (kv.second.cap & 1) free(kv.second.p); else cudaFreeHost(kv.second.p); }
     for (int i = 0; i <= PS_T_COUNT; i++) cudaEventDestroy(tev[i]);
-    cudaEventDestroy(fork_ev); cudaEventDestroy(join_ev);
+    cudaEventDestroy(fork_ev); cudaEventDestroy(join_ev); cudaEventDestroy(wait_ev);
     cudaStreamDestroy(side);
     cudaStreamDestroy(stream);
 }
@@ -1314,7 +1326,7 @@ int Job::download_enqueue()
 int Job::finish(std::vector<double>* align_scores, std::vector<double>* mut_scores)
 {
     const size_t ne = ev.size();
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU((cudaError_t)ps_stream_wait(ctx));
     // scatter the realigned events back into their regions
     std::vector<HostEvent*> hev;
     hev.reserve(ne);
@@ -1788,6 +1800,7 @@ ps_ctx* ps_create(int device)
     ctx->no_stage = getenv("PORESEQ_B200_NO_STAGE") != nullptr;
     if (const char* e = getenv("PORESEQ_B200_VIT_CLUSTER")) ctx->vit_cluster = atoi(e) != 0;
     if (const char* e = getenv("PORESEQ_B200_FILL2")) ctx->fill2 = atoi(e) != 0;
+    if (const char* e = getenv("PORESEQ_B200_BLOCKING_WAIT")) ctx->blocking_wait = atoi(e) != 0;
     if (const char* e = getenv("PORESEQ_B200_CONSENSUS")) ctx->threads_consensus = std::string(e) == "threads";
     if (const char* e = getenv("PORESEQ_B200_GROUPS")) ctx->consensus_groups = std::max(1, atoi(e));
     if (const char* e = getenv("PORESEQ_B200_S32_WARPS")) ctx->s32_warps = std::max(2, std::min(atoi(e), PS_SCORE32_MAX_WARPS));
@@ -2072,7 +2085,7 @@ int ps_score_mutations_sharded(ps_region* R, int n, const int* start, const char
     CU(cudaMemcpyAsync(d_count, &local, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     TRY(psi_comm_allreduce_sum(ctx, d_count, 1));
     CU(cudaMemcpyAsync(&total, d_count, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU((cudaError_t)ps_stream_wait(ctx));
     std::vector<HostMut> v = gather_muts(n, start, orig, mut, nullptr);
     TRY(ps_score_mutation_list(R, v, -1e-6, (int)total));
     for (int i = 0; i < n; i++) scores[i] = v[i].score;

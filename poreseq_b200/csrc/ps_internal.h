@@ -45,6 +45,9 @@ struct ps_ctx
     cudaStream_t stream = nullptr;
     cudaStream_t side = nullptr;              // runs the minority launch classes of the wide fill beside the main one
     cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+    cudaEvent_t wait_ev = nullptr;            // blocking-sync event (see ps_stream_wait)
+    bool blocking_wait = false;               // wait for the stream by sleeping on an event instead of spinning (PORESEQ_B200_BLOCKING_WAIT,
+                                              // and every context ps_consensus_batch drives from its own threads: more threads than cores)
     cudaEvent_t tev[PS_T_COUNT + 1];
     double timing[PS_T_COUNT] = {0};
     double wide_cells = 0, narrow_cells = 0;
@@ -163,6 +166,8 @@ struct ps_region                              // cpp/AlignData.h:24-34
 };
 
 void ps_set_error(ps_ctx* ctx, const char* fmt, ...);
+// wait until everything enqueued on the context's stream is done; cudaError_t
+int ps_stream_wait(ps_ctx* ctx);
 // PS_E_ARG with a message naming the entry point (ctx may be null: the message is then what ps_last_error(NULL) returns)
 #define PS_BAD_ARGS(ctx_, fn_) (ps_set_error((ctx_), "%s: bad arguments", (fn_)), PS_E_ARG)
 // fn(i) for i in [0, n) on the library's host worker threads (PORESEQ_B200_THREADS, default

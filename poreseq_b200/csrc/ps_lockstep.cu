@@ -271,7 +271,7 @@ int ps_consensus_lockstep(ps_ctx* ctx, ps_region* const* regions, int n_regions,
     }
     Lanes L;
     L.ctx.push_back(ctx);
-    for (int k = 0; k + 1 < in_flight; k++) { ctx->helpers[k]->precision = ctx->precision; L.ctx.push_back(ctx->helpers[k]); }
+    for (int k = 0; k + 1 < in_flight; k++) { ctx->helpers[k]->precision = ctx->precision; ctx->helpers[k]->blocking_wait = true; L.ctx.push_back(ctx->helpers[k]); }
     // regions the loop runs for (Mutate.py:50-53: fewer than 5 events -> untouched); all of them move to this context
     std::vector<ps_region*> regs;
     std::vector<ps_ctx*> home;

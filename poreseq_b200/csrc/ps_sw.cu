@@ -252,13 +252,13 @@ int psi_swfull_batch(ps_ctx* ctx, const std::string& s1, const std::vector<std::
         CU(cudaGetLastError());
         if (ctx->trace)
         {
-            CU(cudaStreamSynchronize(ctx->stream));
+            CU((cudaError_t)ps_stream_wait(ctx));
             fprintf(stderr, "[ps] swfull batch: %zu pairs of %d x ~%zu: fill %.2f ms, traceback %.2f ms\n", np, n1, cat.size() / np, t1 - t0, now() - t1);
         }
         CU(cudaMemcpyAsync(best.data(), d_best, np * sizeof(SwBest), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaMemcpyAsync(o1.data(), d_o1, (size_t)out_off * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaMemcpyAsync(o2.data(), d_o2, (size_t)out_off * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
+        CU((cudaError_t)ps_stream_wait(ctx));
         for (size_t k = 0; k < np; k++)
         {
             SWResult& r = out[a + k];

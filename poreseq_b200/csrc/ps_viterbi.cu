@@ -507,7 +507,7 @@ int ps_viterbi_list(ps_region* R, int nkeep, double skip_prob, double stay_prob,
     PinVec<double> last = ctx->pinned<double>("vit_last_h");
     if (!last.resize(N_STATES)) { ps_set_error(ctx, "out of host memory staging ViterbiMutate"); return PS_E_INTERNAL; }
     CU(cudaMemcpyAsync(last.data(), d_last, N_STATES * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU((cudaError_t)ps_stream_wait(ctx));
     const double t_chain = now();
     const int startst = (int)(std::max_element(last.begin(), last.end()) - last.begin());
 
@@ -517,7 +517,7 @@ int ps_viterbi_list(ps_region* R, int nkeep, double skip_prob, double stay_prob,
         PinVec<int> bp = ctx->pinned<int>("vit_bp_h");
         if (!bp.resize((size_t)n_pos * N_STATES)) { ps_set_error(ctx, "out of host memory staging ViterbiMutate"); return PS_E_INTERNAL; }
         CU(cudaMemcpyAsync(bp.data(), d_bp, bp.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
+        CU((cudaError_t)ps_stream_wait(ctx));
         int cur = startst;
         for (int t = n_pos - 1; t >= 0; t--) { path[t] = cur; cur = bp[(size_t)t * N_STATES + cur]; }
         out.push_back(states_to_sequence(path));
@@ -540,7 +540,7 @@ int ps_viterbi_list(ps_region* R, int nkeep, double skip_prob, double stay_prob,
     ctx->launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(paths.data(), d_paths, paths.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU((cudaError_t)ps_stream_wait(ctx));
     if (ctx->trace)
         fprintf(stderr, "[ps] ViterbiMutate: %d positions, %d reads: host + emission pooling %.1f ms, chain %.1f ms, %d sampled walks %.1f ms\n",
                 n_pos, E, t_obs - t_begin, t_chain - t_obs, nkeep, now() - t_chain);
