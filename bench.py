@@ -127,10 +127,12 @@ def algorithmic_cells(reg):
 
 # ------------------------------------------------------------------------------------------------
 def cpu_score_points_worker(args):
-    which, seed = args
+    """One region through the reference's ScorePoints on this core.  `args` = (checker, seed) or (checker, region): the
+    reference arm hands over regions generated before its timed region starts."""
+    which, what = args
     from oracle import binding
     chk = binding.load(which)
-    reg = synth.make_region(REGION_LEN, COVERAGE, seed=seed)
+    reg = synth.make_region(REGION_LEN, COVERAGE, seed=what) if isinstance(what, int) else what
     t0 = time.perf_counter()
     chk.score_points(reg)
     return time.perf_counter() - t0
@@ -412,12 +414,15 @@ def run_reference_arm(args, rank, world, out=sys.stdout):
     reg = synth.make_region(REGION_LEN, COVERAGE, seed=1)
     wide, narrow = algorithmic_cells(reg)
     cells_per_region = wide + narrow
+    # the inputs of every step exist before the clock starts (the workers get them pickled: ~2 MB per region)
+    steps_in = [[(which, synth.make_region(REGION_LEN, COVERAGE, seed=2000 + k * cores + i)) for i in range(cores)]
+                for k in range(args.steps_ref)]
     with mp.get_context("spawn").Pool(cores) as pool:
         for w in range(args.warmup_ref):
             pool.map(cpu_score_points_worker, [(which, 1000 + i) for i in range(cores)])
         t0 = time.perf_counter()
         for k in range(args.steps_ref):
-            pool.map(cpu_score_points_worker, [(which, 2000 + k * cores + i) for i in range(cores)])
+            pool.map(cpu_score_points_worker, steps_in[k])
         dt = time.perf_counter() - t0
     value = cells_per_region * cores * args.steps_ref / dt / 1e9
     sample = "%d regions of 1 kb x 10x per step, one process per region on %d host cores" % (cores, cores)
