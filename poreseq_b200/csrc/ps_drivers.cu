@@ -228,8 +228,7 @@ int ps_find_mutation_list(ps_region* R, const std::vector<std::string>& seeds, s
     ps_parallel_for((int)S, [&](int s) {
         if (need[s])
         {
-            ps_region* nd = new ps_region(*R);
-            nd->seqlikes.clear();
+            ps_region* nd = ps_shadow_region(R);          // level data borrowed from R, not copied
             als[s] = sw_gpu ? psi_map_alignments_with(nd, seeds[s], sw[s]) : psi_map_alignments(nd, seeds[s]);
             nds[s] = nd;
         }

@@ -782,7 +782,9 @@ int Job::build()
         const EvDesc& d = ev[e];
         he.ensure_refs();
         const size_t at = (size_t)d.lev_off, n = (size_t)he.n0;
-        if ((he.staged++ == 0 && he.levrec.empty()) || he.ext_mean)
+        if (he.ext_levrec)
+            memcpy(lev.data() + at, he.ext_levrec, n * sizeof(LevIn));     // a shadow region: the records of the event it shadows
+        else if ((he.staged++ == 0 && he.levrec.empty()) || he.ext_mean)
         {
             // first batch of this event: (mean, stdv, 3 log stdv) straight into the staging buffer (the log is the only
             // transcendental of the path, cpp/EventData.h:218-220); an event that comes back (Refine's recursion, the
@@ -1761,6 +1763,28 @@ int ps_make_mutation_list(ps_region* R, std::vector<HostMut> muts, int* nbases)
     }
     *nbases = changed;
     return PS_OK;
+}
+
+ps_region* ps_shadow_region(const ps_region* R)
+{
+    ps_region* nd = new ps_region();
+    nd->ctx = R->ctx;
+    nd->bases = R->bases; nd->states = R->states;
+    nd->models = R->models;
+    nd->params = R->params;
+    nd->events.resize(R->events.size());
+    for (size_t e = 0; e < R->events.size(); e++)
+    {
+        const HostEvent& src = R->events[e];
+        HostEvent& he = nd->events[e];
+        he.n0 = src.n0; he.model = src.model; he.complement = src.complement;
+        he.ri_empty = src.ri_empty; he.refstart = src.refstart; he.refend = src.refend;
+        he.ref_align = src.ref_align;                     // remapped by the caller, then update_refs
+        he.ref_like.assign((size_t)src.n0, 0.0);          // written by the realignment
+        he.ext_mean = src.mean.data(); he.ext_stdv = src.stdv.data();
+        he.ext_levrec = src.levrec.size() == (size_t)src.n0 * 3 ? src.levrec.data() : nullptr;
+    }
+    return nd;
 }
 
 void ps_region::rng_seed(unsigned seed)

@@ -127,6 +127,7 @@ struct HostEvent                              // cpp/EventData.h:78-229
     // mean / stdv / ref_align / ref_like above stay empty then
     const double* ext_mean = nullptr;
     const double* ext_stdv = nullptr;
+    const double* ext_levrec = nullptr;       // borrowed staged level records (3 doubles per level) of the event this one shadows
     void update_refs();
     void update_refs_from(const double* ra);  // the same from an array that is not this event's own
     void ensure_refs() { if (ri_stale) update_refs(); }
@@ -180,6 +181,9 @@ int ps_score_mutation_list(ps_region* R, std::vector<HostMut>& muts, double bias
 int ps_make_mutation_list(ps_region* R, std::vector<HostMut> muts, int* nbases);
 void ps_make_mutation_pass(ps_region* R, std::vector<HostMut> muts, int* changed_out, std::vector<HostMut>* deferred);
 int ps_score_mutation_lists(ps_ctx* ctx, const std::vector<ps_region*>& regs, const std::vector<std::vector<HostMut>*>& lists);
+// A copy of R for FindMutations' seed realignments: its own sequence, alignments and models, the level data (mean, stdv,
+// staged level records) borrowed from R's events, which must outlive it and have their level records made (ensure_levrec)
+ps_region* ps_shadow_region(const ps_region* R);
 int ps_consensus_lockstep(ps_ctx* ctx, ps_region* const* regions, int n_regions, int reps, int point_width, int in_flight);
 
 struct SWResult                               // cpp/swlib.h:25-33

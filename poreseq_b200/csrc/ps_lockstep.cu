@@ -115,8 +115,7 @@ int find_mutations(Lanes& L, const std::vector<ps_region*>& regs, const std::vec
         const std::string& seed = (*seeds[r])[s];
         if (need[r][s])
         {
-            ps_region* nd = new ps_region(*R);
-            nd->seqlikes.clear();
+            ps_region* nd = ps_shadow_region(R);          // level data borrowed from R, not copied
             als[r][s] = sw_gpu[r] ? psi_map_alignments_with(nd, seed, sw[r][s]) : psi_map_alignments(nd, seed);
             nds[r][s] = nd;
         }
