@@ -411,37 +411,50 @@ int ps_viterbi_list(ps_region* R, int nkeep, double skip_prob, double stay_prob,
     std::vector<VitSlot> slots;
     std::vector<int> slot_off(1, 0);
     int max_lik = 1;
+    // What each candidate position holds (the reads sitting on it, pooled level / stdv; how many reads span it) does not
+    // depend on the positions before it: computed for all candidates on the worker threads, then the reference's
+    // sequential skip / stop rule (cpp/Viterbi.cpp:310-325) walks over the results.
+    const int ref0 = refind;
+    const int n_cand = (ref0 >= 0 && ref0 <= maxref + 1) ? maxref + 2 - ref0 : 0;
+    std::vector<std::vector<VitSlot>> cand(n_cand);
+    std::vector<int> cand_nal(n_cand, 0);
+    ps_parallel_for(n_cand, [&](int q) {
+        const int ri = ref0 + q;
+        std::vector<VitSlot>& out = cand[q];
+        int nal = 0;
+        for (int k = 0; k < E; k++)
+        {
+            const HostEvent& ev = R->events[k];
+            if (ri >= ev.refstart && ri <= ev.refend) nal++;
+            const int f = first[k][ri];
+            if (f < 0) continue;
+            double lvl = ev.mean[f], sd = ev.stdv[f];
+            int cnt = 1;
+            for (int i = f + 1; i < ev.n0 && ev.ref_align[i] <= ri; i++)
+                if (ev.ref_align[i] > 0) { lvl += ev.mean[i]; sd += ev.stdv[i]; cnt++; }
+            lvl = lvl / cnt;
+            sd = sd / cnt;
+            VitSlot s;
+            s.model = ev.model; s.pad = 0; s.lvl = lvl; s.sd = sd; s.logsd = std::log(sd);
+            out.push_back(s);
+        }
+        cand_nal[q] = nal;
+    });
     while (true)
     {
-        const size_t mark = slots.size();
-        int nlik = 0;
-        if (refind >= 0 && refind <= maxref + 1)
-            for (int k = 0; k < E; k++)
-            {
-                const HostEvent& ev = R->events[k];
-                int f = first[k][refind];
-                if (f < 0) continue;
-                double lvl = ev.mean[f], sd = ev.stdv[f];
-                int cnt = 1;
-                for (int i = f + 1; i < ev.n0 && ev.ref_align[i] <= refind; i++)
-                    if (ev.ref_align[i] > 0) { lvl += ev.mean[i]; sd += ev.stdv[i]; cnt++; }
-                lvl = lvl / cnt;
-                sd = sd / cnt;
-                VitSlot s;
-                s.model = ev.model; s.pad = 0; s.lvl = lvl; s.sd = sd; s.logsd = std::log(sd);
-                slots.push_back(s);
-                nlik++;
-            }
-        int nal = 0;
-        for (const HostEvent& ev : R->events)
-            if (refind >= ev.refstart && refind <= ev.refend) nal++;
+        int nlik = 0, nal = 0;
+        const std::vector<VitSlot>* here = nullptr;
+        if (refind >= ref0 && refind - ref0 < n_cand) { here = &cand[refind - ref0]; nlik = (int)here->size(); nal = cand_nal[refind - ref0]; }
+        else
+            for (const HostEvent& ev : R->events)
+                if (refind >= ev.refstart && refind <= ev.refend) nal++;
         if (nlik <= nal * 0.2)
         {
-            slots.resize(mark);
             if (nal == 0) break;
             refind++;
             continue;
         }
+        slots.insert(slots.end(), here->begin(), here->end());
         slot_off.push_back((int)slots.size());
         max_lik = std::max(max_lik, nlik);
         refind++;
