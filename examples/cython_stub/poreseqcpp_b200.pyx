@@ -35,6 +35,7 @@ cdef extern from "poreseq_b200.h":
     int ps_region_sequence_length(ps_region*)
     int ps_region_get_event_align(ps_region*, int e, double* ref_align, double* ref_like)
     int ps_score_alignments(ps_region*, double* scores, double* likes)
+    int ps_score_events(ps_region*, double* scores)
     int ps_refine(ps_region*, int* nbases)
     int ps_swfull(const char* s1, const char* s2, int* inds1, int* inds2, int cap, int* n, int* score, double* acc)
     int ps_seq_to_states(const char* seq, int len, int* states)
@@ -136,7 +137,7 @@ class PSAlign(object):
         cdef ps_region* r = PythonToRegion(self)
         cdef cnp.ndarray scores = np.zeros(len(self.events))
         try:
-            if ps_score_alignments(r, getPr(scores), NULL) != 0:
+            if ps_score_events(r, getPr(scores)) != 0:
                 raise RuntimeError(_error())
             return scores.tolist()
         finally:
