@@ -33,6 +33,10 @@
 
 using namespace psdev;
 
+#ifndef PS_FILL_MINB
+#define PS_FILL_MINB 3            // CTAs of the 160-thread fill per SM (128 registers); 4 = 96 registers, measured slower
+#endif
+
 // ------------------------------------------------------------------------------------------
 // errors
 static std::string g_create_error;
@@ -288,7 +292,7 @@ int ps_ctx::init()
     for (int i = 0; i <= PS_T_COUNT; i++) CU(cudaEventCreate(&tev[i]));
     CU(cudaEventCreateWithFlags(&wait_ev, cudaEventBlockingSync | cudaEventDisableTiming));
     CU(cudaFuncSetAttribute(k_backtrace, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
-    CU(cudaFuncSetAttribute(k_fill<160, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    CU(cudaFuncSetAttribute(k_fill<160, PS_FILL_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     CU(cudaFuncSetAttribute(k_fill<192, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU(cudaFuncSetAttribute(k_fill<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024));
     CU(cudaFuncSetAttribute(k_mutscore_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -1132,7 +1136,7 @@ int Job::run(bool full)
             LAUNCHED();
             k_fill_best<<<dim3(off3, dirs), 256, 0, ctx->stream>>>(b, fa);
             LAUNCHED();
-            if (fill_count[3]) { k_fill<160, 3><<<dim3(fill_count[3], dirs), 32, smem160, ctx->stream>>>(b, off3); LAUNCHED(); }
+            if (fill_count[3]) { k_fill<160, PS_FILL_MINB><<<dim3(fill_count[3], dirs), 32, smem160, ctx->stream>>>(b, off3); LAUNCHED(); }
         }
         else
         {
@@ -1143,8 +1147,8 @@ int Job::run(bool full)
             LAUNCHED();
         }
         if (fill_count[1]) { k_fill<192, 2><<<dim3(fill_count[1], dirs), 192, smem192, other>>>(b, off1); LAUNCHED(); }
-        if (fill_count[3]) { k_fill<160, 3><<<dim3(fill_count[3], dirs), 32, smem160, other>>>(b, off3); LAUNCHED(); }
-        if (fill_count[0]) { k_fill<160, 3><<<dim3(fill_count[0], dirs), 160, smem160, ctx->stream>>>(b, 0); LAUNCHED(); }
+        if (fill_count[3]) { k_fill<160, PS_FILL_MINB><<<dim3(fill_count[3], dirs), 32, smem160, other>>>(b, off3); LAUNCHED(); }
+        if (fill_count[0]) { k_fill<160, PS_FILL_MINB><<<dim3(fill_count[0], dirs), 160, smem160, ctx->stream>>>(b, 0); LAUNCHED(); }
         }
         if (forked)
         {
