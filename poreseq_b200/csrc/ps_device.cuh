@@ -129,6 +129,15 @@ __device__ __forceinline__ double div_by(double a, double b, double r)
     return q;
 }
 
+// c = x, code = k when x > c -- as setp + selp.  Written in C++ with c == 0 on entry, NVVM turns the first compare of a
+// chain into max.f64, which sm_100 (no FP64 min/max instruction) expands into an 11-instruction NaN-aware sequence;
+// the explicit form is DSETP + 2 FSEL + SEL, and it is the reference's own compare-and-assign (cpp/Alignment.cpp:243-263).
+__device__ __forceinline__ void take_gt(double x, int k, double& c, int& code)
+{
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %2, %0;\n\tselp.f64 %0, %2, %0, p;\n\tselp.s32 %1, %3, %1, p;\n\t}"
+        : "+d"(c), "+r"(code) : "d"(x), "r"(k));
+}
+
 // emission: lognormpdf + logigpdf + lik_offset   (cpp/AlignUtil.h:34-53, cpp/Alignment.cpp:169-173)
 // x = level mean, y = level stdv (ry its reciprocal), lsd3 = 3*log(stdv) of the level the
 // reference indexes (quirk A.3-1: the forward pass reads log_stdv[n0-i] beside stdv[i-1])
@@ -287,8 +296,9 @@ struct StripRec               // 192 bytes: the two columns of a strip, ready to
     int i0[2], i1[2], s[2];   // band and state of each column (empty band, s = -1 past the last column)
     int pp0, pp1;             // band of the column just before the strip
     int rlo, rhi;             // row pairs covered by the union of the two bands (1, 0 for the sentinel strip J)
+    int lean_lo, lean_hi;     // row pairs whose four cells are interior ones (see fill_wave); empty = (1 << 30, -1)
     int slot4;                // (j % ts) * 4: offset of the strip's tile inside a step's run
-    int pad[5];
+    int pad[3];
 };
 static_assert(sizeof(StripRec) == 192, "StripRec is copied as 16-byte chunks (the first eleven carry data)");
 
@@ -331,10 +341,21 @@ __global__ void k_strips(Batch b)
         }
         r.p[c] = md.st[max(r.s[c], 0)];
     }
+    r.lean_lo = 1 << 30; r.lean_hi = -1;
     if (j < J)
     {
         r.rlo = (lo - 1) >> 1; r.rhi = (hi - 1) >> 1;
-        if (j > 0) col_band(b, ev, rev, CW * j, r.pp0, r.pp1);
+        if (j > 0)
+        {
+            col_band(b, ev, rev, CW * j, r.pp0, r.pp1);
+            // interior row pairs: rows 2r+1 and 2r+2 inside both columns' bands and the band of the column before,
+            // 2r+1 not a first row, both states valid:  2r+1 > max(i0a, i0b, pp0)  and  2r+2 <= min(i1a, i1b, pp1)
+            if (r.s[0] >= 0 && r.s[1] >= 0)
+            {
+                r.lean_lo = (max(max(r.i0[0], r.i0[1]), r.pp0) + 1) >> 1;
+                r.lean_hi = (min(min(r.i1[0], r.i1[1]), r.pp1) - 2) >> 1;
+            }
+        }
     }
     b.strips[ev.strip_off + (rev ? J + 1 : 0) + j] = r;
 }
@@ -391,14 +412,14 @@ __device__ __forceinline__ void cell_pre(bool inb, bool valid, bool first, bool 
     const double ext = (upS + eU) + t.lext;
     double s = first ? NEG : 0.0;
     int q = 0;
-    if (stay > s) { s = stay; q = 1; }
-    if (ext > s) { s = ext; q = 2; }
+    take_gt(stay, 1, s, q);
+    take_gt(ext, 2, s, q);
     double c = 0.0;
     int sc = ST_STOP;
-    if (match > c) { c = match; sc = diag_ok ? ST_MATCH : ST_IMPLICIT; }
-    if (ins > c) { c = ins; sc = ST_INSERT; }
-    if (ignore > c) { c = ignore; sc = ST_IGNORE; }
-    if (s > c) { c = s; sc = ST_STAY; }
+    take_gt(match, diag_ok ? ST_MATCH : ST_IMPLICIT, c, sc);
+    take_gt(ins, ST_INSERT, c, sc);
+    take_gt(ignore, ST_IGNORE, c, sc);
+    take_gt(s, ST_STAY, c, sc);
     if (INV && !valid) { c = 0.0; s = 0.0; sc = ST_STOP; q = 0; }
     M1 = inb ? c : NEG; m1 = inb ? sc : ST_STOP; S = inb ? s : NEG; ss = inb ? q : 0;
 }
@@ -423,7 +444,8 @@ struct StripRegs
     int j;                    // strip index, 1<<29 when past the end
     int rlo, rhi, pp0, pp1;
     int i0a, i1a, sa, i0b, i1b, sb;
-    int slot4;
+    int slot4;                // k_fill2 only
+    int lean_lo, lean_hi;
 };
 
 template <int MAXT>
@@ -441,7 +463,7 @@ __device__ __forceinline__ void strip_from_smem(const double2* nxt, StripRegs& c
     c.sa = __double2loint(v[9].x); c.sb = __double2hiint(v[9].x);
     c.pp0 = __double2loint(v[9].y); c.pp1 = __double2hiint(v[9].y);
     c.rlo = __double2loint(v[10].x); c.rhi = __double2hiint(v[10].x);
-    c.slot4 = __double2loint(v[10].y);
+    c.lean_lo = __double2loint(v[10].y); c.lean_hi = __double2hiint(v[10].y);
 }
 
 template <int MAXT>
@@ -456,10 +478,13 @@ struct RowRecs { LevelRec a, b; };                        // row records of the 
 
 __device__ __forceinline__ void load_rows(const LevelRec* rows, int n0, int r, RowRecs& o)
 {
-    // rows ia = 2r+1, ib = 2r+2 clamped into the event (a clamped row is outside every band)
-    const int ia = min(max(2 * r + 1, 1), n0), ib = min(max(2 * r + 2, 1), n0);
-    o.a = rows[ia - 1];
-    o.b = rows[ib - 1];
+    // rows ia = 2r+1 clamped into the event and ia + 1: two adjacent records, one address.  A clamped row is outside
+    // every band, and so is row n0 + 1 (the record after the event's last one: the next event's first, or the spare
+    // record at the end of the array) -- their emissions are computed for nobody.
+    const int ia = min(max(2 * r + 1, 1), n0);
+    const LevelRec* p = rows + (ia - 1);
+    o.a = p[0];
+    o.b = p[1];
 }
 
 // split-phase CTA barrier on an mbarrier object: a warp signals that its step is written, prepares its
@@ -549,6 +574,10 @@ __device__ __forceinline__ void fill_wave(const Batch& b, const EvDesc& ev, cons
     }
     load_rows(rows, n0, dstart + 1 - ((dstart + 1 > cur.j + cur.rhi) ? (cur.j + T < J ? cur.j + T : 1 << 29) : cur.j), rr);
     __syncthreads();                                      // the barrier object is initialised
+    // band storage of step d: the run starts at band_off + d * rs, this thread's tile is at + 4 * tid (a wave class has
+    // ts == blockDim.x slots per step, Job::build, so strip j's slot j % ts is the thread's own index)
+    long long a = ev.band_off + (long long)dstart * ev.rs + 4 * tid;
+    unsigned slot = 0, par = 0;                           // P2P: barrier slot 8 * (q & 7) and parity (q >> 3) & 1 of q = d - dstart
     for (int d = dstart; d <= dend; d++)
     {
 #ifndef PS_ABL_NOSYNC
@@ -557,27 +586,18 @@ __device__ __forceinline__ void fill_wave(const Batch& b, const EvDesc& ev, cons
         if (false)
 #endif
         {
-            if (P2P)
-            {
-                const int q1 = d - 1 - dstart;                           // the left warp has written step d-1
-                mbar_wait(bar_left + 8 * (q1 & 7), (unsigned)(q1 >> 3) & 1u);
-            }
+            if (P2P)                                                     // the left warp has written step d-1
+                mbar_wait(bar_left + ((slot + 56u) & 63u), slot == 0 ? par ^ 1u : par);
             else { mbar_wait(bar0, parity); parity ^= 1u; }              // every warp has written step d-1
         }
         const int r = d - cur.j;
         const int w0 = ph, w1 = (ph + RD - 1) & (RD - 1), w2 = (ph + RD - 2) & (RD - 1);   // steps d, d-1, d-2
 #ifndef PS_NO_LEAN
         // Is every tile of this warp's step an interior one (all four cells inside their bands and past their first
-        // rows, every predecessor inside the band of the column before, valid states)?  Then the warp runs the same
-        // arithmetic with every mask a compile-time `true`: the selects that only apply masks fold away.
-        bool warp_lean;
-        {
-            const int ia = 2 * r + 1, ib = ia + 1;
-            const bool act = r >= cur.rlo && r <= cur.rhi;
-            const bool mine = (!INV || (cur.sa >= 0 && cur.sb >= 0)) && ia > cur.i0a && ia > cur.i0b && ib <= cur.i1a && ib <= cur.i1b &&
-                              ia > cur.pp0 && ib <= cur.pp1 && cur.j > 0;
-            warp_lean = __all_sync(0xffffffffu, !act || mine);
-        }
+        // rows, every predecessor inside the band of the column before, valid states: the strip's lean_lo..lean_hi,
+        // k_strips)?  Then the warp runs the same arithmetic with every mask a compile-time `true`: the selects that
+        // only apply masks fold away.
+        const bool warp_lean = __all_sync(0xffffffffu, !(r >= cur.rlo && r <= cur.rhi) || (r >= cur.lean_lo && r <= cur.lean_hi));
 #endif
         if (r >= cur.rlo && r <= cur.rhi)
         {
@@ -637,7 +657,6 @@ __device__ __forceinline__ void fill_wave(const Batch& b, const EvDesc& ev, cons
             if (v1 && CB > best1) { best1 = CB; besti1 = ia; }
             if (v1 && CD > best1) { best1 = CD; besti1 = ib; }
             upC0 = CC; upS0 = SC; upE0 = eC; upC1 = CD; upS1 = SD; upE1 = eD;
-            const long long a = ev.band_off + (long long)d * ev.rs + cur.slot4;                 // the tile's run
             double2* pm = reinterpret_cast<double2*>(o.Mm + a);
             double2* ps = reinterpret_cast<double2*>(o.Ms + a);
             pm[0] = make_double2(CA, CB); pm[1] = make_double2(CC, CD);
@@ -648,7 +667,9 @@ __device__ __forceinline__ void fill_wave(const Batch& b, const EvDesc& ev, cons
                                                            ((unsigned)(kC | (qC << 3)) << 16) | ((unsigned)(kD | (qD << 3)) << 24);
         }
         __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(P2P ? bar_mine + 8 * ((d - dstart) & 7) : bar0);   // this warp's part of step d is in shared memory
+        if ((tid & 31) == 0) mbar_arrive(P2P ? bar_mine + slot : bar0);   // this warp's part of step d is in shared memory
+        slot = (slot + 8u) & 63u; par ^= (slot == 0);
+        a += ev.rs;
         ph = (ph + 1) & (RD - 1);
         // ---- preparation of step d+1: overlaps the other warps' step d ----
         if (d + 1 > cur.j + cur.rhi)

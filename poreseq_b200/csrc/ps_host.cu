@@ -921,8 +921,8 @@ int Job::upload()
     TRY(room(ctx, "Fs", cells, &b.Fs));
     TRY(room(ctx, "Fstep", cells, &b.Fstep));
     TRY(room(ctx, "strips", (size_t)std::max<long long>(n_strips, 1), &b.strips));
-    TRY(room(ctx, "rowF", (size_t)std::max<long long>(n_levels, 1), &b.rowF));
-    TRY(room(ctx, "rowB", (size_t)std::max<long long>(n_levels, 1), &b.rowB));
+    TRY(room(ctx, "rowF", (size_t)std::max<long long>(n_levels, 1) + 1, &b.rowF));     // + 1: load_rows reads rows ia, ia + 1
+    TRY(room(ctx, "rowB", (size_t)std::max<long long>(n_levels, 1) + 1, &b.rowB));
     TRY(room(ctx, "Fi0", (size_t)n_cols, &b.Fi0));
     TRY(room(ctx, "Flen", (size_t)n_cols, &b.Flen));
     TRY(room(ctx, "Fcb", (size_t)n_cols, &b.Fcb));

@@ -17,7 +17,7 @@ struct StateParams            // one 64-byte record per 5-mer state (cpp/EventDa
     double r_lev_stdv, r_sd_mean;      // correctly rounded reciprocals of the two divisors (host IEEE division)
 };
 
-struct LevelRec               // one 32-byte record per event level (cpp/EventData.h:96-101, :218-220)
+struct __align__(16) LevelRec // one 32-byte record per event level (cpp/EventData.h:96-101, :218-220)
 {
     double mean, stdv;
     double rstdv;                      // RN(1 / stdv)
