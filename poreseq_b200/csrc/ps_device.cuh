@@ -42,6 +42,7 @@ struct EvDesc                 // one event of one region in the batch
     long long strip_off;      // first StripRec of this event: forward strips 0..J (J = sentinel), then reverse
     int       ts;             // strips that can be live on one wavefront step (band storage slot count)
     int       rs;             // row stride of the band storage = ts * CW
+    int       lazy;           // every thread idles >= 9 steps between two strips: strips are switched on every 8th step only
 };
 
 struct MutDev
@@ -399,7 +400,9 @@ struct FillOut               // where one direction's band columns go
 // matrices; nobody reads them except the column's own first row, for which NEG is exactly what makes
 // stay / extend / insert lose (cpp/Alignment.cpp:229-237: a first row has no cell above).  INV: the
 // column's state may be invalid (non-ACGT base), its in-band cells are all zero (cpp/Alignment.cpp:162).
-template <bool INV>
+// SH: the step codes come out shifted to the byte of the cell inside the tile's packed word (main code << SH, stay
+// code << SH + 3), so that packing four cells is three ORs.
+template <bool INV, int SH = 0>
 __device__ __forceinline__ void cell_pre(bool inb, bool valid, bool first, bool diag_ok, double Pd, double eM, double eU,
                                          double upC, double upS, const Trans& t,
                                          double& M1, int& m1, double& S, int& ss)
@@ -412,16 +415,16 @@ __device__ __forceinline__ void cell_pre(bool inb, bool valid, bool first, bool 
     const double ext = (upS + eU) + t.lext;
     double s = first ? NEG : 0.0;
     int q = 0;
-    take_gt(stay, 1, s, q);
-    take_gt(ext, 2, s, q);
+    take_gt(stay, 1 << (SH + 3), s, q);
+    take_gt(ext, 2 << (SH + 3), s, q);
     double c = 0.0;
-    int sc = ST_STOP;
-    take_gt(match, diag_ok ? ST_MATCH : ST_IMPLICIT, c, sc);
-    take_gt(ins, ST_INSERT, c, sc);
-    take_gt(ignore, ST_IGNORE, c, sc);
-    take_gt(s, ST_STAY, c, sc);
-    if (INV && !valid) { c = 0.0; s = 0.0; sc = ST_STOP; q = 0; }
-    M1 = inb ? c : NEG; m1 = inb ? sc : ST_STOP; S = inb ? s : NEG; ss = inb ? q : 0;
+    int sc = ST_STOP << SH;
+    take_gt(match, (diag_ok ? ST_MATCH : ST_IMPLICIT) << SH, c, sc);
+    take_gt(ins, ST_INSERT << SH, c, sc);
+    take_gt(ignore, ST_IGNORE << SH, c, sc);
+    take_gt(s, ST_STAY << SH, c, sc);
+    if (INV && !valid) { c = 0.0; s = 0.0; sc = ST_STOP << SH; q = 0; }
+    M1 = inb ? c : NEG; m1 = inb ? sc : (ST_STOP << SH); S = inb ? s : NEG; ss = inb ? q : 0;
 }
 
 __device__ __forceinline__ void cell_fin(bool skip_pred, double Pc, double M1, int m1, const Trans& t, double& C, int& code)
@@ -429,7 +432,7 @@ __device__ __forceinline__ void cell_fin(bool skip_pred, double Pc, double M1, i
     const double skip = Pc + t.lskip;
     const bool w = skip_pred && (skip >= M1);
     C = w ? skip : M1;
-    code = (w && skip > 0.0) ? ST_SKIP : m1;
+    code = (w && skip > 0.0) ? ST_SKIP : m1;              // ST_SKIP == 0 in every byte
 }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
@@ -626,27 +629,27 @@ __device__ __forceinline__ void fill_wave(const Batch& b, const EvDesc& ev, cons
             const bool lean = warp_lean;
             if (lean)
             {
-                cell_pre<false>(true, true, false, true, Lm, REV ? LEm : eA, REV ? upE0 : eA, upC0, upS0, tr, M, m, SA, qA);
+                cell_pre<false, 0>(true, true, false, true, Lm, REV ? LEm : eA, REV ? upE0 : eA, upC0, upS0, tr, M, m, SA, qA);
                 cell_fin(true, La, M, m, tr, CA, kA);
-                cell_pre<false>(true, true, false, true, upC0, REV ? upE0 : eB, REV ? upE1 : eB, upC1, upS1, tr, M, m, SB, qB);
+                cell_pre<false, 8>(true, true, false, true, upC0, REV ? upE0 : eB, REV ? upE1 : eB, upC1, upS1, tr, M, m, SB, qB);
                 cell_fin(true, CA, M, m, tr, CB, kB);
-                cell_pre<false>(true, true, false, true, La, REV ? LEa : eC, REV ? eA : eC, CA, SA, tr, M, m, SC, qC);
+                cell_pre<false, 16>(true, true, false, true, La, REV ? LEa : eC, REV ? eA : eC, CA, SA, tr, M, m, SC, qC);
                 cell_fin(true, Lb, M, m, tr, CC, kC);
-                cell_pre<false>(true, true, false, true, CA, REV ? eA : eD, REV ? eB : eD, CB, SB, tr, M, m, SD, qD);
+                cell_pre<false, 24>(true, true, false, true, CA, REV ? eA : eD, REV ? eB : eD, CB, SB, tr, M, m, SD, qD);
                 cell_fin(true, CC, M, m, tr, CD, kD);
             }
             else
 #endif
             {
             // row ia
-            cell_pre<INV>(inA, v0, ia == cur.i0a, dgA, Lm, REV ? (dgA ? LEm : 0.0) : eA, REV ? upE0 : eA, upC0, upS0, tr, M, m, SA, qA);
+            cell_pre<INV, 0>(inA, v0, ia == cur.i0a, dgA, Lm, REV ? (dgA ? LEm : 0.0) : eA, REV ? upE0 : eA, upC0, upS0, tr, M, m, SA, qA);
             cell_fin(skA && inA && v0, La, M, m, tr, CA, kA);
-            cell_pre<INV>(inB, v1, ia == cur.i0b, dgB, upC0, REV ? (dgB ? upE0 : 0.0) : eB, REV ? upE1 : eB, upC1, upS1, tr, M, m, SB, qB);
+            cell_pre<INV, 8>(inB, v1, ia == cur.i0b, dgB, upC0, REV ? (dgB ? upE0 : 0.0) : eB, REV ? upE1 : eB, upC1, upS1, tr, M, m, SB, qB);
             cell_fin(skB && inB && v1, CA, M, m, tr, CB, kB);
             // row ib
-            cell_pre<INV>(inC, v0, ib == cur.i0a, dgC, La, REV ? (dgC ? LEa : 0.0) : eC, REV ? eA : eC, CA, SA, tr, M, m, SC, qC);
+            cell_pre<INV, 16>(inC, v0, ib == cur.i0a, dgC, La, REV ? (dgC ? LEa : 0.0) : eC, REV ? eA : eC, CA, SA, tr, M, m, SC, qC);
             cell_fin(skC && inC && v0, Lb, M, m, tr, CC, kC);
-            cell_pre<INV>(inD, v1, ib == cur.i0b, dgD, CA, REV ? (dgD ? eA : 0.0) : eD, REV ? eB : eD, CB, SB, tr, M, m, SD, qD);
+            cell_pre<INV, 24>(inD, v1, ib == cur.i0b, dgD, CA, REV ? (dgD ? eA : 0.0) : eD, REV ? eB : eD, CB, SB, tr, M, m, SD, qD);
             cell_fin(skD && inD && v1, CC, M, m, tr, CD, kD);
             }
             // the second column of the strip is what the right neighbour reads
@@ -663,8 +666,7 @@ __device__ __forceinline__ void fill_wave(const Batch& b, const EvDesc& ev, cons
             // the reverse stay matrix is never read (main >= stay in every cell: the joins need B's main only)
             if (!REV) { ps[0] = make_double2(SA, SB); ps[1] = make_double2(SC, SD); }
             if (!REV)
-                *reinterpret_cast<unsigned*>(b.Fstep + a) = (unsigned)(kA | (qA << 3)) | ((unsigned)(kB | (qB << 3)) << 8) |
-                                                           ((unsigned)(kC | (qC << 3)) << 16) | ((unsigned)(kD | (qD << 3)) << 24);
+                *reinterpret_cast<unsigned*>(b.Fstep + a) = (unsigned)((kA | qA | kB) | (qB | kC | qC) | (kD | qD));
         }
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(P2P ? bar_mine + slot : bar0);   // this warp's part of step d is in shared memory
@@ -672,7 +674,10 @@ __device__ __forceinline__ void fill_wave(const Batch& b, const EvDesc& ev, cons
         a += ev.rs;
         ph = (ph + 1) & (RD - 1);
         // ---- preparation of step d+1: overlaps the other warps' step d ----
-        if (d + 1 > cur.j + cur.rhi)
+        // Lanes finish their strips on different steps (about one lane every other step in the warp at the lower band
+        // edge); when the event leaves every thread enough idle steps between two strips (ev.lazy, Job::plan_event), the
+        // warp switches all its finished lanes together on every 8th step instead of paying the switch every time.
+        if (d + 1 > cur.j + cur.rhi && (!ev.lazy || (d & 7) == 7 || d == dend))
         {
             // strip finished: publish the best cell of its columns, take the next strip from shared memory
             // and request the one after it
