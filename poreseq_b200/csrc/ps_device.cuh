@@ -42,7 +42,7 @@ struct EvDesc                 // one event of one region in the batch
     long long strip_off;      // first StripRec of this event: forward strips 0..J (J = sentinel), then reverse
     int       ts;             // strips that can be live on one wavefront step (band storage slot count)
     int       rs;             // row stride of the band storage = ts * CW
-    int       lazy;           // every thread idles >= 9 steps between two strips: strips are switched on every 8th step only
+    int       lazy;           // P - 1: every thread idles > P steps between two strips, strips are switched on every P-th step (P = 1, 2, 4, 8)
 };
 
 struct MutDev
@@ -139,6 +139,14 @@ __device__ __forceinline__ void take_gt(double x, int k, double& c, int& code)
         : "+d"(c), "+r"(code) : "d"(x), "r"(k));
 }
 
+// x > c ? x : c  (fmax() without the NaN handling: the same three instructions)
+__device__ __forceinline__ double max_gt(double x, double c)
+{
+    double r;
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, %2;\n\tselp.f64 %0, %1, %2, p;\n\t}" : "=d"(r) : "d"(x), "d"(c));
+    return r;
+}
+
 // emission: lognormpdf + logigpdf + lik_offset   (cpp/AlignUtil.h:34-53, cpp/Alignment.cpp:169-173)
 // x = level mean, y = level stdv (ry its reciprocal), lsd3 = 3*log(stdv) of the level the
 // reference indexes (quirk A.3-1: the forward pass reads log_stdv[n0-i] beside stdv[i-1])
@@ -212,15 +220,15 @@ __device__ __forceinline__ void dp_cell(bool first_row, bool skip_ok, bool diag_
     }
     double s = first_row ? NEG : 0.0;
     int ss = 0;
-    if (stay > s) { s = stay; ss = 1; }
-    if (ext > s) { s = ext; ss = 2; }
+    take_gt(stay, 1, s, ss);
+    take_gt(ext, 2, s, ss);
     double c = 0.0;
     int sc = ST_STOP;
-    if (skip > c) { c = skip; sc = skip_ok ? ST_SKIP : ST_IMPLICIT; }
-    if (match > c) { c = match; sc = diag_ok ? ST_MATCH : ST_IMPLICIT; }
-    if (ins > c) { c = ins; sc = ST_INSERT; }
-    if (ignore > c) { c = ignore; sc = ST_IGNORE; }
-    if (s > c) { c = s; sc = ST_STAY; }
+    take_gt(skip, skip_ok ? ST_SKIP : ST_IMPLICIT, c, sc);
+    take_gt(match, diag_ok ? ST_MATCH : ST_IMPLICIT, c, sc);
+    take_gt(ins, ST_INSERT, c, sc);
+    take_gt(ignore, ST_IGNORE, c, sc);
+    take_gt(s, ST_STAY, c, sc);
     C = c; S = s; step = sc | (ss << 3);
 }
 
@@ -500,8 +508,27 @@ __device__ __forceinline__ void mbar_arrive(unsigned bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
 }
+// A failed try_wait comes back after ~10 cycles on sm_100a (ptxas drops the suspend-time hint), so a waiting warp spins:
+// try_wait, branch and yield were 24 % of the instructions the fill executed.  PS_WAIT_SLEEP_NS > 0 puts a nanosleep
+// into the loop (A/B knob; the warps that wait have 4-5 steps of slack around the ring, see fill_wave).
+#ifndef PS_WAIT_SLEEP_NS
+#define PS_WAIT_SLEEP_NS 0
+#endif
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
 {
+#if PS_WAIT_SLEEP_NS > 0
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "WAIT_LOOP:\n"
+        "nanosleep.u32 %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity), "n"(PS_WAIT_SLEEP_NS) : "memory");
+#else
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -511,6 +538,7 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
         "bra WAIT_LOOP;\n"
         "WAIT_DONE:\n"
         "}\n" ::"r"(bar), "r"(parity) : "memory");
+#endif
 }
 
 template <bool REV, int MAXT, bool INV>
@@ -676,8 +704,8 @@ __device__ __forceinline__ void fill_wave(const Batch& b, const EvDesc& ev, cons
         // ---- preparation of step d+1: overlaps the other warps' step d ----
         // Lanes finish their strips on different steps (about one lane every other step in the warp at the lower band
         // edge); when the event leaves every thread enough idle steps between two strips (ev.lazy, Job::plan_event), the
-        // warp switches all its finished lanes together on every 8th step instead of paying the switch every time.
-        if (d + 1 > cur.j + cur.rhi && (!ev.lazy || (d & 7) == 7 || d == dend))
+        // warp switches all its finished lanes together on every 2nd, 4th or 8th step instead of paying the switch every time.
+        if (d + 1 > cur.j + cur.rhi && ((d & ev.lazy) == ev.lazy || d == dend))
         {
             // strip finished: publish the best cell of its columns, take the next strip from shared memory
             // and request the one after it
@@ -1295,11 +1323,11 @@ __global__ void __launch_bounds__(128) k_mutscore(Batch b)
                             if (skip_ok) Pi = first_col ? sv_c : ring[(long long)slot * rstride];
                             double C, Sv; int step;
                             dp_cell(i == i0, skip_ok, diag_ok, Pi, diag, e_i, e_i, upC, upS, tr, C, Sv, step);
-                            if (C > best) best = C;
+                            best = max_gt(C, best);
                             if (last_col)
                             {
                                 const int jb = n0 - i + 1;
-                                if (jb >= b0 && jb < b0 + blen) joinmax = fmax(joinmax, C + bm_c);
+                                if (jb >= b0 && jb < b0 + blen) joinmax = max_gt(C + bm_c, joinmax);
                             }
                             else ring[(long long)slot * rstride] = C;
                             diag = Pi;
@@ -1487,12 +1515,12 @@ __global__ void __launch_bounds__(128) k_mutscore_warp(Batch b)
                                 const double Pd = diag_ok ? recv_prev : 0.0;
                                 int step;
                                 dp_cell(i_c == i0, skip_ok, diag_ok, Pi, Pd, e_i, e_i, upC, upS, tr, C, Sv, step);
-                                if (C > best) best = C;
+                                best = max_gt(C, best);
                             }
                             if (lastl)
                             {
                                 const int jb = n0 - i_c + 1;
-                                if (jb >= b0 && jb < b0 + blen) joinmax = fmax(joinmax, C + bm_c);
+                                if (jb >= b0 && jb < b0 + blen) joinmax = max_gt(C + bm_c, joinmax);
                             }
                             if (handl) bout[i_c - i0] = C;
                             upC = C; upS = Sv;

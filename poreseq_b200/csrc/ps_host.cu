@@ -33,9 +33,6 @@
 
 using namespace psdev;
 
-#ifndef PS_LAZY_GAP
-#define PS_LAZY_GAP 9             // idle steps between a thread's strips that allow the batched strip switch (8 + 1 spare)
-#endif
 #ifndef PS_FILL_MINB
 #define PS_FILL_MINB 3            // CTAs of the 160-thread fill per SM (128 registers); 4 = 96 registers, measured slower
 #endif
@@ -562,7 +559,7 @@ void Job::plan_event(const HostEvent& he, const EvDesc& d, int rw, int* cen, int
 {
     const int N = d.N, n0 = he.n0;
     for (int c = 0; c <= N + cen_pad; c++) cen[c] = 1;
-    int ok = 1, need = 32, need_lazy = 32;
+    int ok = 1, need = 32, need_lazy[3] = {32, 32, 32};
     double cells = 0;
     if (!he.ri_empty)
     {
@@ -605,21 +602,25 @@ void Job::plan_event(const HostEvent& he, const EvDesc& d, int rw, int* cen, int
                 lo[j] = std::min(lo[j], j + ((i0 - 1) >> 1)); hi[j] = std::max(hi[j], j + ((i1 - 1) >> 1));
                 if (!dir) cells += i1 - i0 + 1;
             }
-            // a thread's next strip (j+T) must start after its current one (j) has ended; with PS_LAZY_GAP idle steps
-            // in between, a warp may take up its finished lanes' next strips together every 8th step (fill_wave)
-            int jj = 1, jl = 1;
+            // a thread's next strip (j+T) must start after its current one (j) has ended; with P + 1 idle steps in
+            // between, a warp may take up its finished lanes' next strips together every P-th step (fill_wave):
+            // need_lazy[q] = threads needed for P = 2, 4, 8
+            int jj = 1, jl[3] = {1, 1, 1};
             for (int j = 0; j < J; j++)
             {
                 if (jj <= j) jj = j + 1;
                 while (jj < J && lo[jj] <= hi[j]) jj++;
                 need = std::max(need, jj - j);
-                if (jl <= j) jl = j + 1;
-                while (jl < J && lo[jl] <= hi[j] + PS_LAZY_GAP) jl++;
-                need_lazy = std::max(need_lazy, jl - j);
+                for (int q = 0; q < 3; q++)
+                {
+                    if (jl[q] <= j) jl[q] = j + 1;
+                    while (jl[q] < J && lo[jl[q]] <= hi[j] + (2 << q) + 1) jl[q]++;
+                    need_lazy[q] = std::max(need_lazy[q], jl[q] - j);
+                }
             }
         }
     }
-    *ok_out = ok; *need_out = need; *need_lazy_out = need_lazy; *cells_out = cells;
+    *ok_out = ok; *need_out = need; for (int q = 0; q < 3; q++) need_lazy_out[q] = need_lazy[q]; *cells_out = cells;
 }
 
 int Job::build()
@@ -786,7 +787,7 @@ int Job::build()
     // pass 2b (parallel over events): level records, alignment arrays, band centres, wavefront plan
     const int ne = (int)ev.size();
     wave_need.assign(ne, 32);
-    wave_need_lazy.assign(ne, 1 << 30);
+    wave_need_lazy.assign((size_t)ne * 3, 1 << 30);
     std::vector<double> ev_cells(ne, 0.0);
     const int rw = P.realign_width;
     ps_parallel_for(ne, [&](int e) {
@@ -815,7 +816,7 @@ int Job::build()
         // event, the band centres of the fill are planned here on the host): nothing to stage or upload
         ri_empty[e] = (he.ri_empty || !d.usable) ? 1 : 0;
         int ok = 1;
-        plan_event(he, d, rw, cen_old.data() + d.cen_off, &ok, &wave_need[e], &wave_need_lazy[e], &ev_cells[e]);
+        plan_event(he, d, rw, cen_old.data() + d.cen_off, &ok, &wave_need[e], &wave_need_lazy[(size_t)e * 3], &ev_cells[e]);
         // the wavefront fill assumes log(prob_skip) <= 0 and log(prob_insert) <= 0 (see fill_wave / cell_pre)
         if (!(model_src[d.model]->trans[0] <= 1.0) || !(model_src[d.model]->trans[3] <= 1.0)) ok = 0;
         mono[e] = ok;
@@ -848,7 +849,10 @@ int Job::build()
         if (!d.usable) { d.ts = 1; d.rs = 4; d.band_off = n_band; continue; }
         const int J = (d.N + CW - 1) / CW;
         d.ts = cls[e] == 3 ? J + 1 : fill_threads[cls[e]];
-        d.lazy = cls[e] != 3 && wave_need_lazy[e] <= fill_threads[cls[e]];
+        d.lazy = 0;                               // strip-switch period - 1: the longest of 8, 4, 2 the event's idle steps allow
+        if (cls[e] != 3)
+            for (int q = 0; q < 3; q++)
+                if (wave_need_lazy[(size_t)e * 3 + q] <= fill_threads[cls[e]]) d.lazy = (2 << q) - 1;
         d.rs = d.ts * 4;                          // one 2x2 tile per slot
         d.band_off = n_band;                      // multiple of 4: keeps the 32-byte tiles aligned
         n_band += (long long)(J + (d.n0 + 1) / 2 + 2) * d.rs;
