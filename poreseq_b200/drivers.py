@@ -102,8 +102,8 @@ def variant(pa, muts=None, var_seqs=None, region_start=0):
 # ---------------------------------------------------------------------------------------------------------
 # `poreseq train` (poreseq/cmdline.py:246-267, poreseq/Params.py:31-60): every iteration tries 16
 # random variations of the transition parameters, runs the consensus loop with each, keeps the most accurate.  The
-# reference gives every variant its own process; here the variants are regions in flight on one GPU (one host thread
-# and one context each), like the consensus throughput mode.
+# reference gives every variant to a pool of worker processes; here the variants of an iteration are regions in flight
+# on one GPU through ps_consensus_batch, like the consensus throughput mode.
 
 def vary_params(params, rng, count=16):
     """VaryParams (Params.py:31-60): `count` copies of params, each with 3 randomly chosen `_t` / `_c` parameters multiplied
@@ -130,49 +130,40 @@ def set_params(events, params):
                 setattr(ev.model, name, v)
 
 
-def train(region, params, iters=1, variants=16, in_flight=8, reps=4, seed=None, device=None, log=None):
-    """The training loop on one loaded region with known truth (`region.truth`): returns (best params, [best accuracy per
-    iteration]).  Every variant starts from the region's draft sequence and seed alignments."""
+def variant_region(region, params):
+    """A copy of `region` with one parameter set applied: the transition probabilities of its events' models
+    (set_params) and the region-level lik_offset -- what Mutate(params=...) loads for one training variant."""
     import copy
-    import queue
+    reg = copy.deepcopy(region)
+    set_params(reg.events, params)
+    reg.params = dict(reg.params, **{q: v for q, v in params.items() if q in ("lik_offset",)})
+    return reg
+
+
+def train(region, params, iters=1, variants=16, in_flight=8, reps=4, seed=None, device=None, log=None, details=None):
+    """The training loop on one loaded region with known truth (`region.truth`): returns (best params, [best accuracy per
+    iteration]).  Every variant starts from the region's draft sequence and seed alignments and runs the whole consensus
+    loop below the C-ABI (ps_consensus_batch: the variants of an iteration are regions in flight on one GPU, each with
+    the rand() stream a freshly started process draws -- what the reference's worker pool gives a variant).
+    `details`: a list that receives (parameter sets, accuracies) of every iteration."""
     import random
-    import threading
     rng = random.Random(seed)
     params = dict(params)
-    ctxs = [poreseqcpp.Context(device if device is not None else poreseqcpp.default_context().device) for _ in range(in_flight)]
+    ctx = poreseqcpp.Context(device if device is not None else poreseqcpp.default_context().device)
     history = []
     try:
         for it in range(iters):
             plist = vary_params(params, rng, variants)
-            accs = [None] * len(plist)
-            todo = queue.Queue()
-            for k in range(len(plist)):
-                todo.put(k)
-
-            def worker(ctx):
-                while True:
-                    try:
-                        k = todo.get_nowait()
-                    except queue.Empty:
-                        return
-                    reg = copy.deepcopy(region)
-                    set_params(reg.events, plist[k])
-                    reg.params = dict(reg.params, **{q: v for q, v in plist[k].items() if q in ("lik_offset",)})
-                    pa = make_psalign(reg)
-                    pa.ctx = ctx
-                    accs[k] = consensus(pa, refseq=region.truth, reps=reps)[1]
-
-            ths = [threading.Thread(target=worker, args=(c,)) for c in ctxs]
-            for t in ths:
-                t.start()
-            for t in ths:
-                t.join()
-            best = int(np.argmax(accs))                    # cmdline.py:261: first maximum
+            regs = [variant_region(region, p) for p in plist]
+            out = consensus_native(regs, ctx=ctx, reps=reps, in_flight=in_flight, refseqs=[region.truth] * len(regs))
+            accs = [o[1] for o in out]
+            best = int(np.argmax(accs))                    # cmdline.py:263: first maximum
             params = plist[best]
             history.append(accs[best])
+            if details is not None:
+                details.append((plist, accs))
             if log is not None:
                 log.write('Best at iter {}: {}\n'.format(it + 1, accs[best]))
     finally:
-        for c in ctxs:
-            c.close()
+        ctx.close()
     return params, history

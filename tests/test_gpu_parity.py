@@ -538,17 +538,37 @@ def test_event_pack_regions_score_like_in_memory_ones(ctx, orc, tmp_path):
     poreseqcpp.close_regions(nrs)
 
 
-def test_train_loop_runs_variants_in_flight():
-    """`poreseq train` restated over a loaded region (drivers.train): every iteration scores the variants with several
-    consensus loops in flight on one GPU and keeps the most accurate parameter set."""
+def test_train_loop_matches_reference_per_variant(drv):
+    """`poreseq train` restated over a loaded region (drivers.train, poreseq/cmdline.py:246-267): the variants of an
+    iteration run as regions in flight through ps_consensus_batch.  Every variant's consensus sequence -- hence its
+    accuracy, the choice of the best variant and the parameters carried into the next iteration -- equals what the same
+    loop gives when the checker (the reference's C++) runs each variant's consensus."""
+    import random
     from poreseq_b200 import drivers
-    reg = synth.make_region(300, 3, seed=21, draft_error=0.08, params=dict(realign_width=60, scoring_width=15, point_width=8))
+    from util import reference_consensus
+    reg = synth.make_region(300, 6, seed=21, draft_error=0.08,
+                            params=dict(realign_width=60, scoring_width=15, point_width=8, end_trim=10))
     base = dict(skip_t=0.141, skip_c=0.088, stay_t=0.043, stay_c=0.057, extend_t=0.072, extend_c=0.046,
                 insert_t=0.020, insert_c=0.025, lik_offset=4.5)
-    best, hist = drivers.train(reg, base, iters=2, variants=4, in_flight=2, reps=2, seed=9, device=0)
-    assert len(hist) == 2 and all(90.0 <= a <= 100.0 for a in hist)
+    details = []
+    best, hist = drivers.train(reg, base, iters=2, variants=4, in_flight=4, reps=2, seed=9, device=0, details=details)
+    assert len(hist) == 2 and len(details) == 2
     assert set(best) == set(base) and best["lik_offset"] == 4.5
-    assert 1 <= sum(best[k] != base[k] for k in base) <= 6
+    # the same loop with the reference scoring every variant
+    rng = random.Random(9)
+    params = dict(base)
+    for it in range(2):
+        plist = drivers.vary_params(params, rng, 4)
+        assert plist == details[it][0]
+        accs = []
+        for p in plist:
+            seq = reference_consensus(drv, drivers.variant_region(reg, p), reps=2)
+            accs.append(poreseqcpp.swalign(seq, reg.truth)[0])
+        assert accs == details[it][1], (it, accs, details[it][1])
+        k = int(np.argmax(accs))
+        params = plist[k]
+        assert hist[it] == accs[k]
+    assert best == params
 
 
 def test_native_pack_regions_score_like_in_memory_ones(ctx, orc, tmp_path):

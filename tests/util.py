@@ -51,3 +51,30 @@ def build_cython_stub(tmp_dir):
     if proc.returncode != 0:
         return None, proc.stdout[-2000:] + proc.stderr[-2000:]
     return dst, ""
+
+
+def reference_consensus(drv, reg, reps=4):
+    """poreseq/Mutate.py:47-99 driven through the checker (`drv`: the reference's own C++ when oracle/_ref is built,
+    else the restatement), from a fresh rand() stream: the end-trimmed consensus sequence."""
+    import copy
+    rr = copy.deepcopy(reg)
+
+    def sync(al):
+        for ev, (ra, rl) in zip(rr.events, al):
+            ev.ref_align, ev.ref_like = ra, rl
+
+    if len(rr.events) < 5:
+        return rr.sequence
+    drv.srand(1)
+    seq, _, al = drv.mutate(rr, [ev.sequence for ev in rr.events[::2]], reps=reps)
+    rr.sequence = seq; sync(al)
+    for _ in range(reps):
+        seeds = drv.viterbi_mutate(rr, nkeep=16, seed=None)
+        seq, _, al = drv.mutate(rr, seeds, reps=reps)
+        rr.sequence = seq; sync(al)
+        seq, nb, al = drv.refine(rr)
+        rr.sequence = seq; sync(al)
+        if nb == 0:
+            break
+    t = int(rr.params.get("end_trim", 0))
+    return rr.sequence[t:-t] if t and len(rr.sequence) > 2 * t else rr.sequence
