@@ -914,14 +914,15 @@ __device__ void dev_updaterefs(const double* ra, double* ri, int n0, int& empty,
 
 // k_backtrace: one WARP per event.  The best path is followed from the best cell through the packed step
 // bytes (cpp/Alignment.cpp:516-605).  A pointer chase through global memory costs one memory round trip
-// per move, so the warp fetches a block of 16 columns x 16 rows below and left of the current cell in one
-// go -- in the wavefront-major layout a 2x2 tile is one 32-bit word of step bytes, lane l takes the tiles of
-// (strips s_hi - (l & 3) and s_hi - 4 - (l & 3), row pair r_hi - (l >> 2)) -- walks inside the block with the words handed around
-// by __shfl_sync (the walk itself is uniform across the warp), and fetches the next block where the walk
-// leaves this one: one round trip per ~16 moves.  Every visited level records its column and matrix; the
+// per move, so the warp fetches a block of 32 columns x 32 rows below and left of the current cell in one
+// go -- in the wavefront-major layout a 2x2 tile is one 32-bit word of step bytes, lane l takes eight tiles of
+// strip s_hi - (l & 15) -- into shared memory, walks inside the block (the walk itself is uniform across the
+// warp; runs of matches are taken by the lanes together), and fetches the next block where the walk
+// leaves this one: one round trip per ~32 moves.  Every visited level records its column and matrix; the
 // warp then gathers ref_like in parallel and lane 0 rebuilds ref_index.  BT_WARPS events per CTA, their
 // per-level scratch in shared memory when the events fit.
 constexpr int BT_WARPS = 4;
+constexpr int BT_BS = 16;           // block side in tiles (strips x row pairs): 32 x 32 cells per fetch
 
 __global__ void __launch_bounds__(32 * BT_WARPS) k_backtrace(Batch b, int smem_levels, int warps_per_cta)
 {
@@ -944,37 +945,79 @@ __global__ void __launch_bounds__(32 * BT_WARPS) k_backtrace(Batch b, int smem_l
     int i = N > 0 ? b.Fbi[ev.col_off + N] : 0, j = N > 0 ? b.Fbj[ev.col_off + N] : 0, arr = 0;
     bool go = i > 0 && j > 0;
     const int ts = ev.ts;
+    // the block of step words around the walk: BT_BS strips x BT_BS row pairs (one 32-bit word per 2x2 tile) and the
+    // bands of its 2 BT_BS columns, staged in shared memory
+    __shared__ unsigned bt_words[BT_WARPS][BT_BS * BT_BS];
+    __shared__ int2 bt_band[BT_WARPS][2 * BT_BS];
+    unsigned* W = bt_words[wrp];
+    int2* BB = bt_band[wrp];
     while (go)
     {
-        // block of strips s_hi-7 .. s_hi and row pairs r_hi-7 .. r_hi around the current cell (its top right corner):
-        // 16 columns x 16 rows, two tile words per lane (strips s and s - 4 of row pair r)
+        // block of strips s_hi-15 .. s_hi and row pairs r_hi-15 .. r_hi, the current cell in its top right tile:
+        // 32 columns x 32 rows.  Lane l fetches the words of strip s_hi - (l & 15), row pairs r_hi - (l >> 4) - 2q.
         const int s_hi = (j - 1) >> 1, r_hi = (i - 1) >> 1;
-        const int s = s_hi - (lane & 3), r = r_hi - (lane >> 2);
-        unsigned word = (unsigned)ST_STOP * 0x01010101u, word2 = word;
-        if (s >= 0 && r >= 0)
-            word = *reinterpret_cast<const unsigned*>(b.Fstep + ev.band_off + ((long long)(s + r) * ts + (s % ts)) * 4);
-        if (s >= 4 && r >= 0)
-            word2 = *reinterpret_cast<const unsigned*>(b.Fstep + ev.band_off + ((long long)(s - 4 + r) * ts + ((s - 4) % ts)) * 4);
-        // bands of the block's 16 columns: lane c holds column 2 (s_hi - 7) + 1 + c
-        const int kcol0 = 2 * (s_hi - 7) + 1;
-        int ci0 = 1, ci1 = 0;
-        if (lane < 16)
+        const int kcol0 = 2 * (s_hi - (BT_BS - 1)) + 1;
+        __syncwarp();                                            // the walk through the previous block is over
         {
-            const int k = kcol0 + lane;
-            if (k >= 1 && k <= N) { const long long g = ev.col_off + k; ci0 = b.Fi0[g]; ci1 = ci0 + b.Flen[g] - 1; }
+            const int ds = lane & (BT_BS - 1), sl = s_hi - ds;
+            int slot = sl >= 0 ? sl % ts : 0;
+            unsigned w[BT_BS / 2];
+#pragma unroll
+            for (int q = 0; q < BT_BS / 2; q++)
+            {
+                const int r = r_hi - (lane >> 4) - 2 * q;
+                w[q] = (unsigned)ST_STOP * 0x01010101u;
+                if (sl >= 0 && r >= 0)
+                    w[q] = *reinterpret_cast<const unsigned*>(b.Fstep + ev.band_off + ((long long)(sl + r) * ts + slot) * 4);
+            }
+            int c0 = 1, c1 = 0;
+            {
+                const int k = kcol0 + lane;
+                if (k >= 1 && k <= N) { const long long g = ev.col_off + k; c0 = b.Fi0[g]; c1 = c0 + b.Flen[g] - 1; }
+            }
+#pragma unroll
+            for (int q = 0; q < BT_BS / 2; q++) W[((lane >> 4) + 2 * q) * BT_BS + ds] = w[q];
+            BB[lane] = make_int2(c0, c1);
         }
-        const int jlo = kcol0, ilo = 2 * (r_hi - 7) + 1;         // the block covers columns >= jlo and rows >= ilo
+        __syncwarp();
+        const int jlo = kcol0, ilo = 2 * (r_hi - (BT_BS - 1)) + 1;   // the block covers columns >= jlo and rows >= ilo
         while (true)
         {
             if (!(i > 0 && j > 0)) { go = false; break; }
             if (j < jlo || i < ilo) break;                       // left the block: fetch the next one
-            const int sj = (j - 1) >> 1, rix = (i - 1) >> 1;
-            const int ds = s_hi - sj, owner = (ds & 3) + 4 * (r_hi - rix);
-            const unsigned wa = __shfl_sync(0xffffffffu, word, owner), wb = __shfl_sync(0xffffffffu, word2, owner);
-            const unsigned w = ds < 4 ? wa : wb;
-            const int b0 = __shfl_sync(0xffffffffu, ci0, j - kcol0), b1 = __shfl_sync(0xffffffffu, ci1, j - kcol0);
+            if (arr == 0)
+            {
+                // Runs of matches (most of a path) in one go: lane l looks at the main-matrix cell l steps down the
+                // diagonal, (i - l, j - l); the lanes before the first one that is not an in-band match inside the
+                // block record their level and the walk jumps over them.  What ends the run is handled by the
+                // one-move code below, exactly as if the moves had been taken one by one.
+                const int il = i - lane, jl = j - lane;
+                bool is_match = false;
+                if (il >= ilo && jl >= jlo && il > 0 && jl > 0)
+                {
+                    const int2 bd = BB[jl - kcol0];
+                    if (il >= bd.x && il <= bd.y)
+                    {
+                        const unsigned wl = W[(r_hi - ((il - 1) >> 1)) * BT_BS + (s_hi - ((jl - 1) >> 1))];
+                        is_match = ((wl >> (8 * ((((il - 1) & 1) << 1) + ((jl - 1) & 1)))) & 7u) == (unsigned)ST_MATCH;
+                    }
+                }
+                const int run = __ffs(~__ballot_sync(0xffffffffu, is_match)) - 1;    // 32 matches: ~0 has no bit, ffs = 0
+                if (run != 0)
+                {
+                    const int n = run < 0 ? 32 : run;
+                    if (lane < n) { val[il - 1] = (double)jl; src[il - 1] = 2 * jl; }
+                    i -= n; j -= n;
+                    continue;
+                }
+            }
+            const int2 bd = BB[j - kcol0];
             int st = ST_STOP;
-            if (i >= b0 && i <= b1) st = (int)((w >> (8 * ((((i - 1) & 1) << 1) + ((j - 1) & 1)))) & 0xffu);
+            if (i >= bd.x && i <= bd.y)
+            {
+                const unsigned w = W[(r_hi - ((i - 1) >> 1)) * BT_BS + (s_hi - ((j - 1) >> 1))];
+                st = (int)((w >> (8 * ((((i - 1) & 1) << 1) + ((j - 1) & 1)))) & 0xffu);
+            }
             const int mv = arr ? ((st >> 3) & 3) : (st & 7);
             if (arr == 0)
             {
