@@ -912,6 +912,76 @@ __device__ void dev_updaterefs(const double* ra, double* ri, int n0, int& empty,
     }
 }
 
+// The same by a whole warp (k_backtrace): every level between the first and the last aligned one that is not aligned
+// itself is interpolated between its nearest aligned neighbours p < i < n with the sequential loop's own expression
+// (m = (ra[n] - ra[p]) / (n - p); ri[i] = m * (i - p) + ra[p]) -- unless p == 0: the loop above tests `last > 0`, so
+// the gap behind an aligned level 0 keeps its raw values; the ends are extrapolated.  p comes from a forward max-scan
+// (kept in `prevpos`, n0 ints of scratch), n from a backward min-scan.  `ri` may alias `ra`: aligned entries are never
+// rewritten and every other entry is read by the lane that rewrites it.
+__device__ void warp_updaterefs(const double* ra, double* ri, int* prevpos, int n0, int lane, int& empty, int& refstart, int& refend)
+{
+    int a = 1 << 30, z = -1;
+    for (int i = lane; i < n0; i += 32)
+        if (ra[i] > 0) { a = min(a, i); z = i; }
+    for (int o = 16; o; o >>= 1)
+    {
+        a = min(a, __shfl_xor_sync(0xffffffffu, a, o));
+        z = max(z, __shfl_xor_sync(0xffffffffu, z, o));
+    }
+    if (z < 0) { empty = 1; refstart = -1; refend = -1; return; }
+    empty = 0;
+    refstart = (int)ra[a];
+    refend = (int)ra[z];
+    const double slope = (ra[z] - ra[a]) / (double)(z - a);
+    const double icpt = ra[a] - slope * a;
+    int carry = -1;
+    for (int c0 = 0; c0 < n0; c0 += 32)
+    {
+        const int i = c0 + lane;
+        int v = (i < n0 && ra[i] > 0) ? i : -1;
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const int u = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v = max(v, u);
+        }
+        v = max(v, carry);
+        if (i < n0) prevpos[i] = v;
+        carry = __shfl_sync(0xffffffffu, v, 31);
+    }
+    __syncwarp();
+    carry = 1 << 30;
+    for (int c0 = ((n0 - 1) >> 5) << 5; c0 >= 0; c0 -= 32)
+    {
+        const int i = c0 + lane;
+        const double x = i < n0 ? ra[i] : 0.0;
+        const bool pos = i < n0 && x > 0;
+        int v = pos ? i : 1 << 30;
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const int u = __shfl_down_sync(0xffffffffu, v, o);
+            if (lane + o < 32) v = min(v, u);
+        }
+        v = min(v, carry);
+        if (i < n0)
+        {
+            double r = x;
+            if (i < a || i > z) r = slope * i + icpt;
+            else if (!pos)
+            {
+                const int p = prevpos[i];
+                if (p > 0)
+                {
+                    const double m = (ra[v] - ra[p]) / (double)(v - p);
+                    r = m * (double)(i - p) + ra[p];
+                }
+            }
+            ri[i] = r;
+        }
+        carry = __shfl_sync(0xffffffffu, v, 0);
+        __syncwarp();
+    }
+}
+
 // k_backtrace: one WARP per event.  The best path is followed from the best cell through the packed step
 // bytes (cpp/Alignment.cpp:516-605).  A pointer chase through global memory costs one memory round trip
 // per move, so the warp fetches a block of 32 columns x 32 rows below and left of the current cell in one
@@ -1053,16 +1123,17 @@ __global__ void __launch_bounds__(32 * BT_WARPS) k_backtrace(Batch b, int smem_l
     }
     __syncwarp();
     int empty = 0;
-    if (lane == 0)
     {
         int rs, re;
-        // in shared memory the interpolation runs in place (every entry is read before it is rewritten)
-        dev_updaterefs(val, in_smem ? val : ri, n0, empty, rs, re);
-        b.ri_empty[e] = empty;
-        b.refstart[e] = rs;
-        b.refend[e] = re;
+        // in shared memory the interpolation runs in place; the walk's `src` is free again and serves as scratch
+        warp_updaterefs(val, in_smem ? val : ri, src, n0, lane, empty, rs, re);
+        if (lane == 0)
+        {
+            b.ri_empty[e] = empty;
+            b.refstart[e] = rs;
+            b.refend[e] = re;
+        }
     }
-    empty = __shfl_sync(0xffffffffu, empty, 0);
     __syncwarp();
     if (in_smem && !empty)
         for (int q = lane; q < n0; q += 32) ri[q] = val[q];
