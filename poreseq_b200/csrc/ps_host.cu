@@ -564,8 +564,11 @@ void Job::plan_event(const HostEvent& he, const EvDesc& d, int rw, int* cen, int
     if (!he.ri_empty)
     {
         const LevelVec& ri = he.ref_index;
+        // (an event with ONE aligned level has a 0/0 slope: every other entry of ref_index is NaN, cpp/EventData.h:143-144;
+        // std::lower_bound's probes then decide, so a NaN anywhere must take the binary search below)
         bool sorted = true;
-        for (int i = 1; i < n0 && sorted; i++) sorted = !(ri[i] < ri[i - 1]);
+        for (int i = 1; i < n0 && sorted; i++) sorted = ri[i] >= ri[i - 1];
+        if (n0 > 0 && ri[0] != ri[0]) sorted = false;
         if (sorted)
         {
             // on sorted data lower_bound is "first element >= c": one linear merge for all columns
@@ -1043,7 +1046,7 @@ int Job::run(bool full)
     {
         int maxn0 = 0;
         for (const EvDesc& d : ev) maxn0 = std::max(maxn0, d.n0);
-        k_rows<<<dim3((maxn0 + 127) / 128, nev), 128, 0, ctx->stream>>>(b);
+        k_rows<<<dim3(std::max(1, (maxn0 + 127) / 128), nev), 128, 0, ctx->stream>>>(b);      // (a batch of events without levels)
         LAUNCHED();
         Score32Args a;
         float* d_out32;
@@ -1117,7 +1120,7 @@ int Job::run(bool full)
             for (const EvDesc& d : ev) maxn0 = std::max(maxn0, d.n0);
             k_strips<<<dim3(((maxN + CW - 1) / CW + 1 + 127) / 128, nev, dirs), 128, 0, ctx->stream>>>(b);
             LAUNCHED();
-            k_rows<<<dim3((maxn0 + 127) / 128, nev), 128, 0, ctx->stream>>>(b);
+            k_rows<<<dim3(std::max(1, (maxn0 + 127) / 128), nev), 128, 0, ctx->stream>>>(b);      // (a batch of events without levels)
             LAUNCHED();
         }
         // the majority class on the main stream, the others beside it on the side stream

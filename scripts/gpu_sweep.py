@@ -1,9 +1,12 @@
 """GPU: the randomised degenerate-region sweep of tests/test_oracle_random_sweep.py run through the CUDA path
-(C-ABI) against the CPU checker.  Not part of the test suite: it was written after the round's GPU budget was
-spent and has not run on a B200 yet -- run it first thing next round:
+(C-ABI) against the CPU checker: tiny regions (6-60 bases, 1-3 reads), narrow bands, events without alignment, with one
+level, with non-ACGT bases; ScoreAlignments, ScorePoints, ScoreMutations and Refine in both precisions.
 
-    gpurun --timeout 600 -- 'timeout 500 python scripts/gpu_sweep.py 240 > gpurun_out/gpu_sweep.log 2>&1'
+    gpurun --timeout 600 -- 'timeout 500 python scripts/gpu_sweep.py 600 > gpurun_out/gpu_sweep.log 2>&1'
 
+Its first run on a B200 found two bugs the fixed cases had not (a zero-sized grid for a batch of events without levels;
+the band planner taking the NaN ref_index of an event with ONE aligned level for a sorted array); 600 seeds x 2
+precisions are clean since.  tests/test_gpu_random_sweep.py runs a part of it with the GPU suite.
 Prints every mismatching seed with the entry point that differed; exit code 1 if there was one."""
 import os
 import sys
@@ -34,15 +37,16 @@ def tiny_region(seed, lo, hi, rng):
                              p_unaligned=float(rng.choice([0, 0.3, 0.9])), jitter=int(rng.choice([0, 2, 6])), params=params)
 
 
-def main():
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 240
+def main(n=None, first=0):
+    if n is None:
+        n = int(sys.argv[1]) if len(sys.argv) > 1 else 240
     binding.build("oracle")
     orc = binding.load("oracle")
     ctx = poreseqcpp.Context(0)
     bad = 0
     for precision in ("exact", "fast"):
         ctx.set_precision(precision)
-        for seed in range(n):
+        for seed in range(first, first + n):
             rng = np.random.default_rng(1000 + seed)
             reg = tiny_region(seed, 6, 60, rng)
             kind = seed % 5

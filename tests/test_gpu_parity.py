@@ -538,6 +538,40 @@ def test_event_pack_regions_score_like_in_memory_ones(ctx, orc, tmp_path):
     poreseqcpp.close_regions(nrs)
 
 
+@pytest.mark.parametrize("precision", ["exact", "fast"])
+def test_event_with_one_aligned_level(ctx, orc, precision):
+    """An event whose ref_align holds ONE aligned level has a 0/0 slope in updaterefs (cpp/EventData.h:143-144): every other
+    entry of its ref_index is NaN and the band centres are whatever std::lower_bound's probes make of that
+    (cpp/EventData.h:172-183).  Found by scripts/gpu_sweep.py in the re-scoring round of Refine; the band planner's
+    linear merge took a NaN array for a sorted one."""
+    import copy
+    reg = copy.deepcopy(region("draft_partial"))
+    for e, lvl in ((1, 22), (2, 0), (3, len(reg.events[3].mean) - 1)):
+        ra = np.zeros_like(reg.events[e].ref_align)
+        ra[lvl] = float(min(lvl + 1, len(reg.sequence) - 4))
+        reg.events[e].ref_align = ra
+    c = poreseqcpp.Context(0)
+    try:
+        c.set_precision(precision)
+        st, og, mu = edge_mutations(reg.sequence, 5, count=60)
+        want, a = orc.score_mutations(reg, st, og, mu)
+        nr = poreseqcpp.NativeRegion(c, reg.sequence, reg.events, reg.params)
+        got = nr.score_mutations(st, og, mu)
+        if precision == "exact":
+            assert np.array_equal(got, want)
+        else:
+            assert np.array_equal(got[want >= 0], want[want >= 0]) and np.all(np.abs(got - want) <= 1e-4 * np.abs(want))
+        assert same_aligns([nr.event_align(e) for e in range(len(reg.events))], a)
+        nr.close()
+        seq, nb, a = orc.refine(reg)
+        nr = poreseqcpp.NativeRegion(c, reg.sequence, reg.events, reg.params, "point_width")
+        assert nr.refine() == nb and nr.sequence() == seq
+        assert same_aligns([nr.event_align(e) for e in range(len(reg.events))], a)
+        nr.close()
+    finally:
+        c.close()
+
+
 def test_train_loop_matches_reference_per_variant(drv):
     """`poreseq train` restated over a loaded region (drivers.train, poreseq/cmdline.py:246-267): the variants of an
     iteration run as regions in flight through ps_consensus_batch.  Every variant's consensus sequence -- hence its

@@ -1,0 +1,17 @@
+"""The randomised degenerate-region sweep (scripts/gpu_sweep.py) as part of the GPU suite: 300 seeded tiny regions
+(events without alignment, with a single level or a single aligned level, non-ACGT bases, bands of a few rows) through
+ScoreAlignments, ScorePoints, ScoreMutations and Refine in both precisions against the CPU checker."""
+import os
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "scripts"))
+
+
+def test_random_degenerate_regions_match_the_checker(capsys):
+    import gpu_sweep
+    rc = gpu_sweep.main(n=300, first=0)
+    out = capsys.readouterr().out
+    assert rc == 0, out[-4000:]
