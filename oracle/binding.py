@@ -149,7 +149,7 @@ class Checker(object):
 
     def refine(self, region):
         pk = Packed(region, "point_width")
-        cap = 2 * len(region.sequence) + 64
+        cap = 16 * len(region.sequence) + 1024           # (insertion probabilities above 1 make every insertion a gain)
         buf = C.create_string_buffer(cap)
         nb = C.c_int(0)
         rc = self.lib.orc_refine(C.byref(pk.c), buf, cap, C.byref(nb))

@@ -341,14 +341,21 @@ __global__ void __launch_bounds__(128) k_mutscore_rows_f32(Batch b)
                 if (flo > fhi) { flo = rhi + 1; fhi = rhi; }
 #pragma unroll
                 for (int c = 0; c < NC; c++) { q.C[c] = q.fl; q.S[c] = q.fl; }
-                q.sd_prev = (float)(seed_raw(q, rlo - 1) - q.a);
+                // (rlo - 1, seed) is the first row's diagonal source; the move exists only while rlo itself is inside the
+                // seed column's band (cpp/Alignment.cpp:213: i <= p1) -- a seed band that ends right above the first
+                // narrow row leaves the floor (found by scripts/gpu_sweep.py; the general rows test the predicate)
+                q.sd_prev = rlo <= q.p1 ? (float)(seed_raw(q, rlo - 1) - q.a) : q.fl;
                 q.sd = (float)(seed_raw(q, rlo) - q.a);
                 {
                     const LevelRecF lr = q.lev[rlo - 1];
 #pragma unroll
                     for (int c = 0; c < NC; c++) q.em[c] = emission_f(lr, q.col[c].sp);
                 }
+#ifdef PS_SCAN_GENERAL_ONLY
+                if (false)
+#else
                 if (all_valid && q.ncol >= 5)
+#endif
                 {
                     // edge rows with sentinels, interior rows with nothing: the column registers start as "outside"
 #pragma unroll

@@ -26,6 +26,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <map>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -392,8 +393,11 @@ int ps_viterbi_list(ps_region* R, int nkeep, double skip_prob, double stay_prob,
     int refind = R->events[0].refstart;
     int maxref = 0;
     for (const HostEvent& ev : R->events) { refind = std::min(refind, ev.refstart); maxref = std::max(maxref, ev.refend); }
-    // first level whose ref_index equals a given integer exactly (std::find in getrefstates)
+    // first level whose ref_index equals a given integer exactly (std::find in getrefstates).  ref_index is extrapolated
+    // past the last aligned level (cpp/EventData.h:148-152), so a read can still "sit" on positions beyond every read's
+    // refend when its tail slope makes the extrapolated values integers: those (rare) positions are kept in `beyond`.
     std::vector<std::vector<int>> first(E);
+    std::vector<std::map<int, int>> beyond(E);
     for (int k = 0; k < E; k++)
     {
         const HostEvent& ev = R->events[k];
@@ -401,11 +405,14 @@ int ps_viterbi_list(ps_region* R, int nkeep, double skip_prob, double stay_prob,
         for (int i = 0; i < ev.n0; i++)
         {
             const double v = ev.ref_index[i];
-            if (v >= 0 && v <= maxref + 1 && v == std::floor(v))
+            if (!(v >= 0) || v != std::floor(v)) continue;
+            if (v <= maxref + 1)
             {
                 int& slot = first[k][(int)v];
                 if (slot < 0) slot = i;
             }
+            else if (v < 2147483647.0)
+                beyond[k].emplace((int)v, i);                 // emplace keeps the first level of a value
         }
     }
     std::vector<VitSlot> slots;
@@ -418,15 +425,15 @@ int ps_viterbi_list(ps_region* R, int nkeep, double skip_prob, double stay_prob,
     const int n_cand = (ref0 >= 0 && ref0 <= maxref + 1) ? maxref + 2 - ref0 : 0;
     std::vector<std::vector<VitSlot>> cand(n_cand);
     std::vector<int> cand_nal(n_cand, 0);
-    ps_parallel_for(n_cand, [&](int q) {
-        const int ri = ref0 + q;
-        std::vector<VitSlot>& out = cand[q];
+    auto position = [&](int ri, std::vector<VitSlot>& out, int& nal_out) {
         int nal = 0;
         for (int k = 0; k < E; k++)
         {
             const HostEvent& ev = R->events[k];
             if (ri >= ev.refstart && ri <= ev.refend) nal++;
-            const int f = first[k][ri];
+            int f = -1;
+            if (ri >= 0 && ri <= maxref + 1) f = first[k][ri];
+            else { auto it = beyond[k].find(ri); if (it != beyond[k].end()) f = it->second; }
             if (f < 0) continue;
             double lvl = ev.mean[f], sd = ev.stdv[f];
             int cnt = 1;
@@ -438,16 +445,17 @@ int ps_viterbi_list(ps_region* R, int nkeep, double skip_prob, double stay_prob,
             s.model = ev.model; s.pad = 0; s.lvl = lvl; s.sd = sd; s.logsd = std::log(sd);
             out.push_back(s);
         }
-        cand_nal[q] = nal;
-    });
+        nal_out = nal;
+    };
+    ps_parallel_for(n_cand, [&](int q) { position(ref0 + q, cand[q], cand_nal[q]); });
+    std::vector<VitSlot> tail;
     while (true)
     {
         int nlik = 0, nal = 0;
         const std::vector<VitSlot>* here = nullptr;
-        if (refind >= ref0 && refind - ref0 < n_cand) { here = &cand[refind - ref0]; nlik = (int)here->size(); nal = cand_nal[refind - ref0]; }
-        else
-            for (const HostEvent& ev : R->events)
-                if (refind >= ev.refstart && refind <= ev.refend) nal++;
+        if (refind >= ref0 && refind - ref0 < n_cand) { here = &cand[refind - ref0]; nal = cand_nal[refind - ref0]; }
+        else { tail.clear(); position(refind, tail, nal); here = &tail; }
+        nlik = (int)here->size();
         if (nlik <= nal * 0.2)
         {
             if (nal == 0) break;

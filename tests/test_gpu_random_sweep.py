@@ -15,3 +15,12 @@ def test_random_degenerate_regions_match_the_checker(capsys):
     rc = gpu_sweep.main(n=300, first=0)
     out = capsys.readouterr().out
     assert rc == 0, out[-4000:]
+
+
+def test_random_degenerate_regions_driver_entry_points(capsys):
+    """swfull on the device, MapAlignments, FindMutations (repeated seed), the Mutate loop and ViterbiMutate (best path and
+    8 sampled walks on one rand() stream) on 120 seeded degenerate regions, incl. transition probabilities above 1."""
+    import gpu_sweep
+    rc = gpu_sweep.main_drivers(n=120, first=0)
+    out = capsys.readouterr().out
+    assert rc == 0, out[-4000:]
