@@ -173,6 +173,106 @@ def main_drivers(n=None, first=0):
     return 1 if bad else 0
 
 
+def main_mid(n=None, first=0):
+    """Mid-sized regions (150-500 bases, 1-4 reads, realign_width 20-300): the wavefront classes of the wide fill, the
+    batched strip switches, interior and masked tiles, the batched and the handle-less entry points and the FP32
+    score-only fill, with jittered / partial / missing alignments."""
+    if n is None:
+        n = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+    binding.build("oracle")
+    orc = binding.load("oracle")
+    ctx = poreseqcpp.Context(0)
+    bad = 0
+    for precision in ("exact", "fast"):
+        ctx.set_precision(precision)
+        for seed in range(first, first + n):
+            rng = np.random.default_rng(7000 + seed)
+            params = dict(realign_width=int(rng.choice([20, 60, 150, 300])), scoring_width=int(rng.integers(5, 40)),
+                          point_width=int(rng.integers(3, 21)), lik_offset=float(rng.choice([2.0, 4.5])))
+            regs = [synth.make_region(int(rng.integers(150, 500)), int(rng.integers(1, 5)), seed=10 * seed + k + 1,
+                                      draft_error=float(rng.choice([0, 0.05, 0.15])), partial=float(rng.choice([0, 0.3, 1.0])),
+                                      p_unaligned=float(rng.choice([0, 0.2])), jitter=int(rng.choice([0, 3, 10])), params=params)
+                    for k in range(2)]
+            if seed % 3 == 1:
+                s = list(regs[0].sequence)
+                s[int(rng.integers(0, len(s)))] = "N"
+                regs[0].sequence = "".join(s)
+            what = []
+            try:
+                wants = [orc.score_points(r) for r in regs]
+                nrs = [native(ctx, r, "point_width") for r in regs]
+                outs = poreseqcpp.score_points_batch(ctx, nrs)
+                packs = [poreseqcpp.PackedRegion(r.sequence, r.events, r.params) for r in regs]
+                direct = poreseqcpp.score_points_direct(ctx, packs)
+                for k, r in enumerate(regs):
+                    w = np.array([x[3] for x in wants[k][0]])
+                    for name, sc in (("batch", outs[k][3]), ("direct", direct[k][3])):
+                        same = np.array_equal(sc, w) if precision == "exact" else (
+                            len(sc) == len(w) and np.array_equal(sc[w >= 0], w[w >= 0]) and bool(np.all(np.abs(sc - w) <= 1e-4 * np.abs(w))))
+                        if not same:
+                            what.append("score_points(%s)[%d]" % (name, k))
+                    if not same_aligns(aligns(nrs[k], r), wants[k][1]):
+                        what.append("score_points aligns[%d]" % k)
+                poreseqcpp.close_regions(nrs)
+                for k, r in enumerate(regs):
+                    sa, _, _ = orc.score_alignments(r, True)
+                    nr = native(ctx, r)
+                    se = nr.score_events()
+                    ok = np.array_equal(se, sa) if precision == "exact" else bool(np.all(np.abs(se - sa) <= 1e-4 * np.abs(sa)))
+                    if not ok:
+                        what.append("score_events[%d]" % k)
+                    seq, nb, a = orc.refine(r)
+                    nr = native(ctx, r, "point_width")
+                    if not (nr.refine() == nb and nr.sequence() == seq and same_aligns(aligns(nr, r), a)):
+                        what.append("refine[%d]" % k)
+            except Exception as e:                                  # noqa: BLE001
+                what.append("exception %r" % (e,))
+            if what:
+                bad += 1
+                print("MISMATCH(mid) precision=%s seed=%d lens=%s events=%s params=%s: %s"
+                      % (precision, seed, [len(r.sequence) for r in regs], [len(r.events) for r in regs], params, ", ".join(what)), flush=True)
+    print("gpu_sweep mid: %d x 2 regions x 2 precisions, %d mismatching" % (n, bad))
+    return 1 if bad else 0
+
+
+def main_consensus(n=None, first=0):
+    """The whole Mutate.py loop below the C-ABI (ps_consensus_batch, regions in lockstep, region-private rand() streams)
+    against the same loop driven through the checker from a fresh rand() stream, on small regions of 3-6 reads."""
+    from poreseq_b200 import drivers
+    from util import reference_consensus
+    if n is None:
+        n = int(sys.argv[4]) if len(sys.argv) > 4 else 12
+    binding.build("oracle")
+    chk = binding.load("ref") if binding.available("ref") else binding.load("oracle")
+    ctx = poreseqcpp.Context(0)
+    bad = 0
+    for precision in ("exact", "fast"):
+        ctx.set_precision(precision)
+        for base in range(first, first + n, 4):
+            regs = []
+            for seed in range(base, min(base + 4, first + n)):
+                rng = np.random.default_rng(11000 + seed)
+                regs.append(synth.make_region(int(rng.integers(80, 260)), int(rng.integers(3, 7)), seed=seed + 1,
+                                              draft_error=float(rng.choice([0.03, 0.08, 0.15])), partial=float(rng.choice([0, 0.3])),
+                                              params=dict(realign_width=60, scoring_width=int(rng.integers(8, 25)),
+                                                          point_width=int(rng.integers(4, 12)), end_trim=int(rng.choice([0, 10])))))
+            what = []
+            try:
+                got = drivers.consensus_native(regs, ctx=ctx, reps=3, in_flight=4)
+                for k, r in enumerate(regs):
+                    if got[k][0] != reference_consensus(chk, r, reps=3):
+                        what.append("consensus[%d]" % (base + k))
+            except Exception as e:                                  # noqa: BLE001
+                what.append("exception %r" % (e,))
+            if what:
+                bad += 1
+                print("MISMATCH(consensus) precision=%s seeds %d..: %s" % (precision, base, ", ".join(what)), flush=True)
+    print("gpu_sweep consensus: %d regions x 2 precisions, %d mismatching batches" % (n, bad))
+    return 1 if bad else 0
+
+
 if __name__ == "__main__":
     rc = main()
-    sys.exit(main_drivers() or rc)
+    rc = main_drivers() or rc
+    rc = main_mid() or rc
+    sys.exit(main_consensus() or rc)

@@ -24,3 +24,21 @@ def test_random_degenerate_regions_driver_entry_points(capsys):
     rc = gpu_sweep.main_drivers(n=120, first=0)
     out = capsys.readouterr().out
     assert rc == 0, out[-4000:]
+
+
+def test_random_mid_sized_regions_batched_entry_points(capsys):
+    """150-500 bases, realign_width 20-300, jittered / partial / missing alignments: ScorePoints through the batched and
+    the handle-less entry points, ScoreEvents (FP32 score-only fill in fast mode), Refine."""
+    import gpu_sweep
+    rc = gpu_sweep.main_mid(n=12, first=0)
+    out = capsys.readouterr().out
+    assert rc == 0, out[-4000:]
+
+
+def test_random_small_regions_whole_consensus_loop(capsys):
+    """ps_consensus_batch (lockstep over regions, region-private rand() streams) against the Mutate.py policy driven
+    through the checker, 8 small regions in both precisions."""
+    import gpu_sweep
+    rc = gpu_sweep.main_consensus(n=8, first=0)
+    out = capsys.readouterr().out
+    assert rc == 0, out[-4000:]

@@ -70,11 +70,14 @@ def reference_consensus(drv, reg, reps=4):
     rr.sequence = seq; sync(al)
     for _ in range(reps):
         seeds = drv.viterbi_mutate(rr, nkeep=16, seed=None)
-        seq, _, al = drv.mutate(rr, seeds, reps=reps)
+        seq, _, al = drv.mutate(rr, seeds, reps=4)          # Mutate.py:76: pa.Mutate(seqs='viterbi'), reps defaults to 4
         rr.sequence = seq; sync(al)
         seq, nb, al = drv.refine(rr)
         rr.sequence = seq; sync(al)
         if nb == 0:
             break
-    t = int(rr.params.get("end_trim", 0))
-    return rr.sequence[t:-t] if t and len(rr.sequence) > 2 * t else rr.sequence
+    seq = rr.sequence
+    if "end_trim" in rr.params and len(seq) > 2 * rr.params["end_trim"]:      # Mutate.py:85-86 as written: an end_trim of 0
+        t = int(rr.params["end_trim"])                                        # slices [0:-0] = the empty string
+        seq = seq[t:-t]
+    return seq
