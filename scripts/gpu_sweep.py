@@ -225,6 +225,26 @@ def main_mid(n=None, first=0):
                     nr = native(ctx, r, "point_width")
                     if not (nr.refine() == nb and nr.sequence() == seq and same_aligns(aligns(nr, r), a)):
                         what.append("refine[%d]" % k)
+                    # multi-base edits at scoring_width (poreseq variant), seed-driven candidate search, the Mutate loop
+                    st, og, mu = edge_mutations(r.sequence, seed, count=80, max_len=6)
+                    want, a = orc.score_mutations(r, st, og, mu)
+                    nr = native(ctx, r)
+                    got = nr.score_mutations(st, og, mu)
+                    same = np.array_equal(got, want) if precision == "exact" else (
+                        np.array_equal(got[want >= 0], want[want >= 0]) and bool(np.all(np.abs(got - want) <= 1e-4 * np.abs(want))))
+                    if not (same and same_aligns(aligns(nr, r), a)):
+                        what.append("score_mutations[%d]" % k)
+                    if k == 0 and len(r.events) >= 2:
+                        seeds = [ev.sequence for ev in r.events[::2]][:3] + [synth.corrupt_sequence(r.sequence, 0.08, rng)[0]]
+                        f, a = orc.find_mutations(r, seeds)
+                        nr = native(ctx, r)
+                        if not (nr.find_mutations(seeds) == f and same_aligns(aligns(nr, r), a)):
+                            what.append("find_mutations")
+                        m = orc.mutate(r, seeds, reps=2)
+                        nr = native(ctx, r)
+                        nb = nr.mutate(seeds, reps=2)
+                        if not (nr.sequence() == m[0] and nb == m[1] and same_aligns(aligns(nr, r), m[2])):
+                            what.append("mutate")
             except Exception as e:                                  # noqa: BLE001
                 what.append("exception %r" % (e,))
             if what:
