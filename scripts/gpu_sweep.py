@@ -255,6 +255,54 @@ def main_mid(n=None, first=0):
     return 1 if bad else 0
 
 
+def main_large(n=None, first=0):
+    """Long events (2-5 kb, 1-2 reads, realign_width 100 / 300): many strips per thread in the wide fill, every wavefront
+    class, backtrace walks over thousands of levels, long updaterefs scans -- ScoreAlignments (+ profile), ScorePoints
+    and Refine against the checker in both precisions (the checker runs once per region: ~20 s of CPU each)."""
+    if n is None:
+        n = int(sys.argv[5]) if len(sys.argv) > 5 else 3
+    binding.build("oracle")
+    orc = binding.load("oracle")
+    ctx = poreseqcpp.Context(0)
+    bad = 0
+    for seed in range(first, first + n):
+        rng = np.random.default_rng(13000 + seed)
+        reg = synth.make_region(int(rng.integers(2000, 5000)), int(rng.integers(1, 3)), seed=seed + 1,
+                                draft_error=float(rng.choice([0.02, 0.1])), partial=float(rng.choice([0, 0.3])),
+                                p_unaligned=float(rng.choice([0, 0.1])), jitter=int(rng.choice([0, 5, 40])),
+                                params=dict(realign_width=int(rng.choice([100, 300])), scoring_width=30,
+                                            point_width=int(rng.integers(5, 21))))
+        s, l, a_sa = orc.score_alignments(reg, True)
+        want, a_sp = orc.score_points(reg)
+        w = np.array([x[3] for x in want])
+        seq, nb, a_rf = orc.refine(reg)
+        for precision in ("exact", "fast"):
+            ctx.set_precision(precision)
+            what = []
+            try:
+                nr = native(ctx, reg)
+                gs, gl = nr.score_alignments(True)
+                if not (np.array_equal(gs, s) and np.array_equal(gl, l) and same_aligns(aligns(nr, reg), a_sa)):
+                    what.append("score_alignments")
+                nr = native(ctx, reg, "point_width")
+                sc = nr.score_points()[3]
+                same = np.array_equal(sc, w) if precision == "exact" else (
+                    len(sc) == len(w) and np.array_equal(sc[w >= 0], w[w >= 0]) and bool(np.all(np.abs(sc - w) <= 1e-4 * np.abs(w))))
+                if not (same and same_aligns(aligns(nr, reg), a_sp)):
+                    what.append("score_points")
+                nr = native(ctx, reg, "point_width")
+                if not (nr.refine() == nb and nr.sequence() == seq and same_aligns(aligns(nr, reg), a_rf)):
+                    what.append("refine")
+            except Exception as e:                                  # noqa: BLE001
+                what.append("exception %r" % (e,))
+            if what:
+                bad += 1
+                print("MISMATCH(large) precision=%s seed=%d len=%d events=%d params=%s: %s"
+                      % (precision, seed, len(reg.sequence), len(reg.events), reg.params, ", ".join(what)), flush=True)
+    print("gpu_sweep large: %d regions x 2 precisions, %d mismatching" % (n, bad))
+    return 1 if bad else 0
+
+
 def main_consensus(n=None, first=0):
     """The whole Mutate.py loop below the C-ABI (ps_consensus_batch, regions in lockstep, region-private rand() streams)
     against the same loop driven through the checker from a fresh rand() stream, on small regions of 3-6 reads."""
