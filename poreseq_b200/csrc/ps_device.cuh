@@ -975,7 +975,7 @@ __device__ void warp_updaterefs(const double* ra, double* ri, int* prevpos, int 
                     r = m * (double)(i - p) + ra[p];
                 }
             }
-            ri[i] = r;
+            if (!(pos && ri == ra)) ri[i] = r;            // in place, an aligned entry stays as it is: other lanes read it
         }
         carry = __shfl_sync(0xffffffffu, v, 0);
         __syncwarp();
