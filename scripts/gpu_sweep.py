@@ -8,7 +8,7 @@ Its first run on a B200 found two bugs the fixed cases had not (a zero-sized gri
 the band planner taking the NaN ref_index of an event with ONE aligned level for a sorted array), then a third and a
 fourth (ViterbiMutate stopped at the last refend although extrapolated ref_index values still matched positions beyond
 it; the FP32 scan took a real diagonal out of a seed column whose band ends right above the first narrow row);
-2400 + 500 seeds x 2 precisions are clean since.  tests/test_gpu_random_sweep.py runs a part of it with the GPU suite.
+5400 + 1100 seeds x 2 precisions are clean since.  tests/test_gpu_random_sweep.py runs a part of it with the GPU suite.
 Prints every mismatching seed with the entry point that differed; exit code 1 if there was one."""
 import os
 import sys
@@ -235,7 +235,7 @@ def main_mid(n=None, first=0):
                     if not (same and same_aligns(aligns(nr, r), a)):
                         what.append("score_mutations[%d]" % k)
                     if k == 0 and len(r.events) >= 2:
-                        seeds = [ev.sequence for ev in r.events[::2]][:3] + [synth.corrupt_sequence(r.sequence, 0.08, rng)[0]]
+                        seeds = [ev.sequence for ev in r.events[::2]][:3] + [synth.corrupt_sequence(r.sequence.replace("N", "A"), 0.08, rng)[0]]
                         f, a = orc.find_mutations(r, seeds)
                         nr = native(ctx, r)
                         if not (nr.find_mutations(seeds) == f and same_aligns(aligns(nr, r), a)):
