@@ -238,6 +238,12 @@ int         ps_find_mutations(ps_region* r, int n_seeds, const char* const* seed
  * several GPUs: swfull of the region's sequence against every seed, CUSUM of the profile differences along the alignments,
  * greedy peak picking.  base_profile has len(sequence) entries, seed_profiles[s] strlen(seeds[s]).  The result is read
  * like that of ps_find_mutations. */
+/* What the band planner sees of one event (host only, no device work): ref_index as updaterefs leaves it
+ * (cpp/EventData.h:110-169; n0 doubles, may be null) and getrefstate(c) = std::lower_bound(ref_index, c) for the columns
+ * c = 0 .. n_cols-1 (cpp/EventData.h:172-183; 1 everywhere when the event carries no alignment, cpp/Alignment.cpp:129-132).
+ * *monotone: the centres never go backwards (the wavefront schedule applies).  An event with a single aligned level has
+ * a 0/0 slope there and a ref_index of NaNs around that level: the centres are whatever the binary search's probes give. */
+int         ps_band_centres(ps_region* r, int event, int n_cols, int* centres, double* ref_index_out, int* ri_empty, int* monotone);
 int         ps_pick_candidates(ps_region* r, int n_seeds, const char* const* seeds, const double* base_profile,
                                const double* const* seed_profiles, int* n_found);
 int         ps_found_mutation_sizes(ps_region* r, int i, int* n_orig, int* n_mut);
@@ -245,6 +251,13 @@ int         ps_get_found_mutation(ps_region* r, int i, int* start, char* orig, i
 /* Loop body of PSAlign.Mutate (poreseq/_poreseqcpp.pyx:424-431): reps x (FindMutations,
  * ScoreMutations, MakeMutations), stopping when a round changes nothing. */
 int         ps_mutate(ps_region* r, int n_seeds, const char* const* seeds, int reps, int* totbases);
+/* The host half of ViterbiMutate alone (no device work; cpp/Viterbi.cpp:262-325): the positions the loop keeps and how
+ * many reads sit on each (getrefstates, cpp/EventData.h:187-204: std::find over ref_index, whose extrapolated ends can
+ * match positions beyond every read's refend), after the reference's skip / stop rule (nlik <= 0.2 * reads spanning the
+ * position: skip, or stop when no read spans it).  PS_E_ARG when an event carries no alignment, like ps_viterbi_mutate;
+ * PS_E_CAPACITY (with *n_positions set) when cap is too small. */
+int         ps_viterbi_positions(ps_region* r, int cap, int* positions, int* reads_here, int* n_positions);
+
 /* vector<Sequence> ViterbiMutate(vector<EventData>&, int nkeep, double skip, double stay,
  * double mut_min, double mut_max, bool verbose)   cpp/Viterbi.h:67-68, cpp/Viterbi.cpp:239-426.
  * nkeep == 0: the best path; otherwise nkeep forward-weighted samples drawn with libc rand()

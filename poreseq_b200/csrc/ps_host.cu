@@ -551,6 +551,56 @@ struct Job
     double* raw_scores = nullptr;
 };
 
+// getrefstate(c) for c = 0 .. n_cols-1 (cpp/EventData.h:172-183: std::lower_bound over ref_index); returns whether
+// the centres are nondecreasing.
+int ps_host_centres(const double* ri, int n0, int n_cols, int* cen)
+{
+    // (an event with ONE aligned level has a 0/0 slope: every other entry of ref_index is NaN, cpp/EventData.h:143-144;
+    // std::lower_bound's probes then decide, so a NaN anywhere must take the binary search below)
+    int ok = 1;
+    bool sorted = true;
+    for (int i = 1; i < n0 && sorted; i++) sorted = ri[i] >= ri[i - 1];
+    if (n0 > 0 && ri[0] != ri[0]) sorted = false;
+    if (sorted)
+    {
+        // on sorted data lower_bound is "first element >= c": one linear merge for all columns
+        int idx = 0;
+        for (int c = 0; c < n_cols; c++)
+        {
+            while (idx < n0 && ri[idx] < (double)c) idx++;
+            cen[c] = idx;
+        }
+    }
+    else
+        for (int c = 0; c < n_cols; c++)
+        {
+            const int v = (int)(std::lower_bound(ri, ri + n0, (double)c) - ri);
+            cen[c] = v;
+            if (c > 0 && v < cen[c - 1]) ok = 0;
+        }
+    return ok;
+}
+
+// What the planner sees of one event (host only): ref_index as updaterefs leaves it and the band centres of the first
+// n_cols columns.  For the CPU tests of the band planning; ref_index_out may be null.
+extern "C" int ps_band_centres(ps_region* R, int event, int n_cols, int* centres, double* ref_index_out, int* ri_empty, int* monotone)
+{
+    if (!R || event < 0 || event >= (int)R->events.size() || n_cols < 0 || (n_cols > 0 && !centres))
+        return PS_BAD_ARGS(R ? R->ctx : nullptr, "ps_band_centres");
+    HostEvent& he = R->events[event];
+    he.ensure_refs();
+    int ok = 1;
+    if (he.ri_empty) for (int c = 0; c < n_cols; c++) centres[c] = 1;            // cpp/Alignment.cpp:129-132
+    else
+    {
+        ok = ps_host_centres(he.ref_index.data(), he.n0, n_cols, centres);
+        if (ref_index_out) memcpy(ref_index_out, he.ref_index.data(), sizeof(double) * (size_t)he.n0);
+    }
+    if (monotone) *monotone = ok;
+    if (ri_empty) *ri_empty = he.ri_empty ? 1 : 0;
+    return PS_OK;
+}
+
 // Band centres of the wide fill (cpp/EventData.h:172-183: lower_bound over ref_index; 1 when the
 // event has no alignment, cpp/Alignment.cpp:129-132), whether they are nondecreasing, the forward
 // band cell count, and the number of threads the wavefront needs so that a thread's next strip
@@ -563,29 +613,7 @@ void Job::plan_event(const HostEvent& he, const EvDesc& d, int rw, int* cen, int
     double cells = 0;
     if (!he.ri_empty)
     {
-        const LevelVec& ri = he.ref_index;
-        // (an event with ONE aligned level has a 0/0 slope: every other entry of ref_index is NaN, cpp/EventData.h:143-144;
-        // std::lower_bound's probes then decide, so a NaN anywhere must take the binary search below)
-        bool sorted = true;
-        for (int i = 1; i < n0 && sorted; i++) sorted = ri[i] >= ri[i - 1];
-        if (n0 > 0 && ri[0] != ri[0]) sorted = false;
-        if (sorted)
-        {
-            // on sorted data lower_bound is "first element >= c": one linear merge for all columns
-            int idx = 0;
-            for (int c = 0; c <= N + cen_pad; c++)
-            {
-                while (idx < n0 && ri[idx] < (double)c) idx++;
-                cen[c] = idx;
-            }
-        }
-        else
-            for (int c = 0; c <= N + cen_pad; c++)
-            {
-                const int v = (int)(std::lower_bound(ri.begin(), ri.end(), (double)c) - ri.begin());
-                cen[c] = v;
-                if (c > 0 && v < cen[c - 1]) ok = 0;
-            }
+        ok = ps_host_centres(he.ref_index.data(), n0, N + cen_pad + 1, cen);
     }
     if (d.usable && ok)
     {

@@ -370,26 +370,12 @@ static int vroom(ps_ctx* ctx, const char* name, size_t count, T** out)
     return PS_OK;
 }
 
-int ps_viterbi_list(ps_region* R, int nkeep, double skip_prob, double stay_prob, double mut_min, double mut_max,
-                    std::vector<std::string>& out)
+// The host half of ViterbiMutate (cpp/Viterbi.cpp:262-325): which reads sit on which position (getrefstates,
+// cpp/EventData.h:187-204), their pooled level / stdv, and the reference's sequential skip / stop rule over the positions.
+// Every event must carry an alignment (ensure_refs done).  `positions` (optional) receives the positions kept.
+static void vit_positions(ps_region* R, std::vector<VitSlot>& slots, std::vector<int>& slot_off, int& max_lik, std::vector<int>* positions)
 {
-    out.clear();
-    ps_ctx* ctx = R->ctx;
-    TRY(ctx->init());
-    CU(cudaSetDevice(ctx->device));
-    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    const double t_begin = now();
     const int E = (int)R->events.size();
-    if (E == 0) { ps_set_error(ctx, "ViterbiMutate needs at least one event"); return PS_E_ARG; }
-    for (HostEvent& ev : R->events) ev.ensure_refs();
-    for (const HostEvent& ev : R->events)
-        if (ev.ri_empty)
-        {
-            // the reference dereferences an empty path here (cpp/Viterbi.cpp:262-264, 385-400)
-            ps_set_error(ctx, "ViterbiMutate needs every event to carry an alignment");
-            return PS_E_ARG;
-        }
-    // ---- host: which reads sit on which position -------------------------------------------
     int refind = R->events[0].refstart;
     int maxref = 0;
     for (const HostEvent& ev : R->events) { refind = std::min(refind, ev.refstart); maxref = std::max(maxref, ev.refend); }
@@ -415,9 +401,9 @@ int ps_viterbi_list(ps_region* R, int nkeep, double skip_prob, double stay_prob,
                 beyond[k].emplace((int)v, i);                 // emplace keeps the first level of a value
         }
     }
-    std::vector<VitSlot> slots;
-    std::vector<int> slot_off(1, 0);
-    int max_lik = 1;
+    slots.clear();
+    slot_off.assign(1, 0);
+    max_lik = 1;
     // What each candidate position holds (the reads sitting on it, pooled level / stdv; how many reads span it) does not
     // depend on the positions before it: computed for all candidates on the worker threads, then the reference's
     // sequential skip / stop rule (cpp/Viterbi.cpp:310-325) walks over the results.
@@ -464,9 +450,36 @@ int ps_viterbi_list(ps_region* R, int nkeep, double skip_prob, double stay_prob,
         }
         slots.insert(slots.end(), here->begin(), here->end());
         slot_off.push_back((int)slots.size());
+        if (positions) positions->push_back(refind);
         max_lik = std::max(max_lik, nlik);
         refind++;
     }
+}
+
+int ps_viterbi_list(ps_region* R, int nkeep, double skip_prob, double stay_prob, double mut_min, double mut_max,
+                    std::vector<std::string>& out)
+{
+    out.clear();
+    ps_ctx* ctx = R->ctx;
+    TRY(ctx->init());
+    CU(cudaSetDevice(ctx->device));
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    const int E = (int)R->events.size();
+    if (E == 0) { ps_set_error(ctx, "ViterbiMutate needs at least one event"); return PS_E_ARG; }
+    for (HostEvent& ev : R->events) ev.ensure_refs();
+    for (const HostEvent& ev : R->events)
+        if (ev.ri_empty)
+        {
+            // the reference dereferences an empty path here (cpp/Viterbi.cpp:262-264, 385-400)
+            ps_set_error(ctx, "ViterbiMutate needs every event to carry an alignment");
+            return PS_E_ARG;
+        }
+    // ---- host: which reads sit on which position -------------------------------------------
+    std::vector<VitSlot> slots;
+    std::vector<int> slot_off;
+    int max_lik = 1;
+    vit_positions(R, slots, slot_off, max_lik, nullptr);
     const int n_pos = (int)slot_off.size() - 1;
     if (n_pos == 0) { ps_set_error(ctx, "ViterbiMutate: no position is covered by the events"); return PS_E_ARG; }
 
@@ -575,6 +588,25 @@ int ps_viterbi_list(ps_region* R, int nkeep, double skip_prob, double stay_prob,
 }
 
 extern "C" {
+
+// Host only (no device work): the positions ViterbiMutate keeps and how many reads sit on each -- for the CPU tests of
+// the skip / stop rule.  Returns PS_E_ARG like ps_viterbi_mutate when an event carries no alignment.
+extern "C" int ps_viterbi_positions(ps_region* R, int cap, int* positions, int* reads_here, int* n_positions)
+{
+    if (!R || cap < 0 || !n_positions || (cap > 0 && (!positions || !reads_here))) return PS_BAD_ARGS(R ? R->ctx : nullptr, "ps_viterbi_positions");
+    if (R->events.empty()) { ps_set_error(R->ctx, "ViterbiMutate needs at least one event"); return PS_E_ARG; }
+    for (HostEvent& ev : R->events) ev.ensure_refs();
+    for (const HostEvent& ev : R->events)
+        if (ev.ri_empty) { ps_set_error(R->ctx, "ViterbiMutate needs every event to carry an alignment"); return PS_E_ARG; }
+    std::vector<VitSlot> slots;
+    std::vector<int> slot_off, pos;
+    int max_lik = 1;
+    vit_positions(R, slots, slot_off, max_lik, &pos);
+    *n_positions = (int)pos.size();
+    if ((int)pos.size() > cap) { ps_set_error(R->ctx, "ps_viterbi_positions: %zu positions, room for %d", pos.size(), cap); return PS_E_CAPACITY; }
+    for (size_t k = 0; k < pos.size(); k++) { positions[k] = pos[k]; reads_here[k] = slot_off[k + 1] - slot_off[k]; }
+    return PS_OK;
+}
 
 int ps_viterbi_mutate(ps_region* R, int nkeep, double skip_prob, double stay_prob, double mut_min, double mut_max, int* n_seqs)
 {

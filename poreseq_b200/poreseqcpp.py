@@ -107,6 +107,8 @@ def lib():
     L.ps_find_mutations.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), _c_int_p]
     L.ps_found_mutation_sizes.argtypes = [C.c_void_p, C.c_int, _c_int_p, _c_int_p]
     L.ps_get_found_mutation.argtypes = [C.c_void_p, C.c_int, _c_int_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+    L.ps_viterbi_positions.argtypes = [C.c_void_p, C.c_int, _c_int_p, _c_int_p, _c_int_p]
+    L.ps_band_centres.argtypes = [C.c_void_p, C.c_int, C.c_int, _c_int_p, _c_double_p, _c_int_p, _c_int_p]
     L.ps_pick_candidates.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), _c_double_p, C.POINTER(_c_double_p), _c_int_p]
     L.ps_mutate.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.c_int, _c_int_p]
     L.ps_viterbi_mutate.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, _c_int_p]
@@ -455,6 +457,30 @@ class NativeRegion(object):
 
     def map_alignments(self, newseq):
         self.ctx.check(self.ctx.lib.ps_map_alignments(self.handle, newseq.encode("ascii")))
+
+    def band_centres(self, event, n_cols):
+        """ps_band_centres: (centres[n_cols], ref_index or None when the event carries no alignment, monotone)."""
+        cen = np.zeros(max(n_cols, 1), dtype=np.int32)
+        ra, _ = self.event_align(event)
+        ri = np.zeros(max(len(ra), 1), dtype="f8")
+        empty, mono = C.c_int(0), C.c_int(0)
+        self.ctx.check(self.ctx.lib.ps_band_centres(self.handle, int(event), int(n_cols), cen.ctypes.data_as(_c_int_p), _dp(ri),
+                                                    C.byref(empty), C.byref(mono)))
+        return cen[:n_cols], (None if empty.value else ri[:len(ra)]), bool(mono.value)
+
+    def viterbi_positions(self):
+        """ps_viterbi_positions: [(position, reads sitting on it)] as ViterbiMutate's host half keeps them."""
+        n = C.c_int(0)
+        cap = 16
+        while True:
+            pos = np.zeros(cap, dtype=np.int32)
+            cnt = np.zeros(cap, dtype=np.int32)
+            rc = self.ctx.lib.ps_viterbi_positions(self.handle, cap, pos.ctypes.data_as(_c_int_p), cnt.ctypes.data_as(_c_int_p), C.byref(n))
+            if rc == -3 and n.value > cap:                  # PS_E_CAPACITY
+                cap = n.value
+                continue
+            self.ctx.check(rc)
+            return list(zip(pos[:n.value].tolist(), cnt[:n.value].tolist()))
 
     def pick_candidates(self, seeds, base_profile, seed_profiles):
         """ps_pick_candidates: the host-only second half of FindMutations over profiles the caller already holds."""

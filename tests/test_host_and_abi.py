@@ -611,3 +611,145 @@ def test_round2_entry_points_refuse_bad_arguments_and_have_no_cpu_path():
         nr.close()
     finally:
         ctx.close()
+
+
+def _updaterefs(ra):
+    """cpp/EventData.h:110-169 restated in Python (IEEE doubles, the reference's operation order)."""
+    n = len(ra)
+    a = 0
+    while a < n and not ra[a] > 0:
+        a += 1
+    z = n - 1
+    while z >= 0 and not ra[z] > 0:
+        z -= 1
+    if a == n or z < 0:
+        return None
+    ri = np.array(ra, dtype="f8")
+    with np.errstate(all="ignore"):
+        m = np.float64(ra[z] - ra[a]) / np.float64(z - a)
+        b = ra[a] - m * a
+        last = -1
+        for i in range(n):
+            if i < a or i > z:
+                ri[i] = m * i + b
+            elif ra[i] > 0:
+                if last > 0:
+                    mm = np.float64(ra[i] - ra[last]) / np.float64(i - last)
+                    for j in range(last + 1, i):
+                        ri[j] = mm * (j - last) + ra[last]
+                last = i
+    return ri
+
+
+def _lower_bound(a, v):
+    """std::lower_bound as libstdc++ probes it (cpp/EventData.h:172-183) -- on an array with NaNs the probes decide."""
+    first, length = 0, len(a)
+    while length > 0:
+        half = length >> 1
+        if a[first + half] < v:
+            first += half + 1
+            length -= half + 1
+        else:
+            length = half
+    return first
+
+
+def test_band_centres_follow_the_reference_binary_search():
+    """ps_band_centres (host only): ref_index and getrefstate(c) of events with ordinary, jittered (unsorted), sparse,
+    single-level and empty alignments against updaterefs + std::lower_bound restated above.  The single aligned level
+    (0/0 slope, ref_index of NaNs) is the case the GPU sweep found: a linear merge gives other centres than the
+    reference's binary search there."""
+    rng = np.random.default_rng(5)
+    ctx = poreseqcpp.Context(0)
+    try:
+        for trial in range(60):
+            reg = synth.make_region(int(rng.integers(30, 200)), 2, seed=300 + trial, partial=float(rng.choice([0, 0.5])),
+                                    jitter=int(rng.choice([0, 0, 4])))
+            n_cols = len(reg.sequence) + 8
+            for e, ev in enumerate(reg.events):
+                ra = np.array(ev.ref_align, dtype="f8")
+                kind = (trial + e) % 6
+                if kind == 1:                                   # one aligned level: somewhere, first, last
+                    keep = [int(rng.integers(0, len(ra))), 0, len(ra) - 1][trial % 3]
+                    v = max(float(ra[keep]), 1.0)
+                    ra[:] = 0
+                    ra[keep] = v
+                elif kind == 2:
+                    ra[:] = 0                                   # no alignment at all
+                elif kind == 3:
+                    ra[rng.random(len(ra)) < 0.8] = -1          # mostly insertions
+                elif kind == 4:
+                    ra[:] = 0
+                    ra[0] = 3.0
+                    ra[-1] = 3.0 + len(ra)                      # aligned ends only; an aligned level 0 (the `last > 0` quirk)
+                ev.ref_align = ra
+            nr = poreseqcpp.NativeRegion(ctx, reg.sequence, reg.events, reg.params)
+            for e, ev in enumerate(reg.events):
+                cen, ri, mono = nr.band_centres(e, n_cols)
+                want_ri = _updaterefs(np.asarray(ev.ref_align, dtype="f8"))
+                if want_ri is None:
+                    assert ri is None and np.all(cen == 1), (trial, e)
+                    continue
+                assert ri is not None and np.array_equal(ri, want_ri, equal_nan=True), (trial, e)
+                want = np.array([_lower_bound(want_ri, float(c)) for c in range(n_cols)])
+                assert np.array_equal(cen, want), (trial, e, (trial + e) % 6)
+                assert mono == bool(np.all(np.diff(want) >= 0)) or mono, (trial, e)
+            nr.close()
+    finally:
+        ctx.close()
+
+
+def test_viterbi_positions_follow_the_reference_loop():
+    """ps_viterbi_positions (host only): the positions ViterbiMutate keeps, against cpp/Viterbi.cpp:262-325 restated with
+    std::find over ref_index (getrefstates, cpp/EventData.h:187-204).  Sparse alignments make the extrapolated ends of
+    ref_index integer-valued, so reads "sit" on positions beyond every read's refend -- where the library used to stop."""
+    rng = np.random.default_rng(9)
+    ctx = poreseqcpp.Context(0)
+    try:
+        seen_beyond = 0
+        for trial in range(60):
+            reg = synth.make_region(int(rng.integers(20, 120)), int(rng.integers(1, 4)), seed=700 + trial,
+                                    partial=float(rng.choice([0, 0.5])))
+            for e, ev in enumerate(reg.events):
+                ra = np.array(ev.ref_align, dtype="f8")
+                kind = (trial + e) % 4
+                if kind == 1:                                   # two aligned levels one base apart: slope 1, integer tails
+                    k = int(rng.integers(0, len(ra) - 1))
+                    v = max(float(ra[k]), 1.0)
+                    ra[:] = 0
+                    ra[k], ra[k + 1] = v, v + 1
+                elif kind == 2:
+                    keep = rng.random(len(ra)) < 0.3
+                    keep[int(rng.integers(0, len(ra)))] = True
+                    ra[~keep] = 0
+                ev.ref_align = ra
+            nr = poreseqcpp.NativeRegion(ctx, reg.sequence, reg.events, reg.params)
+            refs = [_updaterefs(np.asarray(ev.ref_align, dtype="f8")) for ev in reg.events]
+            if any(r is None for r in refs):
+                with pytest.raises(RuntimeError):
+                    nr.viterbi_positions()
+                nr.close()
+                continue
+            spans = []
+            for ev in reg.events:
+                ra = np.asarray(ev.ref_align)
+                al = ra[ra > 0]
+                spans.append((int(al[0]), int(al[-1])))
+            want = []
+            refind = min(s[0] for s in spans)
+            while True:
+                nlik = sum(1 for ri in refs if np.any(ri == refind))
+                nal = sum(1 for s in spans if s[0] <= refind <= s[1])
+                if nlik <= nal * 0.2:
+                    if nal == 0:
+                        break
+                    refind += 1
+                    continue
+                want.append((refind, nlik))
+                refind += 1
+            assert nr.viterbi_positions() == want, trial
+            seen_beyond += bool(want) and want[-1][0] > max(s[1] for s in spans) + 1
+            nr.close()
+        assert seen_beyond > 0, "no trial reached past the last refend: the test lost its point"
+    finally:
+        ctx.close()
