@@ -303,6 +303,58 @@ def main_large(n=None, first=0):
     return 1 if bad else 0
 
 
+def main_psalign(n=None, first=0):
+    """The PSAlign mirror (poreseq_b200/poreseqcpp.py, pyx:189-472) on tiny regions: ScoreMutations -> ApplyMuts (the
+    MakeMutations recursion on a caller-scored list of multi-base edits), Copy independence -- against the checker's
+    score_mutations / make_mutations (RealignTo is Python on both sides: PSEvent.mapaligns)."""
+    from poreseq_b200 import drivers
+    from poreseq_b200.Util import MutationInfo
+    if n is None:
+        n = 100
+    binding.build("oracle")
+    orc = binding.load("oracle")
+    ctx = poreseqcpp.Context(0)
+    bad = 0
+    for precision in ("exact", "fast"):
+        ctx.set_precision(precision)
+        for seed in range(first, first + n):
+            rng = np.random.default_rng(17000 + seed)
+            reg = tiny_region(seed, 12, 90, rng)
+            what = []
+            try:
+                pa = drivers.make_psalign(reg)
+                pa.ctx = ctx
+                st, og, mu = synth.random_mutations(reg.sequence, 40, rng, 4)
+                want_sc, a = orc.score_mutations(reg, st, og, mu)
+                infos = []
+                for s_, o_, m_ in zip(st, og, mu):
+                    mi = MutationInfo(); mi.start, mi.orig, mi.mut = s_, o_, m_
+                    infos.append(mi)
+                keep = pa.Copy()
+                scored = pa.ScoreMutations(infos)
+                got_sc = np.array([x.score for x in scored])
+                if not np.array_equal(got_sc[want_sc >= 0], want_sc[want_sc >= 0]):
+                    what.append("ScoreMutations")
+                # ApplyMuts with the reference's scores on both sides; PSAlign.ScoreMutations does not write the
+                # realignment back (pyx:310-345), so both start from the region's own alignments
+                seq, nb, a2 = orc.make_mutations(reg, st, og, mu, want_sc)
+                for x, w in zip(scored, want_sc):
+                    x.score = float(w)
+                pa.ApplyMuts(scored)
+                if not (pa.sequence == seq and same_aligns([(ev.ref_align, ev.ref_like) for ev in pa.events], a2)):
+                    what.append("ApplyMuts")
+                if keep.sequence != reg.sequence or any(not np.array_equal(x.ref_align, y.ref_align) for x, y in zip(keep.events, reg.events)):
+                    what.append("Copy")
+            except Exception as e:                                  # noqa: BLE001
+                what.append("exception %r" % (e,))
+            if what:
+                bad += 1
+                print("MISMATCH(psalign) precision=%s seed=%d len=%d events=%d: %s"
+                      % (precision, seed, len(reg.sequence), len(reg.events), ", ".join(what)), flush=True)
+    print("gpu_sweep psalign: %d regions x 2 precisions, %d mismatching" % (n, bad))
+    return 1 if bad else 0
+
+
 def main_consensus(n=None, first=0):
     """The whole Mutate.py loop below the C-ABI (ps_consensus_batch, regions in lockstep, region-private rand() streams)
     against the same loop driven through the checker from a fresh rand() stream, on small regions of 3-6 reads."""

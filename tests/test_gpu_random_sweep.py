@@ -42,3 +42,12 @@ def test_random_small_regions_whole_consensus_loop(capsys):
     rc = gpu_sweep.main_consensus(n=8, first=0)
     out = capsys.readouterr().out
     assert rc == 0, out[-4000:]
+
+
+def test_random_regions_through_the_psalign_mirror(capsys):
+    """PSAlign.ScoreMutations -> ApplyMuts (MakeMutations' recursion on a caller-scored list of multi-base edits) and Copy
+    on 60 tiny regions, against the checker."""
+    import gpu_sweep
+    rc = gpu_sweep.main_psalign(n=60, first=0)
+    out = capsys.readouterr().out
+    assert rc == 0, out[-4000:]
